@@ -1,0 +1,228 @@
+/*
+ * waldo_b200 -- C ABI of the B200-native (sm_100a) warp+composite hot path of WALDO.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and a CUDA stream.  No torch types.
+ * All pointers are DEVICE pointers to dense row-major fp32 tensors unless stated; the caller
+ * owns every buffer (outputs, saved state, scratch); kernels never allocate, never keep a pointer
+ * after return and never synchronise.  Every entry point returns 0 on success or a negative
+ * WALDO_E* code; `waldo_last_error()` gives the message for the calling thread.
+ *
+ * The reference (16lemoing/waldo) has no native interface for this path: it is ~170 ATen calls per
+ * decode inside three Python classes.  Each entry point therefore cites the reference Python
+ * function it replaces (paths relative to the reference root).  The reference-side binding is the
+ * ctypes shim shown in INTEGRATION.md (shipped as waldo_b200/_lib.py).
+ *
+ * Symbols (SURVEY.md symbol table): B batch, T frames, Tw frames that get a context alpha
+ * (Tc with restrict_to_ctx, else T), Tc contexts, Tp predicted frames, No objects, L = No+1 layers
+ * (layer 0 = background), C = 3+Nl input channels, H x W low-res, Hd x Wd full-res, Ho x Wo object canvas.
+ */
+#ifndef WALDO_B200_H
+#define WALDO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WALDO_ABI_VERSION 1
+
+/* compile-time capacity of the kernels (per-thread register arrays) */
+#define WALDO_MAX_LAYERS 17   /* L  = num_obj + 1 */
+#define WALDO_MAX_CH     24   /* C  = 3 + num_lyt */
+#define WALDO_MAX_LYT    21   /* Nl */
+#define WALDO_MAX_TPS_K  256  /* control points + 3 */
+
+enum {
+  WALDO_OK = 0,
+  WALDO_EINVAL = -1,    /* bad argument / unsupported size */
+  WALDO_ECUDA = -2,     /* CUDA launch error */
+  WALDO_ENOGPU = -3     /* built without device code (never the case for the shipped .so) */
+};
+
+/* flags of waldo_geom_t.flags */
+enum {
+  WALDO_F_RESTRICT_CTX = 1 << 0, /* lvd.py:707 grid_to_flow_ctx (else :602 grid_to_flow)            */
+  WALDO_F_FILTER       = 1 << 1, /* semantic filter on (always with RESTRICT_CTX; else !no_filter)   */
+  WALDO_F_WEIGHT_CLS   = 1 << 2, /* lvd.py:736-739 weight the class histogram by cls                 */
+  WALDO_F_HAS_CLS      = 1 << 3, /* cls != None                                                      */
+  WALDO_F_IS_OBJ       = 1 << 4, /* lvd.py:788-791 (RESTRICT_CTX and not allow_ghost)                */
+  WALDO_F_INCLUDE_SELF = 1 << 5, /* lvd.py:842-845 extra context = the target frame itself           */
+  WALDO_F_USE_DISOCC   = 1 << 6  /* lvd.py:148-151 disocc appended to raw_output                     */
+};
+
+typedef void* waldo_stream_t; /* cudaStream_t */
+
+const char* waldo_last_error(void);
+int waldo_abi_version(void);
+/* 1 when the library holds sm_100a device code (the shipped build), 0 for the CPU logic-emulation
+ * build that only the unit tests compile (tests/emu). */
+int waldo_has_device_code(void);
+
+/* ------------------------------------------------------------------ a-1  TPSWarp.forward
+ * models/modules/warp.py:49-55.  grid[n,p,:] = tgt_grid_repr[p,:] @ (inverse_kernel @ [pts[n];0_3x2]).
+ * Accumulates in fp64 (the reference's two fp32 matmuls are ill-conditioned for the background). */
+typedef struct {
+  int n;                      /* items (B*T*No objects or B*T backgrounds) */
+  int N;                      /* control points per item */
+  int P;                      /* lattice points h*w */
+  const float* inverse_kernel;/* (N+3, N+3)  buffer TPSWarp.inverse_kernel  warp.py:45 */
+  const float* tgt_grid_repr; /* (P, N+3)    buffer TPSWarp.tgt_grid_repr   warp.py:47 */
+  const float* pts;           /* (n, N, 2) */
+  double* mapping;            /* scratch (n, N+3, 2) */
+  float* grid;                /* out (n, P, 2) */
+} waldo_tps_fwd_t;
+int waldo_tps_fwd(const waldo_tps_fwd_t*, waldo_stream_t);
+
+typedef struct {
+  int n, N, P;
+  const float* inverse_kernel;
+  const float* tgt_grid_repr;
+  const float* dgrid;         /* (n, P, 2) */
+  int chunks;                 /* P is reduced in `chunks` ordered slices */
+  double* partial;            /* scratch (n, chunks, N+3, 2) */
+  float* dpts;                /* out (n, N, 2) */
+} waldo_tps_bwd_t;
+int waldo_tps_bwd(const waldo_tps_bwd_t*, waldo_stream_t);
+
+/* ------------------------------------------------------------------ a-2  InverseWarp.forward
+ * models/modules/warp.py:71-174 (num_perm == 1, pad=True).  Tie rule: lowest sample index wins. */
+typedef struct {
+  int n;                      /* items */
+  int Hs, Ws;                 /* lattice of the forward map */
+  int Ht, Wt;                 /* target (image) lattice */
+  int niter;                  /* dilation (and erosion) iterations, reference default 5 */
+  int erode;                  /* 1 for objects (lvd.py:861), 0 for background (:867) */
+  const float* fwd_grid;      /* (n, Hs, Ws, 2) */
+  const float* id_src;        /* (Hs, Ws, 2) buffer InverseWarp.src_grid  warp.py:65 */
+  const float* id_tgt;        /* (Ht, Wt, 2) buffer InverseWarp.tgt_grid  warp.py:66 */
+  const float* gauss;         /* (9) buffer InverseWarp.kernel            warp.py:64 */
+  float* out;                 /* out (n, Ht, Wt, 2) */
+  /* saved for backward / exposed for the index-map parity checks (int32, uint8) */
+  int32_t* field;             /* (n, Ht*Wt) landing cell of every sample, -1 = outside   warp.py:84-88 */
+  int32_t* winner;            /* (n, Ht*Wt) surviving sample per cell, INT32_MAX = none  warp.py:113-123 */
+  uint8_t* level;             /* (n, Hp*Wp) 0 = hit, k = filled at dilation k, 255 = unknown; Hp = Ht+2(niter+1) */
+  uint8_t* eroded;            /* (n, Hp*Wp) 0 = kept, k = removed at erosion k */
+  float* val;                 /* scratch+saved (n, 2, Hp*Wp) inverse displacement in pixels */
+} waldo_invwarp_fwd_t;
+int waldo_invwarp_fwd(const waldo_invwarp_fwd_t*, waldo_stream_t);
+
+typedef struct {
+  int n, Hs, Ws, Ht, Wt, niter;
+  const float* gauss;
+  const float* dout;          /* (n, Ht, Wt, 2) */
+  const int32_t* field;
+  const int32_t* winner;
+  const uint8_t* level;
+  const uint8_t* eroded;
+  float* gval;                /* scratch (n, 2, Hp*Wp) */
+  float* inv_sw;              /* scratch (n, Hp*Wp) */
+  float* gdisp;               /* scratch (n, Ht*Wt, 2) gradient of the resampled displacement */
+  float* dfwd_grid;           /* out (n, Hs, Ws, 2) */
+} waldo_invwarp_bwd_t;
+int waldo_invwarp_bwd(const waldo_invwarp_bwd_t*, waldo_stream_t);
+
+/* ------------------------------------------------------------------ a-4  LVD.compute_occ
+ * models/nets/lvd.py:59-68. */
+int waldo_occ_fwd(int BT, int No, const float* occ_score /* (BT,No) */, float* occ /* (BT,L,L) */, waldo_stream_t);
+int waldo_occ_bwd(int BT, int No, const float* occ_score, const float* docc, float* dscore, waldo_stream_t);
+
+/* ------------------------------------------------------------------ a-5..a-8  decode_output
+ * LVD.forward(mode="decode_output") models/nets/lvd.py:141-153 =
+ *   Warper.grid_to_flow_ctx :707-828 | Warper.grid_to_flow :602-705, then Warper.input_to_output :830-853. */
+typedef struct {
+  int B, T, Tw, Tc, Tp;
+  int No, Nl, C;
+  int H, W, Hd, Wd, Ho, Wo;
+  int flags;
+  float min_cls;              /* lvd.py:492 */
+} waldo_geom_t;
+
+typedef struct {
+  waldo_geom_t g;
+  /* inputs */
+  const float* input;         /* (B, T, C, Hd, Wd) */
+  const float* tgt_grid_obj;  /* (B, T, No, Ho, Wo, 2) */
+  const float* src_grid_obj;  /* (B, T, No, H, W, 2) */
+  const float* tgt_grid_bg;   /* (B, T, H, W, 2) */
+  const float* src_grid_bg;   /* (B, T, H, W, 2) */
+  const float* occ;           /* (B, T, L, L) */
+  const float* obj_alpha;     /* (B, No, Ho, Wo) in [-1,1] */
+  const float* bg_alpha;      /* (B, H, W) in [-1,1] */
+  const float* cls;           /* (B, No, Nl) or NULL */
+  const int64_t* ctx_ts;      /* (B, Tc, Tp) */
+  const int64_t* pred_ts;     /* (Tp) */
+  const float* xs_hd;         /* (Wd) x of buffer Warper.src_grid_hd  lvd.py:484 */
+  const float* ys_hd;         /* (Hd) y of the same buffer */
+  /* low-res intermediates (saved for backward) */
+  float* a_lo;                /* (B, Tw, L, H, W) projected opacities, lvd.py:727 */
+  float* prof_part;           /* scratch (B, prof_ctas, No*Nl + No) partial sums of the class profile */
+  int prof_ctas;
+  float* prof_sum;            /* (B, No*Nl + No) reduced sums (num | den), lvd.py:740-742 */
+  float* prof_p;              /* (B, No, Nl) class probabilities used by the filter */
+  float* f_lo;                /* (B, Tc, Tp, L, H, W, 2) per-layer flow on the low-res lattice, lvd.py:792 */
+  float* s_lo;                /* (B, Tp, No, H, W) object support, lvd.py:788 */
+  /* outputs */
+  float* alpha;               /* (B, Tw, L, Hd, Wd) in [-1,1]                         lvd.py:822 */
+  float* flow;                /* (B, Tc, Tp, 2, Hd, Wd)                               lvd.py:818 */
+  float* raw_output;          /* (B, Tc+self, Tp, C+L+disocc, Hd, Wd)                 lvd.py:846,151; alpha_ctx = channels C..C+L-1 */
+  float* out_full;            /* (B, Tp, C+1, Hd, Wd): output | raw_alpha             lvd.py:851,147,152 */
+  float* norm;                /* (B, Tp, Hd, Wd) sum_tc(score+eps), saved for backward, may be NULL */
+} waldo_decode_fwd_t;
+int waldo_decode_fwd(const waldo_decode_fwd_t*, waldo_stream_t);
+
+typedef struct {
+  waldo_decode_fwd_t f;       /* the forward call's arguments (inputs, saved intermediates, outputs) */
+  /* upstream gradients; any may be NULL (= zero) */
+  const float* d_out_full;    /* (B, Tp, C+1, Hd, Wd) */
+  const float* d_raw_output;  /* (B, Tc+self, Tp, C+L+disocc, Hd, Wd) */
+  const float* d_flow;        /* (B, Tc, Tp, 2, Hd, Wd) */
+  const float* d_alpha;       /* (B, Tw, L, Hd, Wd) */
+  /* gradient outputs; NULL = not needed.  Buffers must be ZERO-FILLED by the caller. */
+  float* d_input;             /* (B, T, C, Hd, Wd) */
+  float* d_tgt_grid_obj;      /* (B, T, No, Ho, Wo, 2) */
+  float* d_src_grid_obj;      /* (B, T, No, H, W, 2) */
+  float* d_tgt_grid_bg;       /* (B, T, H, W, 2) */
+  float* d_src_grid_bg;       /* (B, T, H, W, 2) */
+  float* d_occ;               /* (B, T, L, L) */
+  float* d_obj_alpha;         /* (B, No, Ho, Wo) */
+  float* d_bg_alpha;          /* (B, H, W) */
+  float* d_cls;               /* (B, No, Nl) */
+  /* zero-filled scratch */
+  float* d_alpha_acc;         /* (B, Tw, L, Hd, Wd) gradient w.r.t. the stored context opacity A */
+  float* d_f_lo;              /* (B, Tc, Tp, L, H, W, 2) */
+  float* d_a_lo;              /* (B, Tw, L, H, W) */
+  float* d_prof_p;            /* (B, No, Nl) */
+  float* d_prof_sum;          /* (B, No*Nl + No) */
+  /* per-CTA partial sums of the small reductions (reduced in CTA order => deterministic); need no zero-fill */
+  int red_ctas;               /* CTAs per (b,tp) / (b,t) group of the two HD backward kernels */
+  float* occ_part;            /* (max(B*Tp, B*Tw), red_ctas, L*L) */
+  float* prof_p_part;         /* (B*Tw, red_ctas, No*Nl) */
+  float* cls_part;            /* (B, prof_ctas, No*Nl) */
+} waldo_decode_bwd_t;
+int waldo_decode_bwd(const waldo_decode_bwd_t*, waldo_stream_t);
+
+/* ------------------------------------------------------------------ a-9  WIF.forward fuse tail
+ * models/nets/wif.py:50-54: frame = sum_tc softmax_tc(u[3]) * (sigmoid(raw[4]+5) * raw[0:3] + u[0:3]). */
+typedef struct {
+  int B, Tc, Tp, Cr;          /* Cr = channels of raw_output */
+  int HW;                     /* Hd*Wd */
+  int ab;                     /* opt.ii_ab */
+  const float* raw_output;    /* (B, Tc, Tp, Cr, HW) */
+  const float* unet_out;      /* (B, Tp, Tc, 4+ab, HW) */
+  float* frame;               /* out (B, Tp, 3, HW) */
+} waldo_wif_fuse_fwd_t;
+int waldo_wif_fuse_fwd(const waldo_wif_fuse_fwd_t*, waldo_stream_t);
+
+typedef struct {
+  waldo_wif_fuse_fwd_t f;
+  const float* d_frame;       /* (B, Tp, 3, HW) */
+  float* d_raw_output;        /* (B, Tc, Tp, Cr, HW) or NULL; channels 0..4 written, the rest must be pre-zeroed */
+  float* d_unet_out;          /* (B, Tp, Tc, 4+ab, HW) or NULL */
+} waldo_wif_fuse_bwd_t;
+int waldo_wif_fuse_bwd(const waldo_wif_fuse_bwd_t*, waldo_stream_t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WALDO_B200_H */

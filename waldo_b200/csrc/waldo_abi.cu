@@ -1,0 +1,202 @@
+// C-ABI entry points of libwaldo_b200.so (see include/waldo_b200.h).  Argument validation + kernel launches;
+// no allocation, no synchronisation, launches on the caller's stream.
+#include <stdio.h>
+#include <stdarg.h>
+#include "wb_common.cuh"
+#include "wb_geom.cuh"
+#include "wb_prep.cuh"
+#include "wb_composite.cuh"
+#include "wb_composite_bwd.cuh"
+#include "wb_wif.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int wb_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#ifndef WB_HOST_EMU
+static int wb_check_launch(const char* file, int line) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return wb_fail(WALDO_ECUDA, "%s:%d: CUDA launch failed: %s", file, line, cudaGetErrorString(e));
+  return 0;
+}
+#endif
+
+#define WB_REQUIRE(cond, ...) do { if (!(cond)) return wb_fail(WALDO_EINVAL, __VA_ARGS__); } while (0)
+#define WB_LAUNCHED() do { int rc_ = WB_CHECK_LAUNCH(); if (rc_) return rc_; } while (0)
+
+static inline unsigned wb_blocks(long long total, int threads, long long cap = 1 << 20) {
+  long long b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (unsigned)b;
+}
+
+extern "C" {
+
+const char* waldo_last_error(void) { return g_err; }
+int waldo_abi_version(void) { return WALDO_ABI_VERSION; }
+int waldo_has_device_code(void) {
+#ifdef WB_HOST_EMU
+  return 0;
+#else
+  return 1;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------ TPS
+int waldo_tps_fwd(const waldo_tps_fwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->N > 0 && a->P > 0, "tps_fwd: bad sizes");
+  WB_REQUIRE(a->N + 3 <= WB_MAX_K, "tps_fwd: %d control points exceed the compiled maximum %d", a->N, WB_MAX_K - 3);
+  WB_REQUIRE(a->inverse_kernel && a->tgt_grid_repr && a->pts && a->mapping && a->grid, "tps_fwd: null pointer");
+  if (a->n == 0) return 0;
+  WB_LAUNCH(k_tps_mapping, dim3(a->n), dim3(128), 0, st, a->n, a->N, a->inverse_kernel, a->pts, a->mapping);
+  WB_LAUNCHED();
+  dim3 grid(wb_blocks(a->P, 128), (a->n + WB_TPS_NI - 1) / WB_TPS_NI);
+  WB_LAUNCH(k_tps_eval, grid, dim3(128), 0, st, a->n, a->N, a->P, a->tgt_grid_repr, a->mapping, a->grid);
+  WB_LAUNCHED();
+  return 0;
+}
+
+int waldo_tps_bwd(const waldo_tps_bwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->N > 0 && a->P > 0 && a->chunks > 0, "tps_bwd: bad sizes");
+  WB_REQUIRE(a->N + 3 <= WB_MAX_K, "tps_bwd: too many control points");
+  WB_REQUIRE(a->inverse_kernel && a->tgt_grid_repr && a->dgrid && a->partial && a->dpts, "tps_bwd: null pointer");
+  if (a->n == 0) return 0;
+  WB_LAUNCH(k_tps_bwd_partial, dim3(a->n, a->chunks), dim3(((a->N + 3 + 31) / 32) * 32), 0, st, a->n, a->N, a->P, a->chunks,
+            a->tgt_grid_repr, a->dgrid, a->partial);
+  WB_LAUNCHED();
+  WB_LAUNCH(k_tps_bwd_final, dim3(a->n), dim3(128), 0, st, a->n, a->N, a->chunks, a->inverse_kernel, a->partial, a->dpts);
+  WB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ inverse warp
+int waldo_invwarp_fwd(const waldo_invwarp_fwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->Hs > 0 && a->Ws > 0 && a->Ht > 0 && a->Wt > 0, "invwarp_fwd: bad sizes");
+  WB_REQUIRE(a->niter >= 0 && a->niter < 120, "invwarp_fwd: niter out of range");
+  WB_REQUIRE(a->fwd_grid && a->id_src && a->id_tgt && a->gauss && a->out && a->field && a->winner && a->level && a->eroded && a->val,
+             "invwarp_fwd: null pointer");
+  if (a->n == 0) return 0;
+  WbInvArgs k = {a->n, a->Hs, a->Ws, a->Ht, a->Wt, a->niter, a->erode, a->fwd_grid, a->id_src, a->id_tgt, a->gauss,
+                 a->out, a->field, a->winner, a->level, a->eroded, a->val};
+  WB_LAUNCH(k_invwarp_fwd, dim3(a->n), dim3(1024), 0, st, k);
+  WB_LAUNCHED();
+  return 0;
+}
+
+int waldo_invwarp_bwd(const waldo_invwarp_bwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->Hs > 0 && a->Ws > 0 && a->Ht > 0 && a->Wt > 0, "invwarp_bwd: bad sizes");
+  WB_REQUIRE(a->gauss && a->dout && a->field && a->winner && a->level && a->eroded && a->gval && a->inv_sw && a->gdisp && a->dfwd_grid,
+             "invwarp_bwd: null pointer");
+  if (a->n == 0) return 0;
+  WbInvBwdArgs k = {a->n, a->Hs, a->Ws, a->Ht, a->Wt, a->niter, a->gauss, a->dout, a->field, a->winner, a->level, a->eroded,
+                    a->gval, a->inv_sw, a->gdisp, a->dfwd_grid};
+  WB_LAUNCH(k_invwarp_bwd, dim3(a->n), dim3(1024), 0, st, k);
+  WB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ occlusion matrix
+int waldo_occ_fwd(int BT, int No, const float* score, float* occ, waldo_stream_t st) {
+  WB_REQUIRE(BT >= 0 && No > 0 && score && occ, "occ_fwd: bad arguments");
+  if (BT == 0) return 0;
+  long long total = (long long)BT * (No + 1) * (No + 1);
+  WB_LAUNCH(k_occ_fwd, dim3(wb_blocks(total, 256)), dim3(256), 0, st, BT, No, score, occ);
+  WB_LAUNCHED();
+  return 0;
+}
+int waldo_occ_bwd(int BT, int No, const float* score, const float* docc, float* dscore, waldo_stream_t st) {
+  WB_REQUIRE(BT >= 0 && No > 0 && score && docc && dscore, "occ_bwd: bad arguments");
+  if (BT == 0) return 0;
+  WB_LAUNCH(k_occ_bwd, dim3(wb_blocks((long long)BT * No, 128)), dim3(128), 0, st, BT, No, score, docc, dscore);
+  WB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ decode_output
+static int wb_check_geom(const waldo_geom_t& g, const char* who) {
+  WB_REQUIRE(g.B > 0 && g.T > 0 && g.Tw > 0 && g.Tc > 0 && g.Tp > 0, "%s: bad batch/time sizes", who);
+  WB_REQUIRE(g.Tw <= g.T, "%s: Tw > T", who);
+  WB_REQUIRE(g.No >= 1 && g.No + 1 <= WB_MAX_L, "%s: num_obj=%d unsupported (compiled max %d)", who, g.No, WB_MAX_L - 1);
+  WB_REQUIRE(g.Nl >= 1 && g.Nl <= WB_MAX_NL, "%s: num_lyt=%d unsupported (compiled max %d)", who, g.Nl, WB_MAX_NL);
+  WB_REQUIRE(g.C == 3 + g.Nl && g.C <= WB_MAX_C, "%s: C=%d must equal 3+num_lyt and be <= %d", who, g.C, WB_MAX_C);
+  WB_REQUIRE(g.H > 0 && g.W > 0 && g.Hd >= g.H && g.Wd >= g.W && g.Ho > 0 && g.Wo > 0, "%s: bad spatial sizes", who);
+  WB_REQUIRE((long long)g.Hd * g.W == (long long)g.H * g.Wd, "%s: HD and low-res aspect differ", who);
+  WB_REQUIRE((long long)g.Hd * g.Wd < (1ll << 30), "%s: frame too large for 32-bit pixel indices", who);
+  if (g.flags & WALDO_F_RESTRICT_CTX) WB_REQUIRE(g.flags & WALDO_F_FILTER, "%s: restrict_to_ctx implies the filter", who);
+  if (g.flags & WALDO_F_WEIGHT_CLS) WB_REQUIRE(g.flags & WALDO_F_HAS_CLS, "%s: weight_cls needs cls", who);
+  return 0;
+}
+
+int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a, "decode_fwd: null argument");
+  const waldo_geom_t& g = a->g;
+  int rc = wb_check_geom(g, "decode_fwd");
+  if (rc) return rc;
+  WB_REQUIRE(a->input && a->tgt_grid_obj && a->src_grid_obj && a->tgt_grid_bg && a->src_grid_bg && a->occ && a->obj_alpha &&
+             a->bg_alpha && a->ctx_ts && a->pred_ts && a->xs_hd && a->ys_hd, "decode_fwd: null input pointer");
+  WB_REQUIRE(a->a_lo && a->f_lo && a->alpha && a->flow && a->raw_output && a->out_full, "decode_fwd: null output pointer");
+  const bool filt = (g.flags & WALDO_F_FILTER) != 0;
+  const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
+  if (g.flags & WALDO_F_HAS_CLS) WB_REQUIRE(a->cls, "decode_fwd: cls flagged but null");
+  if (g.flags & WALDO_F_IS_OBJ) WB_REQUIRE(a->s_lo, "decode_fwd: s_lo needed for is_obj");
+  if (filt) {
+    WB_REQUIRE(a->prof_p, "decode_fwd: prof_p needed for the filter");
+    if (!from_cls) WB_REQUIRE(a->prof_part && a->prof_sum && a->prof_ctas > 0, "decode_fwd: profile scratch needed");
+  }
+  const int L = g.No + 1, HW = g.H * g.W;
+  const long long HWd = (long long)g.Hd * g.Wd;
+  // B1
+  WB_LAUNCH(k_project_alpha, dim3(wb_blocks((long long)g.B * g.Tw * L * HW, 256)), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  // B2
+  if (filt) {
+    if (!from_cls) {
+      WB_LAUNCH(k_class_profile, dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
+      WB_LAUNCHED();
+    }
+    WB_LAUNCH(k_profile_final, dim3(g.B), dim3(64), 0, st, *a);
+    WB_LAUNCHED();
+  }
+  // B2b-B4
+  WB_LAUNCH(k_alpha_prep, dim3(wb_blocks(HWd, 256), g.B * g.Tw), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  // B5
+  WB_LAUNCH(k_layer_flow_lo, dim3(wb_blocks((long long)g.B * g.Tp * L * HW, 256)), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  // B5(up)-B9 + stage C
+  WB_LAUNCH(k_warp_composite_fwd, dim3(wb_blocks(HWd, 256), g.B * g.Tp), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
+int waldo_decode_bwd(const waldo_decode_bwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a, "decode_bwd: null argument");
+  return wb_decode_bwd_launch(*a, st);
+}
+
+// ------------------------------------------------------------------------------------------ WIF fuse tail
+int waldo_wif_fuse_fwd(const waldo_wif_fuse_fwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->B > 0 && a->Tc > 0 && a->Tp > 0 && a->HW > 0, "wif_fuse_fwd: bad sizes");
+  WB_REQUIRE(a->Cr >= 5 || !a->ab, "wif_fuse_fwd: raw_output needs >= 5 channels for the gate");
+  WB_REQUIRE(a->Cr >= 3 && a->raw_output && a->unet_out && a->frame, "wif_fuse_fwd: null pointer");
+  WB_LAUNCH(k_wif_fuse_fwd, dim3(wb_blocks(a->HW, 256), a->B * a->Tp), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+int waldo_wif_fuse_bwd(const waldo_wif_fuse_bwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->f.B > 0 && a->f.Tc > 0 && a->f.Tp > 0 && a->f.HW > 0, "wif_fuse_bwd: bad sizes");
+  WB_REQUIRE(a->f.Tc <= WB_WIF_MAX_TC, "wif_fuse_bwd: Tc=%d exceeds compiled maximum %d", a->f.Tc, WB_WIF_MAX_TC);
+  WB_REQUIRE(a->f.raw_output && a->f.unet_out && a->d_frame, "wif_fuse_bwd: null pointer");
+  WB_LAUNCH(k_wif_fuse_bwd, dim3(wb_blocks(a->f.HW, 256), a->f.B * a->f.Tp), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// Common device helpers of the waldo_b200 kernels (sm_100a).
+//
+// The same sources also compile as plain C++ with -DWB_HOST_EMU: every CTA is then executed by ONE
+// host "thread" (blockDim = 1), all kernels being written with block-/grid-stride loops and using
+// only the reduction helpers below for cross-thread work.  That build exists for the unit tests
+// (tests/emu) to check index arithmetic and formulas without a GPU; it is never loaded by the
+// package (waldo_b200/_lib.py refuses a library whose waldo_has_device_code() is 0).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <limits.h>
+
+#ifdef WB_HOST_EMU
+// ------------------------------------------------------------------ host emulation shims
+#include <algorithm>
+#include <cstring>
+struct wb_dim3 { unsigned x, y, z; wb_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+typedef wb_dim3 dim3;
+static thread_local wb_dim3 threadIdx(0, 0, 0), blockIdx, blockDim, gridDim;
+#define __global__ static
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __shared__ static thread_local
+#define __launch_bounds__(...)
+#define __syncthreads() ((void)0)
+#define __ldg(p) (*(p))
+typedef void* cudaStream_t;
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+// the emulation build is compiled with -ffp-contract=off, so these stay single IEEE operations
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
+static inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }
+static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#define WB_LAUNCH(kern, grid, block, smem, stream, ...)                                     \
+  do {                                                                                      \
+    wb_dim3 g_ = (grid);                                                                    \
+    gridDim = g_; blockDim = wb_dim3(1, 1, 1); threadIdx = wb_dim3(0, 0, 0);                \
+    for (unsigned bz_ = 0; bz_ < g_.z; ++bz_)                                               \
+      for (unsigned by_ = 0; by_ < g_.y; ++by_)                                             \
+        for (unsigned bx_ = 0; bx_ < g_.x; ++bx_) { blockIdx = wb_dim3(bx_, by_, bz_); kern(__VA_ARGS__); } \
+  } while (0)
+#define WB_CHECK_LAUNCH() 0
+#define WB_UNROLL
+#else
+// ------------------------------------------------------------------ device build
+#include <cuda_runtime.h>
+#define WB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define WB_CHECK_LAUNCH() wb_check_launch(__FILE__, __LINE__)
+#define WB_UNROLL _Pragma("unroll")
+#endif
+
+#define WB_MAX_L 17
+#define WB_MAX_C 24
+#define WB_MAX_NL 21
+#define WB_MAX_K 256
+
+#define WB_DEV __device__ __forceinline__
+
+// linear thread id / count inside the CTA and over the grid (1-D launches)
+WB_DEV int wb_tid() { return (int)threadIdx.x; }
+WB_DEV int wb_nthr() { return (int)blockDim.x; }
+
+// ------------------------------------------------------------------ warp / block reductions
+// In the emulation build a "warp" is one lane, so every reduction is the identity.
+WB_DEV float wb_warp_sum(float v) {
+#ifndef WB_HOST_EMU
+  WB_UNROLL for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+WB_DEV int wb_lane() {
+#ifdef WB_HOST_EMU
+  return 0;
+#else
+  return (int)(threadIdx.x & 31);
+#endif
+}
+WB_DEV int wb_warp() {
+#ifdef WB_HOST_EMU
+  return 0;
+#else
+  return (int)(threadIdx.x >> 5);
+#endif
+}
+WB_DEV double wb_warp_sum(double v) {
+#ifndef WB_HOST_EMU
+  WB_UNROLL for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+
+// ------------------------------------------------------------------ ATen-exact bilinear pieces
+// grid_sampler_2d (bilinear, zeros, align_corners=False), SURVEY.md Appendix C.  The association
+// below -- weights as single products, value accumulated nw -> ne -> sw -> se with fused
+// multiply-adds -- reproduces the ATen CPU kernel BIT-EXACTLY (probed: oracle/aten_probe notes in
+// DESIGN.md), which is what makes the thresholded / rounded maps of the path index-exact.
+struct WbTaps {
+  int x0, y0;          // north-west tap (may be out of range)
+  float nw, ne, sw, se;
+  float ix, iy;        // un-normalised sample position
+  float wx0, wx1, wy0, wy1;   // 1-D weights (backward: d/d ix, d/d iy)
+};
+
+WB_DEV WbTaps wb_taps(float gx, float gy, int W, int H) {
+  WbTaps t;
+  t.ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), 1.f), 2.f);
+  t.iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), 1.f), 2.f);
+  float fx = floorf(t.ix), fy = floorf(t.iy);
+  float wx1 = __fsub_rn(t.ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.f), t.ix);
+  float wy1 = __fsub_rn(t.iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.f), t.iy);
+  t.wx0 = wx0; t.wx1 = wx1; t.wy0 = wy0; t.wy1 = wy1;
+  t.nw = __fmul_rn(wx0, wy0); t.ne = __fmul_rn(wx1, wy0);
+  t.sw = __fmul_rn(wx0, wy1); t.se = __fmul_rn(wx1, wy1);
+  // clamp before the int conversion so that wild coordinates (the 2W sentinel is fine, NaN is not
+  // expected) cannot overflow; anything outside [-1, size] is out of range for both taps anyway
+  fx = fminf(fmaxf(fx, -2.f), (float)W + 1.f);
+  fy = fminf(fmaxf(fy, -2.f), (float)H + 1.f);
+  t.x0 = (int)fx; t.y0 = (int)fy;
+  return t;
+}
+
+// 4-bit validity mask of the taps: bit0 nw, bit1 ne, bit2 sw, bit3 se
+WB_DEV int wb_tap_mask(const WbTaps& t, int W, int H) {
+  int xa = (t.x0 >= 0) & (t.x0 <= W - 1), xb = (t.x0 + 1 >= 0) & (t.x0 + 1 <= W - 1);
+  int ya = (t.y0 >= 0) & (t.y0 <= H - 1), yb = (t.y0 + 1 >= 0) & (t.y0 + 1 <= H - 1);
+  return (xa & ya) | ((xb & ya) << 1) | ((xa & yb) << 2) | ((xb & yb) << 3);
+}
+
+WB_DEV float wb_chain(float vnw, float vne, float vsw, float vse, const WbTaps& t) {
+  return __fmaf_rn(vse, t.se, __fmaf_rn(vsw, t.sw, __fmaf_rn(vne, t.ne, __fmul_rn(vnw, t.nw))));
+}
+
+// sample one plane (row-major H x W) with zero padding
+WB_DEV float wb_sample(const float* __restrict__ plane, const WbTaps& t, int m, int W) {
+  const float* p = plane + (long long)t.y0 * W + t.x0;
+  float vnw = (m & 1) ? __ldg(p) : 0.f;
+  float vne = (m & 2) ? __ldg(p + 1) : 0.f;
+  float vsw = (m & 4) ? __ldg(p + W) : 0.f;
+  float vse = (m & 8) ? __ldg(p + W + 1) : 0.f;
+  return wb_chain(vnw, vne, vsw, vse, t);
+}
+
+// upsample_bilinear2d (align_corners=False) source coordinates along one axis, ATen association:
+// src = max(r*(dst+0.5)-0.5, 0); i0 = int(src); i1 = min(i0+1, n-1); l1 = src-i0; l0 = 1-l1.
+struct WbAxis { int i0, i1; float l0, l1; };
+WB_DEV WbAxis wb_axis(int dst, float r, int n_in) {
+  WbAxis a;
+  float s = fmaxf(__fsub_rn(__fmul_rn(r, __fadd_rn((float)dst, 0.5f)), 0.5f), 0.f);
+  a.i0 = min((int)s, n_in - 1);
+  a.i1 = min(a.i0 + 1, n_in - 1);
+  a.l1 = fminf(fmaxf(__fsub_rn(s, (float)a.i0), 0.f), 1.f);
+  a.l0 = __fsub_rn(1.f, a.l1);
+  return a;
+}
+// value = fma(row0, ly0, row1*ly1), row = fma(v[x0], lx0, v[x1]*lx1)  (bit-exact with ATen CPU)
+WB_DEV float wb_lerp2(float v00, float v01, float v10, float v11, const WbAxis& ax, const WbAxis& ay) {
+  float r0 = __fmaf_rn(v00, ax.l0, __fmul_rn(v01, ax.l1));
+  float r1 = __fmaf_rn(v10, ax.l0, __fmul_rn(v11, ax.l1));
+  return __fmaf_rn(r0, ay.l0, __fmul_rn(r1, ay.l1));
+}

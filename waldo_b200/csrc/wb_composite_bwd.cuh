@@ -1,0 +1,701 @@
+// Backward of decode_output: the fused HD backward kernel, the context-alpha
+// backward, and the low-res chain down to grids / opacities / class scores.
+//
+// Accumulation strategy of this revision (see DESIGN.md "backward"):
+//   * small reductions (d occ, d class profile, d cls): per-warp shuffle tree -> per-CTA shared slot ->
+//     per-CTA partial in global scratch -> reduced in CTA order by a second kernel: deterministic, no atomics;
+//   * low-res scatter targets of the HD kernels (d f_lo, d a_lo): shared-memory window per 32x8 HD tile,
+//     flushed once per tile;
+//   * HD scatter targets (d input, d context opacity): red.global.add.f32.
+#pragma once
+#include "wb_common.cuh"
+#include "wb_prep.cuh"
+#include "wb_composite.cuh"
+
+typedef waldo_decode_bwd_t WbDecB;
+
+#define WB_TILE_W 32
+#define WB_TILE_H 8
+#define WB_TILE_PX (WB_TILE_W * WB_TILE_H)
+#define WB_WIN_CAP 128              // low-res cells a tile window may hold (scale_hd >= 2: <= 6 x 18 = 108)
+#define WB_NWARP (WB_TILE_PX / 32)
+
+WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) atomicAdd(p, v); }
+
+// exclusive-product backward of  A_i = R_i * prod_j (1 - R_j occ[j,i]).
+// gR (+=) gets d/dR; when s_acc != nullptr, d/d occ[j,i] summed over the warp is added to s_acc[j*L+i] by lane 0.
+WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, int L, float* gR, float* s_acc) {
+  const int lane = wb_lane();
+  WB_UNROLL for (int i = 0; i < WB_MAX_L; ++i) {
+    if (i < L) {
+      float pre[WB_MAX_L];
+      float run = 1.f;
+      WB_UNROLL for (int j = 0; j < WB_MAX_L; ++j) if (j < L) { pre[j] = run; run *= 1.f - R[j] * s_occ[j * L + i]; }
+      gR[i] += gA[i] * run;
+      const float gV = gA[i] * R[i];
+      float suf = 1.f;
+      WB_UNROLL for (int j = WB_MAX_L - 1; j >= 0; --j) {
+        if (j < L) {
+          const float oc = s_occ[j * L + i];
+          const float excl = pre[j] * suf;
+          suf *= 1.f - R[j] * oc;
+          gR[j] -= gV * oc * excl;
+          if (s_acc) {
+            float v = wb_warp_sum(-gV * R[j] * excl);
+            if (lane == 0) s_acc[j * L + i] += v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ============================================================================ fused HD backward
+// grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration).
+__global__ void __launch_bounds__(WB_TILE_PX) k_warp_composite_bwd(WbDecB a) {
+  const WbDec& d = a.f;
+  const waldo_geom_t g = d.g;
+  const int L = g.No + 1, HW = g.H * g.W, C = g.C;
+  const size_t HWd = (size_t)g.Hd * g.Wd;
+  const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
+  const int u = (int)d.pred_ts[tp];
+  const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  const bool disocc_ch = (g.flags & WALDO_F_USE_DISOCC) != 0;
+  const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + (disocc_ch ? 1 : 0);
+  const bool need_layers = a.d_alpha_acc || a.d_f_lo || a.d_occ;
+  const bool lowres_direct = (g.Hd == g.H);
+  __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
+  __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
+  __shared__ float s_win[WB_WIN_CAP * WB_MAX_L * 2];
+  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + u) * L * L + i);
+  for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
+  for (int i = wb_tid(); i < WB_WIN_CAP * WB_MAX_L * 2; i += wb_nthr()) s_win[i] = 0.f;
+  __syncthreads();
+  float* s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
+  const int tiles_x = (g.Wd + WB_TILE_W - 1) / WB_TILE_W, tiles_y = (g.Hd + WB_TILE_H - 1) / WB_TILE_H;
+  const float rlo = (float)g.H / (float)g.Hd;
+  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+    const int ty0 = (tile / tiles_x) * WB_TILE_H, tx0 = (tile % tiles_x) * WB_TILE_W;
+    // low-res window of this tile
+    const int wy0 = wb_axis(ty0, rlo, g.H).i0, wy1 = wb_axis(min(ty0 + WB_TILE_H, g.Hd) - 1, rlo, g.H).i1;
+    const int wx0 = wb_axis(tx0, rlo, g.W).i0, wx1 = wb_axis(min(tx0 + WB_TILE_W, g.Wd) - 1, rlo, g.W).i1;
+    const int ww = wx1 - wx0 + 1, wcells = ww * (wy1 - wy0 + 1);
+    for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
+      const int X = tx0 + (it & (WB_TILE_W - 1)), Y = ty0 + it / WB_TILE_W;
+      const bool active = X < g.Wd && Y < g.Hd;
+      const size_t q = active ? (size_t)Y * g.Wd + X : 0;
+      WbPix px = wb_pix(d, b, tp, q);
+      // window-relative low-res offsets
+      const int c00 = (px.ay.i0 - wy0) * ww + px.ax.i0 - wx0, c01 = (px.ay.i0 - wy0) * ww + px.ax.i1 - wx0;
+      const int c10 = (px.ay.i1 - wy0) * ww + px.ax.i0 - wx0, c11 = (px.ay.i1 - wy0) * ww + px.ax.i1 - wx0;
+      const float w00 = px.ax.l0 * px.ay.l0, w01 = px.ax.l1 * px.ay.l0, w10 = px.ax.l0 * px.ay.l1, w11 = px.ax.l1 * px.ay.l1;
+      float gO[WB_MAX_C + 1];
+      float S = 0.f;
+      {
+        const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
+        const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+        WB_UNROLL for (int c = 0; c <= WB_MAX_C; ++c) {
+          gO[c] = 0.f;
+          if (c <= C && dof && active) { gO[c] = __ldg(dof + (size_t)c * HWd); S += gO[c] * __ldg(of + (size_t)c * HWd); }
+        }
+      }
+      // note: the score channel of out_full sits at index C (not WB_MAX_C) in memory and in gO[]
+      const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
+      for (int tc = 0; tc < g.Tc; ++tc) {
+        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+        const float* f_lo = d.f_lo + pair * L * HW * 2;
+        const float* alpha_c = d.alpha + ((size_t)b * g.Tw + c_t) * L * HWd;
+        WbLayers ly;
+        wb_layers_fwd(d, px, f_lo, alpha_c, s_occ, ly);
+        const float wgt = ly.score + 1e-6f, n = wgt / D;
+        const float* draw = (a.d_raw_output && active) ? a.d_raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * CR * HWd + q : nullptr;
+        // ---- stage C backward: warped context frame
+        WbTaps t = wb_taps(__fadd_rn(px.gx, ly.flow_x), __fadd_rn(px.gy, ly.flow_y), g.Wd, g.Hd);
+        const int m = wb_tap_mask(t, g.Wd, g.Hd);
+        const float* src = d.input + ((size_t)b * g.T + c_t) * C * HWd + (long long)t.y0 * g.Wd + t.x0;
+        float* din = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * C * HWd + (long long)t.y0 * g.Wd + t.x0 : nullptr;
+        float G = 0.f, gix = 0.f, giy = 0.f;
+        WB_UNROLL for (int c = 0; c < WB_MAX_C; ++c) {
+          if (c < C) {
+            const float* p = src + (size_t)c * HWd;
+            const float vnw = (m & 1) ? __ldg(p) : 0.f, vne = (m & 2) ? __ldg(p + 1) : 0.f;
+            const float vsw = (m & 4) ? __ldg(p + g.Wd) : 0.f, vse = (m & 8) ? __ldg(p + g.Wd + 1) : 0.f;
+            const float O = wb_chain(vnw, vne, vsw, vse, t);
+            const float go = (draw ? __ldg(draw + (size_t)c * HWd) : 0.f) + n * gO[c];
+            G += gO[c] * O;
+            gix += go * ((vne - vnw) * t.wy0 + (vse - vsw) * t.wy1);
+            giy += go * ((vsw - vnw) * t.wx0 + (vse - vne) * t.wx1);
+            if (din && go != 0.f) {
+              float* o = din + (size_t)c * HWd;
+              if (m & 1) wb_atomic_add(o, t.nw * go);
+              if (m & 2) wb_atomic_add(o + 1, t.ne * go);
+              if (m & 4) wb_atomic_add(o + g.Wd, t.sw * go);
+              if (m & 8) wb_atomic_add(o + g.Wd + 1, t.se * go);
+            }
+          }
+        }
+        if (!need_layers) continue;
+        G += gO[C] * (ly.score * 2.f - 1.f);
+        const float* dfl = (a.d_flow && active) ? a.d_flow + pair * 2 * HWd + q : nullptr;
+        const float dfx = (dfl ? __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+        const float dfy = (dfl ? __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
+        const float gs = 2.f * n * gO[C] + (G - S) / D;
+        // ---- B9 / B8 backward
+        float gA[WB_MAX_L], gR[WB_MAX_L], gFx[WB_MAX_L], gFy[WB_MAX_L];
+        WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
+          if (k < L) {
+            gA[k] = gs + 2.f * (draw ? __ldg(draw + (size_t)(C + k) * HWd) : 0.f) + dfx * ly.Fx[k] + dfy * ly.Fy[k];
+            gFx[k] = ly.A[k] * dfx; gFy[k] = ly.A[k] * dfy;
+            gR[k] = 0.f;
+          }
+        }
+        wb_occlude_bwd(ly.R, gA, s_occ, L, gR, s_acc);
+        // ---- B7 backward: disocc = max_k R_k (first maximal layer takes the gradient)
+        if (disocc_ch && draw) {
+          const float gd = __ldg(draw + (size_t)(C + L) * HWd);
+          bool done = false;
+          WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k)
+            if (k < L && !done && ly.R[k] == ly.disocc) { gR[k] += gd; done = true; }
+        }
+        // ---- B6 backward: bilinear sample of the context opacity through layer k's flow
+        float* dal = a.d_alpha_acc ? a.d_alpha_acc + ((size_t)b * g.Tw + c_t) * L * HWd : nullptr;
+        WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
+          if (k < L) {
+            if (((px.isobj >> k) & 1u) && gR[k] != 0.f) {
+              WbTaps tk = wb_taps(__fadd_rn(px.gx, ly.Fx[k]), __fadd_rn(px.gy, ly.Fy[k]), g.Wd, g.Hd);
+              const int mk = wb_tap_mask(tk, g.Wd, g.Hd);
+              const long long off = (long long)k * (long long)HWd + (long long)tk.y0 * g.Wd + tk.x0;
+              const float* p = alpha_c + off;
+              const float vnw = (mk & 1) ? (__ldg(p) + 1.f) * 0.5f : 0.f, vne = (mk & 2) ? (__ldg(p + 1) + 1.f) * 0.5f : 0.f;
+              const float vsw = (mk & 4) ? (__ldg(p + g.Wd) + 1.f) * 0.5f : 0.f, vse = (mk & 8) ? (__ldg(p + g.Wd + 1) + 1.f) * 0.5f : 0.f;
+              const float gr = gR[k];
+              gFx[k] += gr * ((vne - vnw) * tk.wy0 + (vse - vsw) * tk.wy1) * (0.5f * (float)g.Wd);
+              gFy[k] += gr * ((vsw - vnw) * tk.wx0 + (vse - vne) * tk.wx1) * (0.5f * (float)g.Hd);
+              if (dal) {
+                float* o = dal + off;
+                if (mk & 1) wb_atomic_add(o, tk.nw * gr);
+                if (mk & 2) wb_atomic_add(o + 1, tk.ne * gr);
+                if (mk & 4) wb_atomic_add(o + g.Wd, tk.sw * gr);
+                if (mk & 8) wb_atomic_add(o + g.Wd + 1, tk.se * gr);
+              }
+            }
+            // ---- B5(up) backward: transpose of the bilinear up-sampling of the layer flow
+            if (a.d_f_lo) {
+              if (lowres_direct) {
+                float* o = a.d_f_lo + (pair * L + k) * HW * 2 + (size_t)px.o00 * 2;
+                wb_atomic_add(o, gFx[k]); wb_atomic_add(o + 1, gFy[k]);
+              } else {
+                float* w = s_win + (size_t)k * 2;
+                const int st = WB_MAX_L * 2;
+                if (gFx[k] != 0.f || gFy[k] != 0.f) {
+                  atomicAdd(w + c00 * st, w00 * gFx[k]); atomicAdd(w + c00 * st + 1, w00 * gFy[k]);
+                  atomicAdd(w + c01 * st, w01 * gFx[k]); atomicAdd(w + c01 * st + 1, w01 * gFy[k]);
+                  atomicAdd(w + c10 * st, w10 * gFx[k]); atomicAdd(w + c10 * st + 1, w10 * gFy[k]);
+                  atomicAdd(w + c11 * st, w11 * gFx[k]); atomicAdd(w + c11 * st + 1, w11 * gFy[k]);
+                }
+              }
+            }
+          }
+        }
+        if (a.d_f_lo && !lowres_direct) {   // flush the window of this (tile, context)
+          __syncthreads();
+          for (int e = wb_tid(); e < wcells * L * 2; e += wb_nthr()) {
+            const int cell = e / (L * 2), r = e - cell * (L * 2), k = r >> 1, comp = r & 1;
+            const int cy = cell / ww + wy0, cx = cell % ww + wx0;
+            float* sv = s_win + (size_t)cell * WB_MAX_L * 2 + k * 2 + comp;
+            const float v = *sv;
+            if (v != 0.f) { atomicAdd(a.d_f_lo + ((pair * L + k) * HW + (size_t)cy * g.W + cx) * 2 + comp, v); *sv = 0.f; }
+          }
+          __syncthreads();
+        }
+      }
+      if (self && a.d_input && active) {   // lvd.py:845: the target frame passes straight through
+        const float n = (1.f + 1e-6f) / D;
+        const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q : nullptr;
+        float* o = a.d_input + ((size_t)b * g.T + tp) * C * HWd + q;
+        WB_UNROLL for (int c = 0; c < WB_MAX_C; ++c)
+          if (c < C) wb_atomic_add(o + (size_t)c * HWd, (draw ? __ldg(draw + (size_t)c * HWd) : 0.f) + n * gO[c]);
+      }
+    }
+  }
+  if (a.d_occ) {
+    __syncthreads();
+    float* part = a.occ_part + ((size_t)btp * gridDim.x + blockIdx.x) * L * L;
+    for (int e = wb_tid(); e < L * L; e += wb_nthr()) {
+      float acc = 0.f;
+      for (int w = 0; w < WB_NWARP; ++w) acc += s_red[w][e];
+      part[e] = acc;
+    }
+  }
+}
+
+// d_occ[b, frame(group), :] += sum over CTAs (in order) of the partials.  mode 0: group = (b,tp) -> frame pred_ts[tp];
+// mode 1: group = (b,t) -> frame t.
+__global__ void k_occ_reduce(const float* __restrict__ part, int groups, int per_b, int ctas, int LL, int T,
+                             const int64_t* __restrict__ pred_ts, int mode, float* __restrict__ d_occ) {
+  const int grp = blockIdx.x, b = grp / per_b, j = grp - b * per_b;
+  const int frame = mode == 0 ? (int)pred_ts[j] : j;
+  for (int e = wb_tid(); e < LL; e += wb_nthr()) {
+    float acc = 0.f;
+    for (int c = 0; c < ctas; ++c) acc += part[((size_t)grp * ctas + c) * LL + e];
+    d_occ[((size_t)b * T + frame) * LL + e] += acc;
+  }
+}
+
+// ============================================================================ context-alpha backward (B4..B2b)
+// grid = (red_ctas, B*Tw), block = 256.
+__global__ void __launch_bounds__(WB_TILE_PX) k_alpha_prep_bwd(WbDecB a) {
+  const WbDec& d = a.f;
+  const waldo_geom_t g = d.g;
+  const int No = g.No, Nl = g.Nl, L = No + 1, HW = g.H * g.W;
+  const size_t HWd = (size_t)g.Hd * g.Wd;
+  const int bt = blockIdx.y, b = bt / g.Tw, t = bt - b * g.Tw;
+  const bool filt = (g.flags & WALDO_F_FILTER) != 0;
+  const bool lowres_direct = (g.Hd == g.H);
+  const bool need_p = filt && a.d_prof_p;
+  __shared__ float s_P[(WB_MAX_L - 1) * WB_MAX_NL];
+  __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
+  __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
+  __shared__ float s_redp[WB_NWARP][(WB_MAX_L - 1) * WB_MAX_NL];
+  __shared__ float s_win[WB_WIN_CAP * WB_MAX_L];
+  if (filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)b * No * Nl + i];
+  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + t) * L * L + i);
+  for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
+  for (int i = wb_tid(); i < WB_NWARP * (WB_MAX_L - 1) * WB_MAX_NL; i += wb_nthr()) (&s_redp[0][0])[i] = 0.f;
+  for (int i = wb_tid(); i < WB_WIN_CAP * WB_MAX_L; i += wb_nthr()) s_win[i] = 0.f;
+  __syncthreads();
+  float* s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
+  float* s_accp = s_redp[wb_warp()];
+  const int lane = wb_lane();
+  const float rlo = (float)g.H / (float)g.Hd;
+  const float* lyt_base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
+  const float* alo = d.a_lo + ((size_t)b * g.Tw + t) * L * HW;
+  const int tiles_x = (g.Wd + WB_TILE_W - 1) / WB_TILE_W, tiles_y = (g.Hd + WB_TILE_H - 1) / WB_TILE_H;
+  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+    const int ty0 = (tile / tiles_x) * WB_TILE_H, tx0 = (tile % tiles_x) * WB_TILE_W;
+    const int wy0 = wb_axis(ty0, rlo, g.H).i0, wy1 = wb_axis(min(ty0 + WB_TILE_H, g.Hd) - 1, rlo, g.H).i1;
+    const int wx0 = wb_axis(tx0, rlo, g.W).i0, wx1 = wb_axis(min(tx0 + WB_TILE_W, g.Wd) - 1, rlo, g.W).i1;
+    const int ww = wx1 - wx0 + 1, wcells = ww * (wy1 - wy0 + 1);
+    for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
+      const int X = tx0 + (it & (WB_TILE_W - 1)), Y = ty0 + it / WB_TILE_W;
+      const bool active = X < g.Wd && Y < g.Hd;
+      const size_t q = active ? (size_t)Y * g.Wd + X : 0;
+      // ---- recompute the forward of this pixel
+      float sm[WB_MAX_NL];
+      if (filt) {
+        float lyt[WB_MAX_NL];
+        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) lyt[c] = __ldg(lyt_base + c * HWd + q);
+        float mx = lyt[0];
+        WB_UNROLL for (int c = 1; c < WB_MAX_NL; ++c) if (c < Nl) mx = fmaxf(mx, lyt[c]);
+        float s = 0.f;
+        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) { sm[c] = expf(lyt[c] - mx); s += sm[c]; }
+        const float inv = 1.f / s;
+        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) sm[c] *= inv;
+      }
+      WbAxis ay = wb_axis(Y < g.Hd ? Y : 0, rlo, g.H), ax = wb_axis(X < g.Wd ? X : 0, rlo, g.W);
+      const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
+      float aup[WB_MAX_L], av[WB_MAX_L], ell[WB_MAX_L];
+      WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
+        if (k < L) {
+          const float* pl = alo + (size_t)k * HW;
+          float v = lowres_direct ? __ldg(pl + o00)
+                                  : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
+          aup[k] = v; ell[k] = 1.f;
+          if (filt && k >= 1) {
+            float dist = 0.f;
+            WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) dist += fabsf(s_P[(k - 1) * Nl + c] - sm[c]);
+            ell[k] = 1.f - dist * 0.5f;
+          }
+          av[k] = v * ell[k];
+        }
+      }
+      // ---- upstream: scatter-accumulated d/dA plus the returned alpha = 2A - 1
+      float gA[WB_MAX_L], ga[WB_MAX_L];
+      WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
+        if (k < L) {
+          float v = 0.f;
+          if (active) {
+            const size_t o = (((size_t)b * g.Tw + t) * L + k) * HWd + q;
+            if (a.d_alpha_acc) v += a.d_alpha_acc[o];
+            if (a.d_alpha) v += 2.f * __ldg(a.d_alpha + o);
+          }
+          gA[k] = v; ga[k] = 0.f;
+        }
+      }
+      wb_occlude_bwd(av, gA, s_occ, L, ga, s_acc);
+      // ---- filter + up-sampling backward
+      float gsm[WB_MAX_NL];
+      WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) gsm[c] = 0.f;
+      const float w00 = ax.l0 * ay.l0, w01 = ax.l1 * ay.l0, w10 = ax.l0 * ay.l1, w11 = ax.l1 * ay.l1;
+      const int c00 = (ay.i0 - wy0) * ww + ax.i0 - wx0, c01 = (ay.i0 - wy0) * ww + ax.i1 - wx0;
+      const int c10 = (ay.i1 - wy0) * ww + ax.i0 - wx0, c11 = (ay.i1 - wy0) * ww + ax.i1 - wx0;
+      WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
+        if (k < L) {
+          const float gup = ga[k] * ell[k];
+          if (filt && k >= 1) {
+            const float gl = ga[k] * aup[k];   // d / d ell_k
+            WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) {
+              if (c < Nl) {
+                const float df = s_P[(k - 1) * Nl + c] - sm[c];
+                const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+                const float v = -0.5f * sg * gl;
+                gsm[c] -= v;
+                if (need_p) {
+                  float r = wb_warp_sum(v);
+                  if (lane == 0) s_accp[(k - 1) * Nl + c] += r;
+                }
+              }
+            }
+          }
+          if (a.d_a_lo) {
+            if (lowres_direct) wb_atomic_add(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + o00, gup);
+            else if (gup != 0.f) {
+              atomicAdd(s_win + c00 * WB_MAX_L + k, w00 * gup); atomicAdd(s_win + c01 * WB_MAX_L + k, w01 * gup);
+              atomicAdd(s_win + c10 * WB_MAX_L + k, w10 * gup); atomicAdd(s_win + c11 * WB_MAX_L + k, w11 * gup);
+            }
+          }
+        }
+      }
+      if (filt && a.d_input && active) {   // softmax backward into the layout logits of this frame
+        float dot = 0.f;
+        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) dot += gsm[c] * sm[c];
+        float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd + q;
+        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) wb_atomic_add(o + (size_t)c * HWd, sm[c] * (gsm[c] - dot));
+      }
+    }
+    if (a.d_a_lo && !lowres_direct) {
+      __syncthreads();
+      for (int e = wb_tid(); e < wcells * L; e += wb_nthr()) {
+        const int cell = e / L, k = e - cell * L;
+        const int cy = cell / ww + wy0, cx = cell % ww + wx0;
+        float* sv = s_win + (size_t)cell * WB_MAX_L + k;
+        const float v = *sv;
+        if (v != 0.f) { atomicAdd(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + (size_t)cy * g.W + cx, v); *sv = 0.f; }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (a.d_occ) {
+    float* part = a.occ_part + ((size_t)bt * gridDim.x + blockIdx.x) * L * L;
+    for (int e = wb_tid(); e < L * L; e += wb_nthr()) {
+      float acc = 0.f;
+      for (int w = 0; w < WB_NWARP; ++w) acc += s_red[w][e];
+      part[e] = acc;
+    }
+  }
+  if (need_p) {
+    float* part = a.prof_p_part + ((size_t)bt * gridDim.x + blockIdx.x) * No * Nl;
+    for (int e = wb_tid(); e < No * Nl; e += wb_nthr()) {
+      float acc = 0.f;
+      for (int w = 0; w < WB_NWARP; ++w) acc += s_redp[w][e];
+      part[e] = acc;
+    }
+  }
+}
+
+// d_prof_p[b,:] = sum_t sum_cta partial (ordered); then through P = softmax(num/den) (or P = cls).
+__global__ void k_profile_final_bwd(WbDecB a) {
+  const WbDec& d = a.f;
+  const waldo_geom_t g = d.g;
+  const int No = g.No, Nl = g.Nl, nout = No * Nl + No;
+  const int b = blockIdx.x;
+  const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
+  for (int e = wb_tid(); e < No * Nl; e += wb_nthr()) {
+    float acc = 0.f;
+    for (int t = 0; t < g.Tw; ++t)
+      for (int c = 0; c < a.red_ctas; ++c) acc += a.prof_p_part[(((size_t)b * g.Tw + t) * a.red_ctas + c) * No * Nl + e];
+    a.d_prof_p[(size_t)b * No * Nl + e] = acc;
+  }
+  __syncthreads();
+  for (int k = wb_tid(); k < No; k += wb_nthr()) {
+    const float* gP = a.d_prof_p + ((size_t)b * No + k) * Nl;
+    if (from_cls) {
+      if (a.d_cls) for (int c = 0; c < Nl; ++c) a.d_cls[((size_t)b * No + k) * Nl + c] += gP[c];
+      continue;
+    }
+    const float* P = d.prof_p + ((size_t)b * No + k) * Nl;
+    const float den = d.prof_sum[(size_t)b * nout + No * Nl + k];
+    float dot = 0.f;
+    for (int c = 0; c < Nl; ++c) dot += gP[c] * P[c];
+    float gden = 0.f;
+    for (int c = 0; c < Nl; ++c) {
+      const float gM = P[c] * (gP[c] - dot);                  // softmax backward
+      const float num = d.prof_sum[(size_t)b * nout + k * Nl + c];
+      a.d_prof_sum[(size_t)b * nout + k * Nl + c] = gM / den; // M = num / den
+      gden -= gM * num / (den * den);
+    }
+    a.d_prof_sum[(size_t)b * nout + No * Nl + k] = gden;
+  }
+}
+
+// backward of the class-profile sums (lvd.py:735-742) on the low-res lattice; grid = (prof_ctas, B), block 256.
+// d cls uses the same staged, ordered reduction as the forward.
+__global__ void __launch_bounds__(256) k_class_profile_bwd(WbDecB a) {
+  const WbDec& d = a.f;
+  const waldo_geom_t g = d.g;
+  const int No = g.No, Nl = g.Nl, HW = g.H * g.W, L = No + 1, nout = No * Nl + No;
+  const size_t HWd = (size_t)g.Hd * g.Wd;
+  const int b = blockIdx.y;
+  const int nsamp = g.Tw * HW;
+  const bool wcls = (g.flags & WALDO_F_WEIGHT_CLS) != 0;
+  __shared__ float s_sm[WB_PROF_BATCH][WB_MAX_NL + 1];
+  __shared__ float s_gq[WB_PROF_BATCH][WB_MAX_L];
+  __shared__ float s_cls[(WB_MAX_L - 1) * WB_MAX_NL];
+  __shared__ float s_gsum[(WB_MAX_L - 1) * WB_MAX_NL + WB_MAX_L];
+  if (wcls)
+    for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_cls[i] = __ldg(d.cls + (size_t)b * No * Nl + i) + g.min_cls;
+  for (int i = wb_tid(); i < nout; i += wb_nthr()) s_gsum[i] = a.d_prof_sum[(size_t)b * nout + i];
+  float* part = (wcls && a.d_cls) ? a.cls_part + ((size_t)b * gridDim.x + blockIdx.x) * No * Nl : nullptr;
+  if (part) for (int o = wb_tid(); o < No * Nl; o += wb_nthr()) part[o] = 0.f;
+  __syncthreads();
+  const float r = (float)g.Hd / (float)g.H;
+  for (int s0 = blockIdx.x * WB_PROF_BATCH; s0 < nsamp; s0 += gridDim.x * WB_PROF_BATCH) {
+    const int ns = min(WB_PROF_BATCH, nsamp - s0);
+    for (int i = wb_tid(); i < ns; i += wb_nthr()) {
+      const int s = s0 + i, t = s / HW, p = s - t * HW;
+      float lyt[WB_MAX_NL], sm[WB_MAX_NL], glyt[WB_MAX_NL], gsmx[WB_MAX_NL];
+      wb_lyt_lo(d, b, t, p, lyt);
+      if (wcls) wb_softmax(lyt, sm, Nl);
+      for (int c = 0; c < Nl; ++c) { glyt[c] = 0.f; gsmx[c] = 0.f; }
+      for (int k = 0; k < No; ++k) {
+        const size_t ia = (((size_t)b * g.Tw + t) * L + k + 1) * HW + p;
+        const float al = __ldg(d.a_lo + ia) + 1e-6f;
+        float qk = 1.f;
+        if (wcls) { qk = 0.f; for (int c = 0; c < Nl; ++c) qk += s_cls[k * Nl + c] * sm[c]; }
+        const float w = al * qk;
+        float gw = s_gsum[No * Nl + k];
+        for (int c = 0; c < Nl; ++c) { gw += s_gsum[k * Nl + c] * lyt[c]; glyt[c] += s_gsum[k * Nl + c] * w; }
+        if (a.d_a_lo) a.d_a_lo[ia] += gw * qk;
+        const float gq = gw * al;
+        s_gq[i][k] = gq;
+        if (wcls) for (int c = 0; c < Nl; ++c) gsmx[c] += gq * s_cls[k * Nl + c];
+      }
+      if (wcls) {
+        float dot = 0.f;
+        for (int c = 0; c < Nl; ++c) dot += gsmx[c] * sm[c];
+        for (int c = 0; c < Nl; ++c) { glyt[c] += sm[c] * (gsmx[c] - dot); s_sm[i][c] = sm[c]; }
+      }
+      if (a.d_input) {   // transpose of the bilinear down-sampling
+        const int y = p / g.W, x = p - y * g.W;
+        WbAxis ay = wb_axis(y, r, g.Hd), ax = wb_axis(x, r, g.Wd);
+        float* base = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
+        for (int c = 0; c < Nl; ++c) {
+          float* pl = base + (size_t)c * HWd;
+          const float gv = glyt[c];
+          wb_atomic_add(pl + (size_t)ay.i0 * g.Wd + ax.i0, gv * ax.l0 * ay.l0);
+          wb_atomic_add(pl + (size_t)ay.i0 * g.Wd + ax.i1, gv * ax.l1 * ay.l0);
+          wb_atomic_add(pl + (size_t)ay.i1 * g.Wd + ax.i0, gv * ax.l0 * ay.l1);
+          wb_atomic_add(pl + (size_t)ay.i1 * g.Wd + ax.i1, gv * ax.l1 * ay.l1);
+        }
+      }
+    }
+    __syncthreads();
+    if (part) {
+      for (int o = wb_tid(); o < No * Nl; o += wb_nthr()) {
+        const int k = o / Nl, c = o - k * Nl;
+        float acc = part[o];
+        for (int i = 0; i < ns; ++i) acc += s_gq[i][k] * s_sm[i][c];
+        part[o] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_cls_reduce(WbDecB a) {
+  const waldo_geom_t g = a.f.g;
+  const int n = g.No * g.Nl, b = blockIdx.x;
+  for (int e = wb_tid(); e < n; e += wb_nthr()) {
+    float acc = 0.f;
+    for (int c = 0; c < a.f.prof_ctas; ++c) acc += a.cls_part[((size_t)b * a.f.prof_ctas + c) * n + e];
+    a.d_cls[(size_t)b * n + e] += acc;
+  }
+}
+
+// ============================================================================ low-res chain
+// B1 backward: d a_lo -> d (obj|bg) alpha (scatter) and d src_grid (grid gradient).
+__global__ void k_project_alpha_bwd(WbDecB a) {
+  const WbDec& d = a.f;
+  const waldo_geom_t g = d.g;
+  const int L = wb_L(g), HW = g.H * g.W;
+  const long long total = (long long)g.B * g.Tw * L * HW;
+  for (long long e = (long long)blockIdx.x * wb_nthr() + wb_tid(); e < total; e += (long long)gridDim.x * wb_nthr()) {
+    const float gv = a.d_a_lo[e];
+    if (gv == 0.f) continue;
+    int p = (int)(e % HW);
+    int k = (int)((e / HW) % L);
+    int t = (int)((e / ((long long)HW * L)) % g.Tw);
+    int b = (int)(e / ((long long)HW * L * g.Tw));
+    const float* sg; const float* plane; float* dplane; float* dsg; int w, h;
+    if (k == 0) {
+      size_t o = (((size_t)b * g.T + t) * HW + p) * 2;
+      sg = d.src_grid_bg + o; dsg = a.d_src_grid_bg ? a.d_src_grid_bg + o : nullptr;
+      plane = d.bg_alpha + (size_t)b * HW; dplane = a.d_bg_alpha ? a.d_bg_alpha + (size_t)b * HW : nullptr; w = g.W; h = g.H;
+    } else {
+      size_t o = ((((size_t)b * g.T + t) * g.No + (k - 1)) * HW + p) * 2;
+      sg = d.src_grid_obj + o; dsg = a.d_src_grid_obj ? a.d_src_grid_obj + o : nullptr;
+      size_t po = ((size_t)b * g.No + (k - 1)) * g.Ho * g.Wo;
+      plane = d.obj_alpha + po; dplane = a.d_obj_alpha ? a.d_obj_alpha + po : nullptr; w = g.Wo; h = g.Ho;
+    }
+    WbTaps tp = wb_taps(__ldg(sg), __ldg(sg + 1), w, h);
+    const int m = wb_tap_mask(tp, w, h);
+    const long long off = (long long)tp.y0 * w + tp.x0;
+    const float* q = plane + off;
+    const float vnw = (m & 1) ? (__ldg(q) + 1.f) * 0.5f : 0.f, vne = (m & 2) ? (__ldg(q + 1) + 1.f) * 0.5f : 0.f;
+    const float vsw = (m & 4) ? (__ldg(q + w) + 1.f) * 0.5f : 0.f, vse = (m & 8) ? (__ldg(q + w + 1) + 1.f) * 0.5f : 0.f;
+    if (dplane) {
+      float* o = dplane + off;
+      if (m & 1) wb_atomic_add(o, 0.5f * tp.nw * gv);
+      if (m & 2) wb_atomic_add(o + 1, 0.5f * tp.ne * gv);
+      if (m & 4) wb_atomic_add(o + w, 0.5f * tp.sw * gv);
+      if (m & 8) wb_atomic_add(o + w + 1, 0.5f * tp.se * gv);
+    }
+    if (dsg) {
+      wb_atomic_add(dsg, gv * ((vne - vnw) * tp.wy0 + (vse - vsw) * tp.wy1) * (0.5f * (float)w));
+      wb_atomic_add(dsg + 1, gv * ((vsw - vnw) * tp.wx0 + (vse - vne) * tp.wx1) * (0.5f * (float)h));
+    }
+  }
+}
+
+// B5 backward: d f_lo -> d tgt_grid (context +, target -) and d src_grid of the target frame.
+__global__ void k_layer_flow_lo_bwd(WbDecB a) {
+  const WbDec& d = a.f;
+  const waldo_geom_t g = d.g;
+  const int L = wb_L(g), HW = g.H * g.W;
+  const long long total = (long long)g.B * g.Tp * L * HW;
+  for (long long e = (long long)blockIdx.x * wb_nthr() + wb_tid(); e < total; e += (long long)gridDim.x * wb_nthr()) {
+    int p = (int)(e % HW);
+    int k = (int)((e / HW) % L);
+    int tp = (int)((e / ((long long)HW * L)) % g.Tp);
+    int b = (int)(e / ((long long)HW * L * g.Tp));
+    int u = (int)d.pred_ts[tp];
+    const float* sg; float* dsg; int w, h; size_t frame_stride, layer_off;
+    const float* tg; float* dtg;
+    if (k == 0) {
+      w = g.W; h = g.H; frame_stride = (size_t)HW * 2; layer_off = 0;
+      size_t o = (((size_t)b * g.T + u) * HW + p) * 2;
+      sg = d.src_grid_bg + o; dsg = a.d_src_grid_bg ? a.d_src_grid_bg + o : nullptr;
+      tg = d.tgt_grid_bg; dtg = a.d_tgt_grid_bg;
+    } else {
+      w = g.Wo; h = g.Ho; frame_stride = (size_t)g.No * g.Ho * g.Wo * 2; layer_off = (size_t)(k - 1) * g.Ho * g.Wo * 2;
+      size_t o = ((((size_t)b * g.T + u) * g.No + (k - 1)) * HW + p) * 2;
+      sg = d.src_grid_obj + o; dsg = a.d_src_grid_obj ? a.d_src_grid_obj + o : nullptr;
+      tg = d.tgt_grid_obj; dtg = a.d_tgt_grid_obj;
+    }
+    WbTaps t = wb_taps(__ldg(sg), __ldg(sg + 1), w, h);
+    const int m = wb_tap_mask(t, w, h);
+    if (m == 0) continue;
+    const long long o = ((long long)t.y0 * w + t.x0) * 2;
+    const size_t base_u = ((size_t)b * g.T + u) * frame_stride + layer_off;
+    float gsx = 0.f, gsy = 0.f;
+    for (int tc = 0; tc < g.Tc; ++tc) {
+      const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+      const float* gf = a.d_f_lo + (((((size_t)b * g.Tc + tc) * g.Tp + tp) * L + k) * HW + p) * 2;
+      const float g0 = gf[0], g1 = gf[1];
+      if (g0 == 0.f && g1 == 0.f) continue;
+      const size_t base_c = ((size_t)b * g.T + c_t) * frame_stride + layer_off;
+      WB_UNROLL for (int c = 0; c < 2; ++c) {
+        const float gc = c == 0 ? g0 : g1;
+        const float vnw = (m & 1) ? tg[base_c + o + c] - tg[base_u + o + c] : 0.f;
+        const float vne = (m & 2) ? tg[base_c + o + 2 + c] - tg[base_u + o + 2 + c] : 0.f;
+        const float vsw = (m & 4) ? tg[base_c + o + 2 * w + c] - tg[base_u + o + 2 * w + c] : 0.f;
+        const float vse = (m & 8) ? tg[base_c + o + 2 * w + 2 + c] - tg[base_u + o + 2 * w + 2 + c] : 0.f;
+        gsx += gc * ((vne - vnw) * t.wy0 + (vse - vsw) * t.wy1);
+        gsy += gc * ((vsw - vnw) * t.wx0 + (vse - vne) * t.wx1);
+        if (dtg && c_t != u) {
+          if (m & 1) { wb_atomic_add(dtg + base_c + o + c, t.nw * gc); wb_atomic_add(dtg + base_u + o + c, -t.nw * gc); }
+          if (m & 2) { wb_atomic_add(dtg + base_c + o + 2 + c, t.ne * gc); wb_atomic_add(dtg + base_u + o + 2 + c, -t.ne * gc); }
+          if (m & 4) { wb_atomic_add(dtg + base_c + o + 2 * w + c, t.sw * gc); wb_atomic_add(dtg + base_u + o + 2 * w + c, -t.sw * gc); }
+          if (m & 8) { wb_atomic_add(dtg + base_c + o + 2 * w + 2 + c, t.se * gc); wb_atomic_add(dtg + base_u + o + 2 * w + 2 + c, -t.se * gc); }
+        }
+      }
+    }
+    if (dsg) {
+      wb_atomic_add(dsg, gsx * (0.5f * (float)w));
+      wb_atomic_add(dsg + 1, gsy * (0.5f * (float)h));
+    }
+  }
+}
+
+// ============================================================================ launcher
+static inline unsigned wb_blocks_b(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > (1 << 20)) b = 1 << 20;
+  return (unsigned)b;
+}
+
+#ifndef WB_HOST_EMU
+static int wb_check_launch(const char* file, int line);
+#endif
+static int wb_fail(int code, const char* fmt, ...);
+
+static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
+  const WbDec& d = a.f;
+  const waldo_geom_t& g = d.g;
+#define WB_BREQ(cond, msg) do { if (!(cond)) return wb_fail(WALDO_EINVAL, "decode_bwd: %s", msg); } while (0)
+#define WB_BLAUNCHED() do { int rc_ = WB_CHECK_LAUNCH(); if (rc_) return rc_; } while (0)
+  WB_BREQ(g.B > 0 && g.No >= 1 && g.No + 1 <= WB_MAX_L && g.Nl <= WB_MAX_NL && g.C <= WB_MAX_C, "bad geometry");
+  WB_BREQ(d.input && d.alpha && d.f_lo && d.a_lo && d.out_full && d.norm && d.occ && d.ctx_ts && d.pred_ts, "forward state missing");
+  WB_BREQ(a.red_ctas > 0, "red_ctas must be positive");
+  const int L = g.No + 1, HW = g.H * g.W;
+  const bool filt = (g.flags & WALDO_F_FILTER) != 0;
+  const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
+  const bool geom = a.d_tgt_grid_obj || a.d_src_grid_obj || a.d_tgt_grid_bg || a.d_src_grid_bg;
+  const bool need_alpha_chain = geom || a.d_obj_alpha || a.d_bg_alpha || a.d_cls || a.d_occ || (filt && a.d_input) || a.d_alpha;
+  if (a.d_occ) WB_BREQ(a.occ_part, "occ_part scratch missing");
+  if (geom) WB_BREQ(a.d_f_lo && a.d_a_lo && a.d_alpha_acc, "geometry gradients need d_f_lo, d_a_lo, d_alpha_acc scratch");
+  if (a.d_obj_alpha || a.d_bg_alpha || a.d_cls) WB_BREQ(a.d_a_lo && a.d_alpha_acc, "alpha gradients need d_a_lo, d_alpha_acc scratch");
+  if (g.Hd != g.H) {
+    // window capacity of the shared-memory low-res accumulators
+    const float r = (float)g.H / (float)g.Hd;
+    const int wh = (int)ceilf((WB_TILE_H - 1) * r) + 2, wwid = (int)ceilf((WB_TILE_W - 1) * r) + 2;
+    WB_BREQ(wh * wwid <= WB_WIN_CAP, "scale_hd too small for the compiled low-res window (needs scale_hd >= 2)");
+  }
+  // 1. fused HD backward
+  WB_LAUNCH(k_warp_composite_bwd, dim3(a.red_ctas, g.B * g.Tp), dim3(WB_TILE_PX), 0, st, a);
+  WB_BLAUNCHED();
+  if (a.d_occ) {
+    WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);
+    WB_BLAUNCHED();
+  }
+  if (!need_alpha_chain) return 0;
+  // 2. context-alpha backward
+  if (a.d_alpha_acc || a.d_alpha) {
+    if (filt && a.d_prof_p) WB_BREQ(a.prof_p_part, "prof_p_part scratch missing");
+    WB_LAUNCH(k_alpha_prep_bwd, dim3(a.red_ctas, g.B * g.Tw), dim3(WB_TILE_PX), 0, st, a);
+    WB_BLAUNCHED();
+    if (a.d_occ) {
+      WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tw), dim3(128), 0, st, a.occ_part, g.B * g.Tw, g.Tw, a.red_ctas, L * L, g.T, d.pred_ts, 1, a.d_occ);
+      WB_BLAUNCHED();
+    }
+    if (filt && a.d_prof_p) {
+      WB_BREQ(a.d_prof_sum, "d_prof_sum scratch missing");
+      WB_LAUNCH(k_profile_final_bwd, dim3(g.B), dim3(64), 0, st, a);
+      WB_BLAUNCHED();
+      if (!from_cls) {
+        if ((g.flags & WALDO_F_WEIGHT_CLS) && a.d_cls) WB_BREQ(a.cls_part, "cls_part scratch missing");
+        WB_LAUNCH(k_class_profile_bwd, dim3(d.prof_ctas, g.B), dim3(256), 0, st, a);
+        WB_BLAUNCHED();
+        if ((g.flags & WALDO_F_WEIGHT_CLS) && a.d_cls) {
+          WB_LAUNCH(k_cls_reduce, dim3(g.B), dim3(128), 0, st, a);
+          WB_BLAUNCHED();
+        }
+      }
+    }
+  }
+  // 3. low-res chain
+  if (a.d_a_lo && (a.d_obj_alpha || a.d_bg_alpha || a.d_src_grid_obj || a.d_src_grid_bg)) {
+    WB_LAUNCH(k_project_alpha_bwd, dim3(wb_blocks_b((long long)g.B * g.Tw * L * HW, 256)), dim3(256), 0, st, a);
+    WB_BLAUNCHED();
+  }
+  if (a.d_f_lo && geom) {
+    WB_LAUNCH(k_layer_flow_lo_bwd, dim3(wb_blocks_b((long long)g.B * g.Tp * L * HW, 256)), dim3(256), 0, st, a);
+    WB_BLAUNCHED();
+  }
+  return 0;
+#undef WB_BREQ
+#undef WB_BLAUNCHED
+}

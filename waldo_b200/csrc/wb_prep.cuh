@@ -1,0 +1,258 @@
+// Stage B low-res + context-alpha kernels (forward).
+// Reference: models/nets/lvd.py:707-766 (grid_to_flow_ctx B1-B4), :617-653 (grid_to_flow), :771-794 (B5).
+#pragma once
+#include "wb_common.cuh"
+#include "../../include/waldo_b200.h"
+
+typedef waldo_decode_fwd_t WbDec;
+
+WB_DEV int wb_L(const waldo_geom_t& g) { return g.No + 1; }
+
+// ------------------------------------------------------------------ B1: project opacities (lvd.py:723-728)
+// a_lo[b,t,k,p] = bil0((alpha_k+1)/2, src_grid_k[b,t,p]); k = 0 background, k >= 1 objects.
+__global__ void k_project_alpha(WbDec d) {
+  const waldo_geom_t g = d.g;
+  const int L = wb_L(g), HW = g.H * g.W;
+  const long long total = (long long)g.B * g.Tw * L * HW;
+  for (long long e = (long long)blockIdx.x * wb_nthr() + wb_tid(); e < total; e += (long long)gridDim.x * wb_nthr()) {
+    int p = (int)(e % HW);
+    int k = (int)((e / HW) % L);
+    int t = (int)((e / ((long long)HW * L)) % g.Tw);
+    int b = (int)(e / ((long long)HW * L * g.Tw));
+    const float* sg; const float* plane; int w, h;
+    if (k == 0) {
+      sg = d.src_grid_bg + (((size_t)b * g.T + t) * HW + p) * 2;
+      plane = d.bg_alpha + (size_t)b * HW; w = g.W; h = g.H;
+    } else {
+      sg = d.src_grid_obj + ((((size_t)b * g.T + t) * g.No + (k - 1)) * HW + p) * 2;
+      plane = d.obj_alpha + ((size_t)b * g.No + (k - 1)) * g.Ho * g.Wo; w = g.Wo; h = g.Ho;
+    }
+    WbTaps tp = wb_taps(__ldg(sg), __ldg(sg + 1), w, h);
+    int m = wb_tap_mask(tp, w, h);
+    const float* q = plane + (long long)tp.y0 * w + tp.x0;
+    float vnw = (m & 1) ? (__ldg(q) + 1.f) * 0.5f : 0.f;
+    float vne = (m & 2) ? (__ldg(q + 1) + 1.f) * 0.5f : 0.f;
+    float vsw = (m & 4) ? (__ldg(q + w) + 1.f) * 0.5f : 0.f;
+    float vse = (m & 8) ? (__ldg(q + w + 1) + 1.f) * 0.5f : 0.f;
+    d.a_lo[e] = wb_chain(vnw, vne, vsw, vse, tp);
+  }
+}
+
+// low-res layout logits of one (b,t,p): bilinear down-sample of the HD input (lvd.py:716 `scale`)
+WB_DEV void wb_lyt_lo(const WbDec& d, int b, int t, int p, float* lyt /*[Nl]*/) {
+  const waldo_geom_t& g = d.g;
+  int y = p / g.W, x = p - y * g.W;
+  const float r = (float)g.Hd / (float)g.H;   // = 1 / (1/scale_hd)
+  WbAxis ay = wb_axis(y, r, g.Hd), ax = wb_axis(x, r, g.Wd);
+  const size_t HWd = (size_t)g.Hd * g.Wd;
+  const float* base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
+  for (int c = 0; c < g.Nl; ++c) {
+    const float* pl = base + c * HWd;
+    lyt[c] = wb_lerp2(__ldg(pl + (size_t)ay.i0 * g.Wd + ax.i0), __ldg(pl + (size_t)ay.i0 * g.Wd + ax.i1),
+                      __ldg(pl + (size_t)ay.i1 * g.Wd + ax.i0), __ldg(pl + (size_t)ay.i1 * g.Wd + ax.i1), ax, ay);
+  }
+}
+
+WB_DEV void wb_softmax(const float* x, float* y, int n) {
+  float mx = x[0];
+  for (int c = 1; c < n; ++c) mx = fmaxf(mx, x[c]);
+  float s = 0.f;
+  for (int c = 0; c < n; ++c) { y[c] = expf(x[c] - mx); s += y[c]; }
+  float inv = 1.f / s;
+  for (int c = 0; c < n; ++c) y[c] *= inv;
+}
+
+// ------------------------------------------------------------------ B2: class profile partial sums (lvd.py:735-742)
+// Deterministic two-step reduction: every CTA stages WB_PROF_BATCH samples (logits + per-object weights) in
+// shared memory, then thread <-> (object, class) accumulates them in sample order; CTA partials are reduced
+// in CTA order by k_profile_final.  grid = (prof_ctas, B).
+#define WB_PROF_BATCH 128
+__global__ void __launch_bounds__(256) k_class_profile(WbDec d) {
+  const waldo_geom_t g = d.g;
+  const int No = g.No, Nl = g.Nl, HW = g.H * g.W, L = No + 1;
+  const int b = blockIdx.y;
+  const int nsamp = g.Tw * HW;
+  const int nout = No * Nl + No;
+  __shared__ float s_lyt[WB_PROF_BATCH][WB_MAX_NL + 1];
+  __shared__ float s_w[WB_PROF_BATCH][WB_MAX_L];
+  __shared__ float s_cls[(WB_MAX_L - 1) * WB_MAX_NL];
+  const bool wcls = (g.flags & WALDO_F_WEIGHT_CLS) != 0;
+  if (wcls)
+    for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_cls[i] = __ldg(d.cls + (size_t)b * No * Nl + i) + g.min_cls;
+  // accumulators: outputs o = tid, tid + nthr, ... (at most 2 per thread with 256 threads; generic loop for emu)
+  float* part = d.prof_part + ((size_t)b * gridDim.x + blockIdx.x) * nout;
+  for (int o = wb_tid(); o < nout; o += wb_nthr()) part[o] = 0.f;
+  __syncthreads();
+  for (int s0 = blockIdx.x * WB_PROF_BATCH; s0 < nsamp; s0 += gridDim.x * WB_PROF_BATCH) {
+    const int ns = min(WB_PROF_BATCH, nsamp - s0);
+    for (int i = wb_tid(); i < ns; i += wb_nthr()) {
+      int s = s0 + i, t = s / HW, p = s - t * HW;
+      float lyt[WB_MAX_NL], sm[WB_MAX_NL];
+      wb_lyt_lo(d, b, t, p, lyt);
+      if (wcls) wb_softmax(lyt, sm, Nl);
+      for (int c = 0; c < Nl; ++c) s_lyt[i][c] = lyt[c];
+      for (int k = 0; k < No; ++k) {
+        float w = __ldg(d.a_lo + (((size_t)b * g.Tw + t) * L + k + 1) * HW + p) + 1e-6f;
+        if (wcls) {
+          float acc = 0.f;
+          for (int c = 0; c < Nl; ++c) acc += s_cls[k * Nl + c] * sm[c];
+          w *= acc;
+        }
+        s_w[i][k] = w;
+      }
+    }
+    __syncthreads();
+    for (int o = wb_tid(); o < nout; o += wb_nthr()) {
+      float acc = part[o];
+      if (o < No * Nl) {
+        int k = o / Nl, c = o - k * Nl;
+        for (int i = 0; i < ns; ++i) acc += s_lyt[i][c] * s_w[i][k];
+      } else {
+        int k = o - No * Nl;
+        for (int i = 0; i < ns; ++i) acc += s_w[i][k];
+      }
+      part[o] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// reduce CTA partials in order, then P = softmax_c(num / den)  (lvd.py:742,744); or P = cls (lvd.py:753)
+__global__ void k_profile_final(WbDec d) {
+  const waldo_geom_t g = d.g;
+  const int No = g.No, Nl = g.Nl, nout = No * Nl + No;
+  const int b = blockIdx.x;
+  const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
+  if (!from_cls) {
+    for (int o = wb_tid(); o < nout; o += wb_nthr()) {
+      float acc = 0.f;
+      for (int c = 0; c < d.prof_ctas; ++c) acc += d.prof_part[((size_t)b * d.prof_ctas + c) * nout + o];
+      d.prof_sum[(size_t)b * nout + o] = acc;
+    }
+    __syncthreads();
+  }
+  for (int k = wb_tid(); k < No; k += wb_nthr()) {
+    float* P = d.prof_p + ((size_t)b * No + k) * Nl;
+    if (from_cls) {
+      for (int c = 0; c < Nl; ++c) P[c] = __ldg(d.cls + ((size_t)b * No + k) * Nl + c);
+    } else {
+      float mean[WB_MAX_NL];
+      float den = d.prof_sum[(size_t)b * nout + No * Nl + k];
+      for (int c = 0; c < Nl; ++c) mean[c] = d.prof_sum[(size_t)b * nout + k * Nl + c] / den;
+      wb_softmax(mean, P, Nl);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ B2b-B4: context opacity at HD (lvd.py:744-765)
+// One thread per HD pixel of one (b,t); grid = (pixel chunks, B*Tw).
+//   l_k   = 1 - 0.5 * sum_c |P[b,k,c] - softmax(hd_lyt)[c]|
+//   a_k   = up(a_lo[k]) * (k >= 1 ? l_k : 1)
+//   A_i   = a_i * prod_j (1 - a_j * occ[b,t,j,i]);     alpha = 2A - 1
+__global__ void __launch_bounds__(256) k_alpha_prep(WbDec d) {
+  const waldo_geom_t g = d.g;
+  const int No = g.No, Nl = g.Nl, L = No + 1, HW = g.H * g.W;
+  const size_t HWd = (size_t)g.Hd * g.Wd;
+  const int bt = blockIdx.y, b = bt / g.Tw, t = bt - b * g.Tw;
+  const bool filt = (g.flags & WALDO_F_FILTER) != 0;
+  __shared__ float s_P[(WB_MAX_L - 1) * WB_MAX_NL];
+  __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
+  if (filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)b * No * Nl + i];
+  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + t) * L * L + i);
+  __syncthreads();
+  const float r = (float)g.H / (float)g.Hd;   // 1 / scale_hd
+  const float* lyt_base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
+  const float* alo = d.a_lo + ((size_t)b * g.Tw + t) * L * HW;
+  float* out = d.alpha + ((size_t)b * g.Tw + t) * L * HWd;
+  for (size_t q = (size_t)blockIdx.x * wb_nthr() + wb_tid(); q < HWd; q += (size_t)gridDim.x * wb_nthr()) {
+    int Y = (int)(q / g.Wd), X = (int)(q - (size_t)Y * g.Wd);
+    float sm[WB_MAX_NL];
+    if (filt) {
+      float lyt[WB_MAX_NL];
+      WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) lyt[c] = __ldg(lyt_base + c * HWd + q);
+      float mx = lyt[0];
+      WB_UNROLL for (int c = 1; c < WB_MAX_NL; ++c) if (c < Nl) mx = fmaxf(mx, lyt[c]);
+      float s = 0.f;
+      WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) { sm[c] = expf(lyt[c] - mx); s += sm[c]; }
+      float inv = 1.f / s;
+      WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) sm[c] *= inv;
+    }
+    WbAxis ay = wb_axis(Y, r, g.H), ax = wb_axis(X, r, g.W);
+    int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
+    float a[WB_MAX_L];
+    WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
+      if (k < L) {
+        const float* pl = alo + (size_t)k * HW;
+        float v = (g.Hd == g.H) ? __ldg(pl + o00)
+                                : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
+        if (filt && k >= 1) {
+          float dist = 0.f;
+          WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) dist += fabsf(s_P[(k - 1) * Nl + c] - sm[c]);
+          v *= 1.f - dist * 0.5f;
+        }
+        a[k] = v;
+      }
+    }
+    WB_UNROLL for (int i = 0; i < WB_MAX_L; ++i) {
+      if (i < L) {
+        float vis = 1.f;
+        WB_UNROLL for (int j = 0; j < WB_MAX_L; ++j) if (j < L) vis *= 1.f - a[j] * s_occ[j * L + i];
+        out[(size_t)i * HWd + q] = (vis * a[i]) * 2.f - 1.f;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ B5: per-layer flow on the low-res lattice (lvd.py:771-792)
+// One thread per (b,tp,k,p): bilinear taps of src_grid[b,u,k,p] in the layer's canonical frame are shared by all Tc
+// contexts; value sampled = tgt_grid[b,c,k] - tgt_grid[b,u,k].  Also the object support s_lo = bil0(1) (lvd.py:788).
+__global__ void k_layer_flow_lo(WbDec d) {
+  const waldo_geom_t g = d.g;
+  const int L = wb_L(g), HW = g.H * g.W;
+  const long long total = (long long)g.B * g.Tp * L * HW;
+  for (long long e = (long long)blockIdx.x * wb_nthr() + wb_tid(); e < total; e += (long long)gridDim.x * wb_nthr()) {
+    int p = (int)(e % HW);
+    int k = (int)((e / HW) % L);
+    int tp = (int)((e / ((long long)HW * L)) % g.Tp);
+    int b = (int)(e / ((long long)HW * L * g.Tp));
+    int u = (int)d.pred_ts[tp];
+    const float* sg; const float* tg_u; int w, h; size_t frame_stride, layer_off;
+    if (k == 0) {
+      w = g.W; h = g.H; frame_stride = (size_t)HW * 2; layer_off = 0;
+      sg = d.src_grid_bg + (((size_t)b * g.T + u) * HW + p) * 2;
+      tg_u = d.tgt_grid_bg + ((size_t)b * g.T + u) * frame_stride;
+    } else {
+      w = g.Wo; h = g.Ho; frame_stride = (size_t)g.No * g.Ho * g.Wo * 2; layer_off = (size_t)(k - 1) * g.Ho * g.Wo * 2;
+      sg = d.src_grid_obj + ((((size_t)b * g.T + u) * g.No + (k - 1)) * HW + p) * 2;
+      tg_u = d.tgt_grid_obj + ((size_t)b * g.T + u) * frame_stride + layer_off;
+    }
+    const float* tg_b = (k == 0 ? d.tgt_grid_bg : d.tgt_grid_obj) + (size_t)b * g.T * frame_stride + layer_off;
+    WbTaps t = wb_taps(__ldg(sg), __ldg(sg + 1), w, h);
+    int m = wb_tap_mask(t, w, h);
+    long long o = ((long long)t.y0 * w + t.x0) * 2;
+    float un[4][2];
+    WB_UNROLL for (int c = 0; c < 2; ++c) {
+      un[0][c] = (m & 1) ? __ldg(tg_u + o + c) : 0.f;
+      un[1][c] = (m & 2) ? __ldg(tg_u + o + 2 + c) : 0.f;
+      un[2][c] = (m & 4) ? __ldg(tg_u + o + 2 * w + c) : 0.f;
+      un[3][c] = (m & 8) ? __ldg(tg_u + o + 2 * w + 2 + c) : 0.f;
+    }
+    if (k >= 1 && d.s_lo)
+      d.s_lo[(((size_t)b * g.Tp + tp) * g.No + (k - 1)) * HW + p] =
+          wb_chain((m & 1) ? 1.f : 0.f, (m & 2) ? 1.f : 0.f, (m & 4) ? 1.f : 0.f, (m & 8) ? 1.f : 0.f, t);
+    for (int tc = 0; tc < g.Tc; ++tc) {
+      int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+      const float* tg_c = tg_b + (size_t)c_t * frame_stride;
+      float f[2];
+      WB_UNROLL for (int c = 0; c < 2; ++c) {
+        float vnw = (m & 1) ? __fsub_rn(__ldg(tg_c + o + c), un[0][c]) : 0.f;
+        float vne = (m & 2) ? __fsub_rn(__ldg(tg_c + o + 2 + c), un[1][c]) : 0.f;
+        float vsw = (m & 4) ? __fsub_rn(__ldg(tg_c + o + 2 * w + c), un[2][c]) : 0.f;
+        float vse = (m & 8) ? __fsub_rn(__ldg(tg_c + o + 2 * w + 2 + c), un[3][c]) : 0.f;
+        f[c] = wb_chain(vnw, vne, vsw, vse, t);
+      }
+      float* out = d.f_lo + (((((size_t)b * g.Tc + tc) * g.Tp + tp) * L + k) * HW + p) * 2;
+      out[0] = f[0]; out[1] = f[1];
+    }
+  }
+}

@@ -1,0 +1,340 @@
+"""torch.autograd bindings of the C ABI (include/waldo_b200.h).
+
+PyTorch here is plumbing only: it owns device memory and the stream, and chains the backward entry points.
+Every op allocates its outputs / saved state / scratch with torch and hands raw pointers to the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def _c(t: Optional[torch.Tensor], dtype=torch.float32):
+    if t is None:
+        return None
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+# ===================================================================================== a-1 TPS
+class _TpsEval(torch.autograd.Function):
+    """TPSWarp.forward, models/modules/warp.py:49-55."""
+
+    @staticmethod
+    def forward(ctx, src_pts, inverse_kernel, tgt_grid_repr, h, w):
+        lib = L.load()
+        pts = _c(src_pts.detach())
+        inverse_kernel, tgt_grid_repr = _c(inverse_kernel), _c(tgt_grid_repr)
+        n, N = pts.shape[0], pts.shape[1]
+        P = h * w
+        grid = torch.empty(n, h, w, 2, device=pts.device, dtype=torch.float32)
+        mapping = torch.empty(n, N + 3, 2, device=pts.device, dtype=torch.float64)
+        a = L.TpsFwd(n, N, P, L.ptr(inverse_kernel, name="inverse_kernel"), L.ptr(tgt_grid_repr, name="tgt_grid_repr"),
+                     L.ptr(pts, name="src_pts"), L.ptr(mapping, torch.float64), L.ptr(grid))
+        L.check(lib.waldo_tps_fwd(C.byref(a), L.stream_of(pts)), "tps_fwd")
+        ctx.save_for_backward(inverse_kernel, tgt_grid_repr)
+        ctx.dims = (n, N, P)
+        return grid
+
+    @staticmethod
+    def backward(ctx, dgrid):
+        lib = L.load()
+        inverse_kernel, tgt_grid_repr = ctx.saved_tensors
+        n, N, P = ctx.dims
+        dgrid = _c(dgrid)
+        chunks = max(1, min(64, P // 512))
+        partial = torch.empty(n, chunks, N + 3, 2, device=dgrid.device, dtype=torch.float64)
+        dpts = torch.empty(n, N, 2, device=dgrid.device, dtype=torch.float32)
+        a = L.TpsBwd(n, N, P, L.ptr(inverse_kernel), L.ptr(tgt_grid_repr), L.ptr(dgrid), chunks,
+                     L.ptr(partial, torch.float64), L.ptr(dpts))
+        L.check(lib.waldo_tps_bwd(C.byref(a), L.stream_of(dgrid)), "tps_bwd")
+        return dpts, None, None, None, None
+
+
+def tps_eval(src_pts, inverse_kernel, tgt_grid_repr, h, w):
+    return _TpsEval.apply(src_pts, inverse_kernel, tgt_grid_repr, h, w)
+
+
+# ===================================================================================== a-2 inverse warp
+@dataclass
+class InverseWarpTrace:
+    """Index maps of one inverse warp (parity rule 1: bit-exact)."""
+    field: torch.Tensor    # (n, Ht*Wt) int32, -1 = outside                 warp.py:84-88
+    winner: torch.Tensor   # (n, Ht*Wt) int32, INT32_MAX = empty cell       warp.py:113-123
+    level: torch.Tensor    # (n, Hp, Wp) uint8
+    eroded: torch.Tensor   # (n, Hp, Wp) uint8
+
+
+class _InverseWarp(torch.autograd.Function):
+    """InverseWarp.forward, models/modules/warp.py:71-174 (num_perm == 1, pad=True)."""
+
+    @staticmethod
+    def forward(ctx, fwd_grid, id_src, id_tgt, gauss, tgt_h, tgt_w, niter, erode, trace_box):
+        lib = L.load()
+        fg = _c(fwd_grid.detach())
+        n, Hs, Ws, _ = fg.shape
+        dev = fg.device
+        m = niter + 1
+        Hp, Wp = tgt_h + 2 * m, tgt_w + 2 * m
+        out = torch.empty(n, tgt_h, tgt_w, 2, device=dev, dtype=torch.float32)
+        field = torch.empty(n, tgt_h * tgt_w, device=dev, dtype=torch.int32)
+        winner = torch.empty(n, tgt_h * tgt_w, device=dev, dtype=torch.int32)
+        level = torch.empty(n, Hp, Wp, device=dev, dtype=torch.uint8)
+        eroded = torch.empty(n, Hp, Wp, device=dev, dtype=torch.uint8)
+        val = torch.empty(n, 2, Hp, Wp, device=dev, dtype=torch.float32)
+        id_src_c, id_tgt_c, gauss_c = _c(id_src), _c(id_tgt), _c(gauss)
+        a = L.InvWarpFwd(n, Hs, Ws, tgt_h, tgt_w, niter, 1 if erode else 0, L.ptr(fg, name="src_grid"), L.ptr(id_src_c),
+                         L.ptr(id_tgt_c), L.ptr(gauss_c), L.ptr(out), L.ptr(field, torch.int32), L.ptr(winner, torch.int32),
+                         L.ptr(level, torch.uint8), L.ptr(eroded, torch.uint8), L.ptr(val))
+        L.check(lib.waldo_invwarp_fwd(C.byref(a), L.stream_of(fg)), "invwarp_fwd")
+        ctx.save_for_backward(gauss_c, field, winner, level, eroded)
+        ctx.dims = (n, Hs, Ws, tgt_h, tgt_w, niter)
+        if trace_box is not None:
+            trace_box.append(InverseWarpTrace(field, winner, level, eroded))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        gauss, field, winner, level, eroded = ctx.saved_tensors
+        n, Hs, Ws, Ht, Wt, niter = ctx.dims
+        dout = _c(dout)
+        dev = dout.device
+        m = niter + 1
+        PP = (Ht + 2 * m) * (Wt + 2 * m)
+        gval = torch.empty(n, 2, PP, device=dev, dtype=torch.float32)
+        inv_sw = torch.empty(n, PP, device=dev, dtype=torch.float32)
+        gdisp = torch.empty(n, Ht * Wt, 2, device=dev, dtype=torch.float32)
+        dfwd = torch.empty(n, Hs, Ws, 2, device=dev, dtype=torch.float32)
+        a = L.InvWarpBwd(n, Hs, Ws, Ht, Wt, niter, L.ptr(gauss), L.ptr(dout), L.ptr(field, torch.int32),
+                         L.ptr(winner, torch.int32), L.ptr(level, torch.uint8), L.ptr(eroded, torch.uint8),
+                         L.ptr(gval), L.ptr(inv_sw), L.ptr(gdisp), L.ptr(dfwd))
+        L.check(lib.waldo_invwarp_bwd(C.byref(a), L.stream_of(dout)), "invwarp_bwd")
+        return dfwd, None, None, None, None, None, None, None, None
+
+
+def inverse_warp(fwd_grid, id_src, id_tgt, gauss, tgt_h, tgt_w, niter=5, erode=True, trace_box=None):
+    return _InverseWarp.apply(fwd_grid, id_src, id_tgt, gauss, tgt_h, tgt_w, niter, erode, trace_box)
+
+
+# ===================================================================================== a-4 occlusion matrix
+class _ComputeOcc(torch.autograd.Function):
+    """LVD.compute_occ, models/nets/lvd.py:59-68."""
+
+    @staticmethod
+    def forward(ctx, occ_score):
+        lib = L.load()
+        s = _c(occ_score.detach())
+        B, T, No = s.shape
+        occ = torch.empty(B, T, No + 1, No + 1, device=s.device, dtype=torch.float32)
+        L.check(lib.waldo_occ_fwd(B * T, No, L.ptr(s, name="occ_score"), L.ptr(occ), L.stream_of(s)), "occ_fwd")
+        ctx.save_for_backward(s)
+        return occ
+
+    @staticmethod
+    def backward(ctx, docc):
+        lib = L.load()
+        (s,) = ctx.saved_tensors
+        B, T, No = s.shape
+        docc = _c(docc)
+        ds = torch.empty_like(s)
+        L.check(lib.waldo_occ_bwd(B * T, No, L.ptr(s), L.ptr(docc), L.ptr(ds), L.stream_of(s)), "occ_bwd")
+        return ds
+
+
+def compute_occ(occ_score):
+    return _ComputeOcc.apply(occ_score)
+
+
+# ===================================================================================== a-5..a-8 decode_output
+@dataclass
+class DecodeSpec:
+    """Static description of one decode call (everything that is not a tensor)."""
+    H: int
+    W: int
+    Hd: int
+    Wd: int
+    Ho: int
+    Wo: int
+    num_obj: int
+    restrict_to_ctx: bool
+    use_filter: bool
+    weight_cls: bool
+    allow_ghost: bool
+    include_self: bool
+    use_disocc: bool
+    min_cls: float
+
+
+def _geom(spec: DecodeSpec, B, T, Tc, Tp, Nl, has_cls):
+    Tw = Tc if spec.restrict_to_ctx else T
+    flags = 0
+    if spec.restrict_to_ctx:
+        flags |= L.F_RESTRICT_CTX
+    if spec.use_filter:
+        flags |= L.F_FILTER
+    if spec.weight_cls:
+        flags |= L.F_WEIGHT_CLS
+    if has_cls:
+        flags |= L.F_HAS_CLS
+    if spec.restrict_to_ctx and not spec.allow_ghost:
+        flags |= L.F_IS_OBJ
+    if spec.include_self:
+        flags |= L.F_INCLUDE_SELF
+    if spec.use_disocc:
+        flags |= L.F_USE_DISOCC
+    return L.Geom(B, T, Tw, Tc, Tp, spec.num_obj, Nl, 3 + Nl, spec.H, spec.W, spec.Hd, spec.Wd, spec.Ho, spec.Wo,
+                  flags, float(spec.min_cls))
+
+
+class _Decode(torch.autograd.Function):
+    """LVD.forward(mode="decode_output") = Warper.grid_to_flow[_ctx] + Warper.input_to_output, lvd.py:141-153.
+
+    Returns (out_full (B,Tp,C+1,Hd,Wd), raw_output (B,Tc+self,Tp,C+L+disocc,Hd,Wd), flow (B,Tc,Tp,2,Hd,Wd),
+    alpha (B,Tw,L,Hd,Wd))."""
+
+    @staticmethod
+    def forward(ctx, spec, ctx_ts, pred_ts, xs_hd, ys_hd, inp, tgo, sgo, tgb, sgb, occ, obj_alpha, bg_alpha, cls):
+        lib = L.load()
+        inp_c, tgo_c, sgo_c, tgb_c, sgb_c = (_c(t.detach()) for t in (inp, tgo, sgo, tgb, sgb))
+        occ_c, oa_c, ba_c = _c(occ.detach()), _c(obj_alpha.detach()), _c(bg_alpha.detach())
+        cls_c = _c(cls.detach()) if cls is not None else None
+        B, T, Cc, Hd, Wd = inp_c.shape
+        Tc, Tp = ctx_ts.shape[1], pred_ts.shape[0]
+        Nl = Cc - 3
+        if (Hd, Wd) != (spec.Hd, spec.Wd):
+            raise RuntimeError(f"waldo_b200.decode: input is {Hd}x{Wd}, warper expects {spec.Hd}x{spec.Wd}")
+        if spec.weight_cls and cls is None:
+            raise RuntimeError("waldo_b200.decode: weight_cls needs cls (the reference fails here too, lvd.py:737)")
+        g = _geom(spec, B, T, Tc, Tp, Nl, cls is not None)
+        Lr = spec.num_obj + 1
+        dev = inp_c.device
+        ts_c = _c(ctx_ts, torch.int64).to(dev)
+        ps_c = _c(pred_ts, torch.int64).to(dev)
+        if int(ts_c.max()) >= g.Tw or int(ts_c.min()) < 0 or int(ps_c.max()) >= T or int(ps_c.min()) < 0:
+            raise RuntimeError("waldo_b200.decode: ctx_ts / pred_ts out of range")
+        self_ctx = spec.include_self and Tp == T
+        TcR, CR = Tc + (1 if self_ctx else 0), Cc + Lr + (1 if spec.use_disocc else 0)
+        f32 = dict(device=dev, dtype=torch.float32)
+        a_lo = torch.empty(B, g.Tw, Lr, spec.H, spec.W, **f32)
+        nout = spec.num_obj * Nl + spec.num_obj
+        prof_ctas = max(1, min(64, (g.Tw * spec.H * spec.W + 127) // 128))
+        prof_part = torch.empty(B, prof_ctas, nout, **f32)
+        prof_sum = torch.empty(B, nout, **f32)
+        prof_p = torch.empty(B, spec.num_obj, Nl, **f32)
+        f_lo = torch.empty(B, Tc, Tp, Lr, spec.H, spec.W, 2, **f32)
+        s_lo = torch.empty(B, Tp, spec.num_obj, spec.H, spec.W, **f32)
+        alpha = torch.empty(B, g.Tw, Lr, Hd, Wd, **f32)
+        flow = torch.empty(B, Tc, Tp, 2, Hd, Wd, **f32)
+        raw = torch.empty(B, TcR, Tp, CR, Hd, Wd, **f32)
+        out_full = torch.empty(B, Tp, Cc + 1, Hd, Wd, **f32)
+        norm = torch.empty(B, Tp, Hd, Wd, **f32)
+        a = L.DecodeFwd(g, L.ptr(inp_c, name="input"), L.ptr(tgo_c), L.ptr(sgo_c), L.ptr(tgb_c), L.ptr(sgb_c), L.ptr(occ_c),
+                        L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
+                        L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
+                        L.ptr(prof_p), L.ptr(f_lo), L.ptr(s_lo), L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full),
+                        L.ptr(norm))
+        L.check(lib.waldo_decode_fwd(C.byref(a), L.stream_of(inp_c)), "decode_fwd")
+        ctx.spec, ctx.has_cls = spec, cls is not None
+        ctx.keep = (a, inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
+                    prof_sum, prof_p, f_lo, s_lo, alpha, flow, raw, out_full, norm)
+        ctx.shapes = dict(obj_alpha=obj_alpha.shape, bg_alpha=bg_alpha.shape)
+        return out_full, raw, flow, alpha
+
+    @staticmethod
+    def backward(ctx, d_out_full, d_raw, d_flow, d_alpha):
+        lib = L.load()
+        fwd = ctx.keep[0]
+        (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c) = ctx.keep[1:10]
+        g = fwd.g
+        dev = inp_c.device
+        need = ctx.needs_input_grad[5:]   # inp, tgo, sgo, tgb, sgb, occ, obj_alpha, bg_alpha, cls
+        n_inp, n_tgo, n_sgo, n_tgb, n_sgb, n_occ, n_oa, n_ba, n_cls = need
+        n_cls = n_cls and cls_c is not None
+        z = lambda ref, on: torch.zeros_like(ref) if on else None
+        d_input, d_tgo, d_sgo, d_tgb, d_sgb = z(inp_c, n_inp), z(tgo_c, n_tgo), z(sgo_c, n_sgo), z(tgb_c, n_tgb), z(sgb_c, n_sgb)
+        d_occ, d_oa, d_ba, d_cls = z(occ_c, n_occ), z(oa_c, n_oa), z(ba_c, n_ba), z(cls_c, n_cls)
+        filt = bool(g.flags & L.F_FILTER)
+        geom = n_tgo or n_sgo or n_tgb or n_sgb
+        chain = geom or n_occ or n_oa or n_ba or n_cls or (filt and n_inp)
+        a_lo, prof_part, prof_sum, prof_p, f_lo, s_lo, alpha = ctx.keep[14:21]
+        Lr = g.No + 1
+        f32 = dict(device=dev, dtype=torch.float32)
+        d_alpha_acc = torch.zeros_like(alpha) if chain else None
+        # geometry gradients flow through all four grids together: allocate the missing ones as scratch
+        if geom:
+            d_tgo_s = d_tgo if d_tgo is not None else torch.zeros_like(tgo_c)
+            d_sgo_s = d_sgo if d_sgo is not None else torch.zeros_like(sgo_c)
+            d_tgb_s = d_tgb if d_tgb is not None else torch.zeros_like(tgb_c)
+            d_sgb_s = d_sgb if d_sgb is not None else torch.zeros_like(sgb_c)
+        else:
+            d_tgo_s = d_sgo_s = d_tgb_s = d_sgb_s = None
+        d_f_lo = torch.zeros_like(f_lo) if geom else None
+        d_a_lo = torch.zeros_like(a_lo) if chain else None
+        d_prof_p = torch.zeros_like(prof_p) if (chain and filt) else None
+        d_prof_sum = torch.zeros_like(prof_sum) if (chain and filt) else None
+        tiles = ((g.Wd + 31) // 32) * ((g.Hd + 7) // 8)
+        red_ctas = max(1, min(128, tiles))
+        groups = max(g.B * g.Tp, g.B * g.Tw)
+        occ_part = torch.empty(groups, red_ctas, Lr * Lr, **f32) if n_occ else None
+        prof_p_part = torch.empty(g.B * g.Tw, red_ctas, g.No * g.Nl, **f32) if d_prof_p is not None else None
+        cls_part = torch.empty(g.B, fwd.prof_ctas, g.No * g.Nl, **f32) if (n_cls and (g.flags & L.F_WEIGHT_CLS)) else None
+        d_cls_s = d_cls
+        if d_cls_s is None and cls_c is not None and chain and filt and not (g.flags & L.F_WEIGHT_CLS):
+            d_cls_s = None   # P = cls path: nothing to propagate unless cls needs grad
+        grads_in = [_c(t) if t is not None else None for t in (d_out_full, d_raw, d_flow, d_alpha)]
+        b = L.DecodeBwd(fwd, L.ptr(grads_in[0]), L.ptr(grads_in[1]), L.ptr(grads_in[2]), L.ptr(grads_in[3]),
+                        L.ptr(d_input), L.ptr(d_tgo_s), L.ptr(d_sgo_s), L.ptr(d_tgb_s), L.ptr(d_sgb_s), L.ptr(d_occ),
+                        L.ptr(d_oa), L.ptr(d_ba), L.ptr(d_cls_s), L.ptr(d_alpha_acc), L.ptr(d_f_lo), L.ptr(d_a_lo),
+                        L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part))
+        L.check(lib.waldo_decode_bwd(C.byref(b), L.stream_of(inp_c)), "decode_bwd")
+        if d_oa is not None:
+            d_oa = d_oa.view(ctx.shapes["obj_alpha"])
+        if d_ba is not None:
+            d_ba = d_ba.view(ctx.shapes["bg_alpha"])
+        return (None, None, None, None, None, d_input, d_tgo, d_sgo, d_tgb, d_sgb, d_occ, d_oa, d_ba, d_cls)
+
+
+def decode(spec: DecodeSpec, ctx_ts, pred_ts, xs_hd, ys_hd, inp, grid, occ, obj_alpha, bg_alpha, cls):
+    tgo, sgo, tgb, sgb = grid
+    return _Decode.apply(spec, ctx_ts, pred_ts, xs_hd, ys_hd, inp, tgo, sgo, tgb, sgb, occ, obj_alpha, bg_alpha, cls)
+
+
+# ===================================================================================== a-9 WIF fuse tail
+class _WifFuse(torch.autograd.Function):
+    """WIF.forward tail, models/nets/wif.py:50-54."""
+
+    @staticmethod
+    def forward(ctx, raw_output, unet_out, ab):
+        lib = L.load()
+        r, u = _c(raw_output.detach()), _c(unet_out.detach())
+        B, Tc, Tp, Cr, H, W = r.shape
+        if u.shape[:3] != (B, Tp, Tc) or u.shape[3] != 4 + (1 if ab else 0):
+            raise RuntimeError(f"waldo_b200.wif_fuse: unet_out shape {tuple(u.shape)} does not match raw_output {tuple(r.shape)}")
+        frame = torch.empty(B, Tp, 3, H, W, device=r.device, dtype=torch.float32)
+        a = L.WifFuseFwd(B, Tc, Tp, Cr, H * W, 1 if ab else 0, L.ptr(r, name="raw_output"), L.ptr(u, name="unet_out"), L.ptr(frame))
+        L.check(lib.waldo_wif_fuse_fwd(C.byref(a), L.stream_of(r)), "wif_fuse_fwd")
+        ctx.keep = (a, r, u)
+        return frame
+
+    @staticmethod
+    def backward(ctx, d_frame):
+        lib = L.load()
+        a, r, u = ctx.keep
+        d_frame = _c(d_frame)
+        d_raw = torch.zeros_like(r) if ctx.needs_input_grad[0] else None
+        d_u = torch.empty_like(u) if ctx.needs_input_grad[1] else None
+        b = L.WifFuseBwd(a, L.ptr(d_frame), L.ptr(d_raw), L.ptr(d_u))
+        L.check(lib.waldo_wif_fuse_bwd(C.byref(b), L.stream_of(r)), "wif_fuse_bwd")
+        return d_raw, d_u, None
+
+
+def wif_fuse(raw_output, unet_out, ab=True):
+    """raw_output (B,Tc,Tp,Cin,H,W) as produced by decode_output; unet_out (B,Tp,Tc,4|5,H,W)."""
+    return _WifFuse.apply(raw_output, unet_out, ab)

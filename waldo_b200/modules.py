@@ -1,0 +1,261 @@
+"""Drop-in replacements for the reference's hot-path modules, same constructor arguments, registered buffer
+names (state-dict compatible), method names, positional signatures and return tuples:
+
+    TPSWarp, InverseWarp      <- models/modules/warp.py:21-55, :58-174
+    Warper                    <- models/nets/lvd.py:469-870
+    compute_occ, decode_output, estimate_alpha_grid_occ   <- LVD.compute_occ :59-68, LVD.forward :126-153
+    wif_fuse                  <- WIF.forward tail, models/nets/wif.py:50-54
+
+Everything executes in the sm_100a library through waldo_b200.functional; there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+
+
+# ----------------------------------------------------------------------------- a-0 helpers (tools/utils.py:273-297)
+def get_grid(height: int, width: int) -> torch.Tensor:
+    """Pixel-centre normalised lattice (1,H,W,2), (x,y) last -- tools/utils.py:293-297."""
+    xs = torch.linspace(-1.0 + 1.0 / width, 1.0 - 1.0 / width, width)
+    ys = torch.linspace(-1.0 + 1.0 / height, 1.0 - 1.0 / height, height)
+    return torch.stack([xs[None, :].expand(height, width), ys[:, None].expand(height, width)], dim=-1)[None]
+
+
+def get_gaussian_kernel(k: int, sigma_div: float = 6) -> torch.Tensor:
+    """k x k Gaussian with sigma = k / sigma_div, normalised to sum 1 -- tools/utils.py:273-291."""
+    r = torch.arange(k, dtype=torch.float32) - (k - 1) / 2.0
+    var = (k / sigma_div) ** 2.0
+    ker = (1.0 / (2.0 * math.pi * var)) * torch.exp(-(r[None, :] ** 2 + r[:, None] ** 2) / (2 * var))
+    return ker / ker.sum()
+
+
+def kernel_distance(pts_1: torch.Tensor, pts_2: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """TPS radial basis 0.5 * d * log(d + eps) with d in expanded form -- models/modules/warp.py:15-18."""
+    d = (pts_1 ** 2).sum(-1)[:, None] + (pts_2 ** 2).sum(-1)[None, :] - 2 * pts_1 @ pts_2.t()
+    return 0.5 * d * torch.log(d + eps)
+
+
+# ----------------------------------------------------------------------------- a-1
+class TPSWarp(nn.Module):
+    """models/modules/warp.py:21-55.  Buffers: inverse_kernel, pad, tgt_grid_repr."""
+
+    def __init__(self, tgt_height, tgt_width, tgt_pts):
+        super().__init__()
+        self.tgt_shape = [tgt_height, tgt_width]
+        pts = tgt_pts.float()
+        n = pts.size(0)
+        system = torch.zeros(n + 3, n + 3)
+        system[:n, :n] = kernel_distance(pts, pts)
+        system[:n, n] = 1
+        system[n, :n] = 1
+        system[:n, n + 1:] = pts
+        system[n + 1:, :n] = pts.t()
+        lattice = get_grid(tgt_height, tgt_width).view(-1, 2)
+        repr_ = torch.cat([kernel_distance(lattice, pts), torch.ones(lattice.size(0), 1), lattice], dim=1)
+        self.register_buffer("inverse_kernel", torch.inverse(system).contiguous())
+        self.register_buffer("pad", torch.zeros(3, 2))
+        self.register_buffer("tgt_grid_repr", repr_)
+
+    def forward(self, src_pts):
+        h, w = self.tgt_shape
+        return Fn.tps_eval(src_pts, self.inverse_kernel, self.tgt_grid_repr, h, w)
+
+
+# ----------------------------------------------------------------------------- a-2
+class InverseWarp(nn.Module):
+    """models/modules/warp.py:58-174.  Buffers: kernel, src_grid, tgt_grid, x_grid, y_grid, perm."""
+
+    def __init__(self, src_height, src_width, tgt_height, tgt_width, kernel_size=3, num_perm=1):
+        super().__init__()
+        if kernel_size != 3:
+            raise NotImplementedError("waldo_b200.InverseWarp: only the reference's 3x3 fill kernel is compiled")
+        if num_perm != 1:
+            raise NotImplementedError("waldo_b200.InverseWarp: num_perm > 1 (averaged permutations, warp.py:91-111) "
+                                      "is used by no shipped script and is not built")
+        self.kernel_size = kernel_size
+        self.tgt_shape = [tgt_height, tgt_width]
+        self.num_perm = num_perm
+        self.register_buffer("kernel", get_gaussian_kernel(kernel_size).view(1, 1, kernel_size, kernel_size))
+        self.register_buffer("src_grid", get_grid(src_height, src_width))
+        self.register_buffer("tgt_grid", get_grid(tgt_height, tgt_width))
+        self.register_buffer("x_grid", torch.arange(tgt_width).view(1, -1).repeat(tgt_height, 1).view(1, -1).float())
+        self.register_buffer("y_grid", torch.arange(tgt_height).view(-1, 1).repeat(1, tgt_width).view(1, -1).float())
+        self.register_buffer("perm", torch.stack([torch.randperm(tgt_height * tgt_width) for _ in range(num_perm)]))
+
+    def forward(self, src_grid, niter=5, pad=True, erode=True, trace_box=None):
+        if not pad:
+            raise NotImplementedError("waldo_b200.InverseWarp: pad=False has no caller in the reference and is not built")
+        h, w = self.tgt_shape
+        return Fn.inverse_warp(src_grid, self.src_grid[0], self.tgt_grid[0], self.kernel.view(-1), h, w, niter, erode, trace_box)
+
+
+# ----------------------------------------------------------------------------- a-3, a-5..a-7
+class Warper(nn.Module):
+    """models/nets/lvd.py:469-870.  Same option fields, buffers (src_pts, tgt_pts, src_grid, src_grid_hd, tgt_grid,
+    tps_obj.*, invert_obj.*, tps_bg.*, invert_bg.*) and methods as the reference."""
+
+    def __init__(self, opt, repeat_border=False):
+        super().__init__()
+        src_pts = get_grid(*opt.latent_shape).view(-1, 2)
+        tgt_pts = get_grid(*opt.obj_shape).view(-1, 2)
+        self.time_dropout = opt.time_dropout
+        self.num_obj = opt.num_obj
+        self.latent_obj_size = opt.obj_shape[0] * opt.obj_shape[1]
+        self.latent_size = opt.latent_shape[0] * opt.latent_shape[1]
+        self.tgt_shape = [int(opt.obj_shape[0] * opt.patch_size * opt.scale_factor),
+                          int(opt.obj_shape[1] * opt.patch_size * opt.scale_factor)]
+        self.src_shape = [opt.dim, int(opt.dim * opt.aspect_ratio)]
+        self.src_shape_hd = [opt.load_dim, int(opt.load_dim * opt.aspect_ratio)] if opt.load_dim > 0 else self.src_shape
+        self.register_buffer("src_pts", src_pts)
+        self.register_buffer("tgt_pts", tgt_pts)
+        self.register_buffer("src_grid", get_grid(*self.src_shape))
+        self.register_buffer("src_grid_hd", get_grid(*self.src_shape_hd))
+        self.register_buffer("tgt_grid", get_grid(*self.tgt_shape))
+        self.tps_obj = TPSWarp(*self.tgt_shape, tgt_pts)
+        self.invert_obj = InverseWarp(*self.tgt_shape, *self.src_shape, num_perm=opt.num_perm_grid)
+        self.normalize_alpha = opt.normalize_alpha
+        self.use_lyt_filtering = opt.use_lyt_filtering
+        self.use_lyt_opacity = opt.use_lyt_opacity
+        self.weight_cls = opt.weight_cls
+        self.min_cls = opt.min_cls
+        self.include_self = opt.include_self
+        self.fast = opt.load_dim == 0
+        self.scale_hd = opt.load_dim / opt.dim if opt.load_dim > 0 else 1
+        self.tps_bg = TPSWarp(*self.src_shape, src_pts)
+        self.invert_bg = InverseWarp(*self.src_shape, *self.src_shape, num_perm=opt.num_perm_grid)
+        self.no_filter = opt.no_filter
+        self.allow_ghost = opt.allow_ghost
+        self.use_disocc = getattr(opt, "use_disocc", False)
+        self._fused = None   # results of the last fused decode, handed out by input_to_output
+
+    # -- a-3 ---------------------------------------------------------------------------------------------
+    def forward(self, obj_pose, bg_pose, invert=True):
+        """lvd.py:855-870 -> (tgt_grid_obj, src_grid_obj, tgt_grid_bg, src_grid_bg)."""
+        B, T, No = obj_pose.shape[:3]
+        Lo, Lb = self.latent_obj_size, self.latent_size
+        tgo = self.tps_obj(obj_pose.reshape(B * T * No, Lo, 2))
+        sgo = self.invert_obj(tgo) if invert else None
+        tgb = self.tps_bg(bg_pose.reshape(B * T, Lb, 2))
+        sgb = self.invert_bg(tgb, erode=False) if invert else None
+        tgo = tgo.view(B, T, No, *tgo.shape[1:])
+        tgb = tgb.view(B, T, *tgb.shape[1:])
+        if invert:
+            sgo = sgo.view(B, T, No, *sgo.shape[1:])
+            sgb = sgb.view(B, T, *sgb.shape[1:])
+        return tgo, sgo, tgb, sgb
+
+    # -- a-6 + a-7 fused ---------------------------------------------------------------------------------
+    def _spec(self, restrict_to_ctx: bool) -> Fn.DecodeSpec:
+        H, W = self.src_shape
+        Hd, Wd = self.src_shape_hd
+        Ho, Wo = self.tgt_shape
+        return Fn.DecodeSpec(H=H, W=W, Hd=Hd, Wd=Wd, Ho=Ho, Wo=Wo, num_obj=self.num_obj, restrict_to_ctx=restrict_to_ctx,
+                             use_filter=True if restrict_to_ctx else not self.no_filter, weight_cls=bool(self.weight_cls),
+                             allow_ghost=bool(self.allow_ghost), include_self=bool(self.include_self),
+                             use_disocc=bool(self.use_disocc), min_cls=float(self.min_cls))
+
+    def _decode(self, restrict, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts):
+        spec = self._spec(restrict)
+        xs = self.src_grid_hd[0, 0, :, 0].contiguous()
+        ys = self.src_grid_hd[0, :, 0, 1].contiguous()
+        out_full, raw, flow, alpha = Fn.decode(spec, ctx_ts, pred_ts, xs, ys, input, grid, occ, obj_alpha, bg_alpha, cls)
+        C = input.size(2)
+        Lr = self.num_obj + 1
+        Tc = ctx_ts.size(1)
+        alpha_ctx = raw[:, :Tc, :, C:C + Lr]                       # a channel-slice view of raw_output
+        disocc = raw[:, :Tc, :, C + Lr:C + Lr + 1] if spec.use_disocc else None
+        self._fused = (alpha_ctx, flow, out_full, raw, spec.use_disocc)
+        alpha_unflt = alpha if self.fast else None                  # lvd.py:702-705 / :825-828
+        return flow, alpha_unflt, alpha, alpha_ctx, disocc
+
+    def grid_to_flow_ctx(self, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts):
+        """lvd.py:707-828.  Returns (flow, alpha_unflt, alpha, alpha_ctx, disocc).  `disocc` is returned only when
+        opt.use_disocc (the only case in which the reference's caller reads it, lvd.py:148-151); else None."""
+        return self._decode(True, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
+
+    def grid_to_flow(self, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts):
+        """lvd.py:602-705."""
+        return self._decode(False, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
+
+    def input_to_output(self, input, alpha, flow, ctx_ts, eps=1e-6):
+        """lvd.py:830-853 -> (output (B,Tp,C+1,Hd,Wd), raw_output).  The warp + context fusion was already done by the
+        fused kernel of grid_to_flow[_ctx]; this hands its results out.  The raw_output returned here already holds the
+        disocc channel when opt.use_disocc (decode_output below accounts for that)."""
+        f = self._fused
+        if f is None or f[0] is not alpha or f[1] is not flow:
+            raise NotImplementedError(
+                "waldo_b200.Warper.input_to_output must be called with the (alpha_ctx, flow) tensors returned by the "
+                "immediately preceding grid_to_flow[_ctx] call, as LVD.forward does (lvd.py:143-146): the warp of the "
+                "context frames is fused into that kernel.")
+        self._fused = None
+        return f[2], f[3]
+
+
+# ----------------------------------------------------------------------------- a-4, a-8
+def compute_occ(occ_score, eps=1e-6):
+    """LVD.compute_occ, lvd.py:59-68."""
+    if eps != 1e-6:
+        raise NotImplementedError("waldo_b200.compute_occ: eps is compiled as 1e-6 (the reference default)")
+    return Fn.compute_occ(occ_score)
+
+
+def decode_output(warper: Warper, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts,
+                  restrict_to_ctx: bool, use_disocc: Optional[bool] = None, include_self: Optional[bool] = None):
+    """LVD.forward(mode="decode_output"), lvd.py:141-153 -> the reference's 7-tuple
+    (output, flow, alpha_unflt, alpha, raw_alpha, raw_output, alpha_ctx)."""
+    if use_disocc is not None:
+        warper.use_disocc = use_disocc
+    if restrict_to_ctx:
+        flow, alpha_unflt, alpha, alpha_ctx, _ = warper.grid_to_flow_ctx(input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
+    else:
+        flow, alpha_unflt, alpha, alpha_ctx, _ = warper.grid_to_flow(input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
+    output, raw_output = warper.input_to_output(input, alpha_ctx, flow, ctx_ts)
+    raw_alpha = output[:, :, -1:]
+    output = output[:, :, :-1]
+    return output, flow, alpha_unflt, alpha, raw_alpha, raw_output, alpha_ctx
+
+
+def alpha_masks(opt):
+    """The constant buffers LVD.__init__ builds at lvd.py:25-44: (obj_alpha_mask (1,1,1,Ho,Wo) or 1, bg_alpha (1,1,H,W))."""
+    Ho = int(opt.obj_shape[0] * opt.patch_size * opt.scale_factor)
+    Wo = int(opt.obj_shape[1] * opt.patch_size * opt.scale_factor)
+    mask = 1
+    if opt.pad_obj_alpha > 0:
+        p = int(opt.pad_obj_alpha * opt.scale_factor)
+        mask = torch.ones(Ho, Wo)
+        mask[:p] = 0
+        mask[-p:] = 0
+        mask[:, :p] = 0
+        mask[:, -p:] = 0
+        mask = mask.view(1, 1, 1, Ho, Wo)
+    bg = torch.ones(1, 1, opt.dim, int(opt.dim * opt.aspect_ratio))
+    if opt.pad_bg_alpha > 0:
+        p = int(opt.pad_bg_alpha * opt.scale_factor)
+        bg[:, :, :p] = -1
+        bg[:, :, -p:] = -1
+        bg[:, :, :, :p] = -1
+        bg[:, :, :, -p:] = -1
+    return mask, bg
+
+
+def estimate_alpha_grid_occ(warper: Warper, obj_alpha, obj_alpha_mask, bg_alpha_buf, obj_pose, bg_pose, occ_score):
+    """LVD.forward(mode="estimate_alpha_grid_occ") after the decoder, lvd.py:127-135
+    -> (occ, obj_alpha, bg_alpha, grid)."""
+    bg_alpha = bg_alpha_buf.expand(obj_alpha.size(0), -1, -1, -1)
+    obj_alpha = obj_alpha_mask * obj_alpha + (1 - obj_alpha_mask) * (-1.0)
+    grid = warper(obj_pose, bg_pose)
+    occ = compute_occ(occ_score)
+    return occ, obj_alpha, bg_alpha, grid
+
+
+# ----------------------------------------------------------------------------- a-9
+def wif_fuse(vid, unet_out, ab=True):
+    """Tail of WIF.forward (wif.py:50-54).  vid = raw_output (B,Tc,Tp,Cin,H,W) exactly as WIF.forward receives it;
+    unet_out = UNet output reshaped (B,Tp,Tc,5|4,H,W).  Returns (B,Tp,3,H,W)."""
+    return Fn.wif_fuse(vid, unet_out, ab)
