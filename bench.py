@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the WALDO warp+composite hot path (BASELINE.json metric: warped+composited frames/s, fwd+bwd, 512x1024).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl waldo|reference] [--workload city_train|city_rollout|kitti_rollout]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  control points -> TPS grids -> inverse warps -> occlusion matrix -> context alpha -> fused warp+composite (forward),
+  then the whole backward down to input / obj_alpha / obj_pose / bg_pose / occ_score / cls gradients (city_train), or
+  forward only (the *_rollout workloads).
+Default workload = BASELINE.json configs[1]: Cityscapes shape 512x1024, batch 8 per GPU, 4 contexts -> 1 future frame,
+fp32, fwd+bwd.  Under torchrun every rank runs the same per-GPU batch (weak scaling, no data-path collective; the
+training workload adds the DDP-equivalent flat gradient all-reduce of a WIF-sized buffer).
+
+`--impl reference` times the reference's algorithm on the host cores (the oracle port of oracle/waldo_oracle.py: the
+reference itself is Python and cannot travel to the GPU box), one frame per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WIF_GRAD_ELEMS = 14_160_000   # WIF parameters: the per-step DDP all-reduce payload of train_wif.sh
+
+
+def workload_cfg(name):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import waldo_oracle as wo
+    if name == "city_train":
+        return wo.PathConfig(), dict(B=8, T=5, Tc=4, backward=True, label="cityscapes 512x1024 fwd+bwd B=8/GPU Tc=4->Tp=1")
+    if name == "city_rollout":
+        return wo.PathConfig(), dict(B=1, T=14, Tc=4, backward=False, label="cityscapes 512x1024 rollout fwd B=1/GPU Tc=4->Tp=10")
+    if name == "kitti_rollout":
+        cfg = wo.PathConfig(dim=128, load_dim=256, aspect_ratio=3.25, latent_shape=(8, 26), num_lyt=19)
+        return cfg, dict(B=1, T=9, Tc=4, backward=False, label="kitti 256x832 rollout fwd B=1/GPU Tc=4->Tp=5")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def alg_bytes(cfg, B, Tc, Tp, backward):
+    """Algorithmic HBM bytes of one step (SURVEY.md §8d / BASELINE.md §3), fp32."""
+    Hd, Wd = cfg.hd_shape
+    px, s = Hd * Wd, 4
+    C, L, Nl = 3 + cfg.num_lyt, cfg.num_obj + 1, cfg.num_lyt
+    fwd = px * s * (B * Tc * Tp * (C + L) + B * Tc * Tp * ((C + L) + 2 + 1) + B * Tp * (C + 1) + B * Tc * (Nl + L))
+    bwd = px * s * (B * Tc * Tp * ((C + L) + 2 + C + L) + B * Tp * (C + 1) + B * Tc * (C + L))
+    return fwd, (bwd if backward else 0)
+
+
+def kernel_bytes(cfg, B, Tc, Tp):
+    """Algorithmic bytes per launch of the two fused HD kernels (DESIGN.md "kernels")."""
+    Hd, Wd = cfg.hd_shape
+    px, s = Hd * Wd, 4
+    C, L = 3 + cfg.num_lyt, cfg.num_obj + 1
+    fwd = px * s * (B * Tc * Tp * (C + L) + B * Tc * Tp * ((C + L) + 2) + B * Tp * (C + 1 + 1))
+    bwd = px * s * (B * Tc * Tp * ((C + L) + 2 + C + L) + B * Tp * (2 * (C + 1) + 1) + B * Tc * (C + L))
+    return fwd, bwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(cfg, B, T, Tc, seed):
+    import waldo_oracle as wo
+    d = wo.synth_inputs(cfg, B, T, Tc, seed=seed)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_step(wo, st, d, backward):
+    lv = {k: d[k].clone().requires_grad_(backward) for k in ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")}
+    occ, oa, ba, grid = wo.estimate_alpha_grid_occ(st, lv["obj_alpha_raw"], lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
+    with torch.set_grad_enabled(backward):
+        out = wo.decode_output(st, lv["input"], grid, occ, oa, ba, lv["cls"], d["ctx_ts"], d["pred_ts"])
+        loss = out[0].abs().mean() + out[1].abs().mean()
+    if backward:
+        loss.backward()
+    return float(loss)
+
+
+def cpu_baseline(cfg, spec, steps=1, warmup=0):
+    """The oracle port on the host cores, on a bounded sample of the workload: ONE video (B=1) per step."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    import waldo_oracle as wo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = wo.make_state(cfg)
+    d = make_inputs(cfg, 1, spec["T"], spec["Tc"], seed=0)
+    frames = spec["T"] - spec["Tc"]
+    for _ in range(warmup):
+        oracle_step(wo, st, d, spec["backward"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(wo, st, d, spec["backward"])
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"B=1 of the workload ({frames} future frame(s), {'fwd+bwd' if spec['backward'] else 'fwd'}), "
+                      f"{steps} step(s) of {dt:.1f} s, torch {torch.__version__} CPU, oracle/waldo_oracle.py"}, dt
+
+
+def run_reference(args, cfg, spec, rank, world):
+    if rank != 0:
+        return
+    budget_s = 170.0
+    base, dt = cpu_baseline(cfg, spec, steps=1, warmup=0)   # doubles as the first warm-up step
+    steps = max(1, min(args.steps, int(budget_s / dt) - min(args.warmup, 1)))
+    warm = 0 if steps + 1 > budget_s / dt else min(args.warmup, 1)
+    base, dt = cpu_baseline(cfg, spec, steps=steps, warmup=warm)
+    line = {"impl": "reference", "metric": "warped+composited frames/s", "value": base["value"], "unit": "frames/s",
+            "n_gpus": world, "steps": steps, "steps_requested": args.steps, "warmup": warm + 1, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": spec["label"], "sample": "one video (B=1) per step on the host cores"},
+            "cpu_baseline": base, "gpu_launches": 0,
+            "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="waldo", choices=["waldo", "reference"])
+    ap.add_argument("--workload", default="city_train")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    cfg, spec = workload_cfg(args.workload)
+    if args.batch:
+        spec["B"] = args.batch
+    if args.impl == "reference":
+        run_reference(args, cfg, spec, rank, world)
+        return
+
+    import torch.distributed as dist
+    import waldo_b200 as wb
+    from waldo_b200 import _lib, functional as Fn
+    from tests.parity import make_opt
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    B, T, Tc, backward = spec["B"], spec["T"], spec["Tc"], spec["backward"]
+    Tp = T - Tc
+    opt = make_opt(cfg)
+    warper = wb.Warper(opt).to(dev)
+    om, bg = wb.alpha_masks(opt)
+    om, bg = om.to(dev), bg.to(dev)
+    host = make_inputs(cfg, B, T, Tc, seed=rank)
+    keys = ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")
+    pinned = {k: host[k].pin_memory() for k in keys}
+    ctx_ts, pred_ts = host["ctx_ts"].contiguous().to(dev), host["pred_ts"].to(dev)
+    resident = {k: pinned[k].to(dev) for k in keys}
+    grad_buf = torch.zeros(WIF_GRAD_ELEMS, device=dev) if (world > 1 and backward) else None
+    loss_host = torch.zeros(1).pin_memory()
+
+    # upstream gradients as a downstream consumer (WIF / losses) would supply them: fixed seeded tensors, so that no
+    # loss kernel of torch sits inside the timed region and the backward reads d output, d flow and d raw_output
+    C, L = 3 + cfg.num_lyt, cfg.num_obj + 1
+    Hd, Wd = cfg.hd_shape
+    if backward:
+        gen = torch.Generator(device=dev).manual_seed(1 + rank)
+        g_output = torch.randn(B, Tp, C, Hd, Wd, device=dev, generator=gen)
+        g_flow = torch.randn(B, Tc, Tp, 2, Hd, Wd, device=dev, generator=gen)
+        g_raw = torch.randn(B, Tc, Tp, C + L, Hd, Wd, device=dev, generator=gen)
+
+    def step(src):
+        lv = {k: src[k].detach().requires_grad_(backward) for k in keys}
+        with torch.set_grad_enabled(backward):
+            occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, lv["obj_alpha_raw"], om, bg, lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
+            out = wb.decode_output(warper, lv["input"], grid, occ, oa, ba, lv["cls"], ctx_ts, pred_ts, cfg.restrict_to_ctx)
+        if backward:
+            torch.autograd.backward([out[0], out[1], out[5]], [g_output, g_flow, g_raw])
+            if grad_buf is not None:
+                dist.all_reduce(grad_buf)
+        return out[0].detach()[:, :, :3].mean()   # the step's metric (mean predicted RGB), read back in the e2e leg
+
+    def e2e_step():
+        src = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
+        metric = step(src)
+        loss_host.copy_(metric.reshape(1), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    # ---- device-resident timing, with the dominant kernels bracketed by events inside the timed region
+    Fn.PROFILE = {"decode_fwd": [], "decode_bwd": []}
+    launches0 = lib.waldo_launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ms_step = timed(lambda: step(resident), args.steps)
+    launches = lib.waldo_launch_count() - launches0
+    prof = {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in Fn.PROFILE.items()}
+    Fn.PROFILE = None
+    # ---- end to end: pinned host -> device copies and the loss read-back inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
+        e2e = {"value": world * B * Tp / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+
+    if rank == 0:
+        frames = world * B * Tp
+        fwd_b, bwd_b = alg_bytes(cfg, B, Tc, Tp, backward)
+        kf, kb = kernel_bytes(cfg, B, Tc, Tp)
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+        except Exception:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            pass
+        kern = {"k_warp_composite_fwd": (prof.get("decode_fwd", 0.0), kf), "k_warp_composite_bwd": (prof.get("decode_bwd", 0.0), kb)}
+        dom = max(kern, key=lambda k: kern[k][0]) if backward else "k_warp_composite_fwd"
+        dms, dbytes = kern[dom]
+        achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
+        line = {
+            "metric": "warped+composited frames/s", "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": spec["label"], "per_gpu_batch": B, "contexts": Tc, "future_frames": Tp,
+                       "layers": cfg.num_obj + 1, "channels": 3 + cfg.num_lyt, "l2": "inputs larger than L2 (1.9 GB/step), no flush needed",
+                       "parallelism": f"dp{world} batch-sharded" + (", flat fp32 all-reduce of 56.6 MB per step" if grad_buf is not None else "")},
+            "clocks": clocks.summary(), "gpu_launches": launches,
+            "hbm_frac_step": ((fwd_b + bwd_b) / (ms_step * 1e-3) / 1e9) / peak,
+            "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic.get(dom), "ms_per_launch": dms, "alg_bytes_per_launch": dbytes, "peak_source": peak_src,
+                         "other": {k: {"ms_per_launch": v[0], "alg_bytes_per_launch": v[1],
+                                       "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None} for k, v in kern.items() if k != dom}},
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_baseline(cfg, spec, steps=1, warmup=0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,8 @@ int waldo_abi_version(void);
 /* 1 when the library holds sm_100a device code (the shipped build), 0 for the CPU logic-emulation
  * build that only the unit tests compile (tests/emu). */
 int waldo_has_device_code(void);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
+long long waldo_launch_count(void);
 
 /* ------------------------------------------------------------------ a-1  TPSWarp.forward
  * models/modules/warp.py:49-55.  grid[n,p,:] = tgt_grid_repr[p,:] @ (inverse_kernel @ [pts[n];0_3x2]).
@@ -168,6 +170,7 @@ typedef struct {
   float* raw_output;          /* (B, Tc+self, Tp, C+L+disocc, Hd, Wd)                 lvd.py:846,151; alpha_ctx = channels C..C+L-1 */
   float* out_full;            /* (B, Tp, C+1, Hd, Wd): output | raw_alpha             lvd.py:851,147,152 */
   float* norm;                /* (B, Tp, Hd, Wd) sum_tc(score+eps), saved for backward, may be NULL */
+  int stages;                 /* 0 = everything; else bit 0 = low-res + context-alpha kernels (B1-B5), bit 1 = fused HD kernel */
 } waldo_decode_fwd_t;
 int waldo_decode_fwd(const waldo_decode_fwd_t*, waldo_stream_t);
 
@@ -199,6 +202,7 @@ typedef struct {
   float* occ_part;            /* (max(B*Tp, B*Tw), red_ctas, L*L) */
   float* prof_p_part;         /* (B*Tw, red_ctas, No*Nl) */
   float* cls_part;            /* (B, prof_ctas, No*Nl) */
+  int stages;                 /* 0 = everything; else bit 0 = fused HD backward kernel, bit 1 = the rest of the chain */
 } waldo_decode_bwd_t;
 int waldo_decode_bwd(const waldo_decode_bwd_t*, waldo_stream_t);
 

@@ -1,0 +1,348 @@
+"""Parity checks shared by the CPU (kernel-logic emulation) and GPU (the real sm_100a library) test files.
+
+Each check feeds identical inputs to the product path (waldo_b200, through the C ABI) and to the oracle
+(oracle/waldo_oracle.py, fp32 and its fp64 twin) / the committed reference outputs (tests/golden), using the tiers of
+SURVEY.md §8(d):
+  T0 stage-local, T1 chained from an identical `grid`, T2 end-to-end from control points (statistical).
+Tolerances (stated once, used everywhere):
+  * index / threshold maps: bit-exact;
+  * fp32 forward: max-abs <= 1e-5 wherever the reference's own fp32-vs-fp64 floor is below that, else fp64-arbitrated:
+        max|k - f64| <= 2 * max|ref32 - f64| + 1e-6;
+  * fp32 gradients: ||g - g_ref||_inf / ||g_ref||_inf <= 1e-4, or fp64-arbitrated the same way.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import waldo_oracle as wo  # noqa: E402
+import waldo_b200 as wb  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = ["city_x4", "kitti_x2", "train_lo", "cls_plain"]
+OUT_NAMES = ["output", "flow", "alpha_unflt", "alpha", "raw_alpha", "raw_output", "alpha_ctx"]
+
+FWD_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    B, T, Tc, smooth = meta.pop("B"), meta.pop("T"), meta.pop("Tc"), meta.pop("smooth")
+    cfg = wo.PathConfig(**meta)
+    return cfg, (B, T, Tc), {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+
+
+def make_opt(cfg: wo.PathConfig):
+    """The option namespace the reference's Warper reads (lvd.py:470-499), filled from a PathConfig."""
+    return types.SimpleNamespace(
+        latent_shape=list(cfg.latent_shape), obj_shape=list(cfg.obj_shape), time_dropout=False, num_obj=cfg.num_obj,
+        patch_size=cfg.patch_size, scale_factor=cfg.scale_factor, dim=cfg.dim, aspect_ratio=cfg.aspect_ratio,
+        load_dim=cfg.load_dim, num_perm_grid=1, normalize_alpha=False, use_lyt_filtering=True, use_lyt_opacity=True,
+        weight_cls=cfg.weight_cls, min_cls=cfg.min_cls, include_self=cfg.include_self, no_filter=cfg.no_filter,
+        allow_ghost=cfg.allow_ghost, use_disocc=cfg.use_disocc, pad_obj_alpha=cfg.pad_obj_alpha,
+        pad_bg_alpha=cfg.pad_bg_alpha)
+
+
+def arbitrated(k, ref32, f64, tol, what):
+    """max|k-ref32| <= tol, or k is as close to the fp64 twin as the fp32 reference itself is."""
+    k, ref32, f64 = k.detach().cpu().double(), ref32.detach().cpu().double(), f64.detach().cpu().double()
+    direct = float((k - ref32).abs().max())
+    if direct <= tol:
+        return
+    ek, er = float((k - f64).abs().max()), float((ref32 - f64).abs().max())
+    assert ek <= 2 * er + 1e-6, f"{what}: |k-ref32|={direct:.3e} > {tol:.0e} and |k-f64|={ek:.3e} > 2*|ref32-f64|={er:.3e}"
+
+
+def grad_close(g, g32, g64, what, tol=GRAD_TOL):
+    g, g32, g64 = g.detach().cpu().double(), g32.detach().cpu().double(), g64.detach().cpu().double()
+    scale = float(g64.abs().max())
+    if scale == 0:
+        assert float(g.abs().max()) == 0, f"{what}: reference gradient is zero, kernel's is not"
+        return
+    direct = float((g - g32).abs().max()) / scale
+    if direct <= tol:
+        return
+    ek, er = float((g - g64).abs().max()) / scale, float((g32 - g64).abs().max()) / scale
+    assert ek <= 2 * er + 1e-6, f"{what}: rel err vs ref32 {direct:.3e} > {tol:.0e}; vs f64 {ek:.3e} > 2*ref floor {er:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ stage A
+def check_tps(dev, case):
+    """a-1 TPSWarp.forward + backward (warp.py:49-55): fp64-arbitrated (bg system cond ~1e4)."""
+    cfg, (B, T, Tc), z = load_case(case)
+    warper = wb.Warper(make_opt(cfg)).to(dev)
+    st32, st64 = wo.make_state(cfg), wo.make_state(cfg, torch.float64)
+    for which, tps, basis32, basis64, pts in (
+            ("obj", warper.tps_obj, st32.tps_obj, st64.tps_obj, z["in_obj_pose"].reshape(-1, z["in_obj_pose"].shape[-2], 2)),
+            ("bg", warper.tps_bg, st32.tps_bg, st64.tps_bg, z["in_bg_pose"].reshape(-1, z["in_bg_pose"].shape[-2], 2))):
+        p = pts.clone().to(dev).requires_grad_(True)
+        out = tps(p)
+        p32 = pts.clone().requires_grad_(True)
+        p64 = pts.double().clone().requires_grad_(True)
+        o32, o64 = wo.tps_eval(basis32, p32), wo.tps_eval(basis64, p64)
+        arbitrated(out, o32, o64, FWD_TOL, f"tps_{which}")
+        # never worse than the reference's own fp32 error (+1e-6): SURVEY.md §8d
+        assert float((out.detach().cpu().double() - o64).abs().max()) <= float((o32.double() - o64).abs().max()) + 1e-6
+        w = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+        (out * w.to(dev)).sum().backward()
+        (o32 * w).sum().backward()
+        (o64 * w.double()).sum().backward()
+        grad_close(p.grad, p32.grad, p64.grad, f"tps_{which} d pts")
+    # buffers are the reference's (state-dict compatible)
+    assert torch.equal(warper.tps_bg.inverse_kernel.cpu(), st32.tps_bg.inverse_kernel)
+    assert torch.equal(warper.tps_obj.tgt_grid_repr.cpu(), st32.tps_obj.tgt_grid_repr)
+
+
+def check_inverse_warp(dev, case):
+    """a-2 InverseWarp.forward + backward (warp.py:71-174) fed the REFERENCE's tgt_grid: index maps bit-exact."""
+    cfg, (B, T, Tc), z = load_case(case)
+    warper = wb.Warper(make_opt(cfg)).to(dev)
+    H, W = cfg.lo_shape
+    for which, mod, key, erode in (("obj", warper.invert_obj, "tgt_grid_obj", True), ("bg", warper.invert_bg, "tgt_grid_bg", False)):
+        fwd = z[key].reshape(-1, *z[key].shape[-3:])
+        x = fwd.clone().to(dev).requires_grad_(True)
+        box = []
+        out = mod(x, erode=erode, trace_box=box)
+        tr = box[0]
+        x32 = fwd.clone().requires_grad_(True)
+        ref = wo.inverse_warp(x32, (H, W), erode=erode, trace=True)
+        n, P = fwd.shape[0], H * W
+        # rule (1): landing cells, hit mask, winners, known mask -- bit exact
+        assert torch.equal(tr.field.cpu().long(), ref.field), f"{which}: field differs"
+        win = tr.winner.cpu().long()
+        win = torch.where(win == 2 ** 31 - 1, torch.full_like(win, P), win)
+        assert torch.equal(win, ref.winner), f"{which}: winners differ"
+        m = 6
+        known = ((tr.level != 255) & (tr.eroded == 0))[:, m:-m, m:-m].cpu()
+        assert torch.equal(known, ref.known), f"{which}: known mask differs"
+        assert torch.equal((tr.level[:, m:-m, m:-m] == 0).cpu(), ref.hit), f"{which}: hit mask differs"
+        # rule (2): values
+        golden = z["src_grid_" + which].reshape(out.shape)
+        assert float((out.detach().cpu() - ref.grid).abs().max()) <= FWD_TOL
+        assert float((out.detach().cpu() - golden).abs().max()) <= FWD_TOL, f"{which}: differs from the reference's output"
+        # the hit/known masks do not depend on the tie rule: compare with the UNPATCHED reference too
+        unp = z["src_grid_" + which + "_unpatched"].reshape(out.shape)
+        sentinel = unp[..., 0] > 1.5
+        assert torch.equal(sentinel, ~known), f"{which}: known mask differs from the unpatched reference"
+        # backward (values only)
+        w = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+        (out * w.to(dev)).sum().backward()
+        (ref.grid * w).sum().backward()
+        x64 = fwd.double().clone().requires_grad_(True)
+        (wo.inverse_warp(x64, (H, W), erode=erode) * w.double()).sum().backward()
+        grad_close(x.grad, x32.grad, x64.grad, f"inverse_warp_{which} d src_grid")
+
+
+def check_occ(dev, case):
+    """a-4 LVD.compute_occ (lvd.py:59-68)."""
+    cfg, _, z = load_case(case)
+    s = z["in_occ_score"].clone().to(dev).requires_grad_(True)
+    occ = wb.compute_occ(s)
+    assert float((occ.detach().cpu() - z["occ"]).abs().max()) <= 1e-6
+    s32 = z["in_occ_score"].clone().requires_grad_(True)
+    s64 = z["in_occ_score"].double().clone().requires_grad_(True)
+    w = torch.randn(occ.shape, generator=torch.Generator().manual_seed(7))
+    (occ * w.to(dev)).sum().backward()
+    (wo.compute_occ(s32) * w).sum().backward()
+    (wo.compute_occ(s64) * w.double()).sum().backward()
+    grad_close(s.grad, s32.grad, s64.grad, "compute_occ d occ_score")
+
+
+# ------------------------------------------------------------------------------------------------ decode (T1)
+LEAF_KEYS = dict(input="in_input", tgo="tgt_grid_obj", sgo="src_grid_obj", tgb="tgt_grid_bg", sgb="src_grid_bg",
+                 occ="occ", oar="in_obj_alpha_raw", cls="in_cls")
+
+
+def oracle_decode(cfg, z, dtype, with_grad=True):
+    st = wo.make_state(cfg, dtype)
+    lv = {k: z[k2].to(dtype).clone().requires_grad_(with_grad) for k, k2 in LEAF_KEYS.items()}
+    om, bg = wo.alpha_masks(cfg, dtype)
+    oa = om * lv["oar"] + (1 - om) * (-1.0)
+    ba = bg.expand(oa.shape[0], -1, -1, -1)
+    out = wo.decode_output(st, lv["input"], (lv["tgo"], lv["sgo"], lv["tgb"], lv["sgb"]), lv["occ"], oa, ba, lv["cls"],
+                           z["in_ctx_ts"], z["in_pred_ts"])
+    if with_grad:
+        loss = 0
+        for n, o in zip(OUT_NAMES, out):
+            if o is not None and "proj_" + n in z:
+                loss = loss + (o * z["proj_" + n].to(dtype)).sum()
+        loss.backward()
+    return out, {k: v.grad for k, v in lv.items()}
+
+
+def kernel_decode(dev, cfg, z, with_grad=True):
+    opt = make_opt(cfg)
+    warper = wb.Warper(opt).to(dev)
+    lv = {k: z[k2].clone().to(dev).requires_grad_(with_grad) for k, k2 in LEAF_KEYS.items()}
+    om, bg = wb.alpha_masks(opt)
+    om = om.to(dev) if torch.is_tensor(om) else om
+    oa = om * lv["oar"] + (1 - om) * (-1.0)
+    ba = bg.to(dev).expand(oa.shape[0], -1, -1, -1)
+    out = wb.decode_output(warper, lv["input"], (lv["tgo"], lv["sgo"], lv["tgb"], lv["sgb"]), lv["occ"], oa, ba, lv["cls"],
+                           z["in_ctx_ts"].to(dev), z["in_pred_ts"].to(dev), cfg.restrict_to_ctx)
+    if with_grad:
+        loss = 0
+        for n, o in zip(OUT_NAMES, out):
+            if o is not None and "proj_" + n in z:
+                loss = loss + (o * z["proj_" + n].to(dev)).sum()
+        loss.backward()
+    return out, {k: v.grad for k, v in lv.items()}
+
+
+def check_decode(dev, case):
+    """a-5..a-8 decode_output (lvd.py:141-153) from the REFERENCE's grid tuple (tier T1): forward vs the committed
+    reference outputs and the oracle, gradients vs oracle autograd; fp64-arbitrated where the reference's own floor is
+    above the tolerance; layer-assignment argmax maps bit-exact."""
+    cfg, _, z = load_case(case)
+    o32, g32 = oracle_decode(cfg, z, torch.float32)
+    o64, g64 = oracle_decode(cfg, z, torch.float64)
+    out, g = kernel_decode(dev, cfg, z)
+    for n, o, a, b in zip(OUT_NAMES, out, o32, o64):
+        if a is None:
+            assert o is None, f"{n} must be None (lvd.py:825-828)"
+            continue
+        assert tuple(o.shape) == tuple(a.shape), f"{n}: shape {tuple(o.shape)} vs reference {tuple(a.shape)}"
+        assert tuple(o.shape) == tuple(z[n].shape)
+        arbitrated(o, z[n], b, FWD_TOL, f"{case}/{n} (vs reference fixture)")
+        arbitrated(o, a, b, FWD_TOL, f"{case}/{n} (vs oracle)")
+    # rule (1): layer assignment (logger.py:172 `alpha.max(dim=-3)[1]`) bit-exact wherever the reference's own top-2
+    # margin exceeds its fp32 noise floor
+    for n in ("alpha", "alpha_ctx"):
+        i = OUT_NAMES.index(n)
+        k, r = out[i].detach().cpu(), z[n]
+        top2 = r.topk(2, dim=-3)[0]
+        safe = (top2.select(-3, 0) - top2.select(-3, 1)) > 1e-4
+        assert torch.equal(k.argmax(dim=-3)[safe], r.argmax(dim=-3)[safe]), f"{n}: layer argmax differs"
+    for kname in LEAF_KEYS:
+        grad_close(g[kname], g32[kname], g64[kname], f"{case}/d {kname}")
+
+
+def check_end_to_end(dev, case):
+    """Tier T2: control points -> grids -> decode, statistical agreement with the reference's outputs, plus gradients
+    reaching every leaf (obj_pose, bg_pose, occ_score, obj_alpha, cls, input) through the whole chain."""
+    cfg, _, z = load_case(case)
+    opt = make_opt(cfg)
+    warper = wb.Warper(opt).to(dev)
+    lv = {k: z["in_" + k].clone().to(dev).requires_grad_(True) for k in ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")}
+    om, bg = wb.alpha_masks(opt)
+    om = om.to(dev) if torch.is_tensor(om) else om
+    occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, lv["obj_alpha_raw"], om, bg.to(dev), lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
+    out = wb.decode_output(warper, lv["input"], grid, occ, oa, ba, lv["cls"], z["in_ctx_ts"].to(dev), z["in_pred_ts"].to(dev), cfg.restrict_to_ctx)
+    loss = 0
+    for n, o in zip(OUT_NAMES, out):
+        if o is None:
+            continue
+        err = (o.detach().cpu() - z[n]).abs()
+        # the reference's own fp32-vs-fp64 mean discrepancy end to end is 2.5e-3 on raw_output
+        assert float(err.mean()) <= 2.5e-3, f"{case}/{n}: mean abs err {float(err.mean()):.3e}"
+        if "proj_" + n in z:
+            loss = loss + (o * z["proj_" + n].to(dev)).sum()
+    assert abs(float(loss) - float(z["loss"])) <= 1e-3 * max(1.0, abs(float(z["loss"])))
+    loss.backward()
+    for k, v in lv.items():
+        gref = z["grad_" + k]
+        scale = float(gref.abs().max())
+        rel = float((v.grad.cpu() - gref).abs().max()) / max(scale, 1e-30)
+        # chained through the discontinuous inverse warp and the cond~1e4 TPS system: statistical bound only
+        assert rel <= 5e-2, f"{case}/d {k}: rel err {rel:.3e}"
+        assert float(v.grad.abs().max()) > 0 or scale == 0
+
+
+def check_wif(dev, case):
+    """a-9 WIF.forward tail (wif.py:50-54) on the reference's raw_output and a seeded UNet output."""
+    cfg, _, z = load_case(case)
+    raw = z["raw_output"].clone().to(dev).requires_grad_(True)
+    u = z["wif_unet_out"].clone().to(dev).requires_grad_(True)
+    y = wb.wif_fuse(raw, u)
+    assert float((y.detach().cpu() - z["wif_fused"]).abs().max()) <= FWD_TOL
+    w = torch.randn(y.shape, generator=torch.Generator().manual_seed(11))
+    (y * w.to(dev)).sum().backward()
+    r32 = z["raw_output"].clone().requires_grad_(True)
+    u32 = z["wif_unet_out"].clone().requires_grad_(True)
+    (wo.wif_fuse(r32, u32) * w).sum().backward()
+    r64 = z["raw_output"].double().clone().requires_grad_(True)
+    u64 = z["wif_unet_out"].double().clone().requires_grad_(True)
+    (wo.wif_fuse(r64, u64) * w.double()).sum().backward()
+    grad_close(raw.grad, r32.grad, r64.grad, "wif d raw_output")
+    grad_close(u.grad, u32.grad, u64.grad, "wif d unet_out")
+
+
+def check_kats(dev):
+    """Known-answer tests of SURVEY.md §4 through the product path."""
+    # KAT1: TPS of the rest control points is the identity lattice
+    g44 = wb.get_grid(4, 4).view(-1, 2)
+    tps = wb.TPSWarp(64, 64, g44).to(dev)
+    out = tps(g44[None].to(dev))
+    assert float((out.cpu() - wb.get_grid(64, 64)).abs().max()) <= 2e-6
+    # KAT2: TPS reproduces an affine map of the control points
+    A = torch.tensor([[0.9, 0.2], [-0.1, 1.1]])
+    tvec = torch.tensor([0.05, -0.02])
+    out = tps((g44 @ A.t() + tvec)[None].to(dev))
+    want = wb.get_grid(64, 64).view(-1, 2) @ A.t() + tvec
+    assert float((out.cpu().view(-1, 2) - want).abs().max()) <= 2e-6
+    # KAT3: inverse of the identity is the identity, bit-exactly; integer translation inverts exactly
+    inv = wb.InverseWarp(16, 32, 16, 32).to(dev)
+    ident = wb.get_grid(16, 32)
+    out = inv(ident.to(dev), erode=False)
+    assert torch.equal(out.cpu(), ident)
+    shift = ident + torch.tensor([3 * 2 / 32, -2 * 2 / 16])
+    out = inv(shift.to(dev), erode=False).cpu()
+    want = ident - torch.tensor([3 * 2 / 32, -2 * 2 / 16])
+    assert float((out - want).abs().max()) <= 1e-6
+    # KAT5: with a zero UNet output WIF fuses sigma(v4+5)*rgb averaged over contexts
+    v = torch.randn(1, 3, 2, 9, 8, 8, generator=torch.Generator().manual_seed(2))
+    y = wb.wif_fuse(v.to(dev), torch.zeros(1, 2, 3, 5, 8, 8, device=dev)).cpu()
+    want = (torch.sigmoid(v[:, :, :, 4:5] + 5) * v[:, :, :, :3]).mean(dim=1)
+    assert float((y - want).abs().max()) <= 1e-6
+
+
+def check_full_size(dev, B=1, T=5, Tc=4):
+    """Full BASELINE shape through the product path only (the oracle would need minutes and tens of GB):
+      * identity geometry (rest control points, zero flow): raw_output[:, :, :, :C] reproduces the context frames
+        exactly and `flow` is ~0;
+      * output channels are a convex combination of the warped contexts (min <= out <= max);
+      * alpha_ctx is a view of raw_output; all alphas within [-1, 1]; run-to-run determinism of the forward;
+      * the oracle agrees on a random crop-free sub-problem: checked separately at small sizes (check_decode)."""
+    cfg = wo.PathConfig()
+    opt = make_opt(cfg)
+    warper = wb.Warper(opt).to(dev)
+    d = wo.synth_inputs(cfg, B, T, Tc, seed=0)
+    om, bg = wb.alpha_masks(opt)
+    to = lambda t: t.to(dev)
+    occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, to(d["obj_alpha_raw"]), to(om), to(bg), to(d["obj_pose"]), to(d["bg_pose"]), to(d["occ_score"]))
+    args = (to(d["input"]), grid, occ, oa, ba, to(d["cls"]), to(d["ctx_ts"]), to(d["pred_ts"]), True)
+    out1 = wb.decode_output(warper, *args)
+    out2 = wb.decode_output(warper, *args)
+    for a, b in zip(out1, out2):
+        if a is not None:
+            assert torch.equal(a, b), "forward is not run-to-run deterministic"
+    output, flow, a_unflt, alpha, raw_alpha, raw, alpha_ctx = out1
+    C, L = d["input"].shape[2], cfg.num_obj + 1
+    assert a_unflt is None
+    assert tuple(raw.shape) == (B, Tc, T - Tc, C + L, 512, 1024)
+    assert alpha_ctx.data_ptr() == raw[:, :, :, C:].data_ptr()
+    for t_ in (alpha, alpha_ctx, raw_alpha):
+        assert float(t_.min()) >= -1 - 1e-5 and float(t_.max()) <= 1 + 1e-5
+    warped = raw[:, :, :, :C]
+    lo, hi = warped.min(dim=1)[0], warped.max(dim=1)[0]
+    assert bool(((output >= lo - 1e-4) & (output <= hi + 1e-4)).all())
+    assert bool(torch.isfinite(output).all()) and bool(torch.isfinite(flow).all())
+    # identity geometry: every frame has the same control points -> zero flow -> exact copy of the context frames
+    obj_pose = d["obj_pose"][:, :1].expand(-1, T, -1, -1, -1).contiguous()
+    bg_pose = d["bg_pose"][:, :1].expand(-1, T, -1, -1, -1).contiguous()
+    occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, to(d["obj_alpha_raw"]), to(om), to(bg), to(obj_pose), to(bg_pose), to(d["occ_score"]))
+    output, flow, _, _, _, raw, _ = wb.decode_output(warper, to(d["input"]), grid, occ, oa, ba, to(d["cls"]), to(d["ctx_ts"]), to(d["pred_ts"]), True)
+    assert float(flow.abs().max()) == 0.0
+    want = to(d["input"])[:, :Tc].unsqueeze(2)
+    assert torch.equal(raw[:, :, :, :C], want), "zero flow must copy the context frames bit-exactly"

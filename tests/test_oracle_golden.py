@@ -1,0 +1,70 @@
+"""The oracle against the committed reference outputs (tests/golden, produced by oracle/make_golden.py from the
+unmodified reference) and against the known-answer tests of SURVEY.md §4.  CPU only."""
+import math
+
+import pytest
+import torch
+
+from tests import parity
+from tests.parity import wo
+
+
+@pytest.mark.parametrize("case", parity.CASES)
+def test_stage_a_bit_exact(case):
+    cfg, _, z = parity.load_case(case)
+    st = wo.make_state(cfg)
+    occ, oa, ba, grid = wo.estimate_alpha_grid_occ(st, z["in_obj_alpha_raw"], z["in_obj_pose"], z["in_bg_pose"], z["in_occ_score"])
+    for g, k in zip(grid, ("tgt_grid_obj", "src_grid_obj", "tgt_grid_bg", "src_grid_bg")):
+        assert torch.equal(g, z[k]), k
+    assert torch.equal(occ, z["occ"])
+
+
+@pytest.mark.parametrize("case", parity.CASES)
+def test_decode_and_grads(case):
+    cfg, _, z = parity.load_case(case)
+    st = wo.make_state(cfg)
+    lv = {k: z["in_" + k].clone().requires_grad_(True) for k in ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")}
+    occ, oa, ba, grid = wo.estimate_alpha_grid_occ(st, lv["obj_alpha_raw"], lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
+    out = wo.decode_output(st, lv["input"], grid, occ, oa, ba, lv["cls"], z["in_ctx_ts"], z["in_pred_ts"])
+    loss = 0
+    for n, o in zip(parity.OUT_NAMES, out):
+        if o is None:
+            assert n not in z
+            continue
+        tol = 1e-4 if n in ("output", "raw_output") else 5e-6   # warped +-5 one-hot logits amplify a flow ulp (App. D)
+        assert float((o - z[n]).abs().max()) <= tol, n
+        if "proj_" + n in z:
+            loss = loss + (o * z["proj_" + n]).sum()
+    loss.backward()
+    for k, v in lv.items():
+        g = z["grad_" + k]
+        assert float((v.grad - g).abs().max()) <= 1e-4 * float(g.abs().max()), k
+    assert float((wo.wif_fuse(out[5].detach(), z["wif_unet_out"]) - z["wif_fused"]).abs().max()) <= 1e-4
+
+
+def test_kats():
+    g = wo.pixel_grid(2, 4)
+    assert torch.allclose(g[0, 0, :, 0], torch.tensor([-0.75, -0.25, 0.25, 0.75]))
+    assert torch.allclose(g[0, :, 0, 1], torch.tensor([-0.5, 0.5]))
+    k = wo.gaussian3(3)
+    assert abs(float(k[1, 1]) - 0.619347) < 1e-5 and abs(float(k[0, 1]) - 0.083820) < 1e-5 and abs(float(k[0, 0]) - 0.011344) < 1e-5
+    phi = wo.tps_phi(torch.tensor([[0., 0.], [1., 0.], [0., 2.]]), torch.tensor([[0., 0.], [1., 0.], [0., 2.]]))
+    assert abs(float(phi[0, 1])) < 1e-6 and abs(float(phi[0, 2]) - 2.7725887) < 1e-5 and abs(float(phi[1, 2]) - 4.0235949) < 1e-5
+    basis = wo.tps_basis(64, 64, wo.pixel_grid(4, 4).view(-1, 2))
+    out = wo.tps_eval(basis, wo.pixel_grid(4, 4).view(1, -1, 2))
+    assert float((out - wo.pixel_grid(64, 64)).abs().max()) < 2e-6
+    ident = wo.pixel_grid(32, 64)
+    assert torch.equal(wo.inverse_warp(ident, (32, 64), erode=False), ident)
+
+
+def test_aten_formulas_restated():
+    """The first-principles bilinear formulas agree with the ATen calls the reference relies on."""
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 9, 14, generator=gen)
+    g = torch.rand(2, 11, 7, 2, generator=gen) * 2.6 - 1.3
+    assert float((wo.bil0(x, g) - wo.bil0_explicit(x, g)).abs().max()) < 1e-6
+    for f, out_hw, r in ((4, (36, 56), (0.25, 0.25)), (2, (18, 28), (0.5, 0.5))):
+        assert float((wo.resize(x, f) - wo.resize_explicit(x, out_hw, r)).abs().max()) < 1e-6
+    y = torch.randn(2, 3, 16, 24, generator=gen)
+    assert float((wo.resize(y, 0.25) - wo.resize_explicit(y, (4, 6), (4, 4))).abs().max()) < 1e-6
+    assert float((wo.resize(y, 0.25) - y[..., 1::4, :][..., 1::4].add(y[..., 1::4, :][..., 2::4]).add(y[..., 2::4, :][..., 1::4]).add(y[..., 2::4, :][..., 2::4]) / 4).abs().max()) < 1e-6

@@ -63,7 +63,7 @@ class DecodeFwd(C.Structure):
                 ("a_lo", c_void_p), ("prof_part", c_void_p), ("prof_ctas", C.c_int), ("prof_sum", c_void_p),
                 ("prof_p", c_void_p), ("f_lo", c_void_p), ("s_lo", c_void_p),
                 ("alpha", c_void_p), ("flow", c_void_p), ("raw_output", c_void_p), ("out_full", c_void_p),
-                ("norm", c_void_p)]
+                ("norm", c_void_p), ("stages", C.c_int)]
 
 
 class DecodeBwd(C.Structure):
@@ -74,7 +74,8 @@ class DecodeBwd(C.Structure):
                 ("d_obj_alpha", c_void_p), ("d_bg_alpha", c_void_p), ("d_cls", c_void_p),
                 ("d_alpha_acc", c_void_p), ("d_f_lo", c_void_p), ("d_a_lo", c_void_p),
                 ("d_prof_p", c_void_p), ("d_prof_sum", c_void_p),
-                ("red_ctas", C.c_int), ("occ_part", c_void_p), ("prof_p_part", c_void_p), ("cls_part", c_void_p)]
+                ("red_ctas", C.c_int), ("occ_part", c_void_p), ("prof_p_part", c_void_p), ("cls_part", c_void_p),
+                ("stages", C.c_int)]
 
 
 class WifFuseFwd(C.Structure):
@@ -95,7 +96,7 @@ STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwar
              "waldo_invwarp_bwd_t": InvWarpBwd, "waldo_geom_t": Geom, "waldo_decode_fwd_t": DecodeFwd,
              "waldo_decode_bwd_t": DecodeBwd, "waldo_wif_fuse_fwd_t": WifFuseFwd, "waldo_wif_fuse_bwd_t": WifFuseBwd}
 
-EXPORTS = ["waldo_last_error", "waldo_abi_version", "waldo_has_device_code", "waldo_tps_fwd", "waldo_tps_bwd",
+EXPORTS = ["waldo_last_error", "waldo_abi_version", "waldo_has_device_code", "waldo_launch_count", "waldo_tps_fwd", "waldo_tps_bwd",
            "waldo_invwarp_fwd", "waldo_invwarp_bwd", "waldo_occ_fwd", "waldo_occ_bwd", "waldo_decode_fwd",
            "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd"]
 
@@ -108,6 +109,7 @@ def _declare(lib):
     lib.waldo_last_error.restype = C.c_char_p
     lib.waldo_abi_version.restype = C.c_int
     lib.waldo_has_device_code.restype = C.c_int
+    lib.waldo_launch_count.restype = C.c_longlong
     for name, st in (("waldo_tps_fwd", TpsFwd), ("waldo_tps_bwd", TpsBwd), ("waldo_invwarp_fwd", InvWarpFwd),
                      ("waldo_invwarp_bwd", InvWarpBwd), ("waldo_decode_fwd", DecodeFwd), ("waldo_decode_bwd", DecodeBwd),
                      ("waldo_wif_fuse_fwd", WifFuseFwd), ("waldo_wif_fuse_bwd", WifFuseBwd)):

@@ -10,6 +10,7 @@
 #include "wb_wif.cuh"
 
 static thread_local char g_err[512] = "";
+long long g_wb_launches = 0;
 
 static int wb_fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -41,6 +42,7 @@ extern "C" {
 
 const char* waldo_last_error(void) { return g_err; }
 int waldo_abi_version(void) { return WALDO_ABI_VERSION; }
+long long waldo_launch_count(void) { return g_wb_launches; }
 int waldo_has_device_code(void) {
 #ifdef WB_HOST_EMU
   return 0;
@@ -152,6 +154,8 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   }
   const int L = g.No + 1, HW = g.H * g.W;
   const long long HWd = (long long)g.Hd * g.Wd;
+  const bool st_prep = a->stages == 0 || (a->stages & 1), st_main = a->stages == 0 || (a->stages & 2);
+  if (st_prep) {
   // B1
   WB_LAUNCH(k_project_alpha, dim3(wb_blocks((long long)g.B * g.Tw * L * HW, 256)), dim3(256), 0, st, *a);
   WB_LAUNCHED();
@@ -170,9 +174,12 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   // B5
   WB_LAUNCH(k_layer_flow_lo, dim3(wb_blocks((long long)g.B * g.Tp * L * HW, 256)), dim3(256), 0, st, *a);
   WB_LAUNCHED();
+  }
   // B5(up)-B9 + stage C
-  WB_LAUNCH(k_warp_composite_fwd, dim3(wb_blocks(HWd, 256), g.B * g.Tp), dim3(256), 0, st, *a);
-  WB_LAUNCHED();
+  if (st_main) {
+    WB_LAUNCH(k_warp_composite_fwd, dim3(wb_blocks(HWd, 256), g.B * g.Tp), dim3(256), 0, st, *a);
+    WB_LAUNCHED();
+  }
   return 0;
 }
 

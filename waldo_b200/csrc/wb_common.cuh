@@ -42,8 +42,10 @@ struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+extern long long g_wb_launches;
 #define WB_LAUNCH(kern, grid, block, smem, stream, ...)                                     \
   do {                                                                                      \
+    ++g_wb_launches;                                                                        \
     wb_dim3 g_ = (grid);                                                                    \
     gridDim = g_; blockDim = wb_dim3(1, 1, 1); threadIdx = wb_dim3(0, 0, 0);                \
     for (unsigned bz_ = 0; bz_ < g_.z; ++bz_)                                               \
@@ -55,7 +57,9 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 #else
 // ------------------------------------------------------------------ device build
 #include <cuda_runtime.h>
-#define WB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+extern long long g_wb_launches;
+#define WB_LAUNCH(kern, grid, block, smem, stream, ...) \
+  do { ++g_wb_launches; kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); } while (0)
 #define WB_CHECK_LAUNCH() wb_check_launch(__FILE__, __LINE__)
 #define WB_UNROLL _Pragma("unroll")
 #endif

@@ -655,13 +655,15 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     WB_BREQ(wh * wwid <= WB_WIN_CAP, "scale_hd too small for the compiled low-res window (needs scale_hd >= 2)");
   }
   // 1. fused HD backward
-  WB_LAUNCH(k_warp_composite_bwd, dim3(a.red_ctas, g.B * g.Tp), dim3(WB_TILE_PX), 0, st, a);
-  WB_BLAUNCHED();
-  if (a.d_occ) {
-    WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);
+  if (a.stages == 0 || (a.stages & 1)) {
+    WB_LAUNCH(k_warp_composite_bwd, dim3(a.red_ctas, g.B * g.Tp), dim3(WB_TILE_PX), 0, st, a);
     WB_BLAUNCHED();
+    if (a.d_occ) {
+      WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);
+      WB_BLAUNCHED();
+    }
   }
-  if (!need_alpha_chain) return 0;
+  if (!need_alpha_chain || !(a.stages == 0 || (a.stages & 2))) return 0;
   // 2. context-alpha backward
   if (a.d_alpha_acc || a.d_alpha) {
     if (filt && a.d_prof_p) WB_BREQ(a.prof_p_part, "prof_p_part scratch missing");

@@ -193,6 +193,30 @@ def _geom(spec: DecodeSpec, B, T, Tc, Tp, Nl, has_cls):
                   flags, float(spec.min_cls))
 
 
+# When bench.py sets PROFILE = {"decode_fwd": [], "decode_bwd": []}, the two entry points are issued stage by stage
+# (same kernels, same order, same stream) with a CUDA-event pair around the dominant fused HD kernel, so that its
+# duration can be read inside the timed region (the roofline figure).  None = one call per entry point.
+PROFILE = None
+
+
+def _staged(fn, arg, stream, what, main_bit, dev):
+    if PROFILE is None:
+        L.check(fn(C.byref(arg), stream), what)
+        return
+    rest_bit = 3 - main_bit
+    first, second = (rest_bit, main_bit) if what == "decode_fwd" else (main_bit, rest_bit)
+    for bit in (first, second):
+        arg.stages = bit
+        if bit == main_bit:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(dev))
+        L.check(fn(C.byref(arg), stream), what)
+        if bit == main_bit:
+            e1.record(torch.cuda.current_stream(dev))
+            PROFILE[what].append((e0, e1))
+    arg.stages = 0
+
+
 class _Decode(torch.autograd.Function):
     """LVD.forward(mode="decode_output") = Warper.grid_to_flow[_ctx] + Warper.input_to_output, lvd.py:141-153.
 
@@ -239,8 +263,8 @@ class _Decode(torch.autograd.Function):
                         L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
                         L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
                         L.ptr(prof_p), L.ptr(f_lo), L.ptr(s_lo), L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full),
-                        L.ptr(norm))
-        L.check(lib.waldo_decode_fwd(C.byref(a), L.stream_of(inp_c)), "decode_fwd")
+                        L.ptr(norm), 0)
+        _staged(lib.waldo_decode_fwd, a, L.stream_of(inp_c), "decode_fwd", main_bit=2, dev=dev)
         ctx.spec, ctx.has_cls = spec, cls is not None
         ctx.keep = (a, inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
                     prof_sum, prof_p, f_lo, s_lo, alpha, flow, raw, out_full, norm)
@@ -292,8 +316,8 @@ class _Decode(torch.autograd.Function):
         b = L.DecodeBwd(fwd, L.ptr(grads_in[0]), L.ptr(grads_in[1]), L.ptr(grads_in[2]), L.ptr(grads_in[3]),
                         L.ptr(d_input), L.ptr(d_tgo_s), L.ptr(d_sgo_s), L.ptr(d_tgb_s), L.ptr(d_sgb_s), L.ptr(d_occ),
                         L.ptr(d_oa), L.ptr(d_ba), L.ptr(d_cls_s), L.ptr(d_alpha_acc), L.ptr(d_f_lo), L.ptr(d_a_lo),
-                        L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part))
-        L.check(lib.waldo_decode_bwd(C.byref(b), L.stream_of(inp_c)), "decode_bwd")
+                        L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part), 0)
+        _staged(lib.waldo_decode_bwd, b, L.stream_of(inp_c), "decode_bwd", main_bit=1, dev=dev)
         if d_oa is not None:
             d_oa = d_oa.view(ctx.shapes["obj_alpha"])
         if d_ba is not None:
