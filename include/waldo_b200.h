@@ -164,6 +164,8 @@ typedef struct {
   float* prof_p;              /* (B, No, Nl) class probabilities used by the filter */
   float* f_lo;                /* (B, Tc, Tp, L, H, W, 2) per-layer flow on the low-res lattice, lvd.py:792 */
   float* s_lo;                /* (B, Tp, No, H, W) object support, lvd.py:788 */
+  uint32_t* live_ctx;         /* (B, Tw, H, W) bit k: layer k has an in-range tap at this low-res cell of context frame t */
+  uint32_t* live_pred;        /* (B, Tp, H, W) same for the target frames (bit 0 always set) */
   /* outputs */
   float* alpha;               /* (B, Tw, L, Hd, Wd) in [-1,1]                         lvd.py:822 */
   float* flow;                /* (B, Tc, Tp, 2, Hd, Wd)                               lvd.py:818 */

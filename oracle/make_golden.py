@@ -37,6 +37,9 @@ CASES = {
                       patch_size=8, num_lyt=4, restrict_to_ctx=False, include_self=True), 2, 3, 1, True),
     "cls_plain": (dict(dim=16, load_dim=32, aspect_ratio=2.0, num_obj=2, obj_shape=(2, 2), latent_shape=(2, 4),
                        patch_size=8, num_lyt=3, weight_cls=False, use_disocc=True), 1, 3, 2, False),
+    # 11 heavily overlapping layers: exercises the dense (> 8 live layers per warp) code path of the HD kernels
+    "many_obj": (dict(dim=16, load_dim=32, aspect_ratio=2.0, num_obj=10, obj_shape=(2, 2), latent_shape=(2, 4),
+                      patch_size=8, num_lyt=3), 1, 3, 2, True),
 }
 
 
@@ -131,7 +134,10 @@ def run_reference(cfg: wo.PathConfig, B, T, Tc, smooth, seed=0):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    only = sys.argv[1:]
     for name, (kw, B, T, Tc, smooth) in CASES.items():
+        if only and name not in only:
+            continue
         cfg = wo.PathConfig(**kw)
         res = run_reference(cfg, B, T, Tc, smooth)
         meta = dict(kw, B=B, T=T, Tc=Tc, smooth=smooth)

@@ -61,7 +61,7 @@ class DecodeFwd(C.Structure):
                 ("obj_alpha", c_void_p), ("bg_alpha", c_void_p), ("cls", c_void_p),
                 ("ctx_ts", c_void_p), ("pred_ts", c_void_p), ("xs_hd", c_void_p), ("ys_hd", c_void_p),
                 ("a_lo", c_void_p), ("prof_part", c_void_p), ("prof_ctas", C.c_int), ("prof_sum", c_void_p),
-                ("prof_p", c_void_p), ("f_lo", c_void_p), ("s_lo", c_void_p),
+                ("prof_p", c_void_p), ("f_lo", c_void_p), ("s_lo", c_void_p), ("live_ctx", c_void_p), ("live_pred", c_void_p),
                 ("alpha", c_void_p), ("flow", c_void_p), ("raw_output", c_void_p), ("out_full", c_void_p),
                 ("norm", c_void_p), ("stages", C.c_int)]
 

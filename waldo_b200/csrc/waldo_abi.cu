@@ -143,7 +143,8 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   if (rc) return rc;
   WB_REQUIRE(a->input && a->tgt_grid_obj && a->src_grid_obj && a->tgt_grid_bg && a->src_grid_bg && a->occ && a->obj_alpha &&
              a->bg_alpha && a->ctx_ts && a->pred_ts && a->xs_hd && a->ys_hd, "decode_fwd: null input pointer");
-  WB_REQUIRE(a->a_lo && a->f_lo && a->alpha && a->flow && a->raw_output && a->out_full, "decode_fwd: null output pointer");
+  WB_REQUIRE(a->a_lo && a->f_lo && a->alpha && a->flow && a->raw_output && a->out_full && a->live_ctx && a->live_pred,
+             "decode_fwd: null output pointer");
   const bool filt = (g.flags & WALDO_F_FILTER) != 0;
   const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
   if (g.flags & WALDO_F_HAS_CLS) WB_REQUIRE(a->cls, "decode_fwd: cls flagged but null");
@@ -157,7 +158,7 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   const bool st_prep = a->stages == 0 || (a->stages & 1), st_main = a->stages == 0 || (a->stages & 2);
   if (st_prep) {
   // B1
-  WB_LAUNCH(k_project_alpha, dim3(wb_blocks((long long)g.B * g.Tw * L * HW, 256)), dim3(256), 0, st, *a);
+  WB_LAUNCH(k_project_alpha, dim3(wb_blocks((long long)g.B * g.Tw * HW, 128)), dim3(128), 0, st, *a);
   WB_LAUNCHED();
   // B2
   if (filt) {
@@ -169,15 +170,15 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
     WB_LAUNCHED();
   }
   // B2b-B4
-  WB_LAUNCH(k_alpha_prep, dim3(wb_blocks(HWd, 256), g.B * g.Tw), dim3(256), 0, st, *a);
+  WB_LAUNCH(k_alpha_prep, dim3(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tw), dim3(WB_TILE_PX), 0, st, *a);
   WB_LAUNCHED();
   // B5
-  WB_LAUNCH(k_layer_flow_lo, dim3(wb_blocks((long long)g.B * g.Tp * L * HW, 256)), dim3(256), 0, st, *a);
+  WB_LAUNCH(k_layer_flow_lo, dim3(wb_blocks((long long)g.B * g.Tp * HW, 128)), dim3(128), 0, st, *a);
   WB_LAUNCHED();
   }
   // B5(up)-B9 + stage C
   if (st_main) {
-    WB_LAUNCH(k_warp_composite_fwd, dim3(wb_blocks(HWd, 256), g.B * g.Tp), dim3(256), 0, st, *a);
+    WB_LAUNCH(k_warp_composite_fwd, dim3(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tp), dim3(WB_TILE_PX), 0, st, *a);
     WB_LAUNCHED();
   }
   return 0;

@@ -32,6 +32,8 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
@@ -54,6 +56,9 @@ extern long long g_wb_launches;
   } while (0)
 #define WB_CHECK_LAUNCH() 0
 #define WB_UNROLL
+#define WB_UNROLL_NA
+static thread_local float wb_dyn_smem_buf[96 * 1024];
+#define WB_DYN_SMEM(name) float* name = wb_dyn_smem_buf
 #else
 // ------------------------------------------------------------------ device build
 #include <cuda_runtime.h>
@@ -62,6 +67,10 @@ extern long long g_wb_launches;
   do { ++g_wb_launches; kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); } while (0)
 #define WB_CHECK_LAUNCH() wb_check_launch(__FILE__, __LINE__)
 #define WB_UNROLL _Pragma("unroll")
+// loops over the NA layer slots of a template: fully unrolled (register arrays) for the sparse instantiations,
+// rolled (local-memory arrays, small code, few registers) for the rare dense one
+#define WB_UNROLL_NA _Pragma("unroll (NA <= 8 ? NA : 1)")
+#define WB_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
 #endif
 
 #define WB_MAX_L 17
@@ -95,6 +104,14 @@ WB_DEV int wb_warp() {
   return 0;
 #else
   return (int)(threadIdx.x >> 5);
+#endif
+}
+// OR over the warp (all 32 lanes must call it)
+WB_DEV unsigned wb_warp_or(unsigned m) {
+#ifdef WB_HOST_EMU
+  return m;
+#else
+  return __reduce_or_sync(0xffffffffu, m);
 #endif
 }
 WB_DEV double wb_warp_sum(double v) {

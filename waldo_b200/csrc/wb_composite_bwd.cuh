@@ -7,6 +7,7 @@
 //   * low-res scatter targets of the HD kernels (d f_lo, d a_lo): shared-memory window per 32x8 HD tile,
 //     flushed once per tile;
 //   * HD scatter targets (d input, d context opacity): red.global.add.f32.
+// All layer loops run over the warp-wide union of live layers (see wb_composite.cuh).
 #pragma once
 #include "wb_common.cuh"
 #include "wb_prep.cuh"
@@ -14,35 +15,33 @@
 
 typedef waldo_decode_bwd_t WbDecB;
 
-#define WB_TILE_W 32
-#define WB_TILE_H 8
-#define WB_TILE_PX (WB_TILE_W * WB_TILE_H)
 #define WB_WIN_CAP 128              // low-res cells a tile window may hold (scale_hd >= 2: <= 6 x 18 = 108)
 #define WB_NWARP (WB_TILE_PX / 32)
 
 WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) atomicAdd(p, v); }
 
-// exclusive-product backward of  A_i = R_i * prod_j (1 - R_j occ[j,i]).
+// exclusive-product backward of  A_i = R_i * prod_j (1 - R_j occ[j,i])  over the slots of `ix`.
 // gR (+=) gets d/dR; when s_acc != nullptr, d/d occ[j,i] summed over the warp is added to s_acc[j*L+i] by lane 0.
-WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, int L, float* gR, float* s_acc) {
+template <int NA>
+WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, int L, const WbIdx<NA>& ix, float* gR, float* s_acc) {
   const int lane = wb_lane();
-  WB_UNROLL for (int i = 0; i < WB_MAX_L; ++i) {
-    if (i < L) {
-      float pre[WB_MAX_L];
+  WB_UNROLL_NA for (int i = 0; i < NA; ++i) {
+    if (i < ix.n) {
+      float pre[NA];
       float run = 1.f;
-      WB_UNROLL for (int j = 0; j < WB_MAX_L; ++j) if (j < L) { pre[j] = run; run *= 1.f - R[j] * s_occ[j * L + i]; }
+      WB_UNROLL_NA for (int j = 0; j < NA; ++j) if (j < ix.n) { pre[j] = run; run *= 1.f - R[j] * s_occ[ix.k[j] * L + ix.k[i]]; }
       gR[i] += gA[i] * run;
       const float gV = gA[i] * R[i];
       float suf = 1.f;
-      WB_UNROLL for (int j = WB_MAX_L - 1; j >= 0; --j) {
-        if (j < L) {
-          const float oc = s_occ[j * L + i];
+      WB_UNROLL_NA for (int j = NA - 1; j >= 0; --j) {
+        if (j < ix.n) {
+          const float oc = s_occ[ix.k[j] * L + ix.k[i]];
           const float excl = pre[j] * suf;
           suf *= 1.f - R[j] * oc;
           gR[j] -= gV * oc * excl;
           if (s_acc) {
             float v = wb_warp_sum(-gV * R[j] * excl);
-            if (lane == 0) s_acc[j * L + i] += v;
+            if (lane == 0) s_acc[ix.k[j] * L + ix.k[i]] += v;
           }
         }
       }
@@ -51,172 +50,206 @@ WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, 
 }
 
 // ============================================================================ fused HD backward
-// grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration).
-__global__ void __launch_bounds__(WB_TILE_PX) k_warp_composite_bwd(WbDecB a) {
+struct WbBwdCtx {   // per-CTA constants of the fused backward
+  int b, tp, L, C, TcR, CR, HW;
+  size_t HWd;
+  bool self, disocc_ch, need_layers, lowres_direct;
+  const float* s_occ;
+  float* s_acc;      // this warp's d occ accumulators (or null)
+  float* s_win;      // low-res window of the tile: [Tc][WB_WIN_CAP][L][2]
+  int wy0, wx0, ww;  // window origin / width
+};
+
+template <int NA>
+WB_DEV void wb_bwd_pixel(const WbDecB& a, const WbBwdCtx& c, const WbPix& px, unsigned wm, bool active, size_t q) {
+  const WbDec& d = a.f;
+  const waldo_geom_t& g = d.g;
+  const int L = c.L, C = c.C, b = c.b, tp = c.tp, HW = c.HW;
+  const size_t HWd = c.HWd;
+  const WbIdx<NA> ix = wb_idx<NA>(wm);
+  // window-relative low-res offsets
+  const int c00 = (px.ay.i0 - c.wy0) * c.ww + px.ax.i0 - c.wx0, c01 = (px.ay.i0 - c.wy0) * c.ww + px.ax.i1 - c.wx0;
+  const int c10 = (px.ay.i1 - c.wy0) * c.ww + px.ax.i0 - c.wx0, c11 = (px.ay.i1 - c.wy0) * c.ww + px.ax.i1 - c.wx0;
+  const float w00 = px.ax.l0 * px.ay.l0, w01 = px.ax.l1 * px.ay.l0, w10 = px.ax.l0 * px.ay.l1, w11 = px.ax.l1 * px.ay.l1;
+  float gO[WB_MAX_C + 1];   // upstream d out_full; the score channel sits at index C (as in memory)
+  float S = 0.f;
+  {
+    const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
+    const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+    WB_UNROLL for (int ch = 0; ch <= WB_MAX_C; ++ch) {
+      gO[ch] = 0.f;
+      if (ch <= C && dof && active) { gO[ch] = __ldg(dof + (size_t)ch * HWd); S += gO[ch] * __ldg(of + (size_t)ch * HWd); }
+    }
+  }
+  const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
+  for (int tc = 0; tc < g.Tc; ++tc) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+    const float* f_lo = d.f_lo + pair * L * HW * 2;
+    const float* alpha_c = d.alpha + ((size_t)b * g.Tw + c_t) * L * HWd;
+    WbLay<NA> ly;
+    wb_layers_fwd<NA>(d, px, ix, f_lo, alpha_c, c.s_occ, ly);
+    const float wgt = ly.score + 1e-6f, n = wgt / D;
+    const float* draw = (a.d_raw_output && active) ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
+    // ---- stage C backward: warped context frame
+    WbTaps t = wb_taps(__fadd_rn(px.gx, ly.flow_x), __fadd_rn(px.gy, ly.flow_y), g.Wd, g.Hd);
+    const int m = wb_tap_mask(t, g.Wd, g.Hd);
+    const float* src = d.input + ((size_t)b * g.T + c_t) * C * HWd + (long long)t.y0 * g.Wd + t.x0;
+    float* din = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * C * HWd + (long long)t.y0 * g.Wd + t.x0 : nullptr;
+    float G = 0.f, gix = 0.f, giy = 0.f;
+    WB_UNROLL for (int ch = 0; ch < WB_MAX_C; ++ch) {
+      if (ch < C) {
+        const float* p = src + (size_t)ch * HWd;
+        const float vnw = (m & 1) ? __ldg(p) : 0.f, vne = (m & 2) ? __ldg(p + 1) : 0.f;
+        const float vsw = (m & 4) ? __ldg(p + g.Wd) : 0.f, vse = (m & 8) ? __ldg(p + g.Wd + 1) : 0.f;
+        const float O = wb_chain(vnw, vne, vsw, vse, t);
+        const float go = (draw ? __ldg(draw + (size_t)ch * HWd) : 0.f) + n * gO[ch];
+        G += gO[ch] * O;
+        gix += go * ((vne - vnw) * t.wy0 + (vse - vsw) * t.wy1);
+        giy += go * ((vsw - vnw) * t.wx0 + (vse - vne) * t.wx1);
+        if (din && go != 0.f) {
+          float* o = din + (size_t)ch * HWd;
+          if (m & 1) wb_atomic_add(o, t.nw * go);
+          if (m & 2) wb_atomic_add(o + 1, t.ne * go);
+          if (m & 4) wb_atomic_add(o + g.Wd, t.sw * go);
+          if (m & 8) wb_atomic_add(o + g.Wd + 1, t.se * go);
+        }
+      }
+    }
+    if (!c.need_layers) continue;
+    G += gO[C] * (ly.score * 2.f - 1.f);
+    const float* dfl = (a.d_flow && active) ? a.d_flow + pair * 2 * HWd + q : nullptr;
+    const float dfx = (dfl ? __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+    const float dfy = (dfl ? __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
+    const float gs = 2.f * n * gO[C] + (G - S) / D;
+    // ---- B9 / B8 backward
+    float gA[NA], gR[NA], gFx[NA], gFy[NA];
+    WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+      gR[s] = 0.f; gA[s] = 0.f; gFx[s] = 0.f; gFy[s] = 0.f;
+      if (s < ix.n) {
+        gA[s] = gs + 2.f * (draw ? __ldg(draw + (size_t)(C + ix.k[s]) * HWd) : 0.f) + dfx * ly.Fx[s] + dfy * ly.Fy[s];
+        gFx[s] = ly.A[s] * dfx; gFy[s] = ly.A[s] * dfy;
+      }
+    }
+    wb_occlude_bwd<NA>(ly.R, gA, c.s_occ, L, ix, gR, c.s_acc);
+    // ---- B7 backward: disocc = max_k R_k (first maximal layer takes the gradient)
+    if (c.disocc_ch && draw) {
+      const float gd = __ldg(draw + (size_t)(C + L) * HWd);
+      bool done = false;
+      WB_UNROLL_NA for (int s = 0; s < NA; ++s)
+        if (s < ix.n && !done && ly.R[s] == ly.disocc) { gR[s] += gd; done = true; }
+    }
+    // ---- B6 backward: bilinear sample of the context opacity through layer k's flow
+    float* dal = a.d_alpha_acc ? a.d_alpha_acc + ((size_t)b * g.Tw + c_t) * L * HWd : nullptr;
+    WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+      if (s < ix.n) {
+        const int k = ix.k[s];
+        if (((px.isobj >> k) & 1u) && gR[s] != 0.f) {
+          WbTaps tk = wb_taps(__fadd_rn(px.gx, ly.Fx[s]), __fadd_rn(px.gy, ly.Fy[s]), g.Wd, g.Hd);
+          const int mk = wb_tap_mask(tk, g.Wd, g.Hd);
+          const long long off = (long long)k * (long long)HWd + (long long)tk.y0 * g.Wd + tk.x0;
+          const float* p = alpha_c + off;
+          const float vnw = (mk & 1) ? (__ldg(p) + 1.f) * 0.5f : 0.f, vne = (mk & 2) ? (__ldg(p + 1) + 1.f) * 0.5f : 0.f;
+          const float vsw = (mk & 4) ? (__ldg(p + g.Wd) + 1.f) * 0.5f : 0.f, vse = (mk & 8) ? (__ldg(p + g.Wd + 1) + 1.f) * 0.5f : 0.f;
+          const float gr = gR[s];
+          gFx[s] += gr * ((vne - vnw) * tk.wy0 + (vse - vsw) * tk.wy1) * (0.5f * (float)g.Wd);
+          gFy[s] += gr * ((vsw - vnw) * tk.wx0 + (vse - vne) * tk.wx1) * (0.5f * (float)g.Hd);
+          if (dal) {
+            float* o = dal + off;
+            if (mk & 1) wb_atomic_add(o, tk.nw * gr);
+            if (mk & 2) wb_atomic_add(o + 1, tk.ne * gr);
+            if (mk & 4) wb_atomic_add(o + g.Wd, tk.sw * gr);
+            if (mk & 8) wb_atomic_add(o + g.Wd + 1, tk.se * gr);
+          }
+        }
+        // ---- B5(up) backward: transpose of the bilinear up-sampling of the layer flow
+        if (a.d_f_lo && (gFx[s] != 0.f || gFy[s] != 0.f)) {
+          if (c.lowres_direct) {
+            float* o = a.d_f_lo + (pair * L + k) * HW * 2 + (size_t)px.o00 * 2;
+            wb_atomic_add(o, gFx[s]); wb_atomic_add(o + 1, gFy[s]);
+          } else {
+            float* w = c.s_win + ((size_t)tc * WB_WIN_CAP * L + k) * 2;
+            const int st = L * 2;
+            atomicAdd(w + c00 * st, w00 * gFx[s]); atomicAdd(w + c00 * st + 1, w00 * gFy[s]);
+            atomicAdd(w + c01 * st, w01 * gFx[s]); atomicAdd(w + c01 * st + 1, w01 * gFy[s]);
+            atomicAdd(w + c10 * st, w10 * gFx[s]); atomicAdd(w + c10 * st + 1, w10 * gFy[s]);
+            atomicAdd(w + c11 * st, w11 * gFx[s]); atomicAdd(w + c11 * st + 1, w11 * gFy[s]);
+          }
+        }
+      }
+    }
+  }
+  if (c.self && a.d_input && active) {   // lvd.py:845: the target frame passes straight through
+    const float n = (1.f + 1e-6f) / D;
+    const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
+    float* o = a.d_input + ((size_t)b * g.T + tp) * C * HWd + q;
+    WB_UNROLL for (int ch = 0; ch < WB_MAX_C; ++ch)
+      if (ch < C) wb_atomic_add(o + (size_t)ch * HWd, (draw ? __ldg(draw + (size_t)ch * HWd) : 0.f) + n * gO[ch]);
+  }
+}
+
+// grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration); dynamic smem = Tc*WB_WIN_CAP*L*2 floats.
+__global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
-  const int L = g.No + 1, HW = g.H * g.W, C = g.C;
-  const size_t HWd = (size_t)g.Hd * g.Wd;
-  const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
-  const int u = (int)d.pred_ts[tp];
-  const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
-  const bool disocc_ch = (g.flags & WALDO_F_USE_DISOCC) != 0;
-  const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + (disocc_ch ? 1 : 0);
-  const bool need_layers = a.d_alpha_acc || a.d_f_lo || a.d_occ;
-  const bool lowres_direct = (g.Hd == g.H);
+  WbBwdCtx c;
+  c.L = g.No + 1; c.HW = g.H * g.W; c.C = g.C; c.HWd = (size_t)g.Hd * g.Wd;
+  const int btp = blockIdx.y;
+  c.b = btp / g.Tp; c.tp = btp - c.b * g.Tp;
+  const int u = (int)d.pred_ts[c.tp];
+  c.self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  c.disocc_ch = (g.flags & WALDO_F_USE_DISOCC) != 0;
+  c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0);
+  c.need_layers = a.d_alpha_acc || a.d_f_lo || a.d_occ;
+  c.lowres_direct = (g.Hd == g.H);
+  const int L = c.L;
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
-  __shared__ float s_win[WB_WIN_CAP * WB_MAX_L * 2];
-  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + u) * L * L + i);
+  WB_DYN_SMEM(s_win);
+  const bool use_win = a.d_f_lo && !c.lowres_direct;
+  const int win_elems = use_win ? g.Tc * WB_WIN_CAP * L * 2 : 0;
+  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + u) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
-  for (int i = wb_tid(); i < WB_WIN_CAP * WB_MAX_L * 2; i += wb_nthr()) s_win[i] = 0.f;
+  for (int i = wb_tid(); i < win_elems; i += wb_nthr()) s_win[i] = 0.f;
   __syncthreads();
-  float* s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
-  const int tiles_x = (g.Wd + WB_TILE_W - 1) / WB_TILE_W, tiles_y = (g.Hd + WB_TILE_H - 1) / WB_TILE_H;
+  c.s_occ = s_occ; c.s_win = s_win;
+  c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
+  const WbTileIter ti(g.Hd, g.Wd);
   const float rlo = (float)g.H / (float)g.Hd;
-  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
-    const int ty0 = (tile / tiles_x) * WB_TILE_H, tx0 = (tile % tiles_x) * WB_TILE_W;
+  for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
+    const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
     // low-res window of this tile
-    const int wy0 = wb_axis(ty0, rlo, g.H).i0, wy1 = wb_axis(min(ty0 + WB_TILE_H, g.Hd) - 1, rlo, g.H).i1;
-    const int wx0 = wb_axis(tx0, rlo, g.W).i0, wx1 = wb_axis(min(tx0 + WB_TILE_W, g.Wd) - 1, rlo, g.W).i1;
-    const int ww = wx1 - wx0 + 1, wcells = ww * (wy1 - wy0 + 1);
+    c.wy0 = wb_axis(ty0, rlo, g.H).i0; c.wx0 = wb_axis(tx0, rlo, g.W).i0;
+    const int wy1 = wb_axis(min(ty0 + WB_TILE_H, g.Hd) - 1, rlo, g.H).i1, wx1 = wb_axis(min(tx0 + WB_TILE_W, g.Wd) - 1, rlo, g.W).i1;
+    c.ww = wx1 - c.wx0 + 1;
+    const int wcells = c.ww * (wy1 - c.wy0 + 1);
     for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
       const int X = tx0 + (it & (WB_TILE_W - 1)), Y = ty0 + it / WB_TILE_W;
       const bool active = X < g.Wd && Y < g.Hd;
       const size_t q = active ? (size_t)Y * g.Wd + X : 0;
-      WbPix px = wb_pix(d, b, tp, q);
-      // window-relative low-res offsets
-      const int c00 = (px.ay.i0 - wy0) * ww + px.ax.i0 - wx0, c01 = (px.ay.i0 - wy0) * ww + px.ax.i1 - wx0;
-      const int c10 = (px.ay.i1 - wy0) * ww + px.ax.i0 - wx0, c11 = (px.ay.i1 - wy0) * ww + px.ax.i1 - wx0;
-      const float w00 = px.ax.l0 * px.ay.l0, w01 = px.ax.l1 * px.ay.l0, w10 = px.ax.l0 * px.ay.l1, w11 = px.ax.l1 * px.ay.l1;
-      float gO[WB_MAX_C + 1];
-      float S = 0.f;
-      {
-        const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
-        const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
-        WB_UNROLL for (int c = 0; c <= WB_MAX_C; ++c) {
-          gO[c] = 0.f;
-          if (c <= C && dof && active) { gO[c] = __ldg(dof + (size_t)c * HWd); S += gO[c] * __ldg(of + (size_t)c * HWd); }
+      WbPix px = wb_pix(d, c.b, c.tp, active ? X : 0, active ? Y : 0);
+      const unsigned wm = wb_warp_or(active ? px.isobj : 1u);
+      const int n = __popc(wm);
+      if (n <= 4) wb_bwd_pixel<4>(a, c, px, wm, active, q);
+      else if (n <= 8) wb_bwd_pixel<8>(a, c, px, wm, active, q);
+      else wb_bwd_pixel<WB_MAX_L>(a, c, px, wm, active, q);
+    }
+    if (use_win) {   // flush the windows of this tile (all contexts)
+      __syncthreads();
+      const int per_tc = wcells * L * 2;
+      for (int e = wb_tid(); e < g.Tc * per_tc; e += wb_nthr()) {
+        const int tc = e / per_tc, r0 = e - tc * per_tc;
+        const int cell = r0 / (L * 2), r = r0 - cell * (L * 2), k = r >> 1, comp = r & 1;
+        const int cy = cell / c.ww + c.wy0, cx = cell % c.ww + c.wx0;
+        float* sv = s_win + (((size_t)tc * WB_WIN_CAP + cell) * L + k) * 2 + comp;
+        const float v = *sv;
+        if (v != 0.f) {
+          const size_t pair = ((size_t)c.b * g.Tc + tc) * g.Tp + c.tp;
+          atomicAdd(a.d_f_lo + ((pair * L + k) * c.HW + (size_t)cy * g.W + cx) * 2 + comp, v);
+          *sv = 0.f;
         }
       }
-      // note: the score channel of out_full sits at index C (not WB_MAX_C) in memory and in gO[]
-      const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
-      for (int tc = 0; tc < g.Tc; ++tc) {
-        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-        const float* f_lo = d.f_lo + pair * L * HW * 2;
-        const float* alpha_c = d.alpha + ((size_t)b * g.Tw + c_t) * L * HWd;
-        WbLayers ly;
-        wb_layers_fwd(d, px, f_lo, alpha_c, s_occ, ly);
-        const float wgt = ly.score + 1e-6f, n = wgt / D;
-        const float* draw = (a.d_raw_output && active) ? a.d_raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * CR * HWd + q : nullptr;
-        // ---- stage C backward: warped context frame
-        WbTaps t = wb_taps(__fadd_rn(px.gx, ly.flow_x), __fadd_rn(px.gy, ly.flow_y), g.Wd, g.Hd);
-        const int m = wb_tap_mask(t, g.Wd, g.Hd);
-        const float* src = d.input + ((size_t)b * g.T + c_t) * C * HWd + (long long)t.y0 * g.Wd + t.x0;
-        float* din = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * C * HWd + (long long)t.y0 * g.Wd + t.x0 : nullptr;
-        float G = 0.f, gix = 0.f, giy = 0.f;
-        WB_UNROLL for (int c = 0; c < WB_MAX_C; ++c) {
-          if (c < C) {
-            const float* p = src + (size_t)c * HWd;
-            const float vnw = (m & 1) ? __ldg(p) : 0.f, vne = (m & 2) ? __ldg(p + 1) : 0.f;
-            const float vsw = (m & 4) ? __ldg(p + g.Wd) : 0.f, vse = (m & 8) ? __ldg(p + g.Wd + 1) : 0.f;
-            const float O = wb_chain(vnw, vne, vsw, vse, t);
-            const float go = (draw ? __ldg(draw + (size_t)c * HWd) : 0.f) + n * gO[c];
-            G += gO[c] * O;
-            gix += go * ((vne - vnw) * t.wy0 + (vse - vsw) * t.wy1);
-            giy += go * ((vsw - vnw) * t.wx0 + (vse - vne) * t.wx1);
-            if (din && go != 0.f) {
-              float* o = din + (size_t)c * HWd;
-              if (m & 1) wb_atomic_add(o, t.nw * go);
-              if (m & 2) wb_atomic_add(o + 1, t.ne * go);
-              if (m & 4) wb_atomic_add(o + g.Wd, t.sw * go);
-              if (m & 8) wb_atomic_add(o + g.Wd + 1, t.se * go);
-            }
-          }
-        }
-        if (!need_layers) continue;
-        G += gO[C] * (ly.score * 2.f - 1.f);
-        const float* dfl = (a.d_flow && active) ? a.d_flow + pair * 2 * HWd + q : nullptr;
-        const float dfx = (dfl ? __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
-        const float dfy = (dfl ? __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
-        const float gs = 2.f * n * gO[C] + (G - S) / D;
-        // ---- B9 / B8 backward
-        float gA[WB_MAX_L], gR[WB_MAX_L], gFx[WB_MAX_L], gFy[WB_MAX_L];
-        WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
-          if (k < L) {
-            gA[k] = gs + 2.f * (draw ? __ldg(draw + (size_t)(C + k) * HWd) : 0.f) + dfx * ly.Fx[k] + dfy * ly.Fy[k];
-            gFx[k] = ly.A[k] * dfx; gFy[k] = ly.A[k] * dfy;
-            gR[k] = 0.f;
-          }
-        }
-        wb_occlude_bwd(ly.R, gA, s_occ, L, gR, s_acc);
-        // ---- B7 backward: disocc = max_k R_k (first maximal layer takes the gradient)
-        if (disocc_ch && draw) {
-          const float gd = __ldg(draw + (size_t)(C + L) * HWd);
-          bool done = false;
-          WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k)
-            if (k < L && !done && ly.R[k] == ly.disocc) { gR[k] += gd; done = true; }
-        }
-        // ---- B6 backward: bilinear sample of the context opacity through layer k's flow
-        float* dal = a.d_alpha_acc ? a.d_alpha_acc + ((size_t)b * g.Tw + c_t) * L * HWd : nullptr;
-        WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
-          if (k < L) {
-            if (((px.isobj >> k) & 1u) && gR[k] != 0.f) {
-              WbTaps tk = wb_taps(__fadd_rn(px.gx, ly.Fx[k]), __fadd_rn(px.gy, ly.Fy[k]), g.Wd, g.Hd);
-              const int mk = wb_tap_mask(tk, g.Wd, g.Hd);
-              const long long off = (long long)k * (long long)HWd + (long long)tk.y0 * g.Wd + tk.x0;
-              const float* p = alpha_c + off;
-              const float vnw = (mk & 1) ? (__ldg(p) + 1.f) * 0.5f : 0.f, vne = (mk & 2) ? (__ldg(p + 1) + 1.f) * 0.5f : 0.f;
-              const float vsw = (mk & 4) ? (__ldg(p + g.Wd) + 1.f) * 0.5f : 0.f, vse = (mk & 8) ? (__ldg(p + g.Wd + 1) + 1.f) * 0.5f : 0.f;
-              const float gr = gR[k];
-              gFx[k] += gr * ((vne - vnw) * tk.wy0 + (vse - vsw) * tk.wy1) * (0.5f * (float)g.Wd);
-              gFy[k] += gr * ((vsw - vnw) * tk.wx0 + (vse - vne) * tk.wx1) * (0.5f * (float)g.Hd);
-              if (dal) {
-                float* o = dal + off;
-                if (mk & 1) wb_atomic_add(o, tk.nw * gr);
-                if (mk & 2) wb_atomic_add(o + 1, tk.ne * gr);
-                if (mk & 4) wb_atomic_add(o + g.Wd, tk.sw * gr);
-                if (mk & 8) wb_atomic_add(o + g.Wd + 1, tk.se * gr);
-              }
-            }
-            // ---- B5(up) backward: transpose of the bilinear up-sampling of the layer flow
-            if (a.d_f_lo) {
-              if (lowres_direct) {
-                float* o = a.d_f_lo + (pair * L + k) * HW * 2 + (size_t)px.o00 * 2;
-                wb_atomic_add(o, gFx[k]); wb_atomic_add(o + 1, gFy[k]);
-              } else {
-                float* w = s_win + (size_t)k * 2;
-                const int st = WB_MAX_L * 2;
-                if (gFx[k] != 0.f || gFy[k] != 0.f) {
-                  atomicAdd(w + c00 * st, w00 * gFx[k]); atomicAdd(w + c00 * st + 1, w00 * gFy[k]);
-                  atomicAdd(w + c01 * st, w01 * gFx[k]); atomicAdd(w + c01 * st + 1, w01 * gFy[k]);
-                  atomicAdd(w + c10 * st, w10 * gFx[k]); atomicAdd(w + c10 * st + 1, w10 * gFy[k]);
-                  atomicAdd(w + c11 * st, w11 * gFx[k]); atomicAdd(w + c11 * st + 1, w11 * gFy[k]);
-                }
-              }
-            }
-          }
-        }
-        if (a.d_f_lo && !lowres_direct) {   // flush the window of this (tile, context)
-          __syncthreads();
-          for (int e = wb_tid(); e < wcells * L * 2; e += wb_nthr()) {
-            const int cell = e / (L * 2), r = e - cell * (L * 2), k = r >> 1, comp = r & 1;
-            const int cy = cell / ww + wy0, cx = cell % ww + wx0;
-            float* sv = s_win + (size_t)cell * WB_MAX_L * 2 + k * 2 + comp;
-            const float v = *sv;
-            if (v != 0.f) { atomicAdd(a.d_f_lo + ((pair * L + k) * HW + (size_t)cy * g.W + cx) * 2 + comp, v); *sv = 0.f; }
-          }
-          __syncthreads();
-        }
-      }
-      if (self && a.d_input && active) {   // lvd.py:845: the target frame passes straight through
-        const float n = (1.f + 1e-6f) / D;
-        const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q : nullptr;
-        float* o = a.d_input + ((size_t)b * g.T + tp) * C * HWd + q;
-        WB_UNROLL for (int c = 0; c < WB_MAX_C; ++c)
-          if (c < C) wb_atomic_add(o + (size_t)c * HWd, (draw ? __ldg(draw + (size_t)c * HWd) : 0.f) + n * gO[c]);
-      }
+      __syncthreads();
     }
   }
   if (a.d_occ) {
@@ -244,134 +277,160 @@ __global__ void k_occ_reduce(const float* __restrict__ part, int groups, int per
 }
 
 // ============================================================================ context-alpha backward (B4..B2b)
+struct WbPrepBwdCtx {
+  int b, t, L, Nl, HW;
+  size_t HWd;
+  bool filt, lowres_direct, need_p;
+  const float *s_P, *s_occ, *lyt_base, *alo;
+  float *s_acc, *s_accp, *s_win;
+  int wy0, wx0, ww;
+};
+
+template <int NA>
+WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, unsigned wm, bool active, size_t q, const WbAxis& ax, const WbAxis& ay,
+                              int o00, int o01, int o10, int o11) {
+  const WbDec& d = a.f;
+  const waldo_geom_t& g = d.g;
+  const int L = c.L, Nl = c.Nl, HW = c.HW, b = c.b, t = c.t;
+  const size_t HWd = c.HWd;
+  const int lane = wb_lane();
+  const WbIdx<NA> ix = wb_idx<NA>(wm);
+  const bool any_obj = (wm >> 1) != 0u;
+  // ---- recompute the forward of this pixel
+  float sm[WB_MAX_NL];
+  if (c.filt && any_obj) wb_softmax_hd(c.lyt_base, HWd, q, Nl, sm);
+  float aup[NA], av[NA], ell[NA];
+  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+    av[s] = 0.f; aup[s] = 0.f; ell[s] = 1.f;
+    if (s < ix.n) {
+      const int k = ix.k[s];
+      const float* pl = c.alo + (size_t)k * HW;
+      float v = c.lowres_direct ? __ldg(pl + o00)
+                                : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
+      aup[s] = v;
+      if (c.filt && k >= 1) {
+        float dist = 0.f;
+        WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) if (cc < Nl) dist += fabsf(c.s_P[(k - 1) * Nl + cc] - sm[cc]);
+        ell[s] = 1.f - dist * 0.5f;
+      }
+      av[s] = v * ell[s];
+    }
+  }
+  // ---- upstream: scatter-accumulated d/dA plus the returned alpha = 2A - 1
+  float gA[NA], ga[NA];
+  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+    ga[s] = 0.f; gA[s] = 0.f;
+    if (s < ix.n && active) {
+      const size_t o = (((size_t)b * g.Tw + t) * L + ix.k[s]) * HWd + q;
+      float v = 0.f;
+      if (a.d_alpha_acc) v += a.d_alpha_acc[o];
+      if (a.d_alpha) v += 2.f * __ldg(a.d_alpha + o);
+      gA[s] = v;
+    }
+  }
+  wb_occlude_bwd<NA>(av, gA, c.s_occ, L, ix, ga, c.s_acc);
+  // ---- filter + up-sampling backward
+  float gsm[WB_MAX_NL];
+  WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) gsm[cc] = 0.f;
+  const float w00 = ax.l0 * ay.l0, w01 = ax.l1 * ay.l0, w10 = ax.l0 * ay.l1, w11 = ax.l1 * ay.l1;
+  const int c00 = (ay.i0 - c.wy0) * c.ww + ax.i0 - c.wx0, c01 = (ay.i0 - c.wy0) * c.ww + ax.i1 - c.wx0;
+  const int c10 = (ay.i1 - c.wy0) * c.ww + ax.i0 - c.wx0, c11 = (ay.i1 - c.wy0) * c.ww + ax.i1 - c.wx0;
+  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+    if (s < ix.n) {
+      const int k = ix.k[s];
+      const float gup = ga[s] * ell[s];
+      if (c.filt && k >= 1) {
+        const float gl = ga[s] * aup[s];   // d / d ell_k
+        WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) {
+          if (cc < Nl) {
+            const float df = c.s_P[(k - 1) * Nl + cc] - sm[cc];
+            const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+            const float v = -0.5f * sg * gl;
+            gsm[cc] -= v;
+            if (c.need_p) {
+              float r = wb_warp_sum(v);
+              if (lane == 0) c.s_accp[(k - 1) * Nl + cc] += r;
+            }
+          }
+        }
+      }
+      if (a.d_a_lo && gup != 0.f) {
+        if (c.lowres_direct) atomicAdd(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + o00, gup);
+        else {
+          atomicAdd(c.s_win + c00 * L + k, w00 * gup); atomicAdd(c.s_win + c01 * L + k, w01 * gup);
+          atomicAdd(c.s_win + c10 * L + k, w10 * gup); atomicAdd(c.s_win + c11 * L + k, w11 * gup);
+        }
+      }
+    }
+  }
+  if (c.filt && any_obj && a.d_input && active) {   // softmax backward into the layout logits of this frame
+    float dot = 0.f;
+    WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) if (cc < Nl) dot += gsm[cc] * sm[cc];
+    float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd + q;
+    WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc)
+      if (cc < Nl) { const float v = sm[cc] * (gsm[cc] - dot); if (v != 0.f) o[(size_t)cc * HWd] += v; }
+  }
+}
+
 // grid = (red_ctas, B*Tw), block = 256.
-__global__ void __launch_bounds__(WB_TILE_PX) k_alpha_prep_bwd(WbDecB a) {
+__global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
-  const int No = g.No, Nl = g.Nl, L = No + 1, HW = g.H * g.W;
-  const size_t HWd = (size_t)g.Hd * g.Wd;
-  const int bt = blockIdx.y, b = bt / g.Tw, t = bt - b * g.Tw;
-  const bool filt = (g.flags & WALDO_F_FILTER) != 0;
-  const bool lowres_direct = (g.Hd == g.H);
-  const bool need_p = filt && a.d_prof_p;
+  WbPrepBwdCtx c;
+  const int No = g.No, Nl = g.Nl, L = No + 1;
+  c.L = L; c.Nl = Nl; c.HW = g.H * g.W; c.HWd = (size_t)g.Hd * g.Wd;
+  const int bt = blockIdx.y;
+  c.b = bt / g.Tw; c.t = bt - c.b * g.Tw;
+  c.filt = (g.flags & WALDO_F_FILTER) != 0;
+  c.lowres_direct = (g.Hd == g.H);
+  c.need_p = c.filt && a.d_prof_p;
   __shared__ float s_P[(WB_MAX_L - 1) * WB_MAX_NL];
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
   __shared__ float s_redp[WB_NWARP][(WB_MAX_L - 1) * WB_MAX_NL];
   __shared__ float s_win[WB_WIN_CAP * WB_MAX_L];
-  if (filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)b * No * Nl + i];
-  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + t) * L * L + i);
+  if (c.filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)c.b * No * Nl + i];
+  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + c.t) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
   for (int i = wb_tid(); i < WB_NWARP * (WB_MAX_L - 1) * WB_MAX_NL; i += wb_nthr()) (&s_redp[0][0])[i] = 0.f;
   for (int i = wb_tid(); i < WB_WIN_CAP * WB_MAX_L; i += wb_nthr()) s_win[i] = 0.f;
   __syncthreads();
-  float* s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
-  float* s_accp = s_redp[wb_warp()];
-  const int lane = wb_lane();
+  c.s_P = s_P; c.s_occ = s_occ; c.s_win = s_win;
+  c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
+  c.s_accp = s_redp[wb_warp()];
   const float rlo = (float)g.H / (float)g.Hd;
-  const float* lyt_base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
-  const float* alo = d.a_lo + ((size_t)b * g.Tw + t) * L * HW;
-  const int tiles_x = (g.Wd + WB_TILE_W - 1) / WB_TILE_W, tiles_y = (g.Hd + WB_TILE_H - 1) / WB_TILE_H;
-  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
-    const int ty0 = (tile / tiles_x) * WB_TILE_H, tx0 = (tile % tiles_x) * WB_TILE_W;
-    const int wy0 = wb_axis(ty0, rlo, g.H).i0, wy1 = wb_axis(min(ty0 + WB_TILE_H, g.Hd) - 1, rlo, g.H).i1;
-    const int wx0 = wb_axis(tx0, rlo, g.W).i0, wx1 = wb_axis(min(tx0 + WB_TILE_W, g.Wd) - 1, rlo, g.W).i1;
-    const int ww = wx1 - wx0 + 1, wcells = ww * (wy1 - wy0 + 1);
+  c.lyt_base = d.input + (((size_t)c.b * g.T + c.t) * g.C + 3) * c.HWd;
+  c.alo = d.a_lo + ((size_t)c.b * g.Tw + c.t) * L * c.HW;
+  const uint32_t* live = d.live_ctx + ((size_t)c.b * g.Tw + c.t) * c.HW;
+  const WbTileIter ti(g.Hd, g.Wd);
+  for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
+    const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
+    c.wy0 = wb_axis(ty0, rlo, g.H).i0; c.wx0 = wb_axis(tx0, rlo, g.W).i0;
+    const int wy1 = wb_axis(min(ty0 + WB_TILE_H, g.Hd) - 1, rlo, g.H).i1, wx1 = wb_axis(min(tx0 + WB_TILE_W, g.Wd) - 1, rlo, g.W).i1;
+    c.ww = wx1 - c.wx0 + 1;
+    const int wcells = c.ww * (wy1 - c.wy0 + 1);
     for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
       const int X = tx0 + (it & (WB_TILE_W - 1)), Y = ty0 + it / WB_TILE_W;
       const bool active = X < g.Wd && Y < g.Hd;
       const size_t q = active ? (size_t)Y * g.Wd + X : 0;
-      // ---- recompute the forward of this pixel
-      float sm[WB_MAX_NL];
-      if (filt) {
-        float lyt[WB_MAX_NL];
-        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) lyt[c] = __ldg(lyt_base + c * HWd + q);
-        float mx = lyt[0];
-        WB_UNROLL for (int c = 1; c < WB_MAX_NL; ++c) if (c < Nl) mx = fmaxf(mx, lyt[c]);
-        float s = 0.f;
-        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) { sm[c] = expf(lyt[c] - mx); s += sm[c]; }
-        const float inv = 1.f / s;
-        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) sm[c] *= inv;
-      }
-      WbAxis ay = wb_axis(Y < g.Hd ? Y : 0, rlo, g.H), ax = wb_axis(X < g.Wd ? X : 0, rlo, g.W);
+      WbAxis ay = wb_axis(active ? Y : 0, rlo, g.H), ax = wb_axis(active ? X : 0, rlo, g.W);
       const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
-      float aup[WB_MAX_L], av[WB_MAX_L], ell[WB_MAX_L];
-      WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
-        if (k < L) {
-          const float* pl = alo + (size_t)k * HW;
-          float v = lowres_direct ? __ldg(pl + o00)
-                                  : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
-          aup[k] = v; ell[k] = 1.f;
-          if (filt && k >= 1) {
-            float dist = 0.f;
-            WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) dist += fabsf(s_P[(k - 1) * Nl + c] - sm[c]);
-            ell[k] = 1.f - dist * 0.5f;
-          }
-          av[k] = v * ell[k];
-        }
-      }
-      // ---- upstream: scatter-accumulated d/dA plus the returned alpha = 2A - 1
-      float gA[WB_MAX_L], ga[WB_MAX_L];
-      WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
-        if (k < L) {
-          float v = 0.f;
-          if (active) {
-            const size_t o = (((size_t)b * g.Tw + t) * L + k) * HWd + q;
-            if (a.d_alpha_acc) v += a.d_alpha_acc[o];
-            if (a.d_alpha) v += 2.f * __ldg(a.d_alpha + o);
-          }
-          gA[k] = v; ga[k] = 0.f;
-        }
-      }
-      wb_occlude_bwd(av, gA, s_occ, L, ga, s_acc);
-      // ---- filter + up-sampling backward
-      float gsm[WB_MAX_NL];
-      WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) gsm[c] = 0.f;
-      const float w00 = ax.l0 * ay.l0, w01 = ax.l1 * ay.l0, w10 = ax.l0 * ay.l1, w11 = ax.l1 * ay.l1;
-      const int c00 = (ay.i0 - wy0) * ww + ax.i0 - wx0, c01 = (ay.i0 - wy0) * ww + ax.i1 - wx0;
-      const int c10 = (ay.i1 - wy0) * ww + ax.i0 - wx0, c11 = (ay.i1 - wy0) * ww + ax.i1 - wx0;
-      WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
-        if (k < L) {
-          const float gup = ga[k] * ell[k];
-          if (filt && k >= 1) {
-            const float gl = ga[k] * aup[k];   // d / d ell_k
-            WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) {
-              if (c < Nl) {
-                const float df = s_P[(k - 1) * Nl + c] - sm[c];
-                const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
-                const float v = -0.5f * sg * gl;
-                gsm[c] -= v;
-                if (need_p) {
-                  float r = wb_warp_sum(v);
-                  if (lane == 0) s_accp[(k - 1) * Nl + c] += r;
-                }
-              }
-            }
-          }
-          if (a.d_a_lo) {
-            if (lowres_direct) wb_atomic_add(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + o00, gup);
-            else if (gup != 0.f) {
-              atomicAdd(s_win + c00 * WB_MAX_L + k, w00 * gup); atomicAdd(s_win + c01 * WB_MAX_L + k, w01 * gup);
-              atomicAdd(s_win + c10 * WB_MAX_L + k, w10 * gup); atomicAdd(s_win + c11 * WB_MAX_L + k, w11 * gup);
-            }
-          }
-        }
-      }
-      if (filt && a.d_input && active) {   // softmax backward into the layout logits of this frame
-        float dot = 0.f;
-        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) dot += gsm[c] * sm[c];
-        float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd + q;
-        WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) wb_atomic_add(o + (size_t)c * HWd, sm[c] * (gsm[c] - dot));
-      }
+      const unsigned mine = active ? wb_live4(live, o00, o01, o10, o11) : 0u;
+      const unsigned wm = wb_warp_or(mine);
+      const int n = __popc(wm);
+      if (n == 0) continue;   // warp-uniform: nothing live here, every gradient path is dead
+      if (n <= 4) wb_prep_bwd_pixel<4>(a, c, wm, active, q, ax, ay, o00, o01, o10, o11);
+      else if (n <= 8) wb_prep_bwd_pixel<8>(a, c, wm, active, q, ax, ay, o00, o01, o10, o11);
+      else wb_prep_bwd_pixel<WB_MAX_L>(a, c, wm, active, q, ax, ay, o00, o01, o10, o11);
     }
-    if (a.d_a_lo && !lowres_direct) {
+    if (a.d_a_lo && !c.lowres_direct) {
       __syncthreads();
       for (int e = wb_tid(); e < wcells * L; e += wb_nthr()) {
         const int cell = e / L, k = e - cell * L;
-        const int cy = cell / ww + wy0, cx = cell % ww + wx0;
-        float* sv = s_win + (size_t)cell * WB_MAX_L + k;
+        const int cy = cell / c.ww + c.wy0, cx = cell % c.ww + c.wx0;
+        float* sv = s_win + (size_t)cell * L + k;
         const float v = *sv;
-        if (v != 0.f) { atomicAdd(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + (size_t)cy * g.W + cx, v); *sv = 0.f; }
+        if (v != 0.f) { atomicAdd(a.d_a_lo + (((size_t)c.b * g.Tw + c.t) * L + k) * c.HW + (size_t)cy * g.W + cx, v); *sv = 0.f; }
       }
       __syncthreads();
     }
@@ -385,7 +444,7 @@ __global__ void __launch_bounds__(WB_TILE_PX) k_alpha_prep_bwd(WbDecB a) {
       part[e] = acc;
     }
   }
-  if (need_p) {
+  if (c.need_p) {
     float* part = a.prof_p_part + ((size_t)bt * gridDim.x + blockIdx.x) * No * Nl;
     for (int e = wb_tid(); e < No * Nl; e += wb_nthr()) {
       float acc = 0.f;
@@ -656,7 +715,14 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   }
   // 1. fused HD backward
   if (a.stages == 0 || (a.stages & 1)) {
-    WB_LAUNCH(k_warp_composite_bwd, dim3(a.red_ctas, g.B * g.Tp), dim3(WB_TILE_PX), 0, st, a);
+    const size_t win_bytes = (a.d_f_lo && g.Hd != g.H) ? (size_t)g.Tc * WB_WIN_CAP * L * 2 * sizeof(float) : 0;
+    WB_BREQ(win_bytes <= 200 * 1024, "Tc too large for the shared-memory flow window");
+#ifndef WB_HOST_EMU
+    if (win_bytes > 48 * 1024) cudaFuncSetAttribute(k_warp_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes);
+#else
+    WB_BREQ(win_bytes <= sizeof(wb_dyn_smem_buf), "emulation smem buffer too small");
+#endif
+    WB_LAUNCH(k_warp_composite_bwd, dim3(a.red_ctas, g.B * g.Tp), dim3(WB_TILE_PX), win_bytes, st, a);
     WB_BLAUNCHED();
     if (a.d_occ) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);

@@ -9,32 +9,38 @@ typedef waldo_decode_fwd_t WbDec;
 WB_DEV int wb_L(const waldo_geom_t& g) { return g.No + 1; }
 
 // ------------------------------------------------------------------ B1: project opacities (lvd.py:723-728)
-// a_lo[b,t,k,p] = bil0((alpha_k+1)/2, src_grid_k[b,t,p]); k = 0 background, k >= 1 objects.
+// a_lo[b,t,k,p] = bil0((alpha_k+1)/2, src_grid_k[b,t,p]); k = 0 background, k >= 1 objects.  One thread per low-res
+// cell walks the layers and also records which of them have any in-range tap there (live_ctx): everywhere else the
+// layer's opacity AND every gradient path through it are exactly zero, which the HD kernels use to skip layers.
 __global__ void k_project_alpha(WbDec d) {
   const waldo_geom_t g = d.g;
   const int L = wb_L(g), HW = g.H * g.W;
-  const long long total = (long long)g.B * g.Tw * L * HW;
+  const long long total = (long long)g.B * g.Tw * HW;
   for (long long e = (long long)blockIdx.x * wb_nthr() + wb_tid(); e < total; e += (long long)gridDim.x * wb_nthr()) {
     int p = (int)(e % HW);
-    int k = (int)((e / HW) % L);
-    int t = (int)((e / ((long long)HW * L)) % g.Tw);
-    int b = (int)(e / ((long long)HW * L * g.Tw));
-    const float* sg; const float* plane; int w, h;
-    if (k == 0) {
-      sg = d.src_grid_bg + (((size_t)b * g.T + t) * HW + p) * 2;
-      plane = d.bg_alpha + (size_t)b * HW; w = g.W; h = g.H;
-    } else {
-      sg = d.src_grid_obj + ((((size_t)b * g.T + t) * g.No + (k - 1)) * HW + p) * 2;
-      plane = d.obj_alpha + ((size_t)b * g.No + (k - 1)) * g.Ho * g.Wo; w = g.Wo; h = g.Ho;
+    int t = (int)((e / HW) % g.Tw);
+    int b = (int)(e / ((long long)HW * g.Tw));
+    unsigned live = 0u;
+    for (int k = 0; k < L; ++k) {
+      const float* sg; const float* plane; int w, h;
+      if (k == 0) {
+        sg = d.src_grid_bg + (((size_t)b * g.T + t) * HW + p) * 2;
+        plane = d.bg_alpha + (size_t)b * HW; w = g.W; h = g.H;
+      } else {
+        sg = d.src_grid_obj + ((((size_t)b * g.T + t) * g.No + (k - 1)) * HW + p) * 2;
+        plane = d.obj_alpha + ((size_t)b * g.No + (k - 1)) * g.Ho * g.Wo; w = g.Wo; h = g.Ho;
+      }
+      WbTaps tp = wb_taps(__ldg(sg), __ldg(sg + 1), w, h);
+      int m = wb_tap_mask(tp, w, h);
+      if (m) live |= 1u << k;
+      const float* q = plane + (long long)tp.y0 * w + tp.x0;
+      float vnw = (m & 1) ? (__ldg(q) + 1.f) * 0.5f : 0.f;
+      float vne = (m & 2) ? (__ldg(q + 1) + 1.f) * 0.5f : 0.f;
+      float vsw = (m & 4) ? (__ldg(q + w) + 1.f) * 0.5f : 0.f;
+      float vse = (m & 8) ? (__ldg(q + w + 1) + 1.f) * 0.5f : 0.f;
+      d.a_lo[(((size_t)b * g.Tw + t) * L + k) * HW + p] = wb_chain(vnw, vne, vsw, vse, tp);
     }
-    WbTaps tp = wb_taps(__ldg(sg), __ldg(sg + 1), w, h);
-    int m = wb_tap_mask(tp, w, h);
-    const float* q = plane + (long long)tp.y0 * w + tp.x0;
-    float vnw = (m & 1) ? (__ldg(q) + 1.f) * 0.5f : 0.f;
-    float vne = (m & 2) ? (__ldg(q + 1) + 1.f) * 0.5f : 0.f;
-    float vsw = (m & 4) ? (__ldg(q + w) + 1.f) * 0.5f : 0.f;
-    float vse = (m & 8) ? (__ldg(q + w + 1) + 1.f) * 0.5f : 0.f;
-    d.a_lo[e] = wb_chain(vnw, vne, vsw, vse, tp);
+    d.live_ctx[e] = live;
   }
 }
 
@@ -145,114 +151,182 @@ __global__ void k_profile_final(WbDec d) {
 }
 
 // ------------------------------------------------------------------ B2b-B4: context opacity at HD (lvd.py:744-765)
-// One thread per HD pixel of one (b,t); grid = (pixel chunks, B*Tw).
+// One thread per HD pixel of one (b,t), 32x8 pixel tiles; grid = (CTAs, B*Tw).
 //   l_k   = 1 - 0.5 * sum_c |P[b,k,c] - softmax(hd_lyt)[c]|
 //   a_k   = up(a_lo[k]) * (k >= 1 ? l_k : 1)
 //   A_i   = a_i * prod_j (1 - a_j * occ[b,t,j,i]);     alpha = 2A - 1
-__global__ void __launch_bounds__(256) k_alpha_prep(WbDec d) {
+// Layers that are dead at all four low-res taps of a pixel (live_ctx) have a_k == 0 exactly: their factors are exactly
+// 1 and their output exactly -1, so the loops run over the warp-wide union of live layers only (bit-identical result).
+#define WB_TILE_W 32
+#define WB_TILE_H 8
+#define WB_TILE_PX (WB_TILE_W * WB_TILE_H)
+
+struct WbTileIter {
+  int tiles_x, ntiles;
+  __device__ WbTileIter(int Hd, int Wd) { tiles_x = (Wd + WB_TILE_W - 1) / WB_TILE_W; ntiles = tiles_x * ((Hd + WB_TILE_H - 1) / WB_TILE_H); }
+};
+
+WB_DEV unsigned wb_live4(const uint32_t* __restrict__ live, int o00, int o01, int o10, int o11) {
+  return __ldg(live + o00) | __ldg(live + o01) | __ldg(live + o10) | __ldg(live + o11);
+}
+
+// compact slot list of the layers in a (warp-uniform) mask, ascending
+template <int NA> struct WbIdx { int k[NA]; int n; };
+template <int NA> WB_DEV WbIdx<NA> wb_idx(unsigned wm) {
+  WbIdx<NA> r;
+  r.n = __popc(wm);
+  unsigned m = wm;
+  WB_UNROLL_NA for (int s = 0; s < NA; ++s) { r.k[s] = m ? __ffs((int)m) - 1 : 0; m &= m - 1u; }
+  return r;
+}
+
+struct WbPrepCtx {
+  int b, t, L, Nl, HW;
+  size_t HWd;
+  bool filt;
+  const float *s_P, *s_occ, *lyt_base, *alo;
+  float* out;
+};
+
+// softmax of the HD layout logits of pixel q (lvd.py:744)
+WB_DEV void wb_softmax_hd(const float* __restrict__ lyt_base, size_t HWd, size_t q, int Nl, float* sm) {
+  float lyt[WB_MAX_NL];
+  WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) lyt[c] = __ldg(lyt_base + c * HWd + q);
+  float mx = lyt[0];
+  WB_UNROLL for (int c = 1; c < WB_MAX_NL; ++c) if (c < Nl) mx = fmaxf(mx, lyt[c]);
+  float s = 0.f;
+  WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) { sm[c] = expf(lyt[c] - mx); s += sm[c]; }
+  const float inv = 1.f / s;
+  WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) sm[c] *= inv;
+}
+
+template <int NA>
+WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, bool active, size_t q, const WbAxis& ax, const WbAxis& ay,
+                          int o00, int o01, int o10, int o11) {
+  const waldo_geom_t& g = d.g;
+  const int L = c.L, Nl = c.Nl;
+  const WbIdx<NA> ix = wb_idx<NA>(wm);
+  float sm[WB_MAX_NL];
+  if (c.filt && (wm >> 1)) wb_softmax_hd(c.lyt_base, c.HWd, q, Nl, sm);
+  float a[NA];
+  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+    a[s] = 0.f;
+    if (s < ix.n) {
+      const int k = ix.k[s];
+      const float* pl = c.alo + (size_t)k * c.HW;
+      float v = (g.Hd == g.H) ? __ldg(pl + o00)
+                              : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
+      if (c.filt && k >= 1) {
+        float dist = 0.f;
+        WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) if (cc < Nl) dist += fabsf(c.s_P[(k - 1) * Nl + cc] - sm[cc]);
+        v *= 1.f - dist * 0.5f;
+      }
+      a[s] = v;
+    }
+  }
+  if (!active) return;
+  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) if (k < L && !((wm >> k) & 1u)) c.out[(size_t)k * c.HWd + q] = -1.f;
+  WB_UNROLL_NA for (int i = 0; i < NA; ++i) {
+    if (i < ix.n) {
+      float vis = 1.f;
+      WB_UNROLL_NA for (int j = 0; j < NA; ++j) if (j < ix.n) vis *= 1.f - a[j] * c.s_occ[ix.k[j] * L + ix.k[i]];
+      c.out[(size_t)ix.k[i] * c.HWd + q] = (vis * a[i]) * 2.f - 1.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep(WbDec d) {
   const waldo_geom_t g = d.g;
-  const int No = g.No, Nl = g.Nl, L = No + 1, HW = g.H * g.W;
-  const size_t HWd = (size_t)g.Hd * g.Wd;
-  const int bt = blockIdx.y, b = bt / g.Tw, t = bt - b * g.Tw;
-  const bool filt = (g.flags & WALDO_F_FILTER) != 0;
+  WbPrepCtx c;
+  c.L = g.No + 1; c.Nl = g.Nl; c.HW = g.H * g.W; c.HWd = (size_t)g.Hd * g.Wd;
+  const int bt = blockIdx.y;
+  c.b = bt / g.Tw; c.t = bt - c.b * g.Tw;
+  c.filt = (g.flags & WALDO_F_FILTER) != 0;
   __shared__ float s_P[(WB_MAX_L - 1) * WB_MAX_NL];
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
-  if (filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)b * No * Nl + i];
-  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + t) * L * L + i);
+  if (c.filt) for (int i = wb_tid(); i < g.No * g.Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)c.b * g.No * g.Nl + i];
+  for (int i = wb_tid(); i < c.L * c.L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + c.t) * c.L * c.L + i);
   __syncthreads();
+  c.s_P = s_P; c.s_occ = s_occ;
   const float r = (float)g.H / (float)g.Hd;   // 1 / scale_hd
-  const float* lyt_base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
-  const float* alo = d.a_lo + ((size_t)b * g.Tw + t) * L * HW;
-  float* out = d.alpha + ((size_t)b * g.Tw + t) * L * HWd;
-  for (size_t q = (size_t)blockIdx.x * wb_nthr() + wb_tid(); q < HWd; q += (size_t)gridDim.x * wb_nthr()) {
-    int Y = (int)(q / g.Wd), X = (int)(q - (size_t)Y * g.Wd);
-    float sm[WB_MAX_NL];
-    if (filt) {
-      float lyt[WB_MAX_NL];
-      WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) lyt[c] = __ldg(lyt_base + c * HWd + q);
-      float mx = lyt[0];
-      WB_UNROLL for (int c = 1; c < WB_MAX_NL; ++c) if (c < Nl) mx = fmaxf(mx, lyt[c]);
-      float s = 0.f;
-      WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) { sm[c] = expf(lyt[c] - mx); s += sm[c]; }
-      float inv = 1.f / s;
-      WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) sm[c] *= inv;
-    }
-    WbAxis ay = wb_axis(Y, r, g.H), ax = wb_axis(X, r, g.W);
-    int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
-    float a[WB_MAX_L];
-    WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) {
-      if (k < L) {
-        const float* pl = alo + (size_t)k * HW;
-        float v = (g.Hd == g.H) ? __ldg(pl + o00)
-                                : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
-        if (filt && k >= 1) {
-          float dist = 0.f;
-          WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) dist += fabsf(s_P[(k - 1) * Nl + c] - sm[c]);
-          v *= 1.f - dist * 0.5f;
-        }
-        a[k] = v;
-      }
-    }
-    WB_UNROLL for (int i = 0; i < WB_MAX_L; ++i) {
-      if (i < L) {
-        float vis = 1.f;
-        WB_UNROLL for (int j = 0; j < WB_MAX_L; ++j) if (j < L) vis *= 1.f - a[j] * s_occ[j * L + i];
-        out[(size_t)i * HWd + q] = (vis * a[i]) * 2.f - 1.f;
-      }
+  c.lyt_base = d.input + (((size_t)c.b * g.T + c.t) * g.C + 3) * c.HWd;
+  c.alo = d.a_lo + ((size_t)c.b * g.Tw + c.t) * c.L * c.HW;
+  const uint32_t* live = d.live_ctx + ((size_t)c.b * g.Tw + c.t) * c.HW;
+  c.out = d.alpha + ((size_t)c.b * g.Tw + c.t) * c.L * c.HWd;
+  const WbTileIter ti(g.Hd, g.Wd);
+  for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
+    const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
+    for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
+      const int X = tx0 + (it & (WB_TILE_W - 1)), Y = ty0 + it / WB_TILE_W;
+      const bool active = X < g.Wd && Y < g.Hd;
+      const size_t q = active ? (size_t)Y * g.Wd + X : 0;
+      WbAxis ay = wb_axis(active ? Y : 0, r, g.H), ax = wb_axis(active ? X : 0, r, g.W);
+      const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
+      const unsigned mine = active ? wb_live4(live, o00, o01, o10, o11) : 0u;
+      const unsigned wm = wb_warp_or(mine);
+      const int n = __popc(wm);
+      if (n <= 4) wb_prep_pixel<4>(d, c, wm, active, q, ax, ay, o00, o01, o10, o11);
+      else if (n <= 8) wb_prep_pixel<8>(d, c, wm, active, q, ax, ay, o00, o01, o10, o11);
+      else wb_prep_pixel<WB_MAX_L>(d, c, wm, active, q, ax, ay, o00, o01, o10, o11);
     }
   }
 }
 
 // ------------------------------------------------------------------ B5: per-layer flow on the low-res lattice (lvd.py:771-792)
-// One thread per (b,tp,k,p): bilinear taps of src_grid[b,u,k,p] in the layer's canonical frame are shared by all Tc
-// contexts; value sampled = tgt_grid[b,c,k] - tgt_grid[b,u,k].  Also the object support s_lo = bil0(1) (lvd.py:788).
+// One thread per (b,tp,p) walks the layers: the bilinear taps of src_grid[b,u,k,p] in the layer's canonical frame are
+// shared by all Tc contexts; value sampled = tgt_grid[b,c,k] - tgt_grid[b,u,k].  Also the object support
+// s_lo = bil0(1) (lvd.py:788) and the live-layer mask of the target frame.
 __global__ void k_layer_flow_lo(WbDec d) {
   const waldo_geom_t g = d.g;
   const int L = wb_L(g), HW = g.H * g.W;
-  const long long total = (long long)g.B * g.Tp * L * HW;
+  const long long total = (long long)g.B * g.Tp * HW;
   for (long long e = (long long)blockIdx.x * wb_nthr() + wb_tid(); e < total; e += (long long)gridDim.x * wb_nthr()) {
     int p = (int)(e % HW);
-    int k = (int)((e / HW) % L);
-    int tp = (int)((e / ((long long)HW * L)) % g.Tp);
-    int b = (int)(e / ((long long)HW * L * g.Tp));
+    int tp = (int)((e / HW) % g.Tp);
+    int b = (int)(e / ((long long)HW * g.Tp));
     int u = (int)d.pred_ts[tp];
-    const float* sg; const float* tg_u; int w, h; size_t frame_stride, layer_off;
-    if (k == 0) {
-      w = g.W; h = g.H; frame_stride = (size_t)HW * 2; layer_off = 0;
-      sg = d.src_grid_bg + (((size_t)b * g.T + u) * HW + p) * 2;
-      tg_u = d.tgt_grid_bg + ((size_t)b * g.T + u) * frame_stride;
-    } else {
-      w = g.Wo; h = g.Ho; frame_stride = (size_t)g.No * g.Ho * g.Wo * 2; layer_off = (size_t)(k - 1) * g.Ho * g.Wo * 2;
-      sg = d.src_grid_obj + ((((size_t)b * g.T + u) * g.No + (k - 1)) * HW + p) * 2;
-      tg_u = d.tgt_grid_obj + ((size_t)b * g.T + u) * frame_stride + layer_off;
-    }
-    const float* tg_b = (k == 0 ? d.tgt_grid_bg : d.tgt_grid_obj) + (size_t)b * g.T * frame_stride + layer_off;
-    WbTaps t = wb_taps(__ldg(sg), __ldg(sg + 1), w, h);
-    int m = wb_tap_mask(t, w, h);
-    long long o = ((long long)t.y0 * w + t.x0) * 2;
-    float un[4][2];
-    WB_UNROLL for (int c = 0; c < 2; ++c) {
-      un[0][c] = (m & 1) ? __ldg(tg_u + o + c) : 0.f;
-      un[1][c] = (m & 2) ? __ldg(tg_u + o + 2 + c) : 0.f;
-      un[2][c] = (m & 4) ? __ldg(tg_u + o + 2 * w + c) : 0.f;
-      un[3][c] = (m & 8) ? __ldg(tg_u + o + 2 * w + 2 + c) : 0.f;
-    }
-    if (k >= 1 && d.s_lo)
-      d.s_lo[(((size_t)b * g.Tp + tp) * g.No + (k - 1)) * HW + p] =
-          wb_chain((m & 1) ? 1.f : 0.f, (m & 2) ? 1.f : 0.f, (m & 4) ? 1.f : 0.f, (m & 8) ? 1.f : 0.f, t);
-    for (int tc = 0; tc < g.Tc; ++tc) {
-      int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-      const float* tg_c = tg_b + (size_t)c_t * frame_stride;
-      float f[2];
-      WB_UNROLL for (int c = 0; c < 2; ++c) {
-        float vnw = (m & 1) ? __fsub_rn(__ldg(tg_c + o + c), un[0][c]) : 0.f;
-        float vne = (m & 2) ? __fsub_rn(__ldg(tg_c + o + 2 + c), un[1][c]) : 0.f;
-        float vsw = (m & 4) ? __fsub_rn(__ldg(tg_c + o + 2 * w + c), un[2][c]) : 0.f;
-        float vse = (m & 8) ? __fsub_rn(__ldg(tg_c + o + 2 * w + 2 + c), un[3][c]) : 0.f;
-        f[c] = wb_chain(vnw, vne, vsw, vse, t);
+    unsigned live = 1u;
+    for (int k = 0; k < L; ++k) {
+      const float* sg; const float* tg_u; int w, h; size_t frame_stride, layer_off;
+      if (k == 0) {
+        w = g.W; h = g.H; frame_stride = (size_t)HW * 2; layer_off = 0;
+        sg = d.src_grid_bg + (((size_t)b * g.T + u) * HW + p) * 2;
+        tg_u = d.tgt_grid_bg + ((size_t)b * g.T + u) * frame_stride;
+      } else {
+        w = g.Wo; h = g.Ho; frame_stride = (size_t)g.No * g.Ho * g.Wo * 2; layer_off = (size_t)(k - 1) * g.Ho * g.Wo * 2;
+        sg = d.src_grid_obj + ((((size_t)b * g.T + u) * g.No + (k - 1)) * HW + p) * 2;
+        tg_u = d.tgt_grid_obj + ((size_t)b * g.T + u) * frame_stride + layer_off;
       }
-      float* out = d.f_lo + (((((size_t)b * g.Tc + tc) * g.Tp + tp) * L + k) * HW + p) * 2;
-      out[0] = f[0]; out[1] = f[1];
+      const float* tg_b = (k == 0 ? d.tgt_grid_bg : d.tgt_grid_obj) + (size_t)b * g.T * frame_stride + layer_off;
+      WbTaps t = wb_taps(__ldg(sg), __ldg(sg + 1), w, h);
+      int m = wb_tap_mask(t, w, h);
+      if (m) live |= 1u << k;
+      long long o = ((long long)t.y0 * w + t.x0) * 2;
+      float un[4][2];
+      WB_UNROLL for (int c = 0; c < 2; ++c) {
+        un[0][c] = (m & 1) ? __ldg(tg_u + o + c) : 0.f;
+        un[1][c] = (m & 2) ? __ldg(tg_u + o + 2 + c) : 0.f;
+        un[2][c] = (m & 4) ? __ldg(tg_u + o + 2 * w + c) : 0.f;
+        un[3][c] = (m & 8) ? __ldg(tg_u + o + 2 * w + 2 + c) : 0.f;
+      }
+      if (k >= 1 && d.s_lo)
+        d.s_lo[(((size_t)b * g.Tp + tp) * g.No + (k - 1)) * HW + p] =
+            wb_chain((m & 1) ? 1.f : 0.f, (m & 2) ? 1.f : 0.f, (m & 4) ? 1.f : 0.f, (m & 8) ? 1.f : 0.f, t);
+      for (int tc = 0; tc < g.Tc; ++tc) {
+        int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+        const float* tg_c = tg_b + (size_t)c_t * frame_stride;
+        float f[2];
+        WB_UNROLL for (int c = 0; c < 2; ++c) {
+          float vnw = (m & 1) ? __fsub_rn(__ldg(tg_c + o + c), un[0][c]) : 0.f;
+          float vne = (m & 2) ? __fsub_rn(__ldg(tg_c + o + 2 + c), un[1][c]) : 0.f;
+          float vsw = (m & 4) ? __fsub_rn(__ldg(tg_c + o + 2 * w + c), un[2][c]) : 0.f;
+          float vse = (m & 8) ? __fsub_rn(__ldg(tg_c + o + 2 * w + 2 + c), un[3][c]) : 0.f;
+          f[c] = wb_chain(vnw, vne, vsw, vse, t);
+        }
+        float* out = d.f_lo + (((((size_t)b * g.Tc + tc) * g.Tp + tp) * L + k) * HW + p) * 2;
+        out[0] = f[0]; out[1] = f[1];
+      }
     }
+    d.live_pred[e] = live;
   }
 }

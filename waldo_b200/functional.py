@@ -254,6 +254,8 @@ class _Decode(torch.autograd.Function):
         prof_p = torch.empty(B, spec.num_obj, Nl, **f32)
         f_lo = torch.empty(B, Tc, Tp, Lr, spec.H, spec.W, 2, **f32)
         s_lo = torch.empty(B, Tp, spec.num_obj, spec.H, spec.W, **f32)
+        live_ctx = torch.empty(B, g.Tw, spec.H, spec.W, device=dev, dtype=torch.int32)
+        live_pred = torch.empty(B, Tp, spec.H, spec.W, device=dev, dtype=torch.int32)
         alpha = torch.empty(B, g.Tw, Lr, Hd, Wd, **f32)
         flow = torch.empty(B, Tc, Tp, 2, Hd, Wd, **f32)
         raw = torch.empty(B, TcR, Tp, CR, Hd, Wd, **f32)
@@ -262,12 +264,12 @@ class _Decode(torch.autograd.Function):
         a = L.DecodeFwd(g, L.ptr(inp_c, name="input"), L.ptr(tgo_c), L.ptr(sgo_c), L.ptr(tgb_c), L.ptr(sgb_c), L.ptr(occ_c),
                         L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
                         L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
-                        L.ptr(prof_p), L.ptr(f_lo), L.ptr(s_lo), L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full),
+                        L.ptr(prof_p), L.ptr(f_lo), L.ptr(s_lo), L.ptr(live_ctx, torch.int32), L.ptr(live_pred, torch.int32), L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full),
                         L.ptr(norm), 0)
         _staged(lib.waldo_decode_fwd, a, L.stream_of(inp_c), "decode_fwd", main_bit=2, dev=dev)
         ctx.spec, ctx.has_cls = spec, cls is not None
         ctx.keep = (a, inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
-                    prof_sum, prof_p, f_lo, s_lo, alpha, flow, raw, out_full, norm)
+                    prof_sum, prof_p, f_lo, s_lo, alpha, flow, raw, out_full, norm, live_ctx, live_pred)
         ctx.shapes = dict(obj_alpha=obj_alpha.shape, bg_alpha=bg_alpha.shape)
         return out_full, raw, flow, alpha
 
