@@ -37,6 +37,11 @@ CASES = {
                       patch_size=8, num_lyt=4, restrict_to_ctx=False, include_self=True), 2, 3, 1, True),
     "cls_plain": (dict(dim=16, load_dim=32, aspect_ratio=2.0, num_obj=2, obj_shape=(2, 2), latent_shape=(2, 4),
                        patch_size=8, num_lyt=3, weight_cls=False, use_disocc=True), 1, 3, 2, False),
+    # the real channel counts (Cityscapes C = 3+20, KITTI C = 3+19): the compile-time-specialised channel loops
+    "c23_x4": (dict(dim=8, load_dim=32, aspect_ratio=2.0, num_obj=3, obj_shape=(2, 2), latent_shape=(2, 4),
+                    patch_size=8, num_lyt=20), 1, 3, 2, True),
+    "c22_x2": (dict(dim=8, load_dim=16, aspect_ratio=3.25, num_obj=3, obj_shape=(2, 2), latent_shape=(2, 6),
+                    patch_size=8, num_lyt=19), 1, 3, 2, False),
     # 11 heavily overlapping layers: exercises the dense (> 8 live layers per warp) code path of the HD kernels
     "many_obj": (dict(dim=16, load_dim=32, aspect_ratio=2.0, num_obj=10, obj_shape=(2, 2), latent_shape=(2, 4),
                       patch_size=8, num_lyt=3), 1, 3, 2, True),

@@ -28,7 +28,7 @@ import waldo_oracle as wo  # noqa: E402
 import waldo_b200 as wb  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["city_x4", "kitti_x2", "train_lo", "cls_plain", "many_obj"]
+CASES = ["city_x4", "kitti_x2", "train_lo", "cls_plain", "many_obj", "c23_x4", "c22_x2"]
 OUT_NAMES = ["output", "flow", "alpha_unflt", "alpha", "raw_alpha", "raw_output", "alpha_ctx"]
 
 FWD_TOL = 1e-5

@@ -128,7 +128,7 @@ static int wb_check_geom(const waldo_geom_t& g, const char* who) {
   WB_REQUIRE(g.No >= 1 && g.No + 1 <= WB_MAX_L, "%s: num_obj=%d unsupported (compiled max %d)", who, g.No, WB_MAX_L - 1);
   WB_REQUIRE(g.Nl >= 1 && g.Nl <= WB_MAX_NL, "%s: num_lyt=%d unsupported (compiled max %d)", who, g.Nl, WB_MAX_NL);
   WB_REQUIRE(g.C == 3 + g.Nl && g.C <= WB_MAX_C, "%s: C=%d must equal 3+num_lyt and be <= %d", who, g.C, WB_MAX_C);
-  WB_REQUIRE(g.H > 0 && g.W > 0 && g.Hd >= g.H && g.Wd >= g.W && g.Ho > 0 && g.Wo > 0, "%s: bad spatial sizes", who);
+  WB_REQUIRE(g.H > 1 && g.W > 1 && g.Hd >= g.H && g.Wd >= g.W && g.Ho > 1 && g.Wo > 1, "%s: bad spatial sizes", who);
   WB_REQUIRE((long long)g.Hd * g.W == (long long)g.H * g.Wd, "%s: HD and low-res aspect differ", who);
   WB_REQUIRE((long long)g.Hd * g.Wd < (1ll << 30), "%s: frame too large for 32-bit pixel indices", who);
   if (g.flags & WALDO_F_RESTRICT_CTX) WB_REQUIRE(g.flags & WALDO_F_FILTER, "%s: restrict_to_ctx implies the filter", who);
@@ -178,7 +178,10 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   }
   // B5(up)-B9 + stage C
   if (st_main) {
-    WB_LAUNCH(k_warp_composite_fwd, dim3(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tp), dim3(WB_TILE_PX), 0, st, *a);
+    const dim3 grid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tp);
+    if (g.C == 23) WB_LAUNCH(k_warp_composite_fwd<23>, grid, dim3(WB_TILE_PX), 0, st, *a);        // Cityscapes: 3 + 20
+    else if (g.C == 22) WB_LAUNCH(k_warp_composite_fwd<22>, grid, dim3(WB_TILE_PX), 0, st, *a);   // KITTI: 3 + 19
+    else WB_LAUNCH(k_warp_composite_fwd<0>, grid, dim3(WB_TILE_PX), 0, st, *a);
     WB_LAUNCHED();
   }
   return 0;

@@ -172,6 +172,48 @@ WB_DEV float wb_sample(const float* __restrict__ plane, const WbTaps& t, int m, 
   return wb_chain(vnw, vne, vsw, vse, t);
 }
 
+// Branch-free form of the four taps.  Two row offsets (rows clamped into the plane, column xL = clamp(x0, 0, W-2)), the
+// loads are p0[0], p0[1], p1[0], p1[1]; each tap's validity and weight are folded into four POSITIONAL weights
+// (an out-of-range tap gets weight 0 instead of value 0).  Accumulated in position order this is the ATen chain
+// nw -> ne -> sw -> se with exact zeros inserted, i.e. the same rounding sequence.  Needs W >= 2.
+struct WbTap2 {
+  unsigned o0, o1;   // element offsets of (row0, xL) and (row1, xL) inside one H x W plane
+  float w[4];        // positional weights: (row0,L) (row0,R) (row1,L) (row1,R)
+  int sel;           // where the tap columns sit: 0 x0 == xL (interior) / 1 x0 == -1 / 2 x0 == W-1 / 3 none in range
+  int vy;            // bit 0: row y0 in range, bit 1: row y0+1 in range
+};
+// move four per-tap coefficients (nw, ne, sw, se) to positions, zeroing out-of-range taps
+WB_DEV void wb_pos4(const WbTap2& a, float c_nw, float c_ne, float c_sw, float c_se, float* o) {
+  const float r0 = (a.vy & 1) ? 1.f : 0.f, r1 = (a.vy & 2) ? 1.f : 0.f;
+  float l0, rr0, l1, rr1;
+  if (a.sel == 0) { l0 = c_nw; rr0 = c_ne; l1 = c_sw; rr1 = c_se; }
+  else if (a.sel == 1) { l0 = c_ne; rr0 = 0.f; l1 = c_se; rr1 = 0.f; }
+  else if (a.sel == 2) { l0 = 0.f; rr0 = c_nw; l1 = 0.f; rr1 = c_sw; }
+  else { l0 = rr0 = l1 = rr1 = 0.f; }
+  o[0] = l0 * r0; o[1] = rr0 * r0; o[2] = l1 * r1; o[3] = rr1 * r1;
+}
+WB_DEV WbTap2 wb_tap2(const WbTaps& t, int W, int H) {
+  WbTap2 a;
+  const int x0 = t.x0;
+  const int xL = min(max(x0, 0), W - 2);
+  a.sel = (x0 == xL) ? 0 : (x0 == -1 ? 1 : (x0 == W - 1 ? 2 : 3));
+  a.vy = ((t.y0 >= 0 && t.y0 <= H - 1) ? 1 : 0) | ((t.y0 + 1 >= 0 && t.y0 + 1 <= H - 1) ? 2 : 0);
+  const int y0 = min(max(t.y0, 0), H - 1), y1 = min(max(t.y0 + 1, 0), H - 1);
+  a.o0 = (unsigned)(y0 * W + xL); a.o1 = (unsigned)(y1 * W + xL);
+  wb_pos4(a, t.nw, t.ne, t.sw, t.se, a.w);
+  return a;
+}
+// bilinear value through precomputed taps; p0 / p1 point at (row0, xL) / (row1, xL) of the plane
+WB_DEV float wb_gather2(const float* __restrict__ p0, const float* __restrict__ p1, const float* w) {
+  return __fmaf_rn(__ldg(p1 + 1), w[3], __fmaf_rn(__ldg(p1), w[2], __fmaf_rn(__ldg(p0 + 1), w[1], __fmul_rn(__ldg(p0), w[0]))));
+}
+// same for a plane that stores 2A-1 while the sampled quantity is A (zero padding applies to A)
+WB_DEV float wb_gather2_01(const float* __restrict__ p0, const float* __restrict__ p1, const float* w) {
+  const float v0 = (__ldg(p0) + 1.f) * 0.5f, v1 = (__ldg(p0 + 1) + 1.f) * 0.5f;
+  const float v2 = (__ldg(p1) + 1.f) * 0.5f, v3 = (__ldg(p1 + 1) + 1.f) * 0.5f;
+  return __fmaf_rn(v3, w[3], __fmaf_rn(v2, w[2], __fmaf_rn(v1, w[1], __fmul_rn(v0, w[0]))));
+}
+
 // upsample_bilinear2d (align_corners=False) source coordinates along one axis, ATen association:
 // src = max(r*(dst+0.5)-0.5, 0); i0 = int(src); i1 = min(i0+1, n-1); l1 = src-i0; l0 = 1-l1.
 struct WbAxis { int i0, i1; float l0, l1; };

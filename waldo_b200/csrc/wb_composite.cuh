@@ -52,13 +52,14 @@ template <int NA> struct WbLay {
   float flow_x, flow_y, score, disocc;
 };
 
-// alpha_c = stored context alpha (2A-1) of frame (b,c): (L, Hd, Wd)
+// alpha_c = stored context alpha (2A-1) of frame (b,c): (L, Hd, Wd).  All per-thread addressing is 32-bit element
+// offsets against warp-uniform 64-bit bases (a frame never exceeds 2^31 elements).
 template <int NA>
 WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, const float* __restrict__ f_lo /* (L,H,W,2) of this pair */,
                           const float* __restrict__ alpha_c, const float* __restrict__ s_occ, WbLay<NA>& ly) {
   const waldo_geom_t& g = d.g;
-  const int L = g.No + 1, HW = g.H * g.W;
-  const size_t HWd = (size_t)g.Hd * g.Wd;
+  const int L = g.No + 1;
+  const unsigned HW = (unsigned)(g.H * g.W), HWd = (unsigned)(g.Hd * g.Wd);
   float mx = 0.f;   // layers outside the union have R = 0, and R >= 0 always
   WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
     ly.R[s] = 0.f; ly.A[s] = 0.f; ly.Fx[s] = 0.f; ly.Fy[s] = 0.f;
@@ -75,15 +76,10 @@ WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, 
       ly.Fx[s] = fx; ly.Fy[s] = fy;
       float r = 0.f;
       if ((px.isobj >> k) & 1u) {
-        WbTaps t = wb_taps(__fadd_rn(px.gx, fx), __fadd_rn(px.gy, fy), g.Wd, g.Hd);
-        int m = wb_tap_mask(t, g.Wd, g.Hd);
-        const float* p = alpha_c + (size_t)k * HWd + (long long)t.y0 * g.Wd + t.x0;
-        // stored value is 2A-1; zero padding applies to A, so out-of-range taps contribute 0
-        float vnw = (m & 1) ? (__ldg(p) + 1.f) * 0.5f : 0.f;
-        float vne = (m & 2) ? (__ldg(p + 1) + 1.f) * 0.5f : 0.f;
-        float vsw = (m & 4) ? (__ldg(p + g.Wd) + 1.f) * 0.5f : 0.f;
-        float vse = (m & 8) ? (__ldg(p + g.Wd + 1) + 1.f) * 0.5f : 0.f;
-        r = wb_chain(vnw, vne, vsw, vse, t);
+        const WbTaps t = wb_taps(__fadd_rn(px.gx, fx), __fadd_rn(px.gy, fy), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        const float* pl = alpha_c + (size_t)k * HWd;
+        r = wb_gather2_01(pl + t2.o0, pl + t2.o1, t2.w);
       }
       ly.R[s] = r;
       mx = fmaxf(mx, r);
@@ -93,8 +89,9 @@ WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, 
   float fx = 0.f, fy = 0.f, sc = 0.f;
   WB_UNROLL_NA for (int i = 0; i < NA; ++i) {
     if (i < ix.n) {
+      const float* oc = s_occ + ix.k[i];
       float vis = 1.f;
-      WB_UNROLL_NA for (int j = 0; j < NA; ++j) if (j < ix.n) vis *= 1.f - ly.R[j] * s_occ[ix.k[j] * L + ix.k[i]];
+      WB_UNROLL_NA for (int j = 0; j < NA; ++j) if (j < ix.n) vis *= 1.f - ly.R[j] * oc[ix.k[j] * L];
       float a = vis * ly.R[i];
       ly.A[i] = a;
       fx += a * ly.Fx[i]; fy += a * ly.Fy[i]; sc += a;
@@ -105,79 +102,42 @@ WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, 
 
 struct WbFwdCtx {   // per-CTA constants of the fused forward
   int b, tp, L, C, TcR, CR, HW;
-  size_t HWd;
+  unsigned HWd;
   bool self, disocc_ch;
   const float* s_occ;
 };
 
+// Layer part of one (pixel, context): evaluates the live layers, writes the alpha channels of raw_output (+ disocc),
+// the reduced flow, and returns (flow, score) for the channel part.
 template <int NA>
-WB_DEV void wb_fwd_pixel(const WbDec& d, const WbFwdCtx& c, const WbPix& px, unsigned wm, bool active, size_t q) {
+WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, unsigned wm, unsigned q, int c_t, size_t pair,
+                          float* __restrict__ raw, float& flow_x, float& flow_y, float& score) {
   const waldo_geom_t& g = d.g;
-  const int L = c.L, C = c.C, b = c.b, tp = c.tp;
-  const size_t HWd = c.HWd;
+  const int L = c.L, C = c.C;
+  const unsigned HWd = c.HWd;
   const WbIdx<NA> ix = wb_idx<NA>(wm);
-  float acc[WB_MAX_C + 1];
-  WB_UNROLL for (int ch = 0; ch <= WB_MAX_C; ++ch) acc[ch] = 0.f;
-  float den = 0.f;
-  for (int tc = 0; tc < g.Tc; ++tc) {
-    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-    const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-    const float* f_lo = d.f_lo + pair * L * c.HW * 2;
-    const float* alpha_c = d.alpha + ((size_t)b * g.Tw + c_t) * L * HWd;
-    WbLay<NA> ly;
-    wb_layers_fwd<NA>(d, px, ix, f_lo, alpha_c, c.s_occ, ly);
-    // stage C: warp the context frame by the reduced flow
-    WbTaps t = wb_taps(__fadd_rn(px.gx, ly.flow_x), __fadd_rn(px.gy, ly.flow_y), g.Wd, g.Hd);
-    int m = wb_tap_mask(t, g.Wd, g.Hd);
-    const float* src = d.input + ((size_t)b * g.T + c_t) * C * HWd;
-    const float wgt = ly.score + 1e-6f;
-    float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q;
-    WB_UNROLL for (int ch = 0; ch < WB_MAX_C; ++ch) {
-      if (ch < C) {
-        float v = wb_sample(src + (size_t)ch * HWd, t, m, g.Wd);
-        if (active) raw[(size_t)ch * HWd] = v;
-        acc[ch] += wgt * v;
-      }
-    }
-    acc[WB_MAX_C] += wgt * (ly.score * 2.f - 1.f);
-    den += wgt;
-    if (active) {
-      WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) if (k < L && !((wm >> k) & 1u)) raw[(size_t)(C + k) * HWd] = -1.f;
-      WB_UNROLL_NA for (int s = 0; s < NA; ++s) if (s < ix.n) raw[(size_t)(C + ix.k[s]) * HWd] = ly.A[s] * 2.f - 1.f;
-      if (c.disocc_ch) raw[(size_t)(C + L) * HWd] = ly.disocc;
-      float* fl = d.flow + pair * 2 * HWd + q;
-      fl[0] = ly.flow_x; fl[HWd] = ly.flow_y;
-    }
-  }
-  if (c.self) {   // lvd.py:842-845: the target frame itself, fully opaque, score 1
-    float* raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q;
-    const float* src = d.input + ((size_t)b * g.T + tp) * C * HWd + q;
-    const float wgt = 1.f + 1e-6f;
-    WB_UNROLL for (int ch = 0; ch < WB_MAX_C; ++ch) {
-      if (ch < C) { float v = __ldg(src + (size_t)ch * HWd); if (active) raw[(size_t)ch * HWd] = v; acc[ch] += wgt * v; }
-    }
-    if (active) {
-      for (int k = 0; k < L; ++k) raw[(size_t)(C + k) * HWd] = 1.f;
-      if (c.disocc_ch) raw[(size_t)(C + L) * HWd] = 1.f;
-    }
-    acc[WB_MAX_C] += wgt * 1.f;
-    den += wgt;
-  }
-  if (active) {
-    const float inv = 1.f / fmaxf(den, 1e-12f);
-    float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
-    WB_UNROLL for (int ch = 0; ch < WB_MAX_C; ++ch) if (ch < C) of[(size_t)ch * HWd] = acc[ch] * inv;
-    of[(size_t)C * HWd] = acc[WB_MAX_C] * inv;
-    if (d.norm) d.norm[((size_t)b * g.Tp + tp) * HWd + q] = den;
-  }
+  const float* f_lo = d.f_lo + pair * L * c.HW * 2;
+  const float* alpha_c = d.alpha + ((size_t)c.b * g.Tw + c_t) * L * HWd;
+  WbLay<NA> ly;
+  wb_layers_fwd<NA>(d, px, ix, f_lo, alpha_c, c.s_occ, ly);
+  float* ra = raw + (size_t)C * HWd + q;
+  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) *ra = -1.f; ra += HWd; }
+  ra = raw + (size_t)C * HWd + q;
+  WB_UNROLL_NA for (int s = 0; s < NA; ++s) if (s < ix.n) ra[(size_t)ix.k[s] * HWd] = ly.A[s] * 2.f - 1.f;
+  if (c.disocc_ch) ra[(size_t)L * HWd] = ly.disocc;
+  float* fl = d.flow + pair * 2 * HWd + q;
+  fl[0] = ly.flow_x; fl[HWd] = ly.flow_y;
+  flow_x = ly.flow_x; flow_y = ly.flow_y; score = ly.score;
 }
 
 // grid = (CTAs, B*Tp); one thread per HD pixel (32x8 tiles), contexts looped inside so that the fused `output`
-// (lvd.py:850-851) never leaves registers.
+// (lvd.py:850-851) never leaves registers.  CC = compile-time channel count (0: generic, channel count read at run time).
+template <int CC>
 __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
+  constexpr int NCH = CC > 0 ? CC : WB_MAX_C;
   const waldo_geom_t g = d.g;
   WbFwdCtx c;
-  c.L = g.No + 1; c.HW = g.H * g.W; c.C = g.C; c.HWd = (size_t)g.Hd * g.Wd;
+  c.L = g.No + 1; c.HW = g.H * g.W; c.C = CC > 0 ? CC : g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
   const int btp = blockIdx.y;
   c.b = btp / g.Tp; c.tp = btp - c.b * g.Tp;
   const int u = (int)d.pred_ts[c.tp];
@@ -188,19 +148,64 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
   for (int i = wb_tid(); i < c.L * c.L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + u) * c.L * c.L + i);
   __syncthreads();
   c.s_occ = s_occ;
+  const int C = c.C, b = c.b, tp = c.tp;
+  const unsigned HWd = c.HWd;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
     for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
-      const int X = tx0 + (it & (WB_TILE_W - 1)), Y = ty0 + it / WB_TILE_W;
-      const bool active = X < g.Wd && Y < g.Hd;
-      const size_t q = active ? (size_t)Y * g.Wd + X : 0;
-      WbPix px = wb_pix(d, c.b, c.tp, active ? X : 0, active ? Y : 0);
-      const unsigned wm = wb_warp_or(active ? px.isobj : 1u);
+      // threads beyond the image edge recompute (and re-store, identically) the nearest valid pixel: no predicates
+      const int X = min(tx0 + (it & (WB_TILE_W - 1)), g.Wd - 1), Y = min(ty0 + it / WB_TILE_W, g.Hd - 1);
+      const unsigned q = (unsigned)(Y * g.Wd + X);
+      WbPix px = wb_pix(d, b, tp, X, Y);
+      const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
-      if (n <= 4) wb_fwd_pixel<4>(d, c, px, wm, active, q);
-      else if (n <= 8) wb_fwd_pixel<8>(d, c, px, wm, active, q);
-      else wb_fwd_pixel<WB_MAX_L>(d, c, px, wm, active, q);
+      float acc[NCH + 1];
+      WB_UNROLL for (int ch = 0; ch <= NCH; ++ch) acc[ch] = 0.f;
+      float den = 0.f;
+      for (int tc = 0; tc < g.Tc; ++tc) {
+        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+        float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
+        float flow_x, flow_y, score;
+        if (n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
+        else if (n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
+        else wb_fwd_layers<WB_MAX_L>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
+        // stage C: warp the context frame by the reduced flow; channels walked with running pointers
+        const WbTaps t = wb_taps(__fadd_rn(px.gx, flow_x), __fadd_rn(px.gy, flow_y), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        const float* src = d.input + ((size_t)b * g.T + c_t) * C * HWd;
+        const float* p0 = src + t2.o0;
+        const float* p1 = src + t2.o1;
+        const float wgt = score + 1e-6f;
+        float* rp = raw + q;
+        WB_UNROLL for (int ch = 0; ch < NCH; ++ch) {
+          if (CC > 0 || ch < C) {
+            const float v = wb_gather2(p0, p1, t2.w);
+            *rp = v; acc[ch] += wgt * v;
+            p0 += HWd; p1 += HWd; rp += HWd;
+          }
+        }
+        acc[NCH] += wgt * (score * 2.f - 1.f);
+        den += wgt;
+      }
+      if (c.self) {   // lvd.py:842-845: the target frame itself, fully opaque, score 1
+        float* raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd;
+        const float* src = d.input + ((size_t)b * g.T + tp) * C * HWd;
+        const float wgt = 1.f + 1e-6f;
+        WB_UNROLL for (int ch = 0; ch < NCH; ++ch) {
+          if (CC > 0 || ch < C) { float v = __ldg(src + ch * HWd + q); raw[ch * HWd + q] = v; acc[ch] += wgt * v; }
+        }
+        for (int k = 0; k < c.L; ++k) raw[(C + k) * HWd + q] = 1.f;
+        if (c.disocc_ch) raw[(C + c.L) * HWd + q] = 1.f;
+        acc[NCH] += wgt * 1.f;
+        den += wgt;
+      }
+      const float inv = 1.f / fmaxf(den, 1e-12f);
+      float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+      WB_UNROLL for (int ch = 0; ch < NCH; ++ch) if (CC > 0 || ch < C) { *of = acc[ch] * inv; of += HWd; }
+      *of = acc[NCH] * inv;
+      if (d.norm) d.norm[((size_t)b * g.Tp + tp) * HWd + q] = den;
     }
   }
 }

@@ -52,7 +52,7 @@ WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, 
 // ============================================================================ fused HD backward
 struct WbBwdCtx {   // per-CTA constants of the fused backward
   int b, tp, L, C, TcR, CR, HW;
-  size_t HWd;
+  unsigned HWd;
   bool self, disocc_ch, need_layers, lowres_direct;
   const float* s_occ;
   float* s_acc;      // this warp's d occ accumulators (or null)
@@ -60,140 +60,102 @@ struct WbBwdCtx {   // per-CTA constants of the fused backward
   int wy0, wx0, ww;  // window origin / width
 };
 
+// forward of the layer part (recomputed): reduced flow and score of one (pixel, context)
 template <int NA>
-WB_DEV void wb_bwd_pixel(const WbDecB& a, const WbBwdCtx& c, const WbPix& px, unsigned wm, bool active, size_t q) {
+WB_DEV void wb_bwd_layers_fwd(const WbDec& d, const WbBwdCtx& c, const WbPix& px, unsigned wm, int c_t, size_t pair,
+                              float& flow_x, float& flow_y, float& score) {
+  const waldo_geom_t& g = d.g;
+  const WbIdx<NA> ix = wb_idx<NA>(wm);
+  WbLay<NA> ly;
+  wb_layers_fwd<NA>(d, px, ix, d.f_lo + pair * c.L * c.HW * 2, d.alpha + ((size_t)c.b * g.Tw + c_t) * c.L * c.HWd, c.s_occ, ly);
+  flow_x = ly.flow_x; flow_y = ly.flow_y; score = ly.score;
+}
+
+// backward of the layer part: B9, B8, B7, B6, B5(up) of one (pixel, context).  gs = d/d score, (dfx, dfy) = d/d flow,
+// draw = this pixel's upstream d raw_output (null = zero).
+template <int NA>
+WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& px, unsigned wm, int tc, int c_t, size_t pair,
+                              const float* __restrict__ draw, float actf, float gs, float dfx, float dfy) {
   const WbDec& d = a.f;
   const waldo_geom_t& g = d.g;
-  const int L = c.L, C = c.C, b = c.b, tp = c.tp, HW = c.HW;
-  const size_t HWd = c.HWd;
+  const int L = c.L, C = c.C, HW = c.HW;
+  const unsigned HWd = c.HWd;
   const WbIdx<NA> ix = wb_idx<NA>(wm);
+  const float* alpha_c = d.alpha + ((size_t)c.b * g.Tw + c_t) * L * HWd;
+  WbLay<NA> ly;
+  wb_layers_fwd<NA>(d, px, ix, d.f_lo + pair * L * HW * 2, alpha_c, c.s_occ, ly);
+  float gA[NA], gR[NA], gFx[NA], gFy[NA];
+  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+    gR[s] = 0.f; gA[s] = 0.f; gFx[s] = 0.f; gFy[s] = 0.f;
+    if (s < ix.n) {
+      gA[s] = gs + 2.f * (draw ? actf * __ldg(draw + (size_t)(C + ix.k[s]) * HWd) : 0.f) + dfx * ly.Fx[s] + dfy * ly.Fy[s];
+      gFx[s] = ly.A[s] * dfx; gFy[s] = ly.A[s] * dfy;
+    }
+  }
+  wb_occlude_bwd<NA>(ly.R, gA, c.s_occ, L, ix, gR, c.s_acc);
+  // ---- B7 backward: disocc = max_k R_k (first maximal layer takes the gradient)
+  if (c.disocc_ch && draw) {
+    const float gd = actf * __ldg(draw + (size_t)(C + L) * HWd);
+    bool done = false;
+    WB_UNROLL_NA for (int s = 0; s < NA; ++s)
+      if (s < ix.n && !done && ly.R[s] == ly.disocc) { gR[s] += gd; done = true; }
+  }
   // window-relative low-res offsets
   const int c00 = (px.ay.i0 - c.wy0) * c.ww + px.ax.i0 - c.wx0, c01 = (px.ay.i0 - c.wy0) * c.ww + px.ax.i1 - c.wx0;
   const int c10 = (px.ay.i1 - c.wy0) * c.ww + px.ax.i0 - c.wx0, c11 = (px.ay.i1 - c.wy0) * c.ww + px.ax.i1 - c.wx0;
   const float w00 = px.ax.l0 * px.ay.l0, w01 = px.ax.l1 * px.ay.l0, w10 = px.ax.l0 * px.ay.l1, w11 = px.ax.l1 * px.ay.l1;
-  float gO[WB_MAX_C + 1];   // upstream d out_full; the score channel sits at index C (as in memory)
-  float S = 0.f;
-  {
-    const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
-    const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
-    WB_UNROLL for (int ch = 0; ch <= WB_MAX_C; ++ch) {
-      gO[ch] = 0.f;
-      if (ch <= C && dof && active) { gO[ch] = __ldg(dof + (size_t)ch * HWd); S += gO[ch] * __ldg(of + (size_t)ch * HWd); }
-    }
-  }
-  const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
-  for (int tc = 0; tc < g.Tc; ++tc) {
-    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-    const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-    const float* f_lo = d.f_lo + pair * L * HW * 2;
-    const float* alpha_c = d.alpha + ((size_t)b * g.Tw + c_t) * L * HWd;
-    WbLay<NA> ly;
-    wb_layers_fwd<NA>(d, px, ix, f_lo, alpha_c, c.s_occ, ly);
-    const float wgt = ly.score + 1e-6f, n = wgt / D;
-    const float* draw = (a.d_raw_output && active) ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
-    // ---- stage C backward: warped context frame
-    WbTaps t = wb_taps(__fadd_rn(px.gx, ly.flow_x), __fadd_rn(px.gy, ly.flow_y), g.Wd, g.Hd);
-    const int m = wb_tap_mask(t, g.Wd, g.Hd);
-    const float* src = d.input + ((size_t)b * g.T + c_t) * C * HWd + (long long)t.y0 * g.Wd + t.x0;
-    float* din = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * C * HWd + (long long)t.y0 * g.Wd + t.x0 : nullptr;
-    float G = 0.f, gix = 0.f, giy = 0.f;
-    WB_UNROLL for (int ch = 0; ch < WB_MAX_C; ++ch) {
-      if (ch < C) {
-        const float* p = src + (size_t)ch * HWd;
-        const float vnw = (m & 1) ? __ldg(p) : 0.f, vne = (m & 2) ? __ldg(p + 1) : 0.f;
-        const float vsw = (m & 4) ? __ldg(p + g.Wd) : 0.f, vse = (m & 8) ? __ldg(p + g.Wd + 1) : 0.f;
-        const float O = wb_chain(vnw, vne, vsw, vse, t);
-        const float go = (draw ? __ldg(draw + (size_t)ch * HWd) : 0.f) + n * gO[ch];
-        G += gO[ch] * O;
-        gix += go * ((vne - vnw) * t.wy0 + (vse - vsw) * t.wy1);
-        giy += go * ((vsw - vnw) * t.wx0 + (vse - vne) * t.wx1);
-        if (din && go != 0.f) {
-          float* o = din + (size_t)ch * HWd;
-          if (m & 1) wb_atomic_add(o, t.nw * go);
-          if (m & 2) wb_atomic_add(o + 1, t.ne * go);
-          if (m & 4) wb_atomic_add(o + g.Wd, t.sw * go);
-          if (m & 8) wb_atomic_add(o + g.Wd + 1, t.se * go);
+  // ---- B6 backward: bilinear sample of the context opacity through layer k's flow
+  float* dal = a.d_alpha_acc ? a.d_alpha_acc + ((size_t)c.b * g.Tw + c_t) * L * HWd : nullptr;
+  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+    if (s < ix.n) {
+      const int k = ix.k[s];
+      if (((px.isobj >> k) & 1u) && gR[s] != 0.f) {
+        const WbTaps tk = wb_taps(__fadd_rn(px.gx, ly.Fx[s]), __fadd_rn(px.gy, ly.Fy[s]), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(tk, g.Wd, g.Hd);
+        float cx[4], cy[4];
+        wb_pos4(t2, -tk.wy0, tk.wy0, -tk.wy1, tk.wy1, cx);
+        wb_pos4(t2, -tk.wx0, -tk.wx1, tk.wx0, tk.wx1, cy);
+        const float* p0 = alpha_c + (size_t)k * HWd + t2.o0;
+        const float* p1 = alpha_c + (size_t)k * HWd + t2.o1;
+        const float v0 = (__ldg(p0) + 1.f) * 0.5f, v1 = (__ldg(p0 + 1) + 1.f) * 0.5f;
+        const float v2 = (__ldg(p1) + 1.f) * 0.5f, v3 = (__ldg(p1 + 1) + 1.f) * 0.5f;
+        const float gr = gR[s];
+        gFx[s] += gr * (v0 * cx[0] + v1 * cx[1] + v2 * cx[2] + v3 * cx[3]) * (0.5f * (float)g.Wd);
+        gFy[s] += gr * (v0 * cy[0] + v1 * cy[1] + v2 * cy[2] + v3 * cy[3]) * (0.5f * (float)g.Hd);
+        if (dal) {
+          float* o0 = dal + (size_t)k * HWd + t2.o0;
+          float* o1 = dal + (size_t)k * HWd + t2.o1;
+          wb_atomic_add(o0, t2.w[0] * gr); wb_atomic_add(o0 + 1, t2.w[1] * gr);
+          wb_atomic_add(o1, t2.w[2] * gr); wb_atomic_add(o1 + 1, t2.w[3] * gr);
+        }
+      }
+      // ---- B5(up) backward: transpose of the bilinear up-sampling of the layer flow
+      if (a.d_f_lo && (gFx[s] != 0.f || gFy[s] != 0.f)) {
+        if (c.lowres_direct) {
+          float* o = a.d_f_lo + (pair * L + k) * HW * 2 + (size_t)px.o00 * 2;
+          wb_atomic_add(o, gFx[s]); wb_atomic_add(o + 1, gFy[s]);
+        } else {
+          float* w = c.s_win + ((size_t)tc * WB_WIN_CAP * L + k) * 2;
+          const int st = L * 2;
+          atomicAdd(w + c00 * st, w00 * gFx[s]); atomicAdd(w + c00 * st + 1, w00 * gFy[s]);
+          atomicAdd(w + c01 * st, w01 * gFx[s]); atomicAdd(w + c01 * st + 1, w01 * gFy[s]);
+          atomicAdd(w + c10 * st, w10 * gFx[s]); atomicAdd(w + c10 * st + 1, w10 * gFy[s]);
+          atomicAdd(w + c11 * st, w11 * gFx[s]); atomicAdd(w + c11 * st + 1, w11 * gFy[s]);
         }
       }
     }
-    if (!c.need_layers) continue;
-    G += gO[C] * (ly.score * 2.f - 1.f);
-    const float* dfl = (a.d_flow && active) ? a.d_flow + pair * 2 * HWd + q : nullptr;
-    const float dfx = (dfl ? __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
-    const float dfy = (dfl ? __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
-    const float gs = 2.f * n * gO[C] + (G - S) / D;
-    // ---- B9 / B8 backward
-    float gA[NA], gR[NA], gFx[NA], gFy[NA];
-    WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
-      gR[s] = 0.f; gA[s] = 0.f; gFx[s] = 0.f; gFy[s] = 0.f;
-      if (s < ix.n) {
-        gA[s] = gs + 2.f * (draw ? __ldg(draw + (size_t)(C + ix.k[s]) * HWd) : 0.f) + dfx * ly.Fx[s] + dfy * ly.Fy[s];
-        gFx[s] = ly.A[s] * dfx; gFy[s] = ly.A[s] * dfy;
-      }
-    }
-    wb_occlude_bwd<NA>(ly.R, gA, c.s_occ, L, ix, gR, c.s_acc);
-    // ---- B7 backward: disocc = max_k R_k (first maximal layer takes the gradient)
-    if (c.disocc_ch && draw) {
-      const float gd = __ldg(draw + (size_t)(C + L) * HWd);
-      bool done = false;
-      WB_UNROLL_NA for (int s = 0; s < NA; ++s)
-        if (s < ix.n && !done && ly.R[s] == ly.disocc) { gR[s] += gd; done = true; }
-    }
-    // ---- B6 backward: bilinear sample of the context opacity through layer k's flow
-    float* dal = a.d_alpha_acc ? a.d_alpha_acc + ((size_t)b * g.Tw + c_t) * L * HWd : nullptr;
-    WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
-      if (s < ix.n) {
-        const int k = ix.k[s];
-        if (((px.isobj >> k) & 1u) && gR[s] != 0.f) {
-          WbTaps tk = wb_taps(__fadd_rn(px.gx, ly.Fx[s]), __fadd_rn(px.gy, ly.Fy[s]), g.Wd, g.Hd);
-          const int mk = wb_tap_mask(tk, g.Wd, g.Hd);
-          const long long off = (long long)k * (long long)HWd + (long long)tk.y0 * g.Wd + tk.x0;
-          const float* p = alpha_c + off;
-          const float vnw = (mk & 1) ? (__ldg(p) + 1.f) * 0.5f : 0.f, vne = (mk & 2) ? (__ldg(p + 1) + 1.f) * 0.5f : 0.f;
-          const float vsw = (mk & 4) ? (__ldg(p + g.Wd) + 1.f) * 0.5f : 0.f, vse = (mk & 8) ? (__ldg(p + g.Wd + 1) + 1.f) * 0.5f : 0.f;
-          const float gr = gR[s];
-          gFx[s] += gr * ((vne - vnw) * tk.wy0 + (vse - vsw) * tk.wy1) * (0.5f * (float)g.Wd);
-          gFy[s] += gr * ((vsw - vnw) * tk.wx0 + (vse - vne) * tk.wx1) * (0.5f * (float)g.Hd);
-          if (dal) {
-            float* o = dal + off;
-            if (mk & 1) wb_atomic_add(o, tk.nw * gr);
-            if (mk & 2) wb_atomic_add(o + 1, tk.ne * gr);
-            if (mk & 4) wb_atomic_add(o + g.Wd, tk.sw * gr);
-            if (mk & 8) wb_atomic_add(o + g.Wd + 1, tk.se * gr);
-          }
-        }
-        // ---- B5(up) backward: transpose of the bilinear up-sampling of the layer flow
-        if (a.d_f_lo && (gFx[s] != 0.f || gFy[s] != 0.f)) {
-          if (c.lowres_direct) {
-            float* o = a.d_f_lo + (pair * L + k) * HW * 2 + (size_t)px.o00 * 2;
-            wb_atomic_add(o, gFx[s]); wb_atomic_add(o + 1, gFy[s]);
-          } else {
-            float* w = c.s_win + ((size_t)tc * WB_WIN_CAP * L + k) * 2;
-            const int st = L * 2;
-            atomicAdd(w + c00 * st, w00 * gFx[s]); atomicAdd(w + c00 * st + 1, w00 * gFy[s]);
-            atomicAdd(w + c01 * st, w01 * gFx[s]); atomicAdd(w + c01 * st + 1, w01 * gFy[s]);
-            atomicAdd(w + c10 * st, w10 * gFx[s]); atomicAdd(w + c10 * st + 1, w10 * gFy[s]);
-            atomicAdd(w + c11 * st, w11 * gFx[s]); atomicAdd(w + c11 * st + 1, w11 * gFy[s]);
-          }
-        }
-      }
-    }
-  }
-  if (c.self && a.d_input && active) {   // lvd.py:845: the target frame passes straight through
-    const float n = (1.f + 1e-6f) / D;
-    const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
-    float* o = a.d_input + ((size_t)b * g.T + tp) * C * HWd + q;
-    WB_UNROLL for (int ch = 0; ch < WB_MAX_C; ++ch)
-      if (ch < C) wb_atomic_add(o + (size_t)ch * HWd, (draw ? __ldg(draw + (size_t)ch * HWd) : 0.f) + n * gO[ch]);
   }
 }
 
 // grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration); dynamic smem = Tc*WB_WIN_CAP*L*2 floats.
+// CC = compile-time channel count (0: generic).
+template <int CC>
 __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) {
+  constexpr int NCH = CC > 0 ? CC : WB_MAX_C;
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
   WbBwdCtx c;
-  c.L = g.No + 1; c.HW = g.H * g.W; c.C = g.C; c.HWd = (size_t)g.Hd * g.Wd;
+  c.L = g.No + 1; c.HW = g.H * g.W; c.C = CC > 0 ? CC : g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
   const int btp = blockIdx.y;
   c.b = btp / g.Tp; c.tp = btp - c.b * g.Tp;
   const int u = (int)d.pred_ts[c.tp];
@@ -202,13 +164,14 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
   c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0);
   c.need_layers = a.d_alpha_acc || a.d_f_lo || a.d_occ;
   c.lowres_direct = (g.Hd == g.H);
-  const int L = c.L;
+  const int L = c.L, C = c.C, b = c.b, tp = c.tp;
+  const unsigned HWd = c.HWd;
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
   WB_DYN_SMEM(s_win);
   const bool use_win = a.d_f_lo && !c.lowres_direct;
   const int win_elems = use_win ? g.Tc * WB_WIN_CAP * L * 2 : 0;
-  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + u) * L * L + i);
+  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + u) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
   for (int i = wb_tid(); i < win_elems; i += wb_nthr()) s_win[i] = 0.f;
   __syncthreads();
@@ -224,15 +187,83 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
     c.ww = wx1 - c.wx0 + 1;
     const int wcells = c.ww * (wy1 - c.wy0 + 1);
     for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
-      const int X = tx0 + (it & (WB_TILE_W - 1)), Y = ty0 + it / WB_TILE_W;
-      const bool active = X < g.Wd && Y < g.Hd;
-      const size_t q = active ? (size_t)Y * g.Wd + X : 0;
-      WbPix px = wb_pix(d, c.b, c.tp, active ? X : 0, active ? Y : 0);
-      const unsigned wm = wb_warp_or(active ? px.isobj : 1u);
+      const int Xr = tx0 + (it & (WB_TILE_W - 1)), Yr = ty0 + it / WB_TILE_W;
+      const bool active = Xr < g.Wd && Yr < g.Hd;
+      const float actf = active ? 1.f : 0.f;    // threads beyond the edge run on the nearest valid pixel with zero upstream
+      const int X = min(Xr, g.Wd - 1), Y = min(Yr, g.Hd - 1);
+      const unsigned q = (unsigned)(Y * g.Wd + X);
+      WbPix px = wb_pix(d, b, tp, X, Y);
+      const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
-      if (n <= 4) wb_bwd_pixel<4>(a, c, px, wm, active, q);
-      else if (n <= 8) wb_bwd_pixel<8>(a, c, px, wm, active, q);
-      else wb_bwd_pixel<WB_MAX_L>(a, c, px, wm, active, q);
+      float gO[NCH + 1];   // upstream d out_full; the score channel sits at index C (as in memory)
+      float S = 0.f;
+      {
+        const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
+        const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+        WB_UNROLL for (int ch = 0; ch <= NCH; ++ch) {
+          gO[ch] = 0.f;
+          if ((CC > 0 || ch <= C) && dof) { gO[ch] = actf * __ldg(dof + (size_t)ch * HWd); S += gO[ch] * __ldg(of + (size_t)ch * HWd); }
+        }
+      }
+      const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
+      for (int tc = 0; tc < g.Tc; ++tc) {
+        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+        float flow_x, flow_y, score;
+        if (n <= 4) wb_bwd_layers_fwd<4>(d, c, px, wm, c_t, pair, flow_x, flow_y, score);
+        else if (n <= 8) wb_bwd_layers_fwd<8>(d, c, px, wm, c_t, pair, flow_x, flow_y, score);
+        else wb_bwd_layers_fwd<WB_MAX_L>(d, c, px, wm, c_t, pair, flow_x, flow_y, score);
+        const float wgt = score + 1e-6f, nrm = wgt / D;
+        // upstream pointers are warp-uniformly null or valid; threads beyond the edge scale what they read by actf = 0
+        const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
+        // ---- stage C backward: warped context frame
+        const WbTaps t = wb_taps(__fadd_rn(px.gx, flow_x), __fadd_rn(px.gy, flow_y), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        float cx[4], cy[4];
+        wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
+        wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
+        const float* src = d.input + ((size_t)b * g.T + c_t) * C * HWd;
+        const float* p0 = src + t2.o0;
+        const float* p1 = src + t2.o1;
+        float* dsrc = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * C * HWd : nullptr;
+        float* o0 = dsrc + t2.o0;
+        float* o1 = dsrc + t2.o1;
+        const float* dr = draw;
+        float G = 0.f, gix = 0.f, giy = 0.f;
+        WB_UNROLL for (int ch = 0; ch < NCH; ++ch) {
+          if (CC > 0 || ch < C) {
+            const float v0 = __ldg(p0), v1 = __ldg(p0 + 1), v2 = __ldg(p1), v3 = __ldg(p1 + 1);
+            const float O = __fmaf_rn(v3, t2.w[3], __fmaf_rn(v2, t2.w[2], __fmaf_rn(v1, t2.w[1], __fmul_rn(v0, t2.w[0]))));
+            const float go = (dr ? actf * __ldg(dr) : 0.f) + nrm * gO[ch];
+            G += gO[ch] * O;
+            gix += go * (v0 * cx[0] + v1 * cx[1] + v2 * cx[2] + v3 * cx[3]);
+            giy += go * (v0 * cy[0] + v1 * cy[1] + v2 * cy[2] + v3 * cy[3]);
+            if (dsrc) {
+              atomicAdd(o0, t2.w[0] * go); atomicAdd(o0 + 1, t2.w[1] * go);
+              atomicAdd(o1, t2.w[2] * go); atomicAdd(o1 + 1, t2.w[3] * go);
+              o0 += HWd; o1 += HWd;
+            }
+            p0 += HWd; p1 += HWd;
+            if (dr) dr += HWd;
+          }
+        }
+        if (!c.need_layers) continue;
+        G += gO[C] * (score * 2.f - 1.f);
+        const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
+        const float dfx = (dfl ? actf * __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+        const float dfy = (dfl ? actf * __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
+        const float gs = 2.f * nrm * gO[C] + (G - S) / D;
+        if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+      }
+      if (c.self && a.d_input && active) {   // lvd.py:845: the target frame passes straight through
+        const float nrm = (1.f + 1e-6f) / D;
+        const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
+        float* o = a.d_input + ((size_t)b * g.T + tp) * C * HWd + q;
+        WB_UNROLL for (int ch = 0; ch < NCH; ++ch)
+          if (CC > 0 || ch < C) wb_atomic_add(o + (size_t)ch * HWd, (draw ? __ldg(draw + (size_t)ch * HWd) : 0.f) + nrm * gO[ch]);
+      }
     }
     if (use_win) {   // flush the windows of this tile (all contexts)
       __syncthreads();
@@ -244,7 +275,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
         float* sv = s_win + (((size_t)tc * WB_WIN_CAP + cell) * L + k) * 2 + comp;
         const float v = *sv;
         if (v != 0.f) {
-          const size_t pair = ((size_t)c.b * g.Tc + tc) * g.Tp + c.tp;
+          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
           atomicAdd(a.d_f_lo + ((pair * L + k) * c.HW + (size_t)cy * g.W + cx) * 2 + comp, v);
           *sv = 0.f;
         }
@@ -717,12 +748,19 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   if (a.stages == 0 || (a.stages & 1)) {
     const size_t win_bytes = (a.d_f_lo && g.Hd != g.H) ? (size_t)g.Tc * WB_WIN_CAP * L * 2 * sizeof(float) : 0;
     WB_BREQ(win_bytes <= 200 * 1024, "Tc too large for the shared-memory flow window");
+    const dim3 bgrid(a.red_ctas, g.B * g.Tp);
 #ifndef WB_HOST_EMU
-    if (win_bytes > 48 * 1024) cudaFuncSetAttribute(k_warp_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes);
+    if (win_bytes > 48 * 1024) {
+      cudaFuncSetAttribute(k_warp_composite_bwd<23>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes);
+      cudaFuncSetAttribute(k_warp_composite_bwd<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes);
+      cudaFuncSetAttribute(k_warp_composite_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes);
+    }
 #else
     WB_BREQ(win_bytes <= sizeof(wb_dyn_smem_buf), "emulation smem buffer too small");
 #endif
-    WB_LAUNCH(k_warp_composite_bwd, dim3(a.red_ctas, g.B * g.Tp), dim3(WB_TILE_PX), win_bytes, st, a);
+    if (g.C == 23) WB_LAUNCH(k_warp_composite_bwd<23>, bgrid, dim3(WB_TILE_PX), win_bytes, st, a);
+    else if (g.C == 22) WB_LAUNCH(k_warp_composite_bwd<22>, bgrid, dim3(WB_TILE_PX), win_bytes, st, a);
+    else WB_LAUNCH(k_warp_composite_bwd<0>, bgrid, dim3(WB_TILE_PX), win_bytes, st, a);
     WB_BLAUNCHED();
     if (a.d_occ) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);
