@@ -170,7 +170,12 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
     WB_LAUNCHED();
   }
   // B2b-B4
-  WB_LAUNCH(k_alpha_prep, dim3(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tw), dim3(WB_TILE_PX), 0, st, *a);
+  {
+    const dim3 pgrid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tw);
+    if (g.Nl == 20) WB_LAUNCH(k_alpha_prep<20>, pgrid, dim3(WB_TILE_PX), 0, st, *a);        // Cityscapes
+    else if (g.Nl == 19) WB_LAUNCH(k_alpha_prep<19>, pgrid, dim3(WB_TILE_PX), 0, st, *a);   // KITTI
+    else WB_LAUNCH(k_alpha_prep<0>, pgrid, dim3(WB_TILE_PX), 0, st, *a);
+  }
   WB_LAUNCHED();
   // B5
   WB_LAUNCH(k_layer_flow_lo, dim3(wb_blocks((long long)g.B * g.Tp * HW, 128)), dim3(128), 0, st, *a);

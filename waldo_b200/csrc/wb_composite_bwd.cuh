@@ -15,10 +15,84 @@
 
 typedef waldo_decode_bwd_t WbDecB;
 
-#define WB_WIN_CAP 128              // low-res cells a tile window may hold (scale_hd >= 2: <= 6 x 18 = 108)
 #define WB_NWARP (WB_TILE_PX / 32)
 
 WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) atomicAdd(p, v); }
+
+// ---------------------------------------------------------------------------- transpose of the bilinear up-sampling
+// A warp is one row of 32 HD pixels, so all its lanes share the two low-res rows and touch a short run of low-res
+// columns.  Instead of 4 atomics per lane and value, the lanes stage their values in shared memory and the first
+// `ncols` lanes each own one low-res column: they sum the (<= 8, scale_hd <= 4) lanes that touch it in lane order and
+// issue two global reductions (one per low-res row).  No shared-memory atomics, no block barrier.
+#ifdef WB_HOST_EMU
+#define WB_WARP 1
+#define WB_CPL 2          // low-res columns owned per lane (one emulated lane touches 2 columns)
+#define __syncwarp() ((void)0)
+#else
+#define WB_WARP 32
+#define WB_CPL 1
+#endif
+#define WB_COL_TAPS 8     // max lanes touching one low-res column
+#define WB_STAGE_SLOTS 8  // values staged per round and lane
+
+struct WbColRed {
+  int col[WB_CPL];                 // absolute low-res column owned by this lane (-1: none)
+  int lo[WB_CPL];                  // first contributing lane
+  float w[WB_CPL][WB_COL_TAPS];    // x-weights of lanes lo .. lo+7
+  int row0, row1;                  // the two low-res rows (same for the whole warp)
+  float wy0, wy1;
+};
+
+// s_geo: per-warp scratch of 4*WB_WARP floats
+WB_DEV WbColRed wb_colred_setup(const WbAxis& ax, const WbAxis& ay, float* s_geo) {
+  const int lane = wb_lane();
+  int* gi = reinterpret_cast<int*>(s_geo);
+  gi[lane] = ax.i0; gi[WB_WARP + lane] = ax.i1;
+  s_geo[2 * WB_WARP + lane] = ax.l0; s_geo[3 * WB_WARP + lane] = ax.l1;
+  __syncwarp();
+  WbColRed cr;
+  cr.row0 = ay.i0; cr.row1 = ay.i1; cr.wy0 = ay.l0; cr.wy1 = ay.l1;
+  const int colbase = gi[0], ncols = max(gi[2 * WB_WARP - 1], gi[WB_WARP - 1]) - colbase + 1;
+  WB_UNROLL for (int cpl = 0; cpl < WB_CPL; ++cpl) {
+    const int jj = lane + cpl * WB_WARP;
+    cr.col[cpl] = -1; cr.lo[cpl] = 0;
+    WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) cr.w[cpl][t] = 0.f;
+    if (jj < ncols) {
+      const int col = colbase + jj;
+      cr.col[cpl] = col;
+      int lo = -1;
+      for (int l = 0; l < WB_WARP; ++l) {
+        const bool h0 = gi[l] == col, h1 = gi[WB_WARP + l] == col;
+        if (h0 || h1) {
+          if (lo < 0) lo = l;
+          const float wv = (h0 ? s_geo[2 * WB_WARP + l] : 0.f) + (h1 ? s_geo[3 * WB_WARP + l] : 0.f);
+          const int t = l - lo;
+          WB_UNROLL for (int tt = 0; tt < WB_COL_TAPS; ++tt) if (tt == t) cr.w[cpl][tt] = wv;
+        }
+      }
+      cr.lo[cpl] = lo < 0 ? 0 : lo;
+    }
+  }
+  __syncwarp();
+  return cr;
+}
+
+// reduce `nv` staged values per lane (s_stage[v * WB_WARP + lane]) into dst[(row * W + col) * stride + v * vstride]
+WB_DEV void wb_colred_flush(const WbColRed& cr, const float* s_stage, int nv, float* const* dst, int W, int stride) {
+  WB_UNROLL for (int cpl = 0; cpl < WB_CPL; ++cpl) {
+    if (cr.col[cpl] >= 0) {
+      for (int v = 0; v < nv; ++v) {
+        const float* sv = s_stage + v * WB_WARP + cr.lo[cpl];
+        float acc = 0.f;
+        WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) if (cr.lo[cpl] + t < WB_WARP) acc += cr.w[cpl][t] * sv[t];
+        if (acc != 0.f) {
+          atomicAdd(dst[v] + ((size_t)cr.row0 * W + cr.col[cpl]) * stride, acc * cr.wy0);
+          atomicAdd(dst[v] + ((size_t)cr.row1 * W + cr.col[cpl]) * stride, acc * cr.wy1);
+        }
+      }
+    }
+  }
+}
 
 // exclusive-product backward of  A_i = R_i * prod_j (1 - R_j occ[j,i])  over the slots of `ix`.
 // gR (+=) gets d/dR; when s_acc != nullptr, d/d occ[j,i] summed over the warp is added to s_acc[j*L+i] by lane 0.
@@ -56,8 +130,7 @@ struct WbBwdCtx {   // per-CTA constants of the fused backward
   bool self, disocc_ch, need_layers, lowres_direct;
   const float* s_occ;
   float* s_acc;      // this warp's d occ accumulators (or null)
-  float* s_win;      // low-res window of the tile: [Tc][WB_WIN_CAP][L][2]
-  int wy0, wx0, ww;  // window origin / width
+  float* s_stage;    // this warp's staging area: WB_STAGE_SLOTS * 2 * WB_WARP floats
 };
 
 // forward of the layer part (recomputed): reduced flow and score of one (pixel, context)
@@ -74,8 +147,8 @@ WB_DEV void wb_bwd_layers_fwd(const WbDec& d, const WbBwdCtx& c, const WbPix& px
 // backward of the layer part: B9, B8, B7, B6, B5(up) of one (pixel, context).  gs = d/d score, (dfx, dfy) = d/d flow,
 // draw = this pixel's upstream d raw_output (null = zero).
 template <int NA>
-WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& px, unsigned wm, int tc, int c_t, size_t pair,
-                              const float* __restrict__ draw, float actf, float gs, float dfx, float dfy) {
+WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& px, const WbColRed& cr, unsigned wm, int tc, int c_t,
+                              size_t pair, const float* __restrict__ draw, float actf, float gs, float dfx, float dfy) {
   const WbDec& d = a.f;
   const waldo_geom_t& g = d.g;
   const int L = c.L, C = c.C, HW = c.HW;
@@ -100,10 +173,6 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
     WB_UNROLL_NA for (int s = 0; s < NA; ++s)
       if (s < ix.n && !done && ly.R[s] == ly.disocc) { gR[s] += gd; done = true; }
   }
-  // window-relative low-res offsets
-  const int c00 = (px.ay.i0 - c.wy0) * c.ww + px.ax.i0 - c.wx0, c01 = (px.ay.i0 - c.wy0) * c.ww + px.ax.i1 - c.wx0;
-  const int c10 = (px.ay.i1 - c.wy0) * c.ww + px.ax.i0 - c.wx0, c11 = (px.ay.i1 - c.wy0) * c.ww + px.ax.i1 - c.wx0;
-  const float w00 = px.ax.l0 * px.ay.l0, w01 = px.ax.l1 * px.ay.l0, w10 = px.ax.l0 * px.ay.l1, w11 = px.ax.l1 * px.ay.l1;
   // ---- B6 backward: bilinear sample of the context opacity through layer k's flow
   float* dal = a.d_alpha_acc ? a.d_alpha_acc + ((size_t)c.b * g.Tw + c_t) * L * HWd : nullptr;
   WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
@@ -129,18 +198,42 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
           wb_atomic_add(o1, t2.w[2] * gr); wb_atomic_add(o1 + 1, t2.w[3] * gr);
         }
       }
-      // ---- B5(up) backward: transpose of the bilinear up-sampling of the layer flow
-      if (a.d_f_lo && (gFx[s] != 0.f || gFy[s] != 0.f)) {
-        if (c.lowres_direct) {
-          float* o = a.d_f_lo + (pair * L + k) * HW * 2 + (size_t)px.o00 * 2;
+    }
+  }
+  // ---- B5(up) backward: transpose of the bilinear up-sampling of the layer flows
+  if (a.d_f_lo) {
+    if (c.lowres_direct) {
+      WB_UNROLL_NA for (int s = 0; s < NA; ++s)
+        if (s < ix.n) {
+          float* o = a.d_f_lo + (pair * L + ix.k[s]) * HW * 2 + (size_t)px.o00 * 2;
           wb_atomic_add(o, gFx[s]); wb_atomic_add(o + 1, gFy[s]);
-        } else {
-          float* w = c.s_win + ((size_t)tc * WB_WIN_CAP * L + k) * 2;
-          const int st = L * 2;
-          atomicAdd(w + c00 * st, w00 * gFx[s]); atomicAdd(w + c00 * st + 1, w00 * gFy[s]);
-          atomicAdd(w + c01 * st, w01 * gFx[s]); atomicAdd(w + c01 * st + 1, w01 * gFy[s]);
-          atomicAdd(w + c10 * st, w10 * gFx[s]); atomicAdd(w + c10 * st + 1, w10 * gFy[s]);
-          atomicAdd(w + c11 * st, w11 * gFx[s]); atomicAdd(w + c11 * st + 1, w11 * gFy[s]);
+        }
+    } else {
+      const int lane = wb_lane();
+      if constexpr (NA <= WB_STAGE_SLOTS) {
+        float* dst[2 * NA];
+        WB_UNROLL for (int s = 0; s < NA; ++s) {
+          c.s_stage[(2 * s) * WB_WARP + lane] = gFx[s];
+          c.s_stage[(2 * s + 1) * WB_WARP + lane] = gFy[s];
+          float* base = a.d_f_lo + (pair * L + ix.k[s]) * HW * 2;
+          dst[2 * s] = base; dst[2 * s + 1] = base + 1;
+        }
+        __syncwarp();
+        wb_colred_flush(cr, c.s_stage, 2 * ix.n, dst, g.W, 2);
+        __syncwarp();
+      } else {
+        for (int s0 = 0; s0 < ix.n; s0 += WB_STAGE_SLOTS) {
+          float* dst[2 * WB_STAGE_SLOTS];
+          const int ns = min(WB_STAGE_SLOTS, ix.n - s0);
+          for (int j = 0; j < ns; ++j) {
+            c.s_stage[(2 * j) * WB_WARP + lane] = gFx[s0 + j];
+            c.s_stage[(2 * j + 1) * WB_WARP + lane] = gFy[s0 + j];
+            float* base = a.d_f_lo + (pair * L + ix.k[s0 + j]) * HW * 2;
+            dst[2 * j] = base; dst[2 * j + 1] = base + 1;
+          }
+          __syncwarp();
+          wb_colred_flush(cr, c.s_stage, 2 * ns, dst, g.W, 2);
+          __syncwarp();
         }
       }
     }
@@ -168,24 +261,16 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
   const unsigned HWd = c.HWd;
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
-  WB_DYN_SMEM(s_win);
-  const bool use_win = a.d_f_lo && !c.lowres_direct;
-  const int win_elems = use_win ? g.Tc * WB_WIN_CAP * L * 2 : 0;
+  __shared__ float s_stage[WB_NWARP][2 * WB_STAGE_SLOTS * WB_WARP];
+  __shared__ float s_geo[WB_NWARP][4 * WB_WARP];
   for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + u) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
-  for (int i = wb_tid(); i < win_elems; i += wb_nthr()) s_win[i] = 0.f;
   __syncthreads();
-  c.s_occ = s_occ; c.s_win = s_win;
+  c.s_occ = s_occ; c.s_stage = s_stage[wb_warp()];
   c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
   const WbTileIter ti(g.Hd, g.Wd);
-  const float rlo = (float)g.H / (float)g.Hd;
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
-    // low-res window of this tile
-    c.wy0 = wb_axis(ty0, rlo, g.H).i0; c.wx0 = wb_axis(tx0, rlo, g.W).i0;
-    const int wy1 = wb_axis(min(ty0 + WB_TILE_H, g.Hd) - 1, rlo, g.H).i1, wx1 = wb_axis(min(tx0 + WB_TILE_W, g.Wd) - 1, rlo, g.W).i1;
-    c.ww = wx1 - c.wx0 + 1;
-    const int wcells = c.ww * (wy1 - c.wy0 + 1);
     for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
       const int Xr = tx0 + (it & (WB_TILE_W - 1)), Yr = ty0 + it / WB_TILE_W;
       const bool active = Xr < g.Wd && Yr < g.Hd;
@@ -195,6 +280,8 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
       WbPix px = wb_pix(d, b, tp, X, Y);
       const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
+      WbColRed cr;
+      if (a.d_f_lo && !c.lowres_direct) cr = wb_colred_setup(px.ax, px.ay, s_geo[wb_warp()]);
       float gO[NCH + 1];   // upstream d out_full; the score channel sits at index C (as in memory)
       float S = 0.f;
       {
@@ -229,15 +316,16 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
         float* o0 = dsrc + t2.o0;
         float* o1 = dsrc + t2.o1;
         const float* dr = draw;
-        float G = 0.f, gix = 0.f, giy = 0.f;
+        // G = sum_ch gO*O, gix/giy = sum_ch go * dO/d(ix,iy) are bilinear in the four tap values: accumulate
+        // U_pos = sum_ch gO*v_pos and T_pos = sum_ch draw*v_pos once, combine after the loop.
+        float U[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
         WB_UNROLL for (int ch = 0; ch < NCH; ++ch) {
           if (CC > 0 || ch < C) {
             const float v0 = __ldg(p0), v1 = __ldg(p0 + 1), v2 = __ldg(p1), v3 = __ldg(p1 + 1);
-            const float O = __fmaf_rn(v3, t2.w[3], __fmaf_rn(v2, t2.w[2], __fmaf_rn(v1, t2.w[1], __fmul_rn(v0, t2.w[0]))));
-            const float go = (dr ? actf * __ldg(dr) : 0.f) + nrm * gO[ch];
-            G += gO[ch] * O;
-            gix += go * (v0 * cx[0] + v1 * cx[1] + v2 * cx[2] + v3 * cx[3]);
-            giy += go * (v0 * cy[0] + v1 * cy[1] + v2 * cy[2] + v3 * cy[3]);
+            const float gd = dr ? actf * __ldg(dr) : 0.f;
+            const float go = gd + nrm * gO[ch];
+            U[0] += gO[ch] * v0; U[1] += gO[ch] * v1; U[2] += gO[ch] * v2; U[3] += gO[ch] * v3;
+            Tq[0] += gd * v0; Tq[1] += gd * v1; Tq[2] += gd * v2; Tq[3] += gd * v3;
             if (dsrc) {
               atomicAdd(o0, t2.w[0] * go); atomicAdd(o0 + 1, t2.w[1] * go);
               atomicAdd(o1, t2.w[2] * go); atomicAdd(o1 + 1, t2.w[3] * go);
@@ -247,15 +335,21 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
             if (dr) dr += HWd;
           }
         }
+        float G = U[0] * t2.w[0] + U[1] * t2.w[1] + U[2] * t2.w[2] + U[3] * t2.w[3];
+        float gix = 0.f, giy = 0.f;
+        WB_UNROLL for (int j = 0; j < 4; ++j) {
+          const float tj = Tq[j] + nrm * U[j];
+          gix += tj * cx[j]; giy += tj * cy[j];
+        }
         if (!c.need_layers) continue;
         G += gO[C] * (score * 2.f - 1.f);
         const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
         const float dfx = (dfl ? actf * __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
         const float dfy = (dfl ? actf * __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
         const float gs = 2.f * nrm * gO[C] + (G - S) / D;
-        if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
-        else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
-        else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
       }
       if (c.self && a.d_input && active) {   // lvd.py:845: the target frame passes straight through
         const float nrm = (1.f + 1e-6f) / D;
@@ -264,23 +358,6 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
         WB_UNROLL for (int ch = 0; ch < NCH; ++ch)
           if (CC > 0 || ch < C) wb_atomic_add(o + (size_t)ch * HWd, (draw ? __ldg(draw + (size_t)ch * HWd) : 0.f) + nrm * gO[ch]);
       }
-    }
-    if (use_win) {   // flush the windows of this tile (all contexts)
-      __syncthreads();
-      const int per_tc = wcells * L * 2;
-      for (int e = wb_tid(); e < g.Tc * per_tc; e += wb_nthr()) {
-        const int tc = e / per_tc, r0 = e - tc * per_tc;
-        const int cell = r0 / (L * 2), r = r0 - cell * (L * 2), k = r >> 1, comp = r & 1;
-        const int cy = cell / c.ww + c.wy0, cx = cell % c.ww + c.wx0;
-        float* sv = s_win + (((size_t)tc * WB_WIN_CAP + cell) * L + k) * 2 + comp;
-        const float v = *sv;
-        if (v != 0.f) {
-          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-          atomicAdd(a.d_f_lo + ((pair * L + k) * c.HW + (size_t)cy * g.W + cx) * 2 + comp, v);
-          *sv = 0.f;
-        }
-      }
-      __syncthreads();
     }
   }
   if (a.d_occ) {
@@ -308,28 +385,30 @@ __global__ void k_occ_reduce(const float* __restrict__ part, int groups, int per
 }
 
 // ============================================================================ context-alpha backward (B4..B2b)
+#define WB_PSLOTS 4   // object slots staged per round for the class-profile reduction
 struct WbPrepBwdCtx {
   int b, t, L, Nl, HW;
-  size_t HWd;
+  unsigned HWd;
   bool filt, lowres_direct, need_p;
   const float *s_P, *s_occ, *lyt_base, *alo;
-  float *s_acc, *s_accp, *s_win;
-  int wy0, wx0, ww;
+  float *s_acc, *s_accp;
+  float* s_stage;    // this warp's staging area, max(WB_STAGE_SLOTS, 3 * WB_PSLOTS) * WB_WARP floats
 };
 
-template <int NA>
-WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, unsigned wm, bool active, size_t q, const WbAxis& ax, const WbAxis& ay,
-                              int o00, int o01, int o10, int o11) {
+template <int NA, int NLC>
+WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbColRed& cr, unsigned wm, float actf, unsigned q,
+                              const WbAxis& ax, const WbAxis& ay, int o00, int o01, int o10, int o11) {
+  constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
   const WbDec& d = a.f;
   const waldo_geom_t& g = d.g;
-  const int L = c.L, Nl = c.Nl, HW = c.HW, b = c.b, t = c.t;
-  const size_t HWd = c.HWd;
+  const int L = c.L, Nl = NLC > 0 ? NLC : c.Nl, HW = c.HW, b = c.b, t = c.t;
+  const unsigned HWd = c.HWd;
   const int lane = wb_lane();
   const WbIdx<NA> ix = wb_idx<NA>(wm);
   const bool any_obj = (wm >> 1) != 0u;
   // ---- recompute the forward of this pixel
-  float sm[WB_MAX_NL];
-  if (c.filt && any_obj) wb_softmax_hd(c.lyt_base, HWd, q, Nl, sm);
+  float sm[NN];
+  if (c.filt && any_obj) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
   float aup[NA], av[NA], ell[NA];
   WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
     av[s] = 0.f; aup[s] = 0.f; ell[s] = 1.f;
@@ -340,76 +419,123 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, unsigned w
                                 : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
       aup[s] = v;
       if (c.filt && k >= 1) {
+        const float* P = c.s_P + (k - 1) * Nl;
         float dist = 0.f;
-        WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) if (cc < Nl) dist += fabsf(c.s_P[(k - 1) * Nl + cc] - sm[cc]);
+        WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dist += fabsf(P[cc] - sm[cc]);
         ell[s] = 1.f - dist * 0.5f;
       }
       av[s] = v * ell[s];
     }
   }
-  // ---- upstream: scatter-accumulated d/dA plus the returned alpha = 2A - 1
+  // ---- upstream: scatter-accumulated d/dA plus the returned alpha = 2A - 1 (zero beyond the image edge)
   float gA[NA], ga[NA];
   WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
     ga[s] = 0.f; gA[s] = 0.f;
-    if (s < ix.n && active) {
+    if (s < ix.n) {
       const size_t o = (((size_t)b * g.Tw + t) * L + ix.k[s]) * HWd + q;
       float v = 0.f;
       if (a.d_alpha_acc) v += a.d_alpha_acc[o];
       if (a.d_alpha) v += 2.f * __ldg(a.d_alpha + o);
-      gA[s] = v;
+      gA[s] = v * actf;
     }
   }
   wb_occlude_bwd<NA>(av, gA, c.s_occ, L, ix, ga, c.s_acc);
-  // ---- filter + up-sampling backward
-  float gsm[WB_MAX_NL];
-  WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) gsm[cc] = 0.f;
-  const float w00 = ax.l0 * ay.l0, w01 = ax.l1 * ay.l0, w10 = ax.l0 * ay.l1, w11 = ax.l1 * ay.l1;
-  const int c00 = (ay.i0 - c.wy0) * c.ww + ax.i0 - c.wx0, c01 = (ay.i0 - c.wy0) * c.ww + ax.i1 - c.wx0;
-  const int c10 = (ay.i1 - c.wy0) * c.ww + ax.i0 - c.wx0, c11 = (ay.i1 - c.wy0) * c.ww + ax.i1 - c.wx0;
-  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
-    if (s < ix.n) {
-      const int k = ix.k[s];
-      const float gup = ga[s] * ell[s];
-      if (c.filt && k >= 1) {
-        const float gl = ga[s] * aup[s];   // d / d ell_k
-        WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) {
-          if (cc < Nl) {
-            const float df = c.s_P[(k - 1) * Nl + cc] - sm[cc];
-            const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
-            const float v = -0.5f * sg * gl;
-            gsm[cc] -= v;
-            if (c.need_p) {
-              float r = wb_warp_sum(v);
-              if (lane == 0) c.s_accp[(k - 1) * Nl + cc] += r;
+  // ---- filter backward: l_k = 1 - 0.5 sum_c |P_kc - sm_c|.  The sign pattern of each object slot is packed into
+  // two bit masks; d P (a sum over pixels) is reduced per warp by staging (masks, d l_k) of every lane and letting
+  // lane <-> (slot, class) entries walk the 32 pixels in lane order (deterministic, no shuffles).
+  float gsm[NN];
+  WB_UNROLL for (int cc = 0; cc < NN; ++cc) gsm[cc] = 0.f;
+  if (c.filt && any_obj) {
+    for (int s0 = 0; s0 < ix.n; s0 += WB_PSLOTS) {
+      int kk[WB_PSLOTS];
+      WB_UNROLL for (int j = 0; j < WB_PSLOTS; ++j) kk[j] = -1;
+      WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+        if (s >= s0 && s < s0 + WB_PSLOTS && s < ix.n && ix.k[s] >= 1) {
+          const int k = ix.k[s];
+          const float gl = ga[s] * aup[s];   // d / d l_k
+          const float* P = c.s_P + (k - 1) * Nl;
+          unsigned pos = 0u, neg = 0u;
+          WB_UNROLL for (int cc = 0; cc < NN; ++cc) {
+            if (NLC > 0 || cc < Nl) {
+              const float df = P[cc] - sm[cc];
+              if (df > 0.f) { pos |= 1u << cc; gsm[cc] += 0.5f * gl; }
+              else if (df < 0.f) { neg |= 1u << cc; gsm[cc] -= 0.5f * gl; }
             }
           }
+          if (c.need_p) {
+            unsigned* su = reinterpret_cast<unsigned*>(c.s_stage);
+            su[(3 * (s - s0)) * WB_WARP + lane] = pos;
+            su[(3 * (s - s0) + 1) * WB_WARP + lane] = neg;
+            c.s_stage[(3 * (s - s0) + 2) * WB_WARP + lane] = gl;
+          }
+          WB_UNROLL for (int j = 0; j < WB_PSLOTS; ++j) if (j == s - s0) kk[j] = k;
         }
       }
-      if (a.d_a_lo && gup != 0.f) {
-        if (c.lowres_direct) atomicAdd(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + o00, gup);
-        else {
-          atomicAdd(c.s_win + c00 * L + k, w00 * gup); atomicAdd(c.s_win + c01 * L + k, w01 * gup);
-          atomicAdd(c.s_win + c10 * L + k, w10 * gup); atomicAdd(c.s_win + c11 * L + k, w11 * gup);
+      if (c.need_p) {
+        __syncwarp();
+        const unsigned* su = reinterpret_cast<const unsigned*>(c.s_stage);
+        for (int e = lane; e < WB_PSLOTS * Nl; e += WB_WARP) {
+          const int j = e / Nl, cc = e - j * Nl;
+          int k = -1;
+          WB_UNROLL for (int jj = 0; jj < WB_PSLOTS; ++jj) if (jj == j) k = kk[jj];
+          if (k < 1) continue;
+          float acc = 0.f;
+          for (int l = 0; l < WB_WARP; ++l) {
+            const unsigned pm = su[(3 * j) * WB_WARP + l], nm = su[(3 * j + 1) * WB_WARP + l];
+            const float gl = c.s_stage[(3 * j + 2) * WB_WARP + l];
+            acc += ((pm >> cc) & 1u) ? -0.5f * gl : (((nm >> cc) & 1u) ? 0.5f * gl : 0.f);
+          }
+          c.s_accp[(k - 1) * Nl + cc] += acc;
         }
+        __syncwarp();
       }
     }
   }
-  if (c.filt && any_obj && a.d_input && active) {   // softmax backward into the layout logits of this frame
+  // ---- up-sampling backward: d a_lo
+  if (a.d_a_lo) {
+    if (c.lowres_direct) {
+      WB_UNROLL_NA for (int s = 0; s < NA; ++s)
+        if (s < ix.n) wb_atomic_add(a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s]) * HW + o00, ga[s] * ell[s]);
+    } else if constexpr (NA <= WB_STAGE_SLOTS) {
+      float* dst[NA];
+      WB_UNROLL for (int s = 0; s < NA; ++s) {
+        c.s_stage[s * WB_WARP + lane] = ga[s] * ell[s];
+        dst[s] = a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s]) * HW;
+      }
+      __syncwarp();
+      wb_colred_flush(cr, c.s_stage, ix.n, dst, g.W, 1);
+      __syncwarp();
+    } else {
+      for (int s0 = 0; s0 < ix.n; s0 += WB_STAGE_SLOTS) {
+        float* dst[WB_STAGE_SLOTS];
+        const int ns = min(WB_STAGE_SLOTS, ix.n - s0);
+        for (int j = 0; j < ns; ++j) {
+          c.s_stage[j * WB_WARP + lane] = ga[s0 + j] * ell[s0 + j];
+          dst[j] = a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s0 + j]) * HW;
+        }
+        __syncwarp();
+        wb_colred_flush(cr, c.s_stage, ns, dst, g.W, 1);
+        __syncwarp();
+      }
+    }
+  }
+  if (c.filt && any_obj && a.d_input && actf != 0.f) {   // softmax backward into the layout logits of this frame
     float dot = 0.f;
-    WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) if (cc < Nl) dot += gsm[cc] * sm[cc];
+    WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dot += gsm[cc] * sm[cc];
     float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd + q;
-    WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc)
-      if (cc < Nl) { const float v = sm[cc] * (gsm[cc] - dot); if (v != 0.f) o[(size_t)cc * HWd] += v; }
+    WB_UNROLL for (int cc = 0; cc < NN; ++cc)
+      if (NLC > 0 || cc < Nl) { const float v = sm[cc] * (gsm[cc] - dot); if (v != 0.f) *o += v; o += HWd; }
   }
 }
 
 // grid = (red_ctas, B*Tw), block = 256.
+template <int NLC>
 __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
   WbPrepBwdCtx c;
   const int No = g.No, Nl = g.Nl, L = No + 1;
-  c.L = L; c.Nl = Nl; c.HW = g.H * g.W; c.HWd = (size_t)g.Hd * g.Wd;
+  c.L = L; c.Nl = Nl; c.HW = g.H * g.W; c.HWd = (unsigned)(g.Hd * g.Wd);
   const int bt = blockIdx.y;
   c.b = bt / g.Tw; c.t = bt - c.b * g.Tw;
   c.filt = (g.flags & WALDO_F_FILTER) != 0;
@@ -419,14 +545,14 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
   __shared__ float s_redp[WB_NWARP][(WB_MAX_L - 1) * WB_MAX_NL];
-  __shared__ float s_win[WB_WIN_CAP * WB_MAX_L];
+  __shared__ float s_stage[WB_NWARP][(3 * WB_PSLOTS > WB_STAGE_SLOTS ? 3 * WB_PSLOTS : WB_STAGE_SLOTS) * WB_WARP];
+  __shared__ float s_geo[WB_NWARP][4 * WB_WARP];
   if (c.filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)c.b * No * Nl + i];
   for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + c.t) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
   for (int i = wb_tid(); i < WB_NWARP * (WB_MAX_L - 1) * WB_MAX_NL; i += wb_nthr()) (&s_redp[0][0])[i] = 0.f;
-  for (int i = wb_tid(); i < WB_WIN_CAP * WB_MAX_L; i += wb_nthr()) s_win[i] = 0.f;
   __syncthreads();
-  c.s_P = s_P; c.s_occ = s_occ; c.s_win = s_win;
+  c.s_P = s_P; c.s_occ = s_occ; c.s_stage = s_stage[wb_warp()];
   c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
   c.s_accp = s_redp[wb_warp()];
   const float rlo = (float)g.H / (float)g.Hd;
@@ -436,34 +562,21 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
-    c.wy0 = wb_axis(ty0, rlo, g.H).i0; c.wx0 = wb_axis(tx0, rlo, g.W).i0;
-    const int wy1 = wb_axis(min(ty0 + WB_TILE_H, g.Hd) - 1, rlo, g.H).i1, wx1 = wb_axis(min(tx0 + WB_TILE_W, g.Wd) - 1, rlo, g.W).i1;
-    c.ww = wx1 - c.wx0 + 1;
-    const int wcells = c.ww * (wy1 - c.wy0 + 1);
     for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
-      const int X = tx0 + (it & (WB_TILE_W - 1)), Y = ty0 + it / WB_TILE_W;
-      const bool active = X < g.Wd && Y < g.Hd;
-      const size_t q = active ? (size_t)Y * g.Wd + X : 0;
-      WbAxis ay = wb_axis(active ? Y : 0, rlo, g.H), ax = wb_axis(active ? X : 0, rlo, g.W);
+      const int Xr = tx0 + (it & (WB_TILE_W - 1)), Yr = ty0 + it / WB_TILE_W;
+      const float actf = (Xr < g.Wd && Yr < g.Hd) ? 1.f : 0.f;   // beyond the edge: nearest valid pixel, zero upstream
+      const int X = min(Xr, g.Wd - 1), Y = min(Yr, g.Hd - 1);
+      const unsigned q = (unsigned)(Y * g.Wd + X);
+      WbAxis ay = wb_axis(Y, rlo, g.H), ax = wb_axis(X, rlo, g.W);
       const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
-      const unsigned mine = active ? wb_live4(live, o00, o01, o10, o11) : 0u;
-      const unsigned wm = wb_warp_or(mine);
+      const unsigned wm = wb_warp_or(wb_live4(live, o00, o01, o10, o11));
       const int n = __popc(wm);
       if (n == 0) continue;   // warp-uniform: nothing live here, every gradient path is dead
-      if (n <= 4) wb_prep_bwd_pixel<4>(a, c, wm, active, q, ax, ay, o00, o01, o10, o11);
-      else if (n <= 8) wb_prep_bwd_pixel<8>(a, c, wm, active, q, ax, ay, o00, o01, o10, o11);
-      else wb_prep_bwd_pixel<WB_MAX_L>(a, c, wm, active, q, ax, ay, o00, o01, o10, o11);
-    }
-    if (a.d_a_lo && !c.lowres_direct) {
-      __syncthreads();
-      for (int e = wb_tid(); e < wcells * L; e += wb_nthr()) {
-        const int cell = e / L, k = e - cell * L;
-        const int cy = cell / c.ww + c.wy0, cx = cell % c.ww + c.wx0;
-        float* sv = s_win + (size_t)cell * L + k;
-        const float v = *sv;
-        if (v != 0.f) { atomicAdd(a.d_a_lo + (((size_t)c.b * g.Tw + c.t) * L + k) * c.HW + (size_t)cy * g.W + cx, v); *sv = 0.f; }
-      }
-      __syncthreads();
+      WbColRed cr;
+      if (a.d_a_lo && !c.lowres_direct) cr = wb_colred_setup(ax, ay, s_geo[wb_warp()]);
+      if (n <= 4) wb_prep_bwd_pixel<4, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
+      else if (n <= 8) wb_prep_bwd_pixel<8, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
+      else wb_prep_bwd_pixel<WB_MAX_L, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
     }
   }
   __syncthreads();
@@ -738,26 +851,11 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   if (a.d_occ) WB_BREQ(a.occ_part, "occ_part scratch missing");
   if (geom) WB_BREQ(a.d_f_lo && a.d_a_lo && a.d_alpha_acc, "geometry gradients need d_f_lo, d_a_lo, d_alpha_acc scratch");
   if (a.d_obj_alpha || a.d_bg_alpha || a.d_cls) WB_BREQ(a.d_a_lo && a.d_alpha_acc, "alpha gradients need d_a_lo, d_alpha_acc scratch");
-  if (g.Hd != g.H) {
-    // window capacity of the shared-memory low-res accumulators
-    const float r = (float)g.H / (float)g.Hd;
-    const int wh = (int)ceilf((WB_TILE_H - 1) * r) + 2, wwid = (int)ceilf((WB_TILE_W - 1) * r) + 2;
-    WB_BREQ(wh * wwid <= WB_WIN_CAP, "scale_hd too small for the compiled low-res window (needs scale_hd >= 2)");
-  }
+  if (g.Hd != g.H) WB_BREQ(g.Hd >= 2 * g.H && g.Hd <= 4 * g.H, "backward supports scale_hd in {1} or [2, 4]");
   // 1. fused HD backward
   if (a.stages == 0 || (a.stages & 1)) {
-    const size_t win_bytes = (a.d_f_lo && g.Hd != g.H) ? (size_t)g.Tc * WB_WIN_CAP * L * 2 * sizeof(float) : 0;
-    WB_BREQ(win_bytes <= 200 * 1024, "Tc too large for the shared-memory flow window");
+    const size_t win_bytes = 0;
     const dim3 bgrid(a.red_ctas, g.B * g.Tp);
-#ifndef WB_HOST_EMU
-    if (win_bytes > 48 * 1024) {
-      cudaFuncSetAttribute(k_warp_composite_bwd<23>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes);
-      cudaFuncSetAttribute(k_warp_composite_bwd<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes);
-      cudaFuncSetAttribute(k_warp_composite_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes);
-    }
-#else
-    WB_BREQ(win_bytes <= sizeof(wb_dyn_smem_buf), "emulation smem buffer too small");
-#endif
     if (g.C == 23) WB_LAUNCH(k_warp_composite_bwd<23>, bgrid, dim3(WB_TILE_PX), win_bytes, st, a);
     else if (g.C == 22) WB_LAUNCH(k_warp_composite_bwd<22>, bgrid, dim3(WB_TILE_PX), win_bytes, st, a);
     else WB_LAUNCH(k_warp_composite_bwd<0>, bgrid, dim3(WB_TILE_PX), win_bytes, st, a);
@@ -771,7 +869,10 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   // 2. context-alpha backward
   if (a.d_alpha_acc || a.d_alpha) {
     if (filt && a.d_prof_p) WB_BREQ(a.prof_p_part, "prof_p_part scratch missing");
-    WB_LAUNCH(k_alpha_prep_bwd, dim3(a.red_ctas, g.B * g.Tw), dim3(WB_TILE_PX), 0, st, a);
+    const dim3 pgrid(a.red_ctas, g.B * g.Tw);
+    if (g.Nl == 20) WB_LAUNCH(k_alpha_prep_bwd<20>, pgrid, dim3(WB_TILE_PX), 0, st, a);
+    else if (g.Nl == 19) WB_LAUNCH(k_alpha_prep_bwd<19>, pgrid, dim3(WB_TILE_PX), 0, st, a);
+    else WB_LAUNCH(k_alpha_prep_bwd<0>, pgrid, dim3(WB_TILE_PX), 0, st, a);
     WB_BLAUNCHED();
     if (a.d_occ) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tw), dim3(128), 0, st, a.occ_part, g.B * g.Tw, g.Tw, a.red_ctas, L * L, g.T, d.pred_ts, 1, a.d_occ);

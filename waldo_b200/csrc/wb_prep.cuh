@@ -188,26 +188,31 @@ struct WbPrepCtx {
   float* out;
 };
 
-// softmax of the HD layout logits of pixel q (lvd.py:744)
-WB_DEV void wb_softmax_hd(const float* __restrict__ lyt_base, size_t HWd, size_t q, int Nl, float* sm) {
-  float lyt[WB_MAX_NL];
-  WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) lyt[c] = __ldg(lyt_base + c * HWd + q);
+// softmax of the HD layout logits of pixel q (lvd.py:744).  NLC = compile-time class count (0: run-time Nl).
+template <int NLC>
+WB_DEV void wb_softmax_hd(const float* __restrict__ lyt_base, unsigned HWd, unsigned q, int Nl, float* sm) {
+  constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
+  float lyt[NN];
+  const float* p = lyt_base + q;
+  WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { lyt[c] = __ldg(p); p += HWd; }
   float mx = lyt[0];
-  WB_UNROLL for (int c = 1; c < WB_MAX_NL; ++c) if (c < Nl) mx = fmaxf(mx, lyt[c]);
+  WB_UNROLL for (int c = 1; c < NN; ++c) if (NLC > 0 || c < Nl) mx = fmaxf(mx, lyt[c]);
   float s = 0.f;
-  WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) { sm[c] = expf(lyt[c] - mx); s += sm[c]; }
+  WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { sm[c] = expf(lyt[c] - mx); s += sm[c]; }
   const float inv = 1.f / s;
-  WB_UNROLL for (int c = 0; c < WB_MAX_NL; ++c) if (c < Nl) sm[c] *= inv;
+  WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) sm[c] *= inv;
 }
 
-template <int NA>
-WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, bool active, size_t q, const WbAxis& ax, const WbAxis& ay,
+template <int NA, int NLC>
+WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, unsigned q, const WbAxis& ax, const WbAxis& ay,
                           int o00, int o01, int o10, int o11) {
+  constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
   const waldo_geom_t& g = d.g;
-  const int L = c.L, Nl = c.Nl;
+  const int L = c.L, Nl = NLC > 0 ? NLC : c.Nl;
+  const unsigned HWd = (unsigned)c.HWd;
   const WbIdx<NA> ix = wb_idx<NA>(wm);
-  float sm[WB_MAX_NL];
-  if (c.filt && (wm >> 1)) wb_softmax_hd(c.lyt_base, c.HWd, q, Nl, sm);
+  float sm[NN];
+  if (c.filt && (wm >> 1)) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
   float a[NA];
   WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
     a[s] = 0.f;
@@ -217,24 +222,28 @@ WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, bool 
       float v = (g.Hd == g.H) ? __ldg(pl + o00)
                               : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
       if (c.filt && k >= 1) {
+        const float* P = c.s_P + (k - 1) * Nl;
         float dist = 0.f;
-        WB_UNROLL for (int cc = 0; cc < WB_MAX_NL; ++cc) if (cc < Nl) dist += fabsf(c.s_P[(k - 1) * Nl + cc] - sm[cc]);
+        WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dist += fabsf(P[cc] - sm[cc]);
         v *= 1.f - dist * 0.5f;
       }
       a[s] = v;
     }
   }
-  if (!active) return;
-  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) if (k < L && !((wm >> k) & 1u)) c.out[(size_t)k * c.HWd + q] = -1.f;
+  float* o = c.out + q;
+  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) *o = -1.f; o += HWd; }
+  o = c.out + q;
   WB_UNROLL_NA for (int i = 0; i < NA; ++i) {
     if (i < ix.n) {
+      const float* oc = c.s_occ + ix.k[i];
       float vis = 1.f;
-      WB_UNROLL_NA for (int j = 0; j < NA; ++j) if (j < ix.n) vis *= 1.f - a[j] * c.s_occ[ix.k[j] * L + ix.k[i]];
-      c.out[(size_t)ix.k[i] * c.HWd + q] = (vis * a[i]) * 2.f - 1.f;
+      WB_UNROLL_NA for (int j = 0; j < NA; ++j) if (j < ix.n) vis *= 1.f - a[j] * oc[ix.k[j] * L];
+      o[(size_t)ix.k[i] * HWd] = (vis * a[i]) * 2.f - 1.f;
     }
   }
 }
 
+template <int NLC>
 __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep(WbDec d) {
   const waldo_geom_t g = d.g;
   WbPrepCtx c;
@@ -257,17 +266,16 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep(WbDec d) {
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
     for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
-      const int X = tx0 + (it & (WB_TILE_W - 1)), Y = ty0 + it / WB_TILE_W;
-      const bool active = X < g.Wd && Y < g.Hd;
-      const size_t q = active ? (size_t)Y * g.Wd + X : 0;
-      WbAxis ay = wb_axis(active ? Y : 0, r, g.H), ax = wb_axis(active ? X : 0, r, g.W);
+      // threads beyond the image edge recompute (and re-store, identically) the nearest valid pixel: no predicates
+      const int X = min(tx0 + (it & (WB_TILE_W - 1)), g.Wd - 1), Y = min(ty0 + it / WB_TILE_W, g.Hd - 1);
+      const unsigned q = (unsigned)(Y * g.Wd + X);
+      WbAxis ay = wb_axis(Y, r, g.H), ax = wb_axis(X, r, g.W);
       const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
-      const unsigned mine = active ? wb_live4(live, o00, o01, o10, o11) : 0u;
-      const unsigned wm = wb_warp_or(mine);
+      const unsigned wm = wb_warp_or(wb_live4(live, o00, o01, o10, o11));
       const int n = __popc(wm);
-      if (n <= 4) wb_prep_pixel<4>(d, c, wm, active, q, ax, ay, o00, o01, o10, o11);
-      else if (n <= 8) wb_prep_pixel<8>(d, c, wm, active, q, ax, ay, o00, o01, o10, o11);
-      else wb_prep_pixel<WB_MAX_L>(d, c, wm, active, q, ax, ay, o00, o01, o10, o11);
+      if (n <= 4) wb_prep_pixel<4, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
+      else if (n <= 8) wb_prep_pixel<8, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
+      else wb_prep_pixel<WB_MAX_L, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
     }
   }
 }
