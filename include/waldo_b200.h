@@ -204,6 +204,7 @@ typedef struct {
   float* occ_part;            /* (max(B*Tp, B*Tw), red_ctas, L*L) */
   float* prof_p_part;         /* (B*Tw, red_ctas, No*Nl) */
   float* cls_part;            /* (B, prof_ctas, No*Nl) */
+  float* up_tab;              /* scratch (W, 9): per low-res column, first HD column touching it and its 8 x-weights */
   int stages;                 /* 0 = everything; else bit 0 = fused HD backward kernel, bit 1 = the rest of the chain */
 } waldo_decode_bwd_t;
 int waldo_decode_bwd(const waldo_decode_bwd_t*, waldo_stream_t);

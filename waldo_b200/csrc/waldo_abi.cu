@@ -125,6 +125,7 @@ int waldo_occ_bwd(int BT, int No, const float* score, const float* docc, float* 
 static int wb_check_geom(const waldo_geom_t& g, const char* who) {
   WB_REQUIRE(g.B > 0 && g.T > 0 && g.Tw > 0 && g.Tc > 0 && g.Tp > 0, "%s: bad batch/time sizes", who);
   WB_REQUIRE(g.Tw <= g.T, "%s: Tw > T", who);
+  WB_REQUIRE(g.Tc <= 8, "%s: %d contexts exceed the compiled maximum 8", who, g.Tc);
   WB_REQUIRE(g.No >= 1 && g.No + 1 <= WB_MAX_L, "%s: num_obj=%d unsupported (compiled max %d)", who, g.No, WB_MAX_L - 1);
   WB_REQUIRE(g.Nl >= 1 && g.Nl <= WB_MAX_NL, "%s: num_lyt=%d unsupported (compiled max %d)", who, g.Nl, WB_MAX_NL);
   WB_REQUIRE(g.C == 3 + g.Nl && g.C <= WB_MAX_C, "%s: C=%d must equal 3+num_lyt and be <= %d", who, g.C, WB_MAX_C);
@@ -184,9 +185,8 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   // B5(up)-B9 + stage C
   if (st_main) {
     const dim3 grid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tp);
-    if (g.C == 23) WB_LAUNCH(k_warp_composite_fwd<23>, grid, dim3(WB_TILE_PX), 0, st, *a);        // Cityscapes: 3 + 20
-    else if (g.C == 22) WB_LAUNCH(k_warp_composite_fwd<22>, grid, dim3(WB_TILE_PX), 0, st, *a);   // KITTI: 3 + 19
-    else WB_LAUNCH(k_warp_composite_fwd<0>, grid, dim3(WB_TILE_PX), 0, st, *a);
+    if (g.Tc <= 4) WB_LAUNCH(k_warp_composite_fwd<4>, grid, dim3(WB_TILE_PX), 0, st, *a);
+    else WB_LAUNCH(k_warp_composite_fwd<8>, grid, dim3(WB_TILE_PX), 0, st, *a);
     WB_LAUNCHED();
   }
   return 0;

@@ -106,6 +106,14 @@ WB_DEV int wb_warp() {
   return (int)(threadIdx.x >> 5);
 #endif
 }
+// value of lane `src` (all 32 lanes must call it)
+WB_DEV int wb_shfl(int v, int src) {
+#ifdef WB_HOST_EMU
+  return v;
+#else
+  return __shfl_sync(0xffffffffu, v, src);
+#endif
+}
 // OR over the warp (all 32 lanes must call it)
 WB_DEV unsigned wb_warp_or(unsigned m) {
 #ifdef WB_HOST_EMU

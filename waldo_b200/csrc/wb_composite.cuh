@@ -130,14 +130,17 @@ WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, un
   flow_x = ly.flow_x; flow_y = ly.flow_y; score = ly.score;
 }
 
-// grid = (CTAs, B*Tp); one thread per HD pixel (32x8 tiles), contexts looped inside so that the fused `output`
-// (lvd.py:850-851) never leaves registers.  CC = compile-time channel count (0: generic, channel count read at run time).
-template <int CC>
+// grid = (CTAs, B*Tp); one thread per HD pixel (32x8 tiles).  Two phases per pixel:
+//   1. per context: the layer part (flows, warped opacities, compositing) -> alpha channels, flow, and the taps of
+//      the reduced flow kept in registers (TCAP contexts at most);
+//   2. ONE rolled loop over the C image channels with the contexts unrolled inside: every channel of every context
+//      frame is gathered, stored to raw_output and fused into `output` (lvd.py:850-851) on the fly, so no per-channel
+//      accumulator array is needed and the code stays small (instruction-cache friendly).
+template <int TCAP>
 __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
-  constexpr int NCH = CC > 0 ? CC : WB_MAX_C;
   const waldo_geom_t g = d.g;
   WbFwdCtx c;
-  c.L = g.No + 1; c.HW = g.H * g.W; c.C = CC > 0 ? CC : g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
+  c.L = g.No + 1; c.HW = g.H * g.W; c.C = g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
   const int btp = blockIdx.y;
   c.b = btp / g.Tp; c.tp = btp - c.b * g.Tp;
   const int u = (int)d.pred_ts[c.tp];
@@ -145,11 +148,20 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
   c.disocc_ch = (g.flags & WALDO_F_USE_DISOCC) != 0;
   c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0);
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
+  __shared__ const float* s_src[TCAP];   // context frame of every context (CTA-uniform)
+  __shared__ float* s_raw[TCAP];         // raw_output block of every context
+  __shared__ int s_ct[TCAP];
   for (int i = wb_tid(); i < c.L * c.L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + u) * c.L * c.L + i);
-  __syncthreads();
-  c.s_occ = s_occ;
   const int C = c.C, b = c.b, tp = c.tp;
   const unsigned HWd = c.HWd;
+  for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    s_ct[tc] = c_t;
+    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
+    s_raw[tc] = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
+  }
+  __syncthreads();
+  c.s_occ = s_occ;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
@@ -160,51 +172,58 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
       WbPix px = wb_pix(d, b, tp, X, Y);
       const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
-      float acc[NCH + 1];
-      WB_UNROLL for (int ch = 0; ch <= NCH; ++ch) acc[ch] = 0.f;
-      float den = 0.f;
-      for (int tc = 0; tc < g.Tc; ++tc) {
-        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-        float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
-        float flow_x, flow_y, score;
-        if (n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
-        else if (n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
-        else wb_fwd_layers<WB_MAX_L>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
-        // stage C: warp the context frame by the reduced flow; channels walked with running pointers
-        const WbTaps t = wb_taps(__fadd_rn(px.gx, flow_x), __fadd_rn(px.gy, flow_y), g.Wd, g.Hd);
-        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-        const float* src = d.input + ((size_t)b * g.T + c_t) * C * HWd;
-        const float* p0 = src + t2.o0;
-        const float* p1 = src + t2.o1;
-        const float wgt = score + 1e-6f;
-        float* rp = raw + q;
-        WB_UNROLL for (int ch = 0; ch < NCH; ++ch) {
-          if (CC > 0 || ch < C) {
-            const float v = wb_gather2(p0, p1, t2.w);
-            *rp = v; acc[ch] += wgt * v;
-            p0 += HWd; p1 += HWd; rp += HWd;
-          }
+      // ---- phase 1: layers of every context
+      unsigned o0[TCAP], o1[TCAP];
+      float w[TCAP][4], wgt[TCAP];
+      float den = 0.f, accs = 0.f;
+      WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+        o0[tc] = 0u; o1[tc] = 0u; wgt[tc] = 0.f;
+        WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = 0.f;
+        if (tc < g.Tc) {
+          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+          float flow_x, flow_y, score;
+          if (n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
+          else if (n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
+          else wb_fwd_layers<WB_MAX_L>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
+          const WbTaps t = wb_taps(__fadd_rn(px.gx, flow_x), __fadd_rn(px.gy, flow_y), g.Wd, g.Hd);
+          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+          o0[tc] = t2.o0; o1[tc] = t2.o1;
+          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = t2.w[j];
+          wgt[tc] = score + 1e-6f;
+          den += wgt[tc];
+          accs += wgt[tc] * (score * 2.f - 1.f);
         }
-        acc[NCH] += wgt * (score * 2.f - 1.f);
-        den += wgt;
       }
+      const float* self_src = nullptr;
+      float* self_raw = nullptr;
+      float wself = 0.f;
       if (c.self) {   // lvd.py:842-845: the target frame itself, fully opaque, score 1
-        float* raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd;
-        const float* src = d.input + ((size_t)b * g.T + tp) * C * HWd;
-        const float wgt = 1.f + 1e-6f;
-        WB_UNROLL for (int ch = 0; ch < NCH; ++ch) {
-          if (CC > 0 || ch < C) { float v = __ldg(src + ch * HWd + q); raw[ch * HWd + q] = v; acc[ch] += wgt * v; }
-        }
-        for (int k = 0; k < c.L; ++k) raw[(C + k) * HWd + q] = 1.f;
-        if (c.disocc_ch) raw[(C + c.L) * HWd + q] = 1.f;
-        acc[NCH] += wgt * 1.f;
-        den += wgt;
+        self_raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q;
+        self_src = d.input + ((size_t)b * g.T + tp) * C * HWd + q;
+        wself = 1.f + 1e-6f;
+        for (int k = 0; k < c.L; ++k) self_raw[(size_t)(C + k) * HWd] = 1.f;
+        if (c.disocc_ch) self_raw[(size_t)(C + c.L) * HWd] = 1.f;
+        den += wself; accs += wself;
       }
       const float inv = 1.f / fmaxf(den, 1e-12f);
+      // ---- phase 2: image channels, contexts inside
       float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
-      WB_UNROLL for (int ch = 0; ch < NCH; ++ch) if (CC > 0 || ch < C) { *of = acc[ch] * inv; of += HWd; }
-      *of = acc[NCH] * inv;
+      unsigned choff = 0u;   // ch * HWd
+      for (int ch = 0; ch < C; ++ch) {
+        float acc = 0.f;
+        WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+          if (tc < g.Tc) {
+            const float* pl = s_src[tc] + choff;
+            const float v = wb_gather2(pl + o0[tc], pl + o1[tc], w[tc]);
+            s_raw[tc][choff + q] = v;
+            acc += wgt[tc] * v;
+          }
+        }
+        if (c.self) { const float v = __ldg(self_src + choff); self_raw[choff] = v; acc += wself * v; }
+        of[choff] = acc * inv;
+        choff += HWd;
+      }
+      of[choff] = accs * inv;
       if (d.norm) d.norm[((size_t)b * g.Tp + tp) * HWd + q] = den;
     }
   }

@@ -37,43 +37,51 @@ WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) atomicAdd(p, v); }
 
 struct WbColRed {
   int col[WB_CPL];                 // absolute low-res column owned by this lane (-1: none)
-  int lo[WB_CPL];                  // first contributing lane
+  int lo[WB_CPL];                  // lane of the first contributing HD column (may be negative: previous warp's pixel)
   float w[WB_CPL][WB_COL_TAPS];    // x-weights of lanes lo .. lo+7
   int row0, row1;                  // the two low-res rows (same for the whole warp)
   float wy0, wy1;
 };
 
-// s_geo: per-warp scratch of 4*WB_WARP floats
-WB_DEV WbColRed wb_colred_setup(const WbAxis& ax, const WbAxis& ay, float* s_geo) {
+// up_tab[col] = { first HD column X whose up-sampling taps touch low-res column col with non-zero weight,
+//                 the x-weights of X, X+1, ..., X+7 }   -- depends on (W, Wd) only
+__global__ void k_up_tab(int W, int Wd, float* __restrict__ tab) {
+  const float r = (float)W / (float)Wd;
+  for (int col = blockIdx.x * wb_nthr() + wb_tid(); col < W; col += gridDim.x * wb_nthr()) {
+    int lo = -1;
+    float w[WB_COL_TAPS];
+    for (int t = 0; t < WB_COL_TAPS; ++t) w[t] = 0.f;
+    for (int X = 0; X < Wd; ++X) {
+      const WbAxis ax = wb_axis(X, r, W);
+      const float wv = (ax.i0 == col ? ax.l0 : 0.f) + (ax.i1 == col ? ax.l1 : 0.f);
+      if (wv != 0.f) {
+        if (lo < 0) lo = X;
+        if (X - lo < WB_COL_TAPS) w[X - lo] = wv;
+      }
+    }
+    tab[col * 9] = (float)(lo < 0 ? 0 : lo);
+    for (int t = 0; t < WB_COL_TAPS; ++t) tab[col * 9 + 1 + t] = w[t];
+  }
+}
+
+// x0 = HD column of lane 0 of this warp; (i0_first, i1_last) = low-res columns of the first / last lane
+WB_DEV WbColRed wb_colred_setup(const float* __restrict__ tab, int x0, int i0_first, int i1_last, const WbAxis& ay) {
   const int lane = wb_lane();
-  int* gi = reinterpret_cast<int*>(s_geo);
-  gi[lane] = ax.i0; gi[WB_WARP + lane] = ax.i1;
-  s_geo[2 * WB_WARP + lane] = ax.l0; s_geo[3 * WB_WARP + lane] = ax.l1;
-  __syncwarp();
   WbColRed cr;
   cr.row0 = ay.i0; cr.row1 = ay.i1; cr.wy0 = ay.l0; cr.wy1 = ay.l1;
-  const int colbase = gi[0], ncols = max(gi[2 * WB_WARP - 1], gi[WB_WARP - 1]) - colbase + 1;
+  const int ncols = i1_last - i0_first + 1;
   WB_UNROLL for (int cpl = 0; cpl < WB_CPL; ++cpl) {
     const int jj = lane + cpl * WB_WARP;
     cr.col[cpl] = -1; cr.lo[cpl] = 0;
     WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) cr.w[cpl][t] = 0.f;
     if (jj < ncols) {
-      const int col = colbase + jj;
+      const int col = i0_first + jj;
       cr.col[cpl] = col;
-      int lo = -1;
-      for (int l = 0; l < WB_WARP; ++l) {
-        const bool h0 = gi[l] == col, h1 = gi[WB_WARP + l] == col;
-        if (h0 || h1) {
-          if (lo < 0) lo = l;
-          const float wv = (h0 ? s_geo[2 * WB_WARP + l] : 0.f) + (h1 ? s_geo[3 * WB_WARP + l] : 0.f);
-          const int t = l - lo;
-          WB_UNROLL for (int tt = 0; tt < WB_COL_TAPS; ++tt) if (tt == t) cr.w[cpl][tt] = wv;
-        }
-      }
-      cr.lo[cpl] = lo < 0 ? 0 : lo;
+      const float* e = tab + col * 9;
+      cr.lo[cpl] = (int)__ldg(e) - x0;
+      WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) cr.w[cpl][t] = __ldg(e + 1 + t);
     }
   }
-  __syncwarp();
   return cr;
 }
 
@@ -84,7 +92,7 @@ WB_DEV void wb_colred_flush(const WbColRed& cr, const float* s_stage, int nv, fl
       for (int v = 0; v < nv; ++v) {
         const float* sv = s_stage + v * WB_WARP + cr.lo[cpl];
         float acc = 0.f;
-        WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) if (cr.lo[cpl] + t < WB_WARP) acc += cr.w[cpl][t] * sv[t];
+        WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) if (cr.lo[cpl] + t >= 0 && cr.lo[cpl] + t < WB_WARP) acc += cr.w[cpl][t] * sv[t];
         if (acc != 0.f) {
           atomicAdd(dst[v] + ((size_t)cr.row0 * W + cr.col[cpl]) * stride, acc * cr.wy0);
           atomicAdd(dst[v] + ((size_t)cr.row1 * W + cr.col[cpl]) * stride, acc * cr.wy1);
@@ -240,15 +248,17 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
   }
 }
 
-// grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration); dynamic smem = Tc*WB_WIN_CAP*L*2 floats.
-// CC = compile-time channel count (0: generic).
-template <int CC>
+// grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration).  Three phases per pixel (see the forward):
+//   1. per context: recompute the layer forward -> reduced flow, score, taps;
+//   2. ONE rolled loop over the image channels, contexts unrolled inside: scatter d input, and accumulate the
+//      bilinear moments U = sum_ch dOut*v_tap, T = sum_ch dRaw*v_tap from which d score and d flow follow;
+//   3. per context: backward of the layer part.
+template <int TCAP>
 __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) {
-  constexpr int NCH = CC > 0 ? CC : WB_MAX_C;
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
   WbBwdCtx c;
-  c.L = g.No + 1; c.HW = g.H * g.W; c.C = CC > 0 ? CC : g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
+  c.L = g.No + 1; c.HW = g.H * g.W; c.C = g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
   const int btp = blockIdx.y;
   c.b = btp / g.Tp; c.tp = btp - c.b * g.Tp;
   const int u = (int)d.pred_ts[c.tp];
@@ -262,12 +272,23 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
   __shared__ float s_stage[WB_NWARP][2 * WB_STAGE_SLOTS * WB_WARP];
-  __shared__ float s_geo[WB_NWARP][4 * WB_WARP];
+  __shared__ const float* s_src[TCAP];    // context frame of every context (CTA-uniform)
+  __shared__ float* s_dsrc[TCAP];         // its gradient
+  __shared__ const float* s_draw[TCAP];   // upstream d raw_output block of every context (or null)
+  __shared__ int s_ct[TCAP];
   for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + u) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
+  for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    s_ct[tc] = c_t;
+    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
+    s_dsrc[tc] = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * C * HWd : nullptr;
+    s_draw[tc] = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd : nullptr;
+  }
   __syncthreads();
   c.s_occ = s_occ; c.s_stage = s_stage[wb_warp()];
   c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
+  const bool has_din = a.d_input != nullptr, has_draw = a.d_raw_output != nullptr;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
@@ -281,82 +302,88 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
       const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
       WbColRed cr;
-      if (a.d_f_lo && !c.lowres_direct) cr = wb_colred_setup(px.ax, px.ay, s_geo[wb_warp()]);
-      float gO[NCH + 1];   // upstream d out_full; the score channel sits at index C (as in memory)
-      float S = 0.f;
-      {
-        const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
-        const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
-        WB_UNROLL for (int ch = 0; ch <= NCH; ++ch) {
-          gO[ch] = 0.f;
-          if ((CC > 0 || ch <= C) && dof) { gO[ch] = actf * __ldg(dof + (size_t)ch * HWd); S += gO[ch] * __ldg(of + (size_t)ch * HWd); }
+      if (a.d_f_lo && !c.lowres_direct)
+        cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(px.ax.i0, 0), wb_shfl(px.ax.i1, WB_WARP - 1), px.ay);
+      const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
+      // ---- phase 1
+      unsigned o0[TCAP], o1[TCAP];
+      float w[TCAP][4], nrm[TCAP], U[TCAP][4], Tq[TCAP][4], flx[TCAP], fly[TCAP], sco[TCAP];
+      WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+        o0[tc] = 0u; o1[tc] = 0u; nrm[tc] = 0.f; flx[tc] = 0.f; fly[tc] = 0.f; sco[tc] = 0.f;
+        WB_UNROLL for (int j = 0; j < 4; ++j) { w[tc][j] = 0.f; U[tc][j] = 0.f; Tq[tc][j] = 0.f; }
+        if (tc < g.Tc) {
+          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+          if (n <= 4) wb_bwd_layers_fwd<4>(d, c, px, wm, s_ct[tc], pair, flx[tc], fly[tc], sco[tc]);
+          else if (n <= 8) wb_bwd_layers_fwd<8>(d, c, px, wm, s_ct[tc], pair, flx[tc], fly[tc], sco[tc]);
+          else wb_bwd_layers_fwd<WB_MAX_L>(d, c, px, wm, s_ct[tc], pair, flx[tc], fly[tc], sco[tc]);
+          const WbTaps t = wb_taps(__fadd_rn(px.gx, flx[tc]), __fadd_rn(px.gy, fly[tc]), g.Wd, g.Hd);
+          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+          o0[tc] = t2.o0; o1[tc] = t2.o1;
+          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = t2.w[j];
+          nrm[tc] = (sco[tc] + 1e-6f) / D;
         }
       }
-      const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
-      for (int tc = 0; tc < g.Tc; ++tc) {
-        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-        float flow_x, flow_y, score;
-        if (n <= 4) wb_bwd_layers_fwd<4>(d, c, px, wm, c_t, pair, flow_x, flow_y, score);
-        else if (n <= 8) wb_bwd_layers_fwd<8>(d, c, px, wm, c_t, pair, flow_x, flow_y, score);
-        else wb_bwd_layers_fwd<WB_MAX_L>(d, c, px, wm, c_t, pair, flow_x, flow_y, score);
-        const float wgt = score + 1e-6f, nrm = wgt / D;
-        // upstream pointers are warp-uniformly null or valid; threads beyond the edge scale what they read by actf = 0
-        const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
-        // ---- stage C backward: warped context frame
-        const WbTaps t = wb_taps(__fadd_rn(px.gx, flow_x), __fadd_rn(px.gy, flow_y), g.Wd, g.Hd);
-        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-        float cx[4], cy[4];
-        wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
-        wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
-        const float* src = d.input + ((size_t)b * g.T + c_t) * C * HWd;
-        const float* p0 = src + t2.o0;
-        const float* p1 = src + t2.o1;
-        float* dsrc = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * C * HWd : nullptr;
-        float* o0 = dsrc + t2.o0;
-        float* o1 = dsrc + t2.o1;
-        const float* dr = draw;
-        // G = sum_ch gO*O, gix/giy = sum_ch go * dO/d(ix,iy) are bilinear in the four tap values: accumulate
-        // U_pos = sum_ch gO*v_pos and T_pos = sum_ch draw*v_pos once, combine after the loop.
-        float U[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
-        WB_UNROLL for (int ch = 0; ch < NCH; ++ch) {
-          if (CC > 0 || ch < C) {
+      // ---- phase 2: image channels, contexts inside
+      const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
+      const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+      float* dself = (c.self && has_din) ? a.d_input + ((size_t)b * g.T + tp) * C * HWd + q : nullptr;
+      const float* drself = (c.self && has_draw) ? a.d_raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
+      float S = 0.f;
+      unsigned choff = 0u;   // ch * HWd
+      for (int ch = 0; ch < C; ++ch) {
+        const float gO = dof ? actf * __ldg(dof + choff) : 0.f;
+        if (dof) S += gO * __ldg(of + choff);
+        WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+          if (tc < g.Tc) {
+            const float* pl = s_src[tc] + choff;
+            const float* p0 = pl + o0[tc];
+            const float* p1 = pl + o1[tc];
             const float v0 = __ldg(p0), v1 = __ldg(p0 + 1), v2 = __ldg(p1), v3 = __ldg(p1 + 1);
-            const float gd = dr ? actf * __ldg(dr) : 0.f;
-            const float go = gd + nrm * gO[ch];
-            U[0] += gO[ch] * v0; U[1] += gO[ch] * v1; U[2] += gO[ch] * v2; U[3] += gO[ch] * v3;
-            Tq[0] += gd * v0; Tq[1] += gd * v1; Tq[2] += gd * v2; Tq[3] += gd * v3;
-            if (dsrc) {
-              atomicAdd(o0, t2.w[0] * go); atomicAdd(o0 + 1, t2.w[1] * go);
-              atomicAdd(o1, t2.w[2] * go); atomicAdd(o1 + 1, t2.w[3] * go);
-              o0 += HWd; o1 += HWd;
+            const float gd = has_draw ? actf * __ldg(s_draw[tc] + choff + q) : 0.f;
+            const float go = gd + nrm[tc] * gO;
+            U[tc][0] += gO * v0; U[tc][1] += gO * v1; U[tc][2] += gO * v2; U[tc][3] += gO * v3;
+            Tq[tc][0] += gd * v0; Tq[tc][1] += gd * v1; Tq[tc][2] += gd * v2; Tq[tc][3] += gd * v3;
+            if (has_din) {
+              float* dl = s_dsrc[tc] + choff;
+              atomicAdd(dl + o0[tc], w[tc][0] * go); atomicAdd(dl + o0[tc] + 1, w[tc][1] * go);
+              atomicAdd(dl + o1[tc], w[tc][2] * go); atomicAdd(dl + o1[tc] + 1, w[tc][3] * go);
             }
-            p0 += HWd; p1 += HWd;
-            if (dr) dr += HWd;
           }
         }
-        float G = U[0] * t2.w[0] + U[1] * t2.w[1] + U[2] * t2.w[2] + U[3] * t2.w[3];
-        float gix = 0.f, giy = 0.f;
-        WB_UNROLL for (int j = 0; j < 4; ++j) {
-          const float tj = Tq[j] + nrm * U[j];
-          gix += tj * cx[j]; giy += tj * cy[j];
+        if (dself && active) {   // lvd.py:845: the target frame passes straight through
+          const float nself = (1.f + 1e-6f) / D;
+          wb_atomic_add(dself + choff, (drself ? __ldg(drself + choff) : 0.f) + nself * gO);
         }
-        if (!c.need_layers) continue;
-        G += gO[C] * (score * 2.f - 1.f);
-        const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
-        const float dfx = (dfl ? actf * __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
-        const float dfy = (dfl ? actf * __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
-        const float gs = 2.f * nrm * gO[C] + (G - S) / D;
-        if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
-        else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
-        else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        choff += HWd;
       }
-      if (c.self && a.d_input && active) {   // lvd.py:845: the target frame passes straight through
-        const float nrm = (1.f + 1e-6f) / D;
-        const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
-        float* o = a.d_input + ((size_t)b * g.T + tp) * C * HWd + q;
-        WB_UNROLL for (int ch = 0; ch < NCH; ++ch)
-          if (CC > 0 || ch < C) wb_atomic_add(o + (size_t)ch * HWd, (draw ? __ldg(draw + (size_t)ch * HWd) : 0.f) + nrm * gO[ch]);
+      if (!c.need_layers) continue;
+      const float gOs = dof ? actf * __ldg(dof + choff) : 0.f;   // d / d (fused score channel), index C
+      if (dof) S += gOs * __ldg(of + choff);
+      // ---- phase 3: layer backward of every context
+      WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+        if (tc < g.Tc) {
+          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+          const WbTaps t = wb_taps(__fadd_rn(px.gx, flx[tc]), __fadd_rn(px.gy, fly[tc]), g.Wd, g.Hd);
+          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+          float cx[4], cy[4];
+          wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
+          wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
+          float G = U[tc][0] * w[tc][0] + U[tc][1] * w[tc][1] + U[tc][2] * w[tc][2] + U[tc][3] * w[tc][3];
+          float gix = 0.f, giy = 0.f;
+          WB_UNROLL for (int j = 0; j < 4; ++j) {
+            const float tj = Tq[tc][j] + nrm[tc] * U[tc][j];
+            gix += tj * cx[j]; giy += tj * cy[j];
+          }
+          G += gOs * (sco[tc] * 2.f - 1.f);
+          const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
+          const float dfx = (dfl ? actf * __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+          const float dfy = (dfl ? actf * __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
+          const float gs = 2.f * nrm[tc] * gOs + (G - S) / D;
+          const float* draw = has_draw ? s_draw[tc] + q : nullptr;
+          if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
+          else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
+          else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
+        }
       }
     }
   }
@@ -385,15 +412,30 @@ __global__ void k_occ_reduce(const float* __restrict__ part, int groups, int per
 }
 
 // ============================================================================ context-alpha backward (B4..B2b)
-#define WB_PSLOTS 4   // object slots staged per round for the class-profile reduction
 struct WbPrepBwdCtx {
   int b, t, L, Nl, HW;
   unsigned HWd;
   bool filt, lowres_direct, need_p;
   const float *s_P, *s_occ, *lyt_base, *alo;
   float *s_acc, *s_accp;
-  float* s_stage;    // this warp's staging area, max(WB_STAGE_SLOTS, 3 * WB_PSLOTS) * WB_WARP floats
+  float* s_stage;    // this warp's staging area, WB_STAGE_SLOTS * WB_WARP floats
 };
+
+// Sum over the warp of 32 per-lane values v[0..31]: afterwards lane l holds sum_lanes v[l] in v[0] (a fixed butterfly:
+// 31 shuffles instead of 32 x 5, deterministic).  The emulation build (one lane) leaves v untouched.
+WB_DEV void wb_warp_transpose_sum(float* v) {
+#ifndef WB_HOST_EMU
+  const int lane = wb_lane();
+  WB_UNROLL for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+    WB_UNROLL for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+#endif
+}
 
 template <int NA, int NLC>
 WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbColRed& cr, unsigned wm, float actf, unsigned q,
@@ -440,54 +482,35 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
     }
   }
   wb_occlude_bwd<NA>(av, gA, c.s_occ, L, ix, ga, c.s_acc);
-  // ---- filter backward: l_k = 1 - 0.5 sum_c |P_kc - sm_c|.  The sign pattern of each object slot is packed into
-  // two bit masks; d P (a sum over pixels) is reduced per warp by staging (masks, d l_k) of every lane and letting
-  // lane <-> (slot, class) entries walk the 32 pixels in lane order (deterministic, no shuffles).
+  // ---- filter backward: l_k = 1 - 0.5 sum_c |P_kc - sm_c|.  One ROLLED loop over the object slots (a single copy of
+  // the class loop in the code); d P_kc = sum over pixels of -0.5 sign(P_kc - sm_c) d l_k is reduced over the warp with
+  // a transpose butterfly and accumulated by lane c.
   float gsm[NN];
   WB_UNROLL for (int cc = 0; cc < NN; ++cc) gsm[cc] = 0.f;
   if (c.filt && any_obj) {
-    for (int s0 = 0; s0 < ix.n; s0 += WB_PSLOTS) {
-      int kk[WB_PSLOTS];
-      WB_UNROLL for (int j = 0; j < WB_PSLOTS; ++j) kk[j] = -1;
-      WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
-        if (s >= s0 && s < s0 + WB_PSLOTS && s < ix.n && ix.k[s] >= 1) {
-          const int k = ix.k[s];
-          const float gl = ga[s] * aup[s];   // d / d l_k
-          const float* P = c.s_P + (k - 1) * Nl;
-          unsigned pos = 0u, neg = 0u;
-          WB_UNROLL for (int cc = 0; cc < NN; ++cc) {
-            if (NLC > 0 || cc < Nl) {
-              const float df = P[cc] - sm[cc];
-              if (df > 0.f) { pos |= 1u << cc; gsm[cc] += 0.5f * gl; }
-              else if (df < 0.f) { neg |= 1u << cc; gsm[cc] -= 0.5f * gl; }
-            }
-          }
-          if (c.need_p) {
-            unsigned* su = reinterpret_cast<unsigned*>(c.s_stage);
-            su[(3 * (s - s0)) * WB_WARP + lane] = pos;
-            su[(3 * (s - s0) + 1) * WB_WARP + lane] = neg;
-            c.s_stage[(3 * (s - s0) + 2) * WB_WARP + lane] = gl;
-          }
-          WB_UNROLL for (int j = 0; j < WB_PSLOTS; ++j) if (j == s - s0) kk[j] = k;
+    for (int s = 0; s < ix.n; ++s) {
+      float gl = 0.f;
+      int k = 0;
+      WB_UNROLL_NA for (int ss = 0; ss < NA; ++ss) if (ss == s) { gl = ga[ss] * aup[ss]; k = ix.k[ss]; }   // d / d l_k
+      if (k < 1) continue;   // warp-uniform
+      const float* P = c.s_P + (k - 1) * Nl;
+      float v[32];
+      WB_UNROLL for (int cc = 0; cc < 32; ++cc) {
+        v[cc] = 0.f;
+        if (cc < NN && (NLC > 0 || cc < Nl)) {
+          const float df = P[cc] - sm[cc];
+          const float sg = df > 0.f ? 0.5f : (df < 0.f ? -0.5f : 0.f);
+          gsm[cc] += sg * gl;
+          v[cc] = -sg * gl;
         }
       }
       if (c.need_p) {
-        __syncwarp();
-        const unsigned* su = reinterpret_cast<const unsigned*>(c.s_stage);
-        for (int e = lane; e < WB_PSLOTS * Nl; e += WB_WARP) {
-          const int j = e / Nl, cc = e - j * Nl;
-          int k = -1;
-          WB_UNROLL for (int jj = 0; jj < WB_PSLOTS; ++jj) if (jj == j) k = kk[jj];
-          if (k < 1) continue;
-          float acc = 0.f;
-          for (int l = 0; l < WB_WARP; ++l) {
-            const unsigned pm = su[(3 * j) * WB_WARP + l], nm = su[(3 * j + 1) * WB_WARP + l];
-            const float gl = c.s_stage[(3 * j + 2) * WB_WARP + l];
-            acc += ((pm >> cc) & 1u) ? -0.5f * gl : (((nm >> cc) & 1u) ? 0.5f * gl : 0.f);
-          }
-          c.s_accp[(k - 1) * Nl + cc] += acc;
-        }
-        __syncwarp();
+        wb_warp_transpose_sum(v);
+#ifdef WB_HOST_EMU
+        for (int cc = 0; cc < Nl; ++cc) c.s_accp[(k - 1) * Nl + cc] += v[cc];
+#else
+        if (lane < Nl) c.s_accp[(k - 1) * Nl + lane] += v[0];
+#endif
       }
     }
   }
@@ -545,8 +568,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
   __shared__ float s_redp[WB_NWARP][(WB_MAX_L - 1) * WB_MAX_NL];
-  __shared__ float s_stage[WB_NWARP][(3 * WB_PSLOTS > WB_STAGE_SLOTS ? 3 * WB_PSLOTS : WB_STAGE_SLOTS) * WB_WARP];
-  __shared__ float s_geo[WB_NWARP][4 * WB_WARP];
+  __shared__ float s_stage[WB_NWARP][WB_STAGE_SLOTS * WB_WARP];
   if (c.filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)c.b * No * Nl + i];
   for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + c.t) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
@@ -573,9 +595,8 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
       const int n = __popc(wm);
       if (n == 0) continue;   // warp-uniform: nothing live here, every gradient path is dead
       WbColRed cr;
-      if (a.d_a_lo && !c.lowres_direct) cr = wb_colred_setup(ax, ay, s_geo[wb_warp()]);
+      if (a.d_a_lo && !c.lowres_direct) cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(ax.i0, 0), wb_shfl(ax.i1, WB_WARP - 1), ay);
       if (n <= 4) wb_prep_bwd_pixel<4, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
-      else if (n <= 8) wb_prep_bwd_pixel<8, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
       else wb_prep_bwd_pixel<WB_MAX_L, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
     }
   }
@@ -852,13 +873,16 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   if (geom) WB_BREQ(a.d_f_lo && a.d_a_lo && a.d_alpha_acc, "geometry gradients need d_f_lo, d_a_lo, d_alpha_acc scratch");
   if (a.d_obj_alpha || a.d_bg_alpha || a.d_cls) WB_BREQ(a.d_a_lo && a.d_alpha_acc, "alpha gradients need d_a_lo, d_alpha_acc scratch");
   if (g.Hd != g.H) WB_BREQ(g.Hd >= 2 * g.H && g.Hd <= 4 * g.H, "backward supports scale_hd in {1} or [2, 4]");
+  if (g.Hd != g.H && (a.d_f_lo || a.d_a_lo)) {
+    WB_BREQ(a.up_tab, "up_tab scratch missing");
+    WB_LAUNCH(k_up_tab, dim3((g.W + 63) / 64), dim3(64), 0, st, g.W, g.Wd, a.up_tab);
+    WB_BLAUNCHED();
+  }
   // 1. fused HD backward
   if (a.stages == 0 || (a.stages & 1)) {
-    const size_t win_bytes = 0;
     const dim3 bgrid(a.red_ctas, g.B * g.Tp);
-    if (g.C == 23) WB_LAUNCH(k_warp_composite_bwd<23>, bgrid, dim3(WB_TILE_PX), win_bytes, st, a);
-    else if (g.C == 22) WB_LAUNCH(k_warp_composite_bwd<22>, bgrid, dim3(WB_TILE_PX), win_bytes, st, a);
-    else WB_LAUNCH(k_warp_composite_bwd<0>, bgrid, dim3(WB_TILE_PX), win_bytes, st, a);
+    if (g.Tc <= 4) WB_LAUNCH(k_warp_composite_bwd<4>, bgrid, dim3(WB_TILE_PX), 0, st, a);
+    else WB_LAUNCH(k_warp_composite_bwd<8>, bgrid, dim3(WB_TILE_PX), 0, st, a);
     WB_BLAUNCHED();
     if (a.d_occ) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);

@@ -311,6 +311,7 @@ class _Decode(torch.autograd.Function):
         occ_part = torch.empty(groups, red_ctas, Lr * Lr, **f32) if n_occ else None
         prof_p_part = torch.empty(g.B * g.Tw, red_ctas, g.No * g.Nl, **f32) if d_prof_p is not None else None
         cls_part = torch.empty(g.B, fwd.prof_ctas, g.No * g.Nl, **f32) if (n_cls and (g.flags & L.F_WEIGHT_CLS)) else None
+        up_tab = torch.empty(g.W, 9, **f32)
         d_cls_s = d_cls
         if d_cls_s is None and cls_c is not None and chain and filt and not (g.flags & L.F_WEIGHT_CLS):
             d_cls_s = None   # P = cls path: nothing to propagate unless cls needs grad
@@ -318,7 +319,7 @@ class _Decode(torch.autograd.Function):
         b = L.DecodeBwd(fwd, L.ptr(grads_in[0]), L.ptr(grads_in[1]), L.ptr(grads_in[2]), L.ptr(grads_in[3]),
                         L.ptr(d_input), L.ptr(d_tgo_s), L.ptr(d_sgo_s), L.ptr(d_tgb_s), L.ptr(d_sgb_s), L.ptr(d_occ),
                         L.ptr(d_oa), L.ptr(d_ba), L.ptr(d_cls_s), L.ptr(d_alpha_acc), L.ptr(d_f_lo), L.ptr(d_a_lo),
-                        L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part), 0)
+                        L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part), L.ptr(up_tab), 0)
         _staged(lib.waldo_decode_bwd, b, L.stream_of(inp_c), "decode_bwd", main_bit=1, dev=dev)
         if d_oa is not None:
             d_oa = d_oa.view(ctx.shapes["obj_alpha"])
