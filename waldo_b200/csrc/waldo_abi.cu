@@ -185,8 +185,12 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   // B5(up)-B9 + stage C
   if (st_main) {
     const dim3 grid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tp);
-    if (g.Tc <= 4) WB_LAUNCH(k_warp_composite_fwd<4>, grid, dim3(WB_TILE_PX), 0, st, *a);
-    else WB_LAUNCH(k_warp_composite_fwd<8>, grid, dim3(WB_TILE_PX), 0, st, *a);
+    const size_t tap4 = (size_t)4 * WB_TAPF * WB_TILE_PX * sizeof(float), tap8 = 2 * tap4;
+#ifndef WB_HOST_EMU
+    if (g.Tc > 4) cudaFuncSetAttribute(k_warp_composite_fwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tap8);
+#endif
+    if (g.Tc <= 4) WB_LAUNCH(k_warp_composite_fwd<4>, grid, dim3(WB_TILE_PX), tap4, st, *a);
+    else WB_LAUNCH(k_warp_composite_fwd<8>, grid, dim3(WB_TILE_PX), tap8, st, *a);
     WB_LAUNCHED();
   }
   return 0;

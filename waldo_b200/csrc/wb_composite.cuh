@@ -131,11 +131,13 @@ WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, un
 }
 
 // grid = (CTAs, B*Tp); one thread per HD pixel (32x8 tiles).  Two phases per pixel:
-//   1. per context: the layer part (flows, warped opacities, compositing) -> alpha channels, flow, and the taps of
-//      the reduced flow kept in registers (TCAP contexts at most);
+//   1. a ROLLED loop over the contexts runs the layer part (flows, warped opacities, compositing) -> alpha channels,
+//      flow; the taps of the reduced flow go to a per-thread shared-memory slot;
 //   2. ONE rolled loop over the C image channels with the contexts unrolled inside: every channel of every context
 //      frame is gathered, stored to raw_output and fused into `output` (lvd.py:850-851) on the fly, so no per-channel
 //      accumulator array is needed and the code stays small (instruction-cache friendly).
+// dynamic shared memory: TCAP * WB_TAPF * 256 floats.
+#define WB_TAPF 9   // per (thread, context) slot: o0, o1, w[4], weight|score, flow x, flow y
 template <int TCAP>
 __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
   const waldo_geom_t g = d.g;
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
   __shared__ const float* s_src[TCAP];   // context frame of every context (CTA-uniform)
   __shared__ float* s_raw[TCAP];         // raw_output block of every context
   __shared__ int s_ct[TCAP];
+  WB_DYN_SMEM(s_tap);
   for (int i = wb_tid(); i < c.L * c.L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + u) * c.L * c.L + i);
   const int C = c.C, b = c.b, tp = c.tp;
   const unsigned HWd = c.HWd;
@@ -172,27 +175,25 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
       WbPix px = wb_pix(d, b, tp, X, Y);
       const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
+      float* my = s_tap + it;   // this thread's slots: my[(tc * WB_TAPF + f) * WB_TILE_PX]
       // ---- phase 1: layers of every context
-      unsigned o0[TCAP], o1[TCAP];
-      float w[TCAP][4], wgt[TCAP];
       float den = 0.f, accs = 0.f;
-      WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
-        o0[tc] = 0u; o1[tc] = 0u; wgt[tc] = 0.f;
-        WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = 0.f;
-        if (tc < g.Tc) {
-          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-          float flow_x, flow_y, score;
-          if (n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
-          else if (n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
-          else wb_fwd_layers<WB_MAX_L>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
-          const WbTaps t = wb_taps(__fadd_rn(px.gx, flow_x), __fadd_rn(px.gy, flow_y), g.Wd, g.Hd);
-          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-          o0[tc] = t2.o0; o1[tc] = t2.o1;
-          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = t2.w[j];
-          wgt[tc] = score + 1e-6f;
-          den += wgt[tc];
-          accs += wgt[tc] * (score * 2.f - 1.f);
-        }
+      for (int tc = 0; tc < g.Tc; ++tc) {
+        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+        float flow_x, flow_y, score;
+        if (n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
+        else if (n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
+        else wb_fwd_layers<WB_MAX_L>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
+        const WbTaps t = wb_taps(__fadd_rn(px.gx, flow_x), __fadd_rn(px.gy, flow_y), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        float* sl = my + tc * WB_TAPF * WB_TILE_PX;
+        reinterpret_cast<unsigned*>(sl)[0] = t2.o0;
+        reinterpret_cast<unsigned*>(sl)[WB_TILE_PX] = t2.o1;
+        WB_UNROLL for (int j = 0; j < 4; ++j) sl[(2 + j) * WB_TILE_PX] = t2.w[j];
+        const float wg = score + 1e-6f;
+        sl[6 * WB_TILE_PX] = wg;
+        den += wg;
+        accs += wg * (score * 2.f - 1.f);
       }
       const float* self_src = nullptr;
       float* self_raw = nullptr;
@@ -207,6 +208,19 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
       }
       const float inv = 1.f / fmaxf(den, 1e-12f);
       // ---- phase 2: image channels, contexts inside
+      unsigned o0[TCAP], o1[TCAP];
+      float w[TCAP][4], wgt[TCAP];
+      WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+        o0[tc] = 0u; o1[tc] = 0u; wgt[tc] = 0.f;
+        WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = 0.f;
+        if (tc < g.Tc) {
+          const float* sl = my + tc * WB_TAPF * WB_TILE_PX;
+          o0[tc] = reinterpret_cast<const unsigned*>(sl)[0];
+          o1[tc] = reinterpret_cast<const unsigned*>(sl)[WB_TILE_PX];
+          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = sl[(2 + j) * WB_TILE_PX];
+          wgt[tc] = sl[6 * WB_TILE_PX];
+        }
+      }
       float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
       unsigned choff = 0u;   // ch * HWd
       for (int ch = 0; ch < C; ++ch) {

@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
   __shared__ float* s_dsrc[TCAP];         // its gradient
   __shared__ const float* s_draw[TCAP];   // upstream d raw_output block of every context (or null)
   __shared__ int s_ct[TCAP];
+  WB_DYN_SMEM(s_tap);
   for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + u) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
   for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
@@ -305,22 +306,33 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
       if (a.d_f_lo && !c.lowres_direct)
         cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(px.ax.i0, 0), wb_shfl(px.ax.i1, WB_WARP - 1), px.ay);
       const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
-      // ---- phase 1
+      float* my = s_tap + it;   // this thread's slots: my[(tc * WB_TAPF + f) * WB_TILE_PX]
+      // ---- phase 1 (rolled over the contexts): recompute the layer forward, park flow / score / taps in shared memory
+      for (int tc = 0; tc < g.Tc; ++tc) {
+        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+        float fx, fy, sc;
+        if (n <= 4) wb_bwd_layers_fwd<4>(d, c, px, wm, s_ct[tc], pair, fx, fy, sc);
+        else if (n <= 8) wb_bwd_layers_fwd<8>(d, c, px, wm, s_ct[tc], pair, fx, fy, sc);
+        else wb_bwd_layers_fwd<WB_MAX_L>(d, c, px, wm, s_ct[tc], pair, fx, fy, sc);
+        const WbTaps t = wb_taps(__fadd_rn(px.gx, fx), __fadd_rn(px.gy, fy), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        float* sl = my + tc * WB_TAPF * WB_TILE_PX;
+        reinterpret_cast<unsigned*>(sl)[0] = t2.o0;
+        reinterpret_cast<unsigned*>(sl)[WB_TILE_PX] = t2.o1;
+        WB_UNROLL for (int j = 0; j < 4; ++j) sl[(2 + j) * WB_TILE_PX] = t2.w[j];
+        sl[6 * WB_TILE_PX] = sc; sl[7 * WB_TILE_PX] = fx; sl[8 * WB_TILE_PX] = fy;
+      }
       unsigned o0[TCAP], o1[TCAP];
-      float w[TCAP][4], nrm[TCAP], U[TCAP][4], Tq[TCAP][4], flx[TCAP], fly[TCAP], sco[TCAP];
+      float w[TCAP][4], nrm[TCAP], U[TCAP][4], Tq[TCAP][4];
       WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
-        o0[tc] = 0u; o1[tc] = 0u; nrm[tc] = 0.f; flx[tc] = 0.f; fly[tc] = 0.f; sco[tc] = 0.f;
+        o0[tc] = 0u; o1[tc] = 0u; nrm[tc] = 0.f;
         WB_UNROLL for (int j = 0; j < 4; ++j) { w[tc][j] = 0.f; U[tc][j] = 0.f; Tq[tc][j] = 0.f; }
         if (tc < g.Tc) {
-          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-          if (n <= 4) wb_bwd_layers_fwd<4>(d, c, px, wm, s_ct[tc], pair, flx[tc], fly[tc], sco[tc]);
-          else if (n <= 8) wb_bwd_layers_fwd<8>(d, c, px, wm, s_ct[tc], pair, flx[tc], fly[tc], sco[tc]);
-          else wb_bwd_layers_fwd<WB_MAX_L>(d, c, px, wm, s_ct[tc], pair, flx[tc], fly[tc], sco[tc]);
-          const WbTaps t = wb_taps(__fadd_rn(px.gx, flx[tc]), __fadd_rn(px.gy, fly[tc]), g.Wd, g.Hd);
-          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-          o0[tc] = t2.o0; o1[tc] = t2.o1;
-          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = t2.w[j];
-          nrm[tc] = (sco[tc] + 1e-6f) / D;
+          const float* sl = my + tc * WB_TAPF * WB_TILE_PX;
+          o0[tc] = reinterpret_cast<const unsigned*>(sl)[0];
+          o1[tc] = reinterpret_cast<const unsigned*>(sl)[WB_TILE_PX];
+          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = sl[(2 + j) * WB_TILE_PX];
+          nrm[tc] = (sl[6 * WB_TILE_PX] + 1e-6f) / D;
         }
       }
       // ---- phase 2: image channels, contexts inside
@@ -359,31 +371,36 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
       if (!c.need_layers) continue;
       const float gOs = dof ? actf * __ldg(dof + choff) : 0.f;   // d / d (fused score channel), index C
       if (dof) S += gOs * __ldg(of + choff);
-      // ---- phase 3: layer backward of every context
+      // ---- phase 3 (rolled over the contexts): d score, d flow from the moments, then the layer backward
       WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
         if (tc < g.Tc) {
-          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-          const WbTaps t = wb_taps(__fadd_rn(px.gx, flx[tc]), __fadd_rn(px.gy, fly[tc]), g.Wd, g.Hd);
-          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-          float cx[4], cy[4];
-          wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
-          wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
-          float G = U[tc][0] * w[tc][0] + U[tc][1] * w[tc][1] + U[tc][2] * w[tc][2] + U[tc][3] * w[tc][3];
-          float gix = 0.f, giy = 0.f;
-          WB_UNROLL for (int j = 0; j < 4; ++j) {
-            const float tj = Tq[tc][j] + nrm[tc] * U[tc][j];
-            gix += tj * cx[j]; giy += tj * cy[j];
-          }
-          G += gOs * (sco[tc] * 2.f - 1.f);
-          const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
-          const float dfx = (dfl ? actf * __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
-          const float dfy = (dfl ? actf * __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
-          const float gs = 2.f * nrm[tc] * gOs + (G - S) / D;
-          const float* draw = has_draw ? s_draw[tc] + q : nullptr;
-          if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
-          else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
-          else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
+          float* sl = my + tc * WB_TAPF * WB_TILE_PX;
+          const float G = U[tc][0] * w[tc][0] + U[tc][1] * w[tc][1] + U[tc][2] * w[tc][2] + U[tc][3] * w[tc][3];
+          sl[0] = G;
+          WB_UNROLL for (int j = 0; j < 4; ++j) sl[(1 + j) * WB_TILE_PX] = Tq[tc][j] + nrm[tc] * U[tc][j];
         }
+      }
+      for (int tc = 0; tc < g.Tc; ++tc) {
+        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+        const float* sl = my + tc * WB_TAPF * WB_TILE_PX;
+        const float sc = sl[6 * WB_TILE_PX], nr = (sc + 1e-6f) / D;
+        const float fx = sl[7 * WB_TILE_PX], fy = sl[8 * WB_TILE_PX];
+        const WbTaps t = wb_taps(__fadd_rn(px.gx, fx), __fadd_rn(px.gy, fy), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        float cx[4], cy[4];
+        wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
+        wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
+        float gix = 0.f, giy = 0.f;
+        WB_UNROLL for (int j = 0; j < 4; ++j) { const float tj = sl[(1 + j) * WB_TILE_PX]; gix += tj * cx[j]; giy += tj * cy[j]; }
+        const float G = sl[0] + gOs * (sc * 2.f - 1.f);
+        const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
+        const float dfx = (dfl ? actf * __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+        const float dfy = (dfl ? actf * __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
+        const float gs = 2.f * nr * gOs + (G - S) / D;
+        const float* draw = has_draw ? s_draw[tc] + q : nullptr;
+        if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
+        else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
+        else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
       }
     }
   }
@@ -881,8 +898,12 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   // 1. fused HD backward
   if (a.stages == 0 || (a.stages & 1)) {
     const dim3 bgrid(a.red_ctas, g.B * g.Tp);
-    if (g.Tc <= 4) WB_LAUNCH(k_warp_composite_bwd<4>, bgrid, dim3(WB_TILE_PX), 0, st, a);
-    else WB_LAUNCH(k_warp_composite_bwd<8>, bgrid, dim3(WB_TILE_PX), 0, st, a);
+    const size_t tap4 = (size_t)4 * WB_TAPF * WB_TILE_PX * sizeof(float), tap8 = 2 * tap4;
+#ifndef WB_HOST_EMU
+    if (g.Tc > 4) cudaFuncSetAttribute(k_warp_composite_bwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tap8);
+#endif
+    if (g.Tc <= 4) WB_LAUNCH(k_warp_composite_bwd<4>, bgrid, dim3(WB_TILE_PX), tap4, st, a);
+    else WB_LAUNCH(k_warp_composite_bwd<8>, bgrid, dim3(WB_TILE_PX), tap8, st, a);
     WB_BLAUNCHED();
     if (a.d_occ) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);
