@@ -223,6 +223,9 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
       }
       float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
       unsigned choff = 0u;   // ch * HWd
+#ifndef WB_HOST_EMU
+#pragma unroll 4
+#endif
       for (int ch = 0; ch < C; ++ch) {
         float acc = 0.f;
         WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {

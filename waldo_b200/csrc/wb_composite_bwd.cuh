@@ -342,6 +342,9 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
       const float* drself = (c.self && has_draw) ? a.d_raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
       float S = 0.f;
       unsigned choff = 0u;   // ch * HWd
+#ifndef WB_HOST_EMU
+#pragma unroll 2
+#endif
       for (int ch = 0; ch < C; ++ch) {
         const float gO = dof ? actf * __ldg(dof + choff) : 0.f;
         if (dof) S += gO * __ldg(of + choff);
@@ -900,7 +903,9 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     const dim3 bgrid(a.red_ctas, g.B * g.Tp);
     const size_t tap4 = (size_t)4 * WB_TAPF * WB_TILE_PX * sizeof(float), tap8 = 2 * tap4;
 #ifndef WB_HOST_EMU
-    if (g.Tc > 4) cudaFuncSetAttribute(k_warp_composite_bwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tap8);
+    // static + dynamic shared memory exceeds the 48 KB default: opt in (cheap, idempotent)
+    if (g.Tc <= 4) cudaFuncSetAttribute(k_warp_composite_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tap4);
+    else cudaFuncSetAttribute(k_warp_composite_bwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tap8);
 #endif
     if (g.Tc <= 4) WB_LAUNCH(k_warp_composite_bwd<4>, bgrid, dim3(WB_TILE_PX), tap4, st, a);
     else WB_LAUNCH(k_warp_composite_bwd<8>, bgrid, dim3(WB_TILE_PX), tap8, st, a);
