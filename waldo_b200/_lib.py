@@ -63,7 +63,7 @@ class DecodeFwd(C.Structure):
                 ("a_lo", c_void_p), ("prof_part", c_void_p), ("prof_ctas", C.c_int), ("prof_sum", c_void_p),
                 ("prof_p", c_void_p), ("f_lo", c_void_p), ("s_lo", c_void_p), ("live_ctx", c_void_p), ("live_pred", c_void_p),
                 ("alpha", c_void_p), ("flow", c_void_p), ("raw_output", c_void_p), ("out_full", c_void_p),
-                ("norm", c_void_p), ("stages", C.c_int)]
+                ("norm", c_void_p), ("score", c_void_p), ("stages", C.c_int)]
 
 
 class DecodeBwd(C.Structure):
@@ -75,7 +75,7 @@ class DecodeBwd(C.Structure):
                 ("d_alpha_acc", c_void_p), ("d_f_lo", c_void_p), ("d_a_lo", c_void_p),
                 ("d_prof_p", c_void_p), ("d_prof_sum", c_void_p),
                 ("red_ctas", C.c_int), ("occ_part", c_void_p), ("prof_p_part", c_void_p), ("cls_part", c_void_p),
-                ("up_tab", c_void_p), ("stages", C.c_int)]
+                ("up_tab", c_void_p), ("glue", c_void_p), ("stages", C.c_int)]
 
 
 class WifFuseFwd(C.Structure):

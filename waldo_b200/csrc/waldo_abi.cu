@@ -144,7 +144,7 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   if (rc) return rc;
   WB_REQUIRE(a->input && a->tgt_grid_obj && a->src_grid_obj && a->tgt_grid_bg && a->src_grid_bg && a->occ && a->obj_alpha &&
              a->bg_alpha && a->ctx_ts && a->pred_ts && a->xs_hd && a->ys_hd, "decode_fwd: null input pointer");
-  WB_REQUIRE(a->a_lo && a->f_lo && a->alpha && a->flow && a->raw_output && a->out_full && a->live_ctx && a->live_pred,
+  WB_REQUIRE(a->a_lo && a->f_lo && a->alpha && a->flow && a->raw_output && a->out_full && a->live_ctx && a->live_pred && a->norm && a->score,
              "decode_fwd: null output pointer");
   const bool filt = (g.flags & WALDO_F_FILTER) != 0;
   const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
@@ -156,7 +156,7 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   }
   const int L = g.No + 1, HW = g.H * g.W;
   const long long HWd = (long long)g.Hd * g.Wd;
-  const bool st_prep = a->stages == 0 || (a->stages & 1), st_main = a->stages == 0 || (a->stages & 2);
+  const bool st_prep = a->stages == 0 || (a->stages & 1), st_layers = a->stages == 0 || (a->stages & 2), st_gather = a->stages == 0 || (a->stages & 4);
   if (st_prep) {
   // B1
   WB_LAUNCH(k_project_alpha, dim3(wb_blocks((long long)g.B * g.Tw * HW, 128)), dim3(128), 0, st, *a);
@@ -182,15 +182,16 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   WB_LAUNCH(k_layer_flow_lo, dim3(wb_blocks((long long)g.B * g.Tp * HW, 128)), dim3(128), 0, st, *a);
   WB_LAUNCHED();
   }
-  // B5(up)-B9 + stage C
-  if (st_main) {
-    const dim3 grid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tp);
-    const size_t tap4 = (size_t)4 * WB_TAPF * WB_TILE_PX * sizeof(float), tap8 = 2 * tap4;
-#ifndef WB_HOST_EMU
-    if (g.Tc > 4) cudaFuncSetAttribute(k_warp_composite_fwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tap8);
-#endif
-    if (g.Tc <= 4) WB_LAUNCH(k_warp_composite_fwd<4>, grid, dim3(WB_TILE_PX), tap4, st, *a);
-    else WB_LAUNCH(k_warp_composite_fwd<8>, grid, dim3(WB_TILE_PX), tap8, st, *a);
+  // B5(up)-B9: the layer kernel
+  const dim3 grid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tp);
+  if (st_layers) {
+    WB_LAUNCH(k_layers_fwd, grid, dim3(WB_TILE_PX), 0, st, *a);
+    WB_LAUNCHED();
+  }
+  // stage C: the gather kernel
+  if (st_gather) {
+    if (g.Tc <= 4) WB_LAUNCH(k_gather_fwd<4>, grid, dim3(WB_TILE_PX), 0, st, *a);
+    else WB_LAUNCH(k_gather_fwd<8>, grid, dim3(WB_TILE_PX), 0, st, *a);
     WB_LAUNCHED();
   }
   return 0;

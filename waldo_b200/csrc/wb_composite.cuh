@@ -130,16 +130,16 @@ WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, un
   flow_x = ly.flow_x; flow_y = ly.flow_y; score = ly.score;
 }
 
-// grid = (CTAs, B*Tp); one thread per HD pixel (32x8 tiles).  Two phases per pixel:
-//   1. a ROLLED loop over the contexts runs the layer part (flows, warped opacities, compositing) -> alpha channels,
-//      flow; the taps of the reduced flow go to a per-thread shared-memory slot;
-//   2. ONE rolled loop over the C image channels with the contexts unrolled inside: every channel of every context
-//      frame is gathered, stored to raw_output and fused into `output` (lvd.py:850-851) on the fly, so no per-channel
-//      accumulator array is needed and the code stays small (instruction-cache friendly).
-// dynamic shared memory: TCAP * WB_TAPF * 256 floats.
-#define WB_TAPF 9   // per (thread, context) slot: o0, o1, w[4], weight|score, flow x, flow y
-template <int TCAP>
-__global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
+// ------------------------------------------------------------------------------------------------------------------
+// The forward runs as two kernels per (b, tp) so that each gets the register budget it needs:
+//   k_layers_fwd : the irregular layer part (B5up..B9) -> alpha channels of raw_output, flow, score
+//   k_gather_fwd : the streaming part (stage C)        -> image channels of raw_output, fused output, norm
+// Only 3 floats per (pixel, context) pass between them (flow is an output of the path anyway, score is kept for the
+// backward); no per-layer HD tensor ever reaches HBM.
+// ------------------------------------------------------------------------------------------------------------------
+
+// grid = (CTAs, B*Tp), 32x8 pixel tiles, one thread per HD pixel, rolled loop over the contexts.
+__global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_fwd(WbDec d) {
   const waldo_geom_t g = d.g;
   WbFwdCtx c;
   c.L = g.No + 1; c.HW = g.H * g.W; c.C = g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
@@ -150,21 +150,11 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
   c.disocc_ch = (g.flags & WALDO_F_USE_DISOCC) != 0;
   c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0);
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
-  __shared__ const float* s_src[TCAP];   // context frame of every context (CTA-uniform)
-  __shared__ float* s_raw[TCAP];         // raw_output block of every context
-  __shared__ int s_ct[TCAP];
-  WB_DYN_SMEM(s_tap);
   for (int i = wb_tid(); i < c.L * c.L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + u) * c.L * c.L + i);
-  const int C = c.C, b = c.b, tp = c.tp;
-  const unsigned HWd = c.HWd;
-  for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
-    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-    s_ct[tc] = c_t;
-    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
-    s_raw[tc] = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
-  }
   __syncthreads();
   c.s_occ = s_occ;
+  const int b = c.b, tp = c.tp;
+  const unsigned HWd = c.HWd;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
@@ -175,56 +165,84 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
       WbPix px = wb_pix(d, b, tp, X, Y);
       const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
-      float* my = s_tap + it;   // this thread's slots: my[(tc * WB_TAPF + f) * WB_TILE_PX]
-      // ---- phase 1: layers of every context
-      float den = 0.f, accs = 0.f;
       for (int tc = 0; tc < g.Tc; ++tc) {
+        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
         const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+        float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
         float flow_x, flow_y, score;
-        if (n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
-        else if (n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
-        else wb_fwd_layers<WB_MAX_L>(d, c, px, wm, q, s_ct[tc], pair, s_raw[tc], flow_x, flow_y, score);
-        const WbTaps t = wb_taps(__fadd_rn(px.gx, flow_x), __fadd_rn(px.gy, flow_y), g.Wd, g.Hd);
-        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-        float* sl = my + tc * WB_TAPF * WB_TILE_PX;
-        reinterpret_cast<unsigned*>(sl)[0] = t2.o0;
-        reinterpret_cast<unsigned*>(sl)[WB_TILE_PX] = t2.o1;
-        WB_UNROLL for (int j = 0; j < 4; ++j) sl[(2 + j) * WB_TILE_PX] = t2.w[j];
-        const float wg = score + 1e-6f;
-        sl[6 * WB_TILE_PX] = wg;
-        den += wg;
-        accs += wg * (score * 2.f - 1.f);
+        if (n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
+        else if (n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
+        else wb_fwd_layers<WB_MAX_L>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
+        d.score[pair * HWd + q] = score;
       }
-      const float* self_src = nullptr;
-      float* self_raw = nullptr;
-      float wself = 0.f;
-      if (c.self) {   // lvd.py:842-845: the target frame itself, fully opaque, score 1
-        self_raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q;
-        self_src = d.input + ((size_t)b * g.T + tp) * C * HWd + q;
-        wself = 1.f + 1e-6f;
-        for (int k = 0; k < c.L; ++k) self_raw[(size_t)(C + k) * HWd] = 1.f;
-        if (c.disocc_ch) self_raw[(size_t)(C + c.L) * HWd] = 1.f;
-        den += wself; accs += wself;
+      if (c.self) {   // lvd.py:842-845: the target frame itself is fully opaque
+        float* raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q;
+        for (int k = 0; k < c.L; ++k) raw[(size_t)(c.C + k) * HWd] = 1.f;
+        if (c.disocc_ch) raw[(size_t)(c.C + c.L) * HWd] = 1.f;
       }
-      const float inv = 1.f / fmaxf(den, 1e-12f);
-      // ---- phase 2: image channels, contexts inside
+    }
+  }
+}
+
+// grid = (CTAs, B*Tp), 32x8 pixel tiles, one thread per HD pixel.  The taps of the TCAP (>= Tc) contexts live in
+// registers; ONE rolled loop walks the C image channels with the contexts unrolled inside: every channel of every
+// context frame is gathered, stored to raw_output and fused into `output` (lvd.py:850-851) on the fly.
+template <int TCAP>
+__global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_fwd(WbDec d) {
+  const waldo_geom_t g = d.g;
+  const int C = g.C, L = g.No + 1;
+  const unsigned HWd = (unsigned)(g.Hd * g.Wd);
+  const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
+  const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
+  __shared__ const float* s_src[TCAP];   // context frame of every context (CTA-uniform)
+  __shared__ float* s_raw[TCAP];         // raw_output block of every context
+  for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
+    s_raw[tc] = d.raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * CR * HWd;
+  }
+  __syncthreads();
+  const WbTileIter ti(g.Hd, g.Wd);
+  for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
+    const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
+    for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
+      const int X = min(tx0 + (it & (WB_TILE_W - 1)), g.Wd - 1), Y = min(ty0 + it / WB_TILE_W, g.Hd - 1);
+      const unsigned q = (unsigned)(Y * g.Wd + X);
+      const float gx = __ldg(d.xs_hd + X), gy = __ldg(d.ys_hd + Y);
       unsigned o0[TCAP], o1[TCAP];
       float w[TCAP][4], wgt[TCAP];
+      float den = 0.f, accs = 0.f;
       WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
         o0[tc] = 0u; o1[tc] = 0u; wgt[tc] = 0.f;
         WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = 0.f;
         if (tc < g.Tc) {
-          const float* sl = my + tc * WB_TAPF * WB_TILE_PX;
-          o0[tc] = reinterpret_cast<const unsigned*>(sl)[0];
-          o1[tc] = reinterpret_cast<const unsigned*>(sl)[WB_TILE_PX];
-          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = sl[(2 + j) * WB_TILE_PX];
-          wgt[tc] = sl[6 * WB_TILE_PX];
+          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+          const float* fl = d.flow + pair * 2 * HWd + q;
+          const float score = __ldg(d.score + pair * HWd + q);
+          const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+          o0[tc] = t2.o0; o1[tc] = t2.o1;
+          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = t2.w[j];
+          wgt[tc] = score + 1e-6f;
+          den += wgt[tc];
+          accs += wgt[tc] * (score * 2.f - 1.f);
         }
       }
+      const float* self_src = nullptr;
+      float* self_raw = nullptr;
+      float wself = 0.f;
+      if (self) {   // lvd.py:842-845: the target frame itself, score 1
+        self_raw = d.raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q;
+        self_src = d.input + ((size_t)b * g.T + tp) * C * HWd + q;
+        wself = 1.f + 1e-6f;
+        den += wself; accs += wself;
+      }
+      const float inv = 1.f / fmaxf(den, 1e-12f);
       float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
       unsigned choff = 0u;   // ch * HWd
 #ifndef WB_HOST_EMU
-#pragma unroll 4
+#pragma unroll 2
 #endif
       for (int ch = 0; ch < C; ++ch) {
         float acc = 0.f;
@@ -236,12 +254,12 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_fwd(WbDec d) {
             acc += wgt[tc] * v;
           }
         }
-        if (c.self) { const float v = __ldg(self_src + choff); self_raw[choff] = v; acc += wself * v; }
+        if (self) { const float v = __ldg(self_src + choff); self_raw[choff] = v; acc += wself * v; }
         of[choff] = acc * inv;
         choff += HWd;
       }
       of[choff] = accs * inv;
-      if (d.norm) d.norm[((size_t)b * g.Tp + tp) * HWd + q] = den;
+      d.norm[((size_t)b * g.Tp + tp) * HWd + q] = den;
     }
   }
 }

@@ -248,47 +248,35 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
   }
 }
 
-// grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration).  Three phases per pixel (see the forward):
-//   1. per context: recompute the layer forward -> reduced flow, score, taps;
-//   2. ONE rolled loop over the image channels, contexts unrolled inside: scatter d input, and accumulate the
-//      bilinear moments U = sum_ch dOut*v_tap, T = sum_ch dRaw*v_tap from which d score and d flow follow;
-//   3. per context: backward of the layer part.
+// ------------------------------------------------------------------------------------------------------------------
+// The backward of the two HD kernels, in reverse order:
+//   k_gather_bwd : stage C backward.  Scatters d input and reduces, per (pixel, context), the upstream gradients
+//                  of the image channels to three numbers: d score, d flow x, d flow y (`glue`).
+//   k_layers_bwd : backward of the layer part (B9..B5up) driven by `glue` and the alpha channels of d raw_output.
+// ------------------------------------------------------------------------------------------------------------------
+
+// grid = (CTAs, B*Tp), 32x8 pixel tiles.  One rolled loop over the image channels, contexts unrolled inside.  Since the
+// gathered value is bilinear in the four taps, d score and d flow follow from the tap moments
+//   U_j = sum_ch dOut_ch * v_j,   T_j = sum_ch dRaw_ch * v_j     (j = the four tap positions).
 template <int TCAP>
-__global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) {
+__global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
-  WbBwdCtx c;
-  c.L = g.No + 1; c.HW = g.H * g.W; c.C = g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
-  const int btp = blockIdx.y;
-  c.b = btp / g.Tp; c.tp = btp - c.b * g.Tp;
-  const int u = (int)d.pred_ts[c.tp];
-  c.self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
-  c.disocc_ch = (g.flags & WALDO_F_USE_DISOCC) != 0;
-  c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0);
-  c.need_layers = a.d_alpha_acc || a.d_f_lo || a.d_occ;
-  c.lowres_direct = (g.Hd == g.H);
-  const int L = c.L, C = c.C, b = c.b, tp = c.tp;
-  const unsigned HWd = c.HWd;
-  __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
-  __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
-  __shared__ float s_stage[WB_NWARP][2 * WB_STAGE_SLOTS * WB_WARP];
+  const int C = g.C, L = g.No + 1;
+  const unsigned HWd = (unsigned)(g.Hd * g.Wd);
+  const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
+  const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
   __shared__ const float* s_src[TCAP];    // context frame of every context (CTA-uniform)
   __shared__ float* s_dsrc[TCAP];         // its gradient
   __shared__ const float* s_draw[TCAP];   // upstream d raw_output block of every context (or null)
-  __shared__ int s_ct[TCAP];
-  WB_DYN_SMEM(s_tap);
-  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + u) * L * L + i);
-  for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
   for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
     const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-    s_ct[tc] = c_t;
     s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
     s_dsrc[tc] = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * C * HWd : nullptr;
-    s_draw[tc] = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd : nullptr;
+    s_draw[tc] = a.d_raw_output ? a.d_raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * CR * HWd : nullptr;
   }
   __syncthreads();
-  c.s_occ = s_occ; c.s_stage = s_stage[wb_warp()];
-  c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
   const bool has_din = a.d_input != nullptr, has_draw = a.d_raw_output != nullptr;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
@@ -299,52 +287,29 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
       const float actf = active ? 1.f : 0.f;    // threads beyond the edge run on the nearest valid pixel with zero upstream
       const int X = min(Xr, g.Wd - 1), Y = min(Yr, g.Hd - 1);
       const unsigned q = (unsigned)(Y * g.Wd + X);
-      WbPix px = wb_pix(d, b, tp, X, Y);
-      const unsigned wm = wb_warp_or(px.isobj);
-      const int n = __popc(wm);
-      WbColRed cr;
-      if (a.d_f_lo && !c.lowres_direct)
-        cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(px.ax.i0, 0), wb_shfl(px.ax.i1, WB_WARP - 1), px.ay);
+      const float gx = __ldg(d.xs_hd + X), gy = __ldg(d.ys_hd + Y);
       const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
-      float* my = s_tap + it;   // this thread's slots: my[(tc * WB_TAPF + f) * WB_TILE_PX]
-      // ---- phase 1 (rolled over the contexts): recompute the layer forward, park flow / score / taps in shared memory
-      for (int tc = 0; tc < g.Tc; ++tc) {
-        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-        float fx, fy, sc;
-        if (n <= 4) wb_bwd_layers_fwd<4>(d, c, px, wm, s_ct[tc], pair, fx, fy, sc);
-        else if (n <= 8) wb_bwd_layers_fwd<8>(d, c, px, wm, s_ct[tc], pair, fx, fy, sc);
-        else wb_bwd_layers_fwd<WB_MAX_L>(d, c, px, wm, s_ct[tc], pair, fx, fy, sc);
-        const WbTaps t = wb_taps(__fadd_rn(px.gx, fx), __fadd_rn(px.gy, fy), g.Wd, g.Hd);
-        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-        float* sl = my + tc * WB_TAPF * WB_TILE_PX;
-        reinterpret_cast<unsigned*>(sl)[0] = t2.o0;
-        reinterpret_cast<unsigned*>(sl)[WB_TILE_PX] = t2.o1;
-        WB_UNROLL for (int j = 0; j < 4; ++j) sl[(2 + j) * WB_TILE_PX] = t2.w[j];
-        sl[6 * WB_TILE_PX] = sc; sl[7 * WB_TILE_PX] = fx; sl[8 * WB_TILE_PX] = fy;
-      }
       unsigned o0[TCAP], o1[TCAP];
       float w[TCAP][4], nrm[TCAP], U[TCAP][4], Tq[TCAP][4];
       WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
         o0[tc] = 0u; o1[tc] = 0u; nrm[tc] = 0.f;
         WB_UNROLL for (int j = 0; j < 4; ++j) { w[tc][j] = 0.f; U[tc][j] = 0.f; Tq[tc][j] = 0.f; }
         if (tc < g.Tc) {
-          const float* sl = my + tc * WB_TAPF * WB_TILE_PX;
-          o0[tc] = reinterpret_cast<const unsigned*>(sl)[0];
-          o1[tc] = reinterpret_cast<const unsigned*>(sl)[WB_TILE_PX];
-          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = sl[(2 + j) * WB_TILE_PX];
-          nrm[tc] = (sl[6 * WB_TILE_PX] + 1e-6f) / D;
+          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+          const float* fl = d.flow + pair * 2 * HWd + q;
+          const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+          o0[tc] = t2.o0; o1[tc] = t2.o1;
+          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = t2.w[j];
+          nrm[tc] = (__ldg(d.score + pair * HWd + q) + 1e-6f) / D;
         }
       }
-      // ---- phase 2: image channels, contexts inside
       const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
       const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
-      float* dself = (c.self && has_din) ? a.d_input + ((size_t)b * g.T + tp) * C * HWd + q : nullptr;
-      const float* drself = (c.self && has_draw) ? a.d_raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
+      float* dself = (self && has_din) ? a.d_input + ((size_t)b * g.T + tp) * C * HWd + q : nullptr;
+      const float* drself = (self && has_draw) ? a.d_raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q : nullptr;
       float S = 0.f;
       unsigned choff = 0u;   // ch * HWd
-#ifndef WB_HOST_EMU
-#pragma unroll 2
-#endif
       for (int ch = 0; ch < C; ++ch) {
         const float gO = dof ? actf * __ldg(dof + choff) : 0.f;
         if (dof) S += gO * __ldg(of + choff);
@@ -371,39 +336,84 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_warp_composite_bwd(WbDecB a) 
         }
         choff += HWd;
       }
-      if (!c.need_layers) continue;
+      if (!a.glue || !active) continue;   // (threads beyond the edge must not overwrite the pixel they mirror)
       const float gOs = dof ? actf * __ldg(dof + choff) : 0.f;   // d / d (fused score channel), index C
       if (dof) S += gOs * __ldg(of + choff);
-      // ---- phase 3 (rolled over the contexts): d score, d flow from the moments, then the layer backward
       WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
         if (tc < g.Tc) {
-          float* sl = my + tc * WB_TAPF * WB_TILE_PX;
-          const float G = U[tc][0] * w[tc][0] + U[tc][1] * w[tc][1] + U[tc][2] * w[tc][2] + U[tc][3] * w[tc][3];
-          sl[0] = G;
-          WB_UNROLL for (int j = 0; j < 4; ++j) sl[(1 + j) * WB_TILE_PX] = Tq[tc][j] + nrm[tc] * U[tc][j];
+          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+          const float* fl = d.flow + pair * 2 * HWd + q;
+          const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+          float cx[4], cy[4];
+          wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
+          wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
+          const float sc = nrm[tc] * D - 1e-6f;
+          float G = U[tc][0] * w[tc][0] + U[tc][1] * w[tc][1] + U[tc][2] * w[tc][2] + U[tc][3] * w[tc][3];
+          float gix = 0.f, giy = 0.f;
+          WB_UNROLL for (int j = 0; j < 4; ++j) {
+            const float tj = Tq[tc][j] + nrm[tc] * U[tc][j];
+            gix += tj * cx[j]; giy += tj * cy[j];
+          }
+          G += gOs * (sc * 2.f - 1.f);
+          const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
+          float* gl = a.glue + pair * 3 * HWd + q;
+          gl[0] = 2.f * nrm[tc] * gOs + (G - S) / D;
+          gl[HWd] = (dfl ? actf * __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+          gl[2 * HWd] = (dfl ? actf * __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
         }
       }
+    }
+  }
+}
+
+// grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration), rolled loop over the contexts.
+__global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_bwd(WbDecB a) {
+  const WbDec& d = a.f;
+  const waldo_geom_t g = d.g;
+  WbBwdCtx c;
+  c.L = g.No + 1; c.HW = g.H * g.W; c.C = g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
+  const int btp = blockIdx.y;
+  c.b = btp / g.Tp; c.tp = btp - c.b * g.Tp;
+  const int u = (int)d.pred_ts[c.tp];
+  c.self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  c.disocc_ch = (g.flags & WALDO_F_USE_DISOCC) != 0;
+  c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0);
+  c.need_layers = true;
+  c.lowres_direct = (g.Hd == g.H);
+  const int L = c.L, b = c.b, tp = c.tp;
+  const unsigned HWd = c.HWd;
+  __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
+  __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
+  __shared__ float s_stage[WB_NWARP][2 * WB_STAGE_SLOTS * WB_WARP];
+  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + u) * L * L + i);
+  for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
+  __syncthreads();
+  c.s_occ = s_occ; c.s_stage = s_stage[wb_warp()];
+  c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
+  const WbTileIter ti(g.Hd, g.Wd);
+  for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
+    const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
+    for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
+      const int Xr = tx0 + (it & (WB_TILE_W - 1)), Yr = ty0 + it / WB_TILE_W;
+      const float actf = (Xr < g.Wd && Yr < g.Hd) ? 1.f : 0.f;
+      const int X = min(Xr, g.Wd - 1), Y = min(Yr, g.Hd - 1);
+      const unsigned q = (unsigned)(Y * g.Wd + X);
+      WbPix px = wb_pix(d, b, tp, X, Y);
+      const unsigned wm = wb_warp_or(px.isobj);
+      const int n = __popc(wm);
+      WbColRed cr;
+      if (a.d_f_lo && !c.lowres_direct)
+        cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(px.ax.i0, 0), wb_shfl(px.ax.i1, WB_WARP - 1), px.ay);
       for (int tc = 0; tc < g.Tc; ++tc) {
+        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
         const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-        const float* sl = my + tc * WB_TAPF * WB_TILE_PX;
-        const float sc = sl[6 * WB_TILE_PX], nr = (sc + 1e-6f) / D;
-        const float fx = sl[7 * WB_TILE_PX], fy = sl[8 * WB_TILE_PX];
-        const WbTaps t = wb_taps(__fadd_rn(px.gx, fx), __fadd_rn(px.gy, fy), g.Wd, g.Hd);
-        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-        float cx[4], cy[4];
-        wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
-        wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
-        float gix = 0.f, giy = 0.f;
-        WB_UNROLL for (int j = 0; j < 4; ++j) { const float tj = sl[(1 + j) * WB_TILE_PX]; gix += tj * cx[j]; giy += tj * cy[j]; }
-        const float G = sl[0] + gOs * (sc * 2.f - 1.f);
-        const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
-        const float dfx = (dfl ? actf * __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
-        const float dfy = (dfl ? actf * __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
-        const float gs = 2.f * nr * gOs + (G - S) / D;
-        const float* draw = has_draw ? s_draw[tc] + q : nullptr;
-        if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
-        else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
-        else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, cr, wm, tc, s_ct[tc], pair, draw, actf, gs, dfx, dfy);
+        const float* gl = a.glue + pair * 3 * HWd + q;
+        const float gs = actf * __ldg(gl), dfx = actf * __ldg(gl + HWd), dfy = actf * __ldg(gl + 2 * HWd);
+        const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
+        if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
       }
     }
   }
@@ -898,24 +908,28 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     WB_LAUNCH(k_up_tab, dim3((g.W + 63) / 64), dim3(64), 0, st, g.W, g.Wd, a.up_tab);
     WB_BLAUNCHED();
   }
-  // 1. fused HD backward
-  if (a.stages == 0 || (a.stages & 1)) {
-    const dim3 bgrid(a.red_ctas, g.B * g.Tp);
-    const size_t tap4 = (size_t)4 * WB_TAPF * WB_TILE_PX * sizeof(float), tap8 = 2 * tap4;
-#ifndef WB_HOST_EMU
-    // static + dynamic shared memory exceeds the 48 KB default: opt in (cheap, idempotent)
-    if (g.Tc <= 4) cudaFuncSetAttribute(k_warp_composite_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tap4);
-    else cudaFuncSetAttribute(k_warp_composite_bwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tap8);
-#endif
-    if (g.Tc <= 4) WB_LAUNCH(k_warp_composite_bwd<4>, bgrid, dim3(WB_TILE_PX), tap4, st, a);
-    else WB_LAUNCH(k_warp_composite_bwd<8>, bgrid, dim3(WB_TILE_PX), tap8, st, a);
+  const bool st_gather = a.stages == 0 || (a.stages & 1), st_layers = a.stages == 0 || (a.stages & 2), st_rest = a.stages == 0 || (a.stages & 4);
+  const bool need_layers = a.d_alpha_acc || a.d_f_lo || a.d_occ;
+  if (need_layers) WB_BREQ(a.glue && d.score, "glue / score buffers missing");
+  // 1. HD gather backward
+  if (st_gather) {
+    WbDecB ag = a;
+    if (!need_layers) ag.glue = nullptr;
+    const dim3 ggrid(wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX) > 1024 ? 1024 : wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX), g.B * g.Tp);
+    if (g.Tc <= 4) WB_LAUNCH(k_gather_bwd<4>, ggrid, dim3(WB_TILE_PX), 0, st, ag);
+    else WB_LAUNCH(k_gather_bwd<8>, ggrid, dim3(WB_TILE_PX), 0, st, ag);
+    WB_BLAUNCHED();
+  }
+  // 1b. HD layer backward
+  if (st_layers && need_layers) {
+    WB_LAUNCH(k_layers_bwd, dim3(a.red_ctas, g.B * g.Tp), dim3(WB_TILE_PX), 0, st, a);
     WB_BLAUNCHED();
     if (a.d_occ) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);
       WB_BLAUNCHED();
     }
   }
-  if (!need_alpha_chain || !(a.stages == 0 || (a.stages & 2))) return 0;
+  if (!need_alpha_chain || !st_rest) return 0;
   // 2. context-alpha backward
   if (a.d_alpha_acc || a.d_alpha) {
     if (filt && a.d_prof_p) WB_BREQ(a.prof_p_part, "prof_p_part scratch missing");

@@ -199,21 +199,18 @@ def _geom(spec: DecodeSpec, B, T, Tc, Tp, Nl, has_cls):
 PROFILE = None
 
 
-def _staged(fn, arg, stream, what, main_bit, dev):
+def _staged(fn, arg, stream, what, dev):
     if PROFILE is None:
         L.check(fn(C.byref(arg), stream), what)
         return
-    rest_bit = 3 - main_bit
-    first, second = (rest_bit, main_bit) if what == "decode_fwd" else (main_bit, rest_bit)
-    for bit in (first, second):
+    # forward: prep (1), layers (2), gather (4); backward: gather (1), layers (2), rest (4) -- same order as stages = 0
+    for bit, key in ((1, "prep" if what == "decode_fwd" else "gather"), (2, "layers"), (4, "gather" if what == "decode_fwd" else "rest")):
         arg.stages = bit
-        if bit == main_bit:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(torch.cuda.current_stream(dev))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(dev))
         L.check(fn(C.byref(arg), stream), what)
-        if bit == main_bit:
-            e1.record(torch.cuda.current_stream(dev))
-            PROFILE[what].append((e0, e1))
+        e1.record(torch.cuda.current_stream(dev))
+        PROFILE.setdefault(what + ":" + key, []).append((e0, e1))
     arg.stages = 0
 
 
@@ -261,15 +258,16 @@ class _Decode(torch.autograd.Function):
         raw = torch.empty(B, TcR, Tp, CR, Hd, Wd, **f32)
         out_full = torch.empty(B, Tp, Cc + 1, Hd, Wd, **f32)
         norm = torch.empty(B, Tp, Hd, Wd, **f32)
+        score = torch.empty(B, Tc, Tp, Hd, Wd, **f32)
         a = L.DecodeFwd(g, L.ptr(inp_c, name="input"), L.ptr(tgo_c), L.ptr(sgo_c), L.ptr(tgb_c), L.ptr(sgb_c), L.ptr(occ_c),
                         L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
                         L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
                         L.ptr(prof_p), L.ptr(f_lo), L.ptr(s_lo), L.ptr(live_ctx, torch.int32), L.ptr(live_pred, torch.int32), L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full),
-                        L.ptr(norm), 0)
-        _staged(lib.waldo_decode_fwd, a, L.stream_of(inp_c), "decode_fwd", main_bit=2, dev=dev)
+                        L.ptr(norm), L.ptr(score), 0)
+        _staged(lib.waldo_decode_fwd, a, L.stream_of(inp_c), "decode_fwd", dev=dev)
         ctx.spec, ctx.has_cls = spec, cls is not None
         ctx.keep = (a, inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
-                    prof_sum, prof_p, f_lo, s_lo, alpha, flow, raw, out_full, norm, live_ctx, live_pred)
+                    prof_sum, prof_p, f_lo, s_lo, alpha, flow, raw, out_full, norm, live_ctx, live_pred, score)
         ctx.shapes = dict(obj_alpha=obj_alpha.shape, bg_alpha=bg_alpha.shape)
         return out_full, raw, flow, alpha
 
@@ -312,6 +310,7 @@ class _Decode(torch.autograd.Function):
         prof_p_part = torch.empty(g.B * g.Tw, red_ctas, g.No * g.Nl, **f32) if d_prof_p is not None else None
         cls_part = torch.empty(g.B, fwd.prof_ctas, g.No * g.Nl, **f32) if (n_cls and (g.flags & L.F_WEIGHT_CLS)) else None
         up_tab = torch.empty(g.W, 9, **f32)
+        glue = torch.empty(g.B, g.Tc, g.Tp, 3, g.Hd, g.Wd, **f32) if chain else None
         d_cls_s = d_cls
         if d_cls_s is None and cls_c is not None and chain and filt and not (g.flags & L.F_WEIGHT_CLS):
             d_cls_s = None   # P = cls path: nothing to propagate unless cls needs grad
@@ -319,8 +318,8 @@ class _Decode(torch.autograd.Function):
         b = L.DecodeBwd(fwd, L.ptr(grads_in[0]), L.ptr(grads_in[1]), L.ptr(grads_in[2]), L.ptr(grads_in[3]),
                         L.ptr(d_input), L.ptr(d_tgo_s), L.ptr(d_sgo_s), L.ptr(d_tgb_s), L.ptr(d_sgb_s), L.ptr(d_occ),
                         L.ptr(d_oa), L.ptr(d_ba), L.ptr(d_cls_s), L.ptr(d_alpha_acc), L.ptr(d_f_lo), L.ptr(d_a_lo),
-                        L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part), L.ptr(up_tab), 0)
-        _staged(lib.waldo_decode_bwd, b, L.stream_of(inp_c), "decode_bwd", main_bit=1, dev=dev)
+                        L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part), L.ptr(up_tab), L.ptr(glue), 0)
+        _staged(lib.waldo_decode_bwd, b, L.stream_of(inp_c), "decode_bwd", dev=dev)
         if d_oa is not None:
             d_oa = d_oa.view(ctx.shapes["obj_alpha"])
         if d_ba is not None:
