@@ -57,13 +57,22 @@ def alg_bytes(cfg, B, Tc, Tp, backward):
 
 
 def kernel_bytes(cfg, B, Tc, Tp):
-    """Algorithmic bytes per launch of the two fused HD kernels (DESIGN.md "kernels")."""
+    """Algorithmic bytes per launch of the four HD kernels (DESIGN.md "kernels"), fp32.  pair = one (b, tc, tp)."""
     Hd, Wd = cfg.hd_shape
     px, s = Hd * Wd, 4
     C, L = 3 + cfg.num_lyt, cfg.num_obj + 1
-    fwd = px * s * (B * Tc * Tp * (C + L) + B * Tc * Tp * ((C + L) + 2) + B * Tp * (C + 1 + 1))
-    bwd = px * s * (B * Tc * Tp * ((C + L) + 2 + C + L) + B * Tp * (2 * (C + 1) + 1) + B * Tc * (C + L))
-    return fwd, bwd
+    pairs, frames = B * Tc * Tp, B * Tp
+    return {
+        # gather-read the context frame, read flow + score; write the warped channels, the fused output and its norm
+        "k_gather_fwd": px * s * (pairs * (C + 3 + C) + frames * (C + 1 + 1)),
+        # gather-read the context alpha stack; write alpha_ctx, flow, score
+        "k_layers_fwd": px * s * (pairs * (L + L + 2 + 1)),
+        # read d raw_output (image channels), re-read the context frame, flow, score; read d output, output, norm;
+        # write d input once per context frame and the 3-float glue
+        "k_gather_bwd": px * s * (pairs * (C + C + 3 + 3) + frames * (2 * (C + 1) + 1) + B * Tc * C),
+        # read d raw_output (alpha channels), re-read the alpha stack, glue; write d alpha once per context frame
+        "k_layers_bwd": px * s * (pairs * (L + L + 3) + B * Tc * L),
+    }
 
 
 class ClockSampler:
@@ -258,7 +267,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step(resident)
     # ---- device-resident timing, with the dominant kernels bracketed by events inside the timed region
-    Fn.PROFILE = {"decode_fwd": [], "decode_bwd": []}
+    Fn.PROFILE = {}
     launches0 = lib.waldo_launch_count()
     with ClockSampler(local_rank) as clocks:
         ms_step = timed(lambda: step(resident), args.steps)
@@ -277,7 +286,7 @@ def main():
     if rank == 0:
         frames = world * B * Tp
         fwd_b, bwd_b = alg_bytes(cfg, B, Tc, Tp, backward)
-        kf, kb = kernel_bytes(cfg, B, Tc, Tp)
+        kb = kernel_bytes(cfg, B, Tc, Tp)
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
@@ -288,8 +297,12 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             pass
-        kern = {"k_warp_composite_fwd": (prof.get("decode_fwd", 0.0), kf), "k_warp_composite_bwd": (prof.get("decode_bwd", 0.0), kb)}
-        dom = max(kern, key=lambda k: kern[k][0]) if backward else "k_warp_composite_fwd"
+        kern = {"k_gather_fwd": (prof.get("decode_fwd:gather", 0.0), kb["k_gather_fwd"]),
+                "k_layers_fwd": (prof.get("decode_fwd:layers", 0.0), kb["k_layers_fwd"])}
+        if backward:
+            kern["k_gather_bwd"] = (prof.get("decode_bwd:gather", 0.0), kb["k_gather_bwd"])
+            kern["k_layers_bwd"] = (prof.get("decode_bwd:layers", 0.0), kb["k_layers_bwd"])
+        dom = max(kern, key=lambda k: kern[k][0])
         dms, dbytes = kern[dom]
         achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
         line = {
@@ -304,7 +317,8 @@ def main():
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic.get(dom), "ms_per_launch": dms, "alg_bytes_per_launch": dbytes, "peak_source": peak_src,
                          "other": {k: {"ms_per_launch": v[0], "alg_bytes_per_launch": v[1],
-                                       "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None} for k, v in kern.items() if k != dom}},
+                                       "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None} for k, v in kern.items() if k != dom},
+                         "stages_ms": {k: round(v, 4) for k, v in prof.items()}},
         }
         if e2e:
             line["e2e"] = e2e

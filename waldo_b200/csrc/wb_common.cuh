@@ -73,6 +73,8 @@ extern long long g_wb_launches;
 #define WB_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
 #endif
 
+// trip count of the loops over the layer slots of a template: all NA slots when unrolled, the live count when rolled
+#define WB_NEND (NA <= 8 ? NA : ix.n)
 #define WB_MAX_L 17
 #define WB_MAX_C 24
 #define WB_MAX_NL 21

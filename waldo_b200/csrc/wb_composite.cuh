@@ -61,7 +61,7 @@ WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, 
   const int L = g.No + 1;
   const unsigned HW = (unsigned)(g.H * g.W), HWd = (unsigned)(g.Hd * g.Wd);
   float mx = 0.f;   // layers outside the union have R = 0, and R >= 0 always
-  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     ly.R[s] = 0.f; ly.A[s] = 0.f; ly.Fx[s] = 0.f; ly.Fy[s] = 0.f;
     if (s < ix.n) {
       const int k = ix.k[s];
@@ -87,11 +87,11 @@ WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, 
   }
   ly.disocc = mx;
   float fx = 0.f, fy = 0.f, sc = 0.f;
-  WB_UNROLL_NA for (int i = 0; i < NA; ++i) {
+  WB_UNROLL_NA for (int i = 0; i < WB_NEND; ++i) {
     if (i < ix.n) {
       const float* oc = s_occ + ix.k[i];
       float vis = 1.f;
-      WB_UNROLL_NA for (int j = 0; j < NA; ++j) if (j < ix.n) vis *= 1.f - ly.R[j] * oc[ix.k[j] * L];
+      WB_UNROLL_NA for (int j = 0; j < WB_NEND; ++j) if (j < ix.n) vis *= 1.f - ly.R[j] * oc[ix.k[j] * L];
       float a = vis * ly.R[i];
       ly.A[i] = a;
       fx += a * ly.Fx[i]; fy += a * ly.Fy[i]; sc += a;
@@ -123,7 +123,7 @@ WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, un
   float* ra = raw + (size_t)C * HWd + q;
   WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) *ra = -1.f; ra += HWd; }
   ra = raw + (size_t)C * HWd + q;
-  WB_UNROLL_NA for (int s = 0; s < NA; ++s) if (s < ix.n) ra[(size_t)ix.k[s] * HWd] = ly.A[s] * 2.f - 1.f;
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) if (s < ix.n) ra[(size_t)ix.k[s] * HWd] = ly.A[s] * 2.f - 1.f;
   if (c.disocc_ch) ra[(size_t)L * HWd] = ly.disocc;
   float* fl = d.flow + pair * 2 * HWd + q;
   fl[0] = ly.flow_x; fl[HWd] = ly.flow_y;
@@ -245,13 +245,22 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_fwd(WbDec d) {
 #pragma unroll 2
 #endif
       for (int ch = 0; ch < C; ++ch) {
-        float acc = 0.f;
+        // all 4 x TCAP loads of this channel first (read-only path), then the arithmetic and the stores
+        float v[TCAP][4];
         WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
           if (tc < g.Tc) {
             const float* pl = s_src[tc] + choff;
-            const float v = wb_gather2(pl + o0[tc], pl + o1[tc], w[tc]);
-            s_raw[tc][choff + q] = v;
-            acc += wgt[tc] * v;
+            const float* p0 = pl + o0[tc];
+            const float* p1 = pl + o1[tc];
+            v[tc][0] = __ldg(p0); v[tc][1] = __ldg(p0 + 1); v[tc][2] = __ldg(p1); v[tc][3] = __ldg(p1 + 1);
+          }
+        }
+        float acc = 0.f;
+        WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+          if (tc < g.Tc) {
+            const float r = __fmaf_rn(v[tc][3], w[tc][3], __fmaf_rn(v[tc][2], w[tc][2], __fmaf_rn(v[tc][1], w[tc][1], __fmul_rn(v[tc][0], w[tc][0]))));
+            s_raw[tc][choff + q] = r;
+            acc += wgt[tc] * r;
           }
         }
         if (self) { const float v = __ldg(self_src + choff); self_raw[choff] = v; acc += wself * v; }

@@ -34,6 +34,8 @@ WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) atomicAdd(p, v); }
 #endif
 #define WB_COL_TAPS 8     // max lanes touching one low-res column
 #define WB_STAGE_SLOTS 8  // values staged per round and lane
+#define WB_STAGE_ROW (WB_WARP + 2 * WB_COL_TAPS)   // one staged value: 8 zeros | the lanes | 8 zeros (no bounds checks in the flush)
+#define WB_STAGE_AT(v, lane) ((v) * WB_STAGE_ROW + WB_COL_TAPS + (lane))
 
 struct WbColRed {
   int col[WB_CPL];                 // absolute low-res column owned by this lane (-1: none)
@@ -78,8 +80,12 @@ WB_DEV WbColRed wb_colred_setup(const float* __restrict__ tab, int x0, int i0_fi
       const int col = i0_first + jj;
       cr.col[cpl] = col;
       const float* e = tab + col * 9;
-      cr.lo[cpl] = (int)__ldg(e) - x0;
-      WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) cr.w[cpl][t] = __ldg(e + 1 + t);
+      const int lo = (int)__ldg(e) - x0;
+      if (lo < -(WB_COL_TAPS - 1) || lo > WB_WARP - 1) cr.col[cpl] = -1;   // none of this warp's lanes touches the column
+      else {
+        cr.lo[cpl] = lo;
+        WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) cr.w[cpl][t] = __ldg(e + 1 + t);
+      }
     }
   }
   return cr;
@@ -90,9 +96,9 @@ WB_DEV void wb_colred_flush(const WbColRed& cr, const float* s_stage, int nv, fl
   WB_UNROLL for (int cpl = 0; cpl < WB_CPL; ++cpl) {
     if (cr.col[cpl] >= 0) {
       for (int v = 0; v < nv; ++v) {
-        const float* sv = s_stage + v * WB_WARP + cr.lo[cpl];
+        const float* sv = s_stage + WB_STAGE_AT(v, cr.lo[cpl]);   // lo in [-7, WARP-1]: always inside the padded row
         float acc = 0.f;
-        WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) if (cr.lo[cpl] + t >= 0 && cr.lo[cpl] + t < WB_WARP) acc += cr.w[cpl][t] * sv[t];
+        WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) acc += cr.w[cpl][t] * sv[t];
         if (acc != 0.f) {
           atomicAdd(dst[v] + ((size_t)cr.row0 * W + cr.col[cpl]) * stride, acc * cr.wy0);
           atomicAdd(dst[v] + ((size_t)cr.row1 * W + cr.col[cpl]) * stride, acc * cr.wy1);
@@ -107,15 +113,15 @@ WB_DEV void wb_colred_flush(const WbColRed& cr, const float* s_stage, int nv, fl
 template <int NA>
 WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, int L, const WbIdx<NA>& ix, float* gR, float* s_acc) {
   const int lane = wb_lane();
-  WB_UNROLL_NA for (int i = 0; i < NA; ++i) {
+  WB_UNROLL_NA for (int i = 0; i < WB_NEND; ++i) {
     if (i < ix.n) {
       float pre[NA];
       float run = 1.f;
-      WB_UNROLL_NA for (int j = 0; j < NA; ++j) if (j < ix.n) { pre[j] = run; run *= 1.f - R[j] * s_occ[ix.k[j] * L + ix.k[i]]; }
+      WB_UNROLL_NA for (int j = 0; j < WB_NEND; ++j) if (j < ix.n) { pre[j] = run; run *= 1.f - R[j] * s_occ[ix.k[j] * L + ix.k[i]]; }
       gR[i] += gA[i] * run;
       const float gV = gA[i] * R[i];
       float suf = 1.f;
-      WB_UNROLL_NA for (int j = NA - 1; j >= 0; --j) {
+      WB_UNROLL_NA for (int j = WB_NEND - 1; j >= 0; --j) {
         if (j < ix.n) {
           const float oc = s_occ[ix.k[j] * L + ix.k[i]];
           const float excl = pre[j] * suf;
@@ -166,7 +172,7 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
   WbLay<NA> ly;
   wb_layers_fwd<NA>(d, px, ix, d.f_lo + pair * L * HW * 2, alpha_c, c.s_occ, ly);
   float gA[NA], gR[NA], gFx[NA], gFy[NA];
-  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     gR[s] = 0.f; gA[s] = 0.f; gFx[s] = 0.f; gFy[s] = 0.f;
     if (s < ix.n) {
       gA[s] = gs + 2.f * (draw ? actf * __ldg(draw + (size_t)(C + ix.k[s]) * HWd) : 0.f) + dfx * ly.Fx[s] + dfy * ly.Fy[s];
@@ -178,12 +184,12 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
   if (c.disocc_ch && draw) {
     const float gd = actf * __ldg(draw + (size_t)(C + L) * HWd);
     bool done = false;
-    WB_UNROLL_NA for (int s = 0; s < NA; ++s)
+    WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s)
       if (s < ix.n && !done && ly.R[s] == ly.disocc) { gR[s] += gd; done = true; }
   }
   // ---- B6 backward: bilinear sample of the context opacity through layer k's flow
   float* dal = a.d_alpha_acc ? a.d_alpha_acc + ((size_t)c.b * g.Tw + c_t) * L * HWd : nullptr;
-  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     if (s < ix.n) {
       const int k = ix.k[s];
       if (((px.isobj >> k) & 1u) && gR[s] != 0.f) {
@@ -211,7 +217,7 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
   // ---- B5(up) backward: transpose of the bilinear up-sampling of the layer flows
   if (a.d_f_lo) {
     if (c.lowres_direct) {
-      WB_UNROLL_NA for (int s = 0; s < NA; ++s)
+      WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s)
         if (s < ix.n) {
           float* o = a.d_f_lo + (pair * L + ix.k[s]) * HW * 2 + (size_t)px.o00 * 2;
           wb_atomic_add(o, gFx[s]); wb_atomic_add(o + 1, gFy[s]);
@@ -221,8 +227,8 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
       if constexpr (NA <= WB_STAGE_SLOTS) {
         float* dst[2 * NA];
         WB_UNROLL for (int s = 0; s < NA; ++s) {
-          c.s_stage[(2 * s) * WB_WARP + lane] = gFx[s];
-          c.s_stage[(2 * s + 1) * WB_WARP + lane] = gFy[s];
+          c.s_stage[WB_STAGE_AT(2 * s, lane)] = gFx[s];
+          c.s_stage[WB_STAGE_AT(2 * s + 1, lane)] = gFy[s];
           float* base = a.d_f_lo + (pair * L + ix.k[s]) * HW * 2;
           dst[2 * s] = base; dst[2 * s + 1] = base + 1;
         }
@@ -234,8 +240,8 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
           float* dst[2 * WB_STAGE_SLOTS];
           const int ns = min(WB_STAGE_SLOTS, ix.n - s0);
           for (int j = 0; j < ns; ++j) {
-            c.s_stage[(2 * j) * WB_WARP + lane] = gFx[s0 + j];
-            c.s_stage[(2 * j + 1) * WB_WARP + lane] = gFy[s0 + j];
+            c.s_stage[WB_STAGE_AT(2 * j, lane)] = gFx[s0 + j];
+            c.s_stage[WB_STAGE_AT(2 * j + 1, lane)] = gFy[s0 + j];
             float* base = a.d_f_lo + (pair * L + ix.k[s0 + j]) * HW * 2;
             dst[2 * j] = base; dst[2 * j + 1] = base + 1;
           }
@@ -313,16 +319,23 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
       for (int ch = 0; ch < C; ++ch) {
         const float gO = dof ? actf * __ldg(dof + choff) : 0.f;
         if (dof) S += gO * __ldg(of + choff);
+        // all loads of this channel first (read-only path), then the arithmetic and the reductions: keeps
+        // 5 x TCAP independent loads in flight per thread
+        float v[TCAP][4], gd[TCAP];
         WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
           if (tc < g.Tc) {
             const float* pl = s_src[tc] + choff;
             const float* p0 = pl + o0[tc];
             const float* p1 = pl + o1[tc];
-            const float v0 = __ldg(p0), v1 = __ldg(p0 + 1), v2 = __ldg(p1), v3 = __ldg(p1 + 1);
-            const float gd = has_draw ? actf * __ldg(s_draw[tc] + choff + q) : 0.f;
-            const float go = gd + nrm[tc] * gO;
-            U[tc][0] += gO * v0; U[tc][1] += gO * v1; U[tc][2] += gO * v2; U[tc][3] += gO * v3;
-            Tq[tc][0] += gd * v0; Tq[tc][1] += gd * v1; Tq[tc][2] += gd * v2; Tq[tc][3] += gd * v3;
+            v[tc][0] = __ldg(p0); v[tc][1] = __ldg(p0 + 1); v[tc][2] = __ldg(p1); v[tc][3] = __ldg(p1 + 1);
+            gd[tc] = has_draw ? __ldg(s_draw[tc] + choff + q) : 0.f;
+          }
+        }
+        WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+          if (tc < g.Tc) {
+            const float gdt = actf * gd[tc];
+            const float go = gdt + nrm[tc] * gO;
+            WB_UNROLL for (int j = 0; j < 4; ++j) { U[tc][j] += gO * v[tc][j]; Tq[tc][j] += gdt * v[tc][j]; }
             if (has_din) {
               float* dl = s_dsrc[tc] + choff;
               atomicAdd(dl + o0[tc], w[tc][0] * go); atomicAdd(dl + o0[tc] + 1, w[tc][1] * go);
@@ -385,9 +398,10 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_bwd(WbDecB a) {
   const unsigned HWd = c.HWd;
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
-  __shared__ float s_stage[WB_NWARP][2 * WB_STAGE_SLOTS * WB_WARP];
+  __shared__ float s_stage[WB_NWARP][2 * WB_STAGE_SLOTS * WB_STAGE_ROW];
   for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + u) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
+  for (int i = wb_tid(); i < WB_NWARP * 2 * WB_STAGE_SLOTS * WB_STAGE_ROW; i += wb_nthr()) (&s_stage[0][0])[i] = 0.f;
   __syncthreads();
   c.s_occ = s_occ; c.s_stage = s_stage[wb_warp()];
   c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
@@ -482,7 +496,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   float sm[NN];
   if (c.filt && any_obj) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
   float aup[NA], av[NA], ell[NA];
-  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     av[s] = 0.f; aup[s] = 0.f; ell[s] = 1.f;
     if (s < ix.n) {
       const int k = ix.k[s];
@@ -501,7 +515,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   }
   // ---- upstream: scatter-accumulated d/dA plus the returned alpha = 2A - 1 (zero beyond the image edge)
   float gA[NA], ga[NA];
-  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     ga[s] = 0.f; gA[s] = 0.f;
     if (s < ix.n) {
       const size_t o = (((size_t)b * g.Tw + t) * L + ix.k[s]) * HWd + q;
@@ -521,7 +535,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
     for (int s = 0; s < ix.n; ++s) {
       float gl = 0.f;
       int k = 0;
-      WB_UNROLL_NA for (int ss = 0; ss < NA; ++ss) if (ss == s) { gl = ga[ss] * aup[ss]; k = ix.k[ss]; }   // d / d l_k
+      WB_UNROLL_NA for (int ss = 0; ss < WB_NEND; ++ss) if (ss == s) { gl = ga[ss] * aup[ss]; k = ix.k[ss]; }   // d / d l_k
       if (k < 1) continue;   // warp-uniform
       const float* P = c.s_P + (k - 1) * Nl;
       float v[32];
@@ -547,12 +561,12 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   // ---- up-sampling backward: d a_lo
   if (a.d_a_lo) {
     if (c.lowres_direct) {
-      WB_UNROLL_NA for (int s = 0; s < NA; ++s)
+      WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s)
         if (s < ix.n) wb_atomic_add(a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s]) * HW + o00, ga[s] * ell[s]);
     } else if constexpr (NA <= WB_STAGE_SLOTS) {
       float* dst[NA];
       WB_UNROLL for (int s = 0; s < NA; ++s) {
-        c.s_stage[s * WB_WARP + lane] = ga[s] * ell[s];
+        c.s_stage[WB_STAGE_AT(s, lane)] = ga[s] * ell[s];
         dst[s] = a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s]) * HW;
       }
       __syncwarp();
@@ -563,7 +577,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
         float* dst[WB_STAGE_SLOTS];
         const int ns = min(WB_STAGE_SLOTS, ix.n - s0);
         for (int j = 0; j < ns; ++j) {
-          c.s_stage[j * WB_WARP + lane] = ga[s0 + j] * ell[s0 + j];
+          c.s_stage[WB_STAGE_AT(j, lane)] = ga[s0 + j] * ell[s0 + j];
           dst[j] = a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s0 + j]) * HW;
         }
         __syncwarp();
@@ -577,7 +591,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
     WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dot += gsm[cc] * sm[cc];
     float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd + q;
     WB_UNROLL for (int cc = 0; cc < NN; ++cc)
-      if (NLC > 0 || cc < Nl) { const float v = sm[cc] * (gsm[cc] - dot); if (v != 0.f) *o += v; o += HWd; }
+      if (NLC > 0 || cc < Nl) { atomicAdd(o, sm[cc] * (gsm[cc] - dot)); o += HWd; }   // fire-and-forget reduction
   }
 }
 
@@ -598,11 +612,12 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
   __shared__ float s_redp[WB_NWARP][(WB_MAX_L - 1) * WB_MAX_NL];
-  __shared__ float s_stage[WB_NWARP][WB_STAGE_SLOTS * WB_WARP];
+  __shared__ float s_stage[WB_NWARP][WB_STAGE_SLOTS * WB_STAGE_ROW];
   if (c.filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)c.b * No * Nl + i];
   for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + c.t) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
   for (int i = wb_tid(); i < WB_NWARP * (WB_MAX_L - 1) * WB_MAX_NL; i += wb_nthr()) (&s_redp[0][0])[i] = 0.f;
+  for (int i = wb_tid(); i < WB_NWARP * WB_STAGE_SLOTS * WB_STAGE_ROW; i += wb_nthr()) (&s_stage[0][0])[i] = 0.f;
   __syncthreads();
   c.s_P = s_P; c.s_occ = s_occ; c.s_stage = s_stage[wb_warp()];
   c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
@@ -627,6 +642,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
       WbColRed cr;
       if (a.d_a_lo && !c.lowres_direct) cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(ax.i0, 0), wb_shfl(ax.i1, WB_WARP - 1), ay);
       if (n <= 4) wb_prep_bwd_pixel<4, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
+      else if (n <= 8) wb_prep_bwd_pixel<8, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
       else wb_prep_bwd_pixel<WB_MAX_L, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
     }
   }

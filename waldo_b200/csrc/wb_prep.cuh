@@ -214,7 +214,7 @@ WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, unsig
   float sm[NN];
   if (c.filt && (wm >> 1)) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
   float a[NA];
-  WB_UNROLL_NA for (int s = 0; s < NA; ++s) {
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     a[s] = 0.f;
     if (s < ix.n) {
       const int k = ix.k[s];
@@ -233,11 +233,11 @@ WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, unsig
   float* o = c.out + q;
   WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) *o = -1.f; o += HWd; }
   o = c.out + q;
-  WB_UNROLL_NA for (int i = 0; i < NA; ++i) {
+  WB_UNROLL_NA for (int i = 0; i < WB_NEND; ++i) {
     if (i < ix.n) {
       const float* oc = c.s_occ + ix.k[i];
       float vis = 1.f;
-      WB_UNROLL_NA for (int j = 0; j < NA; ++j) if (j < ix.n) vis *= 1.f - a[j] * oc[ix.k[j] * L];
+      WB_UNROLL_NA for (int j = 0; j < WB_NEND; ++j) if (j < ix.n) vis *= 1.f - a[j] * oc[ix.k[j] * L];
       o[(size_t)ix.k[i] * HWd] = (vis * a[i]) * 2.f - 1.f;
     }
   }
