@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-input-grad", action="store_true", help="experiment: do not request d input")
     args = ap.parse_args()
 
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -231,7 +232,7 @@ def main():
         g_raw = torch.randn(B, Tc, Tp, C + L, Hd, Wd, device=dev, generator=gen)
 
     def step(src):
-        lv = {k: src[k].detach().requires_grad_(backward) for k in keys}
+        lv = {k: src[k].detach().requires_grad_(backward and not (args.no_input_grad and k == "input")) for k in keys}
         with torch.set_grad_enabled(backward):
             occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, lv["obj_alpha_raw"], om, bg, lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
             out = wb.decode_output(warper, lv["input"], grid, occ, oa, ba, lv["cls"], ctx_ts, pred_ts, cfg.restrict_to_ctx)

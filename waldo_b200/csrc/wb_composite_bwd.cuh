@@ -261,10 +261,11 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
 //   k_layers_bwd : backward of the layer part (B9..B5up) driven by `glue` and the alpha channels of d raw_output.
 // ------------------------------------------------------------------------------------------------------------------
 
-// grid = (CTAs, B*Tp), 32x8 pixel tiles.  One rolled loop over the image channels, contexts unrolled inside.  Since the
+// grid = (CTAs, B*Tp), 32x8 pixel tiles.  The contexts are processed TG at a time (small register state -> high
+// occupancy); per group ONE rolled loop over the image channels with the TG contexts unrolled inside.  Since the
 // gathered value is bilinear in the four taps, d score and d flow follow from the tap moments
 //   U_j = sum_ch dOut_ch * v_j,   T_j = sum_ch dRaw_ch * v_j     (j = the four tap positions).
-template <int TCAP>
+template <int TG>
 __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
@@ -273,9 +274,9 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
   const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
   const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
   const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
-  __shared__ const float* s_src[TCAP];    // context frame of every context (CTA-uniform)
-  __shared__ float* s_dsrc[TCAP];         // its gradient
-  __shared__ const float* s_draw[TCAP];   // upstream d raw_output block of every context (or null)
+  __shared__ const float* s_src[8];    // context frame of every context (CTA-uniform)
+  __shared__ float* s_dsrc[8];         // its gradient
+  __shared__ const float* s_draw[8];   // upstream d raw_output block of every context (or null)
   for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
     const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
     s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
@@ -295,85 +296,90 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
       const unsigned q = (unsigned)(Y * g.Wd + X);
       const float gx = __ldg(d.xs_hd + X), gy = __ldg(d.ys_hd + Y);
       const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
-      unsigned o0[TCAP], o1[TCAP];
-      float w[TCAP][4], nrm[TCAP], U[TCAP][4], Tq[TCAP][4];
-      WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
-        o0[tc] = 0u; o1[tc] = 0u; nrm[tc] = 0.f;
-        WB_UNROLL for (int j = 0; j < 4; ++j) { w[tc][j] = 0.f; U[tc][j] = 0.f; Tq[tc][j] = 0.f; }
-        if (tc < g.Tc) {
-          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-          const float* fl = d.flow + pair * 2 * HWd + q;
-          const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
-          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-          o0[tc] = t2.o0; o1[tc] = t2.o1;
-          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = t2.w[j];
-          nrm[tc] = (__ldg(d.score + pair * HWd + q) + 1e-6f) / D;
-        }
-      }
       const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
       const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
-      float* dself = (self && has_din) ? a.d_input + ((size_t)b * g.T + tp) * C * HWd + q : nullptr;
-      const float* drself = (self && has_draw) ? a.d_raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q : nullptr;
-      float S = 0.f;
-      unsigned choff = 0u;   // ch * HWd
-      for (int ch = 0; ch < C; ++ch) {
-        const float gO = dof ? actf * __ldg(dof + choff) : 0.f;
-        if (dof) S += gO * __ldg(of + choff);
-        // all loads of this channel first (read-only path), then the arithmetic and the reductions: keeps
-        // 5 x TCAP independent loads in flight per thread
-        float v[TCAP][4], gd[TCAP];
-        WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
-          if (tc < g.Tc) {
-            const float* pl = s_src[tc] + choff;
-            const float* p0 = pl + o0[tc];
-            const float* p1 = pl + o1[tc];
-            v[tc][0] = __ldg(p0); v[tc][1] = __ldg(p0 + 1); v[tc][2] = __ldg(p1); v[tc][3] = __ldg(p1 + 1);
-            gd[tc] = has_draw ? __ldg(s_draw[tc] + choff + q) : 0.f;
+      float S = 0.f;   // sum_ch dOut * out, complete after the first group
+      for (int tc0 = 0; tc0 < g.Tc; tc0 += TG) {
+        unsigned o0[TG], o1[TG];
+        float w[TG][4], nrm[TG], U[TG][4], Tq[TG][4];
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          o0[i] = 0u; o1[i] = 0u; nrm[i] = 0.f;
+          WB_UNROLL for (int j = 0; j < 4; ++j) { w[i][j] = 0.f; U[i][j] = 0.f; Tq[i][j] = 0.f; }
+          if (tc0 + i < g.Tc) {
+            const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
+            const float* fl = d.flow + pair * 2 * HWd + q;
+            const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+            const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+            o0[i] = t2.o0; o1[i] = t2.o1;
+            WB_UNROLL for (int j = 0; j < 4; ++j) w[i][j] = t2.w[j];
+            nrm[i] = (__ldg(d.score + pair * HWd + q) + 1e-6f) / D;
           }
         }
-        WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
-          if (tc < g.Tc) {
-            const float gdt = actf * gd[tc];
-            const float go = gdt + nrm[tc] * gO;
-            WB_UNROLL for (int j = 0; j < 4; ++j) { U[tc][j] += gO * v[tc][j]; Tq[tc][j] += gdt * v[tc][j]; }
-            if (has_din) {
-              float* dl = s_dsrc[tc] + choff;
-              atomicAdd(dl + o0[tc], w[tc][0] * go); atomicAdd(dl + o0[tc] + 1, w[tc][1] * go);
-              atomicAdd(dl + o1[tc], w[tc][2] * go); atomicAdd(dl + o1[tc] + 1, w[tc][3] * go);
+        const bool first = tc0 == 0;
+        float* dself = (first && self && has_din) ? a.d_input + ((size_t)b * g.T + tp) * C * HWd + q : nullptr;
+        const float* drself = (self && has_draw) ? a.d_raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q : nullptr;
+        unsigned choff = 0u;   // ch * HWd
+#ifndef WB_HOST_EMU
+#pragma unroll 2
+#endif
+        for (int ch = 0; ch < C; ++ch) {
+          // all loads of this channel first (read-only path), then the arithmetic and the reductions
+          float v[TG][4], gd[TG];
+          const float gO = dof ? actf * __ldg(dof + choff) : 0.f;
+          WB_UNROLL for (int i = 0; i < TG; ++i) {
+            if (tc0 + i < g.Tc) {
+              const float* pl = s_src[tc0 + i] + choff;
+              const float* p0 = pl + o0[i];
+              const float* p1 = pl + o1[i];
+              v[i][0] = __ldg(p0); v[i][1] = __ldg(p0 + 1); v[i][2] = __ldg(p1); v[i][3] = __ldg(p1 + 1);
+              gd[i] = has_draw ? __ldg(s_draw[tc0 + i] + choff + q) : 0.f;
             }
           }
-        }
-        if (dself && active) {   // lvd.py:845: the target frame passes straight through
-          const float nself = (1.f + 1e-6f) / D;
-          wb_atomic_add(dself + choff, (drself ? __ldg(drself + choff) : 0.f) + nself * gO);
-        }
-        choff += HWd;
-      }
-      if (!a.glue || !active) continue;   // (threads beyond the edge must not overwrite the pixel they mirror)
-      const float gOs = dof ? actf * __ldg(dof + choff) : 0.f;   // d / d (fused score channel), index C
-      if (dof) S += gOs * __ldg(of + choff);
-      WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
-        if (tc < g.Tc) {
-          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-          const float* fl = d.flow + pair * 2 * HWd + q;
-          const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
-          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-          float cx[4], cy[4];
-          wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
-          wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
-          const float sc = nrm[tc] * D - 1e-6f;
-          float G = U[tc][0] * w[tc][0] + U[tc][1] * w[tc][1] + U[tc][2] * w[tc][2] + U[tc][3] * w[tc][3];
-          float gix = 0.f, giy = 0.f;
-          WB_UNROLL for (int j = 0; j < 4; ++j) {
-            const float tj = Tq[tc][j] + nrm[tc] * U[tc][j];
-            gix += tj * cx[j]; giy += tj * cy[j];
+          if (first && dof) S += gO * __ldg(of + choff);
+          WB_UNROLL for (int i = 0; i < TG; ++i) {
+            if (tc0 + i < g.Tc) {
+              const float gdt = actf * gd[i];
+              const float go = gdt + nrm[i] * gO;
+              WB_UNROLL for (int j = 0; j < 4; ++j) { U[i][j] += gO * v[i][j]; Tq[i][j] += gdt * v[i][j]; }
+              if (has_din) {
+                float* dl = s_dsrc[tc0 + i] + choff;
+                atomicAdd(dl + o0[i], w[i][0] * go); atomicAdd(dl + o0[i] + 1, w[i][1] * go);
+                atomicAdd(dl + o1[i], w[i][2] * go); atomicAdd(dl + o1[i] + 1, w[i][3] * go);
+              }
+            }
           }
-          G += gOs * (sc * 2.f - 1.f);
-          const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
-          float* gl = a.glue + pair * 3 * HWd + q;
-          gl[0] = 2.f * nrm[tc] * gOs + (G - S) / D;
-          gl[HWd] = (dfl ? actf * __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
-          gl[2 * HWd] = (dfl ? actf * __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
+          if (dself && active) {   // lvd.py:845: the target frame passes straight through
+            const float nself = (1.f + 1e-6f) / D;
+            wb_atomic_add(dself + choff, (drself ? __ldg(drself + choff) : 0.f) + nself * gO);
+          }
+          choff += HWd;
+        }
+        if (!a.glue || !active) continue;   // (threads beyond the edge must not overwrite the pixel they mirror)
+        const float gOs = dof ? __ldg(dof + choff) : 0.f;   // d / d (fused score channel), index C
+        if (first && dof) S += gOs * __ldg(of + choff);
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          if (tc0 + i < g.Tc) {
+            const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
+            const float* fl = d.flow + pair * 2 * HWd + q;
+            const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+            const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+            float cx[4], cy[4];
+            wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
+            wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
+            const float sc = nrm[i] * D - 1e-6f;
+            float G = U[i][0] * w[i][0] + U[i][1] * w[i][1] + U[i][2] * w[i][2] + U[i][3] * w[i][3];
+            float gix = 0.f, giy = 0.f;
+            WB_UNROLL for (int j = 0; j < 4; ++j) {
+              const float tj = Tq[i][j] + nrm[i] * U[i][j];
+              gix += tj * cx[j]; giy += tj * cy[j];
+            }
+            G += gOs * (sc * 2.f - 1.f);
+            const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
+            float* gl = a.glue + pair * 3 * HWd + q;
+            gl[0] = 2.f * nrm[i] * gOs + (G - S) / D;
+            gl[HWd] = (dfl ? __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+            gl[2 * HWd] = (dfl ? __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
+          }
         }
       }
     }
@@ -932,8 +938,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     WbDecB ag = a;
     if (!need_layers) ag.glue = nullptr;
     const dim3 ggrid(wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX) > 1024 ? 1024 : wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX), g.B * g.Tp);
-    if (g.Tc <= 4) WB_LAUNCH(k_gather_bwd<4>, ggrid, dim3(WB_TILE_PX), 0, st, ag);
-    else WB_LAUNCH(k_gather_bwd<8>, ggrid, dim3(WB_TILE_PX), 0, st, ag);
+    WB_LAUNCH(k_gather_bwd<2>, ggrid, dim3(WB_TILE_PX), 0, st, ag);
     WB_BLAUNCHED();
   }
   // 1b. HD layer backward
