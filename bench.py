@@ -76,29 +76,37 @@ def kernel_bytes(cfg, B, Tc, Tp):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons, polled every 200 ms by ONE long-lived nvidia-smi process that is started
+    well before the timed region (its start-up takes driver locks and would otherwise stall the first timed launches);
+    summary() keeps the samples whose arrival time falls inside [mark_begin(), mark_end()]."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def __enter__(self):
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
-        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def wait_ready(self, timeout=5.0):
+        t = time.time()
+        while self.proc and not self.rows and time.time() - t < timeout:
+            time.sleep(0.05)
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def close(self):
         if self.proc:
-            time.sleep(0.25)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -106,14 +114,16 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if self.t0 is not None and self.t0 - 0.05 <= t <= (self.t1 or t) + 0.25 and len(r) >= 6]
+        if not rows and self.rows:   # timed region shorter than the polling period: take the sample nearest to it
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - (self.t0 or tr[0])))[1]]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 6:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -265,13 +275,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    clocks = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         step(resident)
+    clocks.wait_ready()
     # ---- device-resident timing, with the dominant kernels bracketed by events inside the timed region
     Fn.PROFILE = {}
     launches0 = lib.waldo_launch_count()
-    with ClockSampler(local_rank) as clocks:
-        ms_step = timed(lambda: step(resident), args.steps)
+    clocks.mark_begin()
+    ms_step = timed(lambda: step(resident), args.steps)
+    clocks.mark_end()
     launches = lib.waldo_launch_count() - launches0
     prof = {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in Fn.PROFILE.items()}
     Fn.PROFILE = None
@@ -284,6 +297,7 @@ def main():
         e2e = {"value": world * B * Tp / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
+    clocks.close()
     if rank == 0:
         frames = world * B * Tp
         fwd_b, bwd_b = alg_bytes(cfg, B, Tc, Tp, backward)

@@ -14,7 +14,9 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwaldo_b200.so")
+# WALDO_B200_LIB points at an alternative build of the SAME sources (kernel experiments); it must still be an sm_100a
+# device library -- load() checks waldo_has_device_code() either way.
+LIB_PATH = os.environ.get("WALDO_B200_LIB") or os.path.join(_HERE, "libwaldo_b200.so")
 
 c_float_p = C.c_void_p
 c_void_p = C.c_void_p
@@ -129,7 +131,7 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
-        if build_if_missing:
+        if build_if_missing and not os.environ.get("WALDO_B200_LIB"):
             from . import build as _build
             try:
                 if _build.stale():

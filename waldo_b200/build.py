@@ -29,21 +29,25 @@ def stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """`defines` / `out` are for kernel experiments only (e.g. -DWB_NA_VARIANTS=1 into another file, loaded through
+    the WALDO_B200_LIB environment variable); the package always builds and loads LIB."""
+    if not force and not stale() and out == LIB:
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "--use_fast_math=false",
            "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out] + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     cmd = [c for c in cmd if c != "--use_fast_math=false"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stdout + r.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else LIB))

@@ -76,6 +76,15 @@ extern long long g_wb_launches;
 // trip count of the loops over the layer slots of a template: all NA slots when unrolled, the live count when rolled
 #define WB_NEND (NA <= 8 ? NA : ix.n)
 #define WB_MAX_L 17
+// Which per-warp layer-slot instantiations a kernel carries: 3 = {4 unrolled, 8 unrolled, rolled}, 2 = {4 unrolled, rolled},
+// 1 = {rolled}.  Fewer variants = smaller code = fewer instruction-cache misses.  Measured on B200 (profiles/): the forward
+// kernels are fastest with all three, the (much larger) backward kernels with the rolled body only.
+#ifndef WB_NA_VARIANTS_FWD
+#define WB_NA_VARIANTS_FWD 3
+#endif
+#ifndef WB_NA_VARIANTS_BWD
+#define WB_NA_VARIANTS_BWD 1
+#endif
 #define WB_MAX_C 24
 #define WB_MAX_NL 21
 #define WB_MAX_K 256

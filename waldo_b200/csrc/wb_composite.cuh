@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_fwd(WbDec d) {
         const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
         float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
         float flow_x, flow_y, score;
-        if (n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
-        else if (n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
+        if (WB_NA_VARIANTS_FWD >= 2 && n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
+        else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
         else wb_fwd_layers<WB_MAX_L>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
         d.score[pair * HWd + q] = score;
       }

@@ -431,8 +431,8 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_bwd(WbDecB a) {
         const float* gl = a.glue + pair * 3 * HWd + q;
         const float gs = actf * __ldg(gl), dfx = actf * __ldg(gl + HWd), dfy = actf * __ldg(gl + 2 * HWd);
         const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
-        if (n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
-        else if (n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        if (WB_NA_VARIANTS_BWD >= 2 && n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+        else if (WB_NA_VARIANTS_BWD >= 3 && n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
         else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
       }
     }
@@ -647,8 +647,8 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
       if (n == 0) continue;   // warp-uniform: nothing live here, every gradient path is dead
       WbColRed cr;
       if (a.d_a_lo && !c.lowres_direct) cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(ax.i0, 0), wb_shfl(ax.i1, WB_WARP - 1), ay);
-      if (n <= 4) wb_prep_bwd_pixel<4, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
-      else if (n <= 8) wb_prep_bwd_pixel<8, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
+      if (WB_NA_VARIANTS_BWD >= 2 && n <= 4) wb_prep_bwd_pixel<4, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
+      else if (WB_NA_VARIANTS_BWD >= 3 && n <= 8) wb_prep_bwd_pixel<8, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
       else wb_prep_bwd_pixel<WB_MAX_L, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
     }
   }

@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep(WbDec d) {
       const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
       const unsigned wm = wb_warp_or(wb_live4(live, o00, o01, o10, o11));
       const int n = __popc(wm);
-      if (n <= 4) wb_prep_pixel<4, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
-      else if (n <= 8) wb_prep_pixel<8, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
+      if (WB_NA_VARIANTS_FWD >= 2 && n <= 4) wb_prep_pixel<4, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
+      else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_prep_pixel<8, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
       else wb_prep_pixel<WB_MAX_L, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
     }
   }
