@@ -72,7 +72,7 @@ WB_DEV void wb_softmax(const float* x, float* y, int n) {
 // Deterministic two-step reduction: every CTA stages WB_PROF_BATCH samples (logits + per-object weights) in
 // shared memory, then thread <-> (object, class) accumulates them in sample order; CTA partials are reduced
 // in CTA order by k_profile_final.  grid = (prof_ctas, B).
-#define WB_PROF_BATCH 128
+#define WB_PROF_BATCH 256
 __global__ void __launch_bounds__(256) k_class_profile(WbDec d) {
   const waldo_geom_t g = d.g;
   const int No = g.No, Nl = g.Nl, HW = g.H * g.W, L = No + 1;

@@ -214,6 +214,16 @@ def _staged(fn, arg, stream, what, dev):
     arg.stages = 0
 
 
+def _fwd_struct(g, prof_ctas, t):
+    (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part, prof_sum, prof_p,
+     f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score) = t
+    return L.DecodeFwd(g, L.ptr(inp_c, name="input"), L.ptr(tgo_c), L.ptr(sgo_c), L.ptr(tgb_c), L.ptr(sgb_c), L.ptr(occ_c),
+                       L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
+                       L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
+                       L.ptr(prof_p), L.ptr(f_lo), L.ptr(s_lo), L.ptr(live_ctx, torch.int32), L.ptr(live_pred, torch.int32),
+                       L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full), L.ptr(norm), L.ptr(score), 0)
+
+
 class _Decode(torch.autograd.Function):
     """LVD.forward(mode="decode_output") = Warper.grid_to_flow[_ctx] + Warper.input_to_output, lvd.py:141-153.
 
@@ -245,7 +255,7 @@ class _Decode(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         a_lo = torch.empty(B, g.Tw, Lr, spec.H, spec.W, **f32)
         nout = spec.num_obj * Nl + spec.num_obj
-        prof_ctas = max(1, min(64, (g.Tw * spec.H * spec.W + 127) // 128))
+        prof_ctas = max(1, min(74, (g.Tw * spec.H * spec.W + 255) // 256))
         prof_part = torch.empty(B, prof_ctas, nout, **f32)
         prof_sum = torch.empty(B, nout, **f32)
         prof_p = torch.empty(B, spec.num_obj, Nl, **f32)
@@ -259,23 +269,25 @@ class _Decode(torch.autograd.Function):
         out_full = torch.empty(B, Tp, Cc + 1, Hd, Wd, **f32)
         norm = torch.empty(B, Tp, Hd, Wd, **f32)
         score = torch.empty(B, Tc, Tp, Hd, Wd, **f32)
-        a = L.DecodeFwd(g, L.ptr(inp_c, name="input"), L.ptr(tgo_c), L.ptr(sgo_c), L.ptr(tgb_c), L.ptr(sgb_c), L.ptr(occ_c),
-                        L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
-                        L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
-                        L.ptr(prof_p), L.ptr(f_lo), L.ptr(s_lo), L.ptr(live_ctx, torch.int32), L.ptr(live_pred, torch.int32), L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full),
-                        L.ptr(norm), L.ptr(score), 0)
+        tensors = (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
+                   prof_sum, prof_p, f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score)
+        a = _fwd_struct(g, prof_ctas, tensors)
         _staged(lib.waldo_decode_fwd, a, L.stream_of(inp_c), "decode_fwd", dev=dev)
-        ctx.spec, ctx.has_cls = spec, cls is not None
-        ctx.keep = (a, inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
-                    prof_sum, prof_p, f_lo, s_lo, alpha, flow, raw, out_full, norm, live_ctx, live_pred, score)
+        # saved through save_for_backward (NOT as ctx attributes): four of them are outputs of this very Function, and an
+        # attribute would tie them into a reference cycle that only the cyclic GC frees (tens of GB per step)
+        ctx.save_for_backward(*[t for t in tensors if t is not None])
+        ctx.present = [t is not None for t in tensors]
+        ctx.geom, ctx.prof_ctas = g, prof_ctas
         ctx.shapes = dict(obj_alpha=obj_alpha.shape, bg_alpha=bg_alpha.shape)
         return out_full, raw, flow, alpha
 
     @staticmethod
     def backward(ctx, d_out_full, d_raw, d_flow, d_alpha):
         lib = L.load()
-        fwd = ctx.keep[0]
-        (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c) = ctx.keep[1:10]
+        it = iter(ctx.saved_tensors)
+        tensors = tuple(next(it) if p else None for p in ctx.present)
+        fwd = _fwd_struct(ctx.geom, ctx.prof_ctas, tensors)
+        (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c) = tensors[:9]
         g = fwd.g
         dev = inp_c.device
         need = ctx.needs_input_grad[5:]   # inp, tgo, sgo, tgb, sgb, occ, obj_alpha, bg_alpha, cls
@@ -287,7 +299,8 @@ class _Decode(torch.autograd.Function):
         filt = bool(g.flags & L.F_FILTER)
         geom = n_tgo or n_sgo or n_tgb or n_sgb
         chain = geom or n_occ or n_oa or n_ba or n_cls or (filt and n_inp)
-        a_lo, prof_part, prof_sum, prof_p, f_lo, s_lo, alpha = ctx.keep[14:21]
+        a_lo, prof_part, prof_sum, prof_p, f_lo, s_lo = tensors[13:19]
+        alpha = tensors[21]
         Lr = g.No + 1
         f32 = dict(device=dev, dtype=torch.float32)
         d_alpha_acc = torch.zeros_like(alpha) if chain else None
