@@ -1,0 +1,23 @@
+#!/bin/bash
+# One GPU session: parity tests, bench line, ncu launch list, ncu --set full of the HD kernels.
+# usage (under gpurun): bash profiles/gpu_session.sh <tag> [tests] [bench] [launches] [full]
+TAG=${1:-x}; shift
+OUT=gpurun_out
+mkdir -p $OUT
+for what in "$@"; do
+case $what in
+tests)
+  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/${TAG}_tests.log;;
+bench)
+  timeout 600 python bench.py > $OUT/${TAG}_bench.jsonl 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; cat $OUT/${TAG}_bench.jsonl; tail -3 $OUT/${TAG}_bench.err;;
+benchq)
+  timeout 600 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench.jsonl 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; cat $OUT/${TAG}_bench.jsonl; tail -3 $OUT/${TAG}_bench.err;;
+launches)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/${TAG}_launches.csv \
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_launches.log 2>&1; echo "launches rc=$?";;
+full)
+  timeout 1500 ncu --set full --clock-control none --import-source on \
+     -k 'regex:k_gather_bwd|k_layers_bwd|k_alpha_prep_bwd|k_gather_fwd|k_layers_fwd|k_alpha_prep|k_class_profile' -c 9 \
+     -o $OUT/${TAG}_full -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_full.log 2>&1; echo "full rc=$?"; tail -2 $OUT/${TAG}_full.log;;
+esac
+done
