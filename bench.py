@@ -225,9 +225,17 @@ def main():
     om, bg = om.to(dev), bg.to(dev)
     host = make_inputs(cfg, B, T, Tc, seed=rank)
     keys = ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")
-    pinned = {k: host[k].pin_memory() for k in keys}
+    small = ("obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")
+    # what the dataset really holds (data/base_dataset.py:173-183, :355-372): 8-bit RGB and an 8-bit label map; the
+    # fp32 `input` (normalised RGB | +-5 one-hot logits) is expanded from them on the device by waldo_pack_input
+    rgb8 = ((host["input"][:, :, :3] + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)
+    lab8 = host["input"][:, :, 3:].argmax(dim=2).to(torch.uint8)
+    pinned = {k: host[k].pin_memory() for k in small}
+    pinned["rgb"], pinned["label"] = rgb8.pin_memory(), lab8.pin_memory()
     ctx_ts, pred_ts = host["ctx_ts"].contiguous().to(dev), host["pred_ts"].to(dev)
-    resident = {k: pinned[k].to(dev) for k in keys}
+    resident = {k: pinned[k].to(dev) for k in small}
+    resident["input"] = wb.pack_input(pinned["rgb"].to(dev), pinned["label"].to(dev), cfg.num_lyt)
+    del host
     grad_buf = torch.zeros(WIF_GRAD_ELEMS, device=dev) if (world > 1 and backward) else None
     loss_host = torch.zeros(1).pin_memory()
 
@@ -252,9 +260,16 @@ def main():
                 dist.all_reduce(grad_buf)
         return out[0].detach()[:, :, :3].mean()   # the step's metric (mean predicted RGB), read back in the e2e leg
 
+    def endless(batch):
+        while True:
+            yield batch
+
+    feeder = {}
+
     def e2e_step():
-        src = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
-        metric = step(src)
+        # the public feeding API: the next batch is copied from pinned host memory on a side stream while this one is
+        # processed; every step's inputs cross PCIe inside the timed region and the step's metric is read back
+        metric = step(next(feeder["it"]))
         loss_host.copy_(metric.reshape(1), non_blocking=True)
 
     def barrier():
@@ -291,11 +306,23 @@ def main():
     # ---- end to end: pinned host -> device copies and the loss read-back inside the timed region
     e2e = None
     if not args.no_e2e:
+        nbytes = lambda d: sum(t.numel() * t.element_size() for t in d.values())
+        # (a) 8-bit frames + labels over PCIe, expanded on the device (the shipped input pipeline)
+        feeder["it"] = wb.DevicePrefetcher(endless(pinned), dev, num_lyt=cfg.num_lyt)
         e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
-        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
         e2e = {"value": world * B * Tp / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+               "h2d_bytes_per_step": nbytes(pinned), "d2h_bytes_per_step": 4,
+               "api": "waldo_b200.DevicePrefetcher (8-bit RGB + label map, pack_input on device, copy overlapped with the previous step)"}
+        # (b) for comparison: the fp32 `input` tensor itself shipped every step (what the reference's to_cuda moves)
+        feeder["it"] = None
+        pinned32 = {k: pinned[k] for k in small}
+        pinned32["input"] = resident["input"].cpu().pin_memory()
+        feeder["it"] = wb.DevicePrefetcher(endless(pinned32), dev)
+        e2e_step()
+        ms32 = timed(e2e_step, args.steps)
+        e2e["fp32_input"] = {"value": world * B * Tp / (ms32 * 1e-3), "ms_per_step": ms32, "h2d_bytes_per_step": nbytes(pinned32)}
+        feeder["it"] = None
 
     clocks.close()
     if rank == 0:

@@ -48,7 +48,9 @@ enum {
   WALDO_F_HAS_CLS      = 1 << 3, /* cls != None                                                      */
   WALDO_F_IS_OBJ       = 1 << 4, /* lvd.py:788-791 (RESTRICT_CTX and not allow_ghost)                */
   WALDO_F_INCLUDE_SELF = 1 << 5, /* lvd.py:842-845 extra context = the target frame itself           */
-  WALDO_F_USE_DISOCC   = 1 << 6  /* lvd.py:148-151 disocc appended to raw_output                     */
+  WALDO_F_USE_DISOCC   = 1 << 6, /* lvd.py:148-151 disocc appended to raw_output                     */
+  WALDO_F_OCC_PAIRS    = 1 << 7  /* backward only: d_occ feeds waldo_occ_bwd and nothing else, so its row 0, column 0
+                                    and diagonal (constants of lvd.py:63-66, never read there) are left at zero      */
 };
 
 typedef void* waldo_stream_t; /* cudaStream_t */
@@ -106,6 +108,7 @@ typedef struct {
   uint8_t* level;             /* (n, Hp*Wp) 0 = hit, k = filled at dilation k, 255 = unknown; Hp = Ht+2(niter+1) */
   uint8_t* eroded;            /* (n, Hp*Wp) 0 = kept, k = removed at erosion k */
   float* val;                 /* scratch+saved (n, 2, Hp*Wp) inverse displacement in pixels */
+  int32_t* bbox;              /* saved (n, 4) x0,y0,x1,y1 of the hit cells in padded coordinates (INT32_MAX,.,-1,. if none) */
 } waldo_invwarp_fwd_t;
 int waldo_invwarp_fwd(const waldo_invwarp_fwd_t*, waldo_stream_t);
 
@@ -117,6 +120,7 @@ typedef struct {
   const int32_t* winner;
   const uint8_t* level;
   const uint8_t* eroded;
+  const int32_t* bbox;
   float* gval;                /* scratch (n, 2, Hp*Wp) */
   float* inv_sw;              /* scratch (n, Hp*Wp) */
   float* gdisp;               /* scratch (n, Ht*Wt, 2) gradient of the resampled displacement */
@@ -162,6 +166,7 @@ typedef struct {
   int prof_ctas;
   float* prof_sum;            /* (B, No*Nl + No) reduced sums (num | den), lvd.py:740-742 */
   float* prof_p;              /* (B, No, Nl) class probabilities used by the filter */
+  float* lyt_lo;              /* (B, Tw, Nl, H, W) down-sampled layout logits (lvd.py:716), saved for backward; NULL = recompute */
   float* f_lo;                /* (B, Tc, Tp, L, H, W, 2) per-layer flow on the low-res lattice, lvd.py:792 */
   float* s_lo;                /* (B, Tp, No, H, W) object support, lvd.py:788 */
   uint32_t* live_ctx;         /* (B, Tw, H, W) bit k: layer k has an in-range tap at this low-res cell of context frame t */
@@ -181,7 +186,8 @@ int waldo_decode_fwd(const waldo_decode_fwd_t*, waldo_stream_t);
 typedef struct {
   waldo_decode_fwd_t f;       /* the forward call's arguments (inputs, saved intermediates, outputs) */
   /* upstream gradients; any may be NULL (= zero) */
-  const float* d_out_full;    /* (B, Tp, C+1, Hd, Wd) */
+  const float* d_output;      /* (B, Tp, C, Hd, Wd)   gradient of out_full[:, :, :C]  (the returned `output`)    */
+  const float* d_raw_alpha;   /* (B, Tp, 1, Hd, Wd)   gradient of out_full[:, :, C:]  (the returned `raw_alpha`) */
   const float* d_raw_output;  /* (B, Tc+self, Tp, C+L+disocc, Hd, Wd) */
   const float* d_flow;        /* (B, Tc, Tp, 2, Hd, Wd) */
   const float* d_alpha;       /* (B, Tw, L, Hd, Wd) */
@@ -231,6 +237,21 @@ typedef struct {
   float* d_unet_out;          /* (B, Tp, Tc, 4+ab, HW) or NULL */
 } waldo_wif_fuse_bwd_t;
 int waldo_wif_fuse_bwd(const waldo_wif_fuse_bwd_t*, waldo_stream_t);
+
+/* ------------------------------------------------------------------ f-3  input packing (caller side of the path)
+ * data/base_dataset.py:173-183 (label map -> one-hot -> 5*(2x-1)), :355-372 (ToTensor, Normalize(0.5,0.5)) and
+ * models/synthesizer.py:444 (input = cat([vid, lyt], dim=2)), done on the device so that only 8-bit planes cross PCIe. */
+typedef struct {
+  int n;                      /* frames B*T */
+  int Nl;                     /* classes */
+  int HW;                     /* Hd*Wd */
+  float on, off;              /* 5, -5 in the reference */
+  const uint8_t* rgb_u8;      /* (n, 3, HW) raw 8-bit RGB, or NULL */
+  const float* rgb_f32;       /* (n, 3, HW) already normalised frames (used when rgb_u8 is NULL) */
+  const uint8_t* label;       /* (n, HW) class ids; ids >= Nl light no channel */
+  float* input;               /* out (n, 3+Nl, HW) */
+} waldo_pack_input_t;
+int waldo_pack_input(const waldo_pack_input_t*, waldo_stream_t);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,10 @@ rows = list(csv.reader(sys.stdin))
 hi = next(i for i, r in enumerate(rows) if r and r[0] in ("Address", "#", "Line") or (len(r) > 1 and r[1] == "Source"))
 print(rows[0][:2])
 H = rows[hi]; idx = {h: i for i, h in enumerate(H)}
-body = [r for r in rows[hi + 1:] if len(r) >= len(H) - 2]
+body = []
+for r in rows[hi + 1:]:
+    if r and r[0] in ("Kernel Name", "Address"): break   # next launch of the same kernel
+    if len(r) >= len(H) - 2: body.append(r)
 def f(r, k):
     try: return float(r[idx[k]])
     except Exception: return 0.0

@@ -346,3 +346,36 @@ def check_full_size(dev, B=1, T=5, Tc=4):
     assert float(flow.abs().max()) == 0.0
     want = to(d["input"])[:, :Tc].unsqueeze(2)
     assert torch.equal(raw[:, :, :, :C], want), "zero flow must copy the context frames bit-exactly"
+
+
+# ------------------------------------------------------------------------------------------------ f-3 input packing
+def reference_pack(rgb, label, num_lyt):
+    """What the reference's dataset + Synthesizer do on the host (data/base_dataset.py:173-183, :355-372;
+    models/synthesizer.py:444), restated with the same torch ops: ToTensor (x/255), Normalize(0.5, 0.5), one-hot via
+    scatter_, 5 * (2x - 1), cat on the channel dim."""
+    if rgb.dtype == torch.uint8:
+        vid = (rgb.to(torch.float32).div(255) - 0.5) / 0.5
+    else:
+        vid = rgb
+    B, T, Hd, Wd = label.shape
+    onehot = torch.zeros(B, T, num_lyt, Hd, Wd).scatter_(2, label.long().unsqueeze(2), 1)
+    return torch.cat([vid, 5 * (onehot * 2 - 1)], dim=2)
+
+
+def check_pack_input(dev, B=2, T=3, Hd=12, Wd=20, num_lyt=20, seed=5):
+    """Bit-exact against the reference's host-side formulas, uint8 and fp32 frames, sizes with and without a
+    multiple-of-4 pixel count."""
+    g = torch.Generator().manual_seed(seed)
+    for (h, w) in ((Hd, Wd), (7, 9)):
+        rgb8 = torch.randint(0, 256, (B, T, 3, h, w), generator=g, dtype=torch.uint8)
+        lab = torch.randint(0, num_lyt, (B, T, h, w), generator=g, dtype=torch.uint8)
+        want = reference_pack(rgb8, lab, num_lyt)
+        got = wb.pack_input(rgb8.to(dev), lab.to(dev), num_lyt).cpu()
+        assert torch.equal(got, want), "pack_input(uint8 rgb) differs from ToTensor/Normalize/one-hot"
+        rgbf = torch.rand(B, T, 3, h, w, generator=g) * 2 - 1
+        got = wb.pack_input(rgbf.to(dev), lab.to(dev), num_lyt).cpu()
+        assert torch.equal(got, reference_pack(rgbf, lab, num_lyt))
+    # every 8-bit value maps exactly as torchvision's ToTensor + Normalize
+    ramp = torch.arange(256, dtype=torch.uint8).view(1, 1, 1, 16, 16).expand(1, 1, 3, 16, 16).contiguous()
+    lab = torch.zeros(1, 1, 16, 16, dtype=torch.uint8)
+    assert torch.equal(wb.pack_input(ramp.to(dev), lab.to(dev), 2).cpu()[:, :, :3], reference_pack(ramp, lab, 2)[:, :, :3])

@@ -48,3 +48,7 @@ def test_wif(case):
 
 def test_kats():
     parity.check_kats(DEV)
+
+
+def test_pack_input():
+    parity.check_pack_input(DEV)

@@ -62,3 +62,30 @@ def test_full_size_properties(dev):
     """BASELINE config shape (Cityscapes 512x1024, 16 objects, 20 classes), B=1, 4 contexts -> 1 future frame:
     size-independent properties of the fused path."""
     parity.check_full_size(dev)
+
+
+def test_pack_input(dev):
+    parity.check_pack_input(dev)
+    parity.check_pack_input(dev, B=1, T=2, Hd=256, Wd=832, num_lyt=19)
+
+
+def test_device_prefetcher(dev):
+    """Batches arrive on the device intact and in order while the previous one is still being consumed; 8-bit RGB +
+    labels are expanded to the fp32 `input` exactly as the host formulas do."""
+    import waldo_b200 as wb
+    g = torch.Generator().manual_seed(3)
+    host = []
+    for i in range(5):
+        rgb = torch.randint(0, 256, (2, 3, 3, 32, 64), generator=g, dtype=torch.uint8).pin_memory()
+        lab = torch.randint(0, 20, (2, 3, 32, 64), generator=g, dtype=torch.uint8).pin_memory()
+        pose = torch.randn(2, 3, 4, generator=g).pin_memory()
+        host.append({"rgb": rgb, "label": lab, "pose": pose})
+    seen = 0
+    sink = torch.zeros(4096, 4096, device=dev)
+    for i, batch in enumerate(wb.DevicePrefetcher(host, dev, num_lyt=20)):
+        sink = sink @ sink * 0 + 1          # keep the consumer stream busy while the next copy runs
+        want = parity.reference_pack(host[i]["rgb"], host[i]["label"], 20)
+        assert torch.equal(batch["input"].cpu(), want), i
+        assert torch.equal(batch["pose"].cpu(), host[i]["pose"]), i
+        seen += 1
+    assert seen == 5

@@ -39,13 +39,13 @@ class InvWarpFwd(C.Structure):
                 ("niter", C.c_int), ("erode", C.c_int),
                 ("fwd_grid", c_void_p), ("id_src", c_void_p), ("id_tgt", c_void_p), ("gauss", c_void_p),
                 ("out", c_void_p), ("field", c_void_p), ("winner", c_void_p), ("level", c_void_p),
-                ("eroded", c_void_p), ("val", c_void_p)]
+                ("eroded", c_void_p), ("val", c_void_p), ("bbox", c_void_p)]
 
 
 class InvWarpBwd(C.Structure):
     _fields_ = [("n", C.c_int), ("Hs", C.c_int), ("Ws", C.c_int), ("Ht", C.c_int), ("Wt", C.c_int), ("niter", C.c_int),
                 ("gauss", c_void_p), ("dout", c_void_p), ("field", c_void_p), ("winner", c_void_p),
-                ("level", c_void_p), ("eroded", c_void_p), ("gval", c_void_p), ("inv_sw", c_void_p),
+                ("level", c_void_p), ("eroded", c_void_p), ("bbox", c_void_p), ("gval", c_void_p), ("inv_sw", c_void_p),
                 ("gdisp", c_void_p), ("dfwd_grid", c_void_p)]
 
 
@@ -63,14 +63,14 @@ class DecodeFwd(C.Structure):
                 ("obj_alpha", c_void_p), ("bg_alpha", c_void_p), ("cls", c_void_p),
                 ("ctx_ts", c_void_p), ("pred_ts", c_void_p), ("xs_hd", c_void_p), ("ys_hd", c_void_p),
                 ("a_lo", c_void_p), ("prof_part", c_void_p), ("prof_ctas", C.c_int), ("prof_sum", c_void_p),
-                ("prof_p", c_void_p), ("f_lo", c_void_p), ("s_lo", c_void_p), ("live_ctx", c_void_p), ("live_pred", c_void_p),
+                ("prof_p", c_void_p), ("lyt_lo", c_void_p), ("f_lo", c_void_p), ("s_lo", c_void_p), ("live_ctx", c_void_p), ("live_pred", c_void_p),
                 ("alpha", c_void_p), ("flow", c_void_p), ("raw_output", c_void_p), ("out_full", c_void_p),
                 ("norm", c_void_p), ("score", c_void_p), ("stages", C.c_int)]
 
 
 class DecodeBwd(C.Structure):
     _fields_ = [("f", DecodeFwd),
-                ("d_out_full", c_void_p), ("d_raw_output", c_void_p), ("d_flow", c_void_p), ("d_alpha", c_void_p),
+                ("d_output", c_void_p), ("d_raw_alpha", c_void_p), ("d_raw_output", c_void_p), ("d_flow", c_void_p), ("d_alpha", c_void_p),
                 ("d_input", c_void_p), ("d_tgt_grid_obj", c_void_p), ("d_src_grid_obj", c_void_p),
                 ("d_tgt_grid_bg", c_void_p), ("d_src_grid_bg", c_void_p), ("d_occ", c_void_p),
                 ("d_obj_alpha", c_void_p), ("d_bg_alpha", c_void_p), ("d_cls", c_void_p),
@@ -89,18 +89,24 @@ class WifFuseBwd(C.Structure):
     _fields_ = [("f", WifFuseFwd), ("d_frame", c_void_p), ("d_raw_output", c_void_p), ("d_unet_out", c_void_p)]
 
 
+class PackInput(C.Structure):
+    _fields_ = [("n", C.c_int), ("Nl", C.c_int), ("HW", C.c_int), ("on", C.c_float), ("off", C.c_float),
+                ("rgb_u8", c_void_p), ("rgb_f32", c_void_p), ("label", c_void_p), ("input", c_void_p)]
+
+
 # flags of Geom.flags (include/waldo_b200.h)
-F_RESTRICT_CTX, F_FILTER, F_WEIGHT_CLS, F_HAS_CLS, F_IS_OBJ, F_INCLUDE_SELF, F_USE_DISOCC = (1 << i for i in range(7))
+F_RESTRICT_CTX, F_FILTER, F_WEIGHT_CLS, F_HAS_CLS, F_IS_OBJ, F_INCLUDE_SELF, F_USE_DISOCC, F_OCC_PAIRS = (1 << i for i in range(8))
 
 MAX_LAYERS, MAX_CH, MAX_LYT, MAX_TPS_K = 17, 24, 21, 256
 
 STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwarp_fwd_t": InvWarpFwd,
              "waldo_invwarp_bwd_t": InvWarpBwd, "waldo_geom_t": Geom, "waldo_decode_fwd_t": DecodeFwd,
-             "waldo_decode_bwd_t": DecodeBwd, "waldo_wif_fuse_fwd_t": WifFuseFwd, "waldo_wif_fuse_bwd_t": WifFuseBwd}
+             "waldo_decode_bwd_t": DecodeBwd, "waldo_wif_fuse_fwd_t": WifFuseFwd, "waldo_wif_fuse_bwd_t": WifFuseBwd,
+             "waldo_pack_input_t": PackInput}
 
 EXPORTS = ["waldo_last_error", "waldo_abi_version", "waldo_has_device_code", "waldo_launch_count", "waldo_tps_fwd", "waldo_tps_bwd",
            "waldo_invwarp_fwd", "waldo_invwarp_bwd", "waldo_occ_fwd", "waldo_occ_bwd", "waldo_decode_fwd",
-           "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd"]
+           "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input"]
 
 _lock = threading.Lock()
 _lib = None
@@ -114,7 +120,7 @@ def _declare(lib):
     lib.waldo_launch_count.restype = C.c_longlong
     for name, st in (("waldo_tps_fwd", TpsFwd), ("waldo_tps_bwd", TpsBwd), ("waldo_invwarp_fwd", InvWarpFwd),
                      ("waldo_invwarp_bwd", InvWarpBwd), ("waldo_decode_fwd", DecodeFwd), ("waldo_decode_bwd", DecodeBwd),
-                     ("waldo_wif_fuse_fwd", WifFuseFwd), ("waldo_wif_fuse_bwd", WifFuseBwd)):
+                     ("waldo_wif_fuse_fwd", WifFuseFwd), ("waldo_wif_fuse_bwd", WifFuseBwd), ("waldo_pack_input", PackInput)):
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(st), c_void_p]
         fn.restype = C.c_int

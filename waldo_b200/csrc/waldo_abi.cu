@@ -8,6 +8,7 @@
 #include "wb_composite.cuh"
 #include "wb_composite_bwd.cuh"
 #include "wb_wif.cuh"
+#include "wb_pack.cuh"
 
 static thread_local char g_err[512] = "";
 long long g_wb_launches = 0;
@@ -82,13 +83,23 @@ int waldo_tps_bwd(const waldo_tps_bwd_t* a, waldo_stream_t st) {
 int waldo_invwarp_fwd(const waldo_invwarp_fwd_t* a, waldo_stream_t st) {
   WB_REQUIRE(a && a->n >= 0 && a->Hs > 0 && a->Ws > 0 && a->Ht > 0 && a->Wt > 0, "invwarp_fwd: bad sizes");
   WB_REQUIRE(a->niter >= 0 && a->niter < 120, "invwarp_fwd: niter out of range");
+  WB_REQUIRE(a->n <= 65535, "invwarp_fwd: more than 65535 items in one call");
   WB_REQUIRE(a->fwd_grid && a->id_src && a->id_tgt && a->gauss && a->out && a->field && a->winner && a->level && a->eroded && a->val,
              "invwarp_fwd: null pointer");
   if (a->n == 0) return 0;
+  WB_REQUIRE(a->bbox, "invwarp_fwd: null bbox scratch");
   WbInvArgs k = {a->n, a->Hs, a->Ws, a->Ht, a->Wt, a->niter, a->erode, a->fwd_grid, a->id_src, a->id_tgt, a->gauss,
-                 a->out, a->field, a->winner, a->level, a->eroded, a->val};
-  WB_LAUNCH(k_invwarp_fwd, dim3(a->n), dim3(1024), 0, st, k);
-  WB_LAUNCHED();
+                 a->out, a->field, a->winner, a->level, a->eroded, a->val, a->bbox};
+  const int m = a->niter + 1, PP = (a->Ht + 2 * m) * (a->Wt + 2 * m), P = a->Ht * a->Wt;
+  const dim3 gpp(wb_blocks(PP, 256, 512), a->n), gp(wb_blocks(P, 256, 512), a->n);
+  const dim3 gband((a->Ht + 2 * m + WB_INV_ROWS - 1) / WB_INV_ROWS, a->n);
+  WB_LAUNCH(k_inv_clear, gpp, dim3(256), 0, st, k); WB_LAUNCHED();
+  WB_LAUNCH(k_inv_claim, gp, dim3(256), 0, st, k); WB_LAUNCHED();
+  WB_LAUNCH(k_inv_deposit, gp, dim3(256), 0, st, k); WB_LAUNCHED();
+  for (int it = 1; it <= a->niter; ++it) { WB_LAUNCH(k_inv_dilate, gband, dim3(256), 0, st, k, it); WB_LAUNCHED(); }
+  if (a->erode)
+    for (int it = 1; it <= a->niter; ++it) { WB_LAUNCH(k_inv_erode, gband, dim3(256), 0, st, k, it); WB_LAUNCHED(); }
+  WB_LAUNCH(k_inv_final, gp, dim3(256), 0, st, k); WB_LAUNCHED();
   return 0;
 }
 
@@ -97,10 +108,16 @@ int waldo_invwarp_bwd(const waldo_invwarp_bwd_t* a, waldo_stream_t st) {
   WB_REQUIRE(a->gauss && a->dout && a->field && a->winner && a->level && a->eroded && a->gval && a->inv_sw && a->gdisp && a->dfwd_grid,
              "invwarp_bwd: null pointer");
   if (a->n == 0) return 0;
+  WB_REQUIRE(a->bbox, "invwarp_bwd: null bbox");
   WbInvBwdArgs k = {a->n, a->Hs, a->Ws, a->Ht, a->Wt, a->niter, a->gauss, a->dout, a->field, a->winner, a->level, a->eroded,
-                    a->gval, a->inv_sw, a->gdisp, a->dfwd_grid};
-  WB_LAUNCH(k_invwarp_bwd, dim3(a->n), dim3(1024), 0, st, k);
-  WB_LAUNCHED();
+                    a->bbox, a->gval, a->inv_sw, a->gdisp, a->dfwd_grid};
+  const int m = a->niter + 1, PP = (a->Ht + 2 * m) * (a->Wt + 2 * m), P = a->Ht * a->Wt;
+  const dim3 gpp(wb_blocks(PP, 256, 512), a->n), gp(wb_blocks(P, 256, 512), a->n), gs(wb_blocks(a->Hs * a->Ws, 256, 512), a->n);
+  const dim3 gband((a->Ht + 2 * m + WB_INV_ROWS - 1) / WB_INV_ROWS, a->n);
+  WB_LAUNCH(k_invb_init, gpp, dim3(256), 0, st, k); WB_LAUNCHED();
+  for (int lv = a->niter - 1; lv >= 0; --lv) { WB_LAUNCH(k_invb_level, gband, dim3(256), 0, st, k, lv); WB_LAUNCHED(); }
+  WB_LAUNCH(k_invb_handoff, gp, dim3(256), 0, st, k); WB_LAUNCHED();
+  WB_LAUNCH(k_invb_resize_t, gs, dim3(256), 0, st, k); WB_LAUNCHED();
   return 0;
 }
 
@@ -190,8 +207,10 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   }
   // stage C: the gather kernel
   if (st_gather) {
-    if (g.Tc <= 4) WB_LAUNCH(k_gather_fwd<4>, grid, dim3(WB_TILE_PX), 0, st, *a);
-    else WB_LAUNCH(k_gather_fwd<8>, grid, dim3(WB_TILE_PX), 0, st, *a);
+    const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+    if (g.Tc == 4 && !self) WB_LAUNCH((k_gather_fwd<4, true>), grid, dim3(WB_TILE_PX), 0, st, *a);
+    else if (g.Tc <= 4) WB_LAUNCH((k_gather_fwd<4, false>), grid, dim3(WB_TILE_PX), 0, st, *a);
+    else WB_LAUNCH((k_gather_fwd<8, false>), grid, dim3(WB_TILE_PX), 0, st, *a);
     WB_LAUNCHED();
   }
   return 0;
@@ -216,6 +235,16 @@ int waldo_wif_fuse_bwd(const waldo_wif_fuse_bwd_t* a, waldo_stream_t st) {
   WB_REQUIRE(a->f.Tc <= WB_WIF_MAX_TC, "wif_fuse_bwd: Tc=%d exceeds compiled maximum %d", a->f.Tc, WB_WIF_MAX_TC);
   WB_REQUIRE(a->f.raw_output && a->f.unet_out && a->d_frame, "wif_fuse_bwd: null pointer");
   WB_LAUNCH(k_wif_fuse_bwd, dim3(wb_blocks(a->f.HW, 256), a->f.B * a->f.Tp), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ input packing
+int waldo_pack_input(const waldo_pack_input_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->Nl >= 1 && a->HW > 0, "pack_input: bad sizes");
+  WB_REQUIRE((a->rgb_u8 || a->rgb_f32) && a->label && a->input, "pack_input: null pointer");
+  if (a->n == 0) return 0;
+  WB_LAUNCH(k_pack_input, dim3(wb_blocks(((long long)a->HW + 3) / 4, 256, 1024), a->n), dim3(256), 0, st, *a);
   WB_LAUNCHED();
   return 0;
 }

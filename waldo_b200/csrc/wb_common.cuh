@@ -39,6 +39,7 @@ static inline int max(int a, int b) { return a > b ? a : b; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }
 static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
@@ -84,6 +85,25 @@ extern long long g_wb_launches;
 #endif
 #ifndef WB_NA_VARIANTS_BWD
 #define WB_NA_VARIANTS_BWD 1
+#endif
+// resident CTAs per SM requested through __launch_bounds__ (register budget = 65536 / (256 * N)); tuned on B200
+#ifndef WB_OCC_LAYERS_FWD
+#define WB_OCC_LAYERS_FWD 3
+#endif
+#ifndef WB_OCC_PREP_FWD
+#define WB_OCC_PREP_FWD 3
+#endif
+#ifndef WB_OCC_GATHER_FWD
+#define WB_OCC_GATHER_FWD 4
+#endif
+#ifndef WB_OCC_LAYERS_BWD
+#define WB_OCC_LAYERS_BWD 3
+#endif
+#ifndef WB_OCC_PREP_BWD
+#define WB_OCC_PREP_BWD 2
+#endif
+#ifndef WB_OCC_GATHER_BWD
+#define WB_OCC_GATHER_BWD 3
 #endif
 #define WB_MAX_C 24
 #define WB_MAX_NL 21

@@ -110,12 +110,11 @@ struct WbFwdCtx {   // per-CTA constants of the fused forward
 // Layer part of one (pixel, context): evaluates the live layers, writes the alpha channels of raw_output (+ disocc),
 // the reduced flow, and returns (flow, score) for the channel part.
 template <int NA>
-WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, unsigned wm, unsigned q, int c_t, size_t pair,
+WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, unsigned wm, const WbIdx<NA>& ix, unsigned q, int c_t, size_t pair,
                           float* __restrict__ raw, float& flow_x, float& flow_y, float& score) {
   const waldo_geom_t& g = d.g;
   const int L = c.L, C = c.C;
   const unsigned HWd = c.HWd;
-  const WbIdx<NA> ix = wb_idx<NA>(wm);
   const float* f_lo = d.f_lo + pair * L * c.HW * 2;
   const float* alpha_c = d.alpha + ((size_t)c.b * g.Tw + c_t) * L * HWd;
   WbLay<NA> ly;
@@ -130,6 +129,23 @@ WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, un
   flow_x = ly.flow_x; flow_y = ly.flow_y; score = ly.score;
 }
 
+// all contexts of one pixel: the slot list is built once
+template <int NA>
+WB_DEV void wb_fwd_layers_ctxs(const WbDec& d, const WbFwdCtx& c, const WbPix& px, unsigned wm, unsigned q) {
+  const waldo_geom_t& g = d.g;
+  const int b = c.b, tp = c.tp;
+  const unsigned HWd = c.HWd;
+  const WbIdx<NA> ix = wb_idx<NA>(wm);
+  for (int tc = 0; tc < g.Tc; ++tc) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+    float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
+    float flow_x, flow_y, score;
+    wb_fwd_layers<NA>(d, c, px, wm, ix, q, c_t, pair, raw, flow_x, flow_y, score);
+    d.score[pair * HWd + q] = score;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // The forward runs as two kernels per (b, tp) so that each gets the register budget it needs:
 //   k_layers_fwd : the irregular layer part (B5up..B9) -> alpha channels of raw_output, flow, score
@@ -139,7 +155,7 @@ WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, un
 // ------------------------------------------------------------------------------------------------------------------
 
 // grid = (CTAs, B*Tp), 32x8 pixel tiles, one thread per HD pixel, rolled loop over the contexts.
-__global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_fwd(WbDec d) {
+__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_FWD) k_layers_fwd(WbDec d) {
   const waldo_geom_t g = d.g;
   WbFwdCtx c;
   c.L = g.No + 1; c.HW = g.H * g.W; c.C = g.C; c.HWd = (unsigned)(g.Hd * g.Wd);
@@ -165,16 +181,9 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_fwd(WbDec d) {
       WbPix px = wb_pix(d, b, tp, X, Y);
       const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
-      for (int tc = 0; tc < g.Tc; ++tc) {
-        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-        float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
-        float flow_x, flow_y, score;
-        if (WB_NA_VARIANTS_FWD >= 2 && n <= 4) wb_fwd_layers<4>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
-        else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_fwd_layers<8>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
-        else wb_fwd_layers<WB_MAX_L>(d, c, px, wm, q, c_t, pair, raw, flow_x, flow_y, score);
-        d.score[pair * HWd + q] = score;
-      }
+      if (WB_NA_VARIANTS_FWD >= 2 && n <= 4) wb_fwd_layers_ctxs<4>(d, c, px, wm, q);
+      else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_fwd_layers_ctxs<8>(d, c, px, wm, q);
+      else wb_fwd_layers_ctxs<WB_MAX_L>(d, c, px, wm, q);
       if (c.self) {   // lvd.py:842-845: the target frame itself is fully opaque
         float* raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q;
         for (int k = 0; k < c.L; ++k) raw[(size_t)(c.C + k) * HWd] = 1.f;
@@ -187,13 +196,14 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_fwd(WbDec d) {
 // grid = (CTAs, B*Tp), 32x8 pixel tiles, one thread per HD pixel.  The taps of the TCAP (>= Tc) contexts live in
 // registers; ONE rolled loop walks the C image channels with the contexts unrolled inside: every channel of every
 // context frame is gathered, stored to raw_output and fused into `output` (lvd.py:850-851) on the fly.
-template <int TCAP>
-__global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_fwd(WbDec d) {
+// FAST = exactly TCAP contexts and no include_self context, resolved at compile time (no predicates in the channel loop).
+template <int TCAP, bool FAST>
+__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_FWD) k_gather_fwd(WbDec d) {
   const waldo_geom_t g = d.g;
   const int C = g.C, L = g.No + 1;
   const unsigned HWd = (unsigned)(g.Hd * g.Wd);
   const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
-  const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  const bool self = !FAST && (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
   const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
   __shared__ const float* s_src[TCAP];   // context frame of every context (CTA-uniform)
   __shared__ float* s_raw[TCAP];         // raw_output block of every context
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_fwd(WbDec d) {
       WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
         o0[tc] = 0u; o1[tc] = 0u; wgt[tc] = 0.f;
         WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = 0.f;
-        if (tc < g.Tc) {
+        if (FAST || tc < g.Tc) {
           const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
           const float* fl = d.flow + pair * 2 * HWd + q;
           const float score = __ldg(d.score + pair * HWd + q);
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_fwd(WbDec d) {
         // all 4 x TCAP loads of this channel first (read-only path), then the arithmetic and the stores
         float v[TCAP][4];
         WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
-          if (tc < g.Tc) {
+          if (FAST || tc < g.Tc) {
             const float* pl = s_src[tc] + choff;
             const float* p0 = pl + o0[tc];
             const float* p1 = pl + o1[tc];
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_fwd(WbDec d) {
         }
         float acc = 0.f;
         WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
-          if (tc < g.Tc) {
+          if (FAST || tc < g.Tc) {
             const float r = __fmaf_rn(v[tc][3], w[tc][3], __fmaf_rn(v[tc][2], w[tc][2], __fmaf_rn(v[tc][1], w[tc][1], __fmul_rn(v[tc][0], w[tc][0]))));
             s_raw[tc][choff + q] = r;
             acc += wgt[tc] * r;

@@ -110,8 +110,11 @@ WB_DEV void wb_colred_flush(const WbColRed& cr, const float* s_stage, int nv, fl
 
 // exclusive-product backward of  A_i = R_i * prod_j (1 - R_j occ[j,i])  over the slots of `ix`.
 // gR (+=) gets d/dR; when s_acc != nullptr, d/d occ[j,i] summed over the warp is added to s_acc[j*L+i] by lane 0.
+// pairs_only: d occ is consumed by waldo_occ_bwd alone, which never reads row 0, column 0 or the diagonal (those
+// entries of occ are constants, lvd.py:63-66) -- skip their warp reductions.
 template <int NA>
-WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, int L, const WbIdx<NA>& ix, float* gR, float* s_acc) {
+WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, int L, const WbIdx<NA>& ix, float* gR, float* s_acc,
+                           bool pairs_only) {
   const int lane = wb_lane();
   WB_UNROLL_NA for (int i = 0; i < WB_NEND; ++i) {
     if (i < ix.n) {
@@ -127,7 +130,7 @@ WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, 
           const float excl = pre[j] * suf;
           suf *= 1.f - R[j] * oc;
           gR[j] -= gV * oc * excl;
-          if (s_acc) {
+          if (s_acc && !(pairs_only && (ix.k[i] == 0 || ix.k[j] == 0 || ix.k[i] == ix.k[j]))) {
             float v = wb_warp_sum(-gV * R[j] * excl);
             if (lane == 0) s_acc[ix.k[j] * L + ix.k[i]] += v;
           }
@@ -141,7 +144,7 @@ WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, 
 struct WbBwdCtx {   // per-CTA constants of the fused backward
   int b, tp, L, C, TcR, CR, HW;
   unsigned HWd;
-  bool self, disocc_ch, need_layers, lowres_direct;
+  bool self, disocc_ch, need_layers, lowres_direct, pairs_only;
   const float* s_occ;
   float* s_acc;      // this warp's d occ accumulators (or null)
   float* s_stage;    // this warp's staging area: WB_STAGE_SLOTS * 2 * WB_WARP floats
@@ -161,13 +164,12 @@ WB_DEV void wb_bwd_layers_fwd(const WbDec& d, const WbBwdCtx& c, const WbPix& px
 // backward of the layer part: B9, B8, B7, B6, B5(up) of one (pixel, context).  gs = d/d score, (dfx, dfy) = d/d flow,
 // draw = this pixel's upstream d raw_output (null = zero).
 template <int NA>
-WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& px, const WbColRed& cr, unsigned wm, int tc, int c_t,
+WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& px, const WbColRed& cr, const WbIdx<NA>& ix, int tc, int c_t,
                               size_t pair, const float* __restrict__ draw, float actf, float gs, float dfx, float dfy) {
   const WbDec& d = a.f;
   const waldo_geom_t& g = d.g;
   const int L = c.L, C = c.C, HW = c.HW;
   const unsigned HWd = c.HWd;
-  const WbIdx<NA> ix = wb_idx<NA>(wm);
   const float* alpha_c = d.alpha + ((size_t)c.b * g.Tw + c_t) * L * HWd;
   WbLay<NA> ly;
   wb_layers_fwd<NA>(d, px, ix, d.f_lo + pair * L * HW * 2, alpha_c, c.s_occ, ly);
@@ -179,7 +181,7 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
       gFx[s] = ly.A[s] * dfx; gFy[s] = ly.A[s] * dfy;
     }
   }
-  wb_occlude_bwd<NA>(ly.R, gA, c.s_occ, L, ix, gR, c.s_acc);
+  wb_occlude_bwd<NA>(ly.R, gA, c.s_occ, L, ix, gR, c.s_acc, c.pairs_only);
   // ---- B7 backward: disocc = max_k R_k (first maximal layer takes the gradient)
   if (c.disocc_ch && draw) {
     const float gd = actf * __ldg(draw + (size_t)(C + L) * HWd);
@@ -254,6 +256,24 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
   }
 }
 
+// all contexts of one pixel: the slot list is built once
+template <int NA>
+WB_DEV void wb_bwd_layers_ctxs(const WbDecB& a, const WbBwdCtx& c, const WbPix& px, const WbColRed& cr, unsigned wm, unsigned q, float actf) {
+  const WbDec& d = a.f;
+  const waldo_geom_t& g = d.g;
+  const int b = c.b, tp = c.tp;
+  const unsigned HWd = c.HWd;
+  const WbIdx<NA> ix = wb_idx<NA>(wm);
+  for (int tc = 0; tc < g.Tc; ++tc) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+    const float* gl = a.glue + pair * 3 * HWd + q;
+    const float gs = actf * __ldg(gl), dfx = actf * __ldg(gl + HWd), dfy = actf * __ldg(gl + 2 * HWd);
+    const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
+    wb_bwd_layers_bwd<NA>(a, c, px, cr, ix, tc, c_t, pair, draw, actf, gs, dfx, dfy);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // The backward of the two HD kernels, in reverse order:
 //   k_gather_bwd : stage C backward.  Scatters d input and reduces, per (pixel, context), the upstream gradients
@@ -265,14 +285,16 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
 // occupancy); per group ONE rolled loop over the image channels with the TG contexts unrolled inside.  Since the
 // gathered value is bilinear in the four taps, d score and d flow follow from the tap moments
 //   U_j = sum_ch dOut_ch * v_j,   T_j = sum_ch dRaw_ch * v_j     (j = the four tap positions).
-template <int TG>
-__global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
+// FAST = the common full case, resolved at compile time (no predicates, no divergence bookkeeping in the channel loop):
+// Tc a multiple of TG, every upstream gradient and d_input present, no include_self context.
+template <int TG, bool FAST>
+__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
   const int C = g.C, L = g.No + 1;
   const unsigned HWd = (unsigned)(g.Hd * g.Wd);
   const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
-  const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  const bool self = !FAST && (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
   const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
   __shared__ const float* s_src[8];    // context frame of every context (CTA-uniform)
   __shared__ float* s_dsrc[8];         // its gradient
@@ -284,7 +306,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
     s_draw[tc] = a.d_raw_output ? a.d_raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * CR * HWd : nullptr;
   }
   __syncthreads();
-  const bool has_din = a.d_input != nullptr, has_draw = a.d_raw_output != nullptr;
+  const bool has_din = FAST || a.d_input != nullptr, has_draw = FAST || a.d_raw_output != nullptr;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
@@ -296,7 +318,8 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
       const unsigned q = (unsigned)(Y * g.Wd + X);
       const float gx = __ldg(d.xs_hd + X), gy = __ldg(d.ys_hd + Y);
       const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
-      const float* dof = a.d_out_full ? a.d_out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q : nullptr;
+      const float* dof = a.d_output ? a.d_output + ((size_t)b * g.Tp + tp) * C * HWd + q : nullptr;
+      const float* dra = a.d_raw_alpha ? a.d_raw_alpha + ((size_t)b * g.Tp + tp) * HWd + q : nullptr;
       const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
       float S = 0.f;   // sum_ch dOut * out, complete after the first group
       for (int tc0 = 0; tc0 < g.Tc; tc0 += TG) {
@@ -305,7 +328,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
         WB_UNROLL for (int i = 0; i < TG; ++i) {
           o0[i] = 0u; o1[i] = 0u; nrm[i] = 0.f;
           WB_UNROLL for (int j = 0; j < 4; ++j) { w[i][j] = 0.f; U[i][j] = 0.f; Tq[i][j] = 0.f; }
-          if (tc0 + i < g.Tc) {
+          if (FAST || tc0 + i < g.Tc) {
             const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
             const float* fl = d.flow + pair * 2 * HWd + q;
             const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
@@ -325,9 +348,9 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
         for (int ch = 0; ch < C; ++ch) {
           // all loads of this channel first (read-only path), then the arithmetic and the reductions
           float v[TG][4], gd[TG];
-          const float gO = dof ? actf * __ldg(dof + choff) : 0.f;
+          const float gO = (FAST || dof) ? actf * __ldg(dof + choff) : 0.f;
           WB_UNROLL for (int i = 0; i < TG; ++i) {
-            if (tc0 + i < g.Tc) {
+            if (FAST || tc0 + i < g.Tc) {
               const float* pl = s_src[tc0 + i] + choff;
               const float* p0 = pl + o0[i];
               const float* p1 = pl + o1[i];
@@ -335,9 +358,9 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
               gd[i] = has_draw ? __ldg(s_draw[tc0 + i] + choff + q) : 0.f;
             }
           }
-          if (first && dof) S += gO * __ldg(of + choff);
+          if (first && (FAST || dof)) S += gO * __ldg(of + choff);
           WB_UNROLL for (int i = 0; i < TG; ++i) {
-            if (tc0 + i < g.Tc) {
+            if (FAST || tc0 + i < g.Tc) {
               const float gdt = actf * gd[i];
               const float go = gdt + nrm[i] * gO;
               WB_UNROLL for (int j = 0; j < 4; ++j) { U[i][j] += gO * v[i][j]; Tq[i][j] += gdt * v[i][j]; }
@@ -355,10 +378,10 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
           choff += HWd;
         }
         if (!a.glue || !active) continue;   // (threads beyond the edge must not overwrite the pixel they mirror)
-        const float gOs = dof ? __ldg(dof + choff) : 0.f;   // d / d (fused score channel), index C
-        if (first && dof) S += gOs * __ldg(of + choff);
+        const float gOs = dra ? __ldg(dra) : 0.f;   // d / d (fused score channel), index C of out_full
+        if (first && dra) S += gOs * __ldg(of + choff);
         WB_UNROLL for (int i = 0; i < TG; ++i) {
-          if (tc0 + i < g.Tc) {
+          if (FAST || tc0 + i < g.Tc) {
             const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
             const float* fl = d.flow + pair * 2 * HWd + q;
             const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
@@ -387,7 +410,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 3) k_gather_bwd(WbDecB a) {
 }
 
 // grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration), rolled loop over the contexts.
-__global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_bwd(WbDecB a) {
+__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_BWD) k_layers_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
   WbBwdCtx c;
@@ -400,6 +423,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_bwd(WbDecB a) {
   c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0);
   c.need_layers = true;
   c.lowres_direct = (g.Hd == g.H);
+  c.pairs_only = (g.flags & WALDO_F_OCC_PAIRS) != 0;
   const int L = c.L, b = c.b, tp = c.tp;
   const unsigned HWd = c.HWd;
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
@@ -425,16 +449,9 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_layers_bwd(WbDecB a) {
       WbColRed cr;
       if (a.d_f_lo && !c.lowres_direct)
         cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(px.ax.i0, 0), wb_shfl(px.ax.i1, WB_WARP - 1), px.ay);
-      for (int tc = 0; tc < g.Tc; ++tc) {
-        const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-        const float* gl = a.glue + pair * 3 * HWd + q;
-        const float gs = actf * __ldg(gl), dfx = actf * __ldg(gl + HWd), dfy = actf * __ldg(gl + 2 * HWd);
-        const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
-        if (WB_NA_VARIANTS_BWD >= 2 && n <= 4) wb_bwd_layers_bwd<4>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
-        else if (WB_NA_VARIANTS_BWD >= 3 && n <= 8) wb_bwd_layers_bwd<8>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
-        else wb_bwd_layers_bwd<WB_MAX_L>(a, c, px, cr, wm, tc, c_t, pair, draw, actf, gs, dfx, dfy);
-      }
+      if (WB_NA_VARIANTS_BWD >= 2 && n <= 4) wb_bwd_layers_ctxs<4>(a, c, px, cr, wm, q, actf);
+      else if (WB_NA_VARIANTS_BWD >= 3 && n <= 8) wb_bwd_layers_ctxs<8>(a, c, px, cr, wm, q, actf);
+      else wb_bwd_layers_ctxs<WB_MAX_L>(a, c, px, cr, wm, q, actf);
     }
   }
   if (a.d_occ) {
@@ -465,7 +482,7 @@ __global__ void k_occ_reduce(const float* __restrict__ part, int groups, int per
 struct WbPrepBwdCtx {
   int b, t, L, Nl, HW;
   unsigned HWd;
-  bool filt, lowres_direct, need_p;
+  bool filt, lowres_direct, need_p, pairs_only;
   const float *s_P, *s_occ, *lyt_base, *alo;
   float *s_acc, *s_accp;
   float* s_stage;    // this warp's staging area, WB_STAGE_SLOTS * WB_WARP floats
@@ -531,7 +548,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
       gA[s] = v * actf;
     }
   }
-  wb_occlude_bwd<NA>(av, gA, c.s_occ, L, ix, ga, c.s_acc);
+  wb_occlude_bwd<NA>(av, gA, c.s_occ, L, ix, ga, c.s_acc, c.pairs_only);
   // ---- filter backward: l_k = 1 - 0.5 sum_c |P_kc - sm_c|.  One ROLLED loop over the object slots (a single copy of
   // the class loop in the code); d P_kc = sum over pixels of -0.5 sign(P_kc - sm_c) d l_k is reduced over the warp with
   // a transpose butterfly and accumulated by lane c.
@@ -603,7 +620,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
 
 // grid = (red_ctas, B*Tw), block = 256.
 template <int NLC>
-__global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
+__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
   WbPrepBwdCtx c;
@@ -614,6 +631,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep_bwd(WbDecB a) {
   c.filt = (g.flags & WALDO_F_FILTER) != 0;
   c.lowres_direct = (g.Hd == g.H);
   c.need_p = c.filt && a.d_prof_p;
+  c.pairs_only = (g.flags & WALDO_F_OCC_PAIRS) != 0;
   __shared__ float s_P[(WB_MAX_L - 1) * WB_MAX_NL];
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
@@ -732,7 +750,8 @@ __global__ void __launch_bounds__(256) k_class_profile_bwd(WbDecB a) {
     for (int i = wb_tid(); i < ns; i += wb_nthr()) {
       const int s = s0 + i, t = s / HW, p = s - t * HW;
       float lyt[WB_MAX_NL], sm[WB_MAX_NL], glyt[WB_MAX_NL], gsmx[WB_MAX_NL];
-      wb_lyt_lo(d, b, t, p, lyt);
+      if (d.lyt_lo) for (int c = 0; c < Nl; ++c) lyt[c] = __ldg(d.lyt_lo + (((size_t)b * g.Tw + t) * Nl + c) * HW + p);
+      else wb_lyt_lo(d, b, t, p, lyt);
       if (wcls) wb_softmax(lyt, sm, Nl);
       for (int c = 0; c < Nl; ++c) { glyt[c] = 0.f; gsmx[c] = 0.f; }
       for (int k = 0; k < No; ++k) {
@@ -938,7 +957,9 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     WbDecB ag = a;
     if (!need_layers) ag.glue = nullptr;
     const dim3 ggrid(wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX) > 1024 ? 1024 : wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX), g.B * g.Tp);
-    WB_LAUNCH(k_gather_bwd<2>, ggrid, dim3(WB_TILE_PX), 0, st, ag);
+    const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+    if (g.Tc % 2 == 0 && !self && a.d_input && a.d_raw_output && a.d_output) WB_LAUNCH((k_gather_bwd<2, true>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
+    else WB_LAUNCH((k_gather_bwd<2, false>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
     WB_BLAUNCHED();
   }
   // 1b. HD layer backward

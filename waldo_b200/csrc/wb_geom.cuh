@@ -105,121 +105,174 @@ __global__ void k_tps_bwd_final(int n, int N, int chunks, const float* __restric
 struct WbInvArgs {
   int n, Hs, Ws, Ht, Wt, niter, erode;
   const float* fwd; const float* id_src; const float* id_tgt; const float* gauss;
-  float* out; int32_t* field; int32_t* winner; uint8_t* level; uint8_t* eroded; float* val;
+  float* out; int32_t* field; int32_t* winner; uint8_t* level; uint8_t* eroded; float* val; int32_t* bbox;
 };
 
 WB_DEV bool wb_level_known_before(uint8_t lv, int it) { return lv != 255 && (int)lv < it; }
 
-__global__ void __launch_bounds__(1024) k_invwarp_fwd(WbInvArgs a) {
-  const int item = blockIdx.x;
-  const int Ht = a.Ht, Wt = a.Wt, P = Ht * Wt, m = a.niter + 1;
-  const int Hp = Ht + 2 * m, Wp = Wt + 2 * m, PP = Hp * Wp;
-  const float* fwd = a.fwd + (size_t)item * a.Hs * a.Ws * 2;
-  int32_t* field = a.field + (size_t)item * P;
-  int32_t* winner = a.winner + (size_t)item * P;
-  uint8_t* level = a.level + (size_t)item * PP;
-  uint8_t* eroded = a.eroded + (size_t)item * PP;
-  float* vx = a.val + (size_t)item * 2 * PP;
-  float* vy = vx + PP;
-  const float rh = (float)a.Hs / (float)Ht, rw = (float)a.Ws / (float)Wt;   // area_pixel_compute_scale
+// The forward runs as a sequence of flat kernels, one per phase, each one thread per (item, cell): every phase is
+// embarrassingly parallel over cells, and a kernel boundary is the only ordering it needs (the one-CTA-per-item form
+// with __syncthreads() between phases kept 40 background items on 40 SMs).  Cells outside the bounding box of an
+// item's hit cells grown by the iteration count cannot change in the dilation / erosion phases and exit at once.
+struct WbInvItem {
+  const float* fwd; int32_t* field; int32_t* winner; uint8_t* level; uint8_t* eroded; float* vx; float* vy; int32_t* bbox;
+};
+WB_DEV WbInvItem wb_inv_item(const WbInvArgs& a, int item, int P, int PP) {
+  WbInvItem r;
+  r.fwd = a.fwd + (size_t)item * a.Hs * a.Ws * 2;
+  r.field = a.field + (size_t)item * P; r.winner = a.winner + (size_t)item * P;
+  r.level = a.level + (size_t)item * PP; r.eroded = a.eroded + (size_t)item * PP;
+  r.vx = a.val + (size_t)item * 2 * PP; r.vy = r.vx + PP;
+  r.bbox = a.bbox + (size_t)item * 4;
+  return r;
+}
+#define WB_INV_GEOM \
+  const int Ht = a.Ht, Wt = a.Wt, P = Ht * Wt, m = a.niter + 1; \
+  const int Hp = Ht + 2 * m, Wp = Wt + 2 * m, PP = Hp * Wp; (void)P; (void)PP; (void)Hp; (void)Wp
 
-  // phase 0: clear
-  for (int i = wb_tid(); i < PP; i += wb_nthr()) { level[i] = 255; eroded[i] = 0; vx[i] = 0.f; vy[i] = 0.f; }
-  for (int i = wb_tid(); i < P; i += wb_nthr()) winner[i] = INT_MAX;
-  __syncthreads();
-  // phase 1: landing cell of every lattice sample; lowest sample index claims the cell   warp.py:76-88,113-117
-  for (int s = wb_tid(); s < P; s += wb_nthr()) {
+// displacement of lattice sample (X, Y) in pixels: interpolate (fwd - identity) to the target size   warp.py:76-79
+WB_DEV void wb_inv_disp(const WbInvArgs& a, const float* __restrict__ fwd, int X, int Y, float& dx, float& dy) {
+  const float rh = (float)a.Hs / (float)a.Ht, rw = (float)a.Ws / (float)a.Wt;   // area_pixel_compute_scale
+  WbAxis ay = wb_axis(Y, rh, a.Hs), ax = wb_axis(X, rw, a.Ws);
+  float d[2];
+  WB_UNROLL for (int c = 0; c < 2; ++c) {
+    int i00 = (ay.i0 * a.Ws + ax.i0) * 2 + c, i01 = (ay.i0 * a.Ws + ax.i1) * 2 + c;
+    int i10 = (ay.i1 * a.Ws + ax.i0) * 2 + c, i11 = (ay.i1 * a.Ws + ax.i1) * 2 + c;
+    float v00 = __fsub_rn(__ldg(fwd + i00), __ldg(a.id_src + i00));
+    float v01 = __fsub_rn(__ldg(fwd + i01), __ldg(a.id_src + i01));
+    float v10 = __fsub_rn(__ldg(fwd + i10), __ldg(a.id_src + i10));
+    float v11 = __fsub_rn(__ldg(fwd + i11), __ldg(a.id_src + i11));
+    d[c] = wb_lerp2(v00, v01, v10, v11, ax, ay);
+  }
+  dx = __fdiv_rn(__fmul_rn(d[0], (float)a.Wt), 2.f); dy = __fdiv_rn(__fmul_rn(d[1], (float)a.Ht), 2.f);
+}
+
+// phase 0: clear.  grid = (ctas, n)
+__global__ void __launch_bounds__(256) k_inv_clear(WbInvArgs a) {
+  WB_INV_GEOM;
+  const WbInvItem it = wb_inv_item(a, blockIdx.y, P, PP);
+  for (int i = blockIdx.x * wb_nthr() + wb_tid(); i < PP; i += gridDim.x * wb_nthr()) {
+    it.level[i] = 255; it.eroded[i] = 0; it.vx[i] = 0.f; it.vy[i] = 0.f;
+    if (i < P) it.winner[i] = INT_MAX;
+    if (i < 4) it.bbox[i] = (i < 2) ? INT_MAX : -1;   // x0, y0, x1, y1 of the hit cells (padded coordinates)
+  }
+}
+// phase 1: landing cell of every lattice sample; lowest sample index claims the cell   warp.py:76-88,113-117
+__global__ void __launch_bounds__(256) k_inv_claim(WbInvArgs a) {
+  WB_INV_GEOM;
+  const WbInvItem it = wb_inv_item(a, blockIdx.y, P, PP);
+  for (int s = blockIdx.x * wb_nthr() + wb_tid(); s < P; s += gridDim.x * wb_nthr()) {
     int Y = s / Wt, X = s - Y * Wt;
-    WbAxis ay = wb_axis(Y, rh, a.Hs), ax = wb_axis(X, rw, a.Ws);
-    float d[2];
-    WB_UNROLL for (int c = 0; c < 2; ++c) {
-      int i00 = (ay.i0 * a.Ws + ax.i0) * 2 + c, i01 = (ay.i0 * a.Ws + ax.i1) * 2 + c;
-      int i10 = (ay.i1 * a.Ws + ax.i0) * 2 + c, i11 = (ay.i1 * a.Ws + ax.i1) * 2 + c;
-      float v00 = __fsub_rn(__ldg(fwd + i00), __ldg(a.id_src + i00));
-      float v01 = __fsub_rn(__ldg(fwd + i01), __ldg(a.id_src + i01));
-      float v10 = __fsub_rn(__ldg(fwd + i10), __ldg(a.id_src + i10));
-      float v11 = __fsub_rn(__ldg(fwd + i11), __ldg(a.id_src + i11));
-      d[c] = wb_lerp2(v00, v01, v10, v11, ax, ay);
-    }
-    float dx = __fdiv_rn(__fmul_rn(d[0], (float)Wt), 2.f), dy = __fdiv_rn(__fmul_rn(d[1], (float)Ht), 2.f);
+    float dx, dy;
+    wb_inv_disp(a, it.fwd, X, Y, dx, dy);
     float fx = rintf(__fadd_rn((float)X, dx)), fy = rintf(__fadd_rn((float)Y, dy));   // half-to-even
     int cell = -1;
     if (fx >= 0.f && fy >= 0.f && fx <= (float)(Wt - 1) && fy <= (float)(Ht - 1)) {
       cell = (int)fy * Wt + (int)fx;
-      atomicMin(&winner[cell], s);
+      atomicMin(&it.winner[cell], s);
     }
-    field[s] = cell;
-    // park -dx,-dy at the sample's own padded slot?  no: recomputed below from the winner only
+    it.field[s] = cell;
   }
+}
+// phase 2: winners deposit the negated displacement                                       warp.py:121-123
+__global__ void __launch_bounds__(256) k_inv_deposit(WbInvArgs a) {
+  WB_INV_GEOM;
+  const WbInvItem it = wb_inv_item(a, blockIdx.y, P, PP);
+  __shared__ int s_bb[4];   // the CTA's share of the bounding box: one global atomic per CTA and bound, not per sample
+  for (int i = wb_tid(); i < 4; i += wb_nthr()) s_bb[i] = (i < 2) ? INT_MAX : -1;
   __syncthreads();
-  // phase 2: winners deposit the negated displacement                                       warp.py:121-123
-  for (int s = wb_tid(); s < P; s += wb_nthr()) {
-    int cell = field[s];
-    if (cell < 0 || winner[cell] != s) continue;
+  for (int s = blockIdx.x * wb_nthr() + wb_tid(); s < P; s += gridDim.x * wb_nthr()) {
+    int cell = it.field[s];
+    if (cell < 0 || it.winner[cell] != s) continue;
     int Y = s / Wt, X = s - Y * Wt;
-    WbAxis ay = wb_axis(Y, rh, a.Hs), ax = wb_axis(X, rw, a.Ws);
-    float d[2];
-    WB_UNROLL for (int c = 0; c < 2; ++c) {
-      int i00 = (ay.i0 * a.Ws + ax.i0) * 2 + c, i01 = (ay.i0 * a.Ws + ax.i1) * 2 + c;
-      int i10 = (ay.i1 * a.Ws + ax.i0) * 2 + c, i11 = (ay.i1 * a.Ws + ax.i1) * 2 + c;
-      float v00 = __fsub_rn(__ldg(fwd + i00), __ldg(a.id_src + i00));
-      float v01 = __fsub_rn(__ldg(fwd + i01), __ldg(a.id_src + i01));
-      float v10 = __fsub_rn(__ldg(fwd + i10), __ldg(a.id_src + i10));
-      float v11 = __fsub_rn(__ldg(fwd + i11), __ldg(a.id_src + i11));
-      d[c] = wb_lerp2(v00, v01, v10, v11, ax, ay);
-    }
-    float dx = __fdiv_rn(__fmul_rn(d[0], (float)Wt), 2.f), dy = __fdiv_rn(__fmul_rn(d[1], (float)Ht), 2.f);
+    float dx, dy;
+    wb_inv_disp(a, it.fwd, X, Y, dx, dy);
     int cy = cell / Wt, cx = cell - cy * Wt;
     int pc = (cy + m) * Wp + cx + m;
-    vx[pc] = -dx; vy[pc] = -dy; level[pc] = 0;
+    it.vx[pc] = -dx; it.vy[pc] = -dy; it.level[pc] = 0;
+    atomicMin(&s_bb[0], cx + m); atomicMin(&s_bb[1], cy + m);
+    atomicMax(&s_bb[2], cx + m); atomicMax(&s_bb[3], cy + m);
   }
   __syncthreads();
-  // phase 3: grow `niter` rings; a frontier cell takes the normalised Gaussian mean of known cells   warp.py:135-151
+  for (int i = wb_tid(); i < 4; i += wb_nthr()) {
+    if (i < 2) { if (s_bb[i] != INT_MAX) atomicMin(&it.bbox[i], s_bb[i]); }
+    else if (s_bb[i] >= 0) atomicMax(&it.bbox[i], s_bb[i]);
+  }
+}
+// The padded-lattice phases run on grid = (bands of WB_INV_ROWS rows, n): a CTA walks only the cells of its band that lie
+// inside the hit cells' bounding box grown by `grow` (nothing can change outside it); most CTAs of an object exit at once.
+#define WB_INV_ROWS 8
+struct WbInvBand { int x0, y0, w, cells; };
+WB_DEV WbInvBand wb_inv_band(const int32_t* __restrict__ bbox, int grow, int Hp, int Wp) {
+  WbInvBand r;
+  const int ya = blockIdx.x * WB_INV_ROWS, yb = min(Hp, ya + WB_INV_ROWS) - 1;
+  const int bx0 = bbox[0], by0 = bbox[1], bx1 = bbox[2], by1 = bbox[3];
+  r.x0 = 0; r.y0 = 0; r.w = 0; r.cells = 0;
+  if (bx1 < 0) return r;                                  // no hit cell at all
+  const int x0 = max(0, bx0 - grow), x1 = min(Wp - 1, bx1 + grow);
+  const int y0 = max(ya, by0 - grow), y1 = min(yb, by1 + grow);
+  if (x0 > x1 || y0 > y1) return r;
+  r.x0 = x0; r.y0 = y0; r.w = x1 - x0 + 1; r.cells = r.w * (y1 - y0 + 1);
+  return r;
+}
+// true when padded cell (x, y) lies outside the hit cells' bounding box grown by `grow` (nothing can change there)
+WB_DEV bool wb_inv_outside(const int32_t* __restrict__ bbox, int x, int y, int grow) {
+  return x < bbox[0] - grow || x > bbox[2] + grow || y < bbox[1] - grow || y > bbox[3] + grow;
+}
+// phase 3, iteration `iter`: a frontier cell takes the normalised Gaussian mean of the known cells   warp.py:135-151
+__global__ void __launch_bounds__(256) k_inv_dilate(WbInvArgs a, int iter) {
+  WB_INV_GEOM;
+  const WbInvItem it = wb_inv_item(a, blockIdx.y, P, PP);
+  const uint8_t* level = it.level;
   float g[9];
   WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
-  for (int it = 1; it <= a.niter; ++it) {
-    for (int c = wb_tid(); c < PP; c += wb_nthr()) {
-      if (level[c] != 255) continue;
-      int y = c / Wp, x = c - y * Wp;
-      bool front = (y > 0 && wb_level_known_before(level[c - Wp], it)) || (y < Hp - 1 && wb_level_known_before(level[c + Wp], it)) ||
-                   (x > 0 && wb_level_known_before(level[c - 1], it)) || (x < Wp - 1 && wb_level_known_before(level[c + 1], it));
-      if (!front) continue;
-      float sx = 0.f, sy = 0.f, sw = 0.f;
-      WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
-        WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
-          int yy = y + dy, xx = x + dx;
-          if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
-          int q = yy * Wp + xx;
-          if (!wb_level_known_before(level[q], it)) continue;
-          float w = g[(dy + 1) * 3 + dx + 1];
-          sx += w * vx[q]; sy += w * vy[q]; sw += w;
-        }
-      vx[c] = sx / sw; vy[c] = sy / sw; level[c] = (uint8_t)it;
-    }
-    __syncthreads();
-  }
-  // phase 4: erosion of the known set (objects only)                                       warp.py:153-162
-  if (a.erode) {
-    for (int it = 1; it <= a.niter; ++it) {
-      for (int c = wb_tid(); c < PP; c += wb_nthr()) {
-        if (level[c] == 255 || eroded[c] != 0) continue;
-        int y = c / Wp, x = c - y * Wp;
-#define WB_GONE(q) (level[q] == 255 || (eroded[q] != 0 && (int)eroded[q] < it))
-        bool edge = (y > 0 && WB_GONE(c - Wp)) || (y < Hp - 1 && WB_GONE(c + Wp)) ||
-                    (x > 0 && WB_GONE(c - 1)) || (x < Wp - 1 && WB_GONE(c + 1));
-#undef WB_GONE
-        if (edge) eroded[c] = (uint8_t)it;
+  const WbInvBand band = wb_inv_band(it.bbox, iter, Hp, Wp);
+  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) {
+    const int y = band.y0 + i / band.w, x = band.x0 + i % band.w, c = y * Wp + x;
+    if (level[c] != 255) continue;
+    bool front = (y > 0 && wb_level_known_before(level[c - Wp], iter)) || (y < Hp - 1 && wb_level_known_before(level[c + Wp], iter)) ||
+                 (x > 0 && wb_level_known_before(level[c - 1], iter)) || (x < Wp - 1 && wb_level_known_before(level[c + 1], iter));
+    if (!front) continue;
+    float sx = 0.f, sy = 0.f, sw = 0.f;
+    WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
+      WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
+        int yy = y + dy, xx = x + dx;
+        if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
+        int q = yy * Wp + xx;
+        if (!wb_level_known_before(level[q], iter)) continue;
+        float w = g[(dy + 1) * 3 + dx + 1];
+        sx += w * it.vx[q]; sy += w * it.vy[q]; sw += w;
       }
-      __syncthreads();
-    }
+    it.vx[c] = sx / sw; it.vy[c] = sy / sw; it.level[c] = (uint8_t)iter;
   }
-  // phase 5: sentinel for unknown cells, crop, back to normalised coordinates              warp.py:164-174
-  float* out = a.out + (size_t)item * P * 2;
-  for (int s = wb_tid(); s < P; s += wb_nthr()) {
+}
+// phase 4, iteration `iter`: erosion of the known set (objects only)                      warp.py:153-162
+__global__ void __launch_bounds__(256) k_inv_erode(WbInvArgs a, int iter) {
+  WB_INV_GEOM;
+  const WbInvItem it = wb_inv_item(a, blockIdx.y, P, PP);
+  const uint8_t* level = it.level;
+  const uint8_t* eroded = it.eroded;
+  const WbInvBand band = wb_inv_band(it.bbox, a.niter, Hp, Wp);
+  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) {
+    const int y = band.y0 + i / band.w, x = band.x0 + i % band.w, c = y * Wp + x;
+    if (level[c] == 255 || eroded[c] != 0) continue;
+#define WB_GONE(q) (level[q] == 255 || (eroded[q] != 0 && (int)eroded[q] < iter))
+    bool edge = (y > 0 && WB_GONE(c - Wp)) || (y < Hp - 1 && WB_GONE(c + Wp)) ||
+                (x > 0 && WB_GONE(c - 1)) || (x < Wp - 1 && WB_GONE(c + 1));
+#undef WB_GONE
+    if (edge) it.eroded[c] = (uint8_t)iter;
+  }
+}
+// phase 5: sentinel for unknown cells, crop, back to normalised coordinates              warp.py:164-174
+__global__ void __launch_bounds__(256) k_inv_final(WbInvArgs a) {
+  WB_INV_GEOM;
+  const WbInvItem it = wb_inv_item(a, blockIdx.y, P, PP);
+  float* out = a.out + (size_t)blockIdx.y * P * 2;
+  for (int s = blockIdx.x * wb_nthr() + wb_tid(); s < P; s += gridDim.x * wb_nthr()) {
     int Y = s / Wt, X = s - Y * Wt;
     int pc = (Y + m) * Wp + X + m;
-    bool known = level[pc] != 255 && eroded[pc] == 0;
-    float ix = known ? vx[pc] : (float)(2 * Wt), iy = known ? vy[pc] : (float)(2 * Ht);
+    bool known = it.level[pc] != 255 && it.eroded[pc] == 0;
+    float ix = known ? it.vx[pc] : (float)(2 * Wt), iy = known ? it.vy[pc] : (float)(2 * Ht);
     out[2 * s] = __fadd_rn(__ldg(a.id_tgt + 2 * s), __fdiv_rn(__fmul_rn(ix, 2.f), (float)Wt));
     out[2 * s + 1] = __fadd_rn(__ldg(a.id_tgt + 2 * s + 1), __fdiv_rn(__fmul_rn(iy, 2.f), (float)Ht));
   }
@@ -229,85 +282,103 @@ __global__ void __launch_bounds__(1024) k_invwarp_fwd(WbInvArgs a) {
 struct WbInvBwdArgs {
   int n, Hs, Ws, Ht, Wt, niter;
   const float* gauss; const float* dout; const int32_t* field; const int32_t* winner;
-  const uint8_t* level; const uint8_t* eroded;
+  const uint8_t* level; const uint8_t* eroded; const int32_t* bbox;
   float* gval; float* inv_sw; float* gdisp; float* dfwd;
 };
 
-__global__ void __launch_bounds__(1024) k_invwarp_bwd(WbInvBwdArgs a) {
-  const int item = blockIdx.x;
-  const int Ht = a.Ht, Wt = a.Wt, P = Ht * Wt, m = a.niter + 1;
-  const int Hp = Ht + 2 * m, Wp = Wt + 2 * m, PP = Hp * Wp;
-  const uint8_t* level = a.level + (size_t)item * PP;
-  const uint8_t* eroded = a.eroded + (size_t)item * PP;
-  const int32_t* field = a.field + (size_t)item * P;
-  const int32_t* winner = a.winner + (size_t)item * P;
-  float* gx = a.gval + (size_t)item * 2 * PP;
-  float* gy = gx + PP;
-  float* isw = a.inv_sw + (size_t)item * PP;
-  float* gdisp = a.gdisp + (size_t)item * P * 2;
-  const float* dout = a.dout + (size_t)item * P * 2;
+// Same phase-per-kernel structure as the forward; grid = (ctas, n).
+struct WbInvBItem {
+  const uint8_t* level; const uint8_t* eroded; const int32_t* field; const int32_t* winner; const int32_t* bbox;
+  float* gx; float* gy; float* isw; float* gdisp; const float* dout;
+};
+WB_DEV WbInvBItem wb_invb_item(const WbInvBwdArgs& a, int item, int P, int PP) {
+  WbInvBItem r;
+  r.level = a.level + (size_t)item * PP; r.eroded = a.eroded + (size_t)item * PP;
+  r.field = a.field + (size_t)item * P; r.winner = a.winner + (size_t)item * P;
+  r.bbox = a.bbox + (size_t)item * 4;
+  r.gx = a.gval + (size_t)item * 2 * PP; r.gy = r.gx + PP;
+  r.isw = a.inv_sw + (size_t)item * PP;
+  r.gdisp = a.gdisp + (size_t)item * P * 2;
+  r.dout = a.dout + (size_t)item * P * 2;
+  return r;
+}
+// own gradient of every padded cell + 1/sum-of-weights of the filled ones
+__global__ void __launch_bounds__(256) k_invb_init(WbInvBwdArgs a) {
+  WB_INV_GEOM;
+  const WbInvBItem it = wb_invb_item(a, blockIdx.y, P, PP);
   float g[9];
   WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
-  // own gradient of every padded cell + 1/sum-of-weights of the filled ones
-  for (int c = wb_tid(); c < PP; c += wb_nthr()) {
+  for (int c = blockIdx.x * wb_nthr() + wb_tid(); c < PP; c += gridDim.x * wb_nthr()) {
     int y = c / Wp, x = c - y * Wp;
-    float ox = 0.f, oy = 0.f;
-    int Y = y - m, X = x - m;
-    if (Y >= 0 && Y < Ht && X >= 0 && X < Wt && level[c] != 255 && eroded[c] == 0) {
-      ox = dout[2 * (Y * Wt + X)] * 2.f / (float)Wt;
-      oy = dout[2 * (Y * Wt + X) + 1] * 2.f / (float)Ht;
+    float ox = 0.f, oy = 0.f, sw = 0.f;
+    if (!wb_inv_outside(it.bbox, x, y, a.niter)) {
+      int Y = y - m, X = x - m;
+      const int lv = it.level[c];
+      if (Y >= 0 && Y < Ht && X >= 0 && X < Wt && lv != 255 && it.eroded[c] == 0) {
+        ox = it.dout[2 * (Y * Wt + X)] * 2.f / (float)Wt;
+        oy = it.dout[2 * (Y * Wt + X) + 1] * 2.f / (float)Ht;
+      }
+      if (lv != 255 && lv > 0) {
+        WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
+          WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
+            int yy = y + dy, xx = x + dx;
+            if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
+            if (wb_level_known_before(it.level[yy * Wp + xx], lv)) sw += g[(dy + 1) * 3 + dx + 1];
+          }
+      }
     }
-    gx[c] = ox; gy[c] = oy;
-    float sw = 0.f;
-    int lv = level[c];
-    if (lv != 255 && lv > 0) {
-      WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
-        WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
-          int yy = y + dy, xx = x + dx;
-          if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
-          if (wb_level_known_before(level[yy * Wp + xx], lv)) sw += g[(dy + 1) * 3 + dx + 1];
-        }
-    }
-    isw[c] = sw > 0.f ? 1.f / sw : 0.f;
+    it.gx[c] = ox; it.gy[c] = oy;
+    it.isw[c] = sw > 0.f ? 1.f / sw : 0.f;
   }
-  __syncthreads();
-  // levels niter-1 .. 0 gather from the (complete) totals of the later-filled neighbours
-  for (int lv = a.niter - 1; lv >= 0; --lv) {
-    for (int c = wb_tid(); c < PP; c += wb_nthr()) {
-      if ((int)level[c] != lv) continue;
-      int y = c / Wp, x = c - y * Wp;
-      float ax = 0.f, ay = 0.f;
-      WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
-        WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
-          int yy = y + dy, xx = x + dx;
-          if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
-          int q = yy * Wp + xx;
-          int lq = level[q];
-          if (lq == 255 || lq <= lv) continue;
-          // cell q (filled at lq) read cell c through kernel tap (c - q) = (-dy,-dx)
-          float w = g[(1 - dy) * 3 + (1 - dx)] * isw[q];
-          ax += w * gx[q]; ay += w * gy[q];
-        }
-      gx[c] += ax; gy[c] += ay;
-    }
-    __syncthreads();
+}
+// level `lv` gathers from the (complete) totals of the later-filled neighbours; launched for lv = niter-1 .. 0
+__global__ void __launch_bounds__(256) k_invb_level(WbInvBwdArgs a, int lv) {
+  WB_INV_GEOM;
+  const WbInvBItem it = wb_invb_item(a, blockIdx.y, P, PP);
+  float g[9];
+  WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
+  const WbInvBand band = wb_inv_band(it.bbox, lv, Hp, Wp);
+  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) {
+    const int y = band.y0 + i / band.w, x = band.x0 + i % band.w, c = y * Wp + x;
+    if ((int)it.level[c] != lv) continue;
+    float ax = 0.f, ay = 0.f;
+    WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
+      WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
+        int yy = y + dy, xx = x + dx;
+        if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
+        int q = yy * Wp + xx;
+        int lq = it.level[q];
+        if (lq == 255 || lq <= lv) continue;
+        // cell q (filled at lq) read cell c through kernel tap (c - q) = (-dy,-dx)
+        float w = g[(1 - dy) * 3 + (1 - dx)] * it.isw[q];
+        ax += w * it.gx[q]; ay += w * it.gy[q];
+      }
+    it.gx[c] += ax; it.gy[c] += ay;
   }
-  // hit cells hand their total to the winning sample: val = -dx, dx = disp * Wt / 2
-  for (int s = wb_tid(); s < P; s += wb_nthr()) {
-    int cell = field[s];
+}
+// hit cells hand their total to the winning sample: val = -dx, dx = disp * Wt / 2
+__global__ void __launch_bounds__(256) k_invb_handoff(WbInvBwdArgs a) {
+  WB_INV_GEOM;
+  const WbInvBItem it = wb_invb_item(a, blockIdx.y, P, PP);
+  for (int s = blockIdx.x * wb_nthr() + wb_tid(); s < P; s += gridDim.x * wb_nthr()) {
+    int cell = it.field[s];
     float ox = 0.f, oy = 0.f;
-    if (cell >= 0 && winner[cell] == s) {
+    if (cell >= 0 && it.winner[cell] == s) {
       int cy = cell / Wt, cx = cell - cy * Wt;
       int pc = (cy + m) * Wp + cx + m;
-      ox = -gx[pc] * (float)Wt * 0.5f; oy = -gy[pc] * (float)Ht * 0.5f;
+      ox = -it.gx[pc] * (float)Wt * 0.5f; oy = -it.gy[pc] * (float)Ht * 0.5f;
     }
-    gdisp[2 * s] = ox; gdisp[2 * s + 1] = oy;
+    it.gdisp[2 * s] = ox; it.gdisp[2 * s + 1] = oy;
   }
-  __syncthreads();
-  // transpose of the bilinear resize Hs x Ws -> Ht x Wt, as an ordered gather per source point
+}
+// transpose of the bilinear resize Hs x Ws -> Ht x Wt, as an ordered gather per source point
+__global__ void __launch_bounds__(256) k_invb_resize_t(WbInvBwdArgs a) {
+  WB_INV_GEOM;
+  const WbInvBItem it = wb_invb_item(a, blockIdx.y, P, PP);
+  const float* gdisp = it.gdisp;
   const float rh = (float)a.Hs / (float)Ht, rw = (float)a.Ws / (float)Wt;
-  float* dfwd = a.dfwd + (size_t)item * a.Hs * a.Ws * 2;
-  for (int i = wb_tid(); i < a.Hs * a.Ws; i += wb_nthr()) {
+  float* dfwd = a.dfwd + (size_t)blockIdx.y * a.Hs * a.Ws * 2;
+  for (int i = blockIdx.x * wb_nthr() + wb_tid(); i < a.Hs * a.Ws; i += gridDim.x * wb_nthr()) {
     int sy = i / a.Ws, sx = i - sy * a.Ws;
     int ylo = max(0, (int)floorf(((float)sy - 0.5f) / rh - 0.5f) - 2), yhi = min(Ht - 1, (int)ceilf(((float)sy + 1.5f) / rh - 0.5f) + 2);
     int xlo = max(0, (int)floorf(((float)sx - 0.5f) / rw - 0.5f) - 2), xhi = min(Wt - 1, (int)ceilf(((float)sx + 1.5f) / rw - 0.5f) + 2);

@@ -1,0 +1,57 @@
+// Input packing: build the path's `input` tensor on the device from what the dataset really
+// holds -- 8-bit RGB and an 8-bit label map -- instead of shipping 3 + Nl fp32 planes over PCIe.
+// Reference: data/base_dataset.py:173-183 (label -> one-hot -> 5 * (2x - 1)), :355-372 (ToTensor + Normalize(0.5, 0.5)),
+// models/synthesizer.py:444 (input = cat([vid, lyt], dim=2)).
+//   input[f, 0:3]   = ((rgb / 255) - 0.5) / 0.5          (or a copy of an fp32 frame that is already normalised)
+//   input[f, 3 + c] = label == c ? on : off               (on = 5, off = -5; labels >= Nl give all-off)
+// One thread handles 4 consecutive pixels: one 32-bit load per byte plane, one 128-bit store per output plane.
+#pragma once
+#include "wb_common.cuh"
+#include "../../include/waldo_b200.h"
+
+WB_DEV float wb_norm_u8(unsigned v) { return __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), 0.5f), 0.5f); }
+
+__global__ void __launch_bounds__(256) k_pack_input(waldo_pack_input_t p) {
+  const int C = 3 + p.Nl;
+  const size_t HW = (size_t)p.HW;
+  const size_t nq = (HW + 3) / 4;                     // groups of 4 pixels per frame
+  const bool vec = (HW & 3) == 0;
+  const int f = blockIdx.y;
+  for (size_t gq = (size_t)blockIdx.x * wb_nthr() + wb_tid(); gq < nq; gq += (size_t)gridDim.x * wb_nthr()) {
+    const size_t q = gq * 4;
+    const int npx = (int)(HW - q < 4 ? HW - q : 4);
+    float* out = p.input + (size_t)f * C * HW + q;
+    unsigned lab[4] = {255u, 255u, 255u, 255u};
+    if (vec) {
+      const unsigned w = *reinterpret_cast<const unsigned*>(p.label + (size_t)f * HW + q);
+      WB_UNROLL for (int i = 0; i < 4; ++i) lab[i] = (w >> (8 * i)) & 255u;
+    } else {
+      for (int i = 0; i < npx; ++i) lab[i] = p.label[(size_t)f * HW + q + i];
+    }
+    for (int c = 0; c < 3; ++c) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.rgb_u8) {
+        const uint8_t* s = p.rgb_u8 + ((size_t)f * 3 + c) * HW + q;
+        if (vec) {
+          const unsigned w = *reinterpret_cast<const unsigned*>(s);
+          WB_UNROLL for (int i = 0; i < 4; ++i) v[i] = wb_norm_u8((w >> (8 * i)) & 255u);
+        } else {
+          for (int i = 0; i < npx; ++i) v[i] = wb_norm_u8(s[i]);
+        }
+      } else {
+        const float* s = p.rgb_f32 + ((size_t)f * 3 + c) * HW + q;
+        for (int i = 0; i < npx; ++i) v[i] = s[i];
+      }
+      float* o = out + (size_t)c * HW;
+      if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      else for (int i = 0; i < npx; ++i) o[i] = v[i];
+    }
+    for (int c = 0; c < p.Nl; ++c) {
+      float* o = out + (size_t)(3 + c) * HW;
+      const float v0 = lab[0] == (unsigned)c ? p.on : p.off, v1 = lab[1] == (unsigned)c ? p.on : p.off;
+      const float v2 = lab[2] == (unsigned)c ? p.on : p.off, v3 = lab[3] == (unsigned)c ? p.on : p.off;
+      if (vec) *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
+      else { const float vv[4] = {v0, v1, v2, v3}; for (int i = 0; i < npx; ++i) o[i] = vv[i]; }
+    }
+  }
+}

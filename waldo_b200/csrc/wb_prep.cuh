@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) k_class_profile(WbDec d) {
       wb_lyt_lo(d, b, t, p, lyt);
       if (wcls) wb_softmax(lyt, sm, Nl);
       for (int c = 0; c < Nl; ++c) s_lyt[i][c] = lyt[c];
+      if (d.lyt_lo) for (int c = 0; c < Nl; ++c) d.lyt_lo[(((size_t)b * g.Tw + t) * Nl + c) * HW + p] = lyt[c];
       for (int k = 0; k < No; ++k) {
         float w = __ldg(d.a_lo + (((size_t)b * g.Tw + t) * L + k + 1) * HW + p) + 1e-6f;
         if (wcls) {
@@ -244,7 +245,7 @@ WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, unsig
 }
 
 template <int NLC>
-__global__ void __launch_bounds__(WB_TILE_PX, 2) k_alpha_prep(WbDec d) {
+__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_FWD) k_alpha_prep(WbDec d) {
   const waldo_geom_t g = d.g;
   WbPrepCtx c;
   c.L = g.No + 1; c.Nl = g.Nl; c.HW = g.H * g.W; c.HWd = (size_t)g.Hd * g.Wd;

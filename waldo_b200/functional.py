@@ -6,6 +6,7 @@ Every op allocates its outputs / saved state / scratch with torch and hands raw 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -88,12 +89,13 @@ class _InverseWarp(torch.autograd.Function):
         level = torch.empty(n, Hp, Wp, device=dev, dtype=torch.uint8)
         eroded = torch.empty(n, Hp, Wp, device=dev, dtype=torch.uint8)
         val = torch.empty(n, 2, Hp, Wp, device=dev, dtype=torch.float32)
+        bbox = torch.empty(n, 4, device=dev, dtype=torch.int32)
         id_src_c, id_tgt_c, gauss_c = _c(id_src), _c(id_tgt), _c(gauss)
         a = L.InvWarpFwd(n, Hs, Ws, tgt_h, tgt_w, niter, 1 if erode else 0, L.ptr(fg, name="src_grid"), L.ptr(id_src_c),
                          L.ptr(id_tgt_c), L.ptr(gauss_c), L.ptr(out), L.ptr(field, torch.int32), L.ptr(winner, torch.int32),
-                         L.ptr(level, torch.uint8), L.ptr(eroded, torch.uint8), L.ptr(val))
+                         L.ptr(level, torch.uint8), L.ptr(eroded, torch.uint8), L.ptr(val), L.ptr(bbox, torch.int32))
         L.check(lib.waldo_invwarp_fwd(C.byref(a), L.stream_of(fg)), "invwarp_fwd")
-        ctx.save_for_backward(gauss_c, field, winner, level, eroded)
+        ctx.save_for_backward(gauss_c, field, winner, level, eroded, bbox)
         ctx.dims = (n, Hs, Ws, tgt_h, tgt_w, niter)
         if trace_box is not None:
             trace_box.append(InverseWarpTrace(field, winner, level, eroded))
@@ -102,7 +104,7 @@ class _InverseWarp(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         lib = L.load()
-        gauss, field, winner, level, eroded = ctx.saved_tensors
+        gauss, field, winner, level, eroded, bbox = ctx.saved_tensors
         n, Hs, Ws, Ht, Wt, niter = ctx.dims
         dout = _c(dout)
         dev = dout.device
@@ -114,7 +116,7 @@ class _InverseWarp(torch.autograd.Function):
         dfwd = torch.empty(n, Hs, Ws, 2, device=dev, dtype=torch.float32)
         a = L.InvWarpBwd(n, Hs, Ws, Ht, Wt, niter, L.ptr(gauss), L.ptr(dout), L.ptr(field, torch.int32),
                          L.ptr(winner, torch.int32), L.ptr(level, torch.uint8), L.ptr(eroded, torch.uint8),
-                         L.ptr(gval), L.ptr(inv_sw), L.ptr(gdisp), L.ptr(dfwd))
+                         L.ptr(bbox, torch.int32), L.ptr(gval), L.ptr(inv_sw), L.ptr(gdisp), L.ptr(dfwd))
         L.check(lib.waldo_invwarp_bwd(C.byref(a), L.stream_of(dout)), "invwarp_bwd")
         return dfwd, None, None, None, None, None, None, None, None
 
@@ -170,6 +172,7 @@ class DecodeSpec:
     include_self: bool
     use_disocc: bool
     min_cls: float
+    occ_pairs_only: bool = False   # occ comes straight from compute_occ: its backward reads object-object pairs only
 
 
 def _geom(spec: DecodeSpec, B, T, Tc, Tp, Nl, has_cls):
@@ -189,6 +192,8 @@ def _geom(spec: DecodeSpec, B, T, Tc, Tp, Nl, has_cls):
         flags |= L.F_INCLUDE_SELF
     if spec.use_disocc:
         flags |= L.F_USE_DISOCC
+    if spec.occ_pairs_only:
+        flags |= L.F_OCC_PAIRS
     return L.Geom(B, T, Tw, Tc, Tp, spec.num_obj, Nl, 3 + Nl, spec.H, spec.W, spec.Hd, spec.Wd, spec.Ho, spec.Wo,
                   flags, float(spec.min_cls))
 
@@ -216,23 +221,42 @@ def _staged(fn, arg, stream, what, dev):
 
 def _fwd_struct(g, prof_ctas, t):
     (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part, prof_sum, prof_p,
-     f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score) = t
+     f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score, lyt_lo) = t
     return L.DecodeFwd(g, L.ptr(inp_c, name="input"), L.ptr(tgo_c), L.ptr(sgo_c), L.ptr(tgb_c), L.ptr(sgb_c), L.ptr(occ_c),
                        L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
                        L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
-                       L.ptr(prof_p), L.ptr(f_lo), L.ptr(s_lo), L.ptr(live_ctx, torch.int32), L.ptr(live_pred, torch.int32),
+                       L.ptr(prof_p), L.ptr(lyt_lo), L.ptr(f_lo), L.ptr(s_lo), L.ptr(live_ctx, torch.int32), L.ptr(live_pred, torch.int32),
                        L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full), L.ptr(norm), L.ptr(score), 0)
+
+
+_ts_checked = {}
+
+
+def _check_time_indices(ts_user, ps_user, ts, ps, Tw, T):
+    """The kernels index frames with ctx_ts / pred_ts unchecked: validate them here.  Reading the extrema back is a
+    device synchronisation, so the verdict is remembered for as long as the caller passes the very same (unmodified)
+    tensor objects -- the time indices of a rollout or training loop are the same tensors step after step."""
+    import weakref
+    c = _ts_checked
+    if (c.get("ts") is not None and c["ts"]() is ts_user and c["ps"]() is ps_user and
+            c["ver"] == (ts_user._version, ps_user._version, Tw, T)):
+        return
+    ext = torch.stack([ts.max(), ts.min(), ps.max(), ps.min()]).tolist()   # one read-back
+    if ext[0] >= Tw or ext[1] < 0 or ext[2] >= T or ext[3] < 0:
+        raise RuntimeError("waldo_b200.decode: ctx_ts / pred_ts out of range")
+    c["ts"], c["ps"], c["ver"] = weakref.ref(ts_user), weakref.ref(ps_user), (ts_user._version, ps_user._version, Tw, T)
 
 
 class _Decode(torch.autograd.Function):
     """LVD.forward(mode="decode_output") = Warper.grid_to_flow[_ctx] + Warper.input_to_output, lvd.py:141-153.
 
-    Returns (out_full (B,Tp,C+1,Hd,Wd), raw_output (B,Tc+self,Tp,C+L+disocc,Hd,Wd), flow (B,Tc,Tp,2,Hd,Wd),
-    alpha (B,Tw,L,Hd,Wd))."""
+    Returns (output (B,Tp,C,Hd,Wd), raw_alpha (B,Tp,1,Hd,Wd) -- two channel-slice views of one (B,Tp,C+1,Hd,Wd) buffer,
+    lvd.py:147,152 --, raw_output (B,Tc+self,Tp,C+L+disocc,Hd,Wd), flow (B,Tc,Tp,2,Hd,Wd), alpha (B,Tw,L,Hd,Wd))."""
 
     @staticmethod
     def forward(ctx, spec, ctx_ts, pred_ts, xs_hd, ys_hd, inp, tgo, sgo, tgb, sgb, occ, obj_alpha, bg_alpha, cls):
         lib = L.load()
+        ctx.set_materialize_grads(False)   # unused outputs must not cost a zero-filled HD tensor each
         inp_c, tgo_c, sgo_c, tgb_c, sgb_c = (_c(t.detach()) for t in (inp, tgo, sgo, tgb, sgb))
         occ_c, oa_c, ba_c = _c(occ.detach()), _c(obj_alpha.detach()), _c(bg_alpha.detach())
         cls_c = _c(cls.detach()) if cls is not None else None
@@ -248,8 +272,7 @@ class _Decode(torch.autograd.Function):
         dev = inp_c.device
         ts_c = _c(ctx_ts, torch.int64).to(dev)
         ps_c = _c(pred_ts, torch.int64).to(dev)
-        if int(ts_c.max()) >= g.Tw or int(ts_c.min()) < 0 or int(ps_c.max()) >= T or int(ps_c.min()) < 0:
-            raise RuntimeError("waldo_b200.decode: ctx_ts / pred_ts out of range")
+        _check_time_indices(ctx_ts, pred_ts, ts_c, ps_c, g.Tw, T)
         self_ctx = spec.include_self and Tp == T
         TcR, CR = Tc + (1 if self_ctx else 0), Cc + Lr + (1 if spec.use_disocc else 0)
         f32 = dict(device=dev, dtype=torch.float32)
@@ -269,8 +292,10 @@ class _Decode(torch.autograd.Function):
         out_full = torch.empty(B, Tp, Cc + 1, Hd, Wd, **f32)
         norm = torch.empty(B, Tp, Hd, Wd, **f32)
         score = torch.empty(B, Tc, Tp, Hd, Wd, **f32)
+        # low-res layout logits: kept only when a backward will follow (it saves re-reading the HD layout planes)
+        lyt_lo = torch.empty(B, g.Tw, Nl, spec.H, spec.W, **f32) if (spec.use_filter and any(ctx.needs_input_grad)) else None
         tensors = (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
-                   prof_sum, prof_p, f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score)
+                   prof_sum, prof_p, f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score, lyt_lo)
         a = _fwd_struct(g, prof_ctas, tensors)
         _staged(lib.waldo_decode_fwd, a, L.stream_of(inp_c), "decode_fwd", dev=dev)
         # saved through save_for_backward (NOT as ctx attributes): four of them are outputs of this very Function, and an
@@ -279,10 +304,10 @@ class _Decode(torch.autograd.Function):
         ctx.present = [t is not None for t in tensors]
         ctx.geom, ctx.prof_ctas = g, prof_ctas
         ctx.shapes = dict(obj_alpha=obj_alpha.shape, bg_alpha=bg_alpha.shape)
-        return out_full, raw, flow, alpha
+        return out_full[:, :, :Cc], out_full[:, :, Cc:], raw, flow, alpha
 
     @staticmethod
-    def backward(ctx, d_out_full, d_raw, d_flow, d_alpha):
+    def backward(ctx, d_output, d_raw_alpha, d_raw, d_flow, d_alpha):
         lib = L.load()
         it = iter(ctx.saved_tensors)
         tensors = tuple(next(it) if p else None for p in ctx.present)
@@ -317,8 +342,9 @@ class _Decode(torch.autograd.Function):
         d_prof_p = torch.zeros_like(prof_p) if (chain and filt) else None
         d_prof_sum = torch.zeros_like(prof_sum) if (chain and filt) else None
         tiles = ((g.Wd + 31) // 32) * ((g.Hd + 7) // 8)
-        red_ctas = max(1, min(128, tiles))
         groups = max(g.B * g.Tp, g.B * g.Tw)
+        # CTAs per frame of the two reducing HD kernels: whole waves of the 148 SMs at their 2 resident CTAs per SM
+        red_ctas = int(os.environ.get("WALDO_RED_CTAS", 0)) or max(1, min(tiles, -(-148 * 8 // (g.B * g.Tp))))
         occ_part = torch.empty(groups, red_ctas, Lr * Lr, **f32) if n_occ else None
         prof_p_part = torch.empty(g.B * g.Tw, red_ctas, g.No * g.Nl, **f32) if d_prof_p is not None else None
         cls_part = torch.empty(g.B, fwd.prof_ctas, g.No * g.Nl, **f32) if (n_cls and (g.flags & L.F_WEIGHT_CLS)) else None
@@ -327,8 +353,8 @@ class _Decode(torch.autograd.Function):
         d_cls_s = d_cls
         if d_cls_s is None and cls_c is not None and chain and filt and not (g.flags & L.F_WEIGHT_CLS):
             d_cls_s = None   # P = cls path: nothing to propagate unless cls needs grad
-        grads_in = [_c(t) if t is not None else None for t in (d_out_full, d_raw, d_flow, d_alpha)]
-        b = L.DecodeBwd(fwd, L.ptr(grads_in[0]), L.ptr(grads_in[1]), L.ptr(grads_in[2]), L.ptr(grads_in[3]),
+        grads_in = [_c(t) if t is not None else None for t in (d_output, d_raw_alpha, d_raw, d_flow, d_alpha)]
+        b = L.DecodeBwd(fwd, L.ptr(grads_in[0]), L.ptr(grads_in[1]), L.ptr(grads_in[2]), L.ptr(grads_in[3]), L.ptr(grads_in[4]),
                         L.ptr(d_input), L.ptr(d_tgo_s), L.ptr(d_sgo_s), L.ptr(d_tgb_s), L.ptr(d_sgb_s), L.ptr(d_occ),
                         L.ptr(d_oa), L.ptr(d_ba), L.ptr(d_cls_s), L.ptr(d_alpha_acc), L.ptr(d_f_lo), L.ptr(d_a_lo),
                         L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part), L.ptr(up_tab), L.ptr(glue), 0)
@@ -342,6 +368,7 @@ class _Decode(torch.autograd.Function):
 
 def decode(spec: DecodeSpec, ctx_ts, pred_ts, xs_hd, ys_hd, inp, grid, occ, obj_alpha, bg_alpha, cls):
     tgo, sgo, tgb, sgb = grid
+    spec.occ_pairs_only = type(occ.grad_fn).__name__ == "_ComputeOccBackward"
     return _Decode.apply(spec, ctx_ts, pred_ts, xs_hd, ys_hd, inp, tgo, sgo, tgb, sgb, occ, obj_alpha, bg_alpha, cls)
 
 
@@ -377,3 +404,27 @@ class _WifFuse(torch.autograd.Function):
 def wif_fuse(raw_output, unet_out, ab=True):
     """raw_output (B,Tc,Tp,Cin,H,W) as produced by decode_output; unet_out (B,Tp,Tc,4|5,H,W)."""
     return _WifFuse.apply(raw_output, unet_out, ab)
+
+
+# ===================================================================================== f-3 input packing
+def pack_input(rgb, label, num_lyt, on=5.0, off=-5.0, out=None):
+    """Build `input` (B,T,3+Nl,Hd,Wd) fp32 on the device from rgb (B,T,3,Hd,Wd; uint8 raw pixels or fp32 already in
+    [-1,1]) and label (B,T,Hd,Wd) uint8 class ids -- data/base_dataset.py:173-183,:355-372 + synthesizer.py:444.
+    Data preparation: no gradient."""
+    lib = L.load()
+    if rgb.dim() != 5 or rgb.size(2) != 3 or label.shape != rgb.shape[:2] + rgb.shape[3:]:
+        raise RuntimeError(f"waldo_b200.pack_input: rgb {tuple(rgb.shape)} / label {tuple(label.shape)} shapes do not match")
+    if label.dtype != torch.uint8:
+        raise RuntimeError("waldo_b200.pack_input: label must be uint8 class ids")
+    B, T, _, Hd, Wd = rgb.shape
+    rgb_c, lab_c = rgb.detach().contiguous(), label.contiguous()
+    if out is None:
+        out = torch.empty(B, T, 3 + num_lyt, Hd, Wd, device=rgb.device, dtype=torch.float32)
+    elif out.shape != (B, T, 3 + num_lyt, Hd, Wd):
+        raise RuntimeError("waldo_b200.pack_input: out has the wrong shape")
+    u8 = rgb_c.dtype == torch.uint8
+    a = L.PackInput(B * T, num_lyt, Hd * Wd, float(on), float(off),
+                    L.ptr(rgb_c, torch.uint8, "rgb") if u8 else None, None if u8 else L.ptr(rgb_c, name="rgb"),
+                    L.ptr(lab_c, torch.uint8, "label"), L.ptr(out, name="out"))
+    L.check(lib.waldo_pack_input(C.byref(a), L.stream_of(out)), "pack_input")
+    return out

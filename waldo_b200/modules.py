@@ -164,13 +164,13 @@ class Warper(nn.Module):
         spec = self._spec(restrict)
         xs = self.src_grid_hd[0, 0, :, 0].contiguous()
         ys = self.src_grid_hd[0, :, 0, 1].contiguous()
-        out_full, raw, flow, alpha = Fn.decode(spec, ctx_ts, pred_ts, xs, ys, input, grid, occ, obj_alpha, bg_alpha, cls)
+        output, raw_alpha, raw, flow, alpha = Fn.decode(spec, ctx_ts, pred_ts, xs, ys, input, grid, occ, obj_alpha, bg_alpha, cls)
         C = input.size(2)
         Lr = self.num_obj + 1
         Tc = ctx_ts.size(1)
         alpha_ctx = raw[:, :Tc, :, C:C + Lr]                       # a channel-slice view of raw_output
         disocc = raw[:, :Tc, :, C + Lr:C + Lr + 1] if spec.use_disocc else None
-        self._fused = (alpha_ctx, flow, out_full, raw, spec.use_disocc)
+        self._fused = (alpha_ctx, flow, output, raw_alpha, raw, spec.use_disocc)
         alpha_unflt = alpha if self.fast else None                  # lvd.py:702-705 / :825-828
         return flow, alpha_unflt, alpha, alpha_ctx, disocc
 
@@ -194,7 +194,31 @@ class Warper(nn.Module):
                 "immediately preceding grid_to_flow[_ctx] call, as LVD.forward does (lvd.py:143-146): the warp of the "
                 "context frames is fused into that kernel.")
         self._fused = None
-        return f[2], f[3]
+        return _FusedOutput(f[2], f[3]), f[4]
+
+
+class _FusedOutput:
+    """The reference's `output` of input_to_output: a (B,Tp,C+1,Hd,Wd) tensor that LVD.forward only ever slices into
+    `output[:, :, :-1]` and `output[:, :, -1:]` (lvd.py:147,152).  The fused kernel keeps those two as separate autograd
+    outputs (so that their gradients arrive as two dense tensors instead of one zero-padded copy); this wrapper answers
+    exactly those two slices without a copy and materialises the concatenation for anything else."""
+
+    def __init__(self, image, raw_alpha):
+        self.image, self.raw_alpha = image, raw_alpha
+
+    def full(self):
+        return torch.cat([self.image, self.raw_alpha], dim=2)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple) and len(idx) == 3 and idx[0] == slice(None) and idx[1] == slice(None):
+            if idx[2] == slice(None, -1, None):
+                return self.image
+            if idx[2] == slice(-1, None, None):
+                return self.raw_alpha
+        return self.full()[idx]
+
+    def __getattr__(self, name):          # shape, size(), dtype, device, ... of the concatenated tensor
+        return getattr(self.full(), name)
 
 
 # ----------------------------------------------------------------------------- a-4, a-8
@@ -259,3 +283,10 @@ def wif_fuse(vid, unet_out, ab=True):
     """Tail of WIF.forward (wif.py:50-54).  vid = raw_output (B,Tc,Tp,Cin,H,W) exactly as WIF.forward receives it;
     unet_out = UNet output reshaped (B,Tp,Tc,5|4,H,W).  Returns (B,Tp,3,H,W)."""
     return Fn.wif_fuse(vid, unet_out, ab)
+
+
+# ----------------------------------------------------------------------------- f-3 (caller side: the input pipeline)
+def pack_input(rgb, label, num_lyt, out=None):
+    """`input` = cat([vid, lyt], dim=2) (synthesizer.py:444) built on the device from 8-bit RGB (or normalised fp32
+    frames) and the 8-bit label map, i.e. base_dataset.py:173-183 / :355-372 moved after the host->device copy."""
+    return Fn.pack_input(rgb, label, num_lyt, out=out)
