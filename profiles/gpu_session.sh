@@ -17,6 +17,9 @@ launches)
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_launches.log 2>&1; echo "launches rc=$?";;
 exp)
   timeout 1200 python scratch/exp.py $EXP_NAMES > $OUT/${TAG}_exp.log 2>&1; echo "exp rc=$?"; cat $OUT/${TAG}_exp.log;;
+fullk)
+  timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$FULL_K" -c ${FULL_C:-1} \
+     -o $OUT/${TAG}_fullk -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_fullk.log 2>&1; echo "fullk rc=$?"; tail -2 $OUT/${TAG}_fullk.log;;
 full)
   timeout 1500 ncu --set full --clock-control none --import-source on \
      -k 'regex:k_gather_bwd|k_layers_bwd|k_alpha_prep_bwd|k_gather_fwd|k_layers_fwd|k_alpha_prep|k_class_profile' -c 9 \

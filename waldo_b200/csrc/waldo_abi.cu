@@ -184,7 +184,7 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
       WB_LAUNCH(k_class_profile, dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
       WB_LAUNCHED();
     }
-    WB_LAUNCH(k_profile_final, dim3(g.B), dim3(64), 0, st, *a);
+    WB_LAUNCH(k_profile_final, dim3(g.B), dim3(352), 0, st, *a);
     WB_LAUNCHED();
   }
   // B2b-B4

@@ -57,6 +57,7 @@ extern long long g_wb_launches;
   } while (0)
 #define WB_CHECK_LAUNCH() 0
 #define WB_UNROLL
+#define WB_UNROLL_N(n)
 #define WB_UNROLL_NA
 static thread_local float wb_dyn_smem_buf[96 * 1024];
 #define WB_DYN_SMEM(name) float* name = wb_dyn_smem_buf
@@ -68,6 +69,8 @@ extern long long g_wb_launches;
   do { ++g_wb_launches; kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); } while (0)
 #define WB_CHECK_LAUNCH() wb_check_launch(__FILE__, __LINE__)
 #define WB_UNROLL _Pragma("unroll")
+#define WB_PRAGMA_(x) _Pragma(#x)
+#define WB_UNROLL_N(n) WB_PRAGMA_(unroll n)
 // loops over the NA layer slots of a template: fully unrolled (register arrays) for the sparse instantiations,
 // rolled (local-memory arrays, small code, few registers) for the rare dense one
 #define WB_UNROLL_NA _Pragma("unroll (NA <= 8 ? NA : 1)")
@@ -97,13 +100,23 @@ extern long long g_wb_launches;
 #define WB_OCC_GATHER_FWD 4
 #endif
 #ifndef WB_OCC_LAYERS_BWD
-#define WB_OCC_LAYERS_BWD 3
+#define WB_OCC_LAYERS_BWD 2
 #endif
 #ifndef WB_OCC_PREP_BWD
 #define WB_OCC_PREP_BWD 2
 #endif
 #ifndef WB_OCC_GATHER_BWD
 #define WB_OCC_GATHER_BWD 3
+#endif
+#ifndef WB_LANES_PREP_BWD
+#define WB_LANES_PREP_BWD 0
+#endif
+// k_gather_bwd: contexts processed together and channel-loop unrolling (B200 A/B runs, profiles/)
+#ifndef WB_GB_TG
+#define WB_GB_TG 2
+#endif
+#ifndef WB_GB_UNROLL
+#define WB_GB_UNROLL 2
 #endif
 #define WB_MAX_C 24
 #define WB_MAX_NL 21
@@ -159,6 +172,11 @@ WB_DEV double wb_warp_sum(double v) {
 #endif
   return v;
 }
+
+#ifndef WB_HOST_EMU
+// position of the nth (0-based) set bit of m  (lanes-per-layer kernels: layer of a slot)
+WB_DEV int wb_nth_bit(unsigned m, int nth) { return (int)__fns(m, 0, nth + 1); }
+#endif
 
 // ------------------------------------------------------------------ ATen-exact bilinear pieces
 // grid_sampler_2d (bilinear, zeros, align_corners=False), SURVEY.md Appendix C.  The association

@@ -146,6 +146,80 @@ WB_DEV void wb_fwd_layers_ctxs(const WbDec& d, const WbFwdCtx& c, const WbPix& p
   }
 }
 
+#ifndef WB_HOST_EMU
+// ------------------------------------------------------------------------------------------------------------------
+// Lanes-per-layer form of the layer forward (rows whose union of live layers has n <= 8 members): LP = 1|2|4|8 >= n lanes
+// per pixel, lane = slot * (32/LP) + pixel, LP passes over the 32 pixels of the row.  Every lane owns ONE (pixel, layer):
+// the layers of a pixel load in parallel, the occlusion product and the reductions over layers run on warp shuffles,
+// and there is no per-thread array indexed by a layer.  Results are those of wb_layers_fwd up to the order of the sums
+// over layers in flow / score (each A_k, R_k is bit-identical).
+template <int LP>
+WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, int n, unsigned isobj_lane, int tx0, int Y,
+                                const WbAxis& ay, float gy) {
+  constexpr int PPW = 32 / LP;
+  const waldo_geom_t& g = d.g;
+  const int L = c.L, C = c.C, HW = c.HW, b = c.b, tp = c.tp;
+  const unsigned HWd = c.HWd;
+  const int lane = wb_lane(), pl = lane % PPW, slot = lane / PPW;
+  const bool valid = slot < n;
+  const int k = valid ? wb_nth_bit(wm, slot) : 0;
+  float oc[LP];
+  WB_UNROLL for (int j = 0; j < LP; ++j) oc[j] = (valid && j < n) ? c.s_occ[wb_nth_bit(wm, j) * L + k] : 0.f;
+  const float r_lo = (float)g.H / (float)g.Hd;
+  const bool direct = g.Hd == g.H;
+  const int Xl = min(tx0 + lane, g.Wd - 1);
+  const unsigned ql = (unsigned)(Y * g.Wd + Xl);   // this lane's own pixel (lane = pixel layout, dead-layer stores)
+  for (int tc = 0; tc < g.Tc; ++tc) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+    const float2* fl = reinterpret_cast<const float2*>(d.f_lo) + (pair * L + k) * HW;
+    const float* alpha_k = d.alpha + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
+    float* ra = d.raw_output + ((((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR + C) * HWd;   // alpha channels of this pair
+    float* flo = d.flow + pair * 2 * HWd;
+    float* sco = d.score + pair * HWd;
+    // layers outside the row's union are fully transparent
+    { float* o = ra + ql; WB_UNROLL for (int kk = 0; kk < WB_MAX_L; ++kk) { if (kk < L && !((wm >> kk) & 1u)) *o = -1.f; o += HWd; } }
+#pragma unroll 1
+    for (int r = 0; r < LP; ++r) {
+      const int p = r * PPW + pl, X = min(tx0 + p, g.Wd - 1);
+      const unsigned q = (unsigned)(Y * g.Wd + X);
+      const WbAxis ax = wb_axis(X, r_lo, g.W);
+      const float gx = __ldg(d.xs_hd + X);
+      const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
+      const unsigned isobj = __shfl_sync(0xffffffffu, isobj_lane, p);
+      float2 f00 = __ldg(fl + o00), f01 = f00, f10 = f00, f11 = f00;
+      if (!direct) { f01 = __ldg(fl + o01); f10 = __ldg(fl + o10); f11 = __ldg(fl + o11); }
+      float Fx = 0.f, Fy = 0.f, rr = 0.f;
+      if (valid) {
+        if (direct) { Fx = f00.x; Fy = f00.y; }
+        else {
+          Fx = wb_lerp2(f00.x, f01.x, f10.x, f11.x, ax, ay);
+          Fy = wb_lerp2(f00.y, f01.y, f10.y, f11.y, ax, ay);
+        }
+        if ((isobj >> k) & 1u) {
+          const WbTaps t = wb_taps(__fadd_rn(gx, Fx), __fadd_rn(gy, Fy), g.Wd, g.Hd);
+          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+          rr = wb_gather2_01(alpha_k + t2.o0, alpha_k + t2.o1, t2.w);
+        }
+      }
+      float run = 1.f;
+      WB_UNROLL for (int j = 0; j < LP; ++j) run *= 1.f - __shfl_sync(0xffffffffu, rr, pl + j * PPW) * oc[j];
+      const float A = run * rr;
+      float fx = A * Fx, fy = A * Fy, sc = A, mx = rr;
+      WB_UNROLL for (int o = PPW; o < 32; o <<= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        sc += __shfl_xor_sync(0xffffffffu, sc, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (valid) ra[(size_t)k * HWd + q] = A * 2.f - 1.f;
+      if (slot == 0) {
+        flo[q] = fx; flo[HWd + q] = fy; sco[q] = sc;
+        if (c.disocc_ch) ra[(size_t)L * HWd + q] = mx;
+      }
+    }
+  }
+}
+#endif  // !WB_HOST_EMU
+
 // ------------------------------------------------------------------------------------------------------------------
 // The forward runs as two kernels per (b, tp) so that each gets the register budget it needs:
 //   k_layers_fwd : the irregular layer part (B5up..B9) -> alpha channels of raw_output, flow, score
@@ -181,9 +255,17 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_FWD) k_layers_fwd(Wb
       WbPix px = wb_pix(d, b, tp, X, Y);
       const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
+#if !defined(WB_HOST_EMU) && !defined(WB_NO_LANES) && !defined(WB_NO_LANES_FWD)
+      if (n == 1) wb_lanes_layers_fwd<1>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
+      else if (n == 2) wb_lanes_layers_fwd<2>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
+      else if (n <= 4) wb_lanes_layers_fwd<4>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
+      else if (n <= 8) wb_lanes_layers_fwd<8>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
+      else wb_fwd_layers_ctxs<WB_MAX_L>(d, c, px, wm, q);
+#else
       if (WB_NA_VARIANTS_FWD >= 2 && n <= 4) wb_fwd_layers_ctxs<4>(d, c, px, wm, q);
       else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_fwd_layers_ctxs<8>(d, c, px, wm, q);
       else wb_fwd_layers_ctxs<WB_MAX_L>(d, c, px, wm, q);
+#endif
       if (c.self) {   // lvd.py:842-845: the target frame itself is fully opaque
         float* raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q;
         for (int k = 0; k < c.L; ++k) raw[(size_t)(c.C + k) * HWd] = 1.f;

@@ -150,17 +150,6 @@ struct WbBwdCtx {   // per-CTA constants of the fused backward
   float* s_stage;    // this warp's staging area: WB_STAGE_SLOTS * 2 * WB_WARP floats
 };
 
-// forward of the layer part (recomputed): reduced flow and score of one (pixel, context)
-template <int NA>
-WB_DEV void wb_bwd_layers_fwd(const WbDec& d, const WbBwdCtx& c, const WbPix& px, unsigned wm, int c_t, size_t pair,
-                              float& flow_x, float& flow_y, float& score) {
-  const waldo_geom_t& g = d.g;
-  const WbIdx<NA> ix = wb_idx<NA>(wm);
-  WbLay<NA> ly;
-  wb_layers_fwd<NA>(d, px, ix, d.f_lo + pair * c.L * c.HW * 2, d.alpha + ((size_t)c.b * g.Tw + c_t) * c.L * c.HWd, c.s_occ, ly);
-  flow_x = ly.flow_x; flow_y = ly.flow_y; score = ly.score;
-}
-
 // backward of the layer part: B9, B8, B7, B6, B5(up) of one (pixel, context).  gs = d/d score, (dfx, dfy) = d/d flow,
 // draw = this pixel's upstream d raw_output (null = zero).
 template <int NA>
@@ -274,6 +263,184 @@ WB_DEV void wb_bwd_layers_ctxs(const WbDecB& a, const WbBwdCtx& c, const WbPix& 
   }
 }
 
+#ifndef WB_HOST_EMU
+// ============================================================================ lanes-per-layer form of the layer backward
+// A warp owns a row of 32 pixels whose union of live layers has n <= 8 members.  Instead of one lane per pixel looping
+// over the n layers (serial dependent loads, per-thread arrays), the warp makes LP = 1|2|4|8 >= n passes over the row
+// with LP lanes per pixel: lane = slot * (32/LP) + pixel, every lane owns ONE (pixel, layer).  All layers of a pixel
+// load in parallel, the occlusion products run over warp shuffles, and there is no per-thread array indexed by a layer.
+// n > 8 (dense rows, or training without is_obj) keeps the one-lane-per-pixel form above.
+// v[j] (j < LP) of lane (pixel, slot i)  ->  v[0] of lane (pixel, slot j) = sum_i v_i[j]   (LP - 1 shuffles)
+template <int LP>
+WB_DEV void wb_slot_transpose_sum(float* v, int slot) {
+  constexpr int PPW = 32 / LP;
+  WB_UNROLL for (int o = LP / 2; o >= 1; o >>= 1) {
+    const bool up = (slot & o) != 0;
+    WB_UNROLL for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o * PPW);
+    }
+  }
+}
+
+// flush the staged per-(slot, pixel) values of one row: value rows 2*s (x) and 2*s+1 (y) of slot s go to layer k_s of d_f_lo
+WB_DEV void wb_colred_flush_slots(const WbColRed& cr, const float* s_stage, unsigned wm, int ncomp, float* base, size_t layer_stride,
+                                  int W, int stride) {
+  if (cr.col[0] < 0) return;
+  int s = 0;
+  for (unsigned m = wm; m; m &= m - 1u, ++s) {
+    const int k = __ffs((int)m) - 1;
+    for (int comp = 0; comp < ncomp; ++comp) {
+      const float* sv = s_stage + WB_STAGE_AT(ncomp * s + comp, cr.lo[0]);
+      float acc = 0.f;
+      WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) acc += cr.w[0][t] * sv[t];
+      if (acc != 0.f) {
+        float* dst = base + (size_t)k * layer_stride + comp;
+        atomicAdd(dst + ((size_t)cr.row0 * W + cr.col[0]) * stride, acc * cr.wy0);
+        atomicAdd(dst + ((size_t)cr.row1 * W + cr.col[0]) * stride, acc * cr.wy1);
+      }
+    }
+  }
+}
+
+template <int LP>
+WB_DEV void wb_lanes_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbColRed& cr, unsigned wm, int n, unsigned isobj_lane,
+                                int tx0, bool rowact, int Y, const WbAxis& ay, float gy) {
+  constexpr int PPW = 32 / LP;
+  const WbDec& d = a.f;
+  const waldo_geom_t& g = d.g;
+  const int L = c.L, C = c.C, HW = c.HW, b = c.b, tp = c.tp;
+  const unsigned HWd = c.HWd;
+  const int lane = wb_lane(), pl = lane % PPW, slot = lane / PPW;
+  const bool valid = slot < n;
+  const int k = valid ? wb_nth_bit(wm, slot) : 0;
+  float oc[LP], accj[LP];
+  WB_UNROLL for (int j = 0; j < LP; ++j) {
+    accj[j] = 0.f;
+    oc[j] = (valid && j < n) ? c.s_occ[wb_nth_bit(wm, j) * L + k] : 0.f;
+  }
+  const float r_lo = (float)g.H / (float)g.Hd;
+  const bool stage = a.d_f_lo && !c.lowres_direct;
+  for (int tc = 0; tc < g.Tc; ++tc) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+    const float2* fl = reinterpret_cast<const float2*>(d.f_lo) + (pair * L + k) * HW;
+    const float* alpha_k = d.alpha + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
+    float* dal_k = a.d_alpha_acc ? a.d_alpha_acc + (((size_t)b * g.Tw + c_t) * L + k) * HWd : nullptr;
+    const float* gl = a.glue + pair * 3 * HWd;
+    const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd : nullptr;
+#pragma unroll 1
+    for (int r = 0; r < LP; ++r) {
+      const int p = r * PPW + pl, Xr = tx0 + p, X = min(Xr, g.Wd - 1);
+      const float actf = (rowact && Xr < g.Wd) ? 1.f : 0.f;
+      const unsigned q = (unsigned)(Y * g.Wd + X);
+      const WbAxis ax = wb_axis(X, r_lo, g.W);
+      const float gx = __ldg(d.xs_hd + X);
+      const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
+      const unsigned isobj = __shfl_sync(0xffffffffu, isobj_lane, p);
+      // ---- every load that does not depend on another load is issued first (invalid lanes read layer 0: harmless)
+      const float gs_l = __ldg(gl + q), dfx_l = __ldg(gl + HWd + q), dfy_l = __ldg(gl + 2 * HWd + q);
+      const float dr_l = draw ? __ldg(draw + (size_t)(C + k) * HWd + q) : 0.f;
+      float2 f00 = __ldg(fl + o00), f01 = f00, f10 = f00, f11 = f00;
+      if (!c.lowres_direct) { f01 = __ldg(fl + o01); f10 = __ldg(fl + o10); f11 = __ldg(fl + o11); }
+      // ---- forward of this (pixel, layer), same arithmetic as wb_layers_fwd
+      float Fx = 0.f, Fy = 0.f, rr = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+      bool samp = false;
+      WbTaps tk; WbTap2 t2;
+      if (valid) {
+        if (c.lowres_direct) { Fx = f00.x; Fy = f00.y; }
+        else {
+          Fx = wb_lerp2(f00.x, f01.x, f10.x, f11.x, ax, ay);
+          Fy = wb_lerp2(f00.y, f01.y, f10.y, f11.y, ax, ay);
+        }
+        if ((isobj >> k) & 1u) {
+          samp = true;
+          tk = wb_taps(__fadd_rn(gx, Fx), __fadd_rn(gy, Fy), g.Wd, g.Hd);
+          t2 = wb_tap2(tk, g.Wd, g.Hd);
+          const float* p0 = alpha_k + t2.o0;
+          const float* p1 = alpha_k + t2.o1;
+          v0 = (__ldg(p0) + 1.f) * 0.5f; v1 = (__ldg(p0 + 1) + 1.f) * 0.5f;
+          v2 = (__ldg(p1) + 1.f) * 0.5f; v3 = (__ldg(p1 + 1) + 1.f) * 0.5f;
+          rr = __fmaf_rn(v3, t2.w[3], __fmaf_rn(v2, t2.w[2], __fmaf_rn(v1, t2.w[1], __fmul_rn(v0, t2.w[0]))));
+        }
+      }
+      float Rj[LP], pre[LP];
+      float run = 1.f;
+      WB_UNROLL for (int j = 0; j < LP; ++j) {
+        Rj[j] = __shfl_sync(0xffffffffu, rr, pl + j * PPW);
+        pre[j] = run;
+        run *= 1.f - Rj[j] * oc[j];
+      }
+      const float A = run * rr;
+      // ---- upstream of this (pixel, layer)
+      const float gs = actf * gs_l, dfx = actf * dfx_l, dfy = actf * dfy_l;
+      const float gA = valid ? gs + 2.f * (actf * dr_l) + dfx * Fx + dfy * Fy : 0.f;
+      float gFx = A * dfx, gFy = A * dfy;
+      // ---- exclusive-product backward over the slot lanes
+      float gR = gA * run;
+      const float gV = gA * rr;
+      float term[LP];
+      float suf = 1.f;
+      WB_UNROLL for (int j = LP - 1; j >= 0; --j) {
+        const float excl = pre[j] * suf;
+        suf *= 1.f - Rj[j] * oc[j];
+        term[j] = -gV * oc[j] * excl;
+        accj[j] += -gV * Rj[j] * excl;
+      }
+      wb_slot_transpose_sum<LP>(term, slot);
+      gR += term[0];
+      if (c.disocc_ch && draw) {   // B7 backward: the first maximal layer takes the gradient
+        float mx = rr;
+        WB_UNROLL for (int o = PPW; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        int first = (valid && rr == mx) ? slot : 99;
+        WB_UNROLL for (int o = PPW; o < 32; o <<= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        if (slot == first) gR += actf * __ldg(draw + (size_t)(C + L) * HWd + q);
+      }
+      // ---- B6 backward: bilinear sample of the context opacity through this layer's flow
+      if (samp && gR != 0.f) {
+        float cx[4], cy[4];
+        wb_pos4(t2, -tk.wy0, tk.wy0, -tk.wy1, tk.wy1, cx);
+        wb_pos4(t2, -tk.wx0, -tk.wx1, tk.wx0, tk.wx1, cy);
+        gFx += gR * (v0 * cx[0] + v1 * cx[1] + v2 * cx[2] + v3 * cx[3]) * (0.5f * (float)g.Wd);
+        gFy += gR * (v0 * cy[0] + v1 * cy[1] + v2 * cy[2] + v3 * cy[3]) * (0.5f * (float)g.Hd);
+        if (dal_k) {
+          float* q0 = dal_k + t2.o0;
+          float* q1 = dal_k + t2.o1;
+          wb_atomic_add(q0, t2.w[0] * gR); wb_atomic_add(q0 + 1, t2.w[1] * gR);
+          wb_atomic_add(q1, t2.w[2] * gR); wb_atomic_add(q1 + 1, t2.w[3] * gR);
+        }
+      }
+      // ---- B5(up) backward
+      if (a.d_f_lo && valid) {
+        if (c.lowres_direct) {
+          float* o = a.d_f_lo + (pair * L + k) * HW * 2 + (size_t)o00 * 2;
+          wb_atomic_add(o, gFx); wb_atomic_add(o + 1, gFy);
+        } else {
+          c.s_stage[WB_STAGE_AT(2 * slot, p)] = gFx;
+          c.s_stage[WB_STAGE_AT(2 * slot + 1, p)] = gFy;
+        }
+      }
+    }
+    if (stage) {
+      __syncwarp();
+      wb_colred_flush_slots(cr, c.s_stage, wm, 2, a.d_f_lo + pair * L * HW * 2, (size_t)HW * 2, g.W, 2);
+      __syncwarp();
+    }
+  }
+  if (c.s_acc) {   // d occ: pixels of the row summed over the pixel lanes, one lane per (j, i) pair adds to the warp's slot
+    WB_UNROLL for (int j = 0; j < LP; ++j) {
+      float v = accj[j];
+      WB_UNROLL for (int o = PPW / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (pl == 0 && valid && j < n) {
+        const int kj = wb_nth_bit(wm, j);
+        if (!(c.pairs_only && (k == 0 || kj == 0 || k == kj))) c.s_acc[kj * L + k] += v;
+      }
+    }
+  }
+}
+#endif  // !WB_HOST_EMU
+
 // ------------------------------------------------------------------------------------------------------------------
 // The backward of the two HD kernels, in reverse order:
 //   k_gather_bwd : stage C backward.  Scatters d input and reduces, per (pixel, context), the upstream gradients
@@ -342,9 +509,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd(Wb
         float* dself = (first && self && has_din) ? a.d_input + ((size_t)b * g.T + tp) * C * HWd + q : nullptr;
         const float* drself = (self && has_draw) ? a.d_raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q : nullptr;
         unsigned choff = 0u;   // ch * HWd
-#ifndef WB_HOST_EMU
-#pragma unroll 2
-#endif
+        WB_UNROLL_N(WB_GB_UNROLL)
         for (int ch = 0; ch < C; ++ch) {
           // all loads of this channel first (read-only path), then the arithmetic and the reductions
           float v[TG][4], gd[TG];
@@ -449,6 +614,17 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_BWD) k_layers_bwd(Wb
       WbColRed cr;
       if (a.d_f_lo && !c.lowres_direct)
         cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(px.ax.i0, 0), wb_shfl(px.ax.i1, WB_WARP - 1), px.ay);
+#if !defined(WB_HOST_EMU) && !defined(WB_NO_LANES)
+      if (n <= 8) {
+        const bool rowact = Yr < g.Hd;
+        const unsigned iso = px.isobj;
+        if (n == 1) wb_lanes_layers_bwd<1>(a, c, cr, wm, n, iso, tx0, rowact, Y, px.ay, px.gy);
+        else if (n == 2) wb_lanes_layers_bwd<2>(a, c, cr, wm, n, iso, tx0, rowact, Y, px.ay, px.gy);
+        else if (n <= 4) wb_lanes_layers_bwd<4>(a, c, cr, wm, n, iso, tx0, rowact, Y, px.ay, px.gy);
+        else wb_lanes_layers_bwd<8>(a, c, cr, wm, n, iso, tx0, rowact, Y, px.ay, px.gy);
+        continue;
+      }
+#endif
       if (WB_NA_VARIANTS_BWD >= 2 && n <= 4) wb_bwd_layers_ctxs<4>(a, c, px, cr, wm, q, actf);
       else if (WB_NA_VARIANTS_BWD >= 3 && n <= 8) wb_bwd_layers_ctxs<8>(a, c, px, cr, wm, q, actf);
       else wb_bwd_layers_ctxs<WB_MAX_L>(a, c, px, cr, wm, q, actf);
@@ -473,7 +649,7 @@ __global__ void k_occ_reduce(const float* __restrict__ part, int groups, int per
   const int frame = mode == 0 ? (int)pred_ts[j] : j;
   for (int e = wb_tid(); e < LL; e += wb_nthr()) {
     float acc = 0.f;
-    for (int c = 0; c < ctas; ++c) acc += part[((size_t)grp * ctas + c) * LL + e];
+    WB_UNROLL_N(8) for (int c = 0; c < ctas; ++c) acc += __ldg(part + ((size_t)grp * ctas + c) * LL + e);   // fixed order
     d_occ[((size_t)b * T + frame) * LL + e] += acc;
   }
 }
@@ -618,6 +794,194 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   }
 }
 
+#ifndef WB_HOST_EMU
+// ============================================================================ lanes-per-layer form of the context-alpha backward
+// NOT the default (WB_LANES_PREP_BWD = 0): parity-green, but measured SLOWER on B200 than the one-lane-per-pixel form
+// (4.2 ms vs 3.2 ms per launch, profiles/r1_v10): unlike the layer kernels this one is dominated by the per-object loops
+// over the 20 classes, and with one layer per lane the background / padding lanes of every pixel idle through them.
+// Same layout as wb_lanes_layers_bwd: LP lanes per pixel, one (pixel, layer) per lane, LP passes over the row.
+// Class-indexed quantities (20 classes padded to 32) are spread over lanes with partial transpose-sums:
+
+// over the SLOT lanes of a pixel: afterwards v[0 .. 32/LP) of slot lane s holds the sums (over the LP lanes) of the classes
+// cbase + i, with cbase returned  (= sum over stages t of bit_t(s) * (16 >> t))
+template <int LP>
+WB_DEV int wb_class_split_slots(float* v, int slot) {
+  constexpr int PPW = 32 / LP;
+  int cbase = 0;
+  WB_UNROLL for (int t = 0; (1 << t) < LP; ++t) {
+    const int o = 16 >> t, bit = 1 << t;
+    const bool up = (slot & bit) != 0;
+    WB_UNROLL for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit * PPW);
+    }
+    if (up) cbase += o;
+  }
+  return cbase;
+}
+// over the PPW pixel lanes that share a slot: v[0 .. 32/PPW) of pixel lane pl holds the row sums of the classes cbase + i
+template <int PPW>
+WB_DEV int wb_class_split_pixels(float* v, int pl) {
+  int cbase = 0;
+  WB_UNROLL for (int t = 0; (1 << t) < PPW; ++t) {
+    const int o = 16 >> t, bit = 1 << t;
+    const bool up = (pl & bit) != 0;
+    WB_UNROLL for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+    if (up) cbase += o;
+  }
+  return cbase;
+}
+
+#define WB_SM_ROW 32   // s_sm[class][pixel of the row]
+
+template <int LP, int NLC>
+WB_DEV void wb_lanes_prep_bwd(const WbDecB& a, const WbPrepBwdCtx& c, const WbColRed& cr, unsigned wm, int n, int tx0, bool rowact, int Y,
+                              const WbAxis& ay, float* __restrict__ s_sm) {
+  constexpr int PPW = 32 / LP;
+  constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
+  constexpr int NS = 32 / LP;     // classes per slot lane after the split
+  constexpr int NPX = 32 / PPW;   // classes per pixel lane after the row split (= LP)
+  const WbDec& d = a.f;
+  const waldo_geom_t& g = d.g;
+  const int L = c.L, Nl = NLC > 0 ? NLC : c.Nl, HW = c.HW, b = c.b, t = c.t;
+  const unsigned HWd = c.HWd;
+  const int lane = wb_lane(), pl = lane % PPW, slot = lane / PPW;
+  const bool valid = slot < n;
+  const int k = valid ? wb_nth_bit(wm, slot) : 0;
+  const bool isobjk = valid && k >= 1;
+  float oc[LP], accj[LP];
+  WB_UNROLL for (int j = 0; j < LP; ++j) {
+    accj[j] = 0.f;
+    oc[j] = (valid && j < n) ? c.s_occ[wb_nth_bit(wm, j) * L + k] : 0.f;
+  }
+  const bool filt_row = LP > 1 && c.filt && (wm >> 1) != 0u;   // some object is live in this row
+  // ---- phase A (lane = pixel): softmax of the HD layout logits, staged for the slot lanes
+  if (filt_row) {
+    const int X = min(tx0 + lane, g.Wd - 1);
+    float sm[NN];
+    wb_softmax_hd<NLC>(c.lyt_base, HWd, (unsigned)(Y * g.Wd + X), Nl, sm);
+    WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) s_sm[cc * WB_SM_ROW + lane] = sm[cc];
+    __syncwarp();
+  }
+  float accP[NN];   // d P[k, :] of this lane's layer, summed over the passes
+  WB_UNROLL for (int cc = 0; cc < NN; ++cc) accP[cc] = 0.f;
+  const float* P = c.s_P + (isobjk ? (k - 1) * Nl : 0);
+  const float* alo_k = c.alo + (size_t)k * HW;
+  const size_t plane = (((size_t)b * g.Tw + t) * L + k) * HWd;
+  const float r_lo = (float)g.H / (float)g.Hd;
+  const bool stage = a.d_a_lo && !c.lowres_direct;
+#pragma unroll 1
+  for (int r = 0; r < LP; ++r) {
+    const int p = r * PPW + pl, Xr = tx0 + p, X = min(Xr, g.Wd - 1);
+    const float actf = (rowact && Xr < g.Wd) ? 1.f : 0.f;
+    const unsigned q = (unsigned)(Y * g.Wd + X);
+    const WbAxis ax = wb_axis(X, r_lo, g.W);
+    const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
+    // ---- loads first (invalid lanes read layer 0: harmless)
+    float a00 = __ldg(alo_k + o00), a01 = a00, a10 = a00, a11 = a00;
+    if (!c.lowres_direct) { a01 = __ldg(alo_k + o01); a10 = __ldg(alo_k + o10); a11 = __ldg(alo_k + o11); }
+    const float gacc = a.d_alpha_acc ? a.d_alpha_acc[plane + q] : 0.f;
+    const float gal = a.d_alpha ? __ldg(a.d_alpha + plane + q) : 0.f;
+    // ---- forward of this (pixel, layer), same arithmetic as wb_prep_pixel
+    const float aup = valid ? (c.lowres_direct ? a00 : wb_lerp2(a00, a01, a10, a11, ax, ay)) : 0.f;
+    float ell = 1.f;
+    if (filt_row && isobjk) {
+      float dist = 0.f;
+      WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dist += fabsf(P[cc] - s_sm[cc * WB_SM_ROW + p]);
+      ell = 1.f - dist * 0.5f;
+    }
+    const float av = aup * ell;
+    const float gA = valid ? (gacc + 2.f * gal) * actf : 0.f;
+    // ---- exclusive-product backward over the slot lanes
+    float Rj[LP], pre[LP], term[LP];
+    float run = 1.f;
+    WB_UNROLL for (int j = 0; j < LP; ++j) {
+      Rj[j] = __shfl_sync(0xffffffffu, av, pl + j * PPW);
+      pre[j] = run;
+      run *= 1.f - Rj[j] * oc[j];
+    }
+    float ga = gA * run;
+    const float gV = gA * av;
+    float suf = 1.f;
+    WB_UNROLL for (int j = LP - 1; j >= 0; --j) {
+      const float excl = pre[j] * suf;
+      suf *= 1.f - Rj[j] * oc[j];
+      term[j] = -gV * oc[j] * excl;
+      accj[j] += -gV * Rj[j] * excl;
+    }
+    wb_slot_transpose_sum<LP>(term, slot);
+    ga += term[0];
+    // ---- filter backward: l_k = 1 - 0.5 sum_c |P_kc - sm_c|
+    if (filt_row) {
+      const float gl = isobjk ? ga * aup : 0.f;   // d / d l_k
+      float v[32];
+      WB_UNROLL for (int cc = 0; cc < 32; ++cc) {
+        v[cc] = 0.f;
+        if (cc < NN && (NLC > 0 || cc < Nl)) {
+          const float df = P[cc] - s_sm[cc * WB_SM_ROW + p];
+          const float sg = df > 0.f ? 0.5f : (df < 0.f ? -0.5f : 0.f);
+          v[cc] = sg * gl;          // this layer's share of d / d sm_c
+          accP[cc] -= sg * gl;      // d / d P_kc
+        }
+      }
+      if (a.d_input) {   // softmax backward into the layout logits: d lyt_c = sm_c (gsm_c - sum_c' gsm_c' sm_c')
+        const int cbase = wb_class_split_slots<LP>(v, slot);
+        float smc[NS];
+        float dot = 0.f;
+        WB_UNROLL for (int i = 0; i < NS; ++i) {
+          const int cls = cbase + i;
+          smc[i] = cls < Nl ? s_sm[cls * WB_SM_ROW + p] : 0.f;
+          dot += v[i] * smc[i];
+        }
+        WB_UNROLL for (int o = PPW; o < 32; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (actf != 0.f) {
+          float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3 + cbase) * HWd + q;
+          WB_UNROLL for (int i = 0; i < NS; ++i) {
+            if (cbase + i < Nl) atomicAdd(o, smc[i] * (v[i] - dot));   // fire-and-forget reduction
+            o += HWd;
+          }
+        }
+      }
+    }
+    // ---- up-sampling backward: d a_lo
+    if (a.d_a_lo && valid) {
+      if (c.lowres_direct) wb_atomic_add(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + o00, ga * ell);
+      else c.s_stage[WB_STAGE_AT(slot, p)] = ga * ell;
+    }
+  }
+  if (stage) {
+    __syncwarp();
+    wb_colred_flush_slots(cr, c.s_stage, wm, 1, a.d_a_lo + ((size_t)b * g.Tw + t) * L * HW, (size_t)HW, g.W, 1);
+    __syncwarp();
+  }
+  if (c.s_acc) {
+    WB_UNROLL for (int j = 0; j < LP; ++j) {
+      float v = accj[j];
+      WB_UNROLL for (int o = PPW / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (pl == 0 && valid && j < n) {
+        const int kj = wb_nth_bit(wm, j);
+        if (!(c.pairs_only && (k == 0 || kj == 0 || k == kj))) c.s_acc[kj * L + k] += v;
+      }
+    }
+  }
+  if (filt_row) {
+    if (c.need_p) {   // d P[k, :]: row sums over the pixel lanes, one lane per (layer, class)
+      float v[32];
+      WB_UNROLL for (int cc = 0; cc < 32; ++cc) v[cc] = cc < NN ? accP[cc] : 0.f;
+      const int cbase = wb_class_split_pixels<PPW>(v, pl);
+      WB_UNROLL for (int i = 0; i < NPX; ++i)
+        if (isobjk && cbase + i < Nl) c.s_accp[(k - 1) * Nl + cbase + i] += v[i];
+    }
+    __syncwarp();   // s_sm is rewritten by the warp's next row
+  }
+}
+#endif  // !WB_HOST_EMU
+
 // grid = (red_ctas, B*Tw), block = 256.
 template <int NLC>
 __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(WbDecB a) {
@@ -637,6 +1001,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
   __shared__ float s_redp[WB_NWARP][(WB_MAX_L - 1) * WB_MAX_NL];
   __shared__ float s_stage[WB_NWARP][WB_STAGE_SLOTS * WB_STAGE_ROW];
+  WB_DYN_SMEM(s_dyn);   // WB_NWARP x [WB_MAX_NL][32] softmax staging of the lanes-per-layer path
   if (c.filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)c.b * No * Nl + i];
   for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + c.t) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
@@ -665,6 +1030,17 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(
       if (n == 0) continue;   // warp-uniform: nothing live here, every gradient path is dead
       WbColRed cr;
       if (a.d_a_lo && !c.lowres_direct) cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(ax.i0, 0), wb_shfl(ax.i1, WB_WARP - 1), ay);
+#if !defined(WB_HOST_EMU) && !defined(WB_NO_LANES) && WB_LANES_PREP_BWD
+      if (n <= 8) {
+        float* s_sm = s_dyn + wb_warp() * (WB_MAX_NL * WB_SM_ROW);
+        const bool rowact = Yr < g.Hd;
+        if (n == 1) wb_lanes_prep_bwd<1, NLC>(a, c, cr, wm, n, tx0, rowact, Y, ay, s_sm);
+        else if (n == 2) wb_lanes_prep_bwd<2, NLC>(a, c, cr, wm, n, tx0, rowact, Y, ay, s_sm);
+        else if (n <= 4) wb_lanes_prep_bwd<4, NLC>(a, c, cr, wm, n, tx0, rowact, Y, ay, s_sm);
+        else wb_lanes_prep_bwd<8, NLC>(a, c, cr, wm, n, tx0, rowact, Y, ay, s_sm);
+        continue;
+      }
+#endif
       if (WB_NA_VARIANTS_BWD >= 2 && n <= 4) wb_prep_bwd_pixel<4, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
       else if (WB_NA_VARIANTS_BWD >= 3 && n <= 8) wb_prep_bwd_pixel<8, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
       else wb_prep_bwd_pixel<WB_MAX_L, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
@@ -698,8 +1074,9 @@ __global__ void k_profile_final_bwd(WbDecB a) {
   const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
   for (int e = wb_tid(); e < No * Nl; e += wb_nthr()) {
     float acc = 0.f;
-    for (int t = 0; t < g.Tw; ++t)
-      for (int c = 0; c < a.red_ctas; ++c) acc += a.prof_p_part[(((size_t)b * g.Tw + t) * a.red_ctas + c) * No * Nl + e];
+    const float* pp = a.prof_p_part + (size_t)b * g.Tw * a.red_ctas * No * Nl + e;
+    const int np = g.Tw * a.red_ctas;   // (t, cta) partials are contiguous: one flat, fixed-order loop
+    WB_UNROLL_N(8) for (int c = 0; c < np; ++c) acc += __ldg(pp + (size_t)c * No * Nl);
     a.d_prof_p[(size_t)b * No * Nl + e] = acc;
   }
   __syncthreads();
@@ -958,7 +1335,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     if (!need_layers) ag.glue = nullptr;
     const dim3 ggrid(wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX) > 1024 ? 1024 : wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX), g.B * g.Tp);
     const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
-    if (g.Tc % 2 == 0 && !self && a.d_input && a.d_raw_output && a.d_output) WB_LAUNCH((k_gather_bwd<2, true>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
+    if (g.Tc % WB_GB_TG == 0 && !self && a.d_input && a.d_raw_output && a.d_output) WB_LAUNCH((k_gather_bwd<WB_GB_TG, true>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
     else WB_LAUNCH((k_gather_bwd<2, false>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
     WB_BLAUNCHED();
   }
@@ -976,9 +1353,16 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   if (a.d_alpha_acc || a.d_alpha) {
     if (filt && a.d_prof_p) WB_BREQ(a.prof_p_part, "prof_p_part scratch missing");
     const dim3 pgrid(a.red_ctas, g.B * g.Tw);
-    if (g.Nl == 20) WB_LAUNCH(k_alpha_prep_bwd<20>, pgrid, dim3(WB_TILE_PX), 0, st, a);
-    else if (g.Nl == 19) WB_LAUNCH(k_alpha_prep_bwd<19>, pgrid, dim3(WB_TILE_PX), 0, st, a);
-    else WB_LAUNCH(k_alpha_prep_bwd<0>, pgrid, dim3(WB_TILE_PX), 0, st, a);
+    const size_t dyn = (size_t)WB_NWARP * WB_MAX_NL * 32 * sizeof(float);
+#ifndef WB_HOST_EMU
+    // static + dynamic shared memory exceeds the 48 KB default: opt in (cheap, idempotent)
+    if (g.Nl == 20) cudaFuncSetAttribute(k_alpha_prep_bwd<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    else if (g.Nl == 19) cudaFuncSetAttribute(k_alpha_prep_bwd<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    else cudaFuncSetAttribute(k_alpha_prep_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+#endif
+    if (g.Nl == 20) WB_LAUNCH(k_alpha_prep_bwd<20>, pgrid, dim3(WB_TILE_PX), dyn, st, a);
+    else if (g.Nl == 19) WB_LAUNCH(k_alpha_prep_bwd<19>, pgrid, dim3(WB_TILE_PX), dyn, st, a);
+    else WB_LAUNCH(k_alpha_prep_bwd<0>, pgrid, dim3(WB_TILE_PX), dyn, st, a);
     WB_BLAUNCHED();
     if (a.d_occ) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tw), dim3(128), 0, st, a.occ_part, g.B * g.Tw, g.Tw, a.red_ctas, L * L, g.T, d.pred_ts, 1, a.d_occ);
@@ -986,7 +1370,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     }
     if (filt && a.d_prof_p) {
       WB_BREQ(a.d_prof_sum, "d_prof_sum scratch missing");
-      WB_LAUNCH(k_profile_final_bwd, dim3(g.B), dim3(64), 0, st, a);
+      WB_LAUNCH(k_profile_final_bwd, dim3(g.B), dim3(352), 0, st, a);
       WB_BLAUNCHED();
       if (!from_cls) {
         if ((g.flags & WALDO_F_WEIGHT_CLS) && a.d_cls) WB_BREQ(a.cls_part, "cls_part scratch missing");

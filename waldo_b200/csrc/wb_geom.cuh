@@ -62,7 +62,7 @@ __global__ void k_tps_bwd_partial(int n, int N, int P, int chunks, const float* 
   const int p0 = ch * per, p1 = min(P, p0 + per);
   for (int j = wb_tid(); j < K; j += wb_nthr()) {
     double ax = 0.0, ay = 0.0;
-    for (int p = p0; p < p1; ++p) {
+    WB_UNROLL_N(8) for (int p = p0; p < p1; ++p) {
       double r = (double)__ldg(repr + (size_t)p * K + j);
       ax += r * (double)__ldg(dgrid + ((size_t)item * P + p) * 2);
       ay += r * (double)__ldg(dgrid + ((size_t)item * P + p) * 2 + 1);

@@ -133,7 +133,7 @@ __global__ void k_profile_final(WbDec d) {
   if (!from_cls) {
     for (int o = wb_tid(); o < nout; o += wb_nthr()) {
       float acc = 0.f;
-      for (int c = 0; c < d.prof_ctas; ++c) acc += d.prof_part[((size_t)b * d.prof_ctas + c) * nout + o];
+      WB_UNROLL_N(8) for (int c = 0; c < d.prof_ctas; ++c) acc += d.prof_part[((size_t)b * d.prof_ctas + c) * nout + o];
       d.prof_sum[(size_t)b * nout + o] = acc;
     }
     __syncthreads();
