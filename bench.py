@@ -60,9 +60,13 @@ def kernel_bytes(cfg, B, Tc, Tp):
     """Algorithmic bytes per launch of the four HD kernels (DESIGN.md "kernels"), fp32.  pair = one (b, tc, tp)."""
     Hd, Wd = cfg.hd_shape
     px, s = Hd * Wd, 4
-    C, L = 3 + cfg.num_lyt, cfg.num_obj + 1
+    C, L, Nl = 3 + cfg.num_lyt, cfg.num_obj + 1, cfg.num_lyt
     pairs, frames = B * Tc * Tp, B * Tp
     return {
+        # read the HD layout logits, write the context alpha stack (low-res inputs are L2-resident)
+        "k_alpha_prep": px * s * (B * Tc * (Nl + L)),
+        # read d alpha (scatter-accumulated), re-read the layout logits, write d layout logits
+        "k_alpha_prep_bwd": px * s * (B * Tc * (L + 2 * Nl)),
         # gather-read the context frame, read flow + score; write the warped channels, the fused output and its norm
         "k_gather_fwd": px * s * (pairs * (C + 3 + C) + frames * (C + 1 + 1)),
         # gather-read the context alpha stack; write alpha_ctx, flow, score
@@ -196,6 +200,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-input-grad", action="store_true", help="experiment: do not request d input")
+    ap.add_argument("--no-graph", action="store_true", help="inference workloads: eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
 
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -236,7 +241,12 @@ def main():
     resident = {k: pinned[k].to(dev) for k in small}
     resident["input"] = wb.pack_input(pinned["rgb"].to(dev), pinned["label"].to(dev), cfg.num_lyt)
     del host
-    grad_buf = torch.zeros(WIF_GRAD_ELEMS, device=dev) if (world > 1 and backward) else None
+    from waldo_b200 import sharding
+    grad_buf = None
+    if world > 1 and backward:   # the trainable net's gradients (WIF-sized), exchanged as DDP would: one flat all-reduce per step
+        wif_like = torch.nn.Parameter(torch.zeros(WIF_GRAD_ELEMS, device=dev))
+        wif_like.grad = torch.zeros_like(wif_like)
+        grad_buf = sharding.FlatGradReducer([wif_like])
     loss_host = torch.zeros(1).pin_memory()
 
     # upstream gradients as a downstream consumer (WIF / losses) would supply them: fixed seeded tensors, so that no
@@ -249,7 +259,13 @@ def main():
         g_flow = torch.randn(B, Tc, Tp, 2, Hd, Wd, device=dev, generator=gen)
         g_raw = torch.randn(B, Tc, Tp, C + L, Hd, Wd, device=dev, generator=gen)
 
+    graphed = wb.GraphedDecode(warper, om, bg, cfg.restrict_to_ctx) if (not backward and not args.no_graph) else None
+    use_graph = {"on": graphed is not None}
+
     def step(src):
+        if use_graph["on"]:   # inference: the whole chain replayed from one CUDA graph per set of input buffers
+            out = graphed(src["input"], src["obj_alpha_raw"], src["obj_pose"], src["bg_pose"], src["occ_score"], src["cls"], ctx_ts, pred_ts)
+            return out[0][:, :, :3].mean()
         lv = {k: src[k].detach().requires_grad_(backward and not (args.no_input_grad and k == "input")) for k in keys}
         with torch.set_grad_enabled(backward):
             occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, lv["obj_alpha_raw"], om, bg, lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
@@ -257,7 +273,7 @@ def main():
         if backward:
             torch.autograd.backward([out[0], out[1], out[5]], [g_output, g_flow, g_raw])
             if grad_buf is not None:
-                dist.all_reduce(grad_buf)
+                grad_buf.reduce()
         return out[0].detach()[:, :, :3].mean()   # the step's metric (mean predicted RGB), read back in the e2e leg
 
     def endless(batch):
@@ -285,22 +301,35 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) / steps
+        return sharding.max_over_ranks([e0.elapsed_time(e1)], device=dev)[0] / steps
 
     clocks = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         step(resident)
     clocks.wait_ready()
     # ---- device-resident timing, with the dominant kernels bracketed by events inside the timed region
-    Fn.PROFILE = {}
+    if not use_graph["on"]:
+        Fn.PROFILE = {}
     launches0 = lib.waldo_launch_count()
     clocks.mark_begin()
     ms_step = timed(lambda: step(resident), args.steps)
     clocks.mark_end()
     launches = lib.waldo_launch_count() - launches0
+    kernel_timing = "CUDA events around each kernel inside the timed region"
+    if use_graph["on"]:
+        # a replayed graph cannot be bracketed kernel by kernel: time the same kernels in an extra eager pass
+        with torch.no_grad():
+            launches1 = lib.waldo_launch_count()
+            occ_, oa_, ba_, grid_ = wb.estimate_alpha_grid_occ(warper, resident["obj_alpha_raw"], om, bg, resident["obj_pose"], resident["bg_pose"], resident["occ_score"])
+            wb.decode_output(warper, resident["input"], grid_, occ_, oa_, ba_, resident["cls"], ctx_ts, pred_ts, cfg.restrict_to_ctx)
+            per_step = lib.waldo_launch_count() - launches1   # kernels of this library in one chain = kernel nodes of the graph
+            Fn.PROFILE = {}
+            for _ in range(args.steps):
+                wb.decode_output(warper, resident["input"], grid_, occ_, oa_, ba_, resident["cls"], ctx_ts, pred_ts, cfg.restrict_to_ctx)
+            torch.cuda.synchronize()
+            del occ_, oa_, ba_, grid_
+        launches = args.steps * per_step
+        kernel_timing = "extra eager pass after the timed region (the timed region replays one CUDA graph per step)"
     prof = {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in Fn.PROFILE.items()}
     Fn.PROFILE = None
     # ---- end to end: pinned host -> device copies and the loss read-back inside the timed region
@@ -340,10 +369,12 @@ def main():
         except Exception:
             pass
         kern = {"k_gather_fwd": (prof.get("decode_fwd:gather", 0.0), kb["k_gather_fwd"]),
-                "k_layers_fwd": (prof.get("decode_fwd:layers", 0.0), kb["k_layers_fwd"])}
+                "k_layers_fwd": (prof.get("decode_fwd:layers", 0.0), kb["k_layers_fwd"]),
+                "k_alpha_prep": (prof.get("decode_fwd:alpha_prep", 0.0), kb["k_alpha_prep"])}
         if backward:
             kern["k_gather_bwd"] = (prof.get("decode_bwd:gather", 0.0), kb["k_gather_bwd"])
             kern["k_layers_bwd"] = (prof.get("decode_bwd:layers", 0.0), kb["k_layers_bwd"])
+            kern["k_alpha_prep_bwd"] = (prof.get("decode_bwd:alpha_prep", 0.0), kb["k_alpha_prep_bwd"])
         dom = max(kern, key=lambda k: kern[k][0])
         dms, dbytes = kern[dom]
         achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
@@ -352,7 +383,9 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": spec["label"], "per_gpu_batch": B, "contexts": Tc, "future_frames": Tp,
-                       "layers": cfg.num_obj + 1, "channels": 3 + cfg.num_lyt, "l2": "inputs larger than L2 (1.9 GB/step), no flush needed",
+                       "layers": cfg.num_obj + 1, "channels": 3 + cfg.num_lyt, "l2": "working set per step far larger than the 126 MB L2 (input %.2f GB), no flush needed" % (B * T * (3 + cfg.num_lyt) * Hd * Wd * 4 / 1e9),
+                       "input": "8-bit RGB + label map expanded to fp32 on the device (pack_input)",
+                       "launch": "one CUDA graph replay per step" if use_graph["on"] else "eager kernel launches (autograd)",
                        "parallelism": f"dp{world} batch-sharded" + (", flat fp32 all-reduce of 56.6 MB per step" if grad_buf is not None else "")},
             "clocks": clocks.summary(), "gpu_launches": launches,
             "hbm_frac_step": ((fwd_b + bwd_b) / (ms_step * 1e-3) / 1e9) / peak,
@@ -360,7 +393,7 @@ def main():
                          "traffic": traffic.get(dom), "ms_per_launch": dms, "alg_bytes_per_launch": dbytes, "peak_source": peak_src,
                          "other": {k: {"ms_per_launch": v[0], "alg_bytes_per_launch": v[1],
                                        "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None} for k, v in kern.items() if k != dom},
-                         "stages_ms": {k: round(v, 4) for k, v in prof.items()}},
+                         "stages_ms": {k: round(v, 4) for k, v in prof.items()}, "kernel_timing": kernel_timing},
         }
         if e2e:
             line["e2e"] = e2e

@@ -178,7 +178,7 @@ typedef struct {
   float* out_full;            /* (B, Tp, C+1, Hd, Wd): output | raw_alpha             lvd.py:851,147,152 */
   float* norm;                /* (B, Tp, Hd, Wd) sum_tc(score+eps), saved for backward */
   float* score;               /* (B, Tc, Tp, Hd, Wd) sum_k Actx_k per pair (lvd.py:841), glue between the two HD kernels */
-  int stages;                 /* 0 = everything; else bit 0 = low-res + context-alpha kernels (B1-B5),
+  int stages;                 /* 0 = everything; else bit 0 = low-res kernels (B1, B2, B5), bit 3 = HD context-alpha kernel (B2b-B4),
                                  bit 1 = HD layer kernel (B5up-B9), bit 2 = HD gather kernel (stage C) */
 } waldo_decode_fwd_t;
 int waldo_decode_fwd(const waldo_decode_fwd_t*, waldo_stream_t);
@@ -214,7 +214,8 @@ typedef struct {
   float* cls_part;            /* (B, prof_ctas, No*Nl) */
   float* up_tab;              /* scratch (W, 9): per low-res column, first HD column touching it and its 8 x-weights */
   float* glue;                /* scratch (B, Tc, Tp, 3, Hd, Wd): d score, d flow x, d flow y handed from the gather to the layer kernel */
-  int stages;                 /* 0 = everything; else bit 0 = HD gather backward, bit 1 = HD layer backward, bit 2 = the rest */
+  int stages;                 /* 0 = everything; else bit 0 = HD gather backward, bit 1 = HD layer backward,
+                                 bit 3 = HD context-alpha backward, bit 2 = the rest (low-res chain) */
 } waldo_decode_bwd_t;
 int waldo_decode_bwd(const waldo_decode_bwd_t*, waldo_stream_t);
 

@@ -15,6 +15,12 @@ benchq)
 launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_launches.log 2>&1; echo "launches rc=$?";;
+workloads)
+  for w in city_rollout kitti_rollout; do
+    timeout 600 python bench.py --workload $w --no-cpu-baseline > $OUT/${TAG}_bench_$w.jsonl 2> $OUT/${TAG}_bench_$w.err; echo "bench $w rc=$?"; cat $OUT/${TAG}_bench_$w.jsonl; tail -2 $OUT/${TAG}_bench_$w.err
+  done;;
+ref)
+  timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.jsonl 2> $OUT/${TAG}_bench_ref.err; echo "ref rc=$?"; cat $OUT/${TAG}_bench_ref.jsonl; tail -2 $OUT/${TAG}_bench_ref.err;;
 exp)
   timeout 1200 python scratch/exp.py $EXP_NAMES > $OUT/${TAG}_exp.log 2>&1; echo "exp rc=$?"; cat $OUT/${TAG}_exp.log;;
 fullk)

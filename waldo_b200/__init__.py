@@ -7,6 +7,7 @@ from .modules import (TPSWarp, InverseWarp, Warper, compute_occ, decode_output, 
                       wif_fuse, pack_input, get_grid, get_gaussian_kernel, kernel_distance)
 from . import functional
 from .feed import DevicePrefetcher
+from .graphs import GraphedDecode
 
 __all__ = ["TPSWarp", "InverseWarp", "Warper", "compute_occ", "decode_output", "estimate_alpha_grid_occ", "alpha_masks",
-           "wif_fuse", "pack_input", "get_grid", "get_gaussian_kernel", "kernel_distance", "functional", "DevicePrefetcher"]
+           "wif_fuse", "pack_input", "get_grid", "get_gaussian_kernel", "kernel_distance", "functional", "DevicePrefetcher", "GraphedDecode"]

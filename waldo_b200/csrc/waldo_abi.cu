@@ -174,6 +174,7 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   const int L = g.No + 1, HW = g.H * g.W;
   const long long HWd = (long long)g.Hd * g.Wd;
   const bool st_prep = a->stages == 0 || (a->stages & 1), st_layers = a->stages == 0 || (a->stages & 2), st_gather = a->stages == 0 || (a->stages & 4);
+  const bool st_aprep = a->stages == 0 || (a->stages & 8);
   if (st_prep) {
   // B1
   WB_LAUNCH(k_project_alpha, dim3(wb_blocks((long long)g.B * g.Tw * HW, 128)), dim3(128), 0, st, *a);
@@ -187,14 +188,16 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
     WB_LAUNCH(k_profile_final, dim3(g.B), dim3(352), 0, st, *a);
     WB_LAUNCHED();
   }
+  }
   // B2b-B4
-  {
+  if (st_aprep) {
     const dim3 pgrid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tw);
     if (g.Nl == 20) WB_LAUNCH(k_alpha_prep<20>, pgrid, dim3(WB_TILE_PX), 0, st, *a);        // Cityscapes
     else if (g.Nl == 19) WB_LAUNCH(k_alpha_prep<19>, pgrid, dim3(WB_TILE_PX), 0, st, *a);   // KITTI
     else WB_LAUNCH(k_alpha_prep<0>, pgrid, dim3(WB_TILE_PX), 0, st, *a);
+    WB_LAUNCHED();
   }
-  WB_LAUNCHED();
+  if (st_prep) {
   // B5
   WB_LAUNCH(k_layer_flow_lo, dim3(wb_blocks((long long)g.B * g.Tp * HW, 128)), dim3(128), 0, st, *a);
   WB_LAUNCHED();

@@ -91,7 +91,7 @@ extern long long g_wb_launches;
 #endif
 // resident CTAs per SM requested through __launch_bounds__ (register budget = 65536 / (256 * N)); tuned on B200
 #ifndef WB_OCC_LAYERS_FWD
-#define WB_OCC_LAYERS_FWD 3
+#define WB_OCC_LAYERS_FWD 4
 #endif
 #ifndef WB_OCC_PREP_FWD
 #define WB_OCC_PREP_FWD 3
@@ -107,6 +107,9 @@ extern long long g_wb_launches;
 #endif
 #ifndef WB_OCC_GATHER_BWD
 #define WB_OCC_GATHER_BWD 3
+#endif
+#ifndef WB_LANES_MAX_BWD
+#define WB_LANES_MAX_BWD 8   // rows with more live layers take the one-lane-per-pixel form
 #endif
 #ifndef WB_LANES_PREP_BWD
 #define WB_LANES_PREP_BWD 0

@@ -615,13 +615,15 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_BWD) k_layers_bwd(Wb
       if (a.d_f_lo && !c.lowres_direct)
         cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(px.ax.i0, 0), wb_shfl(px.ax.i1, WB_WARP - 1), px.ay);
 #if !defined(WB_HOST_EMU) && !defined(WB_NO_LANES)
-      if (n <= 8) {
+      if (n <= WB_LANES_MAX_BWD) {
         const bool rowact = Yr < g.Hd;
         const unsigned iso = px.isobj;
         if (n == 1) wb_lanes_layers_bwd<1>(a, c, cr, wm, n, iso, tx0, rowact, Y, px.ay, px.gy);
         else if (n == 2) wb_lanes_layers_bwd<2>(a, c, cr, wm, n, iso, tx0, rowact, Y, px.ay, px.gy);
         else if (n <= 4) wb_lanes_layers_bwd<4>(a, c, cr, wm, n, iso, tx0, rowact, Y, px.ay, px.gy);
+#if WB_LANES_MAX_BWD > 4
         else wb_lanes_layers_bwd<8>(a, c, cr, wm, n, iso, tx0, rowact, Y, px.ay, px.gy);
+#endif
         continue;
       }
 #endif
@@ -1327,6 +1329,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     WB_BLAUNCHED();
   }
   const bool st_gather = a.stages == 0 || (a.stages & 1), st_layers = a.stages == 0 || (a.stages & 2), st_rest = a.stages == 0 || (a.stages & 4);
+  const bool st_aprep = a.stages == 0 || (a.stages & 8);
   const bool need_layers = a.d_alpha_acc || a.d_f_lo || a.d_occ;
   if (need_layers) WB_BREQ(a.glue && d.score, "glue / score buffers missing");
   // 1. HD gather backward
@@ -1348,9 +1351,9 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
       WB_BLAUNCHED();
     }
   }
-  if (!need_alpha_chain || !st_rest) return 0;
+  if (!need_alpha_chain || !(st_rest || st_aprep)) return 0;
   // 2. context-alpha backward
-  if (a.d_alpha_acc || a.d_alpha) {
+  if (st_aprep && (a.d_alpha_acc || a.d_alpha)) {
     if (filt && a.d_prof_p) WB_BREQ(a.prof_p_part, "prof_p_part scratch missing");
     const dim3 pgrid(a.red_ctas, g.B * g.Tw);
     const size_t dyn = (size_t)WB_NWARP * WB_MAX_NL * 32 * sizeof(float);
@@ -1368,6 +1371,9 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tw), dim3(128), 0, st, a.occ_part, g.B * g.Tw, g.Tw, a.red_ctas, L * L, g.T, d.pred_ts, 1, a.d_occ);
       WB_BLAUNCHED();
     }
+  }
+  if (!st_rest) return 0;
+  if (a.d_alpha_acc || a.d_alpha) {
     if (filt && a.d_prof_p) {
       WB_BREQ(a.d_prof_sum, "d_prof_sum scratch missing");
       WB_LAUNCH(k_profile_final_bwd, dim3(g.B), dim3(352), 0, st, a);

@@ -208,8 +208,11 @@ def _staged(fn, arg, stream, what, dev):
     if PROFILE is None:
         L.check(fn(C.byref(arg), stream), what)
         return
-    # forward: prep (1), layers (2), gather (4); backward: gather (1), layers (2), rest (4) -- same order as stages = 0
-    for bit, key in ((1, "prep" if what == "decode_fwd" else "gather"), (2, "layers"), (4, "gather" if what == "decode_fwd" else "rest")):
+    # forward: low-res prep (1), context alpha (8), layers (2), gather (4); backward: gather (1), layers (2), context alpha (8),
+    # rest (4) -- kernels in the same dependency order as with stages = 0
+    order = (((1, "prep"), (8, "alpha_prep"), (2, "layers"), (4, "gather")) if what == "decode_fwd" else
+             ((1, "gather"), (2, "layers"), (8, "alpha_prep"), (4, "rest")))
+    for bit, key in order:
         arg.stages = bit
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(dev))
