@@ -109,6 +109,7 @@ int waldo_invwarp_bwd(const waldo_invwarp_bwd_t* a, waldo_stream_t st) {
              "invwarp_bwd: null pointer");
   if (a->n == 0) return 0;
   WB_REQUIRE(a->bbox, "invwarp_bwd: null bbox");
+  WB_REQUIRE(a->Wt <= 8 * a->Ws, "invwarp_bwd: target lattice more than 8x wider than the source lattice");
   WbInvBwdArgs k = {a->n, a->Hs, a->Ws, a->Ht, a->Wt, a->niter, a->gauss, a->dout, a->field, a->winner, a->level, a->eroded,
                     a->bbox, a->gval, a->inv_sw, a->gdisp, a->dfwd_grid};
   const int m = a->niter + 1, PP = (a->Ht + 2 * m) * (a->Wt + 2 * m), P = a->Ht * a->Wt;
@@ -211,6 +212,13 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   // stage C: the gather kernel
   if (st_gather) {
     const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+#if !defined(WB_HOST_EMU) && WB_GF_ASYNC
+    if (g.Tc == 4 && !self) {
+      const size_t ring = (size_t)WB_GF_DEPTH * 16 * WB_TILE_PX * sizeof(float);
+      cudaFuncSetAttribute(k_gather_fwd_async, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);   // >= 48 KB: opt in
+      WB_LAUNCH(k_gather_fwd_async, grid, dim3(WB_TILE_PX), ring, st, *a);
+    } else
+#endif
     if (g.Tc == 4 && !self) WB_LAUNCH((k_gather_fwd<4, true>), grid, dim3(WB_TILE_PX), 0, st, *a);
     else if (g.Tc <= 4) WB_LAUNCH((k_gather_fwd<4, false>), grid, dim3(WB_TILE_PX), 0, st, *a);
     else WB_LAUNCH((k_gather_fwd<8, false>), grid, dim3(WB_TILE_PX), 0, st, *a);

@@ -58,6 +58,7 @@ extern long long g_wb_launches;
 #define WB_CHECK_LAUNCH() 0
 #define WB_UNROLL
 #define WB_UNROLL_N(n)
+#define WB_UNROLL_NA_LD
 #define WB_UNROLL_NA
 static thread_local float wb_dyn_smem_buf[96 * 1024];
 #define WB_DYN_SMEM(name) float* name = wb_dyn_smem_buf
@@ -70,10 +71,17 @@ extern long long g_wb_launches;
 #define WB_CHECK_LAUNCH() wb_check_launch(__FILE__, __LINE__)
 #define WB_UNROLL _Pragma("unroll")
 #define WB_PRAGMA_(x) _Pragma(#x)
+#define WB_PRAGMA(x) WB_PRAGMA_(x)
 #define WB_UNROLL_N(n) WB_PRAGMA_(unroll n)
 // loops over the NA layer slots of a template: fully unrolled (register arrays) for the sparse instantiations,
 // rolled (local-memory arrays, small code, few registers) for the rare dense one
 #define WB_UNROLL_NA _Pragma("unroll (NA <= 8 ? NA : 1)")
+// the same for slot loops whose bodies are dominated by independent loads: the rolled form is unrolled by WB_SLOT_UNROLL so
+// that the loads of consecutive slots are in flight together
+#ifndef WB_SLOT_UNROLL
+#define WB_SLOT_UNROLL 4
+#endif
+#define WB_UNROLL_NA_LD WB_PRAGMA(unroll (NA <= 8 ? NA : WB_SLOT_UNROLL))
 #define WB_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
 #endif
 
@@ -115,6 +123,18 @@ extern long long g_wb_launches;
 #define WB_LANES_PREP_BWD 0
 #endif
 // k_gather_bwd: contexts processed together and channel-loop unrolling (B200 A/B runs, profiles/)
+#ifndef WB_GB_ASYNC
+#define WB_GB_ASYNC 1   // cp.async operand pipeline in the FAST gather backward (3.15 -> 2.18 ms together with explicit REDG)
+#endif
+#ifndef WB_GB_MERGE
+#define WB_GB_MERGE 1   // neighbouring lanes merge coinciding taps before the global reductions
+#endif
+#ifndef WB_GF_ASYNC
+#define WB_GF_ASYNC 1   // cp.async operand pipeline in the FAST gather forward
+#endif
+#ifndef WB_GF_DEPTH
+#define WB_GF_DEPTH 3
+#endif
 #ifndef WB_GB_TG
 #define WB_GB_TG 2
 #endif
@@ -176,7 +196,35 @@ WB_DEV double wb_warp_sum(double v) {
   return v;
 }
 
+// Fire-and-forget float reduction into GLOBAL memory.  Spelled as PTX on purpose: `atomicAdd` on a pointer whose address
+// space the compiler cannot prove (e.g. one read back from a shared-memory pointer table) compiles to the GENERIC form --
+// a predicated ATOM plus shared-memory and generic CAS loops behind ISSPACEP branches -- instead of one REDG.
+WB_DEV void wb_red(float* p, float v) {
+#ifdef WB_HOST_EMU
+  *p += v;
+#else
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v));   // no "memory" clobber: it would pin every load behind it
+#endif
+}
+
+// plain store to GLOBAL memory through a pointer of unproven address space (same reason as wb_red: STG, not generic ST)
+WB_DEV void wb_stg(float* p, float v) {
+#ifdef WB_HOST_EMU
+  *p = v;
+#else
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v));
+#endif
+}
+
 #ifndef WB_HOST_EMU
+// asynchronous 4-byte copies global -> shared (LDGSTS): operands in flight without holding registers
+WB_DEV void wb_cp4(float* smem_dst, const float* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+WB_DEV void wb_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> WB_DEV void wb_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // position of the nth (0-based) set bit of m  (lanes-per-layer kernels: layer of a slot)
 WB_DEV int wb_nth_bit(unsigned m, int nth) { return (int)__fns(m, 0, nth + 1); }
 #endif

@@ -17,7 +17,7 @@ typedef waldo_decode_bwd_t WbDecB;
 
 #define WB_NWARP (WB_TILE_PX / 32)
 
-WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) atomicAdd(p, v); }
+WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) wb_red(p, v); }
 
 // ---------------------------------------------------------------------------- transpose of the bilinear up-sampling
 // A warp is one row of 32 HD pixels, so all its lanes share the two low-res rows and touch a short run of low-res
@@ -100,8 +100,8 @@ WB_DEV void wb_colred_flush(const WbColRed& cr, const float* s_stage, int nv, fl
         float acc = 0.f;
         WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) acc += cr.w[cpl][t] * sv[t];
         if (acc != 0.f) {
-          atomicAdd(dst[v] + ((size_t)cr.row0 * W + cr.col[cpl]) * stride, acc * cr.wy0);
-          atomicAdd(dst[v] + ((size_t)cr.row1 * W + cr.col[cpl]) * stride, acc * cr.wy1);
+          wb_red(dst[v] + ((size_t)cr.row0 * W + cr.col[cpl]) * stride, acc * cr.wy0);
+          wb_red(dst[v] + ((size_t)cr.row1 * W + cr.col[cpl]) * stride, acc * cr.wy1);
         }
       }
     }
@@ -297,8 +297,8 @@ WB_DEV void wb_colred_flush_slots(const WbColRed& cr, const float* s_stage, unsi
       WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) acc += cr.w[0][t] * sv[t];
       if (acc != 0.f) {
         float* dst = base + (size_t)k * layer_stride + comp;
-        atomicAdd(dst + ((size_t)cr.row0 * W + cr.col[0]) * stride, acc * cr.wy0);
-        atomicAdd(dst + ((size_t)cr.row1 * W + cr.col[0]) * stride, acc * cr.wy1);
+        wb_red(dst + ((size_t)cr.row0 * W + cr.col[0]) * stride, acc * cr.wy0);
+        wb_red(dst + ((size_t)cr.row1 * W + cr.col[0]) * stride, acc * cr.wy1);
       }
     }
   }
@@ -505,6 +505,23 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd(Wb
             nrm[i] = (__ldg(d.score + pair * HWd + q) + 1e-6f) / D;
           }
         }
+        // Neighbouring pixels of a row mostly hit neighbouring source cells: where lane l+1's left taps are lane l's right
+        // taps (o[l+1] == o[l] + 1), lane l hands its right-tap contributions to lane l+1 (one shuffle each) instead of
+        // issuing its own reductions -- about half of the global reductions in smooth-flow regions.
+        bool skipR0[TG], skipR1[TG], mergeL0[TG], mergeL1[TG];
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          skipR0[i] = skipR1[i] = mergeL0[i] = mergeL1[i] = false;
+#if !defined(WB_HOST_EMU) && WB_GB_MERGE
+          if (FAST) {
+            const int lane = wb_lane();
+            const unsigned n0 = __shfl_down_sync(0xffffffffu, o0[i], 1), n1 = __shfl_down_sync(0xffffffffu, o1[i], 1);
+            skipR0[i] = lane < 31 && n0 == o0[i] + 1u;
+            skipR1[i] = lane < 31 && n1 == o1[i] + 1u;
+            mergeL0[i] = __shfl_up_sync(0xffffffffu, (int)skipR0[i], 1) != 0 && lane > 0;
+            mergeL1[i] = __shfl_up_sync(0xffffffffu, (int)skipR1[i], 1) != 0 && lane > 0;
+          }
+#endif
+        }
         const bool first = tc0 == 0;
         float* dself = (first && self && has_din) ? a.d_input + ((size_t)b * g.T + tp) * C * HWd + q : nullptr;
         const float* drself = (self && has_draw) ? a.d_raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q : nullptr;
@@ -531,8 +548,20 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd(Wb
               WB_UNROLL for (int j = 0; j < 4; ++j) { U[i][j] += gO * v[i][j]; Tq[i][j] += gdt * v[i][j]; }
               if (has_din) {
                 float* dl = s_dsrc[tc0 + i] + choff;
-                atomicAdd(dl + o0[i], w[i][0] * go); atomicAdd(dl + o0[i] + 1, w[i][1] * go);
-                atomicAdd(dl + o1[i], w[i][2] * go); atomicAdd(dl + o1[i] + 1, w[i][3] * go);
+#if !defined(WB_HOST_EMU) && WB_GB_MERGE
+                if (FAST) {
+                  const float c1 = w[i][1] * go, c3 = w[i][3] * go;
+                  const float r1 = __shfl_up_sync(0xffffffffu, c1, 1), r3 = __shfl_up_sync(0xffffffffu, c3, 1);
+                  wb_red(dl + o0[i], w[i][0] * go + (mergeL0[i] ? r1 : 0.f));
+                  if (!skipR0[i]) wb_red(dl + o0[i] + 1, c1);
+                  wb_red(dl + o1[i], w[i][2] * go + (mergeL1[i] ? r3 : 0.f));
+                  if (!skipR1[i]) wb_red(dl + o1[i] + 1, c3);
+                } else
+#endif
+                {
+                  wb_red(dl + o0[i], w[i][0] * go); wb_red(dl + o0[i] + 1, w[i][1] * go);
+                  wb_red(dl + o1[i], w[i][2] * go); wb_red(dl + o1[i] + 1, w[i][3] * go);
+                }
               }
             }
           }
@@ -573,6 +602,157 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd(Wb
     }
   }
 }
+
+#ifndef WB_HOST_EMU
+// ------------------------------------------------------------------------------------------------------------------
+// k_gather_bwd with an asynchronous-copy pipeline (the FAST case only).  Every load of the channel loop has an address
+// that is known before the loop starts (fixed taps + ch * HWd), so the kernel is limited by how many loads a thread
+// keeps in flight, i.e. by registers.  cp.async (LDGSTS) moves each thread's operands of the next WB_GB_DEPTH - 1
+// channels into its own shared-memory slots without holding registers: (5 TG + 2) x (DEPTH - 1) loads in flight per
+// thread instead of the ~12 the register file allows.  A thread only ever reads its own slots: no barrier, just
+// cp.async.wait_group.
+
+#ifndef WB_GB_DEPTH
+#define WB_GB_DEPTH 4
+#endif
+
+template <int TG>
+__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd_async(WbDecB a) {
+  constexpr int NF = 5 * TG + 2;            // per channel: TG x (4 taps + d raw) + d out + out
+  constexpr int DEPTH = WB_GB_DEPTH;
+  const WbDec& d = a.f;
+  const waldo_geom_t g = d.g;
+  const int C = g.C, L = g.No + 1;
+  const unsigned HWd = (unsigned)(g.Hd * g.Wd);
+  const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
+  const int CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
+  extern __shared__ __align__(16) float s_ring[];   // [DEPTH][NF][WB_TILE_PX]
+  __shared__ const float* s_src[8];
+  __shared__ float* s_dsrc[8];
+  __shared__ const float* s_draw[8];
+  for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
+    s_dsrc[tc] = a.d_input + ((size_t)b * g.T + c_t) * C * HWd;
+    s_draw[tc] = a.d_raw_output + (((size_t)b * g.Tc + tc) * g.Tp + tp) * CR * HWd;
+  }
+  __syncthreads();
+  float* my = s_ring + wb_tid();
+  const WbTileIter ti(g.Hd, g.Wd);
+  for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
+    const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
+    const int it = wb_tid();
+    const int Xr = tx0 + (it & (WB_TILE_W - 1)), Yr = ty0 + it / WB_TILE_W;
+    const bool active = Xr < g.Wd && Yr < g.Hd;
+    const float actf = active ? 1.f : 0.f;
+    const int X = min(Xr, g.Wd - 1), Y = min(Yr, g.Hd - 1);
+    const unsigned q = (unsigned)(Y * g.Wd + X);
+    const float gx = __ldg(d.xs_hd + X), gy = __ldg(d.ys_hd + Y);
+    const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
+    const float* dof = a.d_output + ((size_t)b * g.Tp + tp) * C * HWd + q;
+    const float* dra = a.d_raw_alpha ? a.d_raw_alpha + ((size_t)b * g.Tp + tp) * HWd + q : nullptr;
+    const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+    float S = 0.f;
+    for (int tc0 = 0; tc0 < g.Tc; tc0 += TG) {
+      unsigned o0[TG], o1[TG];
+      float w[TG][4], nrm[TG], U[TG][4], Tq[TG][4];
+      const float* src[TG];
+      const float* drw[TG];
+      float* dsr[TG];
+      WB_UNROLL for (int i = 0; i < TG; ++i) {
+        WB_UNROLL for (int j = 0; j < 4; ++j) { U[i][j] = 0.f; Tq[i][j] = 0.f; }
+        const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
+        const float* fl = d.flow + pair * 2 * HWd + q;
+        const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        o0[i] = t2.o0; o1[i] = t2.o1;
+        WB_UNROLL for (int j = 0; j < 4; ++j) w[i][j] = t2.w[j];
+        nrm[i] = (__ldg(d.score + pair * HWd + q) + 1e-6f) / D;
+        src[i] = s_src[tc0 + i]; drw[i] = s_draw[tc0 + i] + q; dsr[i] = s_dsrc[tc0 + i];
+      }
+      bool skipR0[TG], skipR1[TG], mergeL0[TG], mergeL1[TG];   // see k_gather_bwd
+      WB_UNROLL for (int i = 0; i < TG; ++i) {
+        const int lane = wb_lane();
+        const unsigned n0 = __shfl_down_sync(0xffffffffu, o0[i], 1), n1 = __shfl_down_sync(0xffffffffu, o1[i], 1);
+        skipR0[i] = WB_GB_MERGE && lane < 31 && n0 == o0[i] + 1u;
+        skipR1[i] = WB_GB_MERGE && lane < 31 && n1 == o1[i] + 1u;
+        mergeL0[i] = __shfl_up_sync(0xffffffffu, (int)skipR0[i], 1) != 0 && lane > 0;
+        mergeL1[i] = __shfl_up_sync(0xffffffffu, (int)skipR1[i], 1) != 0 && lane > 0;
+      }
+      const bool first = tc0 == 0;
+      // stage `ch` -> ring slot ch % DEPTH
+#define WB_GB_ISSUE(ch_)                                                                          \
+      do {                                                                                          \
+        const unsigned off_ = (unsigned)(ch_) * HWd;                                                \
+        float* base_ = my + ((ch_) % DEPTH) * NF * WB_TILE_PX;                                      \
+        WB_UNROLL for (int i = 0; i < TG; ++i) {                                                    \
+          const float* p0_ = src[i] + off_ + o0[i];                                                 \
+          const float* p1_ = src[i] + off_ + o1[i];                                                 \
+          wb_cp4(base_ + (5 * i + 0) * WB_TILE_PX, p0_); wb_cp4(base_ + (5 * i + 1) * WB_TILE_PX, p0_ + 1); \
+          wb_cp4(base_ + (5 * i + 2) * WB_TILE_PX, p1_); wb_cp4(base_ + (5 * i + 3) * WB_TILE_PX, p1_ + 1); \
+          wb_cp4(base_ + (5 * i + 4) * WB_TILE_PX, drw[i] + off_);                                  \
+        }                                                                                           \
+        wb_cp4(base_ + (5 * TG) * WB_TILE_PX, dof + off_);                                          \
+        if (first) wb_cp4(base_ + (5 * TG + 1) * WB_TILE_PX, of + off_);                            \
+      } while (0)
+      WB_UNROLL for (int ch = 0; ch < DEPTH - 1; ++ch) { if (ch < C) WB_GB_ISSUE(ch); wb_cp_commit(); }
+      unsigned choff = 0u;
+#pragma unroll 1
+      for (int ch = 0; ch < C; ++ch) {
+        if (ch + DEPTH - 1 < C) WB_GB_ISSUE(ch + DEPTH - 1);
+        wb_cp_commit();
+        wb_cp_wait<DEPTH - 1>();
+        const float* base = my + (ch % DEPTH) * NF * WB_TILE_PX;
+        const float gO = actf * base[(5 * TG) * WB_TILE_PX];
+        if (first) S += gO * base[(5 * TG + 1) * WB_TILE_PX];
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          const float v0 = base[(5 * i + 0) * WB_TILE_PX], v1 = base[(5 * i + 1) * WB_TILE_PX];
+          const float v2 = base[(5 * i + 2) * WB_TILE_PX], v3 = base[(5 * i + 3) * WB_TILE_PX];
+          const float gdt = actf * base[(5 * i + 4) * WB_TILE_PX];
+          const float go = gdt + nrm[i] * gO;
+          U[i][0] += gO * v0; U[i][1] += gO * v1; U[i][2] += gO * v2; U[i][3] += gO * v3;
+          Tq[i][0] += gdt * v0; Tq[i][1] += gdt * v1; Tq[i][2] += gdt * v2; Tq[i][3] += gdt * v3;
+          float* dl = dsr[i] + choff;
+          const float c1 = w[i][1] * go, c3 = w[i][3] * go;
+          const float r1 = __shfl_up_sync(0xffffffffu, c1, 1), r3 = __shfl_up_sync(0xffffffffu, c3, 1);
+          wb_red(dl + o0[i], w[i][0] * go + (mergeL0[i] ? r1 : 0.f));
+          if (!skipR0[i]) wb_red(dl + o0[i] + 1, c1);
+          wb_red(dl + o1[i], w[i][2] * go + (mergeL1[i] ? r3 : 0.f));
+          if (!skipR1[i]) wb_red(dl + o1[i] + 1, c3);
+        }
+        choff += HWd;
+      }
+#undef WB_GB_ISSUE
+      wb_cp_wait<0>();
+      if (!a.glue || !active) continue;
+      const float gOs = dra ? __ldg(dra) : 0.f;
+      if (first && dra) S += gOs * __ldg(of + choff);
+      WB_UNROLL for (int i = 0; i < TG; ++i) {
+        const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
+        const float* fl = d.flow + pair * 2 * HWd + q;
+        const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        float cx[4], cy[4];
+        wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
+        wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
+        const float sc = nrm[i] * D - 1e-6f;
+        float G = U[i][0] * w[i][0] + U[i][1] * w[i][1] + U[i][2] * w[i][2] + U[i][3] * w[i][3];
+        float gix = 0.f, giy = 0.f;
+        WB_UNROLL for (int j = 0; j < 4; ++j) {
+          const float tj = Tq[i][j] + nrm[i] * U[i][j];
+          gix += tj * cx[j]; giy += tj * cy[j];
+        }
+        G += gOs * (sc * 2.f - 1.f);
+        const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
+        float* gl = a.glue + pair * 3 * HWd + q;
+        gl[0] = 2.f * nrm[i] * gOs + (G - S) / D;
+        gl[HWd] = (dfl ? __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+        gl[2 * HWd] = (dfl ? __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
+      }
+    }
+  }
+}
+#endif  // !WB_HOST_EMU
 
 // grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration), rolled loop over the contexts.
 __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_BWD) k_layers_bwd(WbDecB a) {
@@ -697,7 +877,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   float sm[NN];
   if (c.filt && any_obj) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
   float aup[NA], av[NA], ell[NA];
-  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
+  WB_UNROLL_NA_LD for (int s = 0; s < WB_NEND; ++s) {
     av[s] = 0.f; aup[s] = 0.f; ell[s] = 1.f;
     if (s < ix.n) {
       const int k = ix.k[s];
@@ -716,7 +896,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   }
   // ---- upstream: scatter-accumulated d/dA plus the returned alpha = 2A - 1 (zero beyond the image edge)
   float gA[NA], ga[NA];
-  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
+  WB_UNROLL_NA_LD for (int s = 0; s < WB_NEND; ++s) {
     ga[s] = 0.f; gA[s] = 0.f;
     if (s < ix.n) {
       const size_t o = (((size_t)b * g.Tw + t) * L + ix.k[s]) * HWd + q;
@@ -792,7 +972,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
     WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dot += gsm[cc] * sm[cc];
     float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd + q;
     WB_UNROLL for (int cc = 0; cc < NN; ++cc)
-      if (NLC > 0 || cc < Nl) { atomicAdd(o, sm[cc] * (gsm[cc] - dot)); o += HWd; }   // fire-and-forget reduction
+      if (NLC > 0 || cc < Nl) { wb_red(o, sm[cc] * (gsm[cc] - dot)); o += HWd; }   // fire-and-forget reduction
   }
 }
 
@@ -944,7 +1124,7 @@ WB_DEV void wb_lanes_prep_bwd(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
         if (actf != 0.f) {
           float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3 + cbase) * HWd + q;
           WB_UNROLL for (int i = 0; i < NS; ++i) {
-            if (cbase + i < Nl) atomicAdd(o, smc[i] * (v[i] - dot));   // fire-and-forget reduction
+            if (cbase + i < Nl) wb_red(o, smc[i] * (v[i] - dot));   // fire-and-forget reduction
             o += HWd;
           }
         }
@@ -1338,7 +1518,15 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     if (!need_layers) ag.glue = nullptr;
     const dim3 ggrid(wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX) > 1024 ? 1024 : wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX), g.B * g.Tp);
     const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
-    if (g.Tc % WB_GB_TG == 0 && !self && a.d_input && a.d_raw_output && a.d_output) WB_LAUNCH((k_gather_bwd<WB_GB_TG, true>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
+    const bool fast = g.Tc % WB_GB_TG == 0 && !self && a.d_input && a.d_raw_output && a.d_output;
+#if !defined(WB_HOST_EMU) && WB_GB_ASYNC
+    if (fast) {
+      const size_t ring = (size_t)WB_GB_DEPTH * (5 * WB_GB_TG + 2) * WB_TILE_PX * sizeof(float);
+      cudaFuncSetAttribute(k_gather_bwd_async<WB_GB_TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);   // > 48 KB: opt in
+      WB_LAUNCH((k_gather_bwd_async<WB_GB_TG>), ggrid, dim3(WB_TILE_PX), ring, st, ag);
+    } else
+#endif
+    if (fast) WB_LAUNCH((k_gather_bwd<WB_GB_TG, true>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
     else WB_LAUNCH((k_gather_bwd<2, false>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
     WB_BLAUNCHED();
   }
