@@ -259,7 +259,7 @@ def main():
         g_flow = torch.randn(B, Tc, Tp, 2, Hd, Wd, device=dev, generator=gen)
         g_raw = torch.randn(B, Tc, Tp, C + L, Hd, Wd, device=dev, generator=gen)
 
-    graphed = wb.GraphedDecode(warper, om, bg, cfg.restrict_to_ctx) if (not backward and not args.no_graph) else None
+    graphed = wb.GraphedDecode(warper, om, bg, cfg.restrict_to_ctx, max_graphs=8) if (not backward and not args.no_graph) else None
     use_graph = {"on": graphed is not None}
 
     def step(src):
@@ -338,7 +338,8 @@ def main():
         nbytes = lambda d: sum(t.numel() * t.element_size() for t in d.values())
         # (a) 8-bit frames + labels over PCIe, expanded on the device (the shipped input pipeline)
         feeder["it"] = wb.DevicePrefetcher(endless(pinned), dev, num_lyt=cfg.num_lyt)
-        e2e_step()
+        for _ in range(3):   # every prefetch slot has been seen once (graph replay captures one graph per slot)
+            e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
         e2e = {"value": world * B * Tp / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": nbytes(pinned), "d2h_bytes_per_step": 4,
@@ -348,7 +349,8 @@ def main():
         pinned32 = {k: pinned[k] for k in small}
         pinned32["input"] = resident["input"].cpu().pin_memory()
         feeder["it"] = wb.DevicePrefetcher(endless(pinned32), dev)
-        e2e_step()
+        for _ in range(3):
+            e2e_step()
         ms32 = timed(e2e_step, args.steps)
         e2e["fp32_input"] = {"value": world * B * Tp / (ms32 * 1e-3), "ms_per_step": ms32, "h2d_bytes_per_step": nbytes(pinned32)}
         feeder["it"] = None

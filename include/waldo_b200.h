@@ -239,6 +239,31 @@ typedef struct {
 } waldo_wif_fuse_bwd_t;
 int waldo_wif_fuse_bwd(const waldo_wif_fuse_bwd_t*, waldo_stream_t);
 
+/* ------------------------------------------------------------------ a-5 / a-11  stand-alone field warp and `scale`
+ * Warper.obj_to_output / bg_to_output, models/nets/lvd.py:538-559: out = grid_sample(field + delta, grid) - delta
+ * (bilinear, zeros, align_corners=False).  With `scale` (lvd.py:175-179) they make up the MAT propagation flows
+ * grid_to_{bg,obj}_flow_from_{ref_to_pred,ctx_to_ref} (lvd.py:575-600).  Forward only (inference helpers; inside
+ * decode_output the same steps are fused into waldo_decode_fwd/bwd). */
+typedef struct {
+  int n;                      /* items */
+  int c;                      /* channels per item */
+  int h, w;                   /* lattice of the field (canonical frame) */
+  int H, W;                   /* lattice of the grid / output (image) */
+  float delta;                /* lvd.py:548,559 */
+  const float* field;         /* (n, c, h, w) */
+  const float* grid;          /* (n, H, W, 2) */
+  float* out;                 /* out (n, c, H, W) */
+} waldo_warp_field_t;
+int waldo_warp_field_fwd(const waldo_warp_field_t*, waldo_stream_t);
+
+typedef struct {
+  int n;                      /* planes */
+  int h, w, H, W;             /* in / out sizes */
+  const float* in;            /* (n, h, w) */
+  float* out;                 /* out (n, H, W) */
+} waldo_resize_t;
+int waldo_resize_bilinear_fwd(const waldo_resize_t*, waldo_stream_t);
+
 /* ------------------------------------------------------------------ f-3  input packing (caller side of the path)
  * data/base_dataset.py:173-183 (label map -> one-hot -> 5*(2x-1)), :355-372 (ToTensor, Normalize(0.5,0.5)) and
  * models/synthesizer.py:444 (input = cat([vid, lyt], dim=2)), done on the device so that only 8-bit planes cross PCIe. */

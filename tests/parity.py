@@ -379,3 +379,54 @@ def check_pack_input(dev, B=2, T=3, Hd=12, Wd=20, num_lyt=20, seed=5):
     ramp = torch.arange(256, dtype=torch.uint8).view(1, 1, 1, 16, 16).expand(1, 1, 3, 16, 16).contiguous()
     lab = torch.zeros(1, 1, 16, 16, dtype=torch.uint8)
     assert torch.equal(wb.pack_input(ramp.to(dev), lab.to(dev), 2).cpu()[:, :, :3], reference_pack(ramp, lab, 2)[:, :, :3])
+
+
+# ------------------------------------------------------------------------------------------------ a-5 / a-11
+def check_field_warps(dev, case):
+    """Stand-alone obj/bg/layer_to_output (lvd.py:533-559) and the MAT propagation flows (lvd.py:575-600) against the same
+    steps written with the oracle's grid_sample / interpolate wrappers, on the reference's own grids."""
+    cfg, (B, T, Tc), z = load_case(case)
+    opt = make_opt(cfg)
+    warper = wb.Warper(opt).to(dev)
+    grid = tuple(z[k] for k in ("tgt_grid_obj", "src_grid_obj", "tgt_grid_bg", "src_grid_bg"))
+    gdev = tuple(g.to(dev) for g in grid)
+    tgo, sgo, tgb, sgb = grid
+    No = sgo.shape[2]
+    Ho, Wo = cfg.obj_hw
+    H, W = cfg.lo_shape
+    gen = torch.Generator().manual_seed(21)
+    obj = torch.randn(B, No, 3, Ho, Wo, generator=gen)
+    bg = torch.randn(B, T, 2, H, W, generator=gen)
+    # a-5, both deltas (delta = 1: out-of-range taps read as -1)
+    for delta in (1, 0):
+        want_o = wo.bil0(obj.unsqueeze(1).expand(-1, T, -1, -1, -1, -1).reshape(B * T * No, 3, Ho, Wo) + delta,
+                         sgo.reshape(B * T * No, H, W, 2)).view(B, T, No, 3, H, W) - delta
+        got_o = warper.obj_to_output(obj.to(dev), gdev, delta).cpu()
+        assert float((got_o - want_o).abs().max()) <= FWD_TOL, f"obj_to_output delta={delta}"
+        want_b = wo.bil0(bg.reshape(B * T, 2, H, W) + delta, sgb.reshape(B * T, H, W, 2)).view(B, T, 1, 2, H, W) - delta
+        got_b = warper.bg_to_output(bg.to(dev), gdev, delta).cpu()
+        assert float((got_b - want_b).abs().max()) <= FWD_TOL, f"bg_to_output delta={delta}"
+    lay = warper.layer_to_output(obj[:, :, :2].to(dev), bg.to(dev), gdev, 0, 0).cpu()
+    assert tuple(lay.shape) == (B, T, No + 1, 2, H, W)
+    # a-11
+    ctx_len, ref, obj_id = Tc, Tc - 1, min(1, No - 1)
+    s = cfg.scale_hd
+
+    def want_flow(diff, g):   # diff (B,t,h,w,2) in a canonical frame, g (B,t,H,W,2)
+        b_, t_ = diff.shape[:2]
+        f = wo.bil0(diff.permute(0, 1, 4, 2, 3).reshape(b_ * t_, 2, *diff.shape[2:4]), g.reshape(b_ * t_, H, W, 2))
+        return wo.resize(f, s).view(b_, t_, 2, int(H * s), int(W * s)).permute(0, 1, 3, 4, 2)
+
+    got = warper.grid_to_bg_flow_from_ref_to_pred(gdev, ctx_len, ref).cpu()
+    assert float((got - want_flow(tgb[:, [ref]] - tgb[:, ctx_len:], sgb[:, ctx_len:])).abs().max()) <= FWD_TOL
+    got = warper.grid_to_bg_flow_from_ctx_to_ref(gdev, ctx_len, ref).cpu()
+    assert float((got - want_flow(tgb[:, :ctx_len] - tgb[:, [ref]], sgb[:, [ref]].repeat(1, ctx_len, 1, 1, 1))).abs().max()) <= FWD_TOL
+    got = warper.grid_to_obj_flow_from_ref_to_pred(gdev, ctx_len, ref, obj_id).cpu()
+    want = want_flow(tgo[:, [ref], obj_id] - tgo[:, ctx_len:, obj_id], sgo[:, ctx_len:, obj_id])
+    assert float((got - want).abs().max()) <= FWD_TOL
+    # forward-only helpers refuse to silently drop a gradient
+    try:
+        warper.bg_to_output(bg.to(dev).requires_grad_(True), gdev, 0)
+        raise AssertionError("expected NotImplementedError")
+    except NotImplementedError:
+        pass

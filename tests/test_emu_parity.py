@@ -52,3 +52,8 @@ def test_kats():
 
 def test_pack_input():
     parity.check_pack_input(DEV)
+
+
+@pytest.mark.parametrize("case", ["city_x4", "kitti_x2", "train_lo"])
+def test_field_warps(case):
+    parity.check_field_warps(DEV, case)

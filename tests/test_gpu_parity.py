@@ -117,3 +117,8 @@ def test_graphed_decode_matches_eager(dev):
             if a is not None:
                 assert torch.equal(a, b)
     assert len(gd.cache) == 1
+
+
+@pytest.mark.parametrize("case", ["city_x4", "kitti_x2", "train_lo"])
+def test_field_warps(dev, case):
+    parity.check_field_warps(dev, case)

@@ -89,6 +89,15 @@ class WifFuseBwd(C.Structure):
     _fields_ = [("f", WifFuseFwd), ("d_frame", c_void_p), ("d_raw_output", c_void_p), ("d_unet_out", c_void_p)]
 
 
+class WarpField(C.Structure):
+    _fields_ = [("n", C.c_int), ("c", C.c_int), ("h", C.c_int), ("w", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("delta", C.c_float), ("field", c_void_p), ("grid", c_void_p), ("out", c_void_p)]
+
+
+class Resize(C.Structure):
+    _fields_ = [("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("H", C.c_int), ("W", C.c_int), ("in", c_void_p), ("out", c_void_p)]
+
+
 class PackInput(C.Structure):
     _fields_ = [("n", C.c_int), ("Nl", C.c_int), ("HW", C.c_int), ("on", C.c_float), ("off", C.c_float),
                 ("rgb_u8", c_void_p), ("rgb_f32", c_void_p), ("label", c_void_p), ("input", c_void_p)]
@@ -102,11 +111,11 @@ MAX_LAYERS, MAX_CH, MAX_LYT, MAX_TPS_K = 17, 24, 21, 256
 STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwarp_fwd_t": InvWarpFwd,
              "waldo_invwarp_bwd_t": InvWarpBwd, "waldo_geom_t": Geom, "waldo_decode_fwd_t": DecodeFwd,
              "waldo_decode_bwd_t": DecodeBwd, "waldo_wif_fuse_fwd_t": WifFuseFwd, "waldo_wif_fuse_bwd_t": WifFuseBwd,
-             "waldo_pack_input_t": PackInput}
+             "waldo_pack_input_t": PackInput, "waldo_warp_field_t": WarpField, "waldo_resize_t": Resize}
 
 EXPORTS = ["waldo_last_error", "waldo_abi_version", "waldo_has_device_code", "waldo_launch_count", "waldo_tps_fwd", "waldo_tps_bwd",
            "waldo_invwarp_fwd", "waldo_invwarp_bwd", "waldo_occ_fwd", "waldo_occ_bwd", "waldo_decode_fwd",
-           "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input"]
+           "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input", "waldo_warp_field_fwd", "waldo_resize_bilinear_fwd"]
 
 _lock = threading.Lock()
 _lib = None
@@ -120,7 +129,8 @@ def _declare(lib):
     lib.waldo_launch_count.restype = C.c_longlong
     for name, st in (("waldo_tps_fwd", TpsFwd), ("waldo_tps_bwd", TpsBwd), ("waldo_invwarp_fwd", InvWarpFwd),
                      ("waldo_invwarp_bwd", InvWarpBwd), ("waldo_decode_fwd", DecodeFwd), ("waldo_decode_bwd", DecodeBwd),
-                     ("waldo_wif_fuse_fwd", WifFuseFwd), ("waldo_wif_fuse_bwd", WifFuseBwd), ("waldo_pack_input", PackInput)):
+                     ("waldo_wif_fuse_fwd", WifFuseFwd), ("waldo_wif_fuse_bwd", WifFuseBwd), ("waldo_pack_input", PackInput), ("waldo_warp_field_fwd", WarpField),
+                     ("waldo_resize_bilinear_fwd", Resize)):
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(st), c_void_p]
         fn.restype = C.c_int

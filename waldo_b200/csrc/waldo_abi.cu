@@ -9,6 +9,7 @@
 #include "wb_composite_bwd.cuh"
 #include "wb_wif.cuh"
 #include "wb_pack.cuh"
+#include "wb_field.cuh"
 
 static thread_local char g_err[512] = "";
 long long g_wb_launches = 0;
@@ -96,9 +97,15 @@ int waldo_invwarp_fwd(const waldo_invwarp_fwd_t* a, waldo_stream_t st) {
   WB_LAUNCH(k_inv_clear, gpp, dim3(256), 0, st, k); WB_LAUNCHED();
   WB_LAUNCH(k_inv_claim, gp, dim3(256), 0, st, k); WB_LAUNCHED();
   WB_LAUNCH(k_inv_deposit, gp, dim3(256), 0, st, k); WB_LAUNCHED();
-  for (int it = 1; it <= a->niter; ++it) { WB_LAUNCH(k_inv_dilate, gband, dim3(256), 0, st, k, it); WB_LAUNCHED(); }
-  if (a->erode)
-    for (int it = 1; it <= a->niter; ++it) { WB_LAUNCH(k_inv_erode, gband, dim3(256), 0, st, k, it); WB_LAUNCHED(); }
+  // a forward map defined on a lattice much smaller than the target (an object canvas) lands in a small box of the target:
+  // one CTA per item runs all growth iterations there; otherwise (background) one flat launch per iteration
+  const bool small_box = (long long)a->Hs * a->Ws * 4 <= (long long)a->Ht * a->Wt;
+  if (small_box) { WB_LAUNCH(k_inv_grow_fused, dim3(a->n), dim3(512), 0, st, k); WB_LAUNCHED(); }
+  else {
+    for (int it = 1; it <= a->niter; ++it) { WB_LAUNCH(k_inv_dilate, gband, dim3(256), 0, st, k, it); WB_LAUNCHED(); }
+    if (a->erode)
+      for (int it = 1; it <= a->niter; ++it) { WB_LAUNCH(k_inv_erode, gband, dim3(256), 0, st, k, it); WB_LAUNCHED(); }
+  }
   WB_LAUNCH(k_inv_final, gp, dim3(256), 0, st, k); WB_LAUNCHED();
   return 0;
 }
@@ -116,7 +123,9 @@ int waldo_invwarp_bwd(const waldo_invwarp_bwd_t* a, waldo_stream_t st) {
   const dim3 gpp(wb_blocks(PP, 256, 512), a->n), gp(wb_blocks(P, 256, 512), a->n), gs(wb_blocks(a->Hs * a->Ws, 256, 512), a->n);
   const dim3 gband((a->Ht + 2 * m + WB_INV_ROWS - 1) / WB_INV_ROWS, a->n);
   WB_LAUNCH(k_invb_init, gpp, dim3(256), 0, st, k); WB_LAUNCHED();
-  for (int lv = a->niter - 1; lv >= 0; --lv) { WB_LAUNCH(k_invb_level, gband, dim3(256), 0, st, k, lv); WB_LAUNCHED(); }
+  if ((long long)a->Hs * a->Ws * 4 <= (long long)a->Ht * a->Wt) { WB_LAUNCH(k_invb_levels_fused, dim3(a->n), dim3(512), 0, st, k); WB_LAUNCHED(); }
+  else
+    for (int lv = a->niter - 1; lv >= 0; --lv) { WB_LAUNCH(k_invb_level, gband, dim3(256), 0, st, k, lv); WB_LAUNCHED(); }
   WB_LAUNCH(k_invb_handoff, gp, dim3(256), 0, st, k); WB_LAUNCHED();
   WB_LAUNCH(k_invb_resize_t, gs, dim3(256), 0, st, k); WB_LAUNCHED();
   return 0;
@@ -212,13 +221,6 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   // stage C: the gather kernel
   if (st_gather) {
     const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
-#if !defined(WB_HOST_EMU) && WB_GF_ASYNC
-    if (g.Tc == 4 && !self) {
-      const size_t ring = (size_t)WB_GF_DEPTH * 16 * WB_TILE_PX * sizeof(float);
-      cudaFuncSetAttribute(k_gather_fwd_async, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);   // >= 48 KB: opt in
-      WB_LAUNCH(k_gather_fwd_async, grid, dim3(WB_TILE_PX), ring, st, *a);
-    } else
-#endif
     if (g.Tc == 4 && !self) WB_LAUNCH((k_gather_fwd<4, true>), grid, dim3(WB_TILE_PX), 0, st, *a);
     else if (g.Tc <= 4) WB_LAUNCH((k_gather_fwd<4, false>), grid, dim3(WB_TILE_PX), 0, st, *a);
     else WB_LAUNCH((k_gather_fwd<8, false>), grid, dim3(WB_TILE_PX), 0, st, *a);
@@ -246,6 +248,24 @@ int waldo_wif_fuse_bwd(const waldo_wif_fuse_bwd_t* a, waldo_stream_t st) {
   WB_REQUIRE(a->f.Tc <= WB_WIF_MAX_TC, "wif_fuse_bwd: Tc=%d exceeds compiled maximum %d", a->f.Tc, WB_WIF_MAX_TC);
   WB_REQUIRE(a->f.raw_output && a->f.unet_out && a->d_frame, "wif_fuse_bwd: null pointer");
   WB_LAUNCH(k_wif_fuse_bwd, dim3(wb_blocks(a->f.HW, 256), a->f.B * a->f.Tp), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ field warp / scale
+int waldo_warp_field_fwd(const waldo_warp_field_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->c > 0 && a->h > 1 && a->w > 1 && a->H > 0 && a->W > 0, "warp_field: bad sizes");
+  WB_REQUIRE(a->field && a->grid && a->out, "warp_field: null pointer");
+  if (a->n == 0) return 0;
+  WB_LAUNCH(k_warp_field, dim3(wb_blocks((long long)a->n * a->H * a->W, 256, 8192)), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+int waldo_resize_bilinear_fwd(const waldo_resize_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->h > 0 && a->w > 0 && a->H >= a->h && a->W >= a->w, "resize_bilinear: bad sizes (up-sampling only)");
+  WB_REQUIRE(a->in && a->out, "resize_bilinear: null pointer");
+  if (a->n == 0) return 0;
+  WB_LAUNCH(k_resize_bilinear, dim3(wb_blocks((long long)a->n * a->H * a->W, 256, 8192)), dim3(256), 0, st, *a);
   WB_LAUNCHED();
   return 0;
 }

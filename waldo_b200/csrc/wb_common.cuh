@@ -58,7 +58,6 @@ extern long long g_wb_launches;
 #define WB_CHECK_LAUNCH() 0
 #define WB_UNROLL
 #define WB_UNROLL_N(n)
-#define WB_UNROLL_NA_LD
 #define WB_UNROLL_NA
 static thread_local float wb_dyn_smem_buf[96 * 1024];
 #define WB_DYN_SMEM(name) float* name = wb_dyn_smem_buf
@@ -76,12 +75,7 @@ extern long long g_wb_launches;
 // loops over the NA layer slots of a template: fully unrolled (register arrays) for the sparse instantiations,
 // rolled (local-memory arrays, small code, few registers) for the rare dense one
 #define WB_UNROLL_NA _Pragma("unroll (NA <= 8 ? NA : 1)")
-// the same for slot loops whose bodies are dominated by independent loads: the rolled form is unrolled by WB_SLOT_UNROLL so
-// that the loads of consecutive slots are in flight together
-#ifndef WB_SLOT_UNROLL
-#define WB_SLOT_UNROLL 4
-#endif
-#define WB_UNROLL_NA_LD WB_PRAGMA(unroll (NA <= 8 ? NA : WB_SLOT_UNROLL))
+
 #define WB_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
 #endif
 
@@ -128,12 +122,6 @@ extern long long g_wb_launches;
 #endif
 #ifndef WB_GB_MERGE
 #define WB_GB_MERGE 1   // neighbouring lanes merge coinciding taps before the global reductions
-#endif
-#ifndef WB_GF_ASYNC
-#define WB_GF_ASYNC 1   // cp.async operand pipeline in the FAST gather forward
-#endif
-#ifndef WB_GF_DEPTH
-#define WB_GF_DEPTH 3
 #endif
 #ifndef WB_GB_TG
 #define WB_GB_TG 2
@@ -196,23 +184,16 @@ WB_DEV double wb_warp_sum(double v) {
   return v;
 }
 
-// Fire-and-forget float reduction into GLOBAL memory.  Spelled as PTX on purpose: `atomicAdd` on a pointer whose address
-// space the compiler cannot prove (e.g. one read back from a shared-memory pointer table) compiles to the GENERIC form --
-// a predicated ATOM plus shared-memory and generic CAS loops behind ISSPACEP branches -- instead of one REDG.
+// Fire-and-forget float reduction into GLOBAL memory.  `atomicAdd` on a pointer whose address space the compiler cannot
+// prove (e.g. one read back from a shared-memory pointer table) compiles to the GENERIC form -- a predicated ATOM plus
+// shared-memory and generic CAS loops behind ISSPACEP branches -- instead of one REDG: tell it the space.
 WB_DEV void wb_red(float* p, float v) {
 #ifdef WB_HOST_EMU
   *p += v;
 #else
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v));   // no "memory" clobber: it would pin every load behind it
-#endif
-}
-
-// plain store to GLOBAL memory through a pointer of unproven address space (same reason as wb_red: STG, not generic ST)
-WB_DEV void wb_stg(float* p, float v) {
-#ifdef WB_HOST_EMU
-  *p = v;
-#else
-  asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v));
+  // (no "memory" clobber: it would pin every load behind the reduction.  `__builtin_assume(__isGlobal(p)); atomicAdd(p, v);`
+  //  also yields REDG, but measured 3-4 % slower in the layer kernels on B200, profiles/r1_v21)
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v));
 #endif
 }
 

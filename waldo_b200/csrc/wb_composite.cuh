@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_FWD) k_gather_fwd(Wb
         WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
           if (FAST || tc < g.Tc) {
             const float r = __fmaf_rn(v[tc][3], w[tc][3], __fmaf_rn(v[tc][2], w[tc][2], __fmaf_rn(v[tc][1], w[tc][1], __fmul_rn(v[tc][0], w[tc][0]))));
-            wb_stg(s_raw[tc] + choff + q, r);
+            s_raw[tc][choff + q] = r;
             acc += wgt[tc] * r;
           }
         }
@@ -365,84 +365,3 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_FWD) k_gather_fwd(Wb
   }
 }
 
-#ifndef WB_HOST_EMU
-// k_gather_fwd<4, true> with the tap loads of the next WB_GF_DEPTH - 1 channels kept in flight by cp.async into
-// per-thread shared-memory slots (see k_gather_bwd_async): 16 x (DEPTH - 1) loads in flight per thread, no registers held.
-__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_FWD) k_gather_fwd_async(WbDec d) {
-  constexpr int TC = 4, NF = 4 * TC, DEPTH = WB_GF_DEPTH;
-  const waldo_geom_t g = d.g;
-  const int C = g.C, L = g.No + 1;
-  const unsigned HWd = (unsigned)(g.Hd * g.Wd);
-  const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
-  const int CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
-  extern __shared__ __align__(16) float s_ring[];   // [DEPTH][NF][WB_TILE_PX]
-  __shared__ const float* s_src[TC];
-  __shared__ float* s_raw[TC];
-  for (int tc = wb_tid(); tc < TC; tc += wb_nthr()) {
-    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
-    s_raw[tc] = d.raw_output + (((size_t)b * g.Tc + tc) * g.Tp + tp) * CR * HWd;
-  }
-  __syncthreads();
-  float* my = s_ring + wb_tid();
-  const WbTileIter ti(g.Hd, g.Wd);
-  for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
-    const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
-    const int it = wb_tid();
-    const int X = min(tx0 + (it & (WB_TILE_W - 1)), g.Wd - 1), Y = min(ty0 + it / WB_TILE_W, g.Hd - 1);
-    const unsigned q = (unsigned)(Y * g.Wd + X);
-    const float gx = __ldg(d.xs_hd + X), gy = __ldg(d.ys_hd + Y);
-    const float* p0[TC];
-    const float* p1[TC];
-    float* raw[TC];
-    float w[TC][4], wgt[TC];
-    float den = 0.f, accs = 0.f;
-    WB_UNROLL for (int tc = 0; tc < TC; ++tc) {
-      const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-      const float* fl = d.flow + pair * 2 * HWd + q;
-      const float score = __ldg(d.score + pair * HWd + q);
-      const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
-      const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-      p0[tc] = s_src[tc] + t2.o0; p1[tc] = s_src[tc] + t2.o1; raw[tc] = s_raw[tc] + q;
-      WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = t2.w[j];
-      wgt[tc] = score + 1e-6f;
-      den += wgt[tc];
-      accs += wgt[tc] * (score * 2.f - 1.f);
-    }
-    const float inv = 1.f / fmaxf(den, 1e-12f);
-    float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
-#define WB_GF_ISSUE(ch_)                                                                       \
-    do {                                                                                         \
-      const unsigned off_ = (unsigned)(ch_) * HWd;                                               \
-      float* base_ = my + ((ch_) % DEPTH) * NF * WB_TILE_PX;                                     \
-      WB_UNROLL for (int tc = 0; tc < TC; ++tc) {                                                \
-        wb_cp4(base_ + (4 * tc + 0) * WB_TILE_PX, p0[tc] + off_); wb_cp4(base_ + (4 * tc + 1) * WB_TILE_PX, p0[tc] + off_ + 1); \
-        wb_cp4(base_ + (4 * tc + 2) * WB_TILE_PX, p1[tc] + off_); wb_cp4(base_ + (4 * tc + 3) * WB_TILE_PX, p1[tc] + off_ + 1); \
-      }                                                                                          \
-    } while (0)
-    WB_UNROLL for (int ch = 0; ch < DEPTH - 1; ++ch) { if (ch < C) WB_GF_ISSUE(ch); wb_cp_commit(); }
-    unsigned choff = 0u;
-#pragma unroll 1
-    for (int ch = 0; ch < C; ++ch) {
-      if (ch + DEPTH - 1 < C) WB_GF_ISSUE(ch + DEPTH - 1);
-      wb_cp_commit();
-      wb_cp_wait<DEPTH - 1>();
-      const float* base = my + (ch % DEPTH) * NF * WB_TILE_PX;
-      float acc = 0.f;
-      WB_UNROLL for (int tc = 0; tc < TC; ++tc) {
-        const float v0 = base[(4 * tc + 0) * WB_TILE_PX], v1 = base[(4 * tc + 1) * WB_TILE_PX];
-        const float v2 = base[(4 * tc + 2) * WB_TILE_PX], v3 = base[(4 * tc + 3) * WB_TILE_PX];
-        const float r = __fmaf_rn(v3, w[tc][3], __fmaf_rn(v2, w[tc][2], __fmaf_rn(v1, w[tc][1], __fmul_rn(v0, w[tc][0]))));
-        wb_stg(raw[tc] + choff, r);
-        acc += wgt[tc] * r;
-      }
-      wb_stg(of + choff, acc * inv);
-      choff += HWd;
-    }
-#undef WB_GF_ISSUE
-    wb_cp_wait<0>();
-    of[choff] = accs * inv;
-    d.norm[((size_t)b * g.Tp + tp) * HWd + q] = den;
-  }
-}
-#endif  // !WB_HOST_EMU

@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd(Wb
 // cp.async.wait_group.
 
 #ifndef WB_GB_DEPTH
-#define WB_GB_DEPTH 4
+#define WB_GB_DEPTH 3
 #endif
 
 template <int TG>
@@ -877,7 +877,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   float sm[NN];
   if (c.filt && any_obj) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
   float aup[NA], av[NA], ell[NA];
-  WB_UNROLL_NA_LD for (int s = 0; s < WB_NEND; ++s) {
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     av[s] = 0.f; aup[s] = 0.f; ell[s] = 1.f;
     if (s < ix.n) {
       const int k = ix.k[s];
@@ -896,7 +896,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   }
   // ---- upstream: scatter-accumulated d/dA plus the returned alpha = 2A - 1 (zero beyond the image edge)
   float gA[NA], ga[NA];
-  WB_UNROLL_NA_LD for (int s = 0; s < WB_NEND; ++s) {
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     ga[s] = 0.f; gA[s] = 0.f;
     if (s < ix.n) {
       const size_t o = (((size_t)b * g.Tw + t) * L + ix.k[s]) * HWd + q;

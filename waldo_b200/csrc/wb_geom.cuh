@@ -220,47 +220,77 @@ WB_DEV bool wb_inv_outside(const int32_t* __restrict__ bbox, int x, int y, int g
   return x < bbox[0] - grow || x > bbox[2] + grow || y < bbox[1] - grow || y > bbox[3] + grow;
 }
 // phase 3, iteration `iter`: a frontier cell takes the normalised Gaussian mean of the known cells   warp.py:135-151
+WB_DEV void wb_inv_dilate_cell(const WbInvItem& it, const float* g, int x, int y, int iter, int Hp, int Wp) {
+  const uint8_t* level = it.level;
+  const int c = y * Wp + x;
+  if (level[c] != 255) return;
+  bool front = (y > 0 && wb_level_known_before(level[c - Wp], iter)) || (y < Hp - 1 && wb_level_known_before(level[c + Wp], iter)) ||
+               (x > 0 && wb_level_known_before(level[c - 1], iter)) || (x < Wp - 1 && wb_level_known_before(level[c + 1], iter));
+  if (!front) return;
+  float sx = 0.f, sy = 0.f, sw = 0.f;
+  WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
+    WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
+      int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
+      int q = yy * Wp + xx;
+      if (!wb_level_known_before(level[q], iter)) continue;
+      float w = g[(dy + 1) * 3 + dx + 1];
+      sx += w * it.vx[q]; sy += w * it.vy[q]; sw += w;
+    }
+  it.vx[c] = sx / sw; it.vy[c] = sy / sw; it.level[c] = (uint8_t)iter;
+}
 __global__ void __launch_bounds__(256) k_inv_dilate(WbInvArgs a, int iter) {
   WB_INV_GEOM;
   const WbInvItem it = wb_inv_item(a, blockIdx.y, P, PP);
-  const uint8_t* level = it.level;
   float g[9];
   WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
   const WbInvBand band = wb_inv_band(it.bbox, iter, Hp, Wp);
-  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) {
-    const int y = band.y0 + i / band.w, x = band.x0 + i % band.w, c = y * Wp + x;
-    if (level[c] != 255) continue;
-    bool front = (y > 0 && wb_level_known_before(level[c - Wp], iter)) || (y < Hp - 1 && wb_level_known_before(level[c + Wp], iter)) ||
-                 (x > 0 && wb_level_known_before(level[c - 1], iter)) || (x < Wp - 1 && wb_level_known_before(level[c + 1], iter));
-    if (!front) continue;
-    float sx = 0.f, sy = 0.f, sw = 0.f;
-    WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
-      WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
-        int yy = y + dy, xx = x + dx;
-        if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
-        int q = yy * Wp + xx;
-        if (!wb_level_known_before(level[q], iter)) continue;
-        float w = g[(dy + 1) * 3 + dx + 1];
-        sx += w * it.vx[q]; sy += w * it.vy[q]; sw += w;
-      }
-    it.vx[c] = sx / sw; it.vy[c] = sy / sw; it.level[c] = (uint8_t)iter;
-  }
+  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) wb_inv_dilate_cell(it, g, band.x0 + i % band.w, band.y0 + i / band.w, iter, Hp, Wp);
 }
 // phase 4, iteration `iter`: erosion of the known set (objects only)                      warp.py:153-162
+WB_DEV void wb_inv_erode_cell(const WbInvItem& it, int x, int y, int iter, int Hp, int Wp) {
+  const uint8_t* level = it.level;
+  const uint8_t* eroded = it.eroded;
+  const int c = y * Wp + x;
+  if (level[c] == 255 || eroded[c] != 0) return;
+#define WB_GONE(q) (level[q] == 255 || (eroded[q] != 0 && (int)eroded[q] < iter))
+  bool edge = (y > 0 && WB_GONE(c - Wp)) || (y < Hp - 1 && WB_GONE(c + Wp)) ||
+              (x > 0 && WB_GONE(c - 1)) || (x < Wp - 1 && WB_GONE(c + 1));
+#undef WB_GONE
+  if (edge) it.eroded[c] = (uint8_t)iter;
+}
 __global__ void __launch_bounds__(256) k_inv_erode(WbInvArgs a, int iter) {
   WB_INV_GEOM;
   const WbInvItem it = wb_inv_item(a, blockIdx.y, P, PP);
-  const uint8_t* level = it.level;
-  const uint8_t* eroded = it.eroded;
   const WbInvBand band = wb_inv_band(it.bbox, a.niter, Hp, Wp);
-  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) {
-    const int y = band.y0 + i / band.w, x = band.x0 + i % band.w, c = y * Wp + x;
-    if (level[c] == 255 || eroded[c] != 0) continue;
-#define WB_GONE(q) (level[q] == 255 || (eroded[q] != 0 && (int)eroded[q] < iter))
-    bool edge = (y > 0 && WB_GONE(c - Wp)) || (y < Hp - 1 && WB_GONE(c + Wp)) ||
-                (x > 0 && WB_GONE(c - 1)) || (x < Wp - 1 && WB_GONE(c + 1));
-#undef WB_GONE
-    if (edge) it.eroded[c] = (uint8_t)iter;
+  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) wb_inv_erode_cell(it, band.x0 + i % band.w, band.y0 + i / band.w, iter, Hp, Wp);
+}
+// Items whose hit cells span a small box (objects: a 64x64 canvas splatted into the 128x256 image) run ALL dilation and
+// erosion iterations in one CTA, a __syncthreads() per iteration, over the grown box only.  grid = (n).
+WB_DEV void wb_inv_box(const int32_t* bbox, int grow, int Hp, int Wp, int& x0, int& y0, int& w, int& cells) {
+  x0 = y0 = w = cells = 0;
+  if (bbox[2] < 0) return;
+  x0 = max(0, bbox[0] - grow); y0 = max(0, bbox[1] - grow);
+  const int x1 = min(Wp - 1, bbox[2] + grow), y1 = min(Hp - 1, bbox[3] + grow);
+  w = x1 - x0 + 1; cells = w * (y1 - y0 + 1);
+}
+__global__ void __launch_bounds__(512) k_inv_grow_fused(WbInvArgs a) {
+  WB_INV_GEOM;
+  const WbInvItem it = wb_inv_item(a, blockIdx.x, P, PP);
+  float g[9];
+  WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
+  int x0, y0, w, cells;
+  for (int iter = 1; iter <= a.niter; ++iter) {
+    wb_inv_box(it.bbox, iter, Hp, Wp, x0, y0, w, cells);
+    for (int i = wb_tid(); i < cells; i += wb_nthr()) wb_inv_dilate_cell(it, g, x0 + i % w, y0 + i / w, iter, Hp, Wp);
+    __syncthreads();
+  }
+  if (a.erode) {
+    wb_inv_box(it.bbox, a.niter, Hp, Wp, x0, y0, w, cells);
+    for (int iter = 1; iter <= a.niter; ++iter) {
+      for (int i = wb_tid(); i < cells; i += wb_nthr()) wb_inv_erode_cell(it, x0 + i % w, y0 + i / w, iter, Hp, Wp);
+      __syncthreads();
+    }
   }
 }
 // phase 5: sentinel for unknown cells, crop, back to normalised coordinates              warp.py:164-174
@@ -331,29 +361,43 @@ __global__ void __launch_bounds__(256) k_invb_init(WbInvBwdArgs a) {
     it.isw[c] = sw > 0.f ? 1.f / sw : 0.f;
   }
 }
-// level `lv` gathers from the (complete) totals of the later-filled neighbours; launched for lv = niter-1 .. 0
+// level `lv` gathers from the (complete) totals of the later-filled neighbours; run for lv = niter-1 .. 0
+WB_DEV void wb_invb_level_cell(const WbInvBItem& it, const float* g, int x, int y, int lv, int Hp, int Wp) {
+  const int c = y * Wp + x;
+  if ((int)it.level[c] != lv) return;
+  float ax = 0.f, ay = 0.f;
+  WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
+    WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
+      int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
+      int q = yy * Wp + xx;
+      int lq = it.level[q];
+      if (lq == 255 || lq <= lv) continue;
+      // cell q (filled at lq) read cell c through kernel tap (c - q) = (-dy,-dx)
+      float w = g[(1 - dy) * 3 + (1 - dx)] * it.isw[q];
+      ax += w * it.gx[q]; ay += w * it.gy[q];
+    }
+  it.gx[c] += ax; it.gy[c] += ay;
+}
 __global__ void __launch_bounds__(256) k_invb_level(WbInvBwdArgs a, int lv) {
   WB_INV_GEOM;
   const WbInvBItem it = wb_invb_item(a, blockIdx.y, P, PP);
   float g[9];
   WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
   const WbInvBand band = wb_inv_band(it.bbox, lv, Hp, Wp);
-  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) {
-    const int y = band.y0 + i / band.w, x = band.x0 + i % band.w, c = y * Wp + x;
-    if ((int)it.level[c] != lv) continue;
-    float ax = 0.f, ay = 0.f;
-    WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
-      WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
-        int yy = y + dy, xx = x + dx;
-        if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
-        int q = yy * Wp + xx;
-        int lq = it.level[q];
-        if (lq == 255 || lq <= lv) continue;
-        // cell q (filled at lq) read cell c through kernel tap (c - q) = (-dy,-dx)
-        float w = g[(1 - dy) * 3 + (1 - dx)] * it.isw[q];
-        ax += w * it.gx[q]; ay += w * it.gy[q];
-      }
-    it.gx[c] += ax; it.gy[c] += ay;
+  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) wb_invb_level_cell(it, g, band.x0 + i % band.w, band.y0 + i / band.w, lv, Hp, Wp);
+}
+// small-box items: all levels in one CTA (see k_inv_grow_fused).  grid = (n)
+__global__ void __launch_bounds__(512) k_invb_levels_fused(WbInvBwdArgs a) {
+  WB_INV_GEOM;
+  const WbInvBItem it = wb_invb_item(a, blockIdx.x, P, PP);
+  float g[9];
+  WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
+  int x0, y0, w, cells;
+  for (int lv = a.niter - 1; lv >= 0; --lv) {
+    wb_inv_box(it.bbox, lv, Hp, Wp, x0, y0, w, cells);
+    for (int i = wb_tid(); i < cells; i += wb_nthr()) wb_invb_level_cell(it, g, x0 + i % w, y0 + i / w, lv, Hp, Wp);
+    __syncthreads();
   }
 }
 // hit cells hand their total to the winning sample: val = -dx, dx = disp * Wt / 2

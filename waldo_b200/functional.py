@@ -431,3 +431,42 @@ def pack_input(rgb, label, num_lyt, on=5.0, off=-5.0, out=None):
                     L.ptr(lab_c, torch.uint8, "label"), L.ptr(out, name="out"))
     L.check(lib.waldo_pack_input(C.byref(a), L.stream_of(out)), "pack_input")
     return out
+
+
+# ===================================================================================== a-5 / a-11 field warp, scale
+def _no_grad_path(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError("waldo_b200: the stand-alone field warp / scale helpers are forward-only (inference); inside "
+                                  "decode_output these steps are fused into kernels that carry the gradients")
+
+
+def warp_field(field, grid, delta=0.0):
+    """grid_sample(field + delta, grid) - delta, bilinear / zeros / align_corners=False (lvd.py:548,559).
+    field (n, c, h, w), grid (n, H, W, 2) -> (n, c, H, W)."""
+    _no_grad_path(field, grid)
+    lib = L.load()
+    f, g = _c(field.detach()), _c(grid.detach())
+    n, c, h, w = f.shape
+    if g.shape[0] != n or g.shape[-1] != 2:
+        raise RuntimeError(f"waldo_b200.warp_field: field {tuple(f.shape)} and grid {tuple(g.shape)} do not match")
+    H, W = g.shape[1], g.shape[2]
+    out = torch.empty(n, c, H, W, device=f.device, dtype=torch.float32)
+    a = L.WarpField(n, c, h, w, H, W, float(delta), L.ptr(f, name="field"), L.ptr(g, name="grid"), L.ptr(out))
+    L.check(lib.waldo_warp_field_fwd(C.byref(a), L.stream_of(f)), "warp_field_fwd")
+    return out
+
+
+def resize_bilinear(x, scale_factor):
+    """lvd.py:175-179 `scale`: F.interpolate(bilinear, scale_factor) over the last two dims (up-sampling), any leading dims."""
+    _no_grad_path(x)
+    if scale_factor == 1:
+        return x
+    lib = L.load()
+    xc = _c(x.detach())
+    h, w = xc.shape[-2:]
+    H, W = int(h * scale_factor), int(w * scale_factor)
+    n = xc.numel() // (h * w)
+    out = torch.empty(*xc.shape[:-2], H, W, device=xc.device, dtype=torch.float32)
+    a = L.Resize(n, h, w, H, W, L.ptr(xc, name="x"), L.ptr(out))
+    L.check(lib.waldo_resize_bilinear_fwd(C.byref(a), L.stream_of(xc)), "resize_bilinear_fwd")
+    return out

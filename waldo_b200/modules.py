@@ -150,6 +150,55 @@ class Warper(nn.Module):
             sgb = sgb.view(B, T, *sgb.shape[1:])
         return tgo, sgo, tgb, sgb
 
+    # -- a-5 (stand-alone, forward only) ----------------------------------------------------------------
+    def obj_to_output(self, obj, grid, delta_obj=1):
+        """lvd.py:538-548: obj (B,No,c,Ho,Wo) or (B,T,No,c,Ho,Wo) warped by src_grid_obj -> (B,T,No,c,H,W)."""
+        _, sgo, _, _ = grid
+        B, T, No = sgo.shape[:3]
+        Ho, Wo = self.tgt_shape
+        H, W = self.src_shape
+        c = obj.size(-3)
+        obj = obj.view(B, 1, No, c, Ho, Wo).expand(-1, T, -1, -1, -1, -1) if obj.ndim == 5 else obj
+        out = Fn.warp_field(obj.reshape(B * T * No, c, Ho, Wo), sgo.reshape(B * T * No, H, W, 2), delta_obj)
+        return out.view(B, T, No, c, H, W)
+
+    def bg_to_output(self, bg, grid, delta_bg=1, eps=1e-6):
+        """lvd.py:550-559: bg (B,c,H,W) or (B,T,c,H,W) warped by src_grid_bg -> (B,T,1,c,H,W)."""
+        _, _, _, sgb = grid
+        B, T = sgb.shape[:2]
+        H, W = self.src_shape
+        c = bg.size(-3)
+        bg = bg.view(B, 1, c, H, W).expand(-1, T, -1, -1, -1) if bg.ndim == 4 else bg
+        out = Fn.warp_field(bg.reshape(B * T, c, H, W), sgb.reshape(B * T, H, W, 2), delta_bg)
+        return out.view(B, T, 1, c, H, W)
+
+    def layer_to_output(self, obj, bg, grid, delta_bg=1, delta_obj=1):
+        """lvd.py:533-536."""
+        return torch.cat([self.bg_to_output(bg, grid, delta_bg), self.obj_to_output(obj, grid, delta_obj)], dim=2)
+
+    # -- a-11 MAT propagation flows (inference, --s_use_inpainter) -------------------------------------------
+    def grid_to_bg_flow_from_ref_to_pred(self, grid, ctx_len, ref):
+        """lvd.py:575-582 -> (B, T-ctx_len, Hd, Wd, 2)."""
+        _, _, tgb, sgb = grid
+        flow = (tgb[:, [ref]] - tgb[:, ctx_len:]).permute(0, 1, 4, 2, 3)
+        flow = self.bg_to_output(flow, [None, None, None, sgb[:, ctx_len:]], delta_bg=0).squeeze(2)
+        return Fn.resize_bilinear(flow, self.scale_hd).permute(0, 1, 3, 4, 2)
+
+    def grid_to_obj_flow_from_ref_to_pred(self, grid, ctx_len, ref, obj_id):
+        """lvd.py:584-591 -> (B, T-ctx_len, Hd, Wd, 2).  (The reference's `tgt_grid_obj[:, [ref], [obj_id]]` drops a dim and
+        only broadcasts for B == 1, the batch size its inpainting path runs with; this is the B-general form.)"""
+        tgo, sgo, _, _ = grid
+        flow = (tgo[:, [ref]][:, :, [obj_id]] - tgo[:, ctx_len:][:, :, [obj_id]]).permute(0, 1, 2, 5, 3, 4)
+        flow = self.obj_to_output(flow, [None, sgo[:, ctx_len:][:, :, [obj_id]], None, None], delta_obj=0).squeeze(2)
+        return Fn.resize_bilinear(flow, self.scale_hd).permute(0, 1, 3, 4, 2)
+
+    def grid_to_bg_flow_from_ctx_to_ref(self, grid, ctx_len, ref):
+        """lvd.py:593-600 -> (B, ctx_len, Hd, Wd, 2)."""
+        _, _, tgb, sgb = grid
+        flow = (tgb[:, :ctx_len] - tgb[:, [ref]]).permute(0, 1, 4, 2, 3)
+        flow = self.bg_to_output(flow, [None, None, None, sgb[:, [ref]].repeat(1, ctx_len, 1, 1, 1)], delta_bg=0).squeeze(2)
+        return Fn.resize_bilinear(flow, self.scale_hd).permute(0, 1, 3, 4, 2)
+
     # -- a-6 + a-7 fused ---------------------------------------------------------------------------------
     def _spec(self, restrict_to_ctx: bool) -> Fn.DecodeSpec:
         H, W = self.src_shape
