@@ -873,6 +873,13 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   const int lane = wb_lane();
   const WbIdx<NA> ix = wb_idx<NA>(wm);
   const bool any_obj = (wm >> 1) != 0u;
+  // the scatter-accumulated d/dA of the first four slots is requested up front (most rows have <= 4 live layers): four
+  // independent HBM loads in flight while the forward is recomputed, instead of one exposed load per trip of the rolled loop
+  float pf[4] = {0.f, 0.f, 0.f, 0.f};
+  if (NA > 8 && a.d_alpha_acc) {
+    const float* base = a.d_alpha_acc + ((size_t)b * g.Tw + t) * L * HWd + q;
+    WB_UNROLL for (int u = 0; u < 4; ++u) if (u < ix.n) pf[u] = base[(size_t)ix.k[u] * HWd];
+  }
   // ---- recompute the forward of this pixel
   float sm[NN];
   if (c.filt && any_obj) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
@@ -901,12 +908,29 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
     if (s < ix.n) {
       const size_t o = (((size_t)b * g.Tw + t) * L + ix.k[s]) * HWd + q;
       float v = 0.f;
-      if (a.d_alpha_acc) v += a.d_alpha_acc[o];
+      if (a.d_alpha_acc) {
+        if (NA > 8 && s < 4) v += s == 0 ? pf[0] : (s == 1 ? pf[1] : (s == 2 ? pf[2] : pf[3]));
+        else v += a.d_alpha_acc[o];
+      }
       if (a.d_alpha) v += 2.f * __ldg(a.d_alpha + o);
       gA[s] = v * actf;
     }
   }
-  wb_occlude_bwd<NA>(av, gA, c.s_occ, L, ix, ga, c.s_acc, c.pairs_only);
+  if (NA > 8 && ix.n <= 4) {
+    // most rows have <= 4 live layers: run the O(n^2) exclusive-product backward on registers, fully unrolled, instead of
+    // the rolled double loop over local-memory arrays
+    WbIdx<4> ix4;
+    float R4[4], gA4[4], ga4[4];
+    ix4.n = ix.n;
+    WB_UNROLL for (int u = 0; u < 4; ++u) {
+      const bool on = u < ix.n;
+      ix4.k[u] = on ? ix.k[u] : 0; R4[u] = on ? av[u] : 0.f; gA4[u] = on ? gA[u] : 0.f; ga4[u] = 0.f;
+    }
+    wb_occlude_bwd<4>(R4, gA4, c.s_occ, L, ix4, ga4, c.s_acc, c.pairs_only);
+    WB_UNROLL for (int u = 0; u < 4; ++u) if (u < ix.n) ga[u] = ga4[u];
+  } else {
+    wb_occlude_bwd<NA>(av, gA, c.s_occ, L, ix, ga, c.s_acc, c.pairs_only);
+  }
   // ---- filter backward: l_k = 1 - 0.5 sum_c |P_kc - sm_c|.  One ROLLED loop over the object slots (a single copy of
   // the class loop in the code); d P_kc = sum over pixels of -0.5 sign(P_kc - sm_c) d l_k is reduced over the warp with
   // a transpose butterfly and accumulated by lane c.

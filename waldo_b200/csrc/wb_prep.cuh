@@ -177,7 +177,8 @@ template <int NA> WB_DEV WbIdx<NA> wb_idx(unsigned wm) {
   WbIdx<NA> r;
   r.n = __popc(wm);
   unsigned m = wm;
-  WB_UNROLL_NA for (int s = 0; s < NA; ++s) { r.k[s] = m ? __ffs((int)m) - 1 : 0; m &= m - 1u; }
+  // (rolled form: only the live slots are ever read)
+  WB_UNROLL_NA for (int s = 0; s < (NA <= 8 ? NA : r.n); ++s) { r.k[s] = m ? __ffs((int)m) - 1 : 0; m &= m - 1u; }
   return r;
 }
 
