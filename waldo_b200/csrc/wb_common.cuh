@@ -224,8 +224,9 @@ struct WbTaps {
 
 WB_DEV WbTaps wb_taps(float gx, float gy, int W, int H) {
   WbTaps t;
-  t.ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), 1.f), 2.f);
-  t.iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), 1.f), 2.f);
+  // (x * 0.5f is the same correctly rounded value as ATen's x / 2 for every x, without the division sequence)
+  t.ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), 1.f), 0.5f);
+  t.iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), 1.f), 0.5f);
   float fx = floorf(t.ix), fy = floorf(t.iy);
   float wx1 = __fsub_rn(t.ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.f), t.ix);
   float wy1 = __fsub_rn(t.iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.f), t.iy);
