@@ -169,27 +169,24 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
   const bool direct = g.Hd == g.H;
   const int Xl = min(tx0 + lane, g.Wd - 1);
   const unsigned ql = (unsigned)(Y * g.Wd + Xl);   // this lane's own pixel (lane = pixel layout, dead-layer stores)
-  // layers outside the row's union are fully transparent (lane = pixel layout)
   for (int tc = 0; tc < g.Tc; ++tc) {
-    float* o = d.raw_output + ((((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR + C) * HWd + ql;
-    WB_UNROLL for (int kk = 0; kk < WB_MAX_L; ++kk) { if (kk < L && !((wm >> kk) & 1u)) *o = -1.f; o += HWd; }
-  }
-  // passes outside, contexts inside: the geometry of a pass (up-sampling taps, identity grid, is_obj) serves all contexts
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+    const float2* fl = reinterpret_cast<const float2*>(d.f_lo) + (pair * L + k) * HW;
+    const float* alpha_k = d.alpha + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
+    float* ra = d.raw_output + ((((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR + C) * HWd;   // alpha channels of this pair
+    float* flo = d.flow + pair * 2 * HWd;
+    float* sco = d.score + pair * HWd;
+    // layers outside the row's union are fully transparent
+    { float* o = ra + ql; WB_UNROLL for (int kk = 0; kk < WB_MAX_L; ++kk) { if (kk < L && !((wm >> kk) & 1u)) *o = -1.f; o += HWd; } }
 #pragma unroll 1
-  for (int r = 0; r < LP; ++r) {
-    const int p = r * PPW + pl, X = min(tx0 + p, g.Wd - 1);
-    const unsigned q = (unsigned)(Y * g.Wd + X);
-    const WbAxis ax = wb_axis(X, r_lo, g.W);
-    const float gx = __ldg(d.xs_hd + X);
-    const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
-    const bool samp = valid && ((__shfl_sync(0xffffffffu, isobj_lane, p) >> k) & 1u);
-#pragma unroll 1
-    for (int tc = 0; tc < g.Tc; ++tc) {
-      const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-      const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-      const float2* fl = reinterpret_cast<const float2*>(d.f_lo) + (pair * L + k) * HW;
-      const float* alpha_k = d.alpha + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
-      float* ra = d.raw_output + ((((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR + C) * HWd;   // alpha channels of this pair
+    for (int r = 0; r < LP; ++r) {
+      const int p = r * PPW + pl, X = min(tx0 + p, g.Wd - 1);
+      const unsigned q = (unsigned)(Y * g.Wd + X);
+      const WbAxis ax = wb_axis(X, r_lo, g.W);
+      const float gx = __ldg(d.xs_hd + X);
+      const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
+      const unsigned isobj = __shfl_sync(0xffffffffu, isobj_lane, p);
       float2 f00 = __ldg(fl + o00), f01 = f00, f10 = f00, f11 = f00;
       if (!direct) { f01 = __ldg(fl + o01); f10 = __ldg(fl + o10); f11 = __ldg(fl + o11); }
       float Fx = 0.f, Fy = 0.f, rr = 0.f;
@@ -199,7 +196,7 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
           Fx = wb_lerp2(f00.x, f01.x, f10.x, f11.x, ax, ay);
           Fy = wb_lerp2(f00.y, f01.y, f10.y, f11.y, ax, ay);
         }
-        if (samp) {
+        if ((isobj >> k) & 1u) {
           const WbTaps t = wb_taps(__fadd_rn(gx, Fx), __fadd_rn(gy, Fy), g.Wd, g.Hd);
           const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
           rr = wb_gather2_01(alpha_k + t2.o0, alpha_k + t2.o1, t2.w);
@@ -215,7 +212,7 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
       }
       if (valid) ra[(size_t)k * HWd + q] = A * 2.f - 1.f;
       if (slot == 0) {
-        d.flow[pair * 2 * HWd + q] = fx; d.flow[(pair * 2 + 1) * HWd + q] = fy; d.score[pair * HWd + q] = sc;
+        flo[q] = fx; flo[HWd + q] = fy; sco[q] = sc;
         if (c.disocc_ch) ra[(size_t)L * HWd + q] = mx;
       }
     }
