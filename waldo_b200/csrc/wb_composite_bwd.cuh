@@ -1,13 +1,14 @@
 // Backward of decode_output: the fused HD backward kernel, the context-alpha
 // backward, and the low-res chain down to grids / opacities / class scores.
 //
-// Accumulation strategy of this revision (see DESIGN.md "backward"):
+// Accumulation strategy:
 //   * small reductions (d occ, d class profile, d cls): per-warp shuffle tree -> per-CTA shared slot ->
 //     per-CTA partial in global scratch -> reduced in CTA order by a second kernel: deterministic, no atomics;
-//   * low-res scatter targets of the HD kernels (d f_lo, d a_lo): shared-memory window per 32x8 HD tile,
-//     flushed once per tile;
-//   * HD scatter targets (d input, d context opacity): red.global.add.f32.
-// All layer loops run over the warp-wide union of live layers (see wb_composite.cuh).
+//   * low-res scatter targets of the HD kernels (d f_lo, d a_lo): the 32 pixels of a row are staged in shared memory and
+//     each low-res column is reduced by one lane (transpose of the up-sampling), then two red.global per column;
+//   * HD scatter targets (d input, d context opacity): red.global.add.f32 (wb_red), neighbouring lanes merged by shuffle.
+// All layer loops run over the warp-wide union of live layers (see wb_composite.cuh); rows with <= 8 live layers use the
+// lanes-per-layer form of the layer kernel.
 #pragma once
 #include "wb_common.cuh"
 #include "wb_prep.cuh"
@@ -1568,7 +1569,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   if (st_aprep && (a.d_alpha_acc || a.d_alpha)) {
     if (filt && a.d_prof_p) WB_BREQ(a.prof_p_part, "prof_p_part scratch missing");
     const dim3 pgrid(a.red_ctas, g.B * g.Tw);
-    const size_t dyn = (size_t)WB_NWARP * WB_MAX_NL * 32 * sizeof(float);
+    const size_t dyn = WB_LANES_PREP_BWD ? (size_t)WB_NWARP * WB_MAX_NL * 32 * sizeof(float) : 0;   // softmax staging of the lanes form only
 #ifndef WB_HOST_EMU
     // static + dynamic shared memory exceeds the 48 KB default: opt in (cheap, idempotent)
     if (g.Nl == 20) cudaFuncSetAttribute(k_alpha_prep_bwd<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
