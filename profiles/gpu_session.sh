@@ -7,7 +7,7 @@ mkdir -p $OUT
 for what in "$@"; do
 case $what in
 tests)
-  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/${TAG}_tests.log;;
+  timeout 400 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/${TAG}_tests.log;;
 bench)
   timeout 600 python bench.py > $OUT/${TAG}_bench.jsonl 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; cat $OUT/${TAG}_bench.jsonl; tail -3 $OUT/${TAG}_bench.err;;
 benchq)
@@ -22,7 +22,7 @@ workloads)
 ref)
   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.jsonl 2> $OUT/${TAG}_bench_ref.err; echo "ref rc=$?"; cat $OUT/${TAG}_bench_ref.jsonl; tail -2 $OUT/${TAG}_bench_ref.err;;
 exp)
-  timeout 1200 python scratch/exp.py $EXP_NAMES > $OUT/${TAG}_exp.log 2>&1; echo "exp rc=$?"; cat $OUT/${TAG}_exp.log;;
+  timeout ${EXP_TIMEOUT:-300} python scratch/exp.py $EXP_NAMES > $OUT/${TAG}_exp.log 2>&1; echo "exp rc=$?"; cat $OUT/${TAG}_exp.log;;
 fullk)
   timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$FULL_K" -c ${FULL_C:-1} \
      -o $OUT/${TAG}_fullk -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_fullk.log 2>&1; echo "fullk rc=$?"; tail -2 $OUT/${TAG}_fullk.log;;

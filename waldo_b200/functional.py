@@ -281,7 +281,7 @@ class _Decode(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         a_lo = torch.empty(B, g.Tw, Lr, spec.H, spec.W, **f32)
         nout = spec.num_obj * Nl + spec.num_obj
-        prof_ctas = int(os.environ.get("WALDO_PROF_CTAS", 0)) or max(1, min(74, (g.Tw * spec.H * spec.W + 255) // 256))
+        prof_ctas = int(os.environ.get("WALDO_PROF_CTAS", 0)) or max(1, min(148, (g.Tw * spec.H * spec.W + 255) // 256))   # one per SM
         prof_part = torch.empty(B, prof_ctas, nout, **f32)
         prof_sum = torch.empty(B, nout, **f32)
         prof_p = torch.empty(B, spec.num_obj, Nl, **f32)
