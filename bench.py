@@ -366,10 +366,11 @@ def main():
         except Exception:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
         traffic = {}
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        except Exception:
-            pass
+        if args.workload == "city_train" and not args.batch:   # the ncu --set full capture in profiles/ is of this workload
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            except Exception:
+                pass
         kern = {"k_gather_fwd": (prof.get("decode_fwd:gather", 0.0), kb["k_gather_fwd"]),
                 "k_layers_fwd": (prof.get("decode_fwd:layers", 0.0), kb["k_layers_fwd"]),
                 "k_alpha_prep": (prof.get("decode_fwd:alpha_prep", 0.0), kb["k_alpha_prep"])}
