@@ -430,3 +430,50 @@ def check_field_warps(dev, case):
         raise AssertionError("expected NotImplementedError")
     except NotImplementedError:
         pass
+
+
+# ------------------------------------------------------------------------------------------------ oracle-direct cases
+# Shapes the committed reference fixtures do not hold, checked against the (fixture-pinned) oracle directly: the
+# benchmark's 4-context fast paths, several future frames per video, frame sizes that are not multiples of the 32x8
+# pixel tile, an odd channel count.
+SYNTH_CASES = {
+    # name: (PathConfig kwargs, B, T, Tc)
+    "tc4_ragged": (dict(dim=10, load_dim=20, aspect_ratio=2.2, num_obj=5, num_lyt=6, latent_shape=(2, 4)), 2, 6, 4),
+    "tc4_x4": (dict(dim=8, load_dim=32, aspect_ratio=2.0, num_obj=4, num_lyt=20, latent_shape=(2, 4)), 1, 5, 4),
+    "tc3_odd": (dict(dim=12, load_dim=24, aspect_ratio=1.5, num_obj=2, num_lyt=5, latent_shape=(3, 4)), 1, 5, 3),
+}
+
+
+def synth_case(name):
+    kw, B, T, Tc = SYNTH_CASES[name]
+    cfg = wo.PathConfig(**kw)
+    d = wo.synth_inputs(cfg, B, T, Tc, seed=17, radius=0.2)
+    st = wo.make_state(cfg)
+    with torch.no_grad():
+        occ, _, _, grid = wo.estimate_alpha_grid_occ(st, d["obj_alpha_raw"], d["obj_pose"], d["bg_pose"], d["occ_score"])
+    z = {"in_input": d["input"], "tgt_grid_obj": grid[0], "src_grid_obj": grid[1], "tgt_grid_bg": grid[2], "src_grid_bg": grid[3],
+         "occ": occ, "in_obj_alpha_raw": d["obj_alpha_raw"], "in_cls": d["cls"],
+         "in_ctx_ts": d["ctx_ts"].contiguous(), "in_pred_ts": d["pred_ts"]}
+    with torch.no_grad():
+        out, _ = oracle_decode(cfg, z, torch.float32, with_grad=False)
+    gen = torch.Generator().manual_seed(5)
+    for n, o in zip(OUT_NAMES, out):
+        if o is not None:
+            z["proj_" + n] = torch.randn(o.shape, generator=gen)
+    return cfg, z
+
+
+def check_decode_synth(dev, name):
+    """decode_output against the oracle (fp32, fp64-arbitrated) on a shape outside the reference fixtures."""
+    cfg, z = synth_case(name)
+    o32, g32 = oracle_decode(cfg, z, torch.float32)
+    o64, g64 = oracle_decode(cfg, z, torch.float64)
+    out, g = kernel_decode(dev, cfg, z)
+    for n, o, a, b in zip(OUT_NAMES, out, o32, o64):
+        if a is None:
+            assert o is None
+            continue
+        assert tuple(o.shape) == tuple(a.shape), f"{n}: shape {tuple(o.shape)} vs oracle {tuple(a.shape)}"
+        arbitrated(o, a, b, FWD_TOL, f"{name}/{n} (vs oracle)")
+    for kname in LEAF_KEYS:
+        grad_close(g[kname], g32[kname], g64[kname], f"{name}/d {kname}")

@@ -57,3 +57,8 @@ def test_pack_input():
 @pytest.mark.parametrize("case", ["city_x4", "kitti_x2", "train_lo"])
 def test_field_warps(case):
     parity.check_field_warps(DEV, case)
+
+
+@pytest.mark.parametrize("case", list(parity.SYNTH_CASES))
+def test_decode_oracle_direct(case):
+    parity.check_decode_synth(DEV, case)

@@ -122,3 +122,8 @@ def test_graphed_decode_matches_eager(dev):
 @pytest.mark.parametrize("case", ["city_x4", "kitti_x2", "train_lo"])
 def test_field_warps(dev, case):
     parity.check_field_warps(dev, case)
+
+
+@pytest.mark.parametrize("case", list(parity.SYNTH_CASES))
+def test_decode_oracle_direct(dev, case):
+    parity.check_decode_synth(dev, case)
