@@ -96,7 +96,7 @@ extern long long g_wb_launches;
 #define WB_OCC_LAYERS_FWD 4
 #endif
 #ifndef WB_OCC_PREP_FWD
-#define WB_OCC_PREP_FWD 3
+#define WB_OCC_PREP_FWD 4
 #endif
 #ifndef WB_OCC_GATHER_FWD
 #define WB_OCC_GATHER_FWD 4
