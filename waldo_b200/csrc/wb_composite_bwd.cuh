@@ -941,7 +941,8 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
     for (int s = 0; s < ix.n; ++s) {
       float gl = 0.f;
       int k = 0;
-      WB_UNROLL_NA for (int ss = 0; ss < WB_NEND; ++ss) if (ss == s) { gl = ga[ss] * aup[ss]; k = ix.k[ss]; }   // d / d l_k
+      if (NA > 8) { gl = ga[s] * aup[s]; k = ix.k[s]; }   // rolled form: the arrays live in local memory, index them directly
+      else { WB_UNROLL_NA for (int ss = 0; ss < WB_NEND; ++ss) if (ss == s) { gl = ga[ss] * aup[ss]; k = ix.k[ss]; } }   // d / d l_k
       if (k < 1) continue;   // warp-uniform
       const float* P = c.s_P + (k - 1) * Nl;
       float v[32];
@@ -978,7 +979,16 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
       __syncwarp();
       wb_colred_flush(cr, c.s_stage, ix.n, dst, g.W, 1);
       __syncwarp();
-    } else {
+    }
+#ifndef WB_HOST_EMU
+    else if (ix.n <= WB_STAGE_SLOTS) {   // the usual case: all live slots staged at once, destinations derived from the mask
+      for (int s = 0; s < ix.n; ++s) c.s_stage[WB_STAGE_AT(s, lane)] = ga[s] * ell[s];
+      __syncwarp();
+      wb_colred_flush_slots(cr, c.s_stage, wm, 1, a.d_a_lo + ((size_t)b * g.Tw + t) * L * HW, (size_t)HW, g.W, 1);
+      __syncwarp();
+    }
+#endif
+    else {
       for (int s0 = 0; s0 < ix.n; s0 += WB_STAGE_SLOTS) {
         float* dst[WB_STAGE_SLOTS];
         const int ns = min(WB_STAGE_SLOTS, ix.n - s0);
