@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-input-grad", action="store_true", help="experiment: do not request d input")
     ap.add_argument("--no-graph", action="store_true", help="inference workloads: eager launches instead of CUDA-graph replay")
+    ap.add_argument("--deterministic", action="store_true",
+                    help="backward with 64-bit fixed-point accumulation of the scatter targets (bit-identical gradients run to run)")
     args = ap.parse_args()
 
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -221,6 +223,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    wb.set_deterministic(args.deterministic)
 
     B, T, Tc, backward = spec["B"], spec["T"], spec["Tc"], spec["backward"]
     Tp = T - Tc
@@ -389,6 +392,7 @@ def main():
                        "layers": cfg.num_obj + 1, "channels": 3 + cfg.num_lyt, "l2": "working set per step far larger than the 126 MB L2 (input %.2f GB), no flush needed" % (B * T * (3 + cfg.num_lyt) * Hd * Wd * 4 / 1e9),
                        "input": "8-bit RGB + label map expanded to fp32 on the device (pack_input)",
                        "launch": "one CUDA graph replay per step" if use_graph["on"] else "eager kernel launches (autograd)",
+                       "gradient_accumulation": ("64-bit fixed point (deterministic)" if args.deterministic else "fp32 red.global (default)") if backward else None,
                        "parallelism": f"dp{world} batch-sharded" + (", flat fp32 all-reduce of 56.6 MB per step" if grad_buf is not None else "")},
             "clocks": clocks.summary(), "gpu_launches": launches,
             "hbm_frac_step": ((fwd_b + bwd_b) / (ms_step * 1e-3) / 1e9) / peak,

@@ -216,6 +216,19 @@ typedef struct {
   float* glue;                /* scratch (B, Tc, Tp, 3, Hd, Wd): d score, d flow x, d flow y handed from the gather to the layer kernel */
   int stages;                 /* 0 = everything; else bit 0 = HD gather backward, bit 1 = HD layer backward,
                                  bit 3 = HD context-alpha backward, bit 2 = the rest (low-res chain) */
+  /* Deterministic accumulation (optional; det_shadow == NULL selects fire-and-forget float reductions, whose addition order
+     -- like ATen's grid_sampler_2d_backward -- is not fixed).  With det_shadow set, every scatter target (d_input, the four
+     d_*_grid_*, d_obj_alpha, d_bg_alpha, d_alpha_acc, d_f_lo, d_a_lo) is accumulated as 64-bit fixed point (integer
+     additions commute: the result does not depend on the order) and converted to fp32 once all its addends are in.  All
+     those targets must then be carved from ONE float arena [det_base, det_base + det_n); det_shadow is an int64 arena of
+     det_n elements (element i shadows det_base[i]), zero-filled by the caller like the targets.  The fixed-point unit is
+     2^-26 of the largest upstream gradient magnitude (rounded up to a power of two), found by the call itself; sums up to
+     2^37 times that magnitude are representable. */
+  const float* det_base;
+  int64_t* det_shadow;
+  int64_t det_n;
+  float* det_scale;           /* device scratch, 4 floats: [0] scale, [1] 1/scale, [2] bits of max|upstream|, [3] != 0 after the
+                                 call if an addend left the fixed-point range (the gradients are then invalid) */
 } waldo_decode_bwd_t;
 int waldo_decode_bwd(const waldo_decode_bwd_t*, waldo_stream_t);
 

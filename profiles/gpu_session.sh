@@ -12,6 +12,8 @@ bench)
   timeout 600 python bench.py > $OUT/${TAG}_bench.jsonl 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; cat $OUT/${TAG}_bench.jsonl; tail -3 $OUT/${TAG}_bench.err;;
 benchq)
   timeout 600 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench.jsonl 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; cat $OUT/${TAG}_bench.jsonl; tail -3 $OUT/${TAG}_bench.err;;
+benchdet)
+  timeout 600 python bench.py --no-cpu-baseline --deterministic > $OUT/${TAG}_bench_det.jsonl 2> $OUT/${TAG}_bench_det.err; echo "benchdet rc=$?"; cat $OUT/${TAG}_bench_det.jsonl; tail -3 $OUT/${TAG}_bench_det.err;;
 launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_launches.log 2>&1; echo "launches rc=$?";;

@@ -228,6 +228,38 @@ def check_decode(dev, case):
         grad_close(g[kname], g32[kname], g64[kname], f"{case}/d {kname}")
 
 
+def check_decode_deterministic(dev, case):
+    """Deterministic mode (64-bit fixed-point accumulation of every scatter target, include/waldo_b200.h det_* fields):
+    the gradients meet the same bar as the default mode, are bit-identical from run to run, no addend left the
+    fixed-point range, and the forward outputs are untouched."""
+    from waldo_b200 import functional as F
+    cfg, _, z = load_case(case)
+    _, g32 = oracle_decode(cfg, z, torch.float32)
+    _, g64 = oracle_decode(cfg, z, torch.float64)
+    out0, g0 = kernel_decode(dev, cfg, z)
+    assert not wb.is_deterministic()
+    wb.set_deterministic(True)
+    try:
+        assert wb.is_deterministic()
+        out1, g1 = kernel_decode(dev, cfg, z)
+        sc = F.LAST_DET_SCALE.cpu()
+        assert float(sc[3]) == 0.0, "fixed-point overflow flag set"
+        assert float(sc[0]) * float(sc[1]) == 1.0 and float(sc[2]) > 0
+        out2, g2 = kernel_decode(dev, cfg, z)
+    finally:
+        wb.set_deterministic(False)
+    for a, b in zip(out0, out1):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert torch.equal(a, b)
+    for kname in LEAF_KEYS:
+        assert torch.equal(g1[kname], g2[kname]), f"{case}/d {kname}: deterministic mode is not run-to-run identical"
+        grad_close(g1[kname], g32[kname], g64[kname], f"{case}/d {kname} (deterministic)")
+        # against the float-reduction path: both are sums of the same addends, differing only by rounding
+        ref = g0[kname]
+        assert float((g1[kname] - ref).abs().max()) <= 1e-5 * max(float(ref.abs().max()), 1e-30), f"{case}/d {kname}: det vs default"
+
+
 def check_end_to_end(dev, case):
     """Tier T2: control points -> grids -> decode, statistical agreement with the reference's outputs, plus gradients
     reaching every leaf (obj_pose, bg_pose, occ_score, obj_alpha, cls, input) through the whole chain."""
@@ -257,6 +289,45 @@ def check_end_to_end(dev, case):
         # chained through the discontinuous inverse warp and the cond~1e4 TPS system: statistical bound only
         assert rel <= 5e-2, f"{case}/d {k}: rel err {rel:.3e}"
         assert float(v.grad.abs().max()) > 0 or scale == 0
+
+
+def _chain_grads(dev, cfg, d, warper, om, bg):
+    lv = {k: d[k].clone().to(dev).requires_grad_(True) for k in ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")}
+    occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, lv["obj_alpha_raw"], om, bg, lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
+    out = wb.decode_output(warper, lv["input"], grid, occ, oa, ba, lv["cls"], d["ctx_ts"].to(dev), d["pred_ts"].to(dev), cfg.restrict_to_ctx)
+    output, flow, _, alpha, raw_alpha, raw, _ = out
+    # a loss that reaches every output with non-uniform weights
+    w = torch.linspace(0.5, 1.5, output.shape[-1], device=dev)
+    loss = (output * w).sum() + (raw * raw).mean() * 1e3 + (flow * w).sum() * 0.1 + (raw_alpha * w).sum() + alpha.sum() * 1e-2
+    loss.backward()
+    return {k: v.grad for k, v in lv.items()}
+
+
+def check_chain_deterministic(dev, cfg=None, B=1, T=5, Tc=4, seed=0):
+    """Control points -> grids -> occlusion matrix -> decode -> loss, backward to every leaf, in deterministic mode: all
+    gradients bit-identical from run to run (TPS / inverse-warp / occlusion backward use ordered reductions, the decode
+    backward 64-bit fixed-point accumulation), and equal to the default mode up to rounding."""
+    from waldo_b200 import functional as F
+    cfg = cfg or wo.PathConfig()
+    opt = make_opt(cfg)
+    warper = wb.Warper(opt).to(dev)
+    d = wo.synth_inputs(cfg, B, T, Tc, seed=seed)
+    om, bg = wb.alpha_masks(opt)
+    om, bg = (om.to(dev) if torch.is_tensor(om) else om), bg.to(dev)
+    g0 = _chain_grads(dev, cfg, d, warper, om, bg)
+    wb.set_deterministic(True)
+    try:
+        g1 = _chain_grads(dev, cfg, d, warper, om, bg)
+        assert float(F.LAST_DET_SCALE[3]) == 0.0, "fixed-point overflow flag set"
+        g2 = _chain_grads(dev, cfg, d, warper, om, bg)
+    finally:
+        wb.set_deterministic(False)
+    for k in g1:
+        assert bool(torch.isfinite(g1[k]).all()), k
+        assert torch.equal(g1[k], g2[k]), f"d {k}: not bit-identical from run to run in deterministic mode"
+        scale = max(float(g0[k].abs().max()), 1e-30)
+        assert float((g1[k] - g0[k]).abs().max()) <= 1e-4 * scale, f"d {k}: deterministic vs default mode"
+    return g0, g1
 
 
 def check_wif(dev, case):

@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_ctypes_structs_mirror_the_header():
     from waldo_b200 import _lib
     txt = _header()
-    ctype_of = {"int": C.c_int, "float": C.c_float}
+    ctype_of = {"int": C.c_int, "float": C.c_float, "int64_t": C.c_longlong}
     for m in re.finditer(r"typedef struct \{(.*?)\}\s*(\w+);", txt, flags=re.S):
         body, name = m.group(1), m.group(2)
         st = _lib.STRUCT_OF[name]

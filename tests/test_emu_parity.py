@@ -37,6 +37,11 @@ def test_decode(case):
 
 
 @pytest.mark.parametrize("case", parity.CASES)
+def test_decode_deterministic(case):
+    parity.check_decode_deterministic(DEV, case)
+
+
+@pytest.mark.parametrize("case", parity.CASES)
 def test_end_to_end(case):
     parity.check_end_to_end(DEV, case)
 
@@ -62,3 +67,8 @@ def test_field_warps(case):
 @pytest.mark.parametrize("case", list(parity.SYNTH_CASES))
 def test_decode_oracle_direct(case):
     parity.check_decode_synth(DEV, case)
+
+
+def test_small_chain_deterministic():
+    cfg, (B, T, Tc), _ = parity.load_case("train_lo")
+    parity.check_chain_deterministic(DEV, cfg, B, T, Tc, seed=5)

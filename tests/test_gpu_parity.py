@@ -38,6 +38,11 @@ def test_decode(dev, case):
 
 
 @pytest.mark.parametrize("case", parity.CASES)
+def test_decode_deterministic(dev, case):
+    parity.check_decode_deterministic(dev, case)
+
+
+@pytest.mark.parametrize("case", parity.CASES)
 def test_end_to_end(dev, case):
     parity.check_end_to_end(dev, case)
 
@@ -62,6 +67,17 @@ def test_full_size_properties(dev):
     """BASELINE config shape (Cityscapes 512x1024, 16 objects, 20 classes), B=1, 4 contexts -> 1 future frame:
     size-independent properties of the fused path."""
     parity.check_full_size(dev)
+
+
+def test_full_size_deterministic_gradients(dev):
+    """BASELINE shape (Cityscapes 512x1024, 17 layers, 23 channels), B=1: the whole backward in deterministic mode is
+    bit-identical from run to run and agrees with the default (float-reduction) mode up to rounding."""
+    parity.check_chain_deterministic(dev)
+
+
+def test_small_chain_deterministic_gradients(dev):
+    cfg, (B, T, Tc), _ = parity.load_case("train_lo")
+    parity.check_chain_deterministic(dev, cfg, B, T, Tc, seed=5)
 
 
 def test_pack_input(dev):

@@ -77,7 +77,8 @@ class DecodeBwd(C.Structure):
                 ("d_alpha_acc", c_void_p), ("d_f_lo", c_void_p), ("d_a_lo", c_void_p),
                 ("d_prof_p", c_void_p), ("d_prof_sum", c_void_p),
                 ("red_ctas", C.c_int), ("occ_part", c_void_p), ("prof_p_part", c_void_p), ("cls_part", c_void_p),
-                ("up_tab", c_void_p), ("glue", c_void_p), ("stages", C.c_int)]
+                ("up_tab", c_void_p), ("glue", c_void_p), ("stages", C.c_int),
+                ("det_base", c_void_p), ("det_shadow", c_void_p), ("det_n", C.c_longlong), ("det_scale", c_void_p)]
 
 
 class WifFuseFwd(C.Structure):

@@ -6,7 +6,12 @@
 #include "wb_geom.cuh"
 #include "wb_prep.cuh"
 #include "wb_composite.cuh"
-#include "wb_composite_bwd.cuh"
+#define WB_DET 0
+#include "wb_composite_bwd.cuh"   // namespace wb_plain: float reductions (default)
+#undef WB_DET
+#define WB_DET 1
+#include "wb_composite_bwd.cuh"   // namespace wb_fixed: 64-bit fixed-point accumulation (deterministic gradients)
+#undef WB_DET
 #include "wb_wif.cuh"
 #include "wb_pack.cuh"
 #include "wb_field.cuh"
@@ -231,7 +236,7 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
 
 int waldo_decode_bwd(const waldo_decode_bwd_t* a, waldo_stream_t st) {
   WB_REQUIRE(a, "decode_bwd: null argument");
-  return wb_decode_bwd_launch(*a, st);
+  return a->det_shadow ? wb_fixed::wb_decode_bwd_launch(*a, st) : wb_plain::wb_decode_bwd_launch(*a, st);
 }
 
 // ------------------------------------------------------------------------------------------ WIF fuse tail

@@ -40,6 +40,7 @@ static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; ret
 static inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }
 static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
@@ -195,6 +196,64 @@ WB_DEV void wb_red(float* p, float v) {
   //  also yields REDG, but measured 3-4 % slower in the layer kernels on B200, profiles/r1_v21)
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v));
 #endif
+}
+
+// ------------------------------------------------------------------ deterministic (fixed-point) accumulation
+// Opt-in replacement of wb_red for the scatter targets of decode_bwd (include/waldo_b200.h, det_* fields): the addend is
+// rounded to a multiple of the call's fixed-point unit and added as a 64-bit INTEGER to the shadow element of *p.  Integer
+// additions commute and associate exactly, so the sum does not depend on the order in which the lanes / CTAs arrive.
+// sc[0] = scale (a power of two), sc[3] = overflow flag.
+#define WB_DET_BITS 26          // fixed-point unit = 2^-26 of the largest upstream gradient magnitude (as a power of two):
+                                // 1.5e-8 of it, i.e. fp32-grade for the image gradients (addends <= 2 max|upstream|), with
+                                // 2^37 of it as the range of a sum (intermediate gradients reach ~1e6 x the upstream ones
+                                // where the fused score `norm` is small: measured 1.9e6 on the KITTI fixture)
+WB_DEV void wb_red_fixed(const float* base, int64_t* shadow, float* sc, float* p, float v) {
+  const float x = v * __ldg(sc);
+  if (!(fabsf(x) < 4.0e18f)) { sc[3] = 1.f; return; }   // beyond 2^62 units (or NaN): flag it, never wrap silently
+  unsigned long long* q = reinterpret_cast<unsigned long long*>(shadow + (p - base));
+#ifdef WB_HOST_EMU
+  *q += (unsigned long long)llrintf(x);
+#else
+  const unsigned long long iv = (unsigned long long)__float2ll_rn(x);
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(q), "l"(iv));
+#endif
+}
+
+// max |x| over a buffer as the bit pattern of a non-negative float (ordered like unsigned integers; a NaN sorts above inf)
+__global__ void k_det_absmax(const float* __restrict__ x, long long n, float* sc) {
+  unsigned m = 0u;
+  for (long long i = (long long)blockIdx.x * wb_nthr() + wb_tid(); i < n; i += (long long)gridDim.x * wb_nthr()) {
+    union { float f; unsigned u; } c;
+    c.f = __ldg(x + i);
+    const unsigned b = c.u & 0x7fffffffu;
+    m = b > m ? b : m;
+  }
+#ifndef WB_HOST_EMU
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) != 0) return;
+#endif
+  if (m) atomicMax(reinterpret_cast<unsigned*>(sc) + 2, m);
+}
+__global__ void k_det_clear(float* sc) { if (blockIdx.x == 0 && wb_tid() == 0) { sc[0] = 1.f; sc[1] = 1.f; sc[2] = 0.f; sc[3] = 0.f; } }
+__global__ void k_det_scale(float* sc) {
+  if (blockIdx.x != 0 || wb_tid() != 0) return;
+  const float gmax = sc[2];   // bits of a non-negative float
+  float scale = 1.f, inv = 1.f;
+  if (!(gmax < 3.0e38f)) sc[3] = 1.f;   // inf / NaN upstream
+  else if (gmax > 0.f) {
+    int e;
+    frexpf(gmax, &e);                   // gmax <= 2^e
+    int se = WB_DET_BITS - e;
+    se = se > 100 ? 100 : (se < -100 ? -100 : se);
+    scale = ldexpf(1.f, se); inv = ldexpf(1.f, -se);
+  }
+  sc[0] = scale; sc[1] = inv;
+}
+// shadow -> fp32 (one rounding), grid-stride
+__global__ void k_det_convert(const int64_t* __restrict__ sh, float* __restrict__ dst, long long n, const float* __restrict__ sc) {
+  const double inv = (double)sc[1];
+  for (long long i = (long long)blockIdx.x * wb_nthr() + wb_tid(); i < n; i += (long long)gridDim.x * wb_nthr())
+    dst[i] = (float)((double)sh[i] * inv);
 }
 
 #ifndef WB_HOST_EMU

@@ -9,16 +9,40 @@
 //   * HD scatter targets (d input, d context opacity): red.global.add.f32 (wb_red), neighbouring lanes merged by shuffle.
 // All layer loops run over the warp-wide union of live layers (see wb_composite.cuh); rows with <= 8 live layers use the
 // lanes-per-layer form of the layer kernel.
-#pragma once
+//
+// This file is included TWICE by waldo_abi.cu: with WB_DET 0 (namespace wb_plain: fire-and-forget float reductions, the
+// default) and with WB_DET 1 (namespace wb_fixed: 64-bit fixed-point accumulation of every scatter target, run-to-run
+// bit-identical gradients; include/waldo_b200.h det_* fields).  Two instantiations instead of a run-time switch, so that
+// the default kernels carry no trace of the deterministic path (same SASS as before it existed).
 #include "wb_common.cuh"
 #include "wb_prep.cuh"
 #include "wb_composite.cuh"
 
+#ifndef WB_BWD_SHARED_DECLS
+#define WB_BWD_SHARED_DECLS
 typedef waldo_decode_bwd_t WbDecB;
+#ifndef WB_HOST_EMU
+static int wb_check_launch(const char* file, int line);
+#endif
+static int wb_fail(int code, const char* fmt, ...);
+#endif
+
+#undef WB_RED
+#undef WB_RED_NZ
+#if WB_DET
+namespace wb_fixed {
+// every call site has the kernel argument `a` in scope
+#define WB_RED(p, v) wb_red_fixed(a.det_base, a.det_shadow, a.det_scale, (p), (v))
+#define WB_RED_NZ(p, v) wb_atomic_add(a, (p), (v))
+WB_DEV void wb_atomic_add(const WbDecB& a, float* p, float v) { if (v != 0.f) WB_RED(p, v); }
+#else
+namespace wb_plain {
+#define WB_RED(p, v) wb_red((p), (v))
+#define WB_RED_NZ(p, v) wb_atomic_add((p), (v))
+WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) wb_red(p, v); }
+#endif
 
 #define WB_NWARP (WB_TILE_PX / 32)
-
-WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) wb_red(p, v); }
 
 // ---------------------------------------------------------------------------- transpose of the bilinear up-sampling
 // A warp is one row of 32 HD pixels, so all its lanes share the two low-res rows and touch a short run of low-res
@@ -93,7 +117,7 @@ WB_DEV WbColRed wb_colred_setup(const float* __restrict__ tab, int x0, int i0_fi
 }
 
 // reduce `nv` staged values per lane (s_stage[v * WB_WARP + lane]) into dst[(row * W + col) * stride + v * vstride]
-WB_DEV void wb_colred_flush(const WbColRed& cr, const float* s_stage, int nv, float* const* dst, int W, int stride) {
+WB_DEV void wb_colred_flush(const WbDecB& a, const WbColRed& cr, const float* s_stage, int nv, float* const* dst, int W, int stride) {
   WB_UNROLL for (int cpl = 0; cpl < WB_CPL; ++cpl) {
     if (cr.col[cpl] >= 0) {
       for (int v = 0; v < nv; ++v) {
@@ -101,8 +125,8 @@ WB_DEV void wb_colred_flush(const WbColRed& cr, const float* s_stage, int nv, fl
         float acc = 0.f;
         WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) acc += cr.w[cpl][t] * sv[t];
         if (acc != 0.f) {
-          wb_red(dst[v] + ((size_t)cr.row0 * W + cr.col[cpl]) * stride, acc * cr.wy0);
-          wb_red(dst[v] + ((size_t)cr.row1 * W + cr.col[cpl]) * stride, acc * cr.wy1);
+          WB_RED(dst[v] + ((size_t)cr.row0 * W + cr.col[cpl]) * stride, acc * cr.wy0);
+          WB_RED(dst[v] + ((size_t)cr.row1 * W + cr.col[cpl]) * stride, acc * cr.wy1);
         }
       }
     }
@@ -200,8 +224,8 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
         if (dal) {
           float* o0 = dal + (size_t)k * HWd + t2.o0;
           float* o1 = dal + (size_t)k * HWd + t2.o1;
-          wb_atomic_add(o0, t2.w[0] * gr); wb_atomic_add(o0 + 1, t2.w[1] * gr);
-          wb_atomic_add(o1, t2.w[2] * gr); wb_atomic_add(o1 + 1, t2.w[3] * gr);
+          WB_RED_NZ(o0, t2.w[0] * gr); WB_RED_NZ(o0 + 1, t2.w[1] * gr);
+          WB_RED_NZ(o1, t2.w[2] * gr); WB_RED_NZ(o1 + 1, t2.w[3] * gr);
         }
       }
     }
@@ -212,7 +236,7 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
       WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s)
         if (s < ix.n) {
           float* o = a.d_f_lo + (pair * L + ix.k[s]) * HW * 2 + (size_t)px.o00 * 2;
-          wb_atomic_add(o, gFx[s]); wb_atomic_add(o + 1, gFy[s]);
+          WB_RED_NZ(o, gFx[s]); WB_RED_NZ(o + 1, gFy[s]);
         }
     } else {
       const int lane = wb_lane();
@@ -225,7 +249,7 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
           dst[2 * s] = base; dst[2 * s + 1] = base + 1;
         }
         __syncwarp();
-        wb_colred_flush(cr, c.s_stage, 2 * ix.n, dst, g.W, 2);
+        wb_colred_flush(a, cr, c.s_stage, 2 * ix.n, dst, g.W, 2);
         __syncwarp();
       } else {
         for (int s0 = 0; s0 < ix.n; s0 += WB_STAGE_SLOTS) {
@@ -238,7 +262,7 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
             dst[2 * j] = base; dst[2 * j + 1] = base + 1;
           }
           __syncwarp();
-          wb_colred_flush(cr, c.s_stage, 2 * ns, dst, g.W, 2);
+          wb_colred_flush(a, cr, c.s_stage, 2 * ns, dst, g.W, 2);
           __syncwarp();
         }
       }
@@ -286,7 +310,7 @@ WB_DEV void wb_slot_transpose_sum(float* v, int slot) {
 }
 
 // flush the staged per-(slot, pixel) values of one row: value rows 2*s (x) and 2*s+1 (y) of slot s go to layer k_s of d_f_lo
-WB_DEV void wb_colred_flush_slots(const WbColRed& cr, const float* s_stage, unsigned wm, int ncomp, float* base, size_t layer_stride,
+WB_DEV void wb_colred_flush_slots(const WbDecB& a, const WbColRed& cr, const float* s_stage, unsigned wm, int ncomp, float* base, size_t layer_stride,
                                   int W, int stride) {
   if (cr.col[0] < 0) return;
   int s = 0;
@@ -298,8 +322,8 @@ WB_DEV void wb_colred_flush_slots(const WbColRed& cr, const float* s_stage, unsi
       WB_UNROLL for (int t = 0; t < WB_COL_TAPS; ++t) acc += cr.w[0][t] * sv[t];
       if (acc != 0.f) {
         float* dst = base + (size_t)k * layer_stride + comp;
-        wb_red(dst + ((size_t)cr.row0 * W + cr.col[0]) * stride, acc * cr.wy0);
-        wb_red(dst + ((size_t)cr.row1 * W + cr.col[0]) * stride, acc * cr.wy1);
+        WB_RED(dst + ((size_t)cr.row0 * W + cr.col[0]) * stride, acc * cr.wy0);
+        WB_RED(dst + ((size_t)cr.row1 * W + cr.col[0]) * stride, acc * cr.wy1);
       }
     }
   }
@@ -408,15 +432,15 @@ WB_DEV void wb_lanes_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbColR
         if (dal_k) {
           float* q0 = dal_k + t2.o0;
           float* q1 = dal_k + t2.o1;
-          wb_atomic_add(q0, t2.w[0] * gR); wb_atomic_add(q0 + 1, t2.w[1] * gR);
-          wb_atomic_add(q1, t2.w[2] * gR); wb_atomic_add(q1 + 1, t2.w[3] * gR);
+          WB_RED_NZ(q0, t2.w[0] * gR); WB_RED_NZ(q0 + 1, t2.w[1] * gR);
+          WB_RED_NZ(q1, t2.w[2] * gR); WB_RED_NZ(q1 + 1, t2.w[3] * gR);
         }
       }
       // ---- B5(up) backward
       if (a.d_f_lo && valid) {
         if (c.lowres_direct) {
           float* o = a.d_f_lo + (pair * L + k) * HW * 2 + (size_t)o00 * 2;
-          wb_atomic_add(o, gFx); wb_atomic_add(o + 1, gFy);
+          WB_RED_NZ(o, gFx); WB_RED_NZ(o + 1, gFy);
         } else {
           c.s_stage[WB_STAGE_AT(2 * slot, p)] = gFx;
           c.s_stage[WB_STAGE_AT(2 * slot + 1, p)] = gFy;
@@ -425,7 +449,7 @@ WB_DEV void wb_lanes_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbColR
     }
     if (stage) {
       __syncwarp();
-      wb_colred_flush_slots(cr, c.s_stage, wm, 2, a.d_f_lo + pair * L * HW * 2, (size_t)HW * 2, g.W, 2);
+      wb_colred_flush_slots(a, cr, c.s_stage, wm, 2, a.d_f_lo + pair * L * HW * 2, (size_t)HW * 2, g.W, 2);
       __syncwarp();
     }
   }
@@ -553,22 +577,22 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd(Wb
                 if (FAST) {
                   const float c1 = w[i][1] * go, c3 = w[i][3] * go;
                   const float r1 = __shfl_up_sync(0xffffffffu, c1, 1), r3 = __shfl_up_sync(0xffffffffu, c3, 1);
-                  wb_red(dl + o0[i], w[i][0] * go + (mergeL0[i] ? r1 : 0.f));
-                  if (!skipR0[i]) wb_red(dl + o0[i] + 1, c1);
-                  wb_red(dl + o1[i], w[i][2] * go + (mergeL1[i] ? r3 : 0.f));
-                  if (!skipR1[i]) wb_red(dl + o1[i] + 1, c3);
+                  WB_RED(dl + o0[i], w[i][0] * go + (mergeL0[i] ? r1 : 0.f));
+                  if (!skipR0[i]) WB_RED(dl + o0[i] + 1, c1);
+                  WB_RED(dl + o1[i], w[i][2] * go + (mergeL1[i] ? r3 : 0.f));
+                  if (!skipR1[i]) WB_RED(dl + o1[i] + 1, c3);
                 } else
 #endif
                 {
-                  wb_red(dl + o0[i], w[i][0] * go); wb_red(dl + o0[i] + 1, w[i][1] * go);
-                  wb_red(dl + o1[i], w[i][2] * go); wb_red(dl + o1[i] + 1, w[i][3] * go);
+                  WB_RED(dl + o0[i], w[i][0] * go); WB_RED(dl + o0[i] + 1, w[i][1] * go);
+                  WB_RED(dl + o1[i], w[i][2] * go); WB_RED(dl + o1[i] + 1, w[i][3] * go);
                 }
               }
             }
           }
           if (dself && active) {   // lvd.py:845: the target frame passes straight through
             const float nself = (1.f + 1e-6f) / D;
-            wb_atomic_add(dself + choff, (drself ? __ldg(drself + choff) : 0.f) + nself * gO);
+            WB_RED_NZ(dself + choff, (drself ? __ldg(drself + choff) : 0.f) + nself * gO);
           }
           choff += HWd;
         }
@@ -716,10 +740,10 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd_as
           float* dl = dsr[i] + choff;
           const float c1 = w[i][1] * go, c3 = w[i][3] * go;
           const float r1 = __shfl_up_sync(0xffffffffu, c1, 1), r3 = __shfl_up_sync(0xffffffffu, c3, 1);
-          wb_red(dl + o0[i], w[i][0] * go + (mergeL0[i] ? r1 : 0.f));
-          if (!skipR0[i]) wb_red(dl + o0[i] + 1, c1);
-          wb_red(dl + o1[i], w[i][2] * go + (mergeL1[i] ? r3 : 0.f));
-          if (!skipR1[i]) wb_red(dl + o1[i] + 1, c3);
+          WB_RED(dl + o0[i], w[i][0] * go + (mergeL0[i] ? r1 : 0.f));
+          if (!skipR0[i]) WB_RED(dl + o0[i] + 1, c1);
+          WB_RED(dl + o1[i], w[i][2] * go + (mergeL1[i] ? r3 : 0.f));
+          if (!skipR1[i]) WB_RED(dl + o1[i] + 1, c3);
         }
         choff += HWd;
       }
@@ -969,7 +993,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   if (a.d_a_lo) {
     if (c.lowres_direct) {
       WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s)
-        if (s < ix.n) wb_atomic_add(a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s]) * HW + o00, ga[s] * ell[s]);
+        if (s < ix.n) WB_RED_NZ(a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s]) * HW + o00, ga[s] * ell[s]);
     } else if constexpr (NA <= WB_STAGE_SLOTS) {
       float* dst[NA];
       WB_UNROLL for (int s = 0; s < NA; ++s) {
@@ -977,14 +1001,14 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
         dst[s] = a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s]) * HW;
       }
       __syncwarp();
-      wb_colred_flush(cr, c.s_stage, ix.n, dst, g.W, 1);
+      wb_colred_flush(a, cr, c.s_stage, ix.n, dst, g.W, 1);
       __syncwarp();
     }
 #ifndef WB_HOST_EMU
     else if (ix.n <= WB_STAGE_SLOTS) {   // the usual case: all live slots staged at once, destinations derived from the mask
       for (int s = 0; s < ix.n; ++s) c.s_stage[WB_STAGE_AT(s, lane)] = ga[s] * ell[s];
       __syncwarp();
-      wb_colred_flush_slots(cr, c.s_stage, wm, 1, a.d_a_lo + ((size_t)b * g.Tw + t) * L * HW, (size_t)HW, g.W, 1);
+      wb_colred_flush_slots(a, cr, c.s_stage, wm, 1, a.d_a_lo + ((size_t)b * g.Tw + t) * L * HW, (size_t)HW, g.W, 1);
       __syncwarp();
     }
 #endif
@@ -997,7 +1021,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
           dst[j] = a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s0 + j]) * HW;
         }
         __syncwarp();
-        wb_colred_flush(cr, c.s_stage, ns, dst, g.W, 1);
+        wb_colred_flush(a, cr, c.s_stage, ns, dst, g.W, 1);
         __syncwarp();
       }
     }
@@ -1007,7 +1031,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
     WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dot += gsm[cc] * sm[cc];
     float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd + q;
     WB_UNROLL for (int cc = 0; cc < NN; ++cc)
-      if (NLC > 0 || cc < Nl) { wb_red(o, sm[cc] * (gsm[cc] - dot)); o += HWd; }   // fire-and-forget reduction
+      if (NLC > 0 || cc < Nl) { WB_RED(o, sm[cc] * (gsm[cc] - dot)); o += HWd; }   // fire-and-forget reduction
   }
 }
 
@@ -1159,7 +1183,7 @@ WB_DEV void wb_lanes_prep_bwd(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
         if (actf != 0.f) {
           float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3 + cbase) * HWd + q;
           WB_UNROLL for (int i = 0; i < NS; ++i) {
-            if (cbase + i < Nl) wb_red(o, smc[i] * (v[i] - dot));   // fire-and-forget reduction
+            if (cbase + i < Nl) WB_RED(o, smc[i] * (v[i] - dot));   // fire-and-forget reduction
             o += HWd;
           }
         }
@@ -1167,13 +1191,13 @@ WB_DEV void wb_lanes_prep_bwd(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
     }
     // ---- up-sampling backward: d a_lo
     if (a.d_a_lo && valid) {
-      if (c.lowres_direct) wb_atomic_add(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + o00, ga * ell);
+      if (c.lowres_direct) WB_RED_NZ(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + o00, ga * ell);
       else c.s_stage[WB_STAGE_AT(slot, p)] = ga * ell;
     }
   }
   if (stage) {
     __syncwarp();
-    wb_colred_flush_slots(cr, c.s_stage, wm, 1, a.d_a_lo + ((size_t)b * g.Tw + t) * L * HW, (size_t)HW, g.W, 1);
+    wb_colred_flush_slots(a, cr, c.s_stage, wm, 1, a.d_a_lo + ((size_t)b * g.Tw + t) * L * HW, (size_t)HW, g.W, 1);
     __syncwarp();
   }
   if (c.s_acc) {
@@ -1373,10 +1397,10 @@ __global__ void __launch_bounds__(256) k_class_profile_bwd(WbDecB a) {
         for (int c = 0; c < Nl; ++c) {
           float* pl = base + (size_t)c * HWd;
           const float gv = glyt[c];
-          wb_atomic_add(pl + (size_t)ay.i0 * g.Wd + ax.i0, gv * ax.l0 * ay.l0);
-          wb_atomic_add(pl + (size_t)ay.i0 * g.Wd + ax.i1, gv * ax.l1 * ay.l0);
-          wb_atomic_add(pl + (size_t)ay.i1 * g.Wd + ax.i0, gv * ax.l0 * ay.l1);
-          wb_atomic_add(pl + (size_t)ay.i1 * g.Wd + ax.i1, gv * ax.l1 * ay.l1);
+          WB_RED_NZ(pl + (size_t)ay.i0 * g.Wd + ax.i0, gv * ax.l0 * ay.l0);
+          WB_RED_NZ(pl + (size_t)ay.i0 * g.Wd + ax.i1, gv * ax.l1 * ay.l0);
+          WB_RED_NZ(pl + (size_t)ay.i1 * g.Wd + ax.i0, gv * ax.l0 * ay.l1);
+          WB_RED_NZ(pl + (size_t)ay.i1 * g.Wd + ax.i1, gv * ax.l1 * ay.l1);
         }
       }
     }
@@ -1436,14 +1460,14 @@ __global__ void k_project_alpha_bwd(WbDecB a) {
     const float vsw = (m & 4) ? (__ldg(q + w) + 1.f) * 0.5f : 0.f, vse = (m & 8) ? (__ldg(q + w + 1) + 1.f) * 0.5f : 0.f;
     if (dplane) {
       float* o = dplane + off;
-      if (m & 1) wb_atomic_add(o, 0.5f * tp.nw * gv);
-      if (m & 2) wb_atomic_add(o + 1, 0.5f * tp.ne * gv);
-      if (m & 4) wb_atomic_add(o + w, 0.5f * tp.sw * gv);
-      if (m & 8) wb_atomic_add(o + w + 1, 0.5f * tp.se * gv);
+      if (m & 1) WB_RED_NZ(o, 0.5f * tp.nw * gv);
+      if (m & 2) WB_RED_NZ(o + 1, 0.5f * tp.ne * gv);
+      if (m & 4) WB_RED_NZ(o + w, 0.5f * tp.sw * gv);
+      if (m & 8) WB_RED_NZ(o + w + 1, 0.5f * tp.se * gv);
     }
     if (dsg) {
-      wb_atomic_add(dsg, gv * ((vne - vnw) * tp.wy0 + (vse - vsw) * tp.wy1) * (0.5f * (float)w));
-      wb_atomic_add(dsg + 1, gv * ((vsw - vnw) * tp.wx0 + (vse - vne) * tp.wx1) * (0.5f * (float)h));
+      WB_RED_NZ(dsg, gv * ((vne - vnw) * tp.wy0 + (vse - vsw) * tp.wy1) * (0.5f * (float)w));
+      WB_RED_NZ(dsg + 1, gv * ((vsw - vnw) * tp.wx0 + (vse - vne) * tp.wx1) * (0.5f * (float)h));
     }
   }
 }
@@ -1494,16 +1518,16 @@ __global__ void k_layer_flow_lo_bwd(WbDecB a) {
         gsx += gc * ((vne - vnw) * t.wy0 + (vse - vsw) * t.wy1);
         gsy += gc * ((vsw - vnw) * t.wx0 + (vse - vne) * t.wx1);
         if (dtg && c_t != u) {
-          if (m & 1) { wb_atomic_add(dtg + base_c + o + c, t.nw * gc); wb_atomic_add(dtg + base_u + o + c, -t.nw * gc); }
-          if (m & 2) { wb_atomic_add(dtg + base_c + o + 2 + c, t.ne * gc); wb_atomic_add(dtg + base_u + o + 2 + c, -t.ne * gc); }
-          if (m & 4) { wb_atomic_add(dtg + base_c + o + 2 * w + c, t.sw * gc); wb_atomic_add(dtg + base_u + o + 2 * w + c, -t.sw * gc); }
-          if (m & 8) { wb_atomic_add(dtg + base_c + o + 2 * w + 2 + c, t.se * gc); wb_atomic_add(dtg + base_u + o + 2 * w + 2 + c, -t.se * gc); }
+          if (m & 1) { WB_RED_NZ(dtg + base_c + o + c, t.nw * gc); WB_RED_NZ(dtg + base_u + o + c, -t.nw * gc); }
+          if (m & 2) { WB_RED_NZ(dtg + base_c + o + 2 + c, t.ne * gc); WB_RED_NZ(dtg + base_u + o + 2 + c, -t.ne * gc); }
+          if (m & 4) { WB_RED_NZ(dtg + base_c + o + 2 * w + c, t.sw * gc); WB_RED_NZ(dtg + base_u + o + 2 * w + c, -t.sw * gc); }
+          if (m & 8) { WB_RED_NZ(dtg + base_c + o + 2 * w + 2 + c, t.se * gc); WB_RED_NZ(dtg + base_u + o + 2 * w + 2 + c, -t.se * gc); }
         }
       }
     }
     if (dsg) {
-      wb_atomic_add(dsg, gsx * (0.5f * (float)w));
-      wb_atomic_add(dsg + 1, gsy * (0.5f * (float)h));
+      WB_RED_NZ(dsg, gsx * (0.5f * (float)w));
+      WB_RED_NZ(dsg + 1, gsy * (0.5f * (float)h));
     }
   }
 }
@@ -1515,11 +1539,6 @@ static inline unsigned wb_blocks_b(long long total, int threads) {
   if (b > (1 << 20)) b = 1 << 20;
   return (unsigned)b;
 }
-
-#ifndef WB_HOST_EMU
-static int wb_check_launch(const char* file, int line);
-#endif
-static int wb_fail(int code, const char* fmt, ...);
 
 static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   const WbDec& d = a.f;
@@ -1547,6 +1566,53 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   const bool st_aprep = a.stages == 0 || (a.stages & 8);
   const bool need_layers = a.d_alpha_acc || a.d_f_lo || a.d_occ;
   if (need_layers) WB_BREQ(a.glue && d.score, "glue / score buffers missing");
+#if WB_DET
+  // ---- deterministic accumulation: sizes of the scatter targets, arena checks, conversion helper
+  const long long HWdl = (long long)g.Hd * g.Wd;
+  const bool self_ctx = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  const long long n_input = (long long)g.B * g.T * g.C * HWdl, n_alpha = (long long)g.B * g.Tw * L * HWdl;
+  const long long n_f_lo = (long long)g.B * g.Tc * g.Tp * L * HW * 2, n_a_lo = (long long)g.B * g.Tw * L * HW;
+  const long long n_tgo = (long long)g.B * g.T * g.No * g.Ho * g.Wo * 2, n_sgo = (long long)g.B * g.T * g.No * HW * 2;
+  const long long n_gbg = (long long)g.B * g.T * HW * 2, n_oa = (long long)g.B * g.No * g.Ho * g.Wo, n_ba = (long long)g.B * HW;
+  WB_BREQ(a.det_base && a.det_shadow && a.det_scale && a.det_n > 0, "deterministic mode needs det_base, det_shadow, det_scale");
+  {
+    const float* tg[10] = {a.d_input, a.d_alpha_acc, a.d_f_lo, a.d_a_lo, a.d_tgt_grid_obj, a.d_src_grid_obj, a.d_tgt_grid_bg,
+                           a.d_src_grid_bg, a.d_obj_alpha, a.d_bg_alpha};
+    const long long tn[10] = {n_input, n_alpha, n_f_lo, n_a_lo, n_tgo, n_sgo, n_gbg, n_gbg, n_oa, n_ba};
+    for (int i = 0; i < 10; ++i)
+      WB_BREQ(!tg[i] || (tg[i] >= a.det_base && tg[i] + tn[i] <= a.det_base + a.det_n), "a scatter target lies outside the det arena");
+  }
+  auto det_convert = [&](float* dst, long long n) -> int {
+    if (!dst) return 0;
+    WB_LAUNCH(k_det_convert, dim3(wb_blocks_b(n, 256 * 4) > 1184 ? 1184 : wb_blocks_b(n, 256 * 4)), dim3(256), 0, st,
+              a.det_shadow + (dst - a.det_base), dst, n, a.det_scale);
+    return WB_CHECK_LAUNCH();
+  };
+  auto det_finish = [&]() -> int {   // the targets whose last addend comes from the low-res chain / the context-alpha kernels
+    float* tg[7] = {a.d_input, a.d_tgt_grid_obj, a.d_src_grid_obj, a.d_tgt_grid_bg, a.d_src_grid_bg, a.d_obj_alpha, a.d_bg_alpha};
+    const long long tn[7] = {n_input, n_tgo, n_sgo, n_gbg, n_gbg, n_oa, n_ba};
+    for (int i = 0; i < 7; ++i) { int rc_ = det_convert(tg[i], tn[i]); if (rc_) return rc_; }
+    return 0;
+  };
+  if (st_gather) {   // fixed-point unit from the largest upstream gradient magnitude (a maximum is order-independent)
+    WB_LAUNCH(k_det_clear, dim3(1), dim3(32), 0, st, a.det_scale);
+    WB_BLAUNCHED();
+    const int TcRd = g.Tc + (self_ctx ? 1 : 0), CRd = g.C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
+    const float* up[5] = {a.d_output, a.d_raw_alpha, a.d_raw_output, a.d_flow, a.d_alpha};
+    const long long un[5] = {(long long)g.B * g.Tp * g.C * HWdl, (long long)g.B * g.Tp * HWdl,
+                             (long long)g.B * TcRd * g.Tp * CRd * HWdl, (long long)g.B * g.Tc * g.Tp * 2 * HWdl, n_alpha};
+    for (int i = 0; i < 5; ++i) {
+      if (!up[i]) continue;
+      WB_LAUNCH(k_det_absmax, dim3(wb_blocks_b(un[i], 256 * 8) > 1184 ? 1184 : wb_blocks_b(un[i], 256 * 8)), dim3(256), 0, st, up[i], un[i], a.det_scale);
+      WB_BLAUNCHED();
+    }
+    WB_LAUNCH(k_det_scale, dim3(1), dim3(32), 0, st, a.det_scale);
+    WB_BLAUNCHED();
+  }
+#define WB_DET_DO(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
+#else
+#define WB_DET_DO(expr) ((void)0)
+#endif
   // 1. HD gather backward
   if (st_gather) {
     WbDecB ag = a;
@@ -1573,8 +1639,14 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);
       WB_BLAUNCHED();
     }
+    // (deterministic mode) the two targets of the layer kernel are complete: the kernels below read them as fp32
+    WB_DET_DO(det_convert(a.d_alpha_acc, n_alpha));
+    WB_DET_DO(det_convert(a.d_f_lo, n_f_lo));
   }
-  if (!need_alpha_chain || !(st_rest || st_aprep)) return 0;
+  if (!need_alpha_chain || !(st_rest || st_aprep)) {
+    if (st_rest) WB_DET_DO(det_finish());
+    return 0;
+  }
   // 2. context-alpha backward
   if (st_aprep && (a.d_alpha_acc || a.d_alpha)) {
     if (filt && a.d_prof_p) WB_BREQ(a.prof_p_part, "prof_p_part scratch missing");
@@ -1594,6 +1666,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
       WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tw), dim3(128), 0, st, a.occ_part, g.B * g.Tw, g.Tw, a.red_ctas, L * L, g.T, d.pred_ts, 1, a.d_occ);
       WB_BLAUNCHED();
     }
+    WB_DET_DO(det_convert(a.d_a_lo, n_a_lo));   // k_class_profile_bwd / k_project_alpha_bwd read (and update in place) fp32
   }
   if (!st_rest) return 0;
   if (a.d_alpha_acc || a.d_alpha) {
@@ -1621,7 +1694,11 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     WB_LAUNCH(k_layer_flow_lo_bwd, dim3(wb_blocks_b((long long)g.B * g.Tp * L * HW, 256)), dim3(256), 0, st, a);
     WB_BLAUNCHED();
   }
+  WB_DET_DO(det_finish());
   return 0;
 #undef WB_BREQ
 #undef WB_BLAUNCHED
+#undef WB_DET_DO
 }
+
+}   // namespace wb_plain / wb_fixed

@@ -198,6 +198,49 @@ def _geom(spec: DecodeSpec, B, T, Tc, Tp, Nl, has_cls):
                   flags, float(spec.min_cls))
 
 
+# Deterministic gradients (BASELINE north star: "deterministic gradient accumulation ... instead of global atomics").
+# Default off: the scatter targets of decode_bwd are then accumulated with fire-and-forget fp32 reductions whose order is
+# not fixed (reproducible to fp32 rounding only, like ATen's grid_sampler_2d_backward).  On -- set_deterministic(True), or
+# torch.use_deterministic_algorithms(True) -- they are accumulated as 64-bit fixed point (order-independent), so every
+# gradient of the path is bit-identical from run to run; costs an int64 shadow of the scatter targets and a few
+# conversion passes (include/waldo_b200.h, det_* fields).
+_DETERMINISTIC = False
+LAST_DET_SCALE = None   # (4,) device tensor of the last deterministic backward: scale, 1/scale, max|upstream|, overflow flag
+
+
+def set_deterministic(on: bool = True):
+    global _DETERMINISTIC
+    _DETERMINISTIC = bool(on)
+
+
+def is_deterministic() -> bool:
+    return _DETERMINISTIC or torch.are_deterministic_algorithms_enabled()
+
+
+def _scatter_targets(refs, det):
+    """Zero-filled gradient / scratch buffers shaped like `refs` (None stays None).  In deterministic mode they are views
+    of ONE float arena (16-byte aligned each) shadowed by an int64 arena: returns (targets, arena, shadow)."""
+    if not det:
+        return [torch.zeros_like(r) if r is not None else None for r in refs], None, None
+    live = [r for r in refs if r is not None]
+    offs, n = [], 0
+    for r in live:
+        offs.append(n)
+        n += (r.numel() + 3) // 4 * 4
+    dev = live[0].device
+    arena = torch.zeros(max(n, 4), device=dev, dtype=torch.float32)
+    shadow = torch.zeros(max(n, 4), device=dev, dtype=torch.int64)
+    it = iter(offs)
+    out = []
+    for r in refs:
+        if r is None:
+            out.append(None)
+        else:
+            o = next(it)
+            out.append(arena[o:o + r.numel()].view(r.shape))
+    return out, arena, shadow
+
+
 # When bench.py sets PROFILE = {"decode_fwd": [], "decode_bwd": []}, the two entry points are issued stage by stage
 # (same kernels, same order, same stream) with a CUDA-event pair around the dominant fused HD kernel, so that its
 # duration can be read inside the timed region (the roofline figure).  None = one call per entry point.
@@ -322,8 +365,7 @@ class _Decode(torch.autograd.Function):
         n_inp, n_tgo, n_sgo, n_tgb, n_sgb, n_occ, n_oa, n_ba, n_cls = need
         n_cls = n_cls and cls_c is not None
         z = lambda ref, on: torch.zeros_like(ref) if on else None
-        d_input, d_tgo, d_sgo, d_tgb, d_sgb = z(inp_c, n_inp), z(tgo_c, n_tgo), z(sgo_c, n_sgo), z(tgb_c, n_tgb), z(sgb_c, n_sgb)
-        d_occ, d_oa, d_ba, d_cls = z(occ_c, n_occ), z(oa_c, n_oa), z(ba_c, n_ba), z(cls_c, n_cls)
+        d_occ, d_cls = z(occ_c, n_occ), z(cls_c, n_cls)
         filt = bool(g.flags & L.F_FILTER)
         geom = n_tgo or n_sgo or n_tgb or n_sgb
         chain = geom or n_occ or n_oa or n_ba or n_cls or (filt and n_inp)
@@ -331,17 +373,14 @@ class _Decode(torch.autograd.Function):
         alpha = tensors[21]
         Lr = g.No + 1
         f32 = dict(device=dev, dtype=torch.float32)
-        d_alpha_acc = torch.zeros_like(alpha) if chain else None
-        # geometry gradients flow through all four grids together: allocate the missing ones as scratch
-        if geom:
-            d_tgo_s = d_tgo if d_tgo is not None else torch.zeros_like(tgo_c)
-            d_sgo_s = d_sgo if d_sgo is not None else torch.zeros_like(sgo_c)
-            d_tgb_s = d_tgb if d_tgb is not None else torch.zeros_like(tgb_c)
-            d_sgb_s = d_sgb if d_sgb is not None else torch.zeros_like(sgb_c)
-        else:
-            d_tgo_s = d_sgo_s = d_tgb_s = d_sgb_s = None
-        d_f_lo = torch.zeros_like(f_lo) if geom else None
-        d_a_lo = torch.zeros_like(a_lo) if chain else None
+        # the scatter targets (geometry gradients flow through all four grids together: the ones not asked for are scratch)
+        det = is_deterministic()
+        on = lambda ref, cond: ref if cond else None
+        (d_input, d_alpha_acc, d_f_lo, d_a_lo, d_tgo_s, d_sgo_s, d_tgb_s, d_sgb_s, d_oa, d_ba), det_arena, det_shadow = _scatter_targets(
+            [on(inp_c, n_inp), on(alpha, chain), on(f_lo, geom), on(a_lo, chain), on(tgo_c, geom), on(sgo_c, geom), on(tgb_c, geom),
+             on(sgb_c, geom), on(oa_c, n_oa), on(ba_c, n_ba)], det)
+        d_tgo, d_sgo, d_tgb, d_sgb = on(d_tgo_s, n_tgo), on(d_sgo_s, n_sgo), on(d_tgb_s, n_tgb), on(d_sgb_s, n_sgb)
+        det_scale = torch.empty(4, **f32) if det else None
         d_prof_p = torch.zeros_like(prof_p) if (chain and filt) else None
         d_prof_sum = torch.zeros_like(prof_sum) if (chain and filt) else None
         tiles = ((g.Wd + 31) // 32) * ((g.Hd + 7) // 8)
@@ -360,8 +399,12 @@ class _Decode(torch.autograd.Function):
         b = L.DecodeBwd(fwd, L.ptr(grads_in[0]), L.ptr(grads_in[1]), L.ptr(grads_in[2]), L.ptr(grads_in[3]), L.ptr(grads_in[4]),
                         L.ptr(d_input), L.ptr(d_tgo_s), L.ptr(d_sgo_s), L.ptr(d_tgb_s), L.ptr(d_sgb_s), L.ptr(d_occ),
                         L.ptr(d_oa), L.ptr(d_ba), L.ptr(d_cls_s), L.ptr(d_alpha_acc), L.ptr(d_f_lo), L.ptr(d_a_lo),
-                        L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part), L.ptr(up_tab), L.ptr(glue), 0)
+                        L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part), L.ptr(up_tab), L.ptr(glue), 0,
+                        L.ptr(det_arena), L.ptr(det_shadow, torch.int64), det_arena.numel() if det else 0, L.ptr(det_scale))
         _staged(lib.waldo_decode_bwd, b, L.stream_of(inp_c), "decode_bwd", dev=dev)
+        if det:
+            global LAST_DET_SCALE
+            LAST_DET_SCALE = det_scale
         if d_oa is not None:
             d_oa = d_oa.view(ctx.shapes["obj_alpha"])
         if d_ba is not None:
