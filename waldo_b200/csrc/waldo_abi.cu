@@ -197,7 +197,9 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   // B2
   if (filt) {
     if (!from_cls) {
-      WB_LAUNCH(k_class_profile, dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
+      if (g.Nl == 20) WB_LAUNCH(k_class_profile<20>, dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
+      else if (g.Nl == 19) WB_LAUNCH(k_class_profile<19>, dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
+      else WB_LAUNCH(k_class_profile<0>, dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
       WB_LAUNCHED();
     }
     WB_LAUNCH(k_profile_final, dim3(g.B), dim3(352), 0, st, *a);

@@ -23,6 +23,7 @@ static thread_local wb_dim3 threadIdx(0, 0, 0), blockIdx, blockDim, gridDim;
 #define __forceinline__ inline
 #define __shared__ static thread_local
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 #define __syncthreads() ((void)0)
 #define __ldg(p) (*(p))
 typedef void* cudaStream_t;

@@ -1343,19 +1343,30 @@ __global__ void k_profile_final_bwd(WbDecB a) {
 }
 
 // backward of the class-profile sums (lvd.py:735-742) on the low-res lattice; grid = (prof_ctas, B), block 256.
-// d cls uses the same staged, ordered reduction as the forward.
-__global__ void __launch_bounds__(256) k_class_profile_bwd(WbDecB a) {
+// d cls uses the same staged, ordered reduction as the forward.  One thread per low-res sample; the class count is a
+// template parameter (20 / 19 / generic) and the object loop is unrolled over the compiled maximum, so that the four
+// per-class vectors live in registers (with run-time trip counts they sat in local memory: 336 bytes of stack and half of
+// the kernel's stall samples, profiles/r1_v37) and the rows of the two shared-memory tables are read as 128-bit words at
+// compile-time offsets.  The per-object loads (a_lo, d a_lo) are issued before the arithmetic instead of one dependent
+// load per trip.  Same operations in the same order as before: results are bit-identical.
+#ifndef WB_OCC_PROF_BWD
+#define WB_OCC_PROF_BWD 2   // 128 registers, 2 CTAs/SM: 1.05 ms vs 1.13 ms for the whole low-res tail at 1 CTA/SM (B200 A/B, r1_v42)
+#endif
+template <int NLC>
+__global__ void __launch_bounds__(256, WB_OCC_PROF_BWD) k_class_profile_bwd(WbDecB a) {
+  constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
+  constexpr int NO = WB_MAX_L - 1;
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
-  const int No = g.No, Nl = g.Nl, HW = g.H * g.W, L = No + 1, nout = No * Nl + No;
+  const int No = g.No, Nl = NLC > 0 ? NLC : g.Nl, HW = g.H * g.W, L = No + 1, nout = No * Nl + No;
   const size_t HWd = (size_t)g.Hd * g.Wd;
   const int b = blockIdx.y;
   const int nsamp = g.Tw * HW;
   const bool wcls = (g.flags & WALDO_F_WEIGHT_CLS) != 0;
   __shared__ float s_sm[WB_PROF_BATCH][WB_MAX_NL + 1];
   __shared__ float s_gq[WB_PROF_BATCH][WB_MAX_L];
-  __shared__ float s_cls[(WB_MAX_L - 1) * WB_MAX_NL];
-  __shared__ float s_gsum[(WB_MAX_L - 1) * WB_MAX_NL + WB_MAX_L];
+  __shared__ __align__(16) float s_cls[(WB_MAX_L - 1) * WB_MAX_NL];
+  __shared__ __align__(16) float s_gsum[(WB_MAX_L - 1) * WB_MAX_NL + WB_MAX_L];
   if (wcls)
     for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_cls[i] = __ldg(d.cls + (size_t)b * No * Nl + i) + g.min_cls;
   for (int i = wb_tid(); i < nout; i += wb_nthr()) s_gsum[i] = a.d_prof_sum[(size_t)b * nout + i];
@@ -1367,40 +1378,69 @@ __global__ void __launch_bounds__(256) k_class_profile_bwd(WbDecB a) {
     const int ns = min(WB_PROF_BATCH, nsamp - s0);
     for (int i = wb_tid(); i < ns; i += wb_nthr()) {
       const int s = s0 + i, t = s / HW, p = s - t * HW;
-      float lyt[WB_MAX_NL], sm[WB_MAX_NL], glyt[WB_MAX_NL], gsmx[WB_MAX_NL];
-      if (d.lyt_lo) for (int c = 0; c < Nl; ++c) lyt[c] = __ldg(d.lyt_lo + (((size_t)b * g.Tw + t) * Nl + c) * HW + p);
-      else wb_lyt_lo(d, b, t, p, lyt);
-      if (wcls) wb_softmax(lyt, sm, Nl);
-      for (int c = 0; c < Nl; ++c) { glyt[c] = 0.f; gsmx[c] = 0.f; }
-      for (int k = 0; k < No; ++k) {
-        const size_t ia = (((size_t)b * g.Tw + t) * L + k + 1) * HW + p;
-        const float al = __ldg(d.a_lo + ia) + 1e-6f;
-        float qk = 1.f;
-        if (wcls) { qk = 0.f; for (int c = 0; c < Nl; ++c) qk += s_cls[k * Nl + c] * sm[c]; }
-        const float w = al * qk;
-        float gw = s_gsum[No * Nl + k];
-        for (int c = 0; c < Nl; ++c) { gw += s_gsum[k * Nl + c] * lyt[c]; glyt[c] += s_gsum[k * Nl + c] * w; }
-        if (a.d_a_lo) a.d_a_lo[ia] += gw * qk;
-        const float gq = gw * al;
-        s_gq[i][k] = gq;
-        if (wcls) for (int c = 0; c < Nl; ++c) gsmx[c] += gq * s_cls[k * Nl + c];
+      const int y = p / g.W, x = p - y * g.W;
+      const WbAxis ay = wb_axis(y, r, g.Hd), ax = wb_axis(x, r, g.Wd);
+      const size_t hd00 = (size_t)ay.i0 * g.Wd + ax.i0, hd01 = (size_t)ay.i0 * g.Wd + ax.i1;
+      const size_t hd10 = (size_t)ay.i1 * g.Wd + ax.i0, hd11 = (size_t)ay.i1 * g.Wd + ax.i1;
+      // ---- every load whose address is known up front
+      const size_t ia0 = (((size_t)b * g.Tw + t) * L + 1) * HW + p;   // object k: ia0 + k * HW
+      float al[NO], dal[NO];
+      WB_UNROLL for (int k = 0; k < NO; ++k) {
+        al[k] = k < No ? __ldg(d.a_lo + ia0 + (size_t)k * HW) + 1e-6f : 0.f;
+        dal[k] = (k < No && a.d_a_lo) ? a.d_a_lo[ia0 + (size_t)k * HW] : 0.f;
+      }
+      float lyt[NN], sm[NN], glyt[NN], gsmx[NN];
+      if (d.lyt_lo) {
+        const float* pl = d.lyt_lo + ((size_t)b * g.Tw + t) * Nl * HW + p;
+        WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) lyt[c] = __ldg(pl + (size_t)c * HW);
+      } else {   // same arithmetic as wb_lyt_lo
+        const float* base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
+        WB_UNROLL for (int c = 0; c < NN; ++c)
+          if (NLC > 0 || c < Nl) {
+            const float* pl = base + c * HWd;
+            lyt[c] = wb_lerp2(__ldg(pl + hd00), __ldg(pl + hd01), __ldg(pl + hd10), __ldg(pl + hd11), ax, ay);
+          }
+      }
+      if (wcls) {   // same arithmetic as wb_softmax
+        float mx = lyt[0];
+        WB_UNROLL for (int c = 1; c < NN; ++c) if (NLC > 0 || c < Nl) mx = fmaxf(mx, lyt[c]);
+        float ssum = 0.f;
+        WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { sm[c] = expf(lyt[c] - mx); ssum += sm[c]; }
+        const float inv = 1.f / ssum;
+        WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) sm[c] *= inv;
+      }
+      WB_UNROLL for (int c = 0; c < NN; ++c) { glyt[c] = 0.f; gsmx[c] = 0.f; }
+      WB_UNROLL for (int k = 0; k < NO; ++k) {
+        if (k < No) {
+          const float* G = s_gsum + k * Nl;
+          const float* Ck = s_cls + k * Nl;
+          float qk = 1.f;
+          if (wcls) { qk = 0.f; WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) qk += Ck[c] * sm[c]; }
+          const float w = al[k] * qk;
+          float gw = s_gsum[No * Nl + k];
+          WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { gw += G[c] * lyt[c]; glyt[c] += G[c] * w; }
+          if (a.d_a_lo) a.d_a_lo[ia0 + (size_t)k * HW] = dal[k] + gw * qk;
+          const float gq = gw * al[k];
+          s_gq[i][k] = gq;
+          if (wcls) { WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) gsmx[c] += gq * Ck[c]; }
+        }
       }
       if (wcls) {
         float dot = 0.f;
-        for (int c = 0; c < Nl; ++c) dot += gsmx[c] * sm[c];
-        for (int c = 0; c < Nl; ++c) { glyt[c] += sm[c] * (gsmx[c] - dot); s_sm[i][c] = sm[c]; }
+        WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) dot += gsmx[c] * sm[c];
+        WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { glyt[c] += sm[c] * (gsmx[c] - dot); s_sm[i][c] = sm[c]; }
       }
       if (a.d_input) {   // transpose of the bilinear down-sampling
-        const int y = p / g.W, x = p - y * g.W;
-        WbAxis ay = wb_axis(y, r, g.Hd), ax = wb_axis(x, r, g.Wd);
         float* base = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
-        for (int c = 0; c < Nl; ++c) {
-          float* pl = base + (size_t)c * HWd;
-          const float gv = glyt[c];
-          WB_RED_NZ(pl + (size_t)ay.i0 * g.Wd + ax.i0, gv * ax.l0 * ay.l0);
-          WB_RED_NZ(pl + (size_t)ay.i0 * g.Wd + ax.i1, gv * ax.l1 * ay.l0);
-          WB_RED_NZ(pl + (size_t)ay.i1 * g.Wd + ax.i0, gv * ax.l0 * ay.l1);
-          WB_RED_NZ(pl + (size_t)ay.i1 * g.Wd + ax.i1, gv * ax.l1 * ay.l1);
+        WB_UNROLL for (int c = 0; c < NN; ++c) {
+          if (NLC > 0 || c < Nl) {
+            float* pl = base + (size_t)c * HWd;
+            const float gv = glyt[c];
+            WB_RED_NZ(pl + hd00, gv * ax.l0 * ay.l0);
+            WB_RED_NZ(pl + hd01, gv * ax.l1 * ay.l0);
+            WB_RED_NZ(pl + hd10, gv * ax.l0 * ay.l1);
+            WB_RED_NZ(pl + hd11, gv * ax.l1 * ay.l1);
+          }
         }
       }
     }
@@ -1676,7 +1716,9 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
       WB_BLAUNCHED();
       if (!from_cls) {
         if ((g.flags & WALDO_F_WEIGHT_CLS) && a.d_cls) WB_BREQ(a.cls_part, "cls_part scratch missing");
-        WB_LAUNCH(k_class_profile_bwd, dim3(d.prof_ctas, g.B), dim3(256), 0, st, a);
+        if (g.Nl == 20) WB_LAUNCH(k_class_profile_bwd<20>, dim3(d.prof_ctas, g.B), dim3(256), 0, st, a);
+        else if (g.Nl == 19) WB_LAUNCH(k_class_profile_bwd<19>, dim3(d.prof_ctas, g.B), dim3(256), 0, st, a);
+        else WB_LAUNCH(k_class_profile_bwd<0>, dim3(d.prof_ctas, g.B), dim3(256), 0, st, a);
         WB_BLAUNCHED();
         if ((g.flags & WALDO_F_WEIGHT_CLS) && a.d_cls) {
           WB_LAUNCH(k_cls_reduce, dim3(g.B), dim3(128), 0, st, a);

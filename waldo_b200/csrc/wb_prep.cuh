@@ -73,15 +73,21 @@ WB_DEV void wb_softmax(const float* x, float* y, int n) {
 // shared memory, then thread <-> (object, class) accumulates them in sample order; CTA partials are reduced
 // in CTA order by k_profile_final.  grid = (prof_ctas, B).
 #define WB_PROF_BATCH 256
+// The class count is a template parameter (20 / 19 / generic) and the object loop is unrolled over the compiled maximum:
+// the per-class vectors stay in registers (run-time trip counts put them in local memory) and the rows of `cls` are read
+// from shared memory at compile-time offsets.  Same operations in the same order as the generic loops.
+template <int NLC>
 __global__ void __launch_bounds__(256) k_class_profile(WbDec d) {
+  constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
+  constexpr int NO = WB_MAX_L - 1;
   const waldo_geom_t g = d.g;
-  const int No = g.No, Nl = g.Nl, HW = g.H * g.W, L = No + 1;
+  const int No = g.No, Nl = NLC > 0 ? NLC : g.Nl, HW = g.H * g.W, L = No + 1;
   const int b = blockIdx.y;
   const int nsamp = g.Tw * HW;
   const int nout = No * Nl + No;
   __shared__ float s_lyt[WB_PROF_BATCH][WB_MAX_NL + 1];
   __shared__ float s_w[WB_PROF_BATCH][WB_MAX_L];
-  __shared__ float s_cls[(WB_MAX_L - 1) * WB_MAX_NL];
+  __shared__ __align__(16) float s_cls[(WB_MAX_L - 1) * WB_MAX_NL];
   const bool wcls = (g.flags & WALDO_F_WEIGHT_CLS) != 0;
   if (wcls)
     for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_cls[i] = __ldg(d.cls + (size_t)b * No * Nl + i) + g.min_cls;
@@ -89,23 +95,52 @@ __global__ void __launch_bounds__(256) k_class_profile(WbDec d) {
   float* part = d.prof_part + ((size_t)b * gridDim.x + blockIdx.x) * nout;
   for (int o = wb_tid(); o < nout; o += wb_nthr()) part[o] = 0.f;
   __syncthreads();
+  const float r = (float)g.Hd / (float)g.H;   // = 1 / (1/scale_hd)
+  const size_t HWd = (size_t)g.Hd * g.Wd;
   for (int s0 = blockIdx.x * WB_PROF_BATCH; s0 < nsamp; s0 += gridDim.x * WB_PROF_BATCH) {
     const int ns = min(WB_PROF_BATCH, nsamp - s0);
     for (int i = wb_tid(); i < ns; i += wb_nthr()) {
-      int s = s0 + i, t = s / HW, p = s - t * HW;
-      float lyt[WB_MAX_NL], sm[WB_MAX_NL];
-      wb_lyt_lo(d, b, t, p, lyt);
-      if (wcls) wb_softmax(lyt, sm, Nl);
-      for (int c = 0; c < Nl; ++c) s_lyt[i][c] = lyt[c];
-      if (d.lyt_lo) for (int c = 0; c < Nl; ++c) d.lyt_lo[(((size_t)b * g.Tw + t) * Nl + c) * HW + p] = lyt[c];
-      for (int k = 0; k < No; ++k) {
-        float w = __ldg(d.a_lo + (((size_t)b * g.Tw + t) * L + k + 1) * HW + p) + 1e-6f;
-        if (wcls) {
-          float acc = 0.f;
-          for (int c = 0; c < Nl; ++c) acc += s_cls[k * Nl + c] * sm[c];
-          w *= acc;
+      const int s = s0 + i, t = s / HW, p = s - t * HW;
+      float al[NO];
+      WB_UNROLL for (int k = 0; k < NO; ++k)
+        al[k] = k < No ? __ldg(d.a_lo + (((size_t)b * g.Tw + t) * L + k + 1) * HW + p) + 1e-6f : 0.f;
+      float lyt[NN], sm[NN];
+      {   // same arithmetic as wb_lyt_lo
+        const int y = p / g.W, x = p - y * g.W;
+        const WbAxis ay = wb_axis(y, r, g.Hd), ax = wb_axis(x, r, g.Wd);
+        const float* base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
+        const size_t h00 = (size_t)ay.i0 * g.Wd + ax.i0, h01 = (size_t)ay.i0 * g.Wd + ax.i1;
+        const size_t h10 = (size_t)ay.i1 * g.Wd + ax.i0, h11 = (size_t)ay.i1 * g.Wd + ax.i1;
+        WB_UNROLL for (int c = 0; c < NN; ++c)
+          if (NLC > 0 || c < Nl) {
+            const float* pl = base + c * HWd;
+            lyt[c] = wb_lerp2(__ldg(pl + h00), __ldg(pl + h01), __ldg(pl + h10), __ldg(pl + h11), ax, ay);
+          }
+      }
+      if (wcls) {   // same arithmetic as wb_softmax
+        float mx = lyt[0];
+        WB_UNROLL for (int c = 1; c < NN; ++c) if (NLC > 0 || c < Nl) mx = fmaxf(mx, lyt[c]);
+        float ssum = 0.f;
+        WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { sm[c] = expf(lyt[c] - mx); ssum += sm[c]; }
+        const float inv = 1.f / ssum;
+        WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) sm[c] *= inv;
+      }
+      WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) s_lyt[i][c] = lyt[c];
+      if (d.lyt_lo) {
+        float* o = d.lyt_lo + ((size_t)b * g.Tw + t) * Nl * HW + p;
+        WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) o[(size_t)c * HW] = lyt[c];
+      }
+      WB_UNROLL for (int k = 0; k < NO; ++k) {
+        if (k < No) {
+          float w = al[k];
+          if (wcls) {
+            const float* Ck = s_cls + k * Nl;
+            float acc = 0.f;
+            WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) acc += Ck[c] * sm[c];
+            w *= acc;
+          }
+          s_w[i][k] = w;
         }
-        s_w[i][k] = w;
       }
     }
     __syncthreads();
