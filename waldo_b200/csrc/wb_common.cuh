@@ -266,6 +266,13 @@ WB_DEV void wb_cp4(float* smem_dst, const float* gsrc) {
 WB_DEV void wb_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> WB_DEV void wb_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// L1 prefetch hint (no register, no dependency): used to pull the NEXT context's low-res flow cells while the current
+// context is processed
+WB_DEV void wb_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef WB_PF_FLO
+#define WB_PF_FLO 0   // measured on B200 (profiles/r1_v44_prefetch_ab.log): SLOWER in both lanes kernels (fwd 0.884 -> 0.912 ms,
+#endif                // bwd 1.977 -> 2.066 ms) -- they are bound by issue slots, not by the latency of these L2-resident cells
+
 // position of the nth (0-based) set bit of m  (lanes-per-layer kernels: layer of a slot)
 WB_DEV int wb_nth_bit(unsigned m, int nth) { return (int)__fns(m, 0, nth + 1); }
 #endif

@@ -189,6 +189,13 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
       const unsigned isobj = __shfl_sync(0xffffffffu, isobj_lane, p);
       float2 f00 = __ldg(fl + o00), f01 = f00, f10 = f00, f11 = f00;
       if (!direct) { f01 = __ldg(fl + o01); f10 = __ldg(fl + o10); f11 = __ldg(fl + o11); }
+#if WB_PF_FLO
+      if (tc + 1 < g.Tc) {   // the same cells of the next context: pair + Tp
+        const float2* fn = fl + (size_t)g.Tp * L * HW;
+        wb_prefetch_l1(fn + o00);
+        if (!direct) wb_prefetch_l1(fn + o10);
+      }
+#endif
       float Fx = 0.f, Fy = 0.f, rr = 0.f;
       if (valid) {
         if (direct) { Fx = f00.x; Fy = f00.y; }

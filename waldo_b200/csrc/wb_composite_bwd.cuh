@@ -43,6 +43,12 @@ WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) wb_red(p, v); }
 #endif
 
 #define WB_NWARP (WB_TILE_PX / 32)
+#ifndef WB_PF_GB
+#define WB_PF_GB 0   // L1 prefetch of the next context group's flow / score lines in k_gather_bwd_async: no effect (2.172 vs 2.176 ms)
+#endif
+#ifndef WB_PREP_OCC8
+#define WB_PREP_OCC8 1   // context-alpha backward: 8-slot register form of the occlusion backward for rows with 5..8 live layers
+#endif
 
 // ---------------------------------------------------------------------------- transpose of the bilinear up-sampling
 // A warp is one row of 32 HD pixels, so all its lanes share the two low-res rows and touch a short run of low-res
@@ -369,6 +375,13 @@ WB_DEV void wb_lanes_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbColR
       const float dr_l = draw ? __ldg(draw + (size_t)(C + k) * HWd + q) : 0.f;
       float2 f00 = __ldg(fl + o00), f01 = f00, f10 = f00, f11 = f00;
       if (!c.lowres_direct) { f01 = __ldg(fl + o01); f10 = __ldg(fl + o10); f11 = __ldg(fl + o11); }
+#if WB_PF_FLO
+      if (tc + 1 < g.Tc) {   // the same cells of the next context: pair + Tp
+        const float2* fn = fl + (size_t)g.Tp * L * HW;
+        wb_prefetch_l1(fn + o00);
+        if (!c.lowres_direct) wb_prefetch_l1(fn + o10);
+      }
+#endif
       // ---- forward of this (pixel, layer), same arithmetic as wb_layers_fwd
       float Fx = 0.f, Fy = 0.f, rr = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
       bool samp = false;
@@ -679,6 +692,15 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd_as
     const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
     float S = 0.f;
     for (int tc0 = 0; tc0 < g.Tc; tc0 += TG) {
+#if WB_PF_GB
+      if (tc0 + TG < g.Tc) {   // this pixel's flow / score lines of the next context group: their latency heads its prologue
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          const size_t pn = ((size_t)b * g.Tc + tc0 + TG + i) * g.Tp + tp;
+          wb_prefetch_l1(d.flow + pn * 2 * HWd + q); wb_prefetch_l1(d.flow + pn * 2 * HWd + HWd + q);
+          wb_prefetch_l1(d.score + pn * HWd + q);
+        }
+      }
+#endif
       unsigned o0[TG], o1[TG];
       float w[TG][4], nrm[TG], U[TG][4], Tq[TG][4];
       const float* src[TG];
@@ -953,7 +975,21 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
     }
     wb_occlude_bwd<4>(R4, gA4, c.s_occ, L, ix4, ga4, c.s_acc, c.pairs_only);
     WB_UNROLL for (int u = 0; u < 4; ++u) if (u < ix.n) ga[u] = ga4[u];
-  } else {
+  }
+#if WB_PREP_OCC8
+  else if (NA > 8 && ix.n <= 8) {   // 5..8 live layers (30 % of the rows at the benchmark shape): same on 8 register slots
+    WbIdx<8> ix8;
+    float R8[8], gA8[8], ga8[8];
+    ix8.n = ix.n;
+    WB_UNROLL for (int u = 0; u < 8; ++u) {
+      const bool on = u < ix.n;
+      ix8.k[u] = on ? ix.k[u] : 0; R8[u] = on ? av[u] : 0.f; gA8[u] = on ? gA[u] : 0.f; ga8[u] = 0.f;
+    }
+    wb_occlude_bwd<8>(R8, gA8, c.s_occ, L, ix8, ga8, c.s_acc, c.pairs_only);
+    WB_UNROLL for (int u = 0; u < 8; ++u) if (u < ix.n) ga[u] = ga8[u];
+  }
+#endif
+  else {
     wb_occlude_bwd<NA>(av, gA, c.s_occ, L, ix, ga, c.s_acc, c.pairs_only);
   }
   // ---- filter backward: l_k = 1 - 0.5 sum_c |P_kc - sm_c|.  One ROLLED loop over the object slots (a single copy of
