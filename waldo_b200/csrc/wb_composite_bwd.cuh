@@ -84,7 +84,10 @@ __global__ void k_up_tab(int W, int Wd, float* __restrict__ tab) {
     int lo = -1;
     float w[WB_COL_TAPS];
     for (int t = 0; t < WB_COL_TAPS; ++t) w[t] = 0.f;
-    for (int X = 0; X < Wd; ++X) {
+    // only HD columns whose source position lies within (col - 1, col + 1) can touch `col` (two columns of margin)
+    const float inv_r = (float)Wd / (float)W;
+    const int Xa = max(0, (int)(((float)col - 1.f) * inv_r) - 2), Xb = min(Wd, (int)(((float)col + 2.f) * inv_r) + 3);
+    for (int X = Xa; X < Xb; ++X) {
       const WbAxis ax = wb_axis(X, r, W);
       const float wv = (ax.i0 == col ? ax.l0 : 0.f) + (ax.i1 == col ? ax.l1 : 0.f);
       if (wv != 0.f) {
@@ -872,11 +875,13 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_BWD) k_layers_bwd(Wb
 
 // d_occ[b, frame(group), :] += sum over CTAs (in order) of the partials.  mode 0: group = (b,tp) -> frame pred_ts[tp];
 // mode 1: group = (b,t) -> frame t.
+// grid = (groups, slices of the L*L entries): the serial loop over the CTA partials is the critical path, so the entries
+// are spread over many CTAs instead of one CTA per group.
 __global__ void k_occ_reduce(const float* __restrict__ part, int groups, int per_b, int ctas, int LL, int T,
                              const int64_t* __restrict__ pred_ts, int mode, float* __restrict__ d_occ) {
   const int grp = blockIdx.x, b = grp / per_b, j = grp - b * per_b;
   const int frame = mode == 0 ? (int)pred_ts[j] : j;
-  for (int e = wb_tid(); e < LL; e += wb_nthr()) {
+  for (int e = blockIdx.y * wb_nthr() + wb_tid(); e < LL; e += gridDim.y * wb_nthr()) {
     float acc = 0.f;
     WB_UNROLL_N(8) for (int c = 0; c < ctas; ++c) acc += __ldg(part + ((size_t)grp * ctas + c) * LL + e);   // fixed order
     d_occ[((size_t)b * T + frame) * LL + e] += acc;
@@ -1712,7 +1717,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     WB_LAUNCH(k_layers_bwd, dim3(a.red_ctas, g.B * g.Tp), dim3(WB_TILE_PX), 0, st, a);
     WB_BLAUNCHED();
     if (a.d_occ) {
-      WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp), dim3(128), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);
+      WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tp, (L * L + 31) / 32), dim3(32), 0, st, a.occ_part, g.B * g.Tp, g.Tp, a.red_ctas, L * L, g.T, d.pred_ts, 0, a.d_occ);
       WB_BLAUNCHED();
     }
     // (deterministic mode) the two targets of the layer kernel are complete: the kernels below read them as fp32
@@ -1739,7 +1744,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     else WB_LAUNCH(k_alpha_prep_bwd<0>, pgrid, dim3(WB_TILE_PX), dyn, st, a);
     WB_BLAUNCHED();
     if (a.d_occ) {
-      WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tw), dim3(128), 0, st, a.occ_part, g.B * g.Tw, g.Tw, a.red_ctas, L * L, g.T, d.pred_ts, 1, a.d_occ);
+      WB_LAUNCH(k_occ_reduce, dim3(g.B * g.Tw, (L * L + 31) / 32), dim3(32), 0, st, a.occ_part, g.B * g.Tw, g.Tw, a.red_ctas, L * L, g.T, d.pred_ts, 1, a.d_occ);
       WB_BLAUNCHED();
     }
     WB_DET_DO(det_convert(a.d_a_lo, n_a_lo));   // k_class_profile_bwd / k_project_alpha_bwd read (and update in place) fp32
