@@ -17,7 +17,7 @@ def gb(r, k):
     return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1e9)
 out, lines = {}, []
 for r in rows[2:]:
-    name = r[idx['Kernel Name']].split('(')[0].replace('void ', '').split('<')[0]
+    name = r[idx['Kernel Name']].split('(')[0].replace('void ', '').replace('wb_plain::', '').split('<')[0]
     if name in out: continue
     rd, wr = gb(r, 'dram__bytes_read.sum'), gb(r, 'dram__bytes_write.sum')
     out[name.replace('_async', '')] = int(rd + wr)   # bench.py's kernel names
