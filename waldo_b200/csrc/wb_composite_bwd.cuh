@@ -1348,18 +1348,21 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(
 }
 
 // d_prof_p[b,:] = sum_t sum_cta partial (ordered); then through P = softmax(num/den) (or P = cls).
-__global__ void k_profile_final_bwd(WbDecB a) {
+__global__ void __launch_bounds__(1024) k_profile_final_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
   const int No = g.No, Nl = g.Nl, nout = No * Nl + No;
   const int b = blockIdx.x;
   const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
-  for (int e = wb_tid(); e < No * Nl; e += wb_nthr()) {
+  // one warp per element: the lanes stride over the (t, cta) partials (contiguous), then a fixed butterfly -- the serial
+  // loop over 592 partials per thread was the whole duration of this kernel
+  for (int e = wb_warp(); e < No * Nl; e += wb_nthr() / WB_WARP) {
     float acc = 0.f;
     const float* pp = a.prof_p_part + (size_t)b * g.Tw * a.red_ctas * No * Nl + e;
-    const int np = g.Tw * a.red_ctas;   // (t, cta) partials are contiguous: one flat, fixed-order loop
-    WB_UNROLL_N(8) for (int c = 0; c < np; ++c) acc += __ldg(pp + (size_t)c * No * Nl);
-    a.d_prof_p[(size_t)b * No * Nl + e] = acc;
+    const int np = g.Tw * a.red_ctas;
+    for (int c = wb_lane(); c < np; c += WB_WARP) acc += __ldg(pp + (size_t)c * No * Nl);
+    acc = wb_warp_sum(acc);
+    if (wb_lane() == 0) a.d_prof_p[(size_t)b * No * Nl + e] = acc;
   }
   __syncthreads();
   for (int k = wb_tid(); k < No; k += wb_nthr()) {
@@ -1498,13 +1501,14 @@ __global__ void __launch_bounds__(256, WB_OCC_PROF_BWD) k_class_profile_bwd(WbDe
   }
 }
 
-__global__ void k_cls_reduce(WbDecB a) {
+__global__ void __launch_bounds__(1024) k_cls_reduce(WbDecB a) {
   const waldo_geom_t g = a.f.g;
   const int n = g.No * g.Nl, b = blockIdx.x;
-  for (int e = wb_tid(); e < n; e += wb_nthr()) {
+  for (int e = wb_warp(); e < n; e += wb_nthr() / WB_WARP) {   // one warp per element, lanes over the CTA partials
     float acc = 0.f;
-    for (int c = 0; c < a.f.prof_ctas; ++c) acc += a.cls_part[((size_t)b * a.f.prof_ctas + c) * n + e];
-    a.d_cls[(size_t)b * n + e] += acc;
+    for (int c = wb_lane(); c < a.f.prof_ctas; c += WB_WARP) acc += a.cls_part[((size_t)b * a.f.prof_ctas + c) * n + e];
+    acc = wb_warp_sum(acc);
+    if (wb_lane() == 0) a.d_cls[(size_t)b * n + e] += acc;
   }
 }
 
@@ -1753,7 +1757,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   if (a.d_alpha_acc || a.d_alpha) {
     if (filt && a.d_prof_p) {
       WB_BREQ(a.d_prof_sum, "d_prof_sum scratch missing");
-      WB_LAUNCH(k_profile_final_bwd, dim3(g.B), dim3(352), 0, st, a);
+      WB_LAUNCH(k_profile_final_bwd, dim3(g.B), dim3(1024), 0, st, a);
       WB_BLAUNCHED();
       if (!from_cls) {
         if ((g.flags & WALDO_F_WEIGHT_CLS) && a.d_cls) WB_BREQ(a.cls_part, "cls_part scratch missing");
@@ -1762,7 +1766,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
         else WB_LAUNCH(k_class_profile_bwd<0>, dim3(d.prof_ctas, g.B), dim3(256), 0, st, a);
         WB_BLAUNCHED();
         if ((g.flags & WALDO_F_WEIGHT_CLS) && a.d_cls) {
-          WB_LAUNCH(k_cls_reduce, dim3(g.B), dim3(128), 0, st, a);
+          WB_LAUNCH(k_cls_reduce, dim3(g.B), dim3(1024), 0, st, a);
           WB_BLAUNCHED();
         }
       }
