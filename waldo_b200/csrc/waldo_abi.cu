@@ -77,8 +77,8 @@ int waldo_tps_bwd(const waldo_tps_bwd_t* a, waldo_stream_t st) {
   WB_REQUIRE(a->N + 3 <= WB_MAX_K, "tps_bwd: too many control points");
   WB_REQUIRE(a->inverse_kernel && a->tgt_grid_repr && a->dgrid && a->partial && a->dpts, "tps_bwd: null pointer");
   if (a->n == 0) return 0;
-  WB_LAUNCH(k_tps_bwd_partial, dim3(a->n, (a->chunks + 3) / 4), dim3(128), 0, st, a->n, a->N, a->P, a->chunks,
-            a->tgt_grid_repr, a->dgrid, a->partial);   // 4 warps per CTA, one (item, chunk) per warp
+  WB_LAUNCH(k_tps_bwd_partial, dim3(a->n, a->chunks), dim3(((a->N + 3 + 31) / 32) * 32), 0, st, a->n, a->N, a->P, a->chunks,
+            a->tgt_grid_repr, a->dgrid, a->partial);
   WB_LAUNCHED();
   WB_LAUNCH(k_tps_bwd_final, dim3(a->n), dim3(128), 0, st, a->n, a->N, a->chunks, a->inverse_kernel, a->partial, a->dpts);
   WB_LAUNCHED();

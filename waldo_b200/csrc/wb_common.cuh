@@ -25,6 +25,7 @@ static thread_local wb_dim3 threadIdx(0, 0, 0), blockIdx, blockDim, gridDim;
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __syncthreads() ((void)0)
+#define __syncwarp() ((void)0)
 #define __ldg(p) (*(p))
 typedef void* cudaStream_t;
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }

@@ -1354,15 +1354,26 @@ __global__ void __launch_bounds__(1024) k_profile_final_bwd(WbDecB a) {
   const int No = g.No, Nl = g.Nl, nout = No * Nl + No;
   const int b = blockIdx.x;
   const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
-  // one warp per element: the lanes stride over the (t, cta) partials (contiguous), then a fixed butterfly -- the serial
-  // loop over 592 partials per thread was the whole duration of this kernel
-  for (int e = wb_warp(); e < No * Nl; e += wb_nthr() / WB_WARP) {
-    float acc = 0.f;
-    const float* pp = a.prof_p_part + (size_t)b * g.Tw * a.red_ctas * No * Nl + e;
-    const int np = g.Tw * a.red_ctas;
-    for (int c = wb_lane(); c < np; c += WB_WARP) acc += __ldg(pp + (size_t)c * No * Nl);
-    acc = wb_warp_sum(acc);
-    if (wb_lane() == 0) a.d_prof_p[(size_t)b * No * Nl + e] = acc;
+  // warp w sums slice w of the (t, cta) partials with its lanes on consecutive elements (coalesced, independent loads);
+  // the slices are then added in slice order.  (One thread per element looping over all 592 partials was the whole
+  // duration of this kernel.)
+  {
+    const int np = g.Tw * a.red_ctas, ne = No * Nl;
+    const int nw = wb_nthr() / WB_WARP, w = wb_warp();
+    const int per = (np + nw - 1) / nw, c0 = min(np, w * per), c1 = min(np, c0 + per);
+    const float* pp = a.prof_p_part + (size_t)b * np * ne;
+    __shared__ float s_slice[32][(WB_MAX_L - 1) * WB_MAX_NL];
+    for (int e = wb_lane(); e < ne; e += WB_WARP) {
+      float acc = 0.f;
+      WB_UNROLL_N(4) for (int c = c0; c < c1; ++c) acc += __ldg(pp + (size_t)c * ne + e);
+      s_slice[w][e] = acc;
+    }
+    __syncthreads();
+    for (int e = wb_tid(); e < ne; e += wb_nthr()) {
+      float acc = 0.f;
+      for (int ww = 0; ww < nw; ++ww) acc += s_slice[ww][e];
+      a.d_prof_p[(size_t)b * ne + e] = acc;
+    }
   }
   __syncthreads();
   for (int k = wb_tid(); k < No; k += wb_nthr()) {

@@ -53,46 +53,27 @@ __global__ void __launch_bounds__(128) k_tps_eval(int n, int N, int P, const flo
   }
 }
 
-// backward: partial[n,chunk,j,:] = sum_{p in chunk} repr[p,j] * dgrid[n,p,:].  One WARP per (item, chunk): the lanes stride
-// over the chunk's points (coalesced float2 loads of dgrid; the K-float rows of repr are contiguous, so the warp's strided
-// row reads fill whole sectors) with the K x 2 sums of a lane in fp64 registers, then a fixed xor-butterfly over the lanes.
-// The order of the additions is fixed by (lane, butterfly), i.e. run-to-run identical.  (The first version put one thread on
-// each j with a serial loop over the points: 19 of 32 lanes busy and 20 480 one-warp CTAs, 0.14 ms per launch.)
-#ifdef WB_HOST_EMU
-#define WB_TPS_LANES 1
-#else
-#define WB_TPS_LANES 32
-#endif
-#define WB_TPS_KB 8   // control-point columns accumulated per sweep (registers: 2 * WB_TPS_KB doubles)
-__global__ void __launch_bounds__(128) k_tps_bwd_partial(int n, int N, int P, int chunks, const float* __restrict__ repr,
-                                                         const float* __restrict__ dgrid, double* __restrict__ partial) {
+// backward: partial[n,chunk,j,:] = sum_{p in chunk} repr[p,j] * dgrid[n,p,:]  (ordered, one thread per j)
+__global__ void k_tps_bwd_partial(int n, int N, int P, int chunks, const float* __restrict__ repr,
+                                  const float* __restrict__ dgrid, double* __restrict__ partial) {
   const int K = N + 3;
-  const int wpb = wb_nthr() / WB_TPS_LANES;                 // warps per CTA
-  const int item = blockIdx.x;
-  const int lane = wb_lane();
+  const int item = blockIdx.x, ch = blockIdx.y;
   const int per = (P + chunks - 1) / chunks;
-  const float2* dg = reinterpret_cast<const float2*>(dgrid) + (size_t)item * P;
-  for (int ch = blockIdx.y * wpb + wb_warp(); ch < chunks; ch += gridDim.y * wpb)   // whole warps only: no block barrier
-  for (int j0 = 0; j0 < K; j0 += WB_TPS_KB) {
-    const int p0 = ch * per, p1 = min(P, p0 + per);
-    double ax[WB_TPS_KB], ay[WB_TPS_KB];
-    WB_UNROLL for (int u = 0; u < WB_TPS_KB; ++u) { ax[u] = 0.0; ay[u] = 0.0; }
-    for (int p = p0 + lane; p < p1; p += WB_TPS_LANES) {
-      const float2 gv = __ldg(dg + p);
-      const double gx = (double)gv.x, gy = (double)gv.y;
-      const float* rp = repr + (size_t)p * K + j0;
-      WB_UNROLL for (int u = 0; u < WB_TPS_KB; ++u)
-        if (j0 + u < K) { const double r = (double)__ldg(rp + u); ax[u] += r * gx; ay[u] += r * gy; }
+  const int p0 = ch * per, p1 = min(P, p0 + per);
+  for (int j = wb_tid(); j < K; j += wb_nthr()) {
+    double ax = 0.0, ay = 0.0;
+    WB_UNROLL_N(8) for (int p = p0; p < p1; ++p) {
+      double r = (double)__ldg(repr + (size_t)p * K + j);
+      ax += r * (double)__ldg(dgrid + ((size_t)item * P + p) * 2);
+      ay += r * (double)__ldg(dgrid + ((size_t)item * P + p) * 2 + 1);
     }
-    WB_UNROLL for (int u = 0; u < WB_TPS_KB; ++u) {
-      const double sx = wb_warp_sum(ax[u]), sy = wb_warp_sum(ay[u]);
-      if (lane == 0 && j0 + u < K) {
-        double* o = partial + (((size_t)item * chunks + ch) * K + j0 + u) * 2;
-        o[0] = sx; o[1] = sy;
-      }
-    }
+    double* o = partial + (((size_t)item * chunks + ch) * K + j) * 2;
+    o[0] = ax; o[1] = ay;
   }
 }
+// (Measured alternatives on B200, profiles/r1_v48_tps_bwd_ab.md: one warp per (item, slice) with lanes over the points and the
+//  K x 2 sums in registers -- rows of repr read straight from global memory 0.18 ms, staged through shared memory 0.43 ms per
+//  launch -- both slower than this form's 0.14 ms.)
 // dpts[n,i,:] = sum_j inverse_kernel[j,i] * (sum_chunks partial[n,chunk,j,:])
 __global__ void k_tps_bwd_final(int n, int N, int chunks, const float* __restrict__ inv,
                                 const double* __restrict__ partial, float* __restrict__ dpts) {

@@ -49,7 +49,7 @@ class _TpsEval(torch.autograd.Function):
         inverse_kernel, tgt_grid_repr = ctx.saved_tensors
         n, N, P = ctx.dims
         dgrid = _c(dgrid)
-        chunks = max(1, min(256, P // 512))   # slices of the pixel reduction, one warp each (16 points per lane)
+        chunks = max(1, min(256, P // 128))   # ordered slices of the pixel reduction: short serial loops, many CTAs
         partial = torch.empty(n, chunks, N + 3, 2, device=dgrid.device, dtype=torch.float64)
         dpts = torch.empty(n, N, 2, device=dgrid.device, dtype=torch.float32)
         a = L.TpsBwd(n, N, P, L.ptr(inverse_kernel), L.ptr(tgt_grid_repr), L.ptr(dgrid), chunks,
