@@ -72,3 +72,51 @@ def test_decode_oracle_direct(case):
 def test_small_chain_deterministic():
     cfg, (B, T, Tc), _ = parity.load_case("train_lo")
     parity.check_chain_deterministic(DEV, cfg, B, T, Tc, seed=5)
+
+
+def test_deterministic_mode_rejects_targets_outside_the_arena(monkeypatch):
+    """C ABI contract of the det_* fields: every scatter target must lie inside [det_base, det_base + det_n)."""
+    import waldo_b200 as wb
+    from waldo_b200 import functional as F
+    orig = F._scatter_targets
+
+    def broken(refs, det):
+        out, arena, shadow = orig(refs, det)
+        if det:   # d_input allocated on its own instead of as a view of the arena
+            out[0] = torch.zeros_like(refs[0]) if refs[0] is not None else None
+        return out, arena, shadow
+    monkeypatch.setattr(F, "_scatter_targets", broken)
+    cfg, _, z = parity.load_case("train_lo")
+    wb.set_deterministic(True)
+    try:
+        with pytest.raises(RuntimeError, match="outside the det arena"):
+            parity.kernel_decode(DEV, cfg, z)
+    finally:
+        wb.set_deterministic(False)
+
+
+def test_deterministic_flag_follows_torch():
+    import waldo_b200 as wb
+    assert not wb.is_deterministic()
+    torch.use_deterministic_algorithms(True)
+    try:
+        assert wb.is_deterministic()
+    finally:
+        torch.use_deterministic_algorithms(False)
+    assert not wb.is_deterministic()
+
+
+def test_scatter_targets_are_aligned_views_of_one_arena():
+    from waldo_b200 import functional as F
+    refs = [torch.empty(3, 5), None, torch.empty(7), torch.empty(2, 2, 2)]
+    out, arena, shadow = F._scatter_targets(refs, True)
+    assert out[1] is None and arena.dtype == torch.float32 and shadow.dtype == torch.int64 and arena.numel() == shadow.numel()
+    base = arena.data_ptr()
+    for r, t in zip(refs, out):
+        if r is None:
+            continue
+        assert t.shape == r.shape and float(t.abs().sum()) == 0.0
+        off = t.data_ptr() - base
+        assert 0 <= off and off + 4 * t.numel() <= 4 * arena.numel() and off % 16 == 0
+    plain, a2, s2 = F._scatter_targets(refs, False)
+    assert a2 is None and s2 is None and plain[1] is None and plain[0].shape == refs[0].shape
