@@ -43,6 +43,9 @@ def workload_cfg(name):
     if name == "kitti_rollout":
         cfg = wo.PathConfig(dim=128, load_dim=256, aspect_ratio=3.25, latent_shape=(8, 26), num_lyt=19)
         return cfg, dict(B=1, T=9, Tc=4, backward=False, label="kitti 256x832 rollout fwd B=1/GPU Tc=4->Tp=5")
+    if name == "nonrigid_train":   # BASELINE configs[4]: the reference ships no UCF-Sports / H3.6M script; SURVEY §8d C5 shape
+        cfg = wo.PathConfig(dim=128, load_dim=256, aspect_ratio=1.0, latent_shape=(8, 8))
+        return cfg, dict(B=8, T=5, Tc=4, backward=True, label="non-rigid 256x256 fwd+bwd B=8/GPU Tc=4->Tp=1")
     raise SystemExit(f"unknown workload {name}")
 
 

@@ -515,8 +515,15 @@ SYNTH_CASES = {
 }
 
 
+# Checked on the host emulation only so far (added after the round's last GPU session): the square, scale-2 shape family
+# of BASELINE configs[4] (bench.py --workload nonrigid_train), reduced.
+SYNTH_CASES_EMU_ONLY = {
+    "square_x2": (dict(dim=12, load_dim=24, aspect_ratio=1.0, num_obj=3, num_lyt=20, latent_shape=(2, 2)), 2, 5, 4),
+}
+
+
 def synth_case(name):
-    kw, B, T, Tc = SYNTH_CASES[name]
+    kw, B, T, Tc = (SYNTH_CASES.get(name) or SYNTH_CASES_EMU_ONLY[name])
     cfg = wo.PathConfig(**kw)
     d = wo.synth_inputs(cfg, B, T, Tc, seed=17, radius=0.2)
     st = wo.make_state(cfg)

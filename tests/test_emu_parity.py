@@ -120,3 +120,17 @@ def test_scatter_targets_are_aligned_views_of_one_arena():
         assert 0 <= off and off + 4 * t.numel() <= 4 * arena.numel() and off % 16 == 0
     plain, a2, s2 = F._scatter_targets(refs, False)
     assert a2 is None and s2 is None and plain[1] is None and plain[0].shape == refs[0].shape
+
+
+@pytest.mark.parametrize("case", list(parity.SYNTH_CASES_EMU_ONLY))
+def test_decode_oracle_direct_emu_only(case):
+    parity.check_decode_synth(DEV, case)
+
+
+def test_nonrigid_workload_shape_runs_the_whole_chain():
+    """bench.py --workload nonrigid_train (256x256, scale 2, 8x8 background control points) at B=1: the chain runs, every
+    gradient is finite, deterministic mode agrees with the default mode."""
+    import bench
+    cfg, spec = bench.workload_cfg("nonrigid_train")
+    assert cfg.hd_shape == (256, 256) and cfg.lo_shape == (128, 128) and spec["backward"]
+    parity.check_chain_deterministic(DEV, cfg, 1, spec["T"], spec["Tc"], seed=2)
