@@ -223,6 +223,8 @@ def _scatter_targets(refs, det):
     if not det:
         return [torch.zeros_like(r) if r is not None else None for r in refs], None, None
     live = [r for r in refs if r is not None]
+    if not live:   # nothing to accumulate: the call degenerates to the default path
+        return [None] * len(refs), None, None
     offs, n = [], 0
     for r in live:
         offs.append(n)
@@ -400,7 +402,8 @@ class _Decode(torch.autograd.Function):
                         L.ptr(d_input), L.ptr(d_tgo_s), L.ptr(d_sgo_s), L.ptr(d_tgb_s), L.ptr(d_sgb_s), L.ptr(d_occ),
                         L.ptr(d_oa), L.ptr(d_ba), L.ptr(d_cls_s), L.ptr(d_alpha_acc), L.ptr(d_f_lo), L.ptr(d_a_lo),
                         L.ptr(d_prof_p), L.ptr(d_prof_sum), red_ctas, L.ptr(occ_part), L.ptr(prof_p_part), L.ptr(cls_part), L.ptr(up_tab), L.ptr(glue), 0,
-                        L.ptr(det_arena), L.ptr(det_shadow, torch.int64), det_arena.numel() if det else 0, L.ptr(det_scale))
+                        L.ptr(det_arena), L.ptr(det_shadow, torch.int64), det_arena.numel() if det_arena is not None else 0,
+                        L.ptr(det_scale))
         _staged(lib.waldo_decode_bwd, b, L.stream_of(inp_c), "decode_bwd", dev=dev)
         if det:
             global LAST_DET_SCALE
