@@ -134,3 +134,29 @@ def test_nonrigid_workload_shape_runs_the_whole_chain():
     cfg, spec = bench.workload_cfg("nonrigid_train")
     assert cfg.hd_shape == (256, 256) and cfg.lo_shape == (128, 128) and spec["backward"]
     parity.check_chain_deterministic(DEV, cfg, 1, spec["T"], spec["Tc"], seed=2)
+
+
+def test_no_kernel_reads_uninitialised_scratch():
+    """torch.use_deterministic_algorithms(True) fills every torch.empty buffer with NaN: the whole chain (control points ->
+    loss -> every leaf) must still give finite results, bit-identical to the ones obtained with ordinary allocations --
+    i.e. no kernel depends on the previous contents of an output / scratch buffer."""
+    import waldo_b200 as wb
+    cfg, (B, T, Tc), _ = parity.load_case("train_lo")
+    opt = parity.make_opt(cfg)
+    warper = wb.Warper(opt).to(DEV)
+    d = parity.wo.synth_inputs(cfg, B, T, Tc, seed=9)
+    om, bg = wb.alpha_masks(opt)
+    wb.set_deterministic(True)
+    try:
+        g1 = parity._chain_grads(DEV, cfg, d, warper, om, bg)
+    finally:
+        wb.set_deterministic(False)
+    torch.use_deterministic_algorithms(True)
+    try:
+        assert torch.utils.deterministic.fill_uninitialized_memory
+        g2 = parity._chain_grads(DEV, cfg, d, warper, om, bg)
+    finally:
+        torch.use_deterministic_algorithms(False)
+    for k in g1:
+        assert bool(torch.isfinite(g2[k]).all()), k
+        assert torch.equal(g1[k], g2[k]), k
