@@ -142,40 +142,123 @@ def make_inputs(cfg, B, T, Tc, seed):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def _ref_loss(out):
+    return out[0].abs().mean() + out[1].abs().mean()
+
+
 def oracle_step(wo, st, d, backward):
     lv = {k: d[k].clone().requires_grad_(backward) for k in ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")}
     occ, oa, ba, grid = wo.estimate_alpha_grid_occ(st, lv["obj_alpha_raw"], lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
     with torch.set_grad_enabled(backward):
         out = wo.decode_output(st, lv["input"], grid, occ, oa, ba, lv["cls"], d["ctx_ts"], d["pred_ts"])
-        loss = out[0].abs().mean() + out[1].abs().mean()
+        loss = _ref_loss(out)
     if backward:
         loss.backward()
     return float(loss)
 
 
+def reference_runner(cfg, device):
+    """(step(d, backward), kind, what): the UNMODIFIED reference's own code (oracle/ref_runner.py: /root/reference here, its
+    staged byte-for-byte copy oracle/_ref on the GPU box) when present, else the oracle port."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import waldo_oracle as wo
+    try:
+        import ref_runner
+        if ref_runner.available():
+            rp = ref_runner.RefPath(cfg, device)
+
+            def step(d, backward):
+                # the stable tie rule only matters for parity; the timed arm runs the reference exactly as shipped
+                out, _, _, _, loss = rp.chain(d, backward=backward, stable=False, loss_fn=_ref_loss)
+                return float(loss) if loss is not None else float(_ref_loss(out))
+            where = "staged copy oracle/_ref" if ref_runner.ref_loader.is_staged_copy() else ref_runner.ref_loader.REF_ROOT
+            return step, "reference", f"the reference's own code ({where}: Warper.forward + compute_occ + LVD.forward decode_output)"
+    except Exception as e:   # pragma: no cover - the port below always exists
+        print(f"[bench] reference not loadable ({e}); timing the oracle port", file=sys.stderr)
+    st = wo.make_state(cfg)
+    return (lambda d, backward: oracle_step(wo, st, d, backward)), "port", "oracle/waldo_oracle.py (port of the reference)"
+
+
 def cpu_baseline(cfg, spec, steps=1, warmup=0):
-    """The oracle port on the host cores, on a bounded sample of the workload: ONE video (B=1) per step."""
+    """The reference on the host cores, on a bounded sample of the workload: ONE video (B=1) per step."""
     import warnings
     warnings.filterwarnings("ignore")
-    import waldo_oracle as wo
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    st = wo.make_state(cfg)
+    step, kind, what = reference_runner(cfg, "cpu")
     d = make_inputs(cfg, 1, spec["T"], spec["Tc"], seed=0)
     frames = spec["T"] - spec["Tc"]
     for _ in range(warmup):
-        oracle_step(wo, st, d, spec["backward"])
+        step(d, spec["backward"])
     t0 = time.perf_counter()
     for _ in range(steps):
-        oracle_step(wo, st, d, spec["backward"])
+        step(d, spec["backward"])
     dt = (time.perf_counter() - t0) / steps
-    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": kind,
             "sample": f"B=1 of the workload ({frames} future frame(s), {'fwd+bwd' if spec['backward'] else 'fwd'}), "
-                      f"{steps} step(s) of {dt:.1f} s, torch {torch.__version__} CPU, oracle/waldo_oracle.py"}, dt
+                      f"{steps} step(s) of {dt:.1f} s, torch {torch.__version__} CPU, {what}"}, dt
+
+
+def cpu_c1_split(cfg):
+    """BASELINE configs[0] (C1): the reference's forward on the host cores, B=1, 4 contexts -> 1 frame, split per stage
+    (SURVEY.md §8d): Warper.forward + compute_occ / decode_output / WIF.forward (UNet + fuse tail)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_runner
+        if not ref_runner.available():
+            return None
+        rp = ref_runner.RefPath(cfg, "cpu")
+        d = make_inputs(cfg, 1, 5, 4, seed=0)
+        ns = ref_runner.ref_loader.load()
+        wif = ns.wif.WIF(ref_runner.ref_opt(cfg)).eval()
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            occ, oa, ba, grid = rp.stage_a(d["obj_alpha_raw"], d["obj_pose"], d["bg_pose"], d["occ_score"], stable=False)
+            t1 = time.perf_counter()
+            out = rp.decode(d["input"], grid, occ, oa, ba, d["cls"], d["ctx_ts"], d["pred_ts"])
+            t2 = time.perf_counter()
+            wif(out[5])
+            t3 = time.perf_counter()
+        return {"config": "C1: Cityscapes-shape forward on CPU, B=1, 4 contexts -> 1 frame (BASELINE configs[0])",
+                "warper_forward_s": t1 - t0, "decode_output_s": t2 - t1, "wif_forward_s": t3 - t2,
+                "frames_per_s_hot_path": 1.0 / (t2 - t0), "frames_per_s_with_wif": 1.0 / (t3 - t0), "cores": os.cpu_count()}
+    except Exception as e:
+        return {"error": str(e)[:200]}
+
+
+def gpu_stock_baseline(cfg, spec, dev, steps=3, batch=1):
+    """The honest GPU comparator ('the bar is stock PyTorch-on-B200 running the reference code'): the
+    reference's own modules moved to CUDA, ~170 ATen launches per decode, same workload at a bounded batch."""
+    step, kind, what = reference_runner(cfg, dev)
+    d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in make_inputs(cfg, batch, spec["T"], spec["Tc"], seed=0).items()}
+    frames = batch * (spec["T"] - spec["Tc"])
+    for _ in range(2):
+        step(d, spec["backward"])
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step(d, spec["backward"])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    peak = torch.cuda.max_memory_allocated(dev) / 1e9
+    return {"value": frames / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "kind": kind, "device": "cuda (stock PyTorch ATen kernels)",
+            "sample": f"B={batch} of the workload per step ({'fwd+bwd' if spec['backward'] else 'fwd'}), {steps} timed steps after 2 warm-ups, "
+                      f"peak {peak:.1f} GB; {what}"}
 
 
 def run_reference(args, cfg, spec, rank, world):
     if rank != 0:
+        return
+    if args.impl == "reference-gpu":
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+        g = gpu_stock_baseline(cfg, spec, dev, steps=max(1, args.steps), batch=args.batch or 1)
+        line = {"impl": "reference-gpu", "metric": "warped+composited frames/s", "value": g["value"], "unit": "frames/s", "n_gpus": 1,
+                "steps": max(1, args.steps), "warmup": 2, "ms_per_step": g["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": spec["label"], "sample": g["sample"]},
+                "gpu_stock_baseline": g, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
         return
     budget_s = 170.0
     base, dt = cpu_baseline(cfg, spec, steps=1, warmup=0)   # doubles as the first warm-up step
@@ -197,7 +280,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="waldo", choices=["waldo", "reference"])
+    ap.add_argument("--impl", default="waldo", choices=["waldo", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="city_train")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -212,7 +295,7 @@ def main():
     cfg, spec = workload_cfg(args.workload)
     if args.batch:
         spec["B"] = args.batch
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-gpu"):
         run_reference(args, cfg, spec, rank, world)
         return
 
@@ -408,7 +491,15 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
+            torch.cuda.empty_cache()
+            try:
+                line["gpu_stock_baseline"] = gpu_stock_baseline(cfg, spec, dev, steps=3, batch=1)
+            except Exception as e:   # never lose the line to the comparator
+                line["gpu_stock_baseline"] = {"error": str(e)[:200]}
+            torch.cuda.empty_cache()
             line["cpu_baseline"], _ = cpu_baseline(cfg, spec, steps=1, warmup=0)
+            if args.workload == "city_train":
+                line["cpu_baseline"]["c1_forward_split"] = cpu_c1_split(cfg)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -45,49 +45,32 @@ CASES = {
     # 11 heavily overlapping layers: exercises the dense (> 8 live layers per warp) code path of the HD kernels
     "many_obj": (dict(dim=16, load_dim=32, aspect_ratio=2.0, num_obj=10, obj_shape=(2, 2), latent_shape=(2, 4),
                       patch_size=8, num_lyt=3), 1, 3, 2, True),
+    # The REAL structure of the benchmarked configurations at reduced resolution: 16 objects with 4x4
+    # control points on 64x64 canvases, the 8x16 (Cityscapes, K = 131) / 8x26 (KITTI, K = 211) background systems, 4
+    # contexts, 20 / 19 classes, scale_hd 4 / 2.  Stored lean (LEAN below): projections are re-drawn from the seed and
+    # alpha_ctx is read back from raw_output by the tests.
+    "city_real": (dict(dim=16, load_dim=64, aspect_ratio=2.0), 1, 5, 4, False),
+    "kitti_real": (dict(dim=16, load_dim=32, aspect_ratio=3.25, latent_shape=(8, 26), num_lyt=19), 1, 6, 4, True),
 }
+LEAN = ("city_real", "kitti_real")
+PROJ_SEED = 1234
+PROJ_ORDER = ("output", "flow", "alpha", "raw_alpha", "raw_output")
 
 
-def ref_opt(cfg: wo.PathConfig):
-    """A reference option namespace carrying this PathConfig (only the fields Warper/LVD.forward read)."""
-    opt = ref_loader.parse_opts("scripts/cityscapes/test.sh")
-    for k in ("dim", "load_dim", "aspect_ratio", "num_obj", "patch_size", "scale_factor", "num_lyt", "weight_cls",
-              "min_cls", "include_self", "restrict_to_ctx", "use_disocc", "no_filter", "allow_ghost",
-              "pad_obj_alpha", "pad_bg_alpha"):
-        setattr(opt, k, getattr(cfg, k))
-    opt.obj_shape = list(cfg.obj_shape)
-    opt.latent_shape = list(cfg.latent_shape)
-    opt.num_perm_grid = 1
-    opt.time_dropout = False
-    return opt
+def draw_projections(shapes):
+    """The seeded random projections of the fixture loss, in PROJ_ORDER, then the fake UNet output (B*Tp*Tc, 5, Hd, Wd).
+    `shapes`: name -> shape for PROJ_ORDER.  Shared with tests/parity.py (lean fixtures do not store them)."""
+    gen = torch.Generator().manual_seed(PROJ_SEED)
+    proj = {n: torch.randn(tuple(shapes[n]), generator=gen) for n in PROJ_ORDER}
+    Bq, Tcq, Tpq, Cq, Hq, Wq = shapes["raw_output"]
+    unet_out = torch.randn(Bq * Tpq * Tcq, 5, Hq, Wq, generator=gen)
+    return proj, unet_out
 
 
-def ref_modules(cfg: wo.PathConfig):
-    """(warper, lvd_like) where lvd_like exposes the reference's LVD.forward / compute_occ without
-    constructing the (out-of-scope) encoder / transformer stacks."""
-    ns = ref_loader.load()
-    opt = ref_opt(cfg)
-    warper = ns.lvd.Warper(opt)
-    om, bg = wo.alpha_masks(cfg)
-    fake = types.SimpleNamespace(
-        warper=warper, restrict_to_ctx=cfg.restrict_to_ctx, use_disocc=cfg.use_disocc,
-        include_self=cfg.include_self, diag=torch.eye(cfg.num_obj)[None, None],
-        remove_obj=False, freeze_obj=False)
-    fake.compute_occ = lambda s: ns.lvd.LVD.compute_occ(fake, s)
-    fake.forward = lambda **kw: ns.lvd.LVD.forward(fake, **kw)
-    return warper, fake
+from ref_runner import ref_opt, ref_modules, ctx_pred  # noqa: E402,F401
 
 
-def ctx_pred(cfg, B, T, Tc):
-    if cfg.restrict_to_ctx:
-        Tp = T - Tc
-        return torch.arange(Tc).view(1, Tc, 1).expand(B, Tc, Tp), torch.arange(Tc, T)
-    # train_lvd: ctx_mode "prev" (synthesizer.py:833-839): previous frame is the context of every frame
-    ts = torch.roll(torch.arange(T), 1).view(1, 1, T).expand(B, 1, T)
-    return ts, torch.arange(T)
-
-
-def run_reference(cfg: wo.PathConfig, B, T, Tc, smooth, seed=0):
+def run_reference(cfg: wo.PathConfig, B, T, Tc, smooth, seed=0, lean=False):
     ns = ref_loader.load()
     warper, lvd = ref_modules(cfg)
     d = wo.synth_inputs(cfg, B, T, Tc, seed=seed, smooth=smooth, radius=0.2)
@@ -106,18 +89,14 @@ def run_reference(cfg: wo.PathConfig, B, T, Tc, smooth, seed=0):
                       ctx_ts=d["ctx_ts"], pred_ts=d["pred_ts"], cls=leaves["cls"], mode="decode_output")
     output, flow, a_unflt, alpha, raw_alpha, raw_output, alpha_ctx = out
     # fixed scalar loss touching every differentiable output; weights are a seeded random projection
-    gen = torch.Generator().manual_seed(1234)
-    proj = {}
+    outs = dict(output=output, flow=flow, alpha=alpha, raw_alpha=raw_alpha, raw_output=raw_output)
+    proj, unet_out = draw_projections({n: t.shape for n, t in outs.items()})
     loss = 0
-    for name, t in (("output", output), ("flow", flow), ("alpha", alpha), ("raw_alpha", raw_alpha),
-                    ("raw_output", raw_output)):
-        w = torch.randn(t.shape, generator=gen)
-        proj[name] = w
-        loss = loss + (t * w).sum()
+    for name in PROJ_ORDER:
+        loss = loss + (outs[name] * proj[name]).sum()
     loss.backward()
     # WIF fuse tail on a seeded fake UNet output (wif.py:50-54 via the real WIF.forward with a stub unet)
     Bq, Tcq, Tpq, Cq, Hq, Wq = raw_output.shape
-    unet_out = torch.randn(Bq * Tpq * Tcq, 5, Hq, Wq, generator=gen)
     wif_self = types.SimpleNamespace(score=True, ab=True, unet=lambda x: unet_out)
     fused = ns.wif.WIF.forward(wif_self, raw_output.detach())
     res = dict(
@@ -129,8 +108,11 @@ def run_reference(cfg: wo.PathConfig, B, T, Tc, smooth, seed=0):
         res["alpha_unflt"] = a_unflt
     for k, v in leaves.items():
         res["grad_" + k] = v.grad
-    for k, v in proj.items():
-        res["proj_" + k] = v
+    if lean:
+        del res["alpha_ctx"], res["wif_unet_out"]
+    else:
+        for k, v in proj.items():
+            res["proj_" + k] = v
     for k in ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls", "ctx_ts", "pred_ts"):
         res["in_" + k] = d[k]
     return {k: v.detach().cpu().numpy() for k, v in res.items()}
@@ -144,7 +126,7 @@ def main():
         if only and name not in only:
             continue
         cfg = wo.PathConfig(**kw)
-        res = run_reference(cfg, B, T, Tc, smooth)
+        res = run_reference(cfg, B, T, Tc, smooth, lean=name in LEAN)
         meta = dict(kw, B=B, T=T, Tc=Tc, smooth=smooth)
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, meta=np.array(repr(meta)), **res)

@@ -1,9 +1,10 @@
 """Load the UNMODIFIED reference (/root/reference) on CPU as ground truth.
 
 TEST INFRASTRUCTURE ONLY.  This module is used by `oracle/make_golden.py` (to
-generate the committed fixtures under tests/golden/) and by the optional
-`tests/test_oracle_vs_reference.py` (skipped when /root/reference is absent,
-i.e. on the GPU box).  Nothing in `waldo_b200/` imports it.
+generate the committed fixtures under tests/golden/), by `tests/test_reference_dropin.py`
+/ `tests/test_full_shape.py` (the reference's own code as the checker, skipped when neither
+/root/reference nor the staged copy oracle/_ref exists) and by `bench.py --impl reference[-gpu]`.
+Nothing in `waldo_b200/` imports it.
 
 Recipe = SURVEY.md Appendix A: three stubs (matplotlib, models.modules.mat,
 lpips), `Tensor.cuda` identity on CPU (wif.py:31), options resolved by the
@@ -21,11 +22,27 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("WALDO_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """/root/reference in the build container; on the GPU box the byte-for-byte staged copy oracle/_ref
+    (oracle/build_ref.py)."""
+    for cand in (os.environ.get("WALDO_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "models", "nets", "lvd.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "models", "nets", "lvd.py"))
+
+
+def is_staged_copy() -> bool:
+    return os.path.abspath(REF_ROOT) == os.path.join(_HERE, "_ref")
 
 
 _loaded = {}
@@ -58,6 +75,7 @@ def load():
     _install_stubs()
     if not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self  # wif.py:31
+    # tools/ has no __init__.py in the reference either: a namespace package rooted at REF_ROOT
     ns = types.SimpleNamespace()
     import tools.utils as ref_utils  # noqa
     import models.modules.warp as ref_warp  # noqa

@@ -439,9 +439,10 @@ def layer_flows(st: WarperState, grid, ctx_ts: torch.Tensor, pred_ts: torch.Tens
     return resize(fl, cfg.scale_hd), s_lo
 
 
-def grid_to_flow(st: WarperState, inp, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts):
+def grid_to_flow(st: WarperState, inp, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts, trace: Optional[dict] = None):
     """lvd.py:707-828 when cfg.restrict_to_ctx else lvd.py:602-705.
-    Returns (flow, alpha_unflt|None, alpha, alpha_ctx, disocc) with the reference's shapes."""
+    Returns (flow, alpha_unflt|None, alpha, alpha_ctx, disocc) with the reference's shapes.
+    `trace` (a dict) receives the index-class intermediates: is_obj (B,Tp,L,Hd,Wd) bool, lvd.py:788-791."""
     cfg = st.cfg
     B, T = inp.shape[:2]
     Tc, Tp = ctx_ts.shape[1], pred_ts.shape[0]
@@ -459,6 +460,8 @@ def grid_to_flow(st: WarperState, inp, grid, occ, obj_alpha, bg_alpha, cls, ctx_
     if cfg.restrict_to_ctx and not cfg.allow_ghost:
         is_obj = (resize(s_lo.unsqueeze(3), cfg.scale_hd).squeeze(3) > 0.9).to(inp.dtype)   # B Tp No Hd Wd
         is_obj = torch.cat([torch.ones_like(is_obj[:, :, :1]), is_obj], dim=2)
+        if trace is not None:
+            trace["is_obj"] = is_obj.detach() > 0
         R = R * is_obj.unsqueeze(1)
     disocc = R.max(dim=3, keepdim=True)[0]                                      # B7  lvd.py:803 / :680
     Actx = occlude(R, occ[:, pred_ts].unsqueeze(1))                             # B8  lvd.py:806-815
@@ -487,11 +490,11 @@ def input_to_output(st: WarperState, inp, alpha_ctx, flow, ctx_ts, eps: float = 
     return out, raw
 
 
-def decode_output(st: WarperState, inp, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts):
+def decode_output(st: WarperState, inp, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts, trace: Optional[dict] = None):
     """lvd.py:141-153.  Returns the reference's 7-tuple
     (output, flow, alpha_unflt, alpha, raw_alpha, raw_output, alpha_ctx)."""
     cfg = st.cfg
-    flow, a_unflt, alpha, alpha_ctx, disocc = grid_to_flow(st, inp, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
+    flow, a_unflt, alpha, alpha_ctx, disocc = grid_to_flow(st, inp, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts, trace)
     out, raw = input_to_output(st, inp, alpha_ctx, flow, ctx_ts)
     raw_alpha = out[:, :, -1:]
     if cfg.use_disocc:

@@ -28,7 +28,10 @@ import waldo_oracle as wo  # noqa: E402
 import waldo_b200 as wb  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["city_x4", "kitti_x2", "train_lo", "cls_plain", "many_obj", "c23_x4", "c22_x2"]
+CASES = ["city_x4", "kitti_x2", "train_lo", "cls_plain", "many_obj", "c23_x4", "c22_x2", "city_real", "kitti_real"]
+# city_real / kitti_real: the REAL structure of the benchmarked configurations at reduced resolution -- 16 objects with 4x4
+# control points, the K = 131 / 211 background TPS systems, 4 contexts, 20 / 19 classes, scale_hd 4 / 2 (oracle/make_golden.py)
+PROJ_SEED, PROJ_ORDER = 1234, ("output", "flow", "alpha", "raw_alpha", "raw_output")
 OUT_NAMES = ["output", "flow", "alpha_unflt", "alpha", "raw_alpha", "raw_output", "alpha_ctx"]
 
 FWD_TOL = 1e-5
@@ -40,7 +43,16 @@ def load_case(name):
     meta = ast.literal_eval(str(z["meta"]))
     B, T, Tc, smooth = meta.pop("B"), meta.pop("T"), meta.pop("Tc"), meta.pop("smooth")
     cfg = wo.PathConfig(**meta)
-    return cfg, (B, T, Tc), {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    d = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    if "proj_output" not in d:   # lean fixture: the projections / fake UNet output are re-drawn from the seed, in the
+        gen = torch.Generator().manual_seed(PROJ_SEED)   # order oracle/make_golden.draw_projections drew them
+        for n in PROJ_ORDER:
+            d["proj_" + n] = torch.randn(tuple(d[n].shape), generator=gen)
+        Bq, Tcq, Tpq, Cq, Hq, Wq = d["raw_output"].shape
+        d["wif_unet_out"] = torch.randn(Bq * Tpq * Tcq, 5, Hq, Wq, generator=gen).view(Bq, Tpq, Tcq, 5, Hq, Wq)
+        C, L = d["in_input"].shape[2], cfg.num_obj + 1
+        d["alpha_ctx"] = d["raw_output"][:, :Tc, :, C:C + L]
+    return cfg, (B, T, Tc), d
 
 
 def make_opt(cfg: wo.PathConfig):
@@ -261,34 +273,47 @@ def check_decode_deterministic(dev, case):
 
 
 def check_end_to_end(dev, case):
-    """Tier T2: control points -> grids -> decode, statistical agreement with the reference's outputs, plus gradients
-    reaching every leaf (obj_pose, bg_pose, occ_score, obj_alpha, cls, input) through the whole chain."""
+    """Tier T2: control points -> grids -> decode, plus gradients reaching every leaf (obj_pose, bg_pose, occ_score,
+    obj_alpha, cls, input) through the whole chain.  The chain is discontinuous (round / dedupe / > 0.9 in the inverse
+    warp) and the K = 131 / 211 background TPS system has cond ~1e4, so the reference's OWN fp32 run differs from exact
+    arithmetic by O(1) on some pixels: agreement is statistical and fp64-arbitrated -- the kernel must
+    be as close to the oracle's fp64 twin as the reference's fp32 outputs (the committed fixture) are, within 2x."""
     cfg, _, z = load_case(case)
     opt = make_opt(cfg)
     warper = wb.Warper(opt).to(dev)
-    lv = {k: z["in_" + k].clone().to(dev).requires_grad_(True) for k in ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")}
+    names = ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")
+    lv = {k: z["in_" + k].clone().to(dev).requires_grad_(True) for k in names}
     om, bg = wb.alpha_masks(opt)
     om = om.to(dev) if torch.is_tensor(om) else om
     occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, lv["obj_alpha_raw"], om, bg.to(dev), lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
     out = wb.decode_output(warper, lv["input"], grid, occ, oa, ba, lv["cls"], z["in_ctx_ts"].to(dev), z["in_pred_ts"].to(dev), cfg.restrict_to_ctx)
-    loss = 0
-    for n, o in zip(OUT_NAMES, out):
+    # the fp64 twin of the whole chain
+    st64 = wo.make_state(cfg, torch.float64)
+    l64 = {k: z["in_" + k].double().clone().requires_grad_(True) for k in names}
+    occ64, oa64, ba64, grid64 = wo.estimate_alpha_grid_occ(st64, l64["obj_alpha_raw"], l64["obj_pose"], l64["bg_pose"], l64["occ_score"])
+    out64 = wo.decode_output(st64, l64["input"], grid64, occ64, oa64, ba64, l64["cls"], z["in_ctx_ts"], z["in_pred_ts"])
+    loss, loss64 = 0, 0
+    for n, o, o64 in zip(OUT_NAMES, out, out64):
         if o is None:
             continue
-        err = (o.detach().cpu() - z[n]).abs()
-        # the reference's own fp32-vs-fp64 mean discrepancy end to end is 2.5e-3 on raw_output (SURVEY.md App. D)
-        assert float(err.mean()) <= 2.5e-3, f"{case}/{n}: mean abs err {float(err.mean()):.3e}"
+        ek = (o.detach().cpu().double() - o64.detach()).abs().mean()
+        er = (z[n].double() - o64.detach()).abs().mean()
+        # floor: the reference's own fp32-vs-fp64 mean discrepancy end to end (2.5e-3 on raw_output, SURVEY.md App. D)
+        assert float(ek) <= max(2 * float(er), 2.5e-3), f"{case}/{n}: mean |k - f64| {float(ek):.3e} vs reference's {float(er):.3e}"
         if "proj_" + n in z:
             loss = loss + (o * z["proj_" + n].to(dev)).sum()
-    assert abs(float(loss) - float(z["loss"])) <= 1e-3 * max(1.0, abs(float(z["loss"])))
+            loss64 = loss64 + (o64 * z["proj_" + n].double()).sum()
+    dk, dr = abs(float(loss) - float(loss64)), abs(float(z["loss"]) - float(loss64))
+    assert dk <= 2 * dr + 1e-3 * max(1.0, abs(float(loss64))), f"{case}: loss {float(loss):.6f} vs f64 {float(loss64):.6f} (reference {float(z['loss']):.6f})"
     loss.backward()
+    loss64.backward()
     for k, v in lv.items():
-        gref = z["grad_" + k]
-        scale = float(gref.abs().max())
-        rel = float((v.grad.cpu() - gref).abs().max()) / max(scale, 1e-30)
-        # chained through the discontinuous inverse warp and the cond~1e4 TPS system: statistical bound only
-        assert rel <= 5e-2, f"{case}/d {k}: rel err {rel:.3e}"
-        assert float(v.grad.abs().max()) > 0 or scale == 0
+        gref, g64 = z["grad_" + k].double(), l64[k].grad
+        scale = max(float(g64.abs().max()), 1e-30)
+        ek = float((v.grad.cpu().double() - g64).abs().max()) / scale
+        er = float((gref - g64).abs().max()) / scale
+        assert ek <= 2 * er + 5e-2, f"{case}/d {k}: rel err vs f64 {ek:.3e}, reference's own {er:.3e}"
+        assert float(v.grad.abs().max()) > 0 or float(gref.abs().max()) == 0
 
 
 def _chain_grads(dev, cfg, d, warper, om, bg):
@@ -555,3 +580,141 @@ def check_decode_synth(dev, name):
         arbitrated(o, a, b, FWD_TOL, f"{name}/{n} (vs oracle)")
     for kname in LEAF_KEYS:
         grad_close(g[kname], g32[kname], g64[kname], f"{name}/d {kname}")
+
+
+# ------------------------------------------------------------------------------------------------ the benchmarked shapes
+# the shapes that are shipped and benchmarked, compared with the oracle (fp32 + fp64 twin) and -- where
+# the staged reference oracle/_ref (or /root/reference) is present -- with the reference's own code, at FULL size:
+# 16 objects x 4x4 control points, K = 131 / 211 / 67 background TPS systems, 17 layers, scale_hd 4 / 2, the dense-layer
+# branch, the FAST gather kernels at real tile counts.
+FULL_SHAPES = {
+    # name: (PathConfig kwargs, B, T, Tc)          BASELINE.json configs
+    "city_512x1024": (dict(), 1, 5, 4),                                                                      # [0], [1], [3]
+    "kitti_256x832": (dict(dim=128, load_dim=256, aspect_ratio=3.25, latent_shape=(8, 26), num_lyt=19), 1, 6, 4),   # [2]
+    "nonrigid_256x256": (dict(dim=128, load_dim=256, aspect_ratio=1.0, latent_shape=(8, 8)), 2, 5, 4),       # [4]
+}
+REDUCED_SHAPES = {   # same structure at 1/4 of the resolution: the host-emulation (CPU suite) version of the same check
+    "city_128x256": (dict(dim=32, load_dim=128), 1, 5, 4),
+    "kitti_64x208": (dict(dim=32, load_dim=64, aspect_ratio=3.25, latent_shape=(8, 26), num_lyt=19), 1, 6, 4),
+    "nonrigid_64x64": (dict(dim=32, load_dim=64, aspect_ratio=1.0, latent_shape=(8, 8)), 2, 5, 4),
+}
+
+
+def _argmax_report(k, r, what, tol=FWD_TOL):
+    """Rule (1): the layer-assignment map (logger.py:172 `alpha.max(dim=-3)[1]`) is identical.  No margin filter: every
+    mismatching pixel is counted, and each one must be a numerical tie of the reference itself (top-2 margin within twice
+    the forward tolerance, i.e. the two layers are interchangeable within rule (2))."""
+    ka, ra = k.argmax(dim=-3), r.argmax(dim=-3)
+    bad = ka != ra
+    n_bad = int(bad.sum())
+    if n_bad:
+        top2 = r.topk(2, dim=-3)[0]
+        margin = (top2.select(-3, 0) - top2.select(-3, 1))[bad]
+        assert float(margin.max()) <= 2 * tol, f"{what}: {n_bad} argmax mismatches, largest reference margin {float(margin.max()):.3e}"
+    return n_bad, ka.numel()
+
+
+def check_full_shape(dev, name, with_reference=True, report=None):
+    kw, B, T, Tc = (FULL_SHAPES.get(name) or REDUCED_SHAPES[name])
+    cfg = wo.PathConfig(**kw)
+    opt = make_opt(cfg)
+    warper = wb.Warper(opt).to(dev)
+    d = wo.synth_inputs(cfg, B, T, Tc, seed=0)
+    H, W = cfg.lo_shape
+    rep = report if report is not None else {}
+    st32, st64 = wo.make_state(cfg), wo.make_state(cfg, torch.float64)
+    # ---------------- stage A, T0: TPS at the real K (fp64-arbitrated), inverse warp fed the ORACLE's tgt_grid (bit-exact maps)
+    with torch.no_grad():
+        for which, tps, b32, b64, pts in (("obj", warper.tps_obj, st32.tps_obj, st64.tps_obj, d["obj_pose"].reshape(-1, d["obj_pose"].shape[-2], 2)),
+                                          ("bg", warper.tps_bg, st32.tps_bg, st64.tps_bg, d["bg_pose"].reshape(-1, d["bg_pose"].shape[-2], 2))):
+            out = tps(pts.to(dev))
+            o32, o64 = wo.tps_eval(b32, pts), wo.tps_eval(b64, pts.double())
+            arbitrated(out, o32, o64, FWD_TOL, f"{name}/tps_{which}")
+            ek, er = float((out.cpu().double() - o64).abs().max()), float((o32.double() - o64).abs().max())
+            assert ek <= er + 1e-6, f"{name}/tps_{which}: kernel {ek:.3e} further from fp64 than the reference's fp32 {er:.3e}"
+            rep[f"tps_{which}_err_vs_f64"] = (ek, er)
+        occ32, oa32, ba32, grid32 = wo.estimate_alpha_grid_occ(st32, d["obj_alpha_raw"], d["obj_pose"], d["bg_pose"], d["occ_score"])
+        for which, mod, fwd, erode in (("obj", warper.invert_obj, grid32[0], True), ("bg", warper.invert_bg, grid32[2], False)):
+            fwd = fwd.reshape(-1, *fwd.shape[-3:])
+            box = []
+            out = mod(fwd.to(dev), erode=erode, trace_box=box)
+            tr = box[0]
+            ref = wo.inverse_warp(fwd, (H, W), erode=erode, trace=True)
+            P = H * W
+            assert torch.equal(tr.field.cpu().long(), ref.field), f"{name}/{which}: field differs"
+            win = tr.winner.cpu().long()
+            assert torch.equal(torch.where(win == 2 ** 31 - 1, torch.full_like(win, P), win), ref.winner), f"{name}/{which}: winners differ"
+            m = 6
+            assert torch.equal(((tr.level != 255) & (tr.eroded == 0))[:, m:-m, m:-m].cpu(), ref.known), f"{name}/{which}: known mask differs"
+            assert torch.equal((tr.level[:, m:-m, m:-m] == 0).cpu(), ref.hit), f"{name}/{which}: hit mask differs"
+            assert float((out.cpu() - ref.grid).abs().max()) <= FWD_TOL, f"{name}/{which}: inverse-warp values"
+        occ_k = wb.compute_occ(d["occ_score"].to(dev))
+        assert float((occ_k.cpu() - occ32).abs().max()) <= 1e-6
+    # ---------------- decode, T1 (identical grid tuple on both sides): every output, all 8 leaf gradients
+    z = {"in_input": d["input"], "tgt_grid_obj": grid32[0], "src_grid_obj": grid32[1], "tgt_grid_bg": grid32[2], "src_grid_bg": grid32[3],
+         "occ": occ32, "in_obj_alpha_raw": d["obj_alpha_raw"], "in_cls": d["cls"],
+         "in_ctx_ts": d["ctx_ts"].contiguous(), "in_pred_ts": d["pred_ts"]}
+    trace = {}
+    with torch.no_grad():
+        om, bg = wo.alpha_masks(cfg)
+        oa = om * d["obj_alpha_raw"] + (1 - om) * (-1.0)
+        o_probe = wo.decode_output(st32, d["input"], grid32, occ32, oa, bg.expand(B, -1, -1, -1), d["cls"], z["in_ctx_ts"], z["in_pred_ts"], trace=trace)
+    gen = torch.Generator().manual_seed(5)
+    for n, o in zip(OUT_NAMES, o_probe):
+        if o is not None:
+            z["proj_" + n] = torch.randn(o.shape, generator=gen)
+    del o_probe
+    o32, g32 = oracle_decode(cfg, z, torch.float32)
+    o32 = [o.detach() if o is not None else None for o in o32]
+    out, g = kernel_decode(dev, cfg, z)
+    out = [o.detach().cpu() if o is not None else None for o in out]
+    g = {k: v.cpu() for k, v in g.items()}
+    o64, g64 = oracle_decode(cfg, z, torch.float64)
+    o64 = [o.detach() if o is not None else None for o in o64]
+    for n, o, a, b in zip(OUT_NAMES, out, o32, o64):
+        if a is None:
+            assert o is None, f"{n} must be None (lvd.py:825-828)"
+            continue
+        assert tuple(o.shape) == tuple(a.shape), f"{n}: shape {tuple(o.shape)} vs oracle {tuple(a.shape)}"
+        arbitrated(o, a, b, FWD_TOL, f"{name}/{n} (vs oracle)")
+        rep[f"{n}_max_abs"] = [float((o - a).abs().max()), float((o.double() - b).abs().max()), float((a.double() - b).abs().max())]
+    for kname in LEAF_KEYS:
+        grad_close(g[kname], g32[kname], g64[kname], f"{name}/d {kname}")
+        sc = max(float(g64[kname].abs().max()), 1e-30)
+        # [kernel vs oracle fp32, kernel vs fp64 twin, oracle fp32 vs fp64 twin (= the reference arithmetic's own floor)]
+        rep[f"d_{kname}_rel"] = [float((g[kname].double() - g32[kname].double()).abs().max()) / sc,
+                                 float((g[kname].double() - g64[kname]).abs().max()) / sc,
+                                 float((g32[kname].double() - g64[kname]).abs().max()) / sc]
+    # ---------------- rule (1): index / threshold maps
+    ia, ic = OUT_NAMES.index("alpha"), OUT_NAMES.index("alpha_ctx")
+    rep["alpha_argmax_mismatch"] = _argmax_report(out[ia], o32[ia], f"{name}/alpha")
+    rep["alpha_ctx_argmax_mismatch"] = _argmax_report(out[ic], o32[ic], f"{name}/alpha_ctx")
+    if "is_obj" in trace:
+        # is_obj (lvd.py:788-791) is not an output; it gates alpha_ctx: where the reference's mask is off the composited
+        # opacity is EXACTLY 0 (alpha_ctx == -1), where it is on and the reference shows the layer, so does the kernel
+        off = ~trace["is_obj"].unsqueeze(1).expand_as(out[ic])
+        assert bool((out[ic][off] == -1).all()), f"{name}: a layer shows where the reference's is_obj mask is off"
+        shown = (~off) & (o32[ic] > -1 + 1e-4)
+        assert bool((out[ic][shown] > -1).all()), f"{name}: a layer is hidden where the reference's is_obj mask is on"
+    # ---------------- the reference's own code on the same inputs (staged copy oracle/_ref on the GPU box)
+    if with_reference:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_runner
+        if ref_runner.available():
+            rp = ref_runner.RefPath(cfg)
+            lv = {k: z[k2].clone().requires_grad_(True) for k, k2 in LEAF_KEYS.items()}
+            oa_r = rp.om * lv["oar"] + (1 - rp.om) * (-1.0)
+            r_out = rp.decode(lv["input"], (lv["tgo"], lv["sgo"], lv["tgb"], lv["sgb"]), lv["occ"], oa_r, rp.bg.expand(B, -1, -1, -1),
+                              lv["cls"], z["in_ctx_ts"], z["in_pred_ts"])
+            sum((o * z["proj_" + n]).sum() for n, o in zip(OUT_NAMES, r_out) if o is not None).backward()
+            for n, o, r, b in zip(OUT_NAMES, out, r_out, o64):
+                assert (o is None) == (r is None), n
+                if r is not None:
+                    arbitrated(o, r.detach(), b, FWD_TOL, f"{name}/{n} (vs the reference's own code)")
+                    rep[f"{n}_max_abs_vs_reference"] = float((o - r.detach()).abs().max())
+            for kname in LEAF_KEYS:
+                grad_close(g[kname], lv[kname].grad, g64[kname], f"{name}/d {kname} (vs the reference's autograd)")
+            rep["reference"] = "staged copy oracle/_ref" if ref_runner.ref_loader.is_staged_copy() else ref_runner.ref_loader.REF_ROOT
+        else:
+            rep["reference"] = "absent"
+    return rep

@@ -31,14 +31,26 @@ def test_decode_and_grads(case):
         if o is None:
             assert n not in z
             continue
-        tol = 1e-4 if n in ("output", "raw_output") else 5e-6   # warped +-5 one-hot logits amplify a flow ulp (App. D)
+        # warped +-5 one-hot logits amplify a flow ulp (3e-8) by |grad image| * Wd/2 = 10 * Wd/2 per tap
+        tol = 3e-6 * z[n].shape[-1] if n in ("output", "raw_output") else 5e-6
         assert float((o - z[n]).abs().max()) <= tol, n
         if "proj_" + n in z:
             loss = loss + (o * z["proj_" + n]).sum()
     loss.backward()
+    g64 = None
     for k, v in lv.items():
         g = z["grad_" + k]
-        assert float((v.grad - g).abs().max()) <= 1e-4 * float(g.abs().max()), k
+        if float((v.grad - g).abs().max()) <= 1e-4 * float(g.abs().max()):
+            continue
+        # above 1e-4: only legitimate where the reference's own fp32 arithmetic is that far from exact (the K = 131 / 211
+        # background TPS systems, cond ~1e4): arbitrate with the oracle's fp64 twin
+        if g64 is None:
+            l64 = {kk: z["in_" + kk].double().clone().requires_grad_(True) for kk in lv}
+            occ, oa, ba, grid = wo.estimate_alpha_grid_occ(wo.make_state(cfg, torch.float64), l64["obj_alpha_raw"], l64["obj_pose"], l64["bg_pose"], l64["occ_score"])
+            o64 = wo.decode_output(wo.make_state(cfg, torch.float64), l64["input"], grid, occ, oa, ba, l64["cls"], z["in_ctx_ts"], z["in_pred_ts"])
+            sum((o * z["proj_" + n].double()).sum() for n, o in zip(parity.OUT_NAMES, o64) if o is not None and "proj_" + n in z).backward()
+            g64 = {kk: vv.grad for kk, vv in l64.items()}
+        parity.grad_close(v.grad, g, g64[k], f"{case}/d {k} (oracle vs reference)")
     assert float((wo.wif_fuse(out[5].detach(), z["wif_unet_out"]) - z["wif_fused"]).abs().max()) <= 1e-4
 
 

@@ -173,6 +173,20 @@ def check(rc: int, what: str):
         raise RuntimeError(f"waldo_b200.{what} failed ({rc}): {load().waldo_last_error().decode()}")
 
 
+def device_of(dev):
+    """Device guard for a library call: kernels launch on the calling thread's CURRENT device, while the stream handed over
+    is the current stream of the TENSORS' device (reference precedent: the OptionalCUDAGuard of bias_act.cpp:54)."""
+    import contextlib
+    dev = torch.device(dev)
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+
+
+def call(fn, arg, ref: torch.Tensor, what: str):
+    """fn(&arg, current stream of ref's device) under a device guard; raises on a non-zero return code."""
+    with device_of(ref.device):
+        check(fn(C.byref(arg), stream_of(ref)), what)
+
+
 def stream_of(t: torch.Tensor):
     if t.is_cuda:
         return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)

@@ -17,7 +17,7 @@
 #include "wb_field.cuh"
 
 static thread_local char g_err[512] = "";
-long long g_wb_launches = 0;
+std::atomic<long long> g_wb_launches{0};
 
 static int wb_fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -49,7 +49,7 @@ extern "C" {
 
 const char* waldo_last_error(void) { return g_err; }
 int waldo_abi_version(void) { return WALDO_ABI_VERSION; }
-long long waldo_launch_count(void) { return g_wb_launches; }
+long long waldo_launch_count(void) { return g_wb_launches.load(); }
 int waldo_has_device_code(void) {
 #ifdef WB_HOST_EMU
   return 0;

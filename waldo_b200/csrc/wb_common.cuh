@@ -48,7 +48,8 @@ struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
-extern long long g_wb_launches;
+#include <atomic>
+extern std::atomic<long long> g_wb_launches;
 #define WB_LAUNCH(kern, grid, block, smem, stream, ...)                                     \
   do {                                                                                      \
     ++g_wb_launches;                                                                        \
@@ -67,7 +68,8 @@ static thread_local float wb_dyn_smem_buf[96 * 1024];
 #else
 // ------------------------------------------------------------------ device build
 #include <cuda_runtime.h>
-extern long long g_wb_launches;
+#include <atomic>
+extern std::atomic<long long> g_wb_launches;   // forward on the main thread, backward on autograd's worker thread
 #define WB_LAUNCH(kern, grid, block, smem, stream, ...) \
   do { ++g_wb_launches; kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); } while (0)
 #define WB_CHECK_LAUNCH() wb_check_launch(__FILE__, __LINE__)
@@ -211,7 +213,9 @@ WB_DEV void wb_red(float* p, float v) {
                                 // where the fused score `norm` is small: measured 1.9e6 on the KITTI fixture)
 WB_DEV void wb_red_fixed(const float* base, int64_t* shadow, float* sc, float* p, float v) {
   const float x = v * __ldg(sc);
-  if (!(fabsf(x) < 4.0e18f)) { sc[3] = 1.f; return; }   // beyond 2^62 units (or NaN): flag it, never wrap silently
+  // beyond 2^52 units (or NaN / inf): flag it, never wrap silently.  2^52 per addend leaves 2^11 such addends before the
+  // 64-bit sum itself could wrap; k_det_convert turns a raised flag into NaN gradients, so the caller's NaN guard sees it
+  if (!(fabsf(x) < 4.5e15f)) { sc[3] = 1.f; return; }
   unsigned long long* q = reinterpret_cast<unsigned long long*>(shadow + (p - base));
 #ifdef WB_HOST_EMU
   *q += (unsigned long long)llrintf(x);
@@ -251,11 +255,15 @@ __global__ void k_det_scale(float* sc) {
   }
   sc[0] = scale; sc[1] = inv;
 }
-// shadow -> fp32 (one rounding), grid-stride
+// shadow -> fp32 (one rounding), grid-stride.  If any addend so far was NaN / inf / out of the fixed-point range (sc[3]),
+// the sums are meaningless: the targets are written as NaN, exactly what the float-reduction path would have propagated,
+// so that the caller's NaN guard (reference: synthesizer.py:619) fires instead of wrong gradients being applied.
 __global__ void k_det_convert(const int64_t* __restrict__ sh, float* __restrict__ dst, long long n, const float* __restrict__ sc) {
   const double inv = (double)sc[1];
+  const bool bad = sc[3] != 0.f;
+  const float poison = nanf("");
   for (long long i = (long long)blockIdx.x * wb_nthr() + wb_tid(); i < n; i += (long long)gridDim.x * wb_nthr())
-    dst[i] = (float)((double)sh[i] * inv);
+    dst[i] = bad ? poison : (float)((double)sh[i] * inv);
 }
 
 #ifndef WB_HOST_EMU

@@ -38,7 +38,7 @@ class _TpsEval(torch.autograd.Function):
         mapping = torch.empty(n, N + 3, 2, device=pts.device, dtype=torch.float64)
         a = L.TpsFwd(n, N, P, L.ptr(inverse_kernel, name="inverse_kernel"), L.ptr(tgt_grid_repr, name="tgt_grid_repr"),
                      L.ptr(pts, name="src_pts"), L.ptr(mapping, torch.float64), L.ptr(grid))
-        L.check(lib.waldo_tps_fwd(C.byref(a), L.stream_of(pts)), "tps_fwd")
+        L.call(lib.waldo_tps_fwd, a, pts, "tps_fwd")
         ctx.save_for_backward(inverse_kernel, tgt_grid_repr)
         ctx.dims = (n, N, P)
         return grid
@@ -54,7 +54,7 @@ class _TpsEval(torch.autograd.Function):
         dpts = torch.empty(n, N, 2, device=dgrid.device, dtype=torch.float32)
         a = L.TpsBwd(n, N, P, L.ptr(inverse_kernel), L.ptr(tgt_grid_repr), L.ptr(dgrid), chunks,
                      L.ptr(partial, torch.float64), L.ptr(dpts))
-        L.check(lib.waldo_tps_bwd(C.byref(a), L.stream_of(dgrid)), "tps_bwd")
+        L.call(lib.waldo_tps_bwd, a, dgrid, "tps_bwd")
         return dpts, None, None, None, None
 
 
@@ -94,7 +94,7 @@ class _InverseWarp(torch.autograd.Function):
         a = L.InvWarpFwd(n, Hs, Ws, tgt_h, tgt_w, niter, 1 if erode else 0, L.ptr(fg, name="src_grid"), L.ptr(id_src_c),
                          L.ptr(id_tgt_c), L.ptr(gauss_c), L.ptr(out), L.ptr(field, torch.int32), L.ptr(winner, torch.int32),
                          L.ptr(level, torch.uint8), L.ptr(eroded, torch.uint8), L.ptr(val), L.ptr(bbox, torch.int32))
-        L.check(lib.waldo_invwarp_fwd(C.byref(a), L.stream_of(fg)), "invwarp_fwd")
+        L.call(lib.waldo_invwarp_fwd, a, fg, "invwarp_fwd")
         ctx.save_for_backward(gauss_c, field, winner, level, eroded, bbox)
         ctx.dims = (n, Hs, Ws, tgt_h, tgt_w, niter)
         if trace_box is not None:
@@ -117,7 +117,7 @@ class _InverseWarp(torch.autograd.Function):
         a = L.InvWarpBwd(n, Hs, Ws, Ht, Wt, niter, L.ptr(gauss), L.ptr(dout), L.ptr(field, torch.int32),
                          L.ptr(winner, torch.int32), L.ptr(level, torch.uint8), L.ptr(eroded, torch.uint8),
                          L.ptr(bbox, torch.int32), L.ptr(gval), L.ptr(inv_sw), L.ptr(gdisp), L.ptr(dfwd))
-        L.check(lib.waldo_invwarp_bwd(C.byref(a), L.stream_of(dout)), "invwarp_bwd")
+        L.call(lib.waldo_invwarp_bwd, a, dout, "invwarp_bwd")
         return dfwd, None, None, None, None, None, None, None, None
 
 
@@ -135,7 +135,8 @@ class _ComputeOcc(torch.autograd.Function):
         s = _c(occ_score.detach())
         B, T, No = s.shape
         occ = torch.empty(B, T, No + 1, No + 1, device=s.device, dtype=torch.float32)
-        L.check(lib.waldo_occ_fwd(B * T, No, L.ptr(s, name="occ_score"), L.ptr(occ), L.stream_of(s)), "occ_fwd")
+        with L.device_of(s.device):
+            L.check(lib.waldo_occ_fwd(B * T, No, L.ptr(s, name="occ_score"), L.ptr(occ), L.stream_of(s)), "occ_fwd")
         ctx.save_for_backward(s)
         return occ
 
@@ -146,7 +147,8 @@ class _ComputeOcc(torch.autograd.Function):
         B, T, No = s.shape
         docc = _c(docc)
         ds = torch.empty_like(s)
-        L.check(lib.waldo_occ_bwd(B * T, No, L.ptr(s), L.ptr(docc), L.ptr(ds), L.stream_of(s)), "occ_bwd")
+        with L.device_of(s.device):
+            L.check(lib.waldo_occ_bwd(B * T, No, L.ptr(s), L.ptr(docc), L.ptr(ds), L.stream_of(s)), "occ_bwd")
         return ds
 
 
@@ -251,7 +253,8 @@ PROFILE = None
 
 def _staged(fn, arg, stream, what, dev):
     if PROFILE is None:
-        L.check(fn(C.byref(arg), stream), what)
+        with L.device_of(dev):
+            L.check(fn(C.byref(arg), stream), what)
         return
     # forward: low-res prep (1), context alpha (8), layers (2), gather (4); backward: gather (1), layers (2), context alpha (8),
     # rest (4) -- kernels in the same dependency order as with stages = 0
@@ -261,7 +264,8 @@ def _staged(fn, arg, stream, what, dev):
         arg.stages = bit
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(dev))
-        L.check(fn(C.byref(arg), stream), what)
+        with L.device_of(dev):
+            L.check(fn(C.byref(arg), stream), what)
         e1.record(torch.cuda.current_stream(dev))
         PROFILE.setdefault(what + ":" + key, []).append((e0, e1))
     arg.stages = 0
@@ -318,6 +322,23 @@ class _Decode(torch.autograd.Function):
         g = _geom(spec, B, T, Tc, Tp, Nl, cls is not None)
         Lr = spec.num_obj + 1
         dev = inp_c.device
+        # the kernels index every buffer from the geometry: a tensor of another shape would be read / written out of bounds
+        No = spec.num_obj
+        want = dict(tgt_grid_obj=(tgo_c, (B, T, No, spec.Ho, spec.Wo, 2)), src_grid_obj=(sgo_c, (B, T, No, spec.H, spec.W, 2)),
+                    tgt_grid_bg=(tgb_c, (B, T, spec.H, spec.W, 2)), src_grid_bg=(sgb_c, (B, T, spec.H, spec.W, 2)),
+                    occ=(occ_c, (B, T, Lr, Lr)), ctx_ts=(ctx_ts, (B, Tc, Tp)), xs_hd=(xs_hd, (Wd,)), ys_hd=(ys_hd, (Hd,)))
+        if cls_c is not None:
+            want["cls"] = (cls_c, (B, No, Nl))
+        for name, (t, shape) in want.items():
+            if tuple(t.shape) != shape:
+                raise RuntimeError(f"waldo_b200.decode: {name} has shape {tuple(t.shape)}, expected {shape} "
+                                   f"(B={B}, T={T}, num_obj={No}, low-res {spec.H}x{spec.W}, canvas {spec.Ho}x{spec.Wo})")
+        if oa_c.numel() != B * No * spec.Ho * spec.Wo or ba_c.numel() != B * spec.H * spec.W:
+            raise RuntimeError(f"waldo_b200.decode: obj_alpha {tuple(oa_c.shape)} / bg_alpha {tuple(ba_c.shape)} do not match "
+                               f"(B={B}, num_obj={No}, canvas {spec.Ho}x{spec.Wo}, low-res {spec.H}x{spec.W})")
+        for name, t in (("grid", tgo_c), ("occ", occ_c), ("obj_alpha", oa_c), ("bg_alpha", ba_c), ("cls", cls_c)):
+            if t is not None and t.device != dev:
+                raise RuntimeError(f"waldo_b200.decode: {name} is on {t.device}, input on {dev}")
         ts_c = _c(ctx_ts, torch.int64).to(dev)
         ps_c = _c(pred_ts, torch.int64).to(dev)
         _check_time_indices(ctx_ts, pred_ts, ts_c, ps_c, g.Tw, T)
@@ -432,9 +453,11 @@ class _WifFuse(torch.autograd.Function):
         B, Tc, Tp, Cr, H, W = r.shape
         if u.shape[:3] != (B, Tp, Tc) or u.shape[3] != 4 + (1 if ab else 0):
             raise RuntimeError(f"waldo_b200.wif_fuse: unet_out shape {tuple(u.shape)} does not match raw_output {tuple(r.shape)}")
+        if Cr < 5:   # wif.py:53 reads INPUT channel 4 as the gate; the backward writes d raw_output channels 0..4
+            raise RuntimeError(f"waldo_b200.wif_fuse: raw_output needs at least 5 channels, got {Cr}")
         frame = torch.empty(B, Tp, 3, H, W, device=r.device, dtype=torch.float32)
         a = L.WifFuseFwd(B, Tc, Tp, Cr, H * W, 1 if ab else 0, L.ptr(r, name="raw_output"), L.ptr(u, name="unet_out"), L.ptr(frame))
-        L.check(lib.waldo_wif_fuse_fwd(C.byref(a), L.stream_of(r)), "wif_fuse_fwd")
+        L.call(lib.waldo_wif_fuse_fwd, a, r, "wif_fuse_fwd")
         ctx.keep = (a, r, u)
         return frame
 
@@ -446,7 +469,7 @@ class _WifFuse(torch.autograd.Function):
         d_raw = torch.zeros_like(r) if ctx.needs_input_grad[0] else None
         d_u = torch.empty_like(u) if ctx.needs_input_grad[1] else None
         b = L.WifFuseBwd(a, L.ptr(d_frame), L.ptr(d_raw), L.ptr(d_u))
-        L.check(lib.waldo_wif_fuse_bwd(C.byref(b), L.stream_of(r)), "wif_fuse_bwd")
+        L.call(lib.waldo_wif_fuse_bwd, b, r, "wif_fuse_bwd")
         return d_raw, d_u, None
 
 
@@ -475,7 +498,7 @@ def pack_input(rgb, label, num_lyt, on=5.0, off=-5.0, out=None):
     a = L.PackInput(B * T, num_lyt, Hd * Wd, float(on), float(off),
                     L.ptr(rgb_c, torch.uint8, "rgb") if u8 else None, None if u8 else L.ptr(rgb_c, name="rgb"),
                     L.ptr(lab_c, torch.uint8, "label"), L.ptr(out, name="out"))
-    L.check(lib.waldo_pack_input(C.byref(a), L.stream_of(out)), "pack_input")
+    L.call(lib.waldo_pack_input, a, out, "pack_input")
     return out
 
 
@@ -498,7 +521,7 @@ def warp_field(field, grid, delta=0.0):
     H, W = g.shape[1], g.shape[2]
     out = torch.empty(n, c, H, W, device=f.device, dtype=torch.float32)
     a = L.WarpField(n, c, h, w, H, W, float(delta), L.ptr(f, name="field"), L.ptr(g, name="grid"), L.ptr(out))
-    L.check(lib.waldo_warp_field_fwd(C.byref(a), L.stream_of(f)), "warp_field_fwd")
+    L.call(lib.waldo_warp_field_fwd, a, f, "warp_field_fwd")
     return out
 
 
@@ -514,5 +537,5 @@ def resize_bilinear(x, scale_factor):
     n = xc.numel() // (h * w)
     out = torch.empty(*xc.shape[:-2], H, W, device=xc.device, dtype=torch.float32)
     a = L.Resize(n, h, w, H, W, L.ptr(xc, name="x"), L.ptr(out))
-    L.check(lib.waldo_resize_bilinear_fwd(C.byref(a), L.stream_of(xc)), "resize_bilinear_fwd")
+    L.call(lib.waldo_resize_bilinear_fwd, a, xc, "resize_bilinear_fwd")
     return out

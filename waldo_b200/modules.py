@@ -209,8 +209,12 @@ class Warper(nn.Module):
                              allow_ghost=bool(self.allow_ghost), include_self=bool(self.include_self),
                              use_disocc=bool(self.use_disocc), min_cls=float(self.min_cls))
 
-    def _decode(self, restrict, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts):
+    def _decode(self, restrict, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts, want_disocc):
+        """One fused decode.  Returns (output, raw_alpha, raw, flow, alpha, alpha_unflt, alpha_ctx, disocc); `raw` holds
+        C + L (+1 with want_disocc) channels, alpha_ctx / disocc are channel-slice views of it."""
+        self._fused = None   # never keep the HD tensors of an earlier call alive
         spec = self._spec(restrict)
+        spec.use_disocc = bool(want_disocc)
         xs = self.src_grid_hd[0, 0, :, 0].contiguous()
         ys = self.src_grid_hd[0, :, 0, 1].contiguous()
         output, raw_alpha, raw, flow, alpha = Fn.decode(spec, ctx_ts, pred_ts, xs, ys, input, grid, occ, obj_alpha, bg_alpha, cls)
@@ -218,56 +222,41 @@ class Warper(nn.Module):
         Lr = self.num_obj + 1
         Tc = ctx_ts.size(1)
         alpha_ctx = raw[:, :Tc, :, C:C + Lr]                       # a channel-slice view of raw_output
-        disocc = raw[:, :Tc, :, C + Lr:C + Lr + 1] if spec.use_disocc else None
-        self._fused = (alpha_ctx, flow, output, raw_alpha, raw, spec.use_disocc)
+        disocc = raw[:, :Tc, :, C + Lr:C + Lr + 1] if want_disocc else None
         alpha_unflt = alpha if self.fast else None                  # lvd.py:702-705 / :825-828
+        return output, raw_alpha, raw, flow, alpha, alpha_unflt, alpha_ctx, disocc
+
+    def _method_decode(self, restrict, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts):
+        # Through the reference's METHOD interface the disocclusion map is always produced, as the reference does
+        # (lvd.py:680 / :803): its caller decides whether to append it (lvd.py:148-151).
+        output, raw_alpha, raw, flow, alpha, alpha_unflt, alpha_ctx, disocc = self._decode(
+            restrict, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts, want_disocc=True)
+        self._fused = (alpha_ctx, flow, output, raw_alpha, raw[:, :, :, :input.size(2) + self.num_obj + 1])
         return flow, alpha_unflt, alpha, alpha_ctx, disocc
 
     def grid_to_flow_ctx(self, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts):
-        """lvd.py:707-828.  Returns (flow, alpha_unflt, alpha, alpha_ctx, disocc).  `disocc` is returned only when
-        opt.use_disocc (the only case in which the reference's caller reads it, lvd.py:148-151); else None."""
-        return self._decode(True, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
+        """lvd.py:707-828.  Returns (flow, alpha_unflt, alpha, alpha_ctx, disocc), `disocc` (B,Tc,Tp,1,Hd,Wd) always, as
+        the reference."""
+        return self._method_decode(True, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
 
     def grid_to_flow(self, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts):
         """lvd.py:602-705."""
-        return self._decode(False, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
+        return self._method_decode(False, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
 
     def input_to_output(self, input, alpha, flow, ctx_ts, eps=1e-6):
-        """lvd.py:830-853 -> (output (B,Tp,C+1,Hd,Wd), raw_output).  The warp + context fusion was already done by the
-        fused kernel of grid_to_flow[_ctx]; this hands its results out.  The raw_output returned here already holds the
-        disocc channel when opt.use_disocc (decode_output below accounts for that)."""
+        """lvd.py:830-853 -> (output (B,Tp,C+1,Hd,Wd), raw_output (B,Tc[+1],Tp,C+L,Hd,Wd)), both plain tensors exactly as
+        the reference returns them (raw_output WITHOUT the disocc channel: the unmodified LVD.forward appends it itself,
+        lvd.py:148-151).  The warp + context fusion was already done by the fused kernel of grid_to_flow[_ctx]; this hands
+        its results out, which is why it must be called with the tensors that call returned, as LVD.forward does
+        (lvd.py:143-146).  waldo_b200.decode_output() is the copy-free form of the same pair of calls."""
         f = self._fused
+        self._fused = None
         if f is None or f[0] is not alpha or f[1] is not flow:
             raise NotImplementedError(
                 "waldo_b200.Warper.input_to_output must be called with the (alpha_ctx, flow) tensors returned by the "
                 "immediately preceding grid_to_flow[_ctx] call, as LVD.forward does (lvd.py:143-146): the warp of the "
                 "context frames is fused into that kernel.")
-        self._fused = None
-        return _FusedOutput(f[2], f[3]), f[4]
-
-
-class _FusedOutput:
-    """The reference's `output` of input_to_output: a (B,Tp,C+1,Hd,Wd) tensor that LVD.forward only ever slices into
-    `output[:, :, :-1]` and `output[:, :, -1:]` (lvd.py:147,152).  The fused kernel keeps those two as separate autograd
-    outputs (so that their gradients arrive as two dense tensors instead of one zero-padded copy); this wrapper answers
-    exactly those two slices without a copy and materialises the concatenation for anything else."""
-
-    def __init__(self, image, raw_alpha):
-        self.image, self.raw_alpha = image, raw_alpha
-
-    def full(self):
-        return torch.cat([self.image, self.raw_alpha], dim=2)
-
-    def __getitem__(self, idx):
-        if isinstance(idx, tuple) and len(idx) == 3 and idx[0] == slice(None) and idx[1] == slice(None):
-            if idx[2] == slice(None, -1, None):
-                return self.image
-            if idx[2] == slice(-1, None, None):
-                return self.raw_alpha
-        return self.full()[idx]
-
-    def __getattr__(self, name):          # shape, size(), dtype, device, ... of the concatenated tensor
-        return getattr(self.full(), name)
+        return torch.cat([f[2], f[3]], dim=2), f[4]
 
 
 # ----------------------------------------------------------------------------- a-4, a-8
@@ -281,17 +270,17 @@ def compute_occ(occ_score, eps=1e-6):
 def decode_output(warper: Warper, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts,
                   restrict_to_ctx: bool, use_disocc: Optional[bool] = None, include_self: Optional[bool] = None):
     """LVD.forward(mode="decode_output"), lvd.py:141-153 -> the reference's 7-tuple
-    (output, flow, alpha_unflt, alpha, raw_alpha, raw_output, alpha_ctx)."""
+    (output, flow, alpha_unflt, alpha, raw_alpha, raw_output, alpha_ctx), copy-free: `output` / `raw_alpha` are the two
+    channel slices of one buffer, `raw_output` already carries the disocc channel when opt.use_disocc, `alpha_ctx` is a
+    view of it.  `use_disocc` / `include_self` override the warper's option fields (LVD.use_disocc / LVD.include_self in
+    the reference, lvd.py:21-22) for this and later calls."""
     if use_disocc is not None:
-        warper.use_disocc = use_disocc
-    if restrict_to_ctx:
-        flow, alpha_unflt, alpha, alpha_ctx, _ = warper.grid_to_flow_ctx(input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
-    else:
-        flow, alpha_unflt, alpha, alpha_ctx, _ = warper.grid_to_flow(input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts)
-    output, raw_output = warper.input_to_output(input, alpha_ctx, flow, ctx_ts)
-    raw_alpha = output[:, :, -1:]
-    output = output[:, :, :-1]
-    return output, flow, alpha_unflt, alpha, raw_alpha, raw_output, alpha_ctx
+        warper.use_disocc = bool(use_disocc)
+    if include_self is not None:
+        warper.include_self = bool(include_self)
+    output, raw_alpha, raw, flow, alpha, alpha_unflt, alpha_ctx, _ = warper._decode(
+        restrict_to_ctx, input, grid, occ, obj_alpha, bg_alpha, cls, ctx_ts, pred_ts, want_disocc=warper.use_disocc)
+    return output, flow, alpha_unflt, alpha, raw_alpha, raw, alpha_ctx
 
 
 def alpha_masks(opt):

@@ -71,8 +71,13 @@ class FlatGradReducer:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(ws)
         for p, o in zip(self.params, self.offsets):
+            seg = self.flat[o:o + p.numel()]
             if p.grad is not None:
-                p.grad.copy_(self.flat[o:o + p.numel()].view_as(p.grad))
+                p.grad.copy_(seg.view_as(p.grad))
+            elif ws > 1:
+                # unused on THIS rank but maybe not on another: every rank must apply the same averaged gradient (what DDP
+                # does), or the replicas diverge
+                p.grad = seg.to(p.dtype).view_as(p).clone()
         return self.flat
 
 
