@@ -7,7 +7,7 @@ mkdir -p $OUT
 for what in "$@"; do
 case $what in
 tests)
-  timeout 400 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/${TAG}_tests.log;;
+  timeout ${TESTS_TIMEOUT:-1500} python -m pytest tests -m gpu -x -q --durations=8 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/${TAG}_tests.log;;
 bench)
   timeout 600 python bench.py > $OUT/${TAG}_bench.jsonl 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; cat $OUT/${TAG}_bench.jsonl; tail -3 $OUT/${TAG}_bench.err;;
 benchq)
@@ -21,6 +21,8 @@ workloads)
   for w in city_rollout kitti_rollout; do
     timeout 600 python bench.py --workload $w --no-cpu-baseline > $OUT/${TAG}_bench_$w.jsonl 2> $OUT/${TAG}_bench_$w.err; echo "bench $w rc=$?"; cat $OUT/${TAG}_bench_$w.jsonl; tail -2 $OUT/${TAG}_bench_$w.err
   done;;
+refgpu)
+  timeout 600 python bench.py --impl reference-gpu --steps 3 > $OUT/${TAG}_bench_refgpu.jsonl 2> $OUT/${TAG}_bench_refgpu.err; echo "refgpu rc=$?"; cat $OUT/${TAG}_bench_refgpu.jsonl; tail -2 $OUT/${TAG}_bench_refgpu.err;;
 ref)
   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.jsonl 2> $OUT/${TAG}_bench_ref.err; echo "ref rc=$?"; cat $OUT/${TAG}_bench_ref.jsonl; tail -2 $OUT/${TAG}_bench_ref.err;;
 exp)
