@@ -15,15 +15,6 @@
  * Symbols (SURVEY.md symbol table): B batch, T frames, Tw frames that get a context alpha
  * (Tc with restrict_to_ctx, else T), Tc contexts, Tp predicted frames, No objects, L = No+1 layers
  * (layer 0 = background), C = 3+Nl input channels, H x W low-res, Hd x Wd full-res, Ho x Wo object canvas.
- *
- * Data layout.  The HD tensors that carry the image channels are CHANNELS-LAST RECORDS: one record of Cp (resp. CRp)
- * consecutive floats per pixel, Cp / CRp multiples of 4 so that every record is a whole number of 16-byte chunks
- * (128-bit loads / stores / reductions), padding floats zero:
- *     input, d_input, out_full, d_output : (frames, Hd*Wd, Cp),   Cp  = ceil4(C + 1)
- *     raw_output, d_raw_output           : (pairs,  Hd*Wd, CRp),  CRp = ceil4(C + L + disocc)
- * Logically they are the reference's (.., C, Hd, Wd) tensors; the Python shim hands out channel-stride-1 views of the same
- * memory (the reference's callers only use shape-level semantics).  Per-layer and per-pair scalar fields
- * (alpha, flow, score, glue, all low-res state) stay planar.  waldo_to_records / waldo_from_records convert.
  */
 #ifndef WALDO_B200_H
 #define WALDO_B200_H
@@ -34,7 +25,7 @@
 extern "C" {
 #endif
 
-#define WALDO_ABI_VERSION 2
+#define WALDO_ABI_VERSION 1
 
 /* compile-time capacity of the kernels (per-thread register arrays) */
 #define WALDO_MAX_LAYERS 17   /* L  = num_obj + 1 */
@@ -151,14 +142,12 @@ typedef struct {
   int H, W, Hd, Wd, Ho, Wo;
   int flags;
   float min_cls;              /* lvd.py:492 */
-  int Cp;                     /* floats per record of input / d_input / out_full / d_output: ceil4(C + 1) */
-  int CRp;                    /* floats per record of raw_output / d_raw_output: ceil4(C + L + disocc) */
 } waldo_geom_t;
 
 typedef struct {
   waldo_geom_t g;
   /* inputs */
-  const float* input;         /* records (B, T, Hd*Wd, Cp): channel c of pixel q at [q*Cp + c]           logical (B, T, C, Hd, Wd) */
+  const float* input;         /* (B, T, C, Hd, Wd) */
   const float* tgt_grid_obj;  /* (B, T, No, Ho, Wo, 2) */
   const float* src_grid_obj;  /* (B, T, No, H, W, 2) */
   const float* tgt_grid_bg;   /* (B, T, H, W, 2) */
@@ -185,12 +174,8 @@ typedef struct {
   /* outputs */
   float* alpha;               /* (B, Tw, L, Hd, Wd) in [-1,1]                         lvd.py:822 */
   float* flow;                /* (B, Tc, Tp, 2, Hd, Wd)                               lvd.py:818 */
-  float* raw_output;          /* records (B, Tc+self, Tp, Hd*Wd, CRp), logical (B, Tc+self, Tp, C+L+disocc, Hd, Wd)   lvd.py:846,151;
-                                 alpha_ctx = channels C..C+L-1 */
-  float* out_full;            /* records (B, Tp, Hd*Wd, Cp), logical (B, Tp, C+1, Hd, Wd): output | raw_alpha   lvd.py:851,147,152 */
-  float* apass;               /* scratch (B, Tc, Tp, ceil4(C)-C, Hd*Wd): the first alpha channels (2A-1 of layers 0..) on their way
-                                 from the layer kernel to the gather kernel, which writes them with the last image channels
-                                 as one 16-byte chunk of the record; unused (may be NULL) when C is a multiple of 4 */
+  float* raw_output;          /* (B, Tc+self, Tp, C+L+disocc, Hd, Wd)                 lvd.py:846,151; alpha_ctx = channels C..C+L-1 */
+  float* out_full;            /* (B, Tp, C+1, Hd, Wd): output | raw_alpha             lvd.py:851,147,152 */
   float* norm;                /* (B, Tp, Hd, Wd) sum_tc(score+eps), saved for backward */
   float* score;               /* (B, Tc, Tp, Hd, Wd) sum_k Actx_k per pair (lvd.py:841), glue between the two HD kernels */
   int stages;                 /* 0 = everything; else bit 0 = low-res kernels (B1, B2, B5), bit 3 = HD context-alpha kernel (B2b-B4),
@@ -201,13 +186,13 @@ int waldo_decode_fwd(const waldo_decode_fwd_t*, waldo_stream_t);
 typedef struct {
   waldo_decode_fwd_t f;       /* the forward call's arguments (inputs, saved intermediates, outputs) */
   /* upstream gradients; any may be NULL (= zero) */
-  const float* d_output;      /* records (B, Tp, Hd*Wd, Cp), channels 0..C-1 read: gradient of out_full[:, :, :C] (the returned `output`) */
+  const float* d_output;      /* (B, Tp, C, Hd, Wd)   gradient of out_full[:, :, :C]  (the returned `output`)    */
   const float* d_raw_alpha;   /* (B, Tp, 1, Hd, Wd)   gradient of out_full[:, :, C:]  (the returned `raw_alpha`) */
-  const float* d_raw_output;  /* records (B, Tc+self, Tp, Hd*Wd, CRp) */
+  const float* d_raw_output;  /* (B, Tc+self, Tp, C+L+disocc, Hd, Wd) */
   const float* d_flow;        /* (B, Tc, Tp, 2, Hd, Wd) */
   const float* d_alpha;       /* (B, Tw, L, Hd, Wd) */
   /* gradient outputs; NULL = not needed.  Buffers must be ZERO-FILLED by the caller. */
-  float* d_input;             /* records (B, T, Hd*Wd, Cp) */
+  float* d_input;             /* (B, T, C, Hd, Wd) */
   float* d_tgt_grid_obj;      /* (B, T, No, Ho, Wo, 2) */
   float* d_src_grid_obj;      /* (B, T, No, H, W, 2) */
   float* d_tgt_grid_bg;       /* (B, T, H, W, 2) */
@@ -253,8 +238,7 @@ typedef struct {
   int B, Tc, Tp, Cr;          /* Cr = channels of raw_output */
   int HW;                     /* Hd*Wd */
   int ab;                     /* opt.ii_ab */
-  int CRp;                    /* floats per raw_output record, >= Cr */
-  const float* raw_output;    /* records (B, Tc, Tp, HW, CRp) */
+  const float* raw_output;    /* (B, Tc, Tp, Cr, HW) */
   const float* unet_out;      /* (B, Tp, Tc, 4+ab, HW) */
   float* frame;               /* out (B, Tp, 3, HW) */
 } waldo_wif_fuse_fwd_t;
@@ -263,7 +247,7 @@ int waldo_wif_fuse_fwd(const waldo_wif_fuse_fwd_t*, waldo_stream_t);
 typedef struct {
   waldo_wif_fuse_fwd_t f;
   const float* d_frame;       /* (B, Tp, 3, HW) */
-  float* d_raw_output;        /* records (B, Tc, Tp, HW, CRp) or NULL; channels 0..4 written, the rest must be pre-zeroed */
+  float* d_raw_output;        /* (B, Tc, Tp, Cr, HW) or NULL; channels 0..4 written, the rest must be pre-zeroed */
   float* d_unet_out;          /* (B, Tp, Tc, 4+ab, HW) or NULL */
 } waldo_wif_fuse_bwd_t;
 int waldo_wif_fuse_bwd(const waldo_wif_fuse_bwd_t*, waldo_stream_t);
@@ -304,16 +288,9 @@ typedef struct {
   const uint8_t* rgb_u8;      /* (n, 3, HW) raw 8-bit RGB, or NULL */
   const float* rgb_f32;       /* (n, 3, HW) already normalised frames (used when rgb_u8 is NULL) */
   const uint8_t* label;       /* (n, HW) class ids; ids >= Nl light no channel */
-  float* input;               /* out records (n, HW, Cp) */
-  int Cp;                     /* floats per record, a multiple of 4, >= 3+Nl */
+  float* input;               /* out (n, 3+Nl, HW) */
 } waldo_pack_input_t;
 int waldo_pack_input(const waldo_pack_input_t*, waldo_stream_t);
-
-/* ------------------------------------------------------------------ layout conversion (boundary helpers)
- * planar (n, C, HW) <-> channels-last records (n, HW, Cp); padding floats of the records are written as zero.
- * For callers that hold (or want) NCHW-contiguous tensors; the path itself only touches records. */
-int waldo_to_records(int n, int C, int Cp, long long HW, const float* planar, float* records, waldo_stream_t);
-int waldo_from_records(int n, int C, int Cp, long long HW, const float* records, float* planar, waldo_stream_t);
 
 #ifdef __cplusplus
 }

@@ -53,7 +53,7 @@ class Geom(C.Structure):
     _fields_ = [("B", C.c_int), ("T", C.c_int), ("Tw", C.c_int), ("Tc", C.c_int), ("Tp", C.c_int),
                 ("No", C.c_int), ("Nl", C.c_int), ("C", C.c_int),
                 ("H", C.c_int), ("W", C.c_int), ("Hd", C.c_int), ("Wd", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int),
-                ("flags", C.c_int), ("min_cls", C.c_float), ("Cp", C.c_int), ("CRp", C.c_int)]
+                ("flags", C.c_int), ("min_cls", C.c_float)]
 
 
 class DecodeFwd(C.Structure):
@@ -64,7 +64,7 @@ class DecodeFwd(C.Structure):
                 ("ctx_ts", c_void_p), ("pred_ts", c_void_p), ("xs_hd", c_void_p), ("ys_hd", c_void_p),
                 ("a_lo", c_void_p), ("prof_part", c_void_p), ("prof_ctas", C.c_int), ("prof_sum", c_void_p),
                 ("prof_p", c_void_p), ("lyt_lo", c_void_p), ("f_lo", c_void_p), ("s_lo", c_void_p), ("live_ctx", c_void_p), ("live_pred", c_void_p),
-                ("alpha", c_void_p), ("flow", c_void_p), ("raw_output", c_void_p), ("out_full", c_void_p), ("apass", c_void_p),
+                ("alpha", c_void_p), ("flow", c_void_p), ("raw_output", c_void_p), ("out_full", c_void_p),
                 ("norm", c_void_p), ("score", c_void_p), ("stages", C.c_int)]
 
 
@@ -82,7 +82,7 @@ class DecodeBwd(C.Structure):
 
 
 class WifFuseFwd(C.Structure):
-    _fields_ = [("B", C.c_int), ("Tc", C.c_int), ("Tp", C.c_int), ("Cr", C.c_int), ("HW", C.c_int), ("ab", C.c_int), ("CRp", C.c_int),
+    _fields_ = [("B", C.c_int), ("Tc", C.c_int), ("Tp", C.c_int), ("Cr", C.c_int), ("HW", C.c_int), ("ab", C.c_int),
                 ("raw_output", c_void_p), ("unet_out", c_void_p), ("frame", c_void_p)]
 
 
@@ -101,14 +101,13 @@ class Resize(C.Structure):
 
 class PackInput(C.Structure):
     _fields_ = [("n", C.c_int), ("Nl", C.c_int), ("HW", C.c_int), ("on", C.c_float), ("off", C.c_float),
-                ("rgb_u8", c_void_p), ("rgb_f32", c_void_p), ("label", c_void_p), ("input", c_void_p), ("Cp", C.c_int)]
+                ("rgb_u8", c_void_p), ("rgb_f32", c_void_p), ("label", c_void_p), ("input", c_void_p)]
 
 
 # flags of Geom.flags (include/waldo_b200.h)
 F_RESTRICT_CTX, F_FILTER, F_WEIGHT_CLS, F_HAS_CLS, F_IS_OBJ, F_INCLUDE_SELF, F_USE_DISOCC, F_OCC_PAIRS = (1 << i for i in range(8))
 
 MAX_LAYERS, MAX_CH, MAX_LYT, MAX_TPS_K = 17, 24, 21, 256
-ABI_VERSION = 2
 
 STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwarp_fwd_t": InvWarpFwd,
              "waldo_invwarp_bwd_t": InvWarpBwd, "waldo_geom_t": Geom, "waldo_decode_fwd_t": DecodeFwd,
@@ -117,8 +116,7 @@ STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwar
 
 EXPORTS = ["waldo_last_error", "waldo_abi_version", "waldo_has_device_code", "waldo_launch_count", "waldo_tps_fwd", "waldo_tps_bwd",
            "waldo_invwarp_fwd", "waldo_invwarp_bwd", "waldo_occ_fwd", "waldo_occ_bwd", "waldo_decode_fwd",
-           "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input", "waldo_warp_field_fwd", "waldo_resize_bilinear_fwd",
-           "waldo_to_records", "waldo_from_records"]
+           "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input", "waldo_warp_field_fwd", "waldo_resize_bilinear_fwd"]
 
 _lock = threading.Lock()
 _lib = None
@@ -141,10 +139,6 @@ def _declare(lib):
     lib.waldo_occ_fwd.restype = C.c_int
     lib.waldo_occ_bwd.argtypes = [C.c_int, C.c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.waldo_occ_bwd.restype = C.c_int
-    for name in ("waldo_to_records", "waldo_from_records"):
-        fn = getattr(lib, name)
-        fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_longlong, c_void_p, c_void_p, c_void_p]
-        fn.restype = C.c_int
     return lib
 
 
@@ -166,7 +160,7 @@ def load(build_if_missing: bool = True):
             raise RuntimeError(f"waldo_b200: {LIB_PATH} not found; run `python -m waldo_b200.build` (needs nvcc). "
                                "There is no CPU fallback.")
         lib = _declare(C.CDLL(LIB_PATH))
-        if lib.waldo_abi_version() != ABI_VERSION:
+        if lib.waldo_abi_version() != 1:
             raise RuntimeError("waldo_b200: ABI version mismatch between _lib.py and libwaldo_b200.so")
         if lib.waldo_has_device_code() != 1:
             raise RuntimeError("waldo_b200: library was built without device code; refusing to use it")

@@ -164,11 +164,6 @@ static int wb_check_geom(const waldo_geom_t& g, const char* who) {
   WB_REQUIRE(g.H > 1 && g.W > 1 && g.Hd >= g.H && g.Wd >= g.W && g.Ho > 1 && g.Wo > 1, "%s: bad spatial sizes", who);
   WB_REQUIRE((long long)g.Hd * g.W == (long long)g.H * g.Wd, "%s: HD and low-res aspect differ", who);
   WB_REQUIRE((long long)g.Hd * g.Wd < (1ll << 30), "%s: frame too large for 32-bit pixel indices", who);
-  {
-    const int cr = g.C + g.No + 1 + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
-    WB_REQUIRE(g.Cp == ((g.C + 1 + 3) & ~3), "%s: Cp=%d must be ceil4(C+1)=%d (floats per input / out_full record)", who, g.Cp, (g.C + 1 + 3) & ~3);
-    WB_REQUIRE(g.CRp == ((cr + 3) & ~3), "%s: CRp=%d must be ceil4(C+L+disocc)=%d (floats per raw_output record)", who, g.CRp, (cr + 3) & ~3);
-  }
   if (g.flags & WALDO_F_RESTRICT_CTX) WB_REQUIRE(g.flags & WALDO_F_FILTER, "%s: restrict_to_ctx implies the filter", who);
   if (g.flags & WALDO_F_WEIGHT_CLS) WB_REQUIRE(g.flags & WALDO_F_HAS_CLS, "%s: weight_cls needs cls", who);
   return 0;
@@ -183,9 +178,6 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
              a->bg_alpha && a->ctx_ts && a->pred_ts && a->xs_hd && a->ys_hd, "decode_fwd: null input pointer");
   WB_REQUIRE(a->a_lo && a->f_lo && a->alpha && a->flow && a->raw_output && a->out_full && a->live_ctx && a->live_pred && a->norm && a->score,
              "decode_fwd: null output pointer");
-  WB_REQUIRE((g.C & 3) == 0 || a->apass, "decode_fwd: apass scratch needed when C is not a multiple of 4");
-  WB_REQUIRE(((uintptr_t)a->input & 15) == 0 && ((uintptr_t)a->raw_output & 15) == 0 && ((uintptr_t)a->out_full & 15) == 0,
-             "decode_fwd: record buffers must be 16-byte aligned");
   const bool filt = (g.flags & WALDO_F_FILTER) != 0;
   const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
   if (g.flags & WALDO_F_HAS_CLS) WB_REQUIRE(a->cls, "decode_fwd: cls flagged but null");
@@ -235,7 +227,10 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
   }
   // stage C: the gather kernel
   if (st_gather) {
-    WB_LAUNCH(k_gather_fwd, grid, dim3(WB_TILE_PX), 0, st, *a);
+    const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+    if (g.Tc == 4 && !self) WB_LAUNCH((k_gather_fwd<4, true>), grid, dim3(WB_TILE_PX), 0, st, *a);
+    else if (g.Tc <= 4) WB_LAUNCH((k_gather_fwd<4, false>), grid, dim3(WB_TILE_PX), 0, st, *a);
+    else WB_LAUNCH((k_gather_fwd<8, false>), grid, dim3(WB_TILE_PX), 0, st, *a);
     WB_LAUNCHED();
   }
   return 0;
@@ -251,7 +246,6 @@ int waldo_wif_fuse_fwd(const waldo_wif_fuse_fwd_t* a, waldo_stream_t st) {
   WB_REQUIRE(a && a->B > 0 && a->Tc > 0 && a->Tp > 0 && a->HW > 0, "wif_fuse_fwd: bad sizes");
   WB_REQUIRE(a->Cr >= 5 || !a->ab, "wif_fuse_fwd: raw_output needs >= 5 channels for the gate");
   WB_REQUIRE(a->Cr >= 3 && a->raw_output && a->unet_out && a->frame, "wif_fuse_fwd: null pointer");
-  WB_REQUIRE(a->CRp >= a->Cr, "wif_fuse_fwd: CRp (floats per raw_output record) must be >= Cr");
   WB_LAUNCH(k_wif_fuse_fwd, dim3(wb_blocks(a->HW, 256), a->B * a->Tp), dim3(256), 0, st, *a);
   WB_LAUNCHED();
   return 0;
@@ -260,7 +254,6 @@ int waldo_wif_fuse_bwd(const waldo_wif_fuse_bwd_t* a, waldo_stream_t st) {
   WB_REQUIRE(a && a->f.B > 0 && a->f.Tc > 0 && a->f.Tp > 0 && a->f.HW > 0, "wif_fuse_bwd: bad sizes");
   WB_REQUIRE(a->f.Tc <= WB_WIF_MAX_TC, "wif_fuse_bwd: Tc=%d exceeds compiled maximum %d", a->f.Tc, WB_WIF_MAX_TC);
   WB_REQUIRE(a->f.raw_output && a->f.unet_out && a->d_frame, "wif_fuse_bwd: null pointer");
-  WB_REQUIRE(a->f.CRp >= a->f.Cr && a->f.Cr >= 5, "wif_fuse_bwd: needs Cr >= 5 and CRp >= Cr");
   WB_LAUNCH(k_wif_fuse_bwd, dim3(wb_blocks(a->f.HW, 256), a->f.B * a->f.Tp), dim3(256), 0, st, *a);
   WB_LAUNCHED();
   return 0;
@@ -288,26 +281,8 @@ int waldo_resize_bilinear_fwd(const waldo_resize_t* a, waldo_stream_t st) {
 int waldo_pack_input(const waldo_pack_input_t* a, waldo_stream_t st) {
   WB_REQUIRE(a && a->n >= 0 && a->Nl >= 1 && a->HW > 0, "pack_input: bad sizes");
   WB_REQUIRE((a->rgb_u8 || a->rgb_f32) && a->label && a->input, "pack_input: null pointer");
-  WB_REQUIRE(a->Cp >= 3 + a->Nl && (a->Cp & 3) == 0 && ((uintptr_t)a->input & 15) == 0, "pack_input: Cp must be a multiple of 4, >= 3+Nl; input 16-byte aligned");
   if (a->n == 0) return 0;
-  WB_LAUNCH(k_pack_input, dim3(wb_blocks(a->HW, 256, 1024), a->n), dim3(256), 0, st, *a);
-  WB_LAUNCHED();
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------ layout conversion
-int waldo_to_records(int n, int C, int Cp, long long HW, const float* planar, float* records, waldo_stream_t st) {
-  WB_REQUIRE(n >= 0 && C > 0 && Cp >= C && (Cp & 3) == 0 && HW > 0 && planar && records, "to_records: bad arguments");
-  WB_REQUIRE(((uintptr_t)records & 15) == 0, "to_records: records must be 16-byte aligned");
-  if (n == 0) return 0;
-  WB_LAUNCH(k_to_records, dim3(wb_blocks(HW, 256, 1024), n), dim3(256), 0, st, n, C, Cp, HW, planar, records);
-  WB_LAUNCHED();
-  return 0;
-}
-int waldo_from_records(int n, int C, int Cp, long long HW, const float* records, float* planar, waldo_stream_t st) {
-  WB_REQUIRE(n >= 0 && C > 0 && Cp >= C && HW > 0 && records && planar, "from_records: bad arguments");
-  if (n == 0) return 0;
-  WB_LAUNCH(k_from_records, dim3(wb_blocks(HW, 256, 1024), n), dim3(256), 0, st, n, C, Cp, HW, records, planar);
+  WB_LAUNCH(k_pack_input, dim3(wb_blocks(((long long)a->HW + 3) / 4, 256, 1024), a->n), dim3(256), 0, st, *a);
   WB_LAUNCHED();
   return 0;
 }

@@ -286,49 +286,6 @@ WB_DEV void wb_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0
 WB_DEV int wb_nth_bit(unsigned m, int nth) { return (int)__fns(m, 0, nth + 1); }
 #endif
 
-// ------------------------------------------------------------------ channels-last records, 128-bit access
-// `input`, `d input`, `out_full`, `d output` and `raw_output` / `d raw_output` live in HBM as one record per pixel
-// (channels last, record length a multiple of 4 floats: include/waldo_b200.h, Cp / CRp).  The gather kernels spread the
-// 16-byte chunks of a record over the lanes of a PIXEL GROUP: WB_GRP lanes per pixel, lane <-> chunk, so that a warp-wide
-// 128-bit access covers whole consecutive records (coalesced, one wavefront per 128-byte line) and the scatter of
-// `d input` is one red.global.add.v4.f32 per lane and tap.  In the host emulation a "warp" is one lane: that lane walks the
-// WB_GCH chunks of its pixel in a loop and the group reductions are the identity.
-#ifdef WB_HOST_EMU
-#define WB_GRP 1
-#define WB_GCH 8
-#else
-#define WB_GRP 8
-#define WB_GCH 1
-#endif
-#define WB_CHUNKS for (int ci = 0; ci < WB_GCH; ++ci)
-
-WB_DEV float4 wb_ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-WB_DEV float4 wb_ld4_rw(const float* p) { return *reinterpret_cast<const float4*>(p); }   // data written earlier in the same kernel
-WB_DEV void wb_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-WB_DEV float wb_get(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
-WB_DEV void wb_set(float4& v, int e, float x) { if (e == 0) v.x = x; else if (e == 1) v.y = x; else if (e == 2) v.z = x; else v.w = x; }
-// keep the components whose channel index (c0 + e) is below `lim`, zero the rest
-WB_DEV float4 wb_mask4(float4 v, int c0, int lim) {
-  return make_float4(c0 < lim ? v.x : 0.f, c0 + 1 < lim ? v.y : 0.f, c0 + 2 < lim ? v.z : 0.f, c0 + 3 < lim ? v.w : 0.f);
-}
-WB_DEV float wb_dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
-// sum over the lanes of a pixel group (all 32 lanes must call it)
-WB_DEV float wb_group_sum(float v) {
-#ifndef WB_HOST_EMU
-  WB_UNROLL for (int o = WB_GRP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-#endif
-  return v;
-}
-// Fire-and-forget 128-bit float reduction into GLOBAL memory (REDG.E.ADD.F32x4): one L2 atomic per 16-byte chunk instead of
-// four.  p must be 16-byte aligned.
-WB_DEV void wb_red4(float* p, float4 v) {
-#ifdef WB_HOST_EMU
-  p[0] += v.x; p[1] += v.y; p[2] += v.z; p[3] += v.w;
-#else
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
-#endif
-}
-
 // ------------------------------------------------------------------ ATen-exact bilinear pieces
 // grid_sampler_2d (bilinear, zeros, align_corners=False), SURVEY.md Appendix C.  The association
 // below -- weights as single products, value accumulated nw -> ne -> sw -> se with fused

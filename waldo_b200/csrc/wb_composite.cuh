@@ -47,7 +47,6 @@ WB_DEV WbPix wb_pix(const WbDec& d, int b, int tp, int X, int Y) {
 }
 
 // Layers of one (b,tc,tp) pixel in slot order: per-layer flow F, warped context opacity R, composited opacity A.
-#define WB_ROW_AL 20   // floats of the alpha part of a raw_output record staged per pixel: CRp - ceil4(C) <= 17 + 1 + pad
 template <int NA> struct WbLay {
   float Fx[NA], Fy[NA], R[NA], A[NA];
   float flow_x, flow_y, score, disocc;
@@ -103,19 +102,10 @@ WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, 
 
 struct WbFwdCtx {   // per-CTA constants of the fused forward
   int b, tp, L, C, TcR, CR, HW;
-  int CRp, npass;     // floats per raw_output record; alpha channels handed to the gather kernel through `apass`
   unsigned HWd;
   bool self, disocc_ch;
   const float* s_occ;
-  float* s_row;       // this warp's staging row of the alpha part of 32 records (lanes form)
 };
-
-// alpha channel k of pixel q of one (b,tc,tp) pair: the first `npass` layers travel through `apass` (the gather kernel
-// writes them together with the last image channels as one 16-byte chunk), the others go straight into the record
-WB_DEV void wb_store_alpha(const WbFwdCtx& c, float* __restrict__ raw, float* __restrict__ apass, int k, unsigned q, float v) {
-  if (k < c.npass) apass[(size_t)k * c.HWd + q] = v;
-  else raw[(size_t)q * c.CRp + c.C + k] = v;
-}
 
 // Layer part of one (pixel, context): evaluates the live layers, writes the alpha channels of raw_output (+ disocc),
 // the reduced flow, and returns (flow, score) for the channel part.
@@ -129,12 +119,11 @@ WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, un
   const float* alpha_c = d.alpha + ((size_t)c.b * g.Tw + c_t) * L * HWd;
   WbLay<NA> ly;
   wb_layers_fwd<NA>(d, px, ix, f_lo, alpha_c, c.s_occ, ly);
-  float* ap = d.apass + pair * c.npass * HWd;
-  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) if (k < L && !((wm >> k) & 1u)) wb_store_alpha(c, raw, ap, k, q, -1.f);
-  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) if (s < ix.n) wb_store_alpha(c, raw, ap, ix.k[s], q, ly.A[s] * 2.f - 1.f);
-  float* rec = raw + (size_t)q * c.CRp;
-  if (c.disocc_ch) rec[C + L] = ly.disocc;
-  for (int ch = c.CR; ch < c.CRp; ++ch) rec[ch] = 0.f;   // record padding
+  float* ra = raw + (size_t)C * HWd + q;
+  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) *ra = -1.f; ra += HWd; }
+  ra = raw + (size_t)C * HWd + q;
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) if (s < ix.n) ra[(size_t)ix.k[s] * HWd] = ly.A[s] * 2.f - 1.f;
+  if (c.disocc_ch) ra[(size_t)L * HWd] = ly.disocc;
   float* fl = d.flow + pair * 2 * HWd + q;
   fl[0] = ly.flow_x; fl[HWd] = ly.flow_y;
   flow_x = ly.flow_x; flow_y = ly.flow_y; score = ly.score;
@@ -150,7 +139,7 @@ WB_DEV void wb_fwd_layers_ctxs(const WbDec& d, const WbFwdCtx& c, const WbPix& p
   for (int tc = 0; tc < g.Tc; ++tc) {
     const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
     const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-    float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * (size_t)HWd * c.CRp;
+    float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
     float flow_x, flow_y, score;
     wb_fwd_layers<NA>(d, c, px, wm, ix, q, c_t, pair, raw, flow_x, flow_y, score);
     d.score[pair * HWd + q] = score;
@@ -185,19 +174,11 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
     const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
     const float2* fl = reinterpret_cast<const float2*>(d.f_lo) + (pair * L + k) * HW;
     const float* alpha_k = d.alpha + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
-    float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * (size_t)HWd * c.CRp;   // records of this pair
-    float* ap = d.apass + pair * c.npass * HWd;
+    float* ra = d.raw_output + ((((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR + C) * HWd;   // alpha channels of this pair
     float* flo = d.flow + pair * 2 * HWd;
     float* sco = d.score + pair * HWd;
-    // The alpha part of the 32 records of this row (floats Csplit .. CRp of each) is assembled in shared memory and leaves
-    // as 128-bit stores.  Layers outside the row's union are fully transparent (-1), record padding is 0.
-    const int Csplit = C + c.npass, nal = c.CRp - Csplit;   // nal: a multiple of 4, <= WB_ROW_AL
-    {
-      float* mine = c.s_row + lane * WB_ROW_AL;
-      for (int e = 0; e < nal; ++e) mine[e] = (Csplit + e < C + L) ? -1.f : 0.f;
-      WB_UNROLL for (int kk = 0; kk < 3; ++kk) if (kk < c.npass && !((wm >> kk) & 1u)) ap[(size_t)kk * HWd + ql] = -1.f;
-    }
-    __syncwarp();
+    // layers outside the row's union are fully transparent
+    { float* o = ra + ql; WB_UNROLL for (int kk = 0; kk < WB_MAX_L; ++kk) { if (kk < L && !((wm >> kk) & 1u)) *o = -1.f; o += HWd; } }
 #pragma unroll 1
     for (int r = 0; r < LP; ++r) {
       const int p = r * PPW + pl, X = min(tx0 + p, g.Wd - 1);
@@ -236,23 +217,12 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
         fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o);
         sc += __shfl_xor_sync(0xffffffffu, sc, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       }
-      if (valid) {
-        if (k < c.npass) ap[(size_t)k * HWd + q] = A * 2.f - 1.f;
-        else c.s_row[p * WB_ROW_AL + (k - c.npass)] = A * 2.f - 1.f;
-      }
+      if (valid) ra[(size_t)k * HWd + q] = A * 2.f - 1.f;
       if (slot == 0) {
         flo[q] = fx; flo[HWd + q] = fy; sco[q] = sc;
-        if (c.disocc_ch) c.s_row[p * WB_ROW_AL + (L - c.npass)] = mx;
+        if (c.disocc_ch) ra[(size_t)L * HWd + q] = mx;
       }
     }
-    __syncwarp();
-    for (int idx = lane; idx < 32 * (nal / 4); idx += 32) {   // (pixel, chunk): consecutive lanes -> consecutive 16-byte chunks
-      const int p = idx / (nal / 4), ch = idx - p * (nal / 4);
-      const int X = min(tx0 + p, g.Wd - 1);
-      const float4 v = *reinterpret_cast<const float4*>(c.s_row + p * WB_ROW_AL + 4 * ch);
-      wb_st4(raw + (size_t)(Y * g.Wd + X) * c.CRp + Csplit + 4 * ch, v);
-    }
-    __syncwarp();
   }
 }
 #endif  // !WB_HOST_EMU
@@ -276,13 +246,10 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_FWD) k_layers_fwd(Wb
   c.self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
   c.disocc_ch = (g.flags & WALDO_F_USE_DISOCC) != 0;
   c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0);
-  c.CRp = g.CRp; c.npass = ((c.C + 3) & ~3) - c.C;
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
-  __shared__ __align__(16) float s_rows[WB_TILE_PX / 32][32 * WB_ROW_AL];
   for (int i = wb_tid(); i < c.L * c.L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + u) * c.L * c.L + i);
   __syncthreads();
   c.s_occ = s_occ;
-  c.s_row = s_rows[wb_warp()];
   const int b = c.b, tp = c.tp;
   const unsigned HWd = c.HWd;
   const WbTileIter ti(g.Hd, g.Wd);
@@ -306,116 +273,102 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_FWD) k_layers_fwd(Wb
       else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_fwd_layers_ctxs<8>(d, c, px, wm, q);
       else wb_fwd_layers_ctxs<WB_MAX_L>(d, c, px, wm, q);
 #endif
-      if (c.self) {   // lvd.py:842-845: the target frame itself is fully opaque (the first npass layers: gather kernel)
-        float* rec = d.raw_output + ((((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * (size_t)HWd + q) * c.CRp;
-        for (int k = c.npass; k < c.L; ++k) rec[c.C + k] = 1.f;
-        if (c.disocc_ch) rec[c.C + c.L] = 1.f;
-        for (int ch = c.CR; ch < c.CRp; ++ch) rec[ch] = 0.f;
+      if (c.self) {   // lvd.py:842-845: the target frame itself is fully opaque
+        float* raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q;
+        for (int k = 0; k < c.L; ++k) raw[(size_t)(c.C + k) * HWd] = 1.f;
+        if (c.disocc_ch) raw[(size_t)(c.C + c.L) * HWd] = 1.f;
       }
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// k_gather_fwd: stage C (lvd.py:830-853) on channels-last records.
-// grid = (CTAs, B*Tp), 32x8 pixel tiles.  A PIXEL GROUP of WB_GRP = 8 lanes owns one pixel; lane j owns the 16-byte chunk j
-// (channels 4j .. 4j+3) of every record of that pixel, so each of the four bilinear taps of a context frame is ONE 128-bit
-// load per lane (LDG.E.128), warp-wide a run of whole consecutive records, and the warped channels leave as one 128-bit store
-// per lane into the raw_output record.  The C image channels fill the first Csplit = ceil4(C) floats of that record; the
-// Csplit - C leftover floats of the last image chunk are the first alpha channels (layer 0 ..), which the layer kernel hands
-// over through `apass` so that this kernel writes whole chunks.  The fused `output` (lvd.py:850-851) accumulates in registers
-// over the contexts.  Bit-identical arithmetic per channel to the reference association (wb_chain).
+// grid = (CTAs, B*Tp), 32x8 pixel tiles, one thread per HD pixel.  The taps of the TCAP (>= Tc) contexts live in
+// registers; ONE rolled loop walks the C image channels with the contexts unrolled inside: every channel of every
+// context frame is gathered, stored to raw_output and fused into `output` (lvd.py:850-851) on the fly.
+// FAST = exactly TCAP contexts and no include_self context, resolved at compile time (no predicates in the channel loop).
+template <int TCAP, bool FAST>
 __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_FWD) k_gather_fwd(WbDec d) {
   const waldo_geom_t g = d.g;
-  const int C = g.C, L = g.No + 1, Cp = g.Cp, CRp = g.CRp;
+  const int C = g.C, L = g.No + 1;
   const unsigned HWd = (unsigned)(g.Hd * g.Wd);
   const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
-  const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
-  const int TcR = g.Tc + (self ? 1 : 0);
-  const int Csplit = (C + 3) & ~3, npass = Csplit - C;
-  const int nchi = Csplit / 4;          // chunks of a raw_output record written here
-  const int ncho = Cp / 4;              // chunks of an out_full record
-  __shared__ const float* s_src[8];     // context frame of every context (CTA-uniform)
-  __shared__ float* s_raw[8];           // raw_output block of every context
+  const bool self = !FAST && (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
+  __shared__ const float* s_src[TCAP];   // context frame of every context (CTA-uniform)
+  __shared__ float* s_raw[TCAP];         // raw_output block of every context
   for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
     const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * HWd * Cp;
-    s_raw[tc] = d.raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * (size_t)HWd * CRp;
+    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
+    s_raw[tc] = d.raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * CR * HWd;
   }
   __syncthreads();
-  const int j0 = wb_tid() % WB_GRP, ppi = max(wb_nthr() / WB_GRP, 1);
-  float* of = d.out_full + ((size_t)b * g.Tp + tp) * (size_t)HWd * Cp;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
-    for (int pi = wb_tid() / WB_GRP; pi < WB_TILE_PX; pi += ppi) {
-      // pixels beyond the image edge recompute (and re-store, identically) the nearest valid pixel: no predicates
-      const int X = min(tx0 + (pi & (WB_TILE_W - 1)), g.Wd - 1), Y = min(ty0 + pi / WB_TILE_W, g.Hd - 1);
+    for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
+      const int X = min(tx0 + (it & (WB_TILE_W - 1)), g.Wd - 1), Y = min(ty0 + it / WB_TILE_W, g.Hd - 1);
       const unsigned q = (unsigned)(Y * g.Wd + X);
       const float gx = __ldg(d.xs_hd + X), gy = __ldg(d.ys_hd + Y);
-      float4 acc[WB_GCH];
-      WB_CHUNKS acc[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned o0[TCAP], o1[TCAP];
+      float w[TCAP][4], wgt[TCAP];
       float den = 0.f, accs = 0.f;
-      for (int tc = 0; tc < g.Tc; ++tc) {
-        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-        const float* fl = d.flow + pair * 2 * HWd + q;
-        const float score = __ldg(d.score + pair * HWd + q);
-        const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
-        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-        const float wgt = score + 1e-6f;
-        den += wgt;
-        accs += wgt * (score * 2.f - 1.f);
-        const float* r0 = s_src[tc] + (size_t)t2.o0 * Cp;
-        const float* r1 = s_src[tc] + (size_t)t2.o1 * Cp;
-        float* rw = s_raw[tc] + (size_t)q * CRp;
-        WB_CHUNKS {
-          const int j = j0 + ci;
-          if (j < nchi) {
-            const float4 v0 = wb_ld4(r0 + 4 * j), v1 = wb_ld4(r0 + Cp + 4 * j), v2 = wb_ld4(r1 + 4 * j), v3 = wb_ld4(r1 + Cp + 4 * j);
-            float4 r;
-            r.x = __fmaf_rn(v3.x, t2.w[3], __fmaf_rn(v2.x, t2.w[2], __fmaf_rn(v1.x, t2.w[1], __fmul_rn(v0.x, t2.w[0]))));
-            r.y = __fmaf_rn(v3.y, t2.w[3], __fmaf_rn(v2.y, t2.w[2], __fmaf_rn(v1.y, t2.w[1], __fmul_rn(v0.y, t2.w[0]))));
-            r.z = __fmaf_rn(v3.z, t2.w[3], __fmaf_rn(v2.z, t2.w[2], __fmaf_rn(v1.z, t2.w[1], __fmul_rn(v0.z, t2.w[0]))));
-            r.w = __fmaf_rn(v3.w, t2.w[3], __fmaf_rn(v2.w, t2.w[2], __fmaf_rn(v1.w, t2.w[1], __fmul_rn(v0.w, t2.w[0]))));
-            acc[ci].x += wgt * r.x; acc[ci].y += wgt * r.y; acc[ci].z += wgt * r.z; acc[ci].w += wgt * r.w;
-            if (4 * j + 3 >= C) {   // the chunk that holds the last image channels: its tail = the first alpha channels
-              const float* ap = d.apass + pair * npass * HWd + q;
-              WB_UNROLL for (int e = 0; e < 4; ++e)
-                if (4 * j + e >= C) wb_set(r, e, __ldg(ap + (size_t)(4 * j + e - C) * HWd));
-            }
-            wb_st4(rw + 4 * j, r);
-          }
+      WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+        o0[tc] = 0u; o1[tc] = 0u; wgt[tc] = 0.f;
+        WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = 0.f;
+        if (FAST || tc < g.Tc) {
+          const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
+          const float* fl = d.flow + pair * 2 * HWd + q;
+          const float score = __ldg(d.score + pair * HWd + q);
+          const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+          const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+          o0[tc] = t2.o0; o1[tc] = t2.o1;
+          WB_UNROLL for (int j = 0; j < 4; ++j) w[tc][j] = t2.w[j];
+          wgt[tc] = score + 1e-6f;
+          den += wgt[tc];
+          accs += wgt[tc] * (score * 2.f - 1.f);
         }
       }
-      if (self) {   // lvd.py:842-845: the target frame itself, score 1, every layer fully opaque
-        const float wself = 1.f + 1e-6f;
+      const float* self_src = nullptr;
+      float* self_raw = nullptr;
+      float wself = 0.f;
+      if (self) {   // lvd.py:842-845: the target frame itself, score 1
+        self_raw = d.raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q;
+        self_src = d.input + ((size_t)b * g.T + tp) * C * HWd + q;
+        wself = 1.f + 1e-6f;
         den += wself; accs += wself;
-        const float* sr = d.input + (((size_t)b * g.T + tp) * HWd + q) * Cp;
-        float* rw = d.raw_output + ((((size_t)b * TcR + g.Tc) * g.Tp + tp) * (size_t)HWd + q) * CRp;
-        WB_CHUNKS {
-          const int j = j0 + ci;
-          if (j < nchi) {
-            float4 v = wb_ld4(sr + 4 * j);
-            acc[ci].x += wself * v.x; acc[ci].y += wself * v.y; acc[ci].z += wself * v.z; acc[ci].w += wself * v.w;
-            WB_UNROLL for (int e = 0; e < 4; ++e) if (4 * j + e >= C) wb_set(v, e, 1.f);
-            wb_st4(rw + 4 * j, v);
-          }
-        }
       }
       const float inv = 1.f / fmaxf(den, 1e-12f);
-      WB_CHUNKS {
-        const int j = j0 + ci;
-        if (j < ncho) {
-          float4 o = j < nchi ? make_float4(acc[ci].x * inv, acc[ci].y * inv, acc[ci].z * inv, acc[ci].w * inv) : make_float4(0.f, 0.f, 0.f, 0.f);
-          WB_UNROLL for (int e = 0; e < 4; ++e) {
-            const int ch = 4 * j + e;
-            if (ch == C) wb_set(o, e, accs * inv);       // the fused score channel = raw_alpha (lvd.py:147)
-            else if (ch > C) wb_set(o, e, 0.f);
+      float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+      unsigned choff = 0u;   // ch * HWd
+#ifndef WB_HOST_EMU
+#pragma unroll 2
+#endif
+      for (int ch = 0; ch < C; ++ch) {
+        // all 4 x TCAP loads of this channel first (read-only path), then the arithmetic and the stores
+        float v[TCAP][4];
+        WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+          if (FAST || tc < g.Tc) {
+            const float* pl = s_src[tc] + choff;
+            const float* p0 = pl + o0[tc];
+            const float* p1 = pl + o1[tc];
+            v[tc][0] = __ldg(p0); v[tc][1] = __ldg(p0 + 1); v[tc][2] = __ldg(p1); v[tc][3] = __ldg(p1 + 1);
           }
-          wb_st4(of + (size_t)q * Cp + 4 * j, o);
         }
-        if (j == 0) d.norm[((size_t)b * g.Tp + tp) * HWd + q] = den;
+        float acc = 0.f;
+        WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
+          if (FAST || tc < g.Tc) {
+            const float r = __fmaf_rn(v[tc][3], w[tc][3], __fmaf_rn(v[tc][2], w[tc][2], __fmaf_rn(v[tc][1], w[tc][1], __fmul_rn(v[tc][0], w[tc][0]))));
+            s_raw[tc][choff + q] = r;
+            acc += wgt[tc] * r;
+          }
+        }
+        if (self) { const float v = __ldg(self_src + choff); self_raw[choff] = v; acc += wself * v; }
+        of[choff] = acc * inv;
+        choff += HWd;
       }
+      of[choff] = accs * inv;
+      d.norm[((size_t)b * g.Tp + tp) * HWd + q] = den;
     }
   }
 }
+

@@ -28,22 +28,16 @@ static int wb_fail(int code, const char* fmt, ...);
 #endif
 
 #undef WB_RED
-#undef WB_RED4
 #undef WB_RED_NZ
 #if WB_DET
 namespace wb_fixed {
 // every call site has the kernel argument `a` in scope
 #define WB_RED(p, v) wb_red_fixed(a.det_base, a.det_shadow, a.det_scale, (p), (v))
-#define WB_RED4(p, v) wb_red4_fixed(a, (p), (v))
 #define WB_RED_NZ(p, v) wb_atomic_add(a, (p), (v))
 WB_DEV void wb_atomic_add(const WbDecB& a, float* p, float v) { if (v != 0.f) WB_RED(p, v); }
-WB_DEV void wb_red4_fixed(const WbDecB& a, float* p, float4 v) {
-  WB_RED(p, v.x); WB_RED(p + 1, v.y); WB_RED(p + 2, v.z); WB_RED(p + 3, v.w);
-}
 #else
 namespace wb_plain {
 #define WB_RED(p, v) wb_red((p), (v))
-#define WB_RED4(p, v) wb_red4((p), (v))
 #define WB_RED_NZ(p, v) wb_atomic_add((p), (v))
 WB_DEV void wb_atomic_add(float* p, float v) { if (v != 0.f) wb_red(p, v); }
 #endif
@@ -182,7 +176,7 @@ WB_DEV void wb_occlude_bwd(const float* R, const float* gA, const float* s_occ, 
 
 // ============================================================================ fused HD backward
 struct WbBwdCtx {   // per-CTA constants of the fused backward
-  int b, tp, L, C, TcR, CR, HW, CRp;
+  int b, tp, L, C, TcR, CR, HW;
   unsigned HWd;
   bool self, disocc_ch, need_layers, lowres_direct, pairs_only;
   const float* s_occ;
@@ -206,14 +200,14 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
   WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     gR[s] = 0.f; gA[s] = 0.f; gFx[s] = 0.f; gFy[s] = 0.f;
     if (s < ix.n) {
-      gA[s] = gs + 2.f * (draw ? actf * __ldg(draw + C + ix.k[s]) : 0.f) + dfx * ly.Fx[s] + dfy * ly.Fy[s];
+      gA[s] = gs + 2.f * (draw ? actf * __ldg(draw + (size_t)(C + ix.k[s]) * HWd) : 0.f) + dfx * ly.Fx[s] + dfy * ly.Fy[s];
       gFx[s] = ly.A[s] * dfx; gFy[s] = ly.A[s] * dfy;
     }
   }
   wb_occlude_bwd<NA>(ly.R, gA, c.s_occ, L, ix, gR, c.s_acc, c.pairs_only);
   // ---- B7 backward: disocc = max_k R_k (first maximal layer takes the gradient)
   if (c.disocc_ch && draw) {
-    const float gd = actf * __ldg(draw + C + L);
+    const float gd = actf * __ldg(draw + (size_t)(C + L) * HWd);
     bool done = false;
     WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s)
       if (s < ix.n && !done && ly.R[s] == ly.disocc) { gR[s] += gd; done = true; }
@@ -298,7 +292,7 @@ WB_DEV void wb_bwd_layers_ctxs(const WbDecB& a, const WbBwdCtx& c, const WbPix& 
     const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
     const float* gl = a.glue + pair * 3 * HWd + q;
     const float gs = actf * __ldg(gl), dfx = actf * __ldg(gl + HWd), dfy = actf * __ldg(gl + 2 * HWd);
-    const float* draw = a.d_raw_output ? a.d_raw_output + ((((size_t)b * c.TcR + tc) * g.Tp + tp) * (size_t)HWd + q) * c.CRp : nullptr;   // this pixel's record
+    const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd + q : nullptr;
     wb_bwd_layers_bwd<NA>(a, c, px, cr, ix, tc, c_t, pair, draw, actf, gs, dfx, dfy);
   }
 }
@@ -369,7 +363,7 @@ WB_DEV void wb_lanes_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbColR
     const float* alpha_k = d.alpha + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
     float* dal_k = a.d_alpha_acc ? a.d_alpha_acc + (((size_t)b * g.Tw + c_t) * L + k) * HWd : nullptr;
     const float* gl = a.glue + pair * 3 * HWd;
-    const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * (size_t)HWd * c.CRp : nullptr;   // records of this pair
+    const float* draw = a.d_raw_output ? a.d_raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd : nullptr;
 #pragma unroll 1
     for (int r = 0; r < LP; ++r) {
       const int p = r * PPW + pl, Xr = tx0 + p, X = min(Xr, g.Wd - 1);
@@ -381,7 +375,7 @@ WB_DEV void wb_lanes_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbColR
       const unsigned isobj = __shfl_sync(0xffffffffu, isobj_lane, p);
       // ---- every load that does not depend on another load is issued first (invalid lanes read layer 0: harmless)
       const float gs_l = __ldg(gl + q), dfx_l = __ldg(gl + HWd + q), dfy_l = __ldg(gl + 2 * HWd + q);
-      const float dr_l = draw ? __ldg(draw + (size_t)q * c.CRp + C + k) : 0.f;
+      const float dr_l = draw ? __ldg(draw + (size_t)(C + k) * HWd + q) : 0.f;
       float2 f00 = __ldg(fl + o00), f01 = f00, f10 = f00, f11 = f00;
       if (!c.lowres_direct) { f01 = __ldg(fl + o01); f10 = __ldg(fl + o10); f11 = __ldg(fl + o11); }
 #if WB_PF_FLO
@@ -442,7 +436,7 @@ WB_DEV void wb_lanes_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbColR
         WB_UNROLL for (int o = PPW; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         int first = (valid && rr == mx) ? slot : 99;
         WB_UNROLL for (int o = PPW; o < 32; o <<= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-        if (slot == first) gR += actf * __ldg(draw + (size_t)q * c.CRp + C + L);
+        if (slot == first) gR += actf * __ldg(draw + (size_t)(C + L) * HWd + q);
       }
       // ---- B6 backward: bilinear sample of the context opacity through this layer's flow
       if (samp && gR != 0.f) {
@@ -495,169 +489,320 @@ WB_DEV void wb_lanes_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbColR
 //   k_layers_bwd : backward of the layer part (B9..B5up) driven by `glue` and the alpha channels of d raw_output.
 // ------------------------------------------------------------------------------------------------------------------
 
-// grid = (CTAs, B*Tp), 32x8 pixel tiles, channels-last records, a PIXEL GROUP of WB_GRP = 8 lanes per pixel (see
-// k_gather_fwd): lane j owns the 16-byte chunk j of every record of its pixel.  Per (pixel, context) a lane issues one
-// 128-bit load per tap of the context frame and one for its chunk of d raw_output, and scatters its chunk of d input with
-// one 128-bit reduction per tap (REDG.E.ADD.F32x4) -- 6 + 24 memory instructions per (pixel, context) where the planar
-// layout needed 115 + 92.  Since the gathered value is bilinear in the four taps, d score and d flow follow from the tap
-// moments
-//   U_j = sum_ch dOut_ch * v_j,   T_j = sum_ch dRaw_ch * v_j     (j = the four tap positions),
-// summed over the chunks of the pixel with three xor-shuffles.  Neighbouring pixels of a row mostly hit neighbouring
-// source cells: where pixel p+1's left taps are pixel p's right taps, p hands its right-tap contributions to p+1 (one
-// shuffle by WB_GRP lanes per component) instead of issuing its own reductions.
+// grid = (CTAs, B*Tp), 32x8 pixel tiles.  The contexts are processed TG at a time (small register state -> high
+// occupancy); per group ONE rolled loop over the image channels with the TG contexts unrolled inside.  Since the
+// gathered value is bilinear in the four taps, d score and d flow follow from the tap moments
+//   U_j = sum_ch dOut_ch * v_j,   T_j = sum_ch dRaw_ch * v_j     (j = the four tap positions).
+// FAST = the common full case, resolved at compile time (no predicates, no divergence bookkeeping in the channel loop):
+// Tc a multiple of TG, every upstream gradient and d_input present, no include_self context.
+template <int TG, bool FAST>
 __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd(WbDecB a) {
   const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
-  const int C = g.C, Cp = g.Cp, CRp = g.CRp;
+  const int C = g.C, L = g.No + 1;
   const unsigned HWd = (unsigned)(g.Hd * g.Wd);
   const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
-  const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
-  const int TcR = g.Tc + (self ? 1 : 0);
-  const int nchi = ((C + 3) & ~3) / 4;   // chunks of a record that hold image channels
+  const bool self = !FAST && (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+  const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
   __shared__ const float* s_src[8];    // context frame of every context (CTA-uniform)
   __shared__ float* s_dsrc[8];         // its gradient
-  __shared__ const float* s_draw[8];   // upstream d raw_output records of every context (or null)
+  __shared__ const float* s_draw[8];   // upstream d raw_output block of every context (or null)
   for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
     const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * HWd * Cp;
-    s_dsrc[tc] = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * HWd * Cp : nullptr;
-    s_draw[tc] = a.d_raw_output ? a.d_raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * (size_t)HWd * CRp : nullptr;
+    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
+    s_dsrc[tc] = a.d_input ? a.d_input + ((size_t)b * g.T + c_t) * C * HWd : nullptr;
+    s_draw[tc] = a.d_raw_output ? a.d_raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * CR * HWd : nullptr;
   }
   __syncthreads();
-  const int j0 = wb_tid() % WB_GRP, ppi = max(wb_nthr() / WB_GRP, 1);
-  const float* dofr = a.d_output ? a.d_output + ((size_t)b * g.Tp + tp) * (size_t)HWd * Cp : nullptr;
-  const float* ofr = d.out_full + ((size_t)b * g.Tp + tp) * (size_t)HWd * Cp;
+  const bool has_din = FAST || a.d_input != nullptr, has_draw = FAST || a.d_raw_output != nullptr;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
-    for (int pi = wb_tid() / WB_GRP; pi < WB_TILE_PX; pi += ppi) {
-      const int Xr = tx0 + (pi & (WB_TILE_W - 1)), Yr = ty0 + pi / WB_TILE_W;
+    for (int it = wb_tid(); it < WB_TILE_PX; it += wb_nthr()) {
+      const int Xr = tx0 + (it & (WB_TILE_W - 1)), Yr = ty0 + it / WB_TILE_W;
       const bool active = Xr < g.Wd && Yr < g.Hd;
-      const float actf = active ? 1.f : 0.f;    // pixels beyond the edge run on the nearest valid pixel with zero upstream
+      const float actf = active ? 1.f : 0.f;    // threads beyond the edge run on the nearest valid pixel with zero upstream
       const int X = min(Xr, g.Wd - 1), Y = min(Yr, g.Hd - 1);
       const unsigned q = (unsigned)(Y * g.Wd + X);
       const float gx = __ldg(d.xs_hd + X), gy = __ldg(d.ys_hd + Y);
       const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
-      const float gOs = a.d_raw_alpha ? actf * __ldg(a.d_raw_alpha + ((size_t)b * g.Tp + tp) * HWd + q) : 0.f;   // d / d fused score channel
-      // this lane's chunk(s) of d output; S = sum_ch dOut_ch * out_ch over the C + 1 channels of out_full
-      float4 gO[WB_GCH];
-      float S = 0.f;
-      WB_CHUNKS {
-        const int j = j0 + ci;
-        gO[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (4 * j <= C) {
-          const float4 ov = wb_ld4(ofr + (size_t)q * Cp + 4 * j);
-          if (dofr && j < nchi) {
-            const float4 v = wb_ld4(dofr + (size_t)q * Cp + 4 * j);
-            gO[ci] = wb_mask4(make_float4(actf * v.x, actf * v.y, actf * v.z, actf * v.w), 4 * j, C);
+      const float* dof = a.d_output ? a.d_output + ((size_t)b * g.Tp + tp) * C * HWd + q : nullptr;
+      const float* dra = a.d_raw_alpha ? a.d_raw_alpha + ((size_t)b * g.Tp + tp) * HWd + q : nullptr;
+      const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+      float S = 0.f;   // sum_ch dOut * out, complete after the first group
+      for (int tc0 = 0; tc0 < g.Tc; tc0 += TG) {
+        unsigned o0[TG], o1[TG];
+        float w[TG][4], nrm[TG], U[TG][4], Tq[TG][4];
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          o0[i] = 0u; o1[i] = 0u; nrm[i] = 0.f;
+          WB_UNROLL for (int j = 0; j < 4; ++j) { w[i][j] = 0.f; U[i][j] = 0.f; Tq[i][j] = 0.f; }
+          if (FAST || tc0 + i < g.Tc) {
+            const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
+            const float* fl = d.flow + pair * 2 * HWd + q;
+            const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+            const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+            o0[i] = t2.o0; o1[i] = t2.o1;
+            WB_UNROLL for (int j = 0; j < 4; ++j) w[i][j] = t2.w[j];
+            nrm[i] = (__ldg(d.score + pair * HWd + q) + 1e-6f) / D;
           }
-          float4 gx4 = gO[ci];
-          WB_UNROLL for (int e = 0; e < 4; ++e) if (4 * j + e == C) wb_set(gx4, e, gOs);
-          S += wb_dot4(gx4, wb_mask4(ov, 4 * j, C + 1));
         }
-      }
-      S = wb_group_sum(S);
-      for (int tc = 0; tc < g.Tc; ++tc) {
-        const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-        const float* fl = d.flow + pair * 2 * HWd + q;
-        const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
-        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-        const float nrm = (__ldg(d.score + pair * HWd + q) + 1e-6f) / D;
-        const float* r0 = s_src[tc] + (size_t)t2.o0 * Cp;
-        const float* r1 = s_src[tc] + (size_t)t2.o1 * Cp;
-        const float* drw = s_draw[tc] ? s_draw[tc] + (size_t)q * CRp : nullptr;
-        float* dl0 = s_dsrc[tc] ? s_dsrc[tc] + (size_t)t2.o0 * Cp : nullptr;
-        float* dl1 = s_dsrc[tc] ? s_dsrc[tc] + (size_t)t2.o1 * Cp : nullptr;
+        // Neighbouring pixels of a row mostly hit neighbouring source cells: where lane l+1's left taps are lane l's right
+        // taps (o[l+1] == o[l] + 1), lane l hands its right-tap contributions to lane l+1 (one shuffle each) instead of
+        // issuing its own reductions -- about half of the global reductions in smooth-flow regions.
+        bool skipR0[TG], skipR1[TG], mergeL0[TG], mergeL1[TG];
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          skipR0[i] = skipR1[i] = mergeL0[i] = mergeL1[i] = false;
 #if !defined(WB_HOST_EMU) && WB_GB_MERGE
-        // pixel p+1 of the same row sits WB_GRP lanes up
-        const int lane = wb_lane();
-        const unsigned n0 = __shfl_down_sync(0xffffffffu, t2.o0, WB_GRP), n1 = __shfl_down_sync(0xffffffffu, t2.o1, WB_GRP);
-        const bool skipR0 = lane < 32 - WB_GRP && n0 == t2.o0 + 1u, skipR1 = lane < 32 - WB_GRP && n1 == t2.o1 + 1u;
-        const bool mergeL0 = __shfl_up_sync(0xffffffffu, (int)skipR0, WB_GRP) != 0 && lane >= WB_GRP;
-        const bool mergeL1 = __shfl_up_sync(0xffffffffu, (int)skipR1, WB_GRP) != 0 && lane >= WB_GRP;
-#endif
-        float U[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
-        WB_CHUNKS {
-          const int j = j0 + ci;
-          float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool on = j < nchi;
-          if (on) {
-            const float4 v0 = wb_ld4(r0 + 4 * j), v1 = wb_ld4(r0 + Cp + 4 * j), v2 = wb_ld4(r1 + 4 * j), v3 = wb_ld4(r1 + Cp + 4 * j);
-            float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (drw) {
-              const float4 x = wb_ld4(drw + 4 * j);
-              gd = wb_mask4(make_float4(actf * x.x, actf * x.y, actf * x.z, actf * x.w), 4 * j, C);
-            }
-            const float4 o = gO[ci];
-            go = make_float4(gd.x + nrm * o.x, gd.y + nrm * o.y, gd.z + nrm * o.z, gd.w + nrm * o.w);
-            U[0] += wb_dot4(o, v0); U[1] += wb_dot4(o, v1); U[2] += wb_dot4(o, v2); U[3] += wb_dot4(o, v3);
-            Tq[0] += wb_dot4(gd, v0); Tq[1] += wb_dot4(gd, v1); Tq[2] += wb_dot4(gd, v2); Tq[3] += wb_dot4(gd, v3);
+          if (FAST) {
+            const int lane = wb_lane();
+            const unsigned n0 = __shfl_down_sync(0xffffffffu, o0[i], 1), n1 = __shfl_down_sync(0xffffffffu, o1[i], 1);
+            skipR0[i] = lane < 31 && n0 == o0[i] + 1u;
+            skipR1[i] = lane < 31 && n1 == o1[i] + 1u;
+            mergeL0[i] = __shfl_up_sync(0xffffffffu, (int)skipR0[i], 1) != 0 && lane > 0;
+            mergeL1[i] = __shfl_up_sync(0xffffffffu, (int)skipR1[i], 1) != 0 && lane > 0;
           }
-          if (dl0) {
-            const float w0 = t2.w[0], w1 = t2.w[1], w2 = t2.w[2], w3 = t2.w[3];
-            float4 c0 = make_float4(w0 * go.x, w0 * go.y, w0 * go.z, w0 * go.w), c1 = make_float4(w1 * go.x, w1 * go.y, w1 * go.z, w1 * go.w);
-            float4 c2 = make_float4(w2 * go.x, w2 * go.y, w2 * go.z, w2 * go.w), c3 = make_float4(w3 * go.x, w3 * go.y, w3 * go.z, w3 * go.w);
+#endif
+        }
+        const bool first = tc0 == 0;
+        float* dself = (first && self && has_din) ? a.d_input + ((size_t)b * g.T + tp) * C * HWd + q : nullptr;
+        const float* drself = (self && has_draw) ? a.d_raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q : nullptr;
+        unsigned choff = 0u;   // ch * HWd
+        WB_UNROLL_N(WB_GB_UNROLL)
+        for (int ch = 0; ch < C; ++ch) {
+          // all loads of this channel first (read-only path), then the arithmetic and the reductions
+          float v[TG][4], gd[TG];
+          const float gO = (FAST || dof) ? actf * __ldg(dof + choff) : 0.f;
+          WB_UNROLL for (int i = 0; i < TG; ++i) {
+            if (FAST || tc0 + i < g.Tc) {
+              const float* pl = s_src[tc0 + i] + choff;
+              const float* p0 = pl + o0[i];
+              const float* p1 = pl + o1[i];
+              v[i][0] = __ldg(p0); v[i][1] = __ldg(p0 + 1); v[i][2] = __ldg(p1); v[i][3] = __ldg(p1 + 1);
+              gd[i] = has_draw ? __ldg(s_draw[tc0 + i] + choff + q) : 0.f;
+            }
+          }
+          if (first && (FAST || dof)) S += gO * __ldg(of + choff);
+          WB_UNROLL for (int i = 0; i < TG; ++i) {
+            if (FAST || tc0 + i < g.Tc) {
+              const float gdt = actf * gd[i];
+              const float go = gdt + nrm[i] * gO;
+              WB_UNROLL for (int j = 0; j < 4; ++j) { U[i][j] += gO * v[i][j]; Tq[i][j] += gdt * v[i][j]; }
+              if (has_din) {
+                float* dl = s_dsrc[tc0 + i] + choff;
 #if !defined(WB_HOST_EMU) && WB_GB_MERGE
-            float4 u1, u3;   // the left neighbour's right-tap contributions (all lanes shuffle)
-            u1.x = __shfl_up_sync(0xffffffffu, c1.x, WB_GRP); u1.y = __shfl_up_sync(0xffffffffu, c1.y, WB_GRP);
-            u1.z = __shfl_up_sync(0xffffffffu, c1.z, WB_GRP); u1.w = __shfl_up_sync(0xffffffffu, c1.w, WB_GRP);
-            u3.x = __shfl_up_sync(0xffffffffu, c3.x, WB_GRP); u3.y = __shfl_up_sync(0xffffffffu, c3.y, WB_GRP);
-            u3.z = __shfl_up_sync(0xffffffffu, c3.z, WB_GRP); u3.w = __shfl_up_sync(0xffffffffu, c3.w, WB_GRP);
-            if (mergeL0) { c0.x += u1.x; c0.y += u1.y; c0.z += u1.z; c0.w += u1.w; }
-            if (mergeL1) { c2.x += u3.x; c2.y += u3.y; c2.z += u3.z; c2.w += u3.w; }
-            if (on) {
-              WB_RED4(dl0 + 4 * j, c0);
-              if (!skipR0) WB_RED4(dl0 + Cp + 4 * j, c1);
-              WB_RED4(dl1 + 4 * j, c2);
-              if (!skipR1) WB_RED4(dl1 + Cp + 4 * j, c3);
-            }
-#else
-            if (on) {
-              WB_RED4(dl0 + 4 * j, c0); WB_RED4(dl0 + Cp + 4 * j, c1);
-              WB_RED4(dl1 + 4 * j, c2); WB_RED4(dl1 + Cp + 4 * j, c3);
-            }
+                if (FAST) {
+                  const float c1 = w[i][1] * go, c3 = w[i][3] * go;
+                  const float r1 = __shfl_up_sync(0xffffffffu, c1, 1), r3 = __shfl_up_sync(0xffffffffu, c3, 1);
+                  WB_RED(dl + o0[i], w[i][0] * go + (mergeL0[i] ? r1 : 0.f));
+                  if (!skipR0[i]) WB_RED(dl + o0[i] + 1, c1);
+                  WB_RED(dl + o1[i], w[i][2] * go + (mergeL1[i] ? r3 : 0.f));
+                  if (!skipR1[i]) WB_RED(dl + o1[i] + 1, c3);
+                } else
 #endif
-          }
-        }
-        WB_UNROLL for (int k = 0; k < 4; ++k) { U[k] = wb_group_sum(U[k]); Tq[k] = wb_group_sum(Tq[k]); }
-        if (a.glue && active && j0 == 0) {   // (pixels beyond the edge must not overwrite the pixel they mirror)
-          float cx[4], cy[4];
-          wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
-          wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
-          const float sc = nrm * D - 1e-6f;
-          float G = U[0] * t2.w[0] + U[1] * t2.w[1] + U[2] * t2.w[2] + U[3] * t2.w[3];
-          float gix = 0.f, giy = 0.f;
-          WB_UNROLL for (int k = 0; k < 4; ++k) {
-            const float tj = Tq[k] + nrm * U[k];
-            gix += tj * cx[k]; giy += tj * cy[k];
-          }
-          G += gOs * (sc * 2.f - 1.f);
-          const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
-          float* gl = a.glue + pair * 3 * HWd + q;
-          gl[0] = 2.f * nrm * gOs + (G - S) / D;
-          gl[HWd] = (dfl ? __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
-          gl[2 * HWd] = (dfl ? __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
-        }
-      }
-      if (self && a.d_input && active) {   // lvd.py:845: the target frame passes straight through
-        const float nself = (1.f + 1e-6f) / D;
-        float* dself = a.d_input + (((size_t)b * g.T + tp) * HWd + q) * Cp;
-        const float* drself = a.d_raw_output ? a.d_raw_output + ((((size_t)b * TcR + g.Tc) * g.Tp + tp) * (size_t)HWd + q) * CRp : nullptr;
-        WB_CHUNKS {
-          const int j = j0 + ci;
-          if (j < nchi) {
-            float4 v = make_float4(nself * gO[ci].x, nself * gO[ci].y, nself * gO[ci].z, nself * gO[ci].w);
-            if (drself) {
-              const float4 x = wb_mask4(wb_ld4(drself + 4 * j), 4 * j, C);
-              v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+                {
+                  WB_RED(dl + o0[i], w[i][0] * go); WB_RED(dl + o0[i] + 1, w[i][1] * go);
+                  WB_RED(dl + o1[i], w[i][2] * go); WB_RED(dl + o1[i] + 1, w[i][3] * go);
+                }
+              }
             }
-            WB_RED4(dself + 4 * j, v);
+          }
+          if (dself && active) {   // lvd.py:845: the target frame passes straight through
+            const float nself = (1.f + 1e-6f) / D;
+            WB_RED_NZ(dself + choff, (drself ? __ldg(drself + choff) : 0.f) + nself * gO);
+          }
+          choff += HWd;
+        }
+        if (!a.glue || !active) continue;   // (threads beyond the edge must not overwrite the pixel they mirror)
+        const float gOs = dra ? __ldg(dra) : 0.f;   // d / d (fused score channel), index C of out_full
+        if (first && dra) S += gOs * __ldg(of + choff);
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          if (FAST || tc0 + i < g.Tc) {
+            const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
+            const float* fl = d.flow + pair * 2 * HWd + q;
+            const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+            const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+            float cx[4], cy[4];
+            wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
+            wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
+            const float sc = nrm[i] * D - 1e-6f;
+            float G = U[i][0] * w[i][0] + U[i][1] * w[i][1] + U[i][2] * w[i][2] + U[i][3] * w[i][3];
+            float gix = 0.f, giy = 0.f;
+            WB_UNROLL for (int j = 0; j < 4; ++j) {
+              const float tj = Tq[i][j] + nrm[i] * U[i][j];
+              gix += tj * cx[j]; giy += tj * cy[j];
+            }
+            G += gOs * (sc * 2.f - 1.f);
+            const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
+            float* gl = a.glue + pair * 3 * HWd + q;
+            gl[0] = 2.f * nrm[i] * gOs + (G - S) / D;
+            gl[HWd] = (dfl ? __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+            gl[2 * HWd] = (dfl ? __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
           }
         }
       }
     }
   }
 }
+
+#ifndef WB_HOST_EMU
+// ------------------------------------------------------------------------------------------------------------------
+// k_gather_bwd with an asynchronous-copy pipeline (the FAST case only).  Every load of the channel loop has an address
+// that is known before the loop starts (fixed taps + ch * HWd), so the kernel is limited by how many loads a thread
+// keeps in flight, i.e. by registers.  cp.async (LDGSTS) moves each thread's operands of the next WB_GB_DEPTH - 1
+// channels into its own shared-memory slots without holding registers: (5 TG + 2) x (DEPTH - 1) loads in flight per
+// thread instead of the ~12 the register file allows.  A thread only ever reads its own slots: no barrier, just
+// cp.async.wait_group.
+
+#ifndef WB_GB_DEPTH
+#define WB_GB_DEPTH 3
+#endif
+
+template <int TG>
+__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_BWD) k_gather_bwd_async(WbDecB a) {
+  constexpr int NF = 5 * TG + 2;            // per channel: TG x (4 taps + d raw) + d out + out
+  constexpr int DEPTH = WB_GB_DEPTH;
+  const WbDec& d = a.f;
+  const waldo_geom_t g = d.g;
+  const int C = g.C, L = g.No + 1;
+  const unsigned HWd = (unsigned)(g.Hd * g.Wd);
+  const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
+  const int CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
+  extern __shared__ __align__(16) float s_ring[];   // [DEPTH][NF][WB_TILE_PX]
+  __shared__ const float* s_src[8];
+  __shared__ float* s_dsrc[8];
+  __shared__ const float* s_draw[8];
+  for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
+    const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
+    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
+    s_dsrc[tc] = a.d_input + ((size_t)b * g.T + c_t) * C * HWd;
+    s_draw[tc] = a.d_raw_output + (((size_t)b * g.Tc + tc) * g.Tp + tp) * CR * HWd;
+  }
+  __syncthreads();
+  float* my = s_ring + wb_tid();
+  const WbTileIter ti(g.Hd, g.Wd);
+  for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
+    const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
+    const int it = wb_tid();
+    const int Xr = tx0 + (it & (WB_TILE_W - 1)), Yr = ty0 + it / WB_TILE_W;
+    const bool active = Xr < g.Wd && Yr < g.Hd;
+    const float actf = active ? 1.f : 0.f;
+    const int X = min(Xr, g.Wd - 1), Y = min(Yr, g.Hd - 1);
+    const unsigned q = (unsigned)(Y * g.Wd + X);
+    const float gx = __ldg(d.xs_hd + X), gy = __ldg(d.ys_hd + Y);
+    const float D = fmaxf(__ldg(d.norm + ((size_t)b * g.Tp + tp) * HWd + q), 1e-12f);
+    const float* dof = a.d_output + ((size_t)b * g.Tp + tp) * C * HWd + q;
+    const float* dra = a.d_raw_alpha ? a.d_raw_alpha + ((size_t)b * g.Tp + tp) * HWd + q : nullptr;
+    const float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+    float S = 0.f;
+    for (int tc0 = 0; tc0 < g.Tc; tc0 += TG) {
+#if WB_PF_GB
+      if (tc0 + TG < g.Tc) {   // this pixel's flow / score lines of the next context group: their latency heads its prologue
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          const size_t pn = ((size_t)b * g.Tc + tc0 + TG + i) * g.Tp + tp;
+          wb_prefetch_l1(d.flow + pn * 2 * HWd + q); wb_prefetch_l1(d.flow + pn * 2 * HWd + HWd + q);
+          wb_prefetch_l1(d.score + pn * HWd + q);
+        }
+      }
+#endif
+      unsigned o0[TG], o1[TG];
+      float w[TG][4], nrm[TG], U[TG][4], Tq[TG][4];
+      const float* src[TG];
+      const float* drw[TG];
+      float* dsr[TG];
+      WB_UNROLL for (int i = 0; i < TG; ++i) {
+        WB_UNROLL for (int j = 0; j < 4; ++j) { U[i][j] = 0.f; Tq[i][j] = 0.f; }
+        const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
+        const float* fl = d.flow + pair * 2 * HWd + q;
+        const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        o0[i] = t2.o0; o1[i] = t2.o1;
+        WB_UNROLL for (int j = 0; j < 4; ++j) w[i][j] = t2.w[j];
+        nrm[i] = (__ldg(d.score + pair * HWd + q) + 1e-6f) / D;
+        src[i] = s_src[tc0 + i]; drw[i] = s_draw[tc0 + i] + q; dsr[i] = s_dsrc[tc0 + i];
+      }
+      bool skipR0[TG], skipR1[TG], mergeL0[TG], mergeL1[TG];   // see k_gather_bwd
+      WB_UNROLL for (int i = 0; i < TG; ++i) {
+        const int lane = wb_lane();
+        const unsigned n0 = __shfl_down_sync(0xffffffffu, o0[i], 1), n1 = __shfl_down_sync(0xffffffffu, o1[i], 1);
+        skipR0[i] = WB_GB_MERGE && lane < 31 && n0 == o0[i] + 1u;
+        skipR1[i] = WB_GB_MERGE && lane < 31 && n1 == o1[i] + 1u;
+        mergeL0[i] = __shfl_up_sync(0xffffffffu, (int)skipR0[i], 1) != 0 && lane > 0;
+        mergeL1[i] = __shfl_up_sync(0xffffffffu, (int)skipR1[i], 1) != 0 && lane > 0;
+      }
+      const bool first = tc0 == 0;
+      // stage `ch` -> ring slot ch % DEPTH
+#define WB_GB_ISSUE(ch_)                                                                          \
+      do {                                                                                          \
+        const unsigned off_ = (unsigned)(ch_) * HWd;                                                \
+        float* base_ = my + ((ch_) % DEPTH) * NF * WB_TILE_PX;                                      \
+        WB_UNROLL for (int i = 0; i < TG; ++i) {                                                    \
+          const float* p0_ = src[i] + off_ + o0[i];                                                 \
+          const float* p1_ = src[i] + off_ + o1[i];                                                 \
+          wb_cp4(base_ + (5 * i + 0) * WB_TILE_PX, p0_); wb_cp4(base_ + (5 * i + 1) * WB_TILE_PX, p0_ + 1); \
+          wb_cp4(base_ + (5 * i + 2) * WB_TILE_PX, p1_); wb_cp4(base_ + (5 * i + 3) * WB_TILE_PX, p1_ + 1); \
+          wb_cp4(base_ + (5 * i + 4) * WB_TILE_PX, drw[i] + off_);                                  \
+        }                                                                                           \
+        wb_cp4(base_ + (5 * TG) * WB_TILE_PX, dof + off_);                                          \
+        if (first) wb_cp4(base_ + (5 * TG + 1) * WB_TILE_PX, of + off_);                            \
+      } while (0)
+      WB_UNROLL for (int ch = 0; ch < DEPTH - 1; ++ch) { if (ch < C) WB_GB_ISSUE(ch); wb_cp_commit(); }
+      unsigned choff = 0u;
+#pragma unroll 1
+      for (int ch = 0; ch < C; ++ch) {
+        if (ch + DEPTH - 1 < C) WB_GB_ISSUE(ch + DEPTH - 1);
+        wb_cp_commit();
+        wb_cp_wait<DEPTH - 1>();
+        const float* base = my + (ch % DEPTH) * NF * WB_TILE_PX;
+        const float gO = actf * base[(5 * TG) * WB_TILE_PX];
+        if (first) S += gO * base[(5 * TG + 1) * WB_TILE_PX];
+        WB_UNROLL for (int i = 0; i < TG; ++i) {
+          const float v0 = base[(5 * i + 0) * WB_TILE_PX], v1 = base[(5 * i + 1) * WB_TILE_PX];
+          const float v2 = base[(5 * i + 2) * WB_TILE_PX], v3 = base[(5 * i + 3) * WB_TILE_PX];
+          const float gdt = actf * base[(5 * i + 4) * WB_TILE_PX];
+          const float go = gdt + nrm[i] * gO;
+          U[i][0] += gO * v0; U[i][1] += gO * v1; U[i][2] += gO * v2; U[i][3] += gO * v3;
+          Tq[i][0] += gdt * v0; Tq[i][1] += gdt * v1; Tq[i][2] += gdt * v2; Tq[i][3] += gdt * v3;
+          float* dl = dsr[i] + choff;
+          const float c1 = w[i][1] * go, c3 = w[i][3] * go;
+          const float r1 = __shfl_up_sync(0xffffffffu, c1, 1), r3 = __shfl_up_sync(0xffffffffu, c3, 1);
+          WB_RED(dl + o0[i], w[i][0] * go + (mergeL0[i] ? r1 : 0.f));
+          if (!skipR0[i]) WB_RED(dl + o0[i] + 1, c1);
+          WB_RED(dl + o1[i], w[i][2] * go + (mergeL1[i] ? r3 : 0.f));
+          if (!skipR1[i]) WB_RED(dl + o1[i] + 1, c3);
+        }
+        choff += HWd;
+      }
+#undef WB_GB_ISSUE
+      wb_cp_wait<0>();
+      if (!a.glue || !active) continue;
+      const float gOs = dra ? __ldg(dra) : 0.f;
+      if (first && dra) S += gOs * __ldg(of + choff);
+      WB_UNROLL for (int i = 0; i < TG; ++i) {
+        const size_t pair = ((size_t)b * g.Tc + tc0 + i) * g.Tp + tp;
+        const float* fl = d.flow + pair * 2 * HWd + q;
+        const WbTaps t = wb_taps(__fadd_rn(gx, __ldg(fl)), __fadd_rn(gy, __ldg(fl + HWd)), g.Wd, g.Hd);
+        const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
+        float cx[4], cy[4];
+        wb_pos4(t2, -t.wy0, t.wy0, -t.wy1, t.wy1, cx);
+        wb_pos4(t2, -t.wx0, -t.wx1, t.wx0, t.wx1, cy);
+        const float sc = nrm[i] * D - 1e-6f;
+        float G = U[i][0] * w[i][0] + U[i][1] * w[i][1] + U[i][2] * w[i][2] + U[i][3] * w[i][3];
+        float gix = 0.f, giy = 0.f;
+        WB_UNROLL for (int j = 0; j < 4; ++j) {
+          const float tj = Tq[i][j] + nrm[i] * U[i][j];
+          gix += tj * cx[j]; giy += tj * cy[j];
+        }
+        G += gOs * (sc * 2.f - 1.f);
+        const float* dfl = a.d_flow ? a.d_flow + pair * 2 * HWd + q : nullptr;
+        float* gl = a.glue + pair * 3 * HWd + q;
+        gl[0] = 2.f * nrm[i] * gOs + (G - S) / D;
+        gl[HWd] = (dfl ? __ldg(dfl) : 0.f) + gix * (0.5f * (float)g.Wd);
+        gl[2 * HWd] = (dfl ? __ldg(dfl + HWd) : 0.f) + giy * (0.5f * (float)g.Hd);
+      }
+    }
+  }
+}
+#endif  // !WB_HOST_EMU
 
 // grid = (red_ctas, B*Tp), block = 256 (one 32x8 pixel tile per iteration), rolled loop over the contexts.
 __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_BWD) k_layers_bwd(WbDecB a) {
@@ -670,7 +815,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_BWD) k_layers_bwd(Wb
   const int u = (int)d.pred_ts[c.tp];
   c.self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
   c.disocc_ch = (g.flags & WALDO_F_USE_DISOCC) != 0;
-  c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0); c.CRp = g.CRp;
+  c.TcR = g.Tc + (c.self ? 1 : 0); c.CR = c.C + c.L + (c.disocc_ch ? 1 : 0);
   c.need_layers = true;
   c.lowres_direct = (g.Hd == g.H);
   c.pairs_only = (g.flags & WALDO_F_OCC_PAIRS) != 0;
@@ -789,7 +934,7 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   }
   // ---- recompute the forward of this pixel
   float sm[NN];
-  if (c.filt && any_obj) wb_softmax_hd<NLC>(c.lyt_base + (size_t)q * g.Cp, Nl, sm);
+  if (c.filt && any_obj) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
   float aup[NA], av[NA], ell[NA];
   WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     av[s] = 0.f; aup[s] = 0.f; ell[s] = 1.f;
@@ -925,9 +1070,9 @@ WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   if (c.filt && any_obj && a.d_input && actf != 0.f) {   // softmax backward into the layout logits of this frame
     float dot = 0.f;
     WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dot += gsm[cc] * sm[cc];
-    float* o = a.d_input + (((size_t)b * g.T + t) * HWd + q) * g.Cp + 3;   // this pixel's record, layout logits from float 3
+    float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd + q;
     WB_UNROLL for (int cc = 0; cc < NN; ++cc)
-      if (NLC > 0 || cc < Nl) WB_RED(o + cc, sm[cc] * (gsm[cc] - dot));   // fire-and-forget reduction
+      if (NLC > 0 || cc < Nl) { WB_RED(o, sm[cc] * (gsm[cc] - dot)); o += HWd; }   // fire-and-forget reduction
   }
 }
 
@@ -1001,7 +1146,7 @@ WB_DEV void wb_lanes_prep_bwd(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
   if (filt_row) {
     const int X = min(tx0 + lane, g.Wd - 1);
     float sm[NN];
-    wb_softmax_hd<NLC>(c.lyt_base + (size_t)(Y * g.Wd + X) * g.Cp, Nl, sm);
+    wb_softmax_hd<NLC>(c.lyt_base, HWd, (unsigned)(Y * g.Wd + X), Nl, sm);
     WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) s_sm[cc * WB_SM_ROW + lane] = sm[cc];
     __syncwarp();
   }
@@ -1077,9 +1222,11 @@ WB_DEV void wb_lanes_prep_bwd(const WbDecB& a, const WbPrepBwdCtx& c, const WbCo
         }
         WB_UNROLL for (int o = PPW; o < 32; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
         if (actf != 0.f) {
-          float* o = a.d_input + (((size_t)b * g.T + t) * HWd + q) * g.Cp + 3 + cbase;
-          WB_UNROLL for (int i = 0; i < NS; ++i)
-            if (cbase + i < Nl) WB_RED(o + i, smc[i] * (v[i] - dot));   // fire-and-forget reduction
+          float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3 + cbase) * HWd + q;
+          WB_UNROLL for (int i = 0; i < NS; ++i) {
+            if (cbase + i < Nl) WB_RED(o, smc[i] * (v[i] - dot));   // fire-and-forget reduction
+            o += HWd;
+          }
         }
       }
     }
@@ -1147,7 +1294,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(
   c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
   c.s_accp = s_redp[wb_warp()];
   const float rlo = (float)g.H / (float)g.Hd;
-  c.lyt_base = d.input + ((size_t)c.b * g.T + c.t) * c.HWd * g.Cp;   // records of this frame
+  c.lyt_base = d.input + (((size_t)c.b * g.T + c.t) * g.C + 3) * c.HWd;
   c.alo = d.a_lo + ((size_t)c.b * g.Tw + c.t) * L * c.HW;
   const uint32_t* live = d.live_ctx + ((size_t)c.b * g.Tw + c.t) * c.HW;
   const WbTileIter ti(g.Hd, g.Wd);
@@ -1302,12 +1449,12 @@ __global__ void __launch_bounds__(256, WB_OCC_PROF_BWD) k_class_profile_bwd(WbDe
         const float* pl = d.lyt_lo + ((size_t)b * g.Tw + t) * Nl * HW + p;
         WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) lyt[c] = __ldg(pl + (size_t)c * HW);
       } else {   // same arithmetic as wb_lyt_lo
-        const float* base = d.input + ((size_t)b * g.T + t) * HWd * g.Cp;
-        float r00[NN], r01[NN], r10[NN], r11[NN];
-        wb_lyt_rec<NLC>(base + hd00 * g.Cp, Nl, r00); wb_lyt_rec<NLC>(base + hd01 * g.Cp, Nl, r01);
-        wb_lyt_rec<NLC>(base + hd10 * g.Cp, Nl, r10); wb_lyt_rec<NLC>(base + hd11 * g.Cp, Nl, r11);
+        const float* base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
         WB_UNROLL for (int c = 0; c < NN; ++c)
-          if (NLC > 0 || c < Nl) lyt[c] = wb_lerp2(r00[c], r01[c], r10[c], r11[c], ax, ay);
+          if (NLC > 0 || c < Nl) {
+            const float* pl = base + c * HWd;
+            lyt[c] = wb_lerp2(__ldg(pl + hd00), __ldg(pl + hd01), __ldg(pl + hd10), __ldg(pl + hd11), ax, ay);
+          }
       }
       if (wcls) {   // same arithmetic as wb_softmax
         float mx = lyt[0];
@@ -1339,15 +1486,15 @@ __global__ void __launch_bounds__(256, WB_OCC_PROF_BWD) k_class_profile_bwd(WbDe
         WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { glyt[c] += sm[c] * (gsmx[c] - dot); s_sm[i][c] = sm[c]; }
       }
       if (a.d_input) {   // transpose of the bilinear down-sampling
-        float* base = a.d_input + ((size_t)b * g.T + t) * HWd * g.Cp + 3;
-        float* q00 = base + hd00 * g.Cp, *q01 = base + hd01 * g.Cp, *q10 = base + hd10 * g.Cp, *q11 = base + hd11 * g.Cp;
+        float* base = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
         WB_UNROLL for (int c = 0; c < NN; ++c) {
           if (NLC > 0 || c < Nl) {
+            float* pl = base + (size_t)c * HWd;
             const float gv = glyt[c];
-            WB_RED_NZ(q00 + c, gv * ax.l0 * ay.l0);
-            WB_RED_NZ(q01 + c, gv * ax.l1 * ay.l0);
-            WB_RED_NZ(q10 + c, gv * ax.l0 * ay.l1);
-            WB_RED_NZ(q11 + c, gv * ax.l1 * ay.l1);
+            WB_RED_NZ(pl + hd00, gv * ax.l0 * ay.l0);
+            WB_RED_NZ(pl + hd01, gv * ax.l1 * ay.l0);
+            WB_RED_NZ(pl + hd10, gv * ax.l0 * ay.l1);
+            WB_RED_NZ(pl + hd11, gv * ax.l1 * ay.l1);
           }
         }
       }
@@ -1519,7 +1666,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   // ---- deterministic accumulation: sizes of the scatter targets, arena checks, conversion helper
   const long long HWdl = (long long)g.Hd * g.Wd;
   const bool self_ctx = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
-  const long long n_input = (long long)g.B * g.T * g.Cp * HWdl, n_alpha = (long long)g.B * g.Tw * L * HWdl;
+  const long long n_input = (long long)g.B * g.T * g.C * HWdl, n_alpha = (long long)g.B * g.Tw * L * HWdl;
   const long long n_f_lo = (long long)g.B * g.Tc * g.Tp * L * HW * 2, n_a_lo = (long long)g.B * g.Tw * L * HW;
   const long long n_tgo = (long long)g.B * g.T * g.No * g.Ho * g.Wo * 2, n_sgo = (long long)g.B * g.T * g.No * HW * 2;
   const long long n_gbg = (long long)g.B * g.T * HW * 2, n_oa = (long long)g.B * g.No * g.Ho * g.Wo, n_ba = (long long)g.B * HW;
@@ -1546,10 +1693,10 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   if (st_gather) {   // fixed-point unit from the largest upstream gradient magnitude (a maximum is order-independent)
     WB_LAUNCH(k_det_clear, dim3(1), dim3(32), 0, st, a.det_scale);
     WB_BLAUNCHED();
-    const int TcRd = g.Tc + (self_ctx ? 1 : 0);
+    const int TcRd = g.Tc + (self_ctx ? 1 : 0), CRd = g.C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
     const float* up[5] = {a.d_output, a.d_raw_alpha, a.d_raw_output, a.d_flow, a.d_alpha};
-    const long long un[5] = {(long long)g.B * g.Tp * g.Cp * HWdl, (long long)g.B * g.Tp * HWdl,
-                             (long long)g.B * TcRd * g.Tp * g.CRp * HWdl, (long long)g.B * g.Tc * g.Tp * 2 * HWdl, n_alpha};
+    const long long un[5] = {(long long)g.B * g.Tp * g.C * HWdl, (long long)g.B * g.Tp * HWdl,
+                             (long long)g.B * TcRd * g.Tp * CRd * HWdl, (long long)g.B * g.Tc * g.Tp * 2 * HWdl, n_alpha};
     for (int i = 0; i < 5; ++i) {
       if (!up[i]) continue;
       WB_LAUNCH(k_det_absmax, dim3(wb_blocks_b(un[i], 256 * 8) > 1184 ? 1184 : wb_blocks_b(un[i], 256 * 8)), dim3(256), 0, st, up[i], un[i], a.det_scale);
@@ -1567,7 +1714,17 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
     WbDecB ag = a;
     if (!need_layers) ag.glue = nullptr;
     const dim3 ggrid(wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX) > 1024 ? 1024 : wb_blocks_b((long long)g.Hd * g.Wd, WB_TILE_PX), g.B * g.Tp);
-    WB_LAUNCH(k_gather_bwd, ggrid, dim3(WB_TILE_PX), 0, st, ag);
+    const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+    const bool fast = g.Tc % WB_GB_TG == 0 && !self && a.d_input && a.d_raw_output && a.d_output;
+#if !defined(WB_HOST_EMU) && WB_GB_ASYNC
+    if (fast) {
+      const size_t ring = (size_t)WB_GB_DEPTH * (5 * WB_GB_TG + 2) * WB_TILE_PX * sizeof(float);
+      cudaFuncSetAttribute(k_gather_bwd_async<WB_GB_TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);   // > 48 KB: opt in
+      WB_LAUNCH((k_gather_bwd_async<WB_GB_TG>), ggrid, dim3(WB_TILE_PX), ring, st, ag);
+    } else
+#endif
+    if (fast) WB_LAUNCH((k_gather_bwd<WB_GB_TG, true>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
+    else WB_LAUNCH((k_gather_bwd<2, false>), ggrid, dim3(WB_TILE_PX), 0, st, ag);
     WB_BLAUNCHED();
   }
   // 1b. HD layer backward

@@ -4,55 +4,54 @@
 // models/synthesizer.py:444 (input = cat([vid, lyt], dim=2)).
 //   input[f, 0:3]   = ((rgb / 255) - 0.5) / 0.5          (or a copy of an fp32 frame that is already normalised)
 //   input[f, 3 + c] = label == c ? on : off               (on = 5, off = -5; labels >= Nl give all-off)
-// The output is written as channels-last records (include/waldo_b200.h): `input` (n, HW, Cp).
+// One thread handles 4 consecutive pixels: one 32-bit load per byte plane, one 128-bit store per output plane.
 #pragma once
 #include "wb_common.cuh"
 #include "../../include/waldo_b200.h"
 
 WB_DEV float wb_norm_u8(unsigned v) { return __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), 0.5f), 0.5f); }
 
-// One thread per pixel builds the whole channels-last record (Cp floats, a multiple of 4: 128-bit stores, padding zeroed).
 __global__ void __launch_bounds__(256) k_pack_input(waldo_pack_input_t p) {
-  const int C = 3 + p.Nl, Cp = p.Cp;
+  const int C = 3 + p.Nl;
   const size_t HW = (size_t)p.HW;
+  const size_t nq = (HW + 3) / 4;                     // groups of 4 pixels per frame
+  const bool vec = (HW & 3) == 0;
   const int f = blockIdx.y;
-  for (size_t q = (size_t)blockIdx.x * wb_nthr() + wb_tid(); q < HW; q += (size_t)gridDim.x * wb_nthr()) {
-    const unsigned lab = p.label[(size_t)f * HW + q];
-    float rgb[3];
-    WB_UNROLL for (int c = 0; c < 3; ++c)
-      rgb[c] = p.rgb_u8 ? wb_norm_u8(p.rgb_u8[((size_t)f * 3 + c) * HW + q]) : p.rgb_f32[((size_t)f * 3 + c) * HW + q];
-    float* out = p.input + ((size_t)f * HW + q) * Cp;
-    for (int j = 0; j < Cp / 4; ++j) {
-      float4 v;
-      WB_UNROLL for (int e = 0; e < 4; ++e) {
-        const int ch = 4 * j + e;
-        const float x = ch < 3 ? (ch == 0 ? rgb[0] : (ch == 1 ? rgb[1] : rgb[2])) : (ch < C ? (lab == (unsigned)(ch - 3) ? p.on : p.off) : 0.f);
-        wb_set(v, e, x);
+  for (size_t gq = (size_t)blockIdx.x * wb_nthr() + wb_tid(); gq < nq; gq += (size_t)gridDim.x * wb_nthr()) {
+    const size_t q = gq * 4;
+    const int npx = (int)(HW - q < 4 ? HW - q : 4);
+    float* out = p.input + (size_t)f * C * HW + q;
+    unsigned lab[4] = {255u, 255u, 255u, 255u};
+    if (vec) {
+      const unsigned w = *reinterpret_cast<const unsigned*>(p.label + (size_t)f * HW + q);
+      WB_UNROLL for (int i = 0; i < 4; ++i) lab[i] = (w >> (8 * i)) & 255u;
+    } else {
+      for (int i = 0; i < npx; ++i) lab[i] = p.label[(size_t)f * HW + q + i];
+    }
+    for (int c = 0; c < 3; ++c) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.rgb_u8) {
+        const uint8_t* s = p.rgb_u8 + ((size_t)f * 3 + c) * HW + q;
+        if (vec) {
+          const unsigned w = *reinterpret_cast<const unsigned*>(s);
+          WB_UNROLL for (int i = 0; i < 4; ++i) v[i] = wb_norm_u8((w >> (8 * i)) & 255u);
+        } else {
+          for (int i = 0; i < npx; ++i) v[i] = wb_norm_u8(s[i]);
+        }
+      } else {
+        const float* s = p.rgb_f32 + ((size_t)f * 3 + c) * HW + q;
+        for (int i = 0; i < npx; ++i) v[i] = s[i];
       }
-      wb_st4(out + 4 * j, v);
+      float* o = out + (size_t)c * HW;
+      if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      else for (int i = 0; i < npx; ++i) o[i] = v[i];
     }
-  }
-}
-
-// Generic relayout: planar (n, C, HW) fp32 -> channels-last records (n, HW, Cp) with zeroed padding, and back.  Used where a
-// caller hands over (or wants) an NCHW-contiguous tensor; the path itself only ever touches records.
-__global__ void __launch_bounds__(256) k_to_records(int n, int C, int Cp, long long HW, const float* __restrict__ src, float* __restrict__ dst) {
-  const int f = blockIdx.y;
-  for (long long q = (long long)blockIdx.x * wb_nthr() + wb_tid(); q < HW; q += (long long)gridDim.x * wb_nthr()) {
-    float* out = dst + ((size_t)f * HW + q) * Cp;
-    const float* in = src + (size_t)f * C * HW + q;
-    for (int j = 0; j < Cp / 4; ++j) {
-      float4 v;
-      WB_UNROLL for (int e = 0; e < 4; ++e) wb_set(v, e, 4 * j + e < C ? __ldg(in + (size_t)(4 * j + e) * HW) : 0.f);
-      wb_st4(out + 4 * j, v);
+    for (int c = 0; c < p.Nl; ++c) {
+      float* o = out + (size_t)(3 + c) * HW;
+      const float v0 = lab[0] == (unsigned)c ? p.on : p.off, v1 = lab[1] == (unsigned)c ? p.on : p.off;
+      const float v2 = lab[2] == (unsigned)c ? p.on : p.off, v3 = lab[3] == (unsigned)c ? p.on : p.off;
+      if (vec) *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
+      else { const float vv[4] = {v0, v1, v2, v3}; for (int i = 0; i < npx; ++i) o[i] = vv[i]; }
     }
-  }
-}
-__global__ void __launch_bounds__(256) k_from_records(int n, int C, int Cp, long long HW, const float* __restrict__ src, float* __restrict__ dst) {
-  const int f = blockIdx.y;
-  for (long long q = (long long)blockIdx.x * wb_nthr() + wb_tid(); q < HW; q += (long long)gridDim.x * wb_nthr()) {
-    const float* in = src + ((size_t)f * HW + q) * Cp;
-    float* out = dst + (size_t)f * C * HW + q;
-    for (int c = 0; c < C; ++c) out[(size_t)c * HW] = __ldg(in + c);
   }
 }

@@ -51,10 +51,12 @@ WB_DEV void wb_lyt_lo(const WbDec& d, int b, int t, int p, float* lyt /*[Nl]*/) 
   const float r = (float)g.Hd / (float)g.H;   // = 1 / (1/scale_hd)
   WbAxis ay = wb_axis(y, r, g.Hd), ax = wb_axis(x, r, g.Wd);
   const size_t HWd = (size_t)g.Hd * g.Wd;
-  const float* base = d.input + ((size_t)b * g.T + t) * HWd * g.Cp + 3;   // records of this frame, layout logits from float 3
-  const float* p00 = base + ((size_t)ay.i0 * g.Wd + ax.i0) * g.Cp, *p01 = base + ((size_t)ay.i0 * g.Wd + ax.i1) * g.Cp;
-  const float* p10 = base + ((size_t)ay.i1 * g.Wd + ax.i0) * g.Cp, *p11 = base + ((size_t)ay.i1 * g.Wd + ax.i1) * g.Cp;
-  for (int c = 0; c < g.Nl; ++c) lyt[c] = wb_lerp2(__ldg(p00 + c), __ldg(p01 + c), __ldg(p10 + c), __ldg(p11 + c), ax, ay);
+  const float* base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
+  for (int c = 0; c < g.Nl; ++c) {
+    const float* pl = base + c * HWd;
+    lyt[c] = wb_lerp2(__ldg(pl + (size_t)ay.i0 * g.Wd + ax.i0), __ldg(pl + (size_t)ay.i0 * g.Wd + ax.i1),
+                      __ldg(pl + (size_t)ay.i1 * g.Wd + ax.i0), __ldg(pl + (size_t)ay.i1 * g.Wd + ax.i1), ax, ay);
+  }
 }
 
 WB_DEV void wb_softmax(const float* x, float* y, int n) {
@@ -64,23 +66,6 @@ WB_DEV void wb_softmax(const float* x, float* y, int n) {
   for (int c = 0; c < n; ++c) { y[c] = expf(x[c] - mx); s += y[c]; }
   float inv = 1.f / s;
   for (int c = 0; c < n; ++c) y[c] *= inv;
-}
-
-// the Nl layout logits of one channels-last input record (floats 3 .. 3+Nl): whole 16-byte chunks when the class count is
-// known at compile time (LDG.E.128), scalar loads otherwise
-template <int NLC>
-WB_DEV void wb_lyt_rec(const float* __restrict__ rec, int Nl, float* lyt) {
-  if (NLC > 0) {
-    constexpr int NCH = (3 + (NLC > 0 ? NLC : 1) + 3) / 4;
-    float buf[NCH * 4];
-    WB_UNROLL for (int j = 0; j < NCH; ++j) {
-      const float4 v = wb_ld4(rec + 4 * j);
-      buf[4 * j] = v.x; buf[4 * j + 1] = v.y; buf[4 * j + 2] = v.z; buf[4 * j + 3] = v.w;
-    }
-    WB_UNROLL for (int c = 0; c < (NLC > 0 ? NLC : 1); ++c) lyt[c] = buf[3 + c];
-  } else {
-    for (int c = 0; c < Nl; ++c) lyt[c] = __ldg(rec + 3 + c);
-  }
 }
 
 // ------------------------------------------------------------------ B2: class profile partial sums (lvd.py:735-742)
@@ -123,14 +108,14 @@ __global__ void __launch_bounds__(256) k_class_profile(WbDec d) {
       {   // same arithmetic as wb_lyt_lo
         const int y = p / g.W, x = p - y * g.W;
         const WbAxis ay = wb_axis(y, r, g.Hd), ax = wb_axis(x, r, g.Wd);
-        const float* base = d.input + ((size_t)b * g.T + t) * HWd * g.Cp;   // records of this frame
-        float r00[NN], r01[NN], r10[NN], r11[NN];
-        wb_lyt_rec<NLC>(base + ((size_t)ay.i0 * g.Wd + ax.i0) * g.Cp, Nl, r00);
-        wb_lyt_rec<NLC>(base + ((size_t)ay.i0 * g.Wd + ax.i1) * g.Cp, Nl, r01);
-        wb_lyt_rec<NLC>(base + ((size_t)ay.i1 * g.Wd + ax.i0) * g.Cp, Nl, r10);
-        wb_lyt_rec<NLC>(base + ((size_t)ay.i1 * g.Wd + ax.i1) * g.Cp, Nl, r11);
+        const float* base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
+        const size_t h00 = (size_t)ay.i0 * g.Wd + ax.i0, h01 = (size_t)ay.i0 * g.Wd + ax.i1;
+        const size_t h10 = (size_t)ay.i1 * g.Wd + ax.i0, h11 = (size_t)ay.i1 * g.Wd + ax.i1;
         WB_UNROLL for (int c = 0; c < NN; ++c)
-          if (NLC > 0 || c < Nl) lyt[c] = wb_lerp2(r00[c], r01[c], r10[c], r11[c], ax, ay);
+          if (NLC > 0 || c < Nl) {
+            const float* pl = base + c * HWd;
+            lyt[c] = wb_lerp2(__ldg(pl + h00), __ldg(pl + h01), __ldg(pl + h10), __ldg(pl + h11), ax, ay);
+          }
       }
       if (wcls) {   // same arithmetic as wb_softmax
         float mx = lyt[0];
@@ -242,10 +227,11 @@ struct WbPrepCtx {
 
 // softmax of the HD layout logits of pixel q (lvd.py:744).  NLC = compile-time class count (0: run-time Nl).
 template <int NLC>
-WB_DEV void wb_softmax_hd(const float* __restrict__ rec /* this pixel's input record */, int Nl, float* sm) {
+WB_DEV void wb_softmax_hd(const float* __restrict__ lyt_base, unsigned HWd, unsigned q, int Nl, float* sm) {
   constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
   float lyt[NN];
-  wb_lyt_rec<NLC>(rec, Nl, lyt);
+  const float* p = lyt_base + q;
+  WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { lyt[c] = __ldg(p); p += HWd; }
   float mx = lyt[0];
   WB_UNROLL for (int c = 1; c < NN; ++c) if (NLC > 0 || c < Nl) mx = fmaxf(mx, lyt[c]);
   float s = 0.f;
@@ -263,7 +249,7 @@ WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, unsig
   const unsigned HWd = (unsigned)c.HWd;
   const WbIdx<NA> ix = wb_idx<NA>(wm);
   float sm[NN];
-  if (c.filt && (wm >> 1)) wb_softmax_hd<NLC>(c.lyt_base + (size_t)q * g.Cp, Nl, sm);
+  if (c.filt && (wm >> 1)) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
   float a[NA];
   WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     a[s] = 0.f;
@@ -309,7 +295,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_FWD) k_alpha_prep(WbDe
   __syncthreads();
   c.s_P = s_P; c.s_occ = s_occ;
   const float r = (float)g.H / (float)g.Hd;   // 1 / scale_hd
-  c.lyt_base = d.input + ((size_t)c.b * g.T + c.t) * c.HWd * g.Cp;   // records of this frame
+  c.lyt_base = d.input + (((size_t)c.b * g.T + c.t) * g.C + 3) * c.HWd;
   c.alo = d.a_lo + ((size_t)c.b * g.Tw + c.t) * c.L * c.HW;
   const uint32_t* live = d.live_ctx + ((size_t)c.b * g.Tw + c.t) * c.HW;
   c.out = d.alpha + ((size_t)c.b * g.Tw + c.t) * c.L * c.HWd;

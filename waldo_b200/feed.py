@@ -49,12 +49,7 @@ class DevicePrefetcher:
                 for k, t in host.items():
                     buf = dev.get(k)
                     if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-                        if k == "input" and t.dim() == 5 and t.dtype == torch.float32:
-                            # an fp32 `input` shipped whole: land it in channels-last records (what the path reads)
-                            B, T, Cc, Hd, Wd = t.shape
-                            buf = Fn.records_view(torch.zeros(B, T, Hd, Wd, Fn.ceil4(Cc + 1), device=self.device), Cc)
-                        else:
-                            buf = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                        buf = torch.empty(t.shape, dtype=t.dtype, device=self.device)
                         dev[k] = buf
                     buf.copy_(t, non_blocking=True)
                     out[k] = buf
@@ -62,10 +57,9 @@ class DevicePrefetcher:
                     inp = dev.get("input")
                     B, T, _, Hd, Wd = out["rgb"].shape
                     if inp is None or inp.shape != (B, T, 3 + self.num_lyt, Hd, Wd):
-                        inp = None
-                    inp = Fn.pack_input(out["rgb"], out["label"], self.num_lyt, out=inp)
-                    dev["input"] = inp
-                    out["input"] = inp
+                        inp = torch.empty(B, T, 3 + self.num_lyt, Hd, Wd, device=self.device, dtype=torch.float32)
+                        dev["input"] = inp
+                    out["input"] = Fn.pack_input(out["rgb"], out["label"], self.num_lyt, out=inp)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
             self.ready[s] = ev

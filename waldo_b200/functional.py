@@ -23,82 +23,6 @@ def _c(t: Optional[torch.Tensor], dtype=torch.float32):
     return t.contiguous()
 
 
-# ===================================================================================== channels-last records
-def ceil4(n: int) -> int:
-    return (n + 3) // 4 * 4
-
-
-def records_view(buf: torch.Tensor, C: int) -> torch.Tensor:
-    """Record buffer (..., Hd, Wd, Cp) -> the reference's logical tensor (..., C, Hd, Wd) as a channel-stride-1 view of the
-    same memory (include/waldo_b200.h "Data layout")."""
-    nd = buf.dim()
-    return buf[..., :C].permute(*range(nd - 3), nd - 1, nd - 3, nd - 2)
-
-
-def find_records(t: torch.Tensor):
-    """If the logical tensor t (..., C, Hd, Wd) already IS a view of a record buffer (channel stride 1, pixel stride Cp a
-    multiple of 4, frames packed back to back, padding floats present in the storage) return (buffer (..., Hd, Wd, Cp), Cp);
-    else None."""
-    if t.dim() < 3 or t.dtype != torch.float32:
-        return None
-    *lead, C, Hd, Wd = t.shape
-    st = t.stride()
-    Cp = st[-1] if Wd > 1 else (st[-2] // max(Wd, 1) if Hd > 1 else ceil4(C))
-    if st[-3] != 1 and C > 1:
-        return None
-    if Cp < C or Cp % 4 or (Wd > 1 and st[-1] != Cp) or (Hd > 1 and st[-2] != Wd * Cp):
-        return None
-    expect = Hd * Wd * Cp
-    for size, stride in zip(reversed(lead), reversed(st[:-3])):
-        if size > 1 and stride != expect:
-            return None
-        expect *= size
-    if t.data_ptr() % 16:
-        return None
-    need = (t.storage_offset() + expect) * 4
-    if t.untyped_storage().nbytes() < need:
-        return None
-    return t.as_strided((*lead, Hd, Wd, Cp), (*[s_ for s_ in st[:-3]], Wd * Cp, Cp, 1)), Cp
-
-
-def as_records(t: torch.Tensor, Cp: Optional[int] = None):
-    """Logical (..., C, Hd, Wd) fp32 tensor -> record buffer (..., Hd, Wd, Cp).  Zero-copy when t already is a view of one
-    with the wanted record length (tensors produced by this package, channels_last-style gradients); otherwise ONE
-    relayout pass on the device (waldo_to_records)."""
-    t = t if t.dtype == torch.float32 else t.float()
-    hit = find_records(t)
-    if hit is not None and (Cp is None or hit[1] == Cp):
-        return hit
-    *lead, C, Hd, Wd = t.shape
-    Cp = Cp or ceil4(C)
-    src = t.contiguous()
-    buf = torch.empty(*lead, Hd, Wd, Cp, device=t.device, dtype=torch.float32)
-    n = 1
-    for v in lead:
-        n *= v
-    lib = L.load()
-    with L.device_of(t.device):
-        L.check(lib.waldo_to_records(n, C, Cp, Hd * Wd, L.ptr(src, name="planar tensor"), L.ptr(buf), L.stream_of(t)), "to_records")
-    return buf, Cp
-
-
-def to_planar(t: torch.Tensor) -> torch.Tensor:
-    """A contiguous (..., C, Hd, Wd) copy of a logical tensor (for consumers that insist on NCHW-contiguous memory)."""
-    hit = find_records(t)
-    if hit is None:
-        return t.contiguous()
-    buf, Cp = hit
-    *lead, C, Hd, Wd = t.shape
-    out = torch.empty(*lead, C, Hd, Wd, device=t.device, dtype=torch.float32)
-    n = 1
-    for v in lead:
-        n *= v
-    lib = L.load()
-    with L.device_of(t.device):
-        L.check(lib.waldo_from_records(n, C, Cp, Hd * Wd, L.ptr(buf), L.ptr(out), L.stream_of(t)), "from_records")
-    return out
-
-
 # ===================================================================================== a-1 TPS
 class _TpsEval(torch.autograd.Function):
     """TPSWarp.forward, models/modules/warp.py:49-55."""
@@ -272,9 +196,8 @@ def _geom(spec: DecodeSpec, B, T, Tc, Tp, Nl, has_cls):
         flags |= L.F_USE_DISOCC
     if spec.occ_pairs_only:
         flags |= L.F_OCC_PAIRS
-    C_ = 3 + Nl
-    return L.Geom(B, T, Tw, Tc, Tp, spec.num_obj, Nl, C_, spec.H, spec.W, spec.Hd, spec.Wd, spec.Ho, spec.Wo,
-                  flags, float(spec.min_cls), ceil4(C_ + 1), ceil4(C_ + spec.num_obj + 1 + (1 if spec.use_disocc else 0)))
+    return L.Geom(B, T, Tw, Tc, Tp, spec.num_obj, Nl, 3 + Nl, spec.H, spec.W, spec.Hd, spec.Wd, spec.Ho, spec.Wo,
+                  flags, float(spec.min_cls))
 
 
 # Deterministic gradients (BASELINE north star: "deterministic gradient accumulation ... instead of global atomics").
@@ -350,12 +273,12 @@ def _staged(fn, arg, stream, what, dev):
 
 def _fwd_struct(g, prof_ctas, t):
     (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part, prof_sum, prof_p,
-     f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score, lyt_lo, apass) = t
+     f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score, lyt_lo) = t
     return L.DecodeFwd(g, L.ptr(inp_c, name="input"), L.ptr(tgo_c), L.ptr(sgo_c), L.ptr(tgb_c), L.ptr(sgb_c), L.ptr(occ_c),
                        L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
                        L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
                        L.ptr(prof_p), L.ptr(lyt_lo), L.ptr(f_lo), L.ptr(s_lo), L.ptr(live_ctx, torch.int32), L.ptr(live_pred, torch.int32),
-                       L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full), L.ptr(apass), L.ptr(norm), L.ptr(score), 0)
+                       L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full), L.ptr(norm), L.ptr(score), 0)
 
 
 _ts_checked = {}
@@ -386,13 +309,10 @@ class _Decode(torch.autograd.Function):
     def forward(ctx, spec, ctx_ts, pred_ts, xs_hd, ys_hd, inp, tgo, sgo, tgb, sgb, occ, obj_alpha, bg_alpha, cls):
         lib = L.load()
         ctx.set_materialize_grads(False)   # unused outputs must not cost a zero-filled HD tensor each
-        tgo_c, sgo_c, tgb_c, sgb_c = (_c(t.detach()) for t in (tgo, sgo, tgb, sgb))
+        inp_c, tgo_c, sgo_c, tgb_c, sgb_c = (_c(t.detach()) for t in (inp, tgo, sgo, tgb, sgb))
         occ_c, oa_c, ba_c = _c(occ.detach()), _c(obj_alpha.detach()), _c(bg_alpha.detach())
         cls_c = _c(cls.detach()) if cls is not None else None
-        if inp.dim() != 5:
-            raise RuntimeError(f"waldo_b200.decode: input must be (B, T, C, Hd, Wd), got {tuple(inp.shape)}")
-        B, T, Cc, Hd, Wd = inp.shape
-        inp_c, _ = as_records(inp.detach(), ceil4(Cc + 1))      # (B, T, Hd, Wd, Cp): zero-copy for pack_input's output
+        B, T, Cc, Hd, Wd = inp_c.shape
         Tc, Tp = ctx_ts.shape[1], pred_ts.shape[0]
         Nl = Cc - 3
         if (Hd, Wd) != (spec.Hd, spec.Wd):
@@ -437,16 +357,14 @@ class _Decode(torch.autograd.Function):
         live_pred = torch.empty(B, Tp, spec.H, spec.W, device=dev, dtype=torch.int32)
         alpha = torch.empty(B, g.Tw, Lr, Hd, Wd, **f32)
         flow = torch.empty(B, Tc, Tp, 2, Hd, Wd, **f32)
-        raw = torch.empty(B, TcR, Tp, Hd, Wd, g.CRp, **f32)     # channels-last records; handed out as (B,TcR,Tp,CR,Hd,Wd) views
-        out_full = torch.empty(B, Tp, Hd, Wd, g.Cp, **f32)
-        npass = ceil4(Cc) - Cc
-        apass = torch.empty(B, Tc, Tp, npass, Hd, Wd, **f32) if npass else None
+        raw = torch.empty(B, TcR, Tp, CR, Hd, Wd, **f32)
+        out_full = torch.empty(B, Tp, Cc + 1, Hd, Wd, **f32)
         norm = torch.empty(B, Tp, Hd, Wd, **f32)
         score = torch.empty(B, Tc, Tp, Hd, Wd, **f32)
         # low-res layout logits: kept only when a backward will follow (it saves re-reading the HD layout planes)
         lyt_lo = torch.empty(B, g.Tw, Nl, spec.H, spec.W, **f32) if (spec.use_filter and any(ctx.needs_input_grad)) else None
         tensors = (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
-                   prof_sum, prof_p, f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score, lyt_lo, apass)
+                   prof_sum, prof_p, f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score, lyt_lo)
         a = _fwd_struct(g, prof_ctas, tensors)
         _staged(lib.waldo_decode_fwd, a, L.stream_of(inp_c), "decode_fwd", dev=dev)
         # saved through save_for_backward (NOT as ctx attributes): four of them are outputs of this very Function, and an
@@ -455,8 +373,7 @@ class _Decode(torch.autograd.Function):
         ctx.present = [t is not None for t in tensors]
         ctx.geom, ctx.prof_ctas = g, prof_ctas
         ctx.shapes = dict(obj_alpha=obj_alpha.shape, bg_alpha=bg_alpha.shape)
-        full = records_view(out_full, Cc + 1)
-        return full[:, :, :Cc], full[:, :, Cc:], records_view(raw, CR), flow, alpha
+        return out_full[:, :, :Cc], out_full[:, :, Cc:], raw, flow, alpha
 
     @staticmethod
     def backward(ctx, d_output, d_raw_alpha, d_raw, d_flow, d_alpha):
@@ -501,10 +418,7 @@ class _Decode(torch.autograd.Function):
         d_cls_s = d_cls
         if d_cls_s is None and cls_c is not None and chain and filt and not (g.flags & L.F_WEIGHT_CLS):
             d_cls_s = None   # P = cls path: nothing to propagate unless cls needs grad
-        grads_in = [as_records(d_output, g.Cp)[0] if d_output is not None else None,
-                    _c(d_raw_alpha) if d_raw_alpha is not None else None,
-                    as_records(d_raw, g.CRp)[0] if d_raw is not None else None,
-                    _c(d_flow) if d_flow is not None else None, _c(d_alpha) if d_alpha is not None else None]
+        grads_in = [_c(t) if t is not None else None for t in (d_output, d_raw_alpha, d_raw, d_flow, d_alpha)]
         b = L.DecodeBwd(fwd, L.ptr(grads_in[0]), L.ptr(grads_in[1]), L.ptr(grads_in[2]), L.ptr(grads_in[3]), L.ptr(grads_in[4]),
                         L.ptr(d_input), L.ptr(d_tgo_s), L.ptr(d_sgo_s), L.ptr(d_tgb_s), L.ptr(d_sgb_s), L.ptr(d_occ),
                         L.ptr(d_oa), L.ptr(d_ba), L.ptr(d_cls_s), L.ptr(d_alpha_acc), L.ptr(d_f_lo), L.ptr(d_a_lo),
@@ -519,8 +433,6 @@ class _Decode(torch.autograd.Function):
             d_oa = d_oa.view(ctx.shapes["obj_alpha"])
         if d_ba is not None:
             d_ba = d_ba.view(ctx.shapes["bg_alpha"])
-        if d_input is not None:
-            d_input = records_view(d_input, g.C)     # logical (B, T, C, Hd, Wd) view of the record buffer
         return (None, None, None, None, None, d_input, d_tgo, d_sgo, d_tgb, d_sgb, d_occ, d_oa, d_ba, d_cls)
 
 
@@ -537,15 +449,14 @@ class _WifFuse(torch.autograd.Function):
     @staticmethod
     def forward(ctx, raw_output, unet_out, ab):
         lib = L.load()
-        u = _c(unet_out.detach())
-        B, Tc, Tp, Cr, H, W = raw_output.shape
-        r, CRp = as_records(raw_output.detach())            # (B, Tc, Tp, H, W, CRp): zero-copy for decode_output's raw_output
+        r, u = _c(raw_output.detach()), _c(unet_out.detach())
+        B, Tc, Tp, Cr, H, W = r.shape
         if u.shape[:3] != (B, Tp, Tc) or u.shape[3] != 4 + (1 if ab else 0):
             raise RuntimeError(f"waldo_b200.wif_fuse: unet_out shape {tuple(u.shape)} does not match raw_output {tuple(r.shape)}")
         if Cr < 5:   # wif.py:53 reads INPUT channel 4 as the gate; the backward writes d raw_output channels 0..4
             raise RuntimeError(f"waldo_b200.wif_fuse: raw_output needs at least 5 channels, got {Cr}")
         frame = torch.empty(B, Tp, 3, H, W, device=r.device, dtype=torch.float32)
-        a = L.WifFuseFwd(B, Tc, Tp, Cr, H * W, 1 if ab else 0, CRp, L.ptr(r, name="raw_output"), L.ptr(u, name="unet_out"), L.ptr(frame))
+        a = L.WifFuseFwd(B, Tc, Tp, Cr, H * W, 1 if ab else 0, L.ptr(r, name="raw_output"), L.ptr(u, name="unet_out"), L.ptr(frame))
         L.call(lib.waldo_wif_fuse_fwd, a, r, "wif_fuse_fwd")
         ctx.keep = (a, r, u)
         return frame
@@ -559,8 +470,6 @@ class _WifFuse(torch.autograd.Function):
         d_u = torch.empty_like(u) if ctx.needs_input_grad[1] else None
         b = L.WifFuseBwd(a, L.ptr(d_frame), L.ptr(d_raw), L.ptr(d_u))
         L.call(lib.waldo_wif_fuse_bwd, b, r, "wif_fuse_bwd")
-        if d_raw is not None:
-            d_raw = records_view(d_raw, a.Cr)
         return d_raw, d_u, None
 
 
@@ -571,8 +480,7 @@ def wif_fuse(raw_output, unet_out, ab=True):
 
 # ===================================================================================== f-3 input packing
 def pack_input(rgb, label, num_lyt, on=5.0, off=-5.0, out=None):
-    """Build `input` (logical (B,T,3+Nl,Hd,Wd) fp32; memory = channels-last records, the layout the path reads without a
-    relayout pass) on the device from rgb (B,T,3,Hd,Wd; uint8 raw pixels or fp32 already in
+    """Build `input` (B,T,3+Nl,Hd,Wd) fp32 on the device from rgb (B,T,3,Hd,Wd; uint8 raw pixels or fp32 already in
     [-1,1]) and label (B,T,Hd,Wd) uint8 class ids -- data/base_dataset.py:173-183,:355-372 + synthesizer.py:444.
     Data preparation: no gradient."""
     lib = L.load()
@@ -582,21 +490,15 @@ def pack_input(rgb, label, num_lyt, on=5.0, off=-5.0, out=None):
         raise RuntimeError("waldo_b200.pack_input: label must be uint8 class ids")
     B, T, _, Hd, Wd = rgb.shape
     rgb_c, lab_c = rgb.detach().contiguous(), label.contiguous()
-    C_ = 3 + num_lyt
-    Cp = ceil4(C_ + 1)
     if out is None:
-        buf = torch.empty(B, T, Hd, Wd, Cp, device=rgb.device, dtype=torch.float32)
-        out = records_view(buf, C_)
-    else:
-        hit = find_records(out) if tuple(out.shape) == (B, T, C_, Hd, Wd) else None
-        if hit is None or hit[1] != Cp:
-            raise RuntimeError("waldo_b200.pack_input: `out` must be a (B, T, 3+num_lyt, Hd, Wd) tensor returned by an earlier pack_input call")
-        buf = hit[0]
+        out = torch.empty(B, T, 3 + num_lyt, Hd, Wd, device=rgb.device, dtype=torch.float32)
+    elif out.shape != (B, T, 3 + num_lyt, Hd, Wd):
+        raise RuntimeError("waldo_b200.pack_input: out has the wrong shape")
     u8 = rgb_c.dtype == torch.uint8
     a = L.PackInput(B * T, num_lyt, Hd * Wd, float(on), float(off),
                     L.ptr(rgb_c, torch.uint8, "rgb") if u8 else None, None if u8 else L.ptr(rgb_c, name="rgb"),
-                    L.ptr(lab_c, torch.uint8, "label"), L.ptr(buf, name="out"), Cp)
-    L.call(lib.waldo_pack_input, a, buf, "pack_input")
+                    L.ptr(lab_c, torch.uint8, "label"), L.ptr(out, name="out"))
+    L.call(lib.waldo_pack_input, a, out, "pack_input")
     return out
 
 

@@ -32,13 +32,10 @@ class GraphedDecode:
 
     def __call__(self, input, obj_alpha_raw, obj_pose, bg_pose, occ_score, cls, ctx_ts, pred_ts):
         args = (input, obj_alpha_raw, obj_pose, bg_pose, occ_score, cls, ctx_ts, pred_ts)
-        from . import functional as Fn
-        for i, t in enumerate(args):
-            ok = t is None or (t.is_cuda and (t.is_contiguous() or (i == 0 and Fn.find_records(t) is not None)))
-            if not ok:
-                raise RuntimeError("waldo_b200.GraphedDecode: inputs must be dense CUDA tensors (static buffers); `input` "
-                                   "contiguous or the channels-last records pack_input returns")
-        key = tuple((t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype) if t is not None else None for t in args)
+        for t in args:
+            if t is not None and (not t.is_cuda or not t.is_contiguous()):
+                raise RuntimeError("waldo_b200.GraphedDecode: inputs must be contiguous CUDA tensors (static buffers)")
+        key = tuple((t.data_ptr(), tuple(t.shape), t.dtype) if t is not None else None for t in args)
         hit = self.cache.get(key)
         if hit is None:
             if len(self.cache) >= self.max_graphs:
