@@ -889,6 +889,15 @@ __global__ void k_occ_reduce(const float* __restrict__ part, int groups, int per
 }
 
 // ============================================================================ context-alpha backward (B4..B2b)
+struct WbPrepBwdCtx {
+  int b, t, L, Nl, HW;
+  unsigned HWd;
+  bool filt, lowres_direct, need_p, pairs_only;
+  const float *s_P, *s_occ, *lyt_base, *alo;
+  float *s_acc, *s_accp;
+  float* s_stage;    // this warp's staging area, WB_STAGE_SLOTS * WB_WARP floats
+};
+
 // Sum over the warp of 32 per-lane values v[0..31]: afterwards lane l holds sum_lanes v[l] in v[0] (a fixed butterfly:
 // 31 shuffles instead of 32 x 5, deterministic).  The emulation build (one lane) leaves v untouched.
 WB_DEV void wb_warp_transpose_sum(float* v) {
@@ -905,56 +914,389 @@ WB_DEV void wb_warp_transpose_sum(float* v) {
 #endif
 }
 
-// grid = (red_ctas, B*Tw), block = 256, one thread per HD pixel of a 32x8 tile (a warp = 32 consecutive pixels of a row).
-//
-// Written for INSTRUCTION COUNT and CODE SIZE: the previous form (unrolled 4- / 8-slot occlusion variants, 32-wide class
-// transposes per variant, a lanes-per-layer twin) was 28 K SASS instructions -- ncu: 1.5 G warp instructions per launch,
-// issue slots 48 % busy, 'no instruction' (instruction-cache) and 'wait' stalls leading, DRAM at 14 % of peak
-// (profiles/r2/r2_v5_ncu_bwd.md).  Here every loop over the live layers of the row (the warp-wide union `wm`, n = popc) is
-// ROLLED and appears once in the code; the per-(pixel, slot) scalars -- up-sampled opacity, filter value, upstream and
-// accumulated gradient -- live in a per-thread column of dynamic shared memory (conflict-free: bank = thread), the class
-// vectors (softmax, its gradient) in registers with compile-time trip counts.
-//   phase A  per slot: a_k = up(a_lo[k]) * l_k,  l_k = 1 - 0.5 sum_c |P[k,c] - softmax(lyt)[c]|,  upstream d A_k
-//   phase B  occlusion backward  A_i = a_i prod_j (1 - a_j occ[j,i])  (exclusive products; exact zeros handled), d occ
-//   phase C  per object slot: d l_k -> d softmax, d P[k,:] (transpose butterfly), d a_lo (staged column reduction)
-//   phase D  softmax backward -> d layout logits of this pixel
-#define WB_PB_FIELDS 4   // aup, ell, gA, ga
-template <int NLC>
-__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(WbDecB a) {
+template <int NA, int NLC>
+WB_DEV void wb_prep_bwd_pixel(const WbDecB& a, const WbPrepBwdCtx& c, const WbColRed& cr, unsigned wm, float actf, unsigned q,
+                              const WbAxis& ax, const WbAxis& ay, int o00, int o01, int o10, int o11) {
   constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
   const WbDec& d = a.f;
+  const waldo_geom_t& g = d.g;
+  const int L = c.L, Nl = NLC > 0 ? NLC : c.Nl, HW = c.HW, b = c.b, t = c.t;
+  const unsigned HWd = c.HWd;
+  const int lane = wb_lane();
+  const WbIdx<NA> ix = wb_idx<NA>(wm);
+  const bool any_obj = (wm >> 1) != 0u;
+  // the scatter-accumulated d/dA of the first four slots is requested up front (most rows have <= 4 live layers): four
+  // independent HBM loads in flight while the forward is recomputed, instead of one exposed load per trip of the rolled loop
+  float pf[4] = {0.f, 0.f, 0.f, 0.f};
+  if (NA > 8 && a.d_alpha_acc) {
+    const float* base = a.d_alpha_acc + ((size_t)b * g.Tw + t) * L * HWd + q;
+    WB_UNROLL for (int u = 0; u < 4; ++u) if (u < ix.n) pf[u] = base[(size_t)ix.k[u] * HWd];
+  }
+  // ---- recompute the forward of this pixel
+  float sm[NN];
+  if (c.filt && any_obj) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
+  float aup[NA], av[NA], ell[NA];
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
+    av[s] = 0.f; aup[s] = 0.f; ell[s] = 1.f;
+    if (s < ix.n) {
+      const int k = ix.k[s];
+      const float* pl = c.alo + (size_t)k * HW;
+      float v = c.lowres_direct ? __ldg(pl + o00)
+                                : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
+      aup[s] = v;
+      if (c.filt && k >= 1) {
+        const float* P = c.s_P + (k - 1) * Nl;
+        float dist = 0.f;
+        WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dist += fabsf(P[cc] - sm[cc]);
+        ell[s] = 1.f - dist * 0.5f;
+      }
+      av[s] = v * ell[s];
+    }
+  }
+  // ---- upstream: scatter-accumulated d/dA plus the returned alpha = 2A - 1 (zero beyond the image edge)
+  float gA[NA], ga[NA];
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
+    ga[s] = 0.f; gA[s] = 0.f;
+    if (s < ix.n) {
+      const size_t o = (((size_t)b * g.Tw + t) * L + ix.k[s]) * HWd + q;
+      float v = 0.f;
+      if (a.d_alpha_acc) {
+        if (NA > 8 && s < 4) v += s == 0 ? pf[0] : (s == 1 ? pf[1] : (s == 2 ? pf[2] : pf[3]));
+        else v += a.d_alpha_acc[o];
+      }
+      if (a.d_alpha) v += 2.f * __ldg(a.d_alpha + o);
+      gA[s] = v * actf;
+    }
+  }
+  if (NA > 8 && ix.n <= 4) {
+    // most rows have <= 4 live layers: run the O(n^2) exclusive-product backward on registers, fully unrolled, instead of
+    // the rolled double loop over local-memory arrays
+    WbIdx<4> ix4;
+    float R4[4], gA4[4], ga4[4];
+    ix4.n = ix.n;
+    WB_UNROLL for (int u = 0; u < 4; ++u) {
+      const bool on = u < ix.n;
+      ix4.k[u] = on ? ix.k[u] : 0; R4[u] = on ? av[u] : 0.f; gA4[u] = on ? gA[u] : 0.f; ga4[u] = 0.f;
+    }
+    wb_occlude_bwd<4>(R4, gA4, c.s_occ, L, ix4, ga4, c.s_acc, c.pairs_only);
+    WB_UNROLL for (int u = 0; u < 4; ++u) if (u < ix.n) ga[u] = ga4[u];
+  }
+#if WB_PREP_OCC8
+  else if (NA > 8 && ix.n <= 8) {   // 5..8 live layers (30 % of the rows at the benchmark shape): same on 8 register slots
+    WbIdx<8> ix8;
+    float R8[8], gA8[8], ga8[8];
+    ix8.n = ix.n;
+    WB_UNROLL for (int u = 0; u < 8; ++u) {
+      const bool on = u < ix.n;
+      ix8.k[u] = on ? ix.k[u] : 0; R8[u] = on ? av[u] : 0.f; gA8[u] = on ? gA[u] : 0.f; ga8[u] = 0.f;
+    }
+    wb_occlude_bwd<8>(R8, gA8, c.s_occ, L, ix8, ga8, c.s_acc, c.pairs_only);
+    WB_UNROLL for (int u = 0; u < 8; ++u) if (u < ix.n) ga[u] = ga8[u];
+  }
+#endif
+  else {
+    wb_occlude_bwd<NA>(av, gA, c.s_occ, L, ix, ga, c.s_acc, c.pairs_only);
+  }
+  // ---- filter backward: l_k = 1 - 0.5 sum_c |P_kc - sm_c|.  One ROLLED loop over the object slots (a single copy of
+  // the class loop in the code); d P_kc = sum over pixels of -0.5 sign(P_kc - sm_c) d l_k is reduced over the warp with
+  // a transpose butterfly and accumulated by lane c.
+  float gsm[NN];
+  WB_UNROLL for (int cc = 0; cc < NN; ++cc) gsm[cc] = 0.f;
+  if (c.filt && any_obj) {
+    for (int s = 0; s < ix.n; ++s) {
+      float gl = 0.f;
+      int k = 0;
+      if (NA > 8) { gl = ga[s] * aup[s]; k = ix.k[s]; }   // rolled form: the arrays live in local memory, index them directly
+      else { WB_UNROLL_NA for (int ss = 0; ss < WB_NEND; ++ss) if (ss == s) { gl = ga[ss] * aup[ss]; k = ix.k[ss]; } }   // d / d l_k
+      if (k < 1) continue;   // warp-uniform
+      const float* P = c.s_P + (k - 1) * Nl;
+      float v[32];
+      WB_UNROLL for (int cc = 0; cc < 32; ++cc) {
+        v[cc] = 0.f;
+        if (cc < NN && (NLC > 0 || cc < Nl)) {
+          const float df = P[cc] - sm[cc];
+          const float sg = df > 0.f ? 0.5f : (df < 0.f ? -0.5f : 0.f);
+          gsm[cc] += sg * gl;
+          v[cc] = -sg * gl;
+        }
+      }
+      if (c.need_p) {
+        wb_warp_transpose_sum(v);
+#ifdef WB_HOST_EMU
+        for (int cc = 0; cc < Nl; ++cc) c.s_accp[(k - 1) * Nl + cc] += v[cc];
+#else
+        if (lane < Nl) c.s_accp[(k - 1) * Nl + lane] += v[0];
+#endif
+      }
+    }
+  }
+  // ---- up-sampling backward: d a_lo
+  if (a.d_a_lo) {
+    if (c.lowres_direct) {
+      WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s)
+        if (s < ix.n) WB_RED_NZ(a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s]) * HW + o00, ga[s] * ell[s]);
+    } else if constexpr (NA <= WB_STAGE_SLOTS) {
+      float* dst[NA];
+      WB_UNROLL for (int s = 0; s < NA; ++s) {
+        c.s_stage[WB_STAGE_AT(s, lane)] = ga[s] * ell[s];
+        dst[s] = a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s]) * HW;
+      }
+      __syncwarp();
+      wb_colred_flush(a, cr, c.s_stage, ix.n, dst, g.W, 1);
+      __syncwarp();
+    }
+#ifndef WB_HOST_EMU
+    else if (ix.n <= WB_STAGE_SLOTS) {   // the usual case: all live slots staged at once, destinations derived from the mask
+      for (int s = 0; s < ix.n; ++s) c.s_stage[WB_STAGE_AT(s, lane)] = ga[s] * ell[s];
+      __syncwarp();
+      wb_colred_flush_slots(a, cr, c.s_stage, wm, 1, a.d_a_lo + ((size_t)b * g.Tw + t) * L * HW, (size_t)HW, g.W, 1);
+      __syncwarp();
+    }
+#endif
+    else {
+      for (int s0 = 0; s0 < ix.n; s0 += WB_STAGE_SLOTS) {
+        float* dst[WB_STAGE_SLOTS];
+        const int ns = min(WB_STAGE_SLOTS, ix.n - s0);
+        for (int j = 0; j < ns; ++j) {
+          c.s_stage[WB_STAGE_AT(j, lane)] = ga[s0 + j] * ell[s0 + j];
+          dst[j] = a.d_a_lo + (((size_t)b * g.Tw + t) * L + ix.k[s0 + j]) * HW;
+        }
+        __syncwarp();
+        wb_colred_flush(a, cr, c.s_stage, ns, dst, g.W, 1);
+        __syncwarp();
+      }
+    }
+  }
+  if (c.filt && any_obj && a.d_input && actf != 0.f) {   // softmax backward into the layout logits of this frame
+    float dot = 0.f;
+    WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dot += gsm[cc] * sm[cc];
+    float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd + q;
+    WB_UNROLL for (int cc = 0; cc < NN; ++cc)
+      if (NLC > 0 || cc < Nl) { WB_RED(o, sm[cc] * (gsm[cc] - dot)); o += HWd; }   // fire-and-forget reduction
+  }
+}
+
+#ifndef WB_HOST_EMU
+// ============================================================================ lanes-per-layer form of the context-alpha backward
+// NOT the default (WB_LANES_PREP_BWD = 0): parity-green, but measured SLOWER on B200 than the one-lane-per-pixel form
+// (4.2 ms vs 3.2 ms per launch, profiles/r1_v10): unlike the layer kernels this one is dominated by the per-object loops
+// over the 20 classes, and with one layer per lane the background / padding lanes of every pixel idle through them.
+// Same layout as wb_lanes_layers_bwd: LP lanes per pixel, one (pixel, layer) per lane, LP passes over the row.
+// Class-indexed quantities (20 classes padded to 32) are spread over lanes with partial transpose-sums:
+
+// over the SLOT lanes of a pixel: afterwards v[0 .. 32/LP) of slot lane s holds the sums (over the LP lanes) of the classes
+// cbase + i, with cbase returned  (= sum over stages t of bit_t(s) * (16 >> t))
+template <int LP>
+WB_DEV int wb_class_split_slots(float* v, int slot) {
+  constexpr int PPW = 32 / LP;
+  int cbase = 0;
+  WB_UNROLL for (int t = 0; (1 << t) < LP; ++t) {
+    const int o = 16 >> t, bit = 1 << t;
+    const bool up = (slot & bit) != 0;
+    WB_UNROLL for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit * PPW);
+    }
+    if (up) cbase += o;
+  }
+  return cbase;
+}
+// over the PPW pixel lanes that share a slot: v[0 .. 32/PPW) of pixel lane pl holds the row sums of the classes cbase + i
+template <int PPW>
+WB_DEV int wb_class_split_pixels(float* v, int pl) {
+  int cbase = 0;
+  WB_UNROLL for (int t = 0; (1 << t) < PPW; ++t) {
+    const int o = 16 >> t, bit = 1 << t;
+    const bool up = (pl & bit) != 0;
+    WB_UNROLL for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+    if (up) cbase += o;
+  }
+  return cbase;
+}
+
+#define WB_SM_ROW 32   // s_sm[class][pixel of the row]
+
+template <int LP, int NLC>
+WB_DEV void wb_lanes_prep_bwd(const WbDecB& a, const WbPrepBwdCtx& c, const WbColRed& cr, unsigned wm, int n, int tx0, bool rowact, int Y,
+                              const WbAxis& ay, float* __restrict__ s_sm) {
+  constexpr int PPW = 32 / LP;
+  constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
+  constexpr int NS = 32 / LP;     // classes per slot lane after the split
+  constexpr int NPX = 32 / PPW;   // classes per pixel lane after the row split (= LP)
+  const WbDec& d = a.f;
+  const waldo_geom_t& g = d.g;
+  const int L = c.L, Nl = NLC > 0 ? NLC : c.Nl, HW = c.HW, b = c.b, t = c.t;
+  const unsigned HWd = c.HWd;
+  const int lane = wb_lane(), pl = lane % PPW, slot = lane / PPW;
+  const bool valid = slot < n;
+  const int k = valid ? wb_nth_bit(wm, slot) : 0;
+  const bool isobjk = valid && k >= 1;
+  float oc[LP], accj[LP];
+  WB_UNROLL for (int j = 0; j < LP; ++j) {
+    accj[j] = 0.f;
+    oc[j] = (valid && j < n) ? c.s_occ[wb_nth_bit(wm, j) * L + k] : 0.f;
+  }
+  const bool filt_row = LP > 1 && c.filt && (wm >> 1) != 0u;   // some object is live in this row
+  // ---- phase A (lane = pixel): softmax of the HD layout logits, staged for the slot lanes
+  if (filt_row) {
+    const int X = min(tx0 + lane, g.Wd - 1);
+    float sm[NN];
+    wb_softmax_hd<NLC>(c.lyt_base, HWd, (unsigned)(Y * g.Wd + X), Nl, sm);
+    WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) s_sm[cc * WB_SM_ROW + lane] = sm[cc];
+    __syncwarp();
+  }
+  float accP[NN];   // d P[k, :] of this lane's layer, summed over the passes
+  WB_UNROLL for (int cc = 0; cc < NN; ++cc) accP[cc] = 0.f;
+  const float* P = c.s_P + (isobjk ? (k - 1) * Nl : 0);
+  const float* alo_k = c.alo + (size_t)k * HW;
+  const size_t plane = (((size_t)b * g.Tw + t) * L + k) * HWd;
+  const float r_lo = (float)g.H / (float)g.Hd;
+  const bool stage = a.d_a_lo && !c.lowres_direct;
+#pragma unroll 1
+  for (int r = 0; r < LP; ++r) {
+    const int p = r * PPW + pl, Xr = tx0 + p, X = min(Xr, g.Wd - 1);
+    const float actf = (rowact && Xr < g.Wd) ? 1.f : 0.f;
+    const unsigned q = (unsigned)(Y * g.Wd + X);
+    const WbAxis ax = wb_axis(X, r_lo, g.W);
+    const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
+    // ---- loads first (invalid lanes read layer 0: harmless)
+    float a00 = __ldg(alo_k + o00), a01 = a00, a10 = a00, a11 = a00;
+    if (!c.lowres_direct) { a01 = __ldg(alo_k + o01); a10 = __ldg(alo_k + o10); a11 = __ldg(alo_k + o11); }
+    const float gacc = a.d_alpha_acc ? a.d_alpha_acc[plane + q] : 0.f;
+    const float gal = a.d_alpha ? __ldg(a.d_alpha + plane + q) : 0.f;
+    // ---- forward of this (pixel, layer), same arithmetic as wb_prep_pixel
+    const float aup = valid ? (c.lowres_direct ? a00 : wb_lerp2(a00, a01, a10, a11, ax, ay)) : 0.f;
+    float ell = 1.f;
+    if (filt_row && isobjk) {
+      float dist = 0.f;
+      WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dist += fabsf(P[cc] - s_sm[cc * WB_SM_ROW + p]);
+      ell = 1.f - dist * 0.5f;
+    }
+    const float av = aup * ell;
+    const float gA = valid ? (gacc + 2.f * gal) * actf : 0.f;
+    // ---- exclusive-product backward over the slot lanes
+    float Rj[LP], pre[LP], term[LP];
+    float run = 1.f;
+    WB_UNROLL for (int j = 0; j < LP; ++j) {
+      Rj[j] = __shfl_sync(0xffffffffu, av, pl + j * PPW);
+      pre[j] = run;
+      run *= 1.f - Rj[j] * oc[j];
+    }
+    float ga = gA * run;
+    const float gV = gA * av;
+    float suf = 1.f;
+    WB_UNROLL for (int j = LP - 1; j >= 0; --j) {
+      const float excl = pre[j] * suf;
+      suf *= 1.f - Rj[j] * oc[j];
+      term[j] = -gV * oc[j] * excl;
+      accj[j] += -gV * Rj[j] * excl;
+    }
+    wb_slot_transpose_sum<LP>(term, slot);
+    ga += term[0];
+    // ---- filter backward: l_k = 1 - 0.5 sum_c |P_kc - sm_c|
+    if (filt_row) {
+      const float gl = isobjk ? ga * aup : 0.f;   // d / d l_k
+      float v[32];
+      WB_UNROLL for (int cc = 0; cc < 32; ++cc) {
+        v[cc] = 0.f;
+        if (cc < NN && (NLC > 0 || cc < Nl)) {
+          const float df = P[cc] - s_sm[cc * WB_SM_ROW + p];
+          const float sg = df > 0.f ? 0.5f : (df < 0.f ? -0.5f : 0.f);
+          v[cc] = sg * gl;          // this layer's share of d / d sm_c
+          accP[cc] -= sg * gl;      // d / d P_kc
+        }
+      }
+      if (a.d_input) {   // softmax backward into the layout logits: d lyt_c = sm_c (gsm_c - sum_c' gsm_c' sm_c')
+        const int cbase = wb_class_split_slots<LP>(v, slot);
+        float smc[NS];
+        float dot = 0.f;
+        WB_UNROLL for (int i = 0; i < NS; ++i) {
+          const int cls = cbase + i;
+          smc[i] = cls < Nl ? s_sm[cls * WB_SM_ROW + p] : 0.f;
+          dot += v[i] * smc[i];
+        }
+        WB_UNROLL for (int o = PPW; o < 32; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (actf != 0.f) {
+          float* o = a.d_input + (((size_t)b * g.T + t) * g.C + 3 + cbase) * HWd + q;
+          WB_UNROLL for (int i = 0; i < NS; ++i) {
+            if (cbase + i < Nl) WB_RED(o, smc[i] * (v[i] - dot));   // fire-and-forget reduction
+            o += HWd;
+          }
+        }
+      }
+    }
+    // ---- up-sampling backward: d a_lo
+    if (a.d_a_lo && valid) {
+      if (c.lowres_direct) WB_RED_NZ(a.d_a_lo + (((size_t)b * g.Tw + t) * L + k) * HW + o00, ga * ell);
+      else c.s_stage[WB_STAGE_AT(slot, p)] = ga * ell;
+    }
+  }
+  if (stage) {
+    __syncwarp();
+    wb_colred_flush_slots(a, cr, c.s_stage, wm, 1, a.d_a_lo + ((size_t)b * g.Tw + t) * L * HW, (size_t)HW, g.W, 1);
+    __syncwarp();
+  }
+  if (c.s_acc) {
+    WB_UNROLL for (int j = 0; j < LP; ++j) {
+      float v = accj[j];
+      WB_UNROLL for (int o = PPW / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (pl == 0 && valid && j < n) {
+        const int kj = wb_nth_bit(wm, j);
+        if (!(c.pairs_only && (k == 0 || kj == 0 || k == kj))) c.s_acc[kj * L + k] += v;
+      }
+    }
+  }
+  if (filt_row) {
+    if (c.need_p) {   // d P[k, :]: row sums over the pixel lanes, one lane per (layer, class)
+      float v[32];
+      WB_UNROLL for (int cc = 0; cc < 32; ++cc) v[cc] = cc < NN ? accP[cc] : 0.f;
+      const int cbase = wb_class_split_pixels<PPW>(v, pl);
+      WB_UNROLL for (int i = 0; i < NPX; ++i)
+        if (isobjk && cbase + i < Nl) c.s_accp[(k - 1) * Nl + cbase + i] += v[i];
+    }
+    __syncwarp();   // s_sm is rewritten by the warp's next row
+  }
+}
+#endif  // !WB_HOST_EMU
+
+// grid = (red_ctas, B*Tw), block = 256.
+template <int NLC>
+__global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(WbDecB a) {
+  const WbDec& d = a.f;
   const waldo_geom_t g = d.g;
-  const int No = g.No, Nl = NLC > 0 ? NLC : g.Nl, L = No + 1, HW = g.H * g.W;
-  const unsigned HWd = (unsigned)(g.Hd * g.Wd);
-  const int bt = blockIdx.y, b = bt / g.Tw, t = bt - b * g.Tw;
-  const bool filt = (g.flags & WALDO_F_FILTER) != 0, lowres_direct = (g.Hd == g.H);
-  const bool need_p = filt && a.d_prof_p, pairs_only = (g.flags & WALDO_F_OCC_PAIRS) != 0;
+  WbPrepBwdCtx c;
+  const int No = g.No, Nl = g.Nl, L = No + 1;
+  c.L = L; c.Nl = Nl; c.HW = g.H * g.W; c.HWd = (unsigned)(g.Hd * g.Wd);
+  const int bt = blockIdx.y;
+  c.b = bt / g.Tw; c.t = bt - c.b * g.Tw;
+  c.filt = (g.flags & WALDO_F_FILTER) != 0;
+  c.lowres_direct = (g.Hd == g.H);
+  c.need_p = c.filt && a.d_prof_p;
+  c.pairs_only = (g.flags & WALDO_F_OCC_PAIRS) != 0;
   __shared__ float s_P[(WB_MAX_L - 1) * WB_MAX_NL];
   __shared__ float s_occ[WB_MAX_L * WB_MAX_L];
   __shared__ float s_red[WB_NWARP][WB_MAX_L * WB_MAX_L];
   __shared__ float s_redp[WB_NWARP][(WB_MAX_L - 1) * WB_MAX_NL];
   __shared__ float s_stage[WB_NWARP][WB_STAGE_SLOTS * WB_STAGE_ROW];
-  WB_DYN_SMEM(s_scr);   // [WB_PB_FIELDS][WB_MAX_L][threads]
-  if (filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)b * No * Nl + i];
-  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)b * g.T + t) * L * L + i);
+  WB_DYN_SMEM(s_dyn);   // WB_NWARP x [WB_MAX_NL][32] softmax staging of the lanes-per-layer path
+  if (c.filt) for (int i = wb_tid(); i < No * Nl; i += wb_nthr()) s_P[i] = d.prof_p[(size_t)c.b * No * Nl + i];
+  for (int i = wb_tid(); i < L * L; i += wb_nthr()) s_occ[i] = __ldg(d.occ + ((size_t)c.b * g.T + c.t) * L * L + i);
   for (int i = wb_tid(); i < WB_NWARP * WB_MAX_L * WB_MAX_L; i += wb_nthr()) (&s_red[0][0])[i] = 0.f;
   for (int i = wb_tid(); i < WB_NWARP * (WB_MAX_L - 1) * WB_MAX_NL; i += wb_nthr()) (&s_redp[0][0])[i] = 0.f;
   for (int i = wb_tid(); i < WB_NWARP * WB_STAGE_SLOTS * WB_STAGE_ROW; i += wb_nthr()) (&s_stage[0][0])[i] = 0.f;
   __syncthreads();
-  const int NT = wb_nthr(), lane = wb_lane();
-  float* const scr = s_scr + wb_tid();
-#define WB_SCR(f, s) scr[((f) * WB_MAX_L + (s)) * NT]
-  float* const my_stage = s_stage[wb_warp()];
-  float* const s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
-  float* const s_accp = s_redp[wb_warp()];
+  c.s_P = s_P; c.s_occ = s_occ; c.s_stage = s_stage[wb_warp()];
+  c.s_acc = a.d_occ ? s_red[wb_warp()] : nullptr;
+  c.s_accp = s_redp[wb_warp()];
   const float rlo = (float)g.H / (float)g.Hd;
-  const float* __restrict__ lyt_f = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;        // layout planes of this frame
-  const float* __restrict__ alo_f = d.a_lo + ((size_t)b * g.Tw + t) * L * HW;
-  const float* __restrict__ dacc_f = a.d_alpha_acc ? a.d_alpha_acc + ((size_t)b * g.Tw + t) * L * HWd : nullptr;
-  const float* __restrict__ dal_f = a.d_alpha ? a.d_alpha + ((size_t)b * g.Tw + t) * L * HWd : nullptr;
-  float* __restrict__ dlyt_f = a.d_input ? a.d_input + (((size_t)b * g.T + t) * g.C + 3) * HWd : nullptr;
-  float* __restrict__ dalo_f = a.d_a_lo ? a.d_a_lo + ((size_t)b * g.Tw + t) * L * HW : nullptr;
-  const uint32_t* __restrict__ live = d.live_ctx + ((size_t)b * g.Tw + t) * HW;
+  c.lyt_base = d.input + (((size_t)c.b * g.T + c.t) * g.C + 3) * c.HWd;
+  c.alo = d.a_lo + ((size_t)c.b * g.Tw + c.t) * L * c.HW;
+  const uint32_t* live = d.live_ctx + ((size_t)c.b * g.Tw + c.t) * c.HW;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
@@ -963,135 +1305,29 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(
       const float actf = (Xr < g.Wd && Yr < g.Hd) ? 1.f : 0.f;   // beyond the edge: nearest valid pixel, zero upstream
       const int X = min(Xr, g.Wd - 1), Y = min(Yr, g.Hd - 1);
       const unsigned q = (unsigned)(Y * g.Wd + X);
-      const WbAxis ay = wb_axis(Y, rlo, g.H), ax = wb_axis(X, rlo, g.W);
+      WbAxis ay = wb_axis(Y, rlo, g.H), ax = wb_axis(X, rlo, g.W);
       const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
       const unsigned wm = wb_warp_or(wb_live4(live, o00, o01, o10, o11));
       const int n = __popc(wm);
       if (n == 0) continue;   // warp-uniform: nothing live here, every gradient path is dead
       WbColRed cr;
-      if (dalo_f && !lowres_direct) cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(ax.i0, 0), wb_shfl(ax.i1, WB_WARP - 1), ay);
-      const bool any_obj = (wm >> 1) != 0u;
-      float sm[NN];
-      if (filt && any_obj) wb_softmax_hd<NLC>(lyt_f, HWd, q, Nl, sm);
-      // ---- phase A: forward of every live slot and its upstream gradient
-      {
-        unsigned m = wm;
-        for (int s = 0; s < n; ++s) {
-          const int k = __ffs((int)m) - 1;
-          m &= m - 1u;
-          const float* pl = alo_f + (unsigned)(k * HW);
-          const float aup = lowres_direct ? __ldg(pl + o00)
-                                          : wb_lerp2(__ldg(pl + o00), __ldg(pl + o01), __ldg(pl + o10), __ldg(pl + o11), ax, ay);
-          float ell = 1.f;
-          if (filt && k >= 1) {
-            const float* P = s_P + (k - 1) * Nl;
-            float dist = 0.f;
-            WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dist += fabsf(P[cc] - sm[cc]);
-            ell = 1.f - dist * 0.5f;
-          }
-          const unsigned o = (unsigned)k * HWd + q;
-          float gA = 0.f;
-          if (dacc_f) gA += dacc_f[o];
-          if (dal_f) gA += 2.f * __ldg(dal_f + o);   // the returned alpha = 2A - 1
-          WB_SCR(0, s) = aup; WB_SCR(1, s) = ell; WB_SCR(2, s) = gA * actf; WB_SCR(3, s) = 0.f;
-        }
+      if (a.d_a_lo && !c.lowres_direct) cr = wb_colred_setup(a.up_tab, wb_shfl(X, 0), wb_shfl(ax.i0, 0), wb_shfl(ax.i1, WB_WARP - 1), ay);
+#if !defined(WB_HOST_EMU) && !defined(WB_NO_LANES) && WB_LANES_PREP_BWD
+      if (n <= 8) {
+        float* s_sm = s_dyn + wb_warp() * (WB_MAX_NL * WB_SM_ROW);
+        const bool rowact = Yr < g.Hd;
+        if (n == 1) wb_lanes_prep_bwd<1, NLC>(a, c, cr, wm, n, tx0, rowact, Y, ay, s_sm);
+        else if (n == 2) wb_lanes_prep_bwd<2, NLC>(a, c, cr, wm, n, tx0, rowact, Y, ay, s_sm);
+        else if (n <= 4) wb_lanes_prep_bwd<4, NLC>(a, c, cr, wm, n, tx0, rowact, Y, ay, s_sm);
+        else wb_lanes_prep_bwd<8, NLC>(a, c, cr, wm, n, tx0, rowact, Y, ay, s_sm);
+        continue;
       }
-      // ---- phase B: exclusive-product backward of A_i = a_i prod_j (1 - a_j occ[j,i]); d occ summed over the warp
-      {
-        unsigned mi = wm;
-        for (int i = 0; i < n; ++i) {
-          const int ki = __ffs((int)mi) - 1;
-          mi &= mi - 1u;
-          float run = 1.f;
-          int zeros = 0;   // exact zero factors do occur (occ[j>=1, 0] = 1 with a saturated opacity): never divide by one
-          {
-            unsigned mj = wm;
-            for (int j = 0; j < n; ++j) {
-              const int kj = __ffs((int)mj) - 1;
-              mj &= mj - 1u;
-              const float f = 1.f - WB_SCR(0, j) * WB_SCR(1, j) * s_occ[kj * L + ki];
-              if (f == 0.f) ++zeros; else run *= f;
-            }
-          }
-          const float gAi = WB_SCR(2, i);
-          const float av_i = WB_SCR(0, i) * WB_SCR(1, i);
-          WB_SCR(3, i) += gAi * (zeros ? 0.f : run);
-          const float gV = gAi * av_i;
-          unsigned mj = wm;
-          for (int j = 0; j < n; ++j) {
-            const int kj = __ffs((int)mj) - 1;
-            mj &= mj - 1u;
-            const float oc = s_occ[kj * L + ki];
-            const float av_j = WB_SCR(0, j) * WB_SCR(1, j);
-            const float f = 1.f - av_j * oc;
-            // product of the other factors: run / f, or `run` itself when f is the only zero factor, 0 with two or more
-            const float excl = (f == 0.f) ? (zeros == 1 ? run : 0.f) : (zeros ? 0.f : __fdiv_rn(run, f));
-            WB_SCR(3, j) -= gV * oc * excl;
-            if (s_acc && !(pairs_only && (ki == 0 || kj == 0 || ki == kj))) {
-              const float v = wb_warp_sum(-gV * av_j * excl);
-              if (lane == 0) s_acc[kj * L + ki] += v;
-            }
-          }
-        }
-      }
-      // ---- phase C: per slot d a_lo (staged, WB_STAGE_SLOTS slots per round) and, for objects, the filter backward
-      float gsm[NN];
-      WB_UNROLL for (int cc = 0; cc < NN; ++cc) gsm[cc] = 0.f;
-      {
-        unsigned m = wm;
-        for (int s0 = 0; s0 < n; s0 += WB_STAGE_SLOTS) {
-          const int ns = min(WB_STAGE_SLOTS, n - s0);
-          float* dst[WB_STAGE_SLOTS];
-          for (int j = 0; j < ns; ++j) {
-            const int s = s0 + j;
-            const int k = __ffs((int)m) - 1;
-            m &= m - 1u;
-            const float ga = WB_SCR(3, s), ell = WB_SCR(1, s);
-            if (dalo_f) {
-              if (lowres_direct) WB_RED_NZ(dalo_f + (unsigned)(k * HW) + o00, ga * ell);
-              else { my_stage[WB_STAGE_AT(j, lane)] = ga * ell; dst[j] = dalo_f + (unsigned)(k * HW); }
-            }
-            if (filt && k >= 1) {   // l_k = 1 - 0.5 sum_c |P_kc - sm_c|; d P_kc = sum over pixels of -0.5 sign(P_kc - sm_c) d l_k
-              const float gl = ga * WB_SCR(0, s);
-              const float* P = s_P + (k - 1) * Nl;
-              float v[32];
-              WB_UNROLL for (int cc = 0; cc < 32; ++cc) {
-                v[cc] = 0.f;
-                if (cc < NN && (NLC > 0 || cc < Nl)) {
-                  const float df = P[cc] - sm[cc];
-                  const float sg = df > 0.f ? 0.5f : (df < 0.f ? -0.5f : 0.f);
-                  gsm[cc] += sg * gl;
-                  v[cc] = -sg * gl;
-                }
-              }
-              if (need_p) {
-                wb_warp_transpose_sum(v);
-#ifdef WB_HOST_EMU
-                for (int cc = 0; cc < Nl; ++cc) s_accp[(k - 1) * Nl + cc] += v[cc];
-#else
-                if (lane < Nl) s_accp[(k - 1) * Nl + lane] += v[0];
 #endif
-              }
-            }
-          }
-          if (dalo_f && !lowres_direct) {
-            __syncwarp();
-            wb_colred_flush(a, cr, my_stage, ns, dst, g.W, 1);
-            __syncwarp();
-          }
-        }
-      }
-      // ---- phase D: softmax backward into the layout logits of this pixel
-      if (filt && any_obj && dlyt_f && actf != 0.f) {
-        float dot = 0.f;
-        WB_UNROLL for (int cc = 0; cc < NN; ++cc) if (NLC > 0 || cc < Nl) dot += gsm[cc] * sm[cc];
-        unsigned o = q;
-        WB_UNROLL for (int cc = 0; cc < NN; ++cc)
-          if (NLC > 0 || cc < Nl) { WB_RED(dlyt_f + o, sm[cc] * (gsm[cc] - dot)); o += HWd; }   // fire-and-forget reduction
-      }
+      if (WB_NA_VARIANTS_BWD >= 2 && n <= 4) wb_prep_bwd_pixel<4, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
+      else if (WB_NA_VARIANTS_BWD >= 3 && n <= 8) wb_prep_bwd_pixel<8, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
+      else wb_prep_bwd_pixel<WB_MAX_L, NLC>(a, c, cr, wm, actf, q, ax, ay, o00, o01, o10, o11);
     }
   }
-#undef WB_SCR
   __syncthreads();
   if (a.d_occ) {
     float* part = a.occ_part + ((size_t)bt * gridDim.x + blockIdx.x) * L * L;
@@ -1101,7 +1337,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_BWD) k_alpha_prep_bwd(
       part[e] = acc;
     }
   }
-  if (need_p) {
+  if (c.need_p) {
     float* part = a.prof_p_part + ((size_t)bt * gridDim.x + blockIdx.x) * No * Nl;
     for (int e = wb_tid(); e < No * Nl; e += wb_nthr()) {
       float acc = 0.f;
@@ -1511,7 +1747,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   if (st_aprep && (a.d_alpha_acc || a.d_alpha)) {
     if (filt && a.d_prof_p) WB_BREQ(a.prof_p_part, "prof_p_part scratch missing");
     const dim3 pgrid(a.red_ctas, g.B * g.Tw);
-    const size_t dyn = (size_t)WB_PB_FIELDS * WB_MAX_L * WB_TILE_PX * sizeof(float);   // per-thread slot scratch
+    const size_t dyn = WB_LANES_PREP_BWD ? (size_t)WB_NWARP * WB_MAX_NL * 32 * sizeof(float) : 0;   // softmax staging of the lanes form only
 #ifndef WB_HOST_EMU
     // static + dynamic shared memory exceeds the 48 KB default: opt in (cheap, idempotent)
     if (g.Nl == 20) cudaFuncSetAttribute(k_alpha_prep_bwd<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
