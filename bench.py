@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the WALDO warp+composite hot path (BASELINE.json metric: warped+composited frames/s, fwd+bwd, 512x1024).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl waldo|reference] [--workload city_train|city_rollout|kitti_rollout]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl waldo|reference|reference-gpu]
+                    [--workload city_train|city_rollout|kitti_rollout|nonrigid_train] [--deterministic]
 
 One "step" = one pass of the hot path over one batch of synthetic input:
   control points -> TPS grids -> inverse warps -> occlusion matrix -> context alpha -> fused warp+composite (forward),
@@ -9,10 +10,15 @@ One "step" = one pass of the hot path over one batch of synthetic input:
   forward only (the *_rollout workloads).
 Default workload = BASELINE.json configs[1]: Cityscapes shape 512x1024, batch 8 per GPU, 4 contexts -> 1 future frame,
 fp32, fwd+bwd.  Under torchrun every rank runs the same per-GPU batch (weak scaling, no data-path collective; the
-training workload adds the DDP-equivalent flat gradient all-reduce of a WIF-sized buffer).
+training workload adds the DDP-equivalent flat gradient all-reduce of a WIF-sized buffer, overlapped with the backward,
+SURVEY.md section 8e).  The default line also carries, measured in the same process at every N:
+  `deterministic`   the same step with order-independent (bit-reproducible) gradient accumulation -- the north star's contract;
+  `other_workloads` BASELINE configs[3] / [2] / [4] (Cityscapes and KITTI rollouts, 256x256 training step);
+and at N = 1: `gpu_stock_baseline` (the reference's own code on the same B200 with stock PyTorch kernels), `cpu_baseline`
+(the reference's own code on the host cores, incl. the C1 forward split of BASELINE configs[0]).
 
-`--impl reference` times the reference's algorithm on the host cores (the oracle port of oracle/waldo_oracle.py: the
-reference itself is Python and cannot travel to the GPU box), one frame per step.
+`--impl reference` times the reference's own code (the byte-for-byte staged copy oracle/_ref; the oracle port only if that
+is absent) on the host cores, one video per step; `--impl reference-gpu` the same code on CUDA.
 """
 from __future__ import annotations
 
@@ -34,29 +40,14 @@ WIF_GRAD_ELEMS = 14_160_000   # WIF parameters: the per-step DD
 
 
 def workload_cfg(name):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import waldo_oracle as wo
-    if name == "city_train":
-        return wo.PathConfig(), dict(B=8, T=5, Tc=4, backward=True, label="cityscapes 512x1024 fwd+bwd B=8/GPU Tc=4->Tp=1")
-    if name == "city_rollout":
-        return wo.PathConfig(), dict(B=1, T=14, Tc=4, backward=False, label="cityscapes 512x1024 rollout fwd B=1/GPU Tc=4->Tp=10")
-    if name == "kitti_rollout":
-        cfg = wo.PathConfig(dim=128, load_dim=256, aspect_ratio=3.25, latent_shape=(8, 26), num_lyt=19)
-        return cfg, dict(B=1, T=9, Tc=4, backward=False, label="kitti 256x832 rollout fwd B=1/GPU Tc=4->Tp=5")
-    if name == "nonrigid_train":   # BASELINE configs[4]: the reference ships no UCF-Sports / H3.6M script; SURVEY §8d C5 shape
-        cfg = wo.PathConfig(dim=128, load_dim=256, aspect_ratio=1.0, latent_shape=(8, 8))
-        return cfg, dict(B=8, T=5, Tc=4, backward=True, label="non-rigid 256x256 fwd+bwd B=8/GPU Tc=4->Tp=1")
-    raise SystemExit(f"unknown workload {name}")
+    from waldo_b200 import workloads as wl
+    return wl.workload(name)
 
 
 def alg_bytes(cfg, B, Tc, Tp, backward):
     """Algorithmic HBM bytes of one step (SURVEY.md §8d / BASELINE.md §3), fp32."""
-    Hd, Wd = cfg.hd_shape
-    px, s = Hd * Wd, 4
-    C, L, Nl = 3 + cfg.num_lyt, cfg.num_obj + 1, cfg.num_lyt
-    fwd = px * s * (B * Tc * Tp * (C + L) + B * Tc * Tp * ((C + L) + 2 + 1) + B * Tp * (C + 1) + B * Tc * (Nl + L))
-    bwd = px * s * (B * Tc * Tp * ((C + L) + 2 + C + L) + B * Tp * (C + 1) + B * Tc * (C + L))
-    return fwd, (bwd if backward else 0)
+    from waldo_b200 import workloads as wl
+    return wl.alg_bytes(cfg, B, Tc, Tp, backward)
 
 
 def kernel_bytes(cfg, B, Tc, Tp):
@@ -136,9 +127,8 @@ class ClockSampler:
 
 
 def make_inputs(cfg, B, T, Tc, seed):
-    import waldo_oracle as wo
-    d = wo.synth_inputs(cfg, B, T, Tc, seed=seed)
-    return d
+    from waldo_b200 import workloads as wl
+    return wl.synth_inputs(cfg, B, T, Tc, seed=seed)
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -275,6 +265,132 @@ def run_reference(args, cfg, spec, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+class Runner:
+    """One workload set up on one GPU: resident inputs, pinned host copies, the step function and the two timers."""
+
+    def __init__(self, args, cfg, spec, rank, local_rank, world, deterministic=False):
+        import torch.distributed as dist
+        import waldo_b200 as wb
+        from waldo_b200 import _lib, functional as Fn, sharding, workloads as wl
+        self.wb, self.Fn, self.sharding, self.dist, self.lib = wb, Fn, sharding, dist, _lib.load()
+        self.args, self.cfg, self.spec, self.rank, self.world = args, cfg, spec, rank, world
+        self.dev = dev = torch.device("cuda", local_rank)
+        self.deterministic = deterministic
+        B, T, Tc, backward = spec["B"], spec["T"], spec["Tc"], spec["backward"]
+        self.B, self.T, self.Tc, self.Tp, self.backward = B, T, Tc, T - Tc, backward
+        opt = wl.make_opt(cfg)
+        self.warper = wb.Warper(opt).to(dev)
+        om, bg = wb.alpha_masks(opt)
+        self.om, self.bg = om.to(dev), bg.to(dev)
+        host = make_inputs(cfg, B, T, Tc, seed=rank)
+        self.keys = ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")
+        self.small = ("obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")
+        # what the dataset really holds (data/base_dataset.py:173-183, :355-372): 8-bit RGB and an 8-bit label map; the
+        # fp32 `input` (normalised RGB | +-5 one-hot logits) is expanded from them on the device by waldo_pack_input
+        rgb8 = ((host["input"][:, :, :3] + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)
+        lab8 = host["input"][:, :, 3:].argmax(dim=2).to(torch.uint8)
+        self.pinned = {k: host[k].pin_memory() for k in self.small}
+        self.pinned["rgb"], self.pinned["label"] = rgb8.pin_memory(), lab8.pin_memory()
+        self.ctx_ts, self.pred_ts = host["ctx_ts"].contiguous().to(dev), host["pred_ts"].to(dev)
+        self.resident = {k: self.pinned[k].to(dev) for k in self.small}
+        self.resident["input"] = wb.pack_input(self.pinned["rgb"].to(dev), self.pinned["label"].to(dev), cfg.num_lyt)
+        del host
+        self.grad_buf = None
+        if world > 1 and backward:   # the trainable net's gradients (WIF-sized), exchanged as DDP would: one flat all-reduce per step
+            wif_like = torch.nn.Parameter(torch.zeros(WIF_GRAD_ELEMS, device=dev))
+            wif_like.grad = torch.zeros_like(wif_like)
+            self.grad_buf = sharding.FlatGradReducer([wif_like])
+        self.loss_host = torch.zeros(1).pin_memory()
+        # upstream gradients as a downstream consumer (WIF / losses) would supply them: fixed seeded tensors, so that no
+        # loss kernel of torch sits inside the timed region and the backward reads d output, d flow and d raw_output
+        C, L = 3 + cfg.num_lyt, cfg.num_obj + 1
+        Hd, Wd = cfg.hd_shape
+        if backward:
+            gen = torch.Generator(device=dev).manual_seed(1 + rank)
+            self.g_output = torch.randn(B, self.Tp, C, Hd, Wd, device=dev, generator=gen)
+            self.g_flow = torch.randn(B, Tc, self.Tp, 2, Hd, Wd, device=dev, generator=gen)
+            self.g_raw = torch.randn(B, Tc, self.Tp, C + L, Hd, Wd, device=dev, generator=gen)
+        self.graphed = wb.GraphedDecode(self.warper, self.om, self.bg, cfg.restrict_to_ctx, max_graphs=8) if (not backward and not args.no_graph) else None
+        self.feeder = None
+
+    def step(self, src):
+        wb, cfg = self.wb, self.cfg
+        if self.graphed is not None:   # inference: the whole chain replayed from one CUDA graph per set of input buffers
+            out = self.graphed(src["input"], src["obj_alpha_raw"], src["obj_pose"], src["bg_pose"], src["occ_score"], src["cls"], self.ctx_ts, self.pred_ts)
+            return out[0][:, :, :3].mean()
+        backward = self.backward
+        lv = {k: src[k].detach().requires_grad_(backward and not (self.args.no_input_grad and k == "input")) for k in self.keys}
+        with torch.set_grad_enabled(backward):
+            occ, oa, ba, grid = wb.estimate_alpha_grid_occ(self.warper, lv["obj_alpha_raw"], self.om, self.bg, lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
+            out = wb.decode_output(self.warper, lv["input"], grid, occ, oa, ba, lv["cls"], self.ctx_ts, self.pred_ts, cfg.restrict_to_ctx)
+        if backward:
+            # the trainable net's gradient exchange rides NCCL's own stream while this path's backward runs (what DDP's
+            # bucketed all-reduce does with the rest of a backward pass); the step ends when both are done
+            work = self.grad_buf.reduce_async() if self.grad_buf is not None else None
+            torch.autograd.backward([out[0], out[1], out[5]], [self.g_output, self.g_flow, self.g_raw])
+            if work is not None:
+                self.grad_buf.finish(work)
+        return out[0].detach()[:, :, :3].mean()   # the step's metric (mean predicted RGB), read back in the e2e leg
+
+    def e2e_step(self):
+        # the public feeding API: the next batch is copied from pinned host memory on a side stream while this one is
+        # processed; every step's inputs cross PCIe inside the timed region and the step's metric is read back
+        metric = self.step(next(self.feeder))
+        self.loss_host.copy_(metric.reshape(1), non_blocking=True)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.sharding.max_over_ranks([e0.elapsed_time(e1)], device=self.dev)[0] / steps
+
+    def measure(self, steps, warmup, profile=True):
+        """(ms per step, launches of this library in the timed region, per-stage event times)."""
+        wb, Fn = self.wb, self.Fn
+        wb.set_deterministic(self.deterministic)
+        try:
+            for _ in range(max(warmup, 3)):
+                self.step(self.resident)
+            if self.graphed is None and profile:
+                Fn.PROFILE = {}
+            launches0 = self.lib.waldo_launch_count()
+            ms_step = self.timed(lambda: self.step(self.resident), steps)
+            launches = self.lib.waldo_launch_count() - launches0
+            prof = {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in (Fn.PROFILE or {}).items()}
+        finally:
+            Fn.PROFILE = None
+            wb.set_deterministic(False)
+        return ms_step, launches, prof
+
+    def frames(self):
+        return self.world * self.B * self.Tp
+
+    def summary(self, ms):
+        fwd_b, bwd_b = alg_bytes(self.cfg, self.B, self.Tc, self.Tp, self.backward)
+        return {"value": self.frames() / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+                "hbm_frac_step": ((fwd_b + bwd_b) / (ms * 1e-3) / 1e9) / PEAK["gbs"]}
+
+
+PEAK = {"gbs": 6650.0, "src": "B200_PROFILING.md fallback"}
+
+
+def load_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        PEAK["gbs"], PEAK["src"] = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,6 +401,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE workloads and the deterministic-mode leg")
     ap.add_argument("--no-input-grad", action="store_true", help="experiment: do not request d input")
     ap.add_argument("--no-graph", action="store_true", help="inference workloads: eager launches instead of CUDA-graph replay")
     ap.add_argument("--deterministic", action="store_true",
@@ -301,159 +418,102 @@ def main():
 
     import torch.distributed as dist
     import waldo_b200 as wb
-    from waldo_b200 import _lib, functional as Fn
-    from tests.parity import make_opt
+    from waldo_b200 import functional as Fn
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    wb.set_deterministic(args.deterministic)
-
-    B, T, Tc, backward = spec["B"], spec["T"], spec["Tc"], spec["backward"]
-    Tp = T - Tc
-    opt = make_opt(cfg)
-    warper = wb.Warper(opt).to(dev)
-    om, bg = wb.alpha_masks(opt)
-    om, bg = om.to(dev), bg.to(dev)
-    host = make_inputs(cfg, B, T, Tc, seed=rank)
-    keys = ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")
-    small = ("obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")
-    # what the dataset really holds (data/base_dataset.py:173-183, :355-372): 8-bit RGB and an 8-bit label map; the
-    # fp32 `input` (normalised RGB | +-5 one-hot logits) is expanded from them on the device by waldo_pack_input
-    rgb8 = ((host["input"][:, :, :3] + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)
-    lab8 = host["input"][:, :, 3:].argmax(dim=2).to(torch.uint8)
-    pinned = {k: host[k].pin_memory() for k in small}
-    pinned["rgb"], pinned["label"] = rgb8.pin_memory(), lab8.pin_memory()
-    ctx_ts, pred_ts = host["ctx_ts"].contiguous().to(dev), host["pred_ts"].to(dev)
-    resident = {k: pinned[k].to(dev) for k in small}
-    resident["input"] = wb.pack_input(pinned["rgb"].to(dev), pinned["label"].to(dev), cfg.num_lyt)
-    del host
-    from waldo_b200 import sharding
-    grad_buf = None
-    if world > 1 and backward:   # the trainable net's gradients (WIF-sized), exchanged as DDP would: one flat all-reduce per step
-        wif_like = torch.nn.Parameter(torch.zeros(WIF_GRAD_ELEMS, device=dev))
-        wif_like.grad = torch.zeros_like(wif_like)
-        grad_buf = sharding.FlatGradReducer([wif_like])
-    loss_host = torch.zeros(1).pin_memory()
-
-    # upstream gradients as a downstream consumer (WIF / losses) would supply them: fixed seeded tensors, so that no
-    # loss kernel of torch sits inside the timed region and the backward reads d output, d flow and d raw_output
-    C, L = 3 + cfg.num_lyt, cfg.num_obj + 1
+    load_peak()
+    r = Runner(args, cfg, spec, rank, local_rank, world, deterministic=args.deterministic)
+    B, T, Tc, Tp, backward = r.B, r.T, r.Tc, r.Tp, r.backward
     Hd, Wd = cfg.hd_shape
-    if backward:
-        gen = torch.Generator(device=dev).manual_seed(1 + rank)
-        g_output = torch.randn(B, Tp, C, Hd, Wd, device=dev, generator=gen)
-        g_flow = torch.randn(B, Tc, Tp, 2, Hd, Wd, device=dev, generator=gen)
-        g_raw = torch.randn(B, Tc, Tp, C + L, Hd, Wd, device=dev, generator=gen)
-
-    graphed = wb.GraphedDecode(warper, om, bg, cfg.restrict_to_ctx, max_graphs=8) if (not backward and not args.no_graph) else None
-    use_graph = {"on": graphed is not None}
-
-    def step(src):
-        if use_graph["on"]:   # inference: the whole chain replayed from one CUDA graph per set of input buffers
-            out = graphed(src["input"], src["obj_alpha_raw"], src["obj_pose"], src["bg_pose"], src["occ_score"], src["cls"], ctx_ts, pred_ts)
-            return out[0][:, :, :3].mean()
-        lv = {k: src[k].detach().requires_grad_(backward and not (args.no_input_grad and k == "input")) for k in keys}
-        with torch.set_grad_enabled(backward):
-            occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, lv["obj_alpha_raw"], om, bg, lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
-            out = wb.decode_output(warper, lv["input"], grid, occ, oa, ba, lv["cls"], ctx_ts, pred_ts, cfg.restrict_to_ctx)
-        if backward:
-            torch.autograd.backward([out[0], out[1], out[5]], [g_output, g_flow, g_raw])
-            if grad_buf is not None:
-                grad_buf.reduce()
-        return out[0].detach()[:, :, :3].mean()   # the step's metric (mean predicted RGB), read back in the e2e leg
-
-    def endless(batch):
-        while True:
-            yield batch
-
-    feeder = {}
-
-    def e2e_step():
-        # the public feeding API: the next batch is copied from pinned host memory on a side stream while this one is
-        # processed; every step's inputs cross PCIe inside the timed region and the step's metric is read back
-        metric = step(next(feeder["it"]))
-        loss_host.copy_(metric.reshape(1), non_blocking=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        return sharding.max_over_ranks([e0.elapsed_time(e1)], device=dev)[0] / steps
 
     clocks = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
-        step(resident)
+        r.step(r.resident)
     clocks.wait_ready()
     # ---- device-resident timing, with the dominant kernels bracketed by events inside the timed region
-    if not use_graph["on"]:
-        Fn.PROFILE = {}
-    launches0 = lib.waldo_launch_count()
     clocks.mark_begin()
-    ms_step = timed(lambda: step(resident), args.steps)
+    ms_step, launches, prof = r.measure(args.steps, 0)
     clocks.mark_end()
-    launches = lib.waldo_launch_count() - launches0
     kernel_timing = "CUDA events around each kernel inside the timed region"
-    if use_graph["on"]:
+    if r.graphed is not None:
         # a replayed graph cannot be bracketed kernel by kernel: time the same kernels in an extra eager pass
         with torch.no_grad():
-            launches1 = lib.waldo_launch_count()
-            occ_, oa_, ba_, grid_ = wb.estimate_alpha_grid_occ(warper, resident["obj_alpha_raw"], om, bg, resident["obj_pose"], resident["bg_pose"], resident["occ_score"])
-            wb.decode_output(warper, resident["input"], grid_, occ_, oa_, ba_, resident["cls"], ctx_ts, pred_ts, cfg.restrict_to_ctx)
-            per_step = lib.waldo_launch_count() - launches1   # kernels of this library in one chain = kernel nodes of the graph
+            launches1 = r.lib.waldo_launch_count()
+            occ_, oa_, ba_, grid_ = wb.estimate_alpha_grid_occ(r.warper, r.resident["obj_alpha_raw"], r.om, r.bg, r.resident["obj_pose"], r.resident["bg_pose"], r.resident["occ_score"])
+            wb.decode_output(r.warper, r.resident["input"], grid_, occ_, oa_, ba_, r.resident["cls"], r.ctx_ts, r.pred_ts, cfg.restrict_to_ctx)
+            per_step = r.lib.waldo_launch_count() - launches1   # kernels of this library in one chain = kernel nodes of the graph
             Fn.PROFILE = {}
             for _ in range(args.steps):
-                wb.decode_output(warper, resident["input"], grid_, occ_, oa_, ba_, resident["cls"], ctx_ts, pred_ts, cfg.restrict_to_ctx)
+                wb.decode_output(r.warper, r.resident["input"], grid_, occ_, oa_, ba_, r.resident["cls"], r.ctx_ts, r.pred_ts, cfg.restrict_to_ctx)
             torch.cuda.synchronize()
             del occ_, oa_, ba_, grid_
         launches = args.steps * per_step
         kernel_timing = "extra eager pass after the timed region (the timed region replays one CUDA graph per step)"
-    prof = {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in Fn.PROFILE.items()}
-    Fn.PROFILE = None
+        prof = {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in Fn.PROFILE.items()}
+        Fn.PROFILE = None
     # ---- end to end: pinned host -> device copies and the loss read-back inside the timed region
     e2e = None
     if not args.no_e2e:
         nbytes = lambda d: sum(t.numel() * t.element_size() for t in d.values())
+
+        def endless(batch):
+            while True:
+                yield batch
         # (a) 8-bit frames + labels over PCIe, expanded on the device (the shipped input pipeline)
-        feeder["it"] = wb.DevicePrefetcher(endless(pinned), dev, num_lyt=cfg.num_lyt)
+        r.feeder = wb.DevicePrefetcher(endless(r.pinned), dev, num_lyt=cfg.num_lyt)
         for _ in range(3):   # every prefetch slot has been seen once (graph replay captures one graph per slot)
-            e2e_step()
-        ms_e2e = timed(e2e_step, args.steps)
+            r.e2e_step()
+        ms_e2e = r.timed(r.e2e_step, args.steps)
         e2e = {"value": world * B * Tp / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": nbytes(pinned), "d2h_bytes_per_step": 4,
+               "h2d_bytes_per_step": nbytes(r.pinned), "d2h_bytes_per_step": 4,
                "api": "waldo_b200.DevicePrefetcher (8-bit RGB + label map, pack_input on device, copy overlapped with the previous step)"}
         # (b) for comparison: the fp32 `input` tensor itself shipped every step (what the reference's to_cuda moves)
-        feeder["it"] = None
-        pinned32 = {k: pinned[k] for k in small}
-        pinned32["input"] = resident["input"].cpu().pin_memory()
-        feeder["it"] = wb.DevicePrefetcher(endless(pinned32), dev)
+        r.feeder = None
+        pinned32 = {k: r.pinned[k] for k in r.small}
+        pinned32["input"] = r.resident["input"].cpu().pin_memory()
+        r.feeder = wb.DevicePrefetcher(endless(pinned32), dev)
         for _ in range(3):
-            e2e_step()
-        ms32 = timed(e2e_step, args.steps)
+            r.e2e_step()
+        ms32 = r.timed(r.e2e_step, args.steps)
         e2e["fp32_input"] = {"value": world * B * Tp / (ms32 * 1e-3), "ms_per_step": ms32, "h2d_bytes_per_step": nbytes(pinned32)}
-        feeder["it"] = None
+        r.feeder = None
+        del pinned32
+
+    # ---- the north star's deterministic-gradient contract and the other BASELINE configurations, same process, every N
+    det_leg, others = None, {}
+    if not args.no_others and args.workload == "city_train" and not args.batch:
+        if backward and not args.deterministic:
+            rd = Runner(args, cfg, spec, rank, local_rank, world, deterministic=True)
+            rd.resident, rd.pinned = r.resident, r.pinned      # same inputs, no second copy
+            ms_d, _, _ = rd.measure(max(3, args.steps // 2), 3, profile=False)
+            det_leg = dict(rd.summary(ms_d), mode="order-independent 64-bit fixed-point accumulation of every scatter target; bit-identical gradients run to run",
+                           slowdown_vs_default=ms_d / ms_step)
+            del rd
+        del r.g_output, r.g_flow, r.g_raw
+        keep_input = r.resident.pop("input")
+        del keep_input
+        torch.cuda.empty_cache()
+        for name in ("city_rollout", "kitti_rollout", "nonrigid_train"):
+            try:
+                c2, s2 = workload_cfg(name)
+                r2 = Runner(args, c2, s2, rank, local_rank, world)
+                ms2, _, _ = r2.measure(max(3, args.steps // 2), 3, profile=False)
+                others[name] = dict(r2.summary(ms2), workload=s2["label"],
+                                    launch="one CUDA graph replay per step" if r2.graphed is not None else "eager kernel launches (autograd)")
+                del r2
+                torch.cuda.empty_cache()
+            except Exception as e:   # never lose the headline line to a side measurement
+                others[name] = {"error": str(e)[:200]}
 
     clocks.close()
     if rank == 0:
         frames = world * B * Tp
         fwd_b, bwd_b = alg_bytes(cfg, B, Tc, Tp, backward)
         kb = kernel_bytes(cfg, B, Tc, Tp)
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
-        except Exception:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+        peak, peak_src = PEAK["gbs"], PEAK["src"]
         traffic = {}
         if args.workload == "city_train" and not args.batch:   # the ncu --set full capture in profiles/ is of this workload
             try:
@@ -477,9 +537,9 @@ def main():
             "config": {"workload": spec["label"], "per_gpu_batch": B, "contexts": Tc, "future_frames": Tp,
                        "layers": cfg.num_obj + 1, "channels": 3 + cfg.num_lyt, "l2": "working set per step far larger than the 126 MB L2 (input %.2f GB), no flush needed" % (B * T * (3 + cfg.num_lyt) * Hd * Wd * 4 / 1e9),
                        "input": "8-bit RGB + label map expanded to fp32 on the device (pack_input)",
-                       "launch": "one CUDA graph replay per step" if use_graph["on"] else "eager kernel launches (autograd)",
+                       "launch": "one CUDA graph replay per step" if r.graphed is not None else "eager kernel launches (autograd)",
                        "gradient_accumulation": ("64-bit fixed point (deterministic)" if args.deterministic else "fp32 red.global (default)") if backward else None,
-                       "parallelism": f"dp{world} batch-sharded" + (", flat fp32 all-reduce of 56.6 MB per step" if grad_buf is not None else "")},
+                       "parallelism": f"dp{world} batch-sharded" + (", flat fp32 all-reduce of 56.6 MB per step on NCCL's stream, overlapped with this path's backward" if r.grad_buf is not None else "")},
             "clocks": clocks.summary(), "gpu_launches": launches,
             "hbm_frac_step": ((fwd_b + bwd_b) / (ms_step * 1e-3) / 1e9) / peak,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -490,6 +550,10 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if det_leg:
+            line["deterministic"] = det_leg
+        if others:
+            line["other_workloads"] = others
         if world == 1 and not args.no_cpu_baseline:
             torch.cuda.empty_cache()
             try:
@@ -502,6 +566,7 @@ def main():
                 line["cpu_baseline"]["c1_forward_split"] = cpu_c1_split(cfg)
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -55,15 +55,10 @@ def load_case(name):
     return cfg, (B, T, Tc), d
 
 
-def make_opt(cfg: wo.PathConfig):
+def make_opt(cfg):
     """The option namespace the reference's Warper reads (lvd.py:470-499), filled from a PathConfig."""
-    return types.SimpleNamespace(
-        latent_shape=list(cfg.latent_shape), obj_shape=list(cfg.obj_shape), time_dropout=False, num_obj=cfg.num_obj,
-        patch_size=cfg.patch_size, scale_factor=cfg.scale_factor, dim=cfg.dim, aspect_ratio=cfg.aspect_ratio,
-        load_dim=cfg.load_dim, num_perm_grid=1, normalize_alpha=False, use_lyt_filtering=True, use_lyt_opacity=True,
-        weight_cls=cfg.weight_cls, min_cls=cfg.min_cls, include_self=cfg.include_self, no_filter=cfg.no_filter,
-        allow_ghost=cfg.allow_ghost, use_disocc=cfg.use_disocc, pad_obj_alpha=cfg.pad_obj_alpha,
-        pad_bg_alpha=cfg.pad_bg_alpha)
+    from waldo_b200 import workloads
+    return workloads.make_opt(cfg)
 
 
 def arbitrated(k, ref32, f64, tol, what):

@@ -48,6 +48,20 @@ def _worker(rank, world, port, out):
             for i, p in enumerate(params):
                 want = sum(per_rank[r][i] for r in range(world)) / world
                 assert torch.allclose(p.grad, want, atol=tol, rtol=tol), (wire, i)
+        # --- the overlapped form (start on the backend's stream, finish later) gives the same averages
+        for p, g in zip(params, per_rank[rank]):
+            p.grad.copy_(g)
+        red = sharding.FlatGradReducer(params)
+        work = red.reduce_async()
+        red.finish(work)
+        for i, p in enumerate(params):
+            want = sum(per_rank[r][i] for r in range(world)) / world
+            assert torch.allclose(p.grad, want, atol=1e-6, rtol=1e-6), ("async", i)
+        # --- a parameter unused on THIS rank still receives the averaged gradient (replicas must not diverge)
+        q = [torch.nn.Parameter(torch.zeros(4))]
+        q[0].grad = torch.full((4,), 2.0) if rank == 0 else None
+        sharding.FlatGradReducer(q).reduce()
+        assert q[0].grad is not None and torch.allclose(q[0].grad, torch.full((4,), 1.0)), "unused-parameter gradient"
         # --- NaN flag and timing reductions
         assert sharding.any_nan(torch.tensor(rank == 1)) is True
         assert sharding.any_nan(torch.tensor(False)) is False

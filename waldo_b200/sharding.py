@@ -58,18 +58,39 @@ class FlatGradReducer:
             self.offsets.append(o)
             o += p.numel()
 
-    def reduce(self) -> torch.Tensor:
-        """Pack -> all_reduce(SUM) -> / world -> unpack into .grad.  Returns the flat (averaged) buffer."""
-        _, ws = world()
+    def _pack(self):
         for p, o in zip(self.params, self.offsets):
             seg = self.flat[o:o + p.numel()]
             if p.grad is None:
                 seg.zero_()
             else:
                 seg.copy_(p.grad.reshape(-1))
+
+    def reduce_async(self):
+        """Pack and START the all-reduce on the backend's own stream (NCCL: its internal stream, so it overlaps with
+        whatever the caller enqueues next -- e.g. the rest of a backward pass).  Returns the work handle for finish()."""
+        _, ws = world()
+        self._pack()
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True) if ws > 1 else None
+
+    def finish(self, work) -> torch.Tensor:
+        """Wait for reduce_async()'s exchange (the caller's stream waits, not the host), average and unpack into .grad."""
+        _, ws = world()
+        if work is not None:
+            work.wait()
+            self.flat.div_(ws)
+        return self._unpack(ws)
+
+    def reduce(self) -> torch.Tensor:
+        """Pack -> all_reduce(SUM) -> / world -> unpack into .grad.  Returns the flat (averaged) buffer."""
+        _, ws = world()
+        self._pack()
         if ws > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(ws)
+        return self._unpack(ws)
+
+    def _unpack(self, ws) -> torch.Tensor:
         for p, o in zip(self.params, self.offsets):
             seg = self.flat[o:o + p.numel()]
             if p.grad is not None:
