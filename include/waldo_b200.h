@@ -292,6 +292,19 @@ typedef struct {
 } waldo_pack_input_t;
 int waldo_pack_input(const waldo_pack_input_t*, waldo_stream_t);
 
+/* ------------------------------------------------------------------ f-4  output side (caller side of the path)
+ * tools/utils.py:246-249 (normalize: clamp to [lo, hi], rescale to [0, 1]) and :258-264 (dump_video: permute to
+ * (T, H, W, 3), * 255, truncate to uint8), done on the device so that one byte per sample crosses PCIe and the layout
+ * the video writer wants comes out of the kernel.  models/synthesizer.py:184-193 save_vid then only encodes. */
+typedef struct {
+  int n;                      /* frames */
+  int HW;                     /* Hd*Wd */
+  float lo, hi;               /* span, [-1, 1] in the reference */
+  const float* frames;        /* (n, 3, HW) fp32, planar */
+  uint8_t* out;               /* out (n, HW, 3) */
+} waldo_frames_u8_t;
+int waldo_frames_to_u8(const waldo_frames_u8_t*, waldo_stream_t);
+
 #ifdef __cplusplus
 }
 #endif

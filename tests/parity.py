@@ -472,6 +472,24 @@ def check_pack_input(dev, B=2, T=3, Hd=12, Wd=20, num_lyt=20, seed=5):
     assert torch.equal(wb.pack_input(ramp.to(dev), lab.to(dev), 2).cpu()[:, :, :3], reference_pack(ramp, lab, 2)[:, :, :3])
 
 
+# ------------------------------------------------------------------------------------------------ f-4 output side
+def check_frames_to_u8(dev, seed=9):
+    """Bit-exact against the reference's own formulas (tools/utils.py:246-249 normalize, :258-264 dump_video), restated
+    with the same torch ops, on values inside, outside and exactly on the span, multiple-of-4 and ragged pixel counts."""
+    g = torch.Generator().manual_seed(seed)
+    for shape in ((2, 3, 3, 16, 24), (5, 3, 7, 9)):
+        vid = torch.rand(*shape, generator=g) * 2.6 - 1.3
+        vid.view(-1)[:6] = torch.tensor([-1.0, 1.0, 0.0, -1.5, 1.5, 1.0 - 1e-7])
+        t = vid.clamp(-1, 1)
+        t = (t - (-1)) / (1 - (-1))
+        want = (t.movedim(-3, -1) * 255).to(dtype=torch.uint8)
+        got = wb.frames_to_u8(vid.to(dev)).cpu()
+        assert got.shape == want.shape and torch.equal(got, want), "frames_to_u8 differs from normalize + dump_video"
+    ramp = torch.linspace(-1, 1, 3 * 64 * 64).view(1, 3, 64, 64)
+    want = (((ramp.clamp(-1, 1) + 1) / 2).movedim(-3, -1) * 255).to(torch.uint8)
+    assert torch.equal(wb.frames_to_u8(ramp.to(dev)).cpu(), want)
+
+
 # ------------------------------------------------------------------------------------------------ a-5 / a-11
 def check_field_warps(dev, case):
     """Stand-alone obj/bg/layer_to_output (lvd.py:533-559) and the MAT propagation flows (lvd.py:575-600) against the same

@@ -59,6 +59,10 @@ def test_pack_input():
     parity.check_pack_input(DEV)
 
 
+def test_frames_to_u8():
+    parity.check_frames_to_u8(DEV)
+
+
 @pytest.mark.parametrize("case", ["city_x4", "kitti_x2", "train_lo"])
 def test_field_warps(case):
     parity.check_field_warps(DEV, case)

@@ -85,6 +85,10 @@ def test_pack_input(dev):
     parity.check_pack_input(dev, B=1, T=2, Hd=256, Wd=832, num_lyt=19)
 
 
+def test_frames_to_u8(dev):
+    parity.check_frames_to_u8(dev)
+
+
 def test_device_prefetcher(dev):
     """Batches arrive on the device intact and in order while the previous one is still being consumed; 8-bit RGB +
     labels are expanded to the fp32 `input` exactly as the host formulas do."""

@@ -104,6 +104,10 @@ class PackInput(C.Structure):
                 ("rgb_u8", c_void_p), ("rgb_f32", c_void_p), ("label", c_void_p), ("input", c_void_p)]
 
 
+class FramesU8(C.Structure):
+    _fields_ = [("n", C.c_int), ("HW", C.c_int), ("lo", C.c_float), ("hi", C.c_float), ("frames", c_void_p), ("out", c_void_p)]
+
+
 # flags of Geom.flags (include/waldo_b200.h)
 F_RESTRICT_CTX, F_FILTER, F_WEIGHT_CLS, F_HAS_CLS, F_IS_OBJ, F_INCLUDE_SELF, F_USE_DISOCC, F_OCC_PAIRS = (1 << i for i in range(8))
 
@@ -112,11 +116,13 @@ MAX_LAYERS, MAX_CH, MAX_LYT, MAX_TPS_K = 17, 24, 21, 256
 STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwarp_fwd_t": InvWarpFwd,
              "waldo_invwarp_bwd_t": InvWarpBwd, "waldo_geom_t": Geom, "waldo_decode_fwd_t": DecodeFwd,
              "waldo_decode_bwd_t": DecodeBwd, "waldo_wif_fuse_fwd_t": WifFuseFwd, "waldo_wif_fuse_bwd_t": WifFuseBwd,
-             "waldo_pack_input_t": PackInput, "waldo_warp_field_t": WarpField, "waldo_resize_t": Resize}
+             "waldo_pack_input_t": PackInput, "waldo_warp_field_t": WarpField, "waldo_resize_t": Resize,
+             "waldo_frames_u8_t": FramesU8}
 
 EXPORTS = ["waldo_last_error", "waldo_abi_version", "waldo_has_device_code", "waldo_launch_count", "waldo_tps_fwd", "waldo_tps_bwd",
            "waldo_invwarp_fwd", "waldo_invwarp_bwd", "waldo_occ_fwd", "waldo_occ_bwd", "waldo_decode_fwd",
-           "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input", "waldo_warp_field_fwd", "waldo_resize_bilinear_fwd"]
+           "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input", "waldo_warp_field_fwd", "waldo_resize_bilinear_fwd",
+           "waldo_frames_to_u8"]
 
 _lock = threading.Lock()
 _lib = None
@@ -131,7 +137,7 @@ def _declare(lib):
     for name, st in (("waldo_tps_fwd", TpsFwd), ("waldo_tps_bwd", TpsBwd), ("waldo_invwarp_fwd", InvWarpFwd),
                      ("waldo_invwarp_bwd", InvWarpBwd), ("waldo_decode_fwd", DecodeFwd), ("waldo_decode_bwd", DecodeBwd),
                      ("waldo_wif_fuse_fwd", WifFuseFwd), ("waldo_wif_fuse_bwd", WifFuseBwd), ("waldo_pack_input", PackInput), ("waldo_warp_field_fwd", WarpField),
-                     ("waldo_resize_bilinear_fwd", Resize)):
+                     ("waldo_resize_bilinear_fwd", Resize), ("waldo_frames_to_u8", FramesU8)):
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(st), c_void_p]
         fn.restype = C.c_int

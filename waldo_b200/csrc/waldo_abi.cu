@@ -287,4 +287,15 @@ int waldo_pack_input(const waldo_pack_input_t* a, waldo_stream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ output side
+int waldo_frames_to_u8(const waldo_frames_u8_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->HW > 0 && a->hi > a->lo, "frames_to_u8: bad sizes / span");
+  WB_REQUIRE(a->frames && a->out, "frames_to_u8: null pointer");
+  WB_REQUIRE(((uintptr_t)a->frames & 15) == 0 && ((uintptr_t)a->out & 3) == 0, "frames_to_u8: frames must be 16-byte, out 4-byte aligned");
+  if (a->n == 0) return 0;
+  WB_LAUNCH(k_frames_to_u8, dim3(wb_blocks(((long long)a->HW + 3) / 4, 256, 1024), a->n), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
 }  // extern "C"

@@ -286,6 +286,9 @@ WB_DEV void wb_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0
 WB_DEV int wb_nth_bit(unsigned m, int nth) { return (int)__fns(m, 0, nth + 1); }
 #endif
 
+// 128-bit read-only load of four consecutive floats (16-byte aligned): LDG.E.128
+WB_DEV float4 wb_ld4f(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
 // ------------------------------------------------------------------ ATen-exact bilinear pieces
 // grid_sampler_2d (bilinear, zeros, align_corners=False), SURVEY.md Appendix C.  The association
 // below -- weights as single products, value accumulated nw -> ne -> sw -> se with fused

@@ -55,3 +55,41 @@ __global__ void __launch_bounds__(256) k_pack_input(waldo_pack_input_t p) {
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// f-4, the output side: tools/utils.py:246-249 `normalize` + :258-264 `dump_video`
+//     tensor.clamp(lo, hi) -> (tensor - lo) / (hi - lo) -> permute(0, 2, 3, 1) * 255 -> uint8 (truncation)
+// done on the device, so that 1 byte per sample crosses PCIe instead of 4 and the (T, H, W, 3) layout the video writer wants
+// is produced by the kernel.  frames (n, 3, HW) fp32 planar -> out (n, HW, 3) uint8.  One thread per 4 consecutive
+// pixels: three 128-bit loads (LDG.E.128, one per colour plane), twelve bytes out as three 32-bit stores.
+WB_DEV unsigned wb_to_u8(float v, float lo, float hi) {
+  // the reference's operation order, one IEEE operation each (no contraction)
+  const float c = fminf(fmaxf(v, lo), hi);
+  const float u = __fmul_rn(__fdiv_rn(__fsub_rn(c, lo), __fsub_rn(hi, lo)), 255.f);
+  return (unsigned)u;   // float -> uint8: truncation toward zero, as Tensor.to(torch.uint8); u is within [0, 255]
+}
+__global__ void __launch_bounds__(256) k_frames_to_u8(waldo_frames_u8_t p) {
+  const size_t HW = (size_t)p.HW;
+  const size_t nq = (HW + 3) / 4;
+  const bool vec = (HW & 3) == 0;
+  const int f = blockIdx.y;
+  const float* base = p.frames + (size_t)f * 3 * HW;
+  uint8_t* out = p.out + (size_t)f * HW * 3;
+  for (size_t gq = (size_t)blockIdx.x * wb_nthr() + wb_tid(); gq < nq; gq += (size_t)gridDim.x * wb_nthr()) {
+    const size_t q = gq * 4;
+    if (vec) {
+      const float4 r = wb_ld4f(base + q), g = wb_ld4f(base + HW + q), b = wb_ld4f(base + 2 * HW + q);
+      const unsigned r0 = wb_to_u8(r.x, p.lo, p.hi), g0 = wb_to_u8(g.x, p.lo, p.hi), b0 = wb_to_u8(b.x, p.lo, p.hi);
+      const unsigned r1 = wb_to_u8(r.y, p.lo, p.hi), g1 = wb_to_u8(g.y, p.lo, p.hi), b1 = wb_to_u8(b.y, p.lo, p.hi);
+      const unsigned r2 = wb_to_u8(r.z, p.lo, p.hi), g2 = wb_to_u8(g.z, p.lo, p.hi), b2 = wb_to_u8(b.z, p.lo, p.hi);
+      const unsigned r3 = wb_to_u8(r.w, p.lo, p.hi), g3 = wb_to_u8(g.w, p.lo, p.hi), b3 = wb_to_u8(b.w, p.lo, p.hi);
+      unsigned* o = reinterpret_cast<unsigned*>(out + q * 3);   // 12 bytes, 4-byte aligned (q is a multiple of 4)
+      o[0] = r0 | (g0 << 8) | (b0 << 16) | (r1 << 24);
+      o[1] = g1 | (b1 << 8) | (r2 << 16) | (g2 << 24);
+      o[2] = b2 | (r3 << 8) | (g3 << 16) | (b3 << 24);
+    } else {
+      for (size_t i = q; i < HW && i < q + 4; ++i)
+        for (int c = 0; c < 3; ++c) out[i * 3 + c] = (uint8_t)wb_to_u8(base[(size_t)c * HW + i], p.lo, p.hi);
+    }
+  }
+}

@@ -555,6 +555,28 @@ def pack_input(rgb, label, num_lyt, on=5.0, off=-5.0, out=None):
     return out
 
 
+# ===================================================================================== f-4 output side
+def frames_to_u8(vid, span=(-1.0, 1.0), out=None):
+    """tools/utils.py:246-249 + :258-264 on the device: vid (..., 3, H, W) fp32 in `span` -> (..., H, W, 3) uint8, the
+    tensor `torchvision.io.write_video` takes (dump_video), so that save_vid's device->host copy (synthesizer.py:184-193)
+    moves one byte per sample.  Data preparation: no gradient."""
+    lib = L.load()
+    if vid.dim() < 3 or vid.size(-3) != 3:
+        raise RuntimeError(f"waldo_b200.frames_to_u8: expected (..., 3, H, W), got {tuple(vid.shape)}")
+    v = _c(vid.detach())
+    *lead, _, H, W = v.shape
+    n = 1
+    for x in lead:
+        n *= x
+    if out is None:
+        out = torch.empty(*lead, H, W, 3, device=v.device, dtype=torch.uint8)
+    elif tuple(out.shape) != (*lead, H, W, 3) or out.dtype != torch.uint8:
+        raise RuntimeError("waldo_b200.frames_to_u8: out has the wrong shape / dtype")
+    a = L.FramesU8(n, H * W, float(span[0]), float(span[1]), L.ptr(v, name="vid"), L.ptr(out, torch.uint8, "out"))
+    L.call(lib.waldo_frames_to_u8, a, v, "frames_to_u8")
+    return out
+
+
 # ===================================================================================== a-5 / a-11 field warp, scale
 def _no_grad_path(*tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):

@@ -328,3 +328,10 @@ def pack_input(rgb, label, num_lyt, out=None):
     """`input` = cat([vid, lyt], dim=2) (synthesizer.py:444) built on the device from 8-bit RGB (or normalised fp32
     frames) and the 8-bit label map, i.e. base_dataset.py:173-183 / :355-372 moved after the host->device copy."""
     return Fn.pack_input(rgb, label, num_lyt, out=out)
+
+
+# ----------------------------------------------------------------------------- f-4 (caller side: the output pipeline)
+def frames_to_u8(vid, span=(-1.0, 1.0), out=None):
+    """What dump_video does to a predicted video before encoding (tools/utils.py:246-249, :258-264), on the device:
+    (..., 3, H, W) fp32 -> (..., H, W, 3) uint8.  save_vid (synthesizer.py:184-193) then copies a quarter of the bytes."""
+    return Fn.frames_to_u8(vid, span, out)
