@@ -50,6 +50,18 @@ def alg_bytes(cfg, B, Tc, Tp, backward):
     return wl.alg_bytes(cfg, B, Tc, Tp, backward)
 
 
+def step_bytes(cfg, B, Tc, Tp, backward, storage="f32"):
+    """alg_bytes for a storage type: with bf16 storage the HD activation streams (input, alpha, raw_output, output) are 2-byte
+    elements, flow (2 floats per pair and pixel, written by the layer kernel and read by the gather kernel) stays fp32."""
+    from waldo_b200 import workloads as wl
+    if storage != "bf16":
+        return wl.alg_bytes(cfg, B, Tc, Tp, backward)
+    assert not backward
+    fwd2, _ = wl.alg_bytes(cfg, B, Tc, Tp, False, elem=2)
+    Hd, Wd = cfg.hd_shape
+    return fwd2 + Hd * Wd * 2 * (B * Tc * Tp * (2 + 2 + 1)), 0   # flow written + read, score read: fp32
+
+
 def kernel_bytes(cfg, B, Tc, Tp):
     """Algorithmic bytes per launch of the four HD kernels (DESIGN.md "kernels"), fp32.  pair = one (b, tc, tp)."""
     Hd, Wd = cfg.hd_shape
@@ -268,7 +280,7 @@ def run_reference(args, cfg, spec, rank, world):
 class Runner:
     """One workload set up on one GPU: resident inputs, pinned host copies, the step function and the two timers."""
 
-    def __init__(self, args, cfg, spec, rank, local_rank, world, deterministic=False):
+    def __init__(self, args, cfg, spec, rank, local_rank, world, deterministic=False, storage="f32"):
         import torch.distributed as dist
         import waldo_b200 as wb
         from waldo_b200 import _lib, functional as Fn, sharding, workloads as wl
@@ -276,6 +288,10 @@ class Runner:
         self.args, self.cfg, self.spec, self.rank, self.world = args, cfg, spec, rank, world
         self.dev = dev = torch.device("cuda", local_rank)
         self.deterministic = deterministic
+        if storage == "bf16" and spec["backward"]:
+            raise SystemExit("--storage bf16 is the forward / inference variant: use it with a *_rollout workload")
+        self.storage = storage
+        self.st_dtype = torch.bfloat16 if storage == "bf16" else torch.float32
         B, T, Tc, backward = spec["B"], spec["T"], spec["Tc"], spec["backward"]
         self.B, self.T, self.Tc, self.Tp, self.backward = B, T, Tc, T - Tc, backward
         opt = wl.make_opt(cfg)
@@ -293,7 +309,7 @@ class Runner:
         self.pinned["rgb"], self.pinned["label"] = rgb8.pin_memory(), lab8.pin_memory()
         self.ctx_ts, self.pred_ts = host["ctx_ts"].contiguous().to(dev), host["pred_ts"].to(dev)
         self.resident = {k: self.pinned[k].to(dev) for k in self.small}
-        self.resident["input"] = wb.pack_input(self.pinned["rgb"].to(dev), self.pinned["label"].to(dev), cfg.num_lyt)
+        self.resident["input"] = wb.pack_input(self.pinned["rgb"].to(dev), self.pinned["label"].to(dev), cfg.num_lyt, dtype=self.st_dtype)
         del host
         self.grad_buf = None
         if world > 1 and backward:   # the trainable net's gradients (WIF-sized), exchanged as DDP would: one flat all-reduce per step
@@ -375,7 +391,7 @@ class Runner:
         return self.world * self.B * self.Tp
 
     def summary(self, ms):
-        fwd_b, bwd_b = alg_bytes(self.cfg, self.B, self.Tc, self.Tp, self.backward)
+        fwd_b, bwd_b = step_bytes(self.cfg, self.B, self.Tc, self.Tp, self.backward, self.storage)
         return {"value": self.frames() / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
                 "hbm_frac_step": ((fwd_b + bwd_b) / (ms * 1e-3) / 1e9) / PEAK["gbs"]}
 
@@ -404,6 +420,8 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE workloads and the deterministic-mode leg")
     ap.add_argument("--no-input-grad", action="store_true", help="experiment: do not request d input")
     ap.add_argument("--no-graph", action="store_true", help="inference workloads: eager launches instead of CUDA-graph replay")
+    ap.add_argument("--storage", default="f32", choices=["f32", "bf16"],
+                    help="bf16: input / alpha / raw_output / output stored as bf16, fp32 arithmetic (forward / inference workloads only)")
     ap.add_argument("--deterministic", action="store_true",
                     help="backward with 64-bit fixed-point accumulation of the scatter targets (bit-identical gradients run to run)")
     args = ap.parse_args()
@@ -425,7 +443,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     load_peak()
-    r = Runner(args, cfg, spec, rank, local_rank, world, deterministic=args.deterministic)
+    r = Runner(args, cfg, spec, rank, local_rank, world, deterministic=args.deterministic, storage=args.storage)
     B, T, Tc, Tp, backward = r.B, r.T, r.Tc, r.Tp, r.backward
     Hd, Wd = cfg.hd_shape
 
@@ -463,24 +481,25 @@ def main():
             while True:
                 yield batch
         # (a) 8-bit frames + labels over PCIe, expanded on the device (the shipped input pipeline)
-        r.feeder = wb.DevicePrefetcher(endless(r.pinned), dev, num_lyt=cfg.num_lyt)
+        r.feeder = wb.DevicePrefetcher(endless(r.pinned), dev, num_lyt=cfg.num_lyt, input_dtype=r.st_dtype)
         for _ in range(3):   # every prefetch slot has been seen once (graph replay captures one graph per slot)
             r.e2e_step()
         ms_e2e = r.timed(r.e2e_step, args.steps)
         e2e = {"value": world * B * Tp / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": nbytes(r.pinned), "d2h_bytes_per_step": 4,
                "api": "waldo_b200.DevicePrefetcher (8-bit RGB + label map, pack_input on device, copy overlapped with the previous step)"}
-        # (b) for comparison: the fp32 `input` tensor itself shipped every step (what the reference's to_cuda moves)
-        r.feeder = None
-        pinned32 = {k: r.pinned[k] for k in r.small}
-        pinned32["input"] = r.resident["input"].cpu().pin_memory()
-        r.feeder = wb.DevicePrefetcher(endless(pinned32), dev)
-        for _ in range(3):
-            r.e2e_step()
-        ms32 = r.timed(r.e2e_step, args.steps)
-        e2e["fp32_input"] = {"value": world * B * Tp / (ms32 * 1e-3), "ms_per_step": ms32, "h2d_bytes_per_step": nbytes(pinned32)}
-        r.feeder = None
-        del pinned32
+        if args.storage == "f32":
+            # (b) for comparison: the fp32 `input` tensor itself shipped every step (what the reference's to_cuda moves)
+            r.feeder = None
+            pinned32 = {k: r.pinned[k] for k in r.small}
+            pinned32["input"] = r.resident["input"].float().cpu().pin_memory()
+            r.feeder = wb.DevicePrefetcher(endless(pinned32), dev)
+            for _ in range(3):
+                r.e2e_step()
+            ms32 = r.timed(r.e2e_step, args.steps)
+            e2e["fp32_input"] = {"value": world * B * Tp / (ms32 * 1e-3), "ms_per_step": ms32, "h2d_bytes_per_step": nbytes(pinned32)}
+            r.feeder = None
+            del pinned32
 
     # ---- the north star's deterministic-gradient contract and the other BASELINE configurations, same process, every N
     det_leg, others = None, {}
@@ -496,11 +515,14 @@ def main():
         keep_input = r.resident.pop("input")
         del keep_input
         torch.cuda.empty_cache()
-        for name in ("city_rollout", "kitti_rollout", "nonrigid_train"):
+        for name, sto in (("city_rollout", "f32"), ("kitti_rollout", "f32"), ("nonrigid_train", "f32"),
+                          ("city_rollout", "bf16"), ("kitti_rollout", "bf16")):
             try:
                 c2, s2 = workload_cfg(name)
-                r2 = Runner(args, c2, s2, rank, local_rank, world)
+                r2 = Runner(args, c2, s2, rank, local_rank, world, storage=sto)
                 ms2, _, _ = r2.measure(max(3, args.steps // 2), 3, profile=False)
+                if sto == "bf16":
+                    name, s2["label"] = name + "_bf16", s2["label"] + ", bf16 storage / fp32 arithmetic (tolerance: tests/parity.py TOL_BF16)"
                 others[name] = dict(r2.summary(ms2), workload=s2["label"],
                                     launch="one CUDA graph replay per step" if r2.graphed is not None else "eager kernel launches (autograd)")
                 del r2
@@ -511,8 +533,13 @@ def main():
     clocks.close()
     if rank == 0:
         frames = world * B * Tp
-        fwd_b, bwd_b = alg_bytes(cfg, B, Tc, Tp, backward)
+        fwd_b, bwd_b = step_bytes(cfg, B, Tc, Tp, backward, args.storage)
         kb = kernel_bytes(cfg, B, Tc, Tp)
+        if args.storage == "bf16":   # per-kernel figures: 2-byte elements except flow / score (see step_bytes)
+            px = Hd * Wd
+            kb = {k: v // 2 for k, v in kb.items()}
+            kb["k_gather_fwd"] += px * 2 * B * Tc * Tp * 3
+            kb["k_layers_fwd"] += px * 2 * B * Tc * Tp * 3
         peak, peak_src = PEAK["gbs"], PEAK["src"]
         traffic = {}
         if args.workload == "city_train" and not args.batch:   # the ncu --set full capture in profiles/ is of this workload
@@ -533,10 +560,10 @@ def main():
         line = {
             "metric": "warped+composited frames/s", "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.storage == "f32" else "f32 arithmetic on bf16 storage", "data": "synthetic",
             "config": {"workload": spec["label"], "per_gpu_batch": B, "contexts": Tc, "future_frames": Tp,
                        "layers": cfg.num_obj + 1, "channels": 3 + cfg.num_lyt, "l2": "working set per step far larger than the 126 MB L2 (input %.2f GB), no flush needed" % (B * T * (3 + cfg.num_lyt) * Hd * Wd * 4 / 1e9),
-                       "input": "8-bit RGB + label map expanded to fp32 on the device (pack_input)",
+                       "input": "8-bit RGB + label map expanded to %s on the device (pack_input)" % ("fp32" if args.storage == "f32" else "bf16"),
                        "launch": "one CUDA graph replay per step" if r.graphed is not None else "eager kernel launches (autograd)",
                        "gradient_accumulation": ("64-bit fixed point (deterministic)" if args.deterministic else "fp32 red.global (default)") if backward else None,
                        "parallelism": f"dp{world} batch-sharded" + (", flat fp32 all-reduce of 56.6 MB per step on NCCL's stream, overlapped with this path's backward" if r.grad_buf is not None else "")},

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define WALDO_ABI_VERSION 1
+#define WALDO_ABI_VERSION 2
 
 /* compile-time capacity of the kernels (per-thread register arrays) */
 #define WALDO_MAX_LAYERS 17   /* L  = num_obj + 1 */
@@ -51,6 +51,13 @@ enum {
   WALDO_F_USE_DISOCC   = 1 << 6, /* lvd.py:148-151 disocc appended to raw_output                     */
   WALDO_F_OCC_PAIRS    = 1 << 7  /* backward only: d_occ feeds waldo_occ_bwd and nothing else, so its row 0, column 0
                                     and diagonal (constants of lvd.py:63-66, never read there) are left at zero      */
+};
+
+/* storage type of the HD activations of waldo_decode_fwd_t (input, alpha, raw_output, out_full) */
+enum {
+  WALDO_ST_F32  = 0,  /* the reference's precision: parity rules 1-3 apply                                                */
+  WALDO_ST_BF16 = 1   /* bf16 storage, fp32 arithmetic, forward / inference only (half the HBM bytes of the HD streams);
+                         the four pointers then address bf16 elements; tolerance stated in tests/parity.py (rule 4)       */
 };
 
 typedef void* waldo_stream_t; /* cudaStream_t */
@@ -180,6 +187,8 @@ typedef struct {
   float* score;               /* (B, Tc, Tp, Hd, Wd) sum_k Actx_k per pair (lvd.py:841), glue between the two HD kernels */
   int stages;                 /* 0 = everything; else bit 0 = low-res kernels (B1, B2, B5), bit 3 = HD context-alpha kernel (B2b-B4),
                                  bit 1 = HD layer kernel (B5up-B9), bit 2 = HD gather kernel (stage C) */
+  int storage;                /* WALDO_ST_F32 | WALDO_ST_BF16: element type of input, alpha, raw_output, out_full (everything else,
+                                 incl. flow / norm / score and all low-res tensors, stays fp32).  waldo_decode_bwd needs WALDO_ST_F32 */
 } waldo_decode_fwd_t;
 int waldo_decode_fwd(const waldo_decode_fwd_t*, waldo_stream_t);
 
@@ -289,6 +298,8 @@ typedef struct {
   const float* rgb_f32;       /* (n, 3, HW) already normalised frames (used when rgb_u8 is NULL) */
   const uint8_t* label;       /* (n, HW) class ids; ids >= Nl light no channel */
   float* input;               /* out (n, 3+Nl, HW) */
+  int storage;                /* element type of `input`: WALDO_ST_F32, or WALDO_ST_BF16 (the pointer then addresses bf16 elements;
+                                 +-5 and the 8-bit colours k/127.5 - 1 round to bf16 once, here) */
 } waldo_pack_input_t;
 int waldo_pack_input(const waldo_pack_input_t*, waldo_stream_t);
 

@@ -36,6 +36,17 @@ OUT_NAMES = ["output", "flow", "alpha_unflt", "alpha", "raw_alpha", "raw_output"
 
 FWD_TOL = 1e-5
 GRAD_TOL = 1e-4
+# Rule (4), the bf16-STORAGE variant (input / alpha / raw_output / output held as bf16 in HBM, fp32 arithmetic, forward only;
+# include/waldo_b200.h WALDO_ST_BF16), stated against the fp32 path on the same inputs:
+#   * flow (stays fp32; only sees the bf16 rounding of the stored context opacities): max-abs <= 1e-3 (normalised units);
+#   * alpha, alpha_ctx, raw_alpha (values in [-1, 1]; one bf16 rounding is 2^-9 relative): max-abs <= 1.6e-2 (= 2^-6);
+#   * raw_output image / layout channels (values in [-5, 5]: one rounding at |v| >= 4 is already 1.56e-2, and the one-hot
+#     +-5 layout logits jump by 10 between neighbouring pixels, so a 1e-3-pixel shift of a tap shows up as 1e-2):
+#     mean-abs <= 5e-3, 99.9th percentile <= 0.1, max-abs <= 0.5;
+#   * output (the score-weighted mean of the contexts, lvd.py:850-851: divides by the summed score, which is ~1e-6 where no
+#     context sees the pixel -- the reference's own fp32-vs-fp64 error is O(1) there): where the summed
+#     context score sum_tc sum_k A_k is >= 0.1: mean-abs <= 8e-3, max-abs <= 0.25; elsewhere finite.
+TOL_BF16 = dict(flow_max=1e-3, alpha_max=1.6e-2, raw_mean=5e-3, raw_p999=0.1, raw_max=0.5, out_norm=0.1, out_mean=8e-3, out_max=0.25)
 
 
 def load_case(name):
@@ -233,6 +244,63 @@ def check_decode(dev, case):
         assert torch.equal(k.argmax(dim=-3)[safe], r.argmax(dim=-3)[safe]), f"{n}: layer argmax differs"
     for kname in LEAF_KEYS:
         grad_close(g[kname], g32[kname], g64[kname], f"{case}/d {kname}")
+
+
+def _pct(e, q):
+    e = e.flatten()
+    return float(e.kthvalue(max(1, min(e.numel(), int(round(e.numel() * q)))))[0])
+
+
+def bf16_close(out32, out16, what, report=None):
+    """TOL_BF16 between a tuple of fp32 outputs (OUT_NAMES order) and the bf16-storage variant's."""
+    t = TOL_BF16
+    ac = out32[OUT_NAMES.index("alpha_ctx")].detach().float().cpu()
+    seen = (((ac + 1) / 2).sum(3).sum(1) >= t["out_norm"]).unsqueeze(2)   # (B, Tp, 1, Hd, Wd): some context sees the pixel
+    for n, x, y in zip(OUT_NAMES, out32, out16):
+        assert (x is None) == (y is None), n
+        if x is None:
+            continue
+        want = torch.float32 if n == "flow" else torch.bfloat16
+        assert y.dtype == want and tuple(y.shape) == tuple(x.shape), f"{what}/{n}: {y.dtype} {tuple(y.shape)}"
+        e = (x.detach().float().cpu() - y.detach().float().cpu()).abs()
+        assert bool(torch.isfinite(e).all()), f"{what}/{n}: non-finite"
+        mx, mean = float(e.max()), float(e.mean())
+        if report is not None:
+            report[n] = dict(max_abs=mx, mean_abs=mean, p99=_pct(e, 0.99), p999=_pct(e, 0.999))
+        if n == "flow":
+            assert mx <= t["flow_max"], f"{what}/flow: {mx:.3e}"
+        elif n in ("alpha", "alpha_unflt", "alpha_ctx", "raw_alpha"):
+            assert mx <= t["alpha_max"], f"{what}/{n}: {mx:.3e}"
+        elif n == "raw_output":
+            assert mean <= t["raw_mean"] and _pct(e, 0.999) <= t["raw_p999"] and mx <= t["raw_max"], \
+                f"{what}/raw_output: mean {mean:.3e} p99.9 {_pct(e, 0.999):.3e} max {mx:.3e}"
+        elif n == "output":
+            es = e[seen.expand_as(e)]
+            if report is not None:
+                report[n].update(seen_frac=float(seen.float().mean()), seen_max_abs=float(es.max()), seen_mean_abs=float(es.mean()))
+            assert float(es.mean()) <= t["out_mean"] and float(es.max()) <= t["out_max"], \
+                f"{what}/output: mean {float(es.mean()):.3e} max {float(es.max()):.3e} over the seen pixels"
+
+
+def check_decode_bf16(dev, case):
+    """Rule (4): the bf16-storage variant of decode_output (forward / inference) against the fp32 kernels AND the oracle on the
+    same inputs, within TOL_BF16; index-valued decisions (live-layer masks, is_obj) do not depend on the storage type, which
+    shows as `flow` agreeing to 1e-3.  Asking for gradients through it must raise."""
+    cfg, _, z = load_case(case)
+    with torch.no_grad():
+        o32, _ = oracle_decode(cfg, z, torch.float32, with_grad=False)
+        k32, _ = kernel_decode(dev, cfg, z, with_grad=False)
+        zb = dict(z)
+        zb["in_input"] = z["in_input"].to(torch.bfloat16)
+        k16, _ = kernel_decode(dev, cfg, zb, with_grad=False)
+    bf16_close(k32, k16, f"{case} (vs fp32 kernels)")
+    bf16_close(o32, k16, f"{case} (vs oracle)")
+    try:
+        kernel_decode(dev, cfg, zb, with_grad=True)
+    except RuntimeError as e:
+        assert "forward / inference only" in str(e)
+    else:
+        raise AssertionError("bf16 storage with gradients must raise")
 
 
 def check_decode_deterministic(dev, case):
@@ -466,6 +534,9 @@ def check_pack_input(dev, B=2, T=3, Hd=12, Wd=20, num_lyt=20, seed=5):
         rgbf = torch.rand(B, T, 3, h, w, generator=g) * 2 - 1
         got = wb.pack_input(rgbf.to(dev), lab.to(dev), num_lyt).cpu()
         assert torch.equal(got, reference_pack(rgbf, lab, num_lyt))
+        # bf16 storage: the same values rounded once to bf16 (round to nearest even, as Tensor.to(torch.bfloat16))
+        got = wb.pack_input(rgb8.to(dev), lab.to(dev), num_lyt, dtype=torch.bfloat16).cpu()
+        assert got.dtype == torch.bfloat16 and torch.equal(got, want.to(torch.bfloat16)), "pack_input(bf16) differs"
     # every 8-bit value maps exactly as torchvision's ToTensor + Normalize
     ramp = torch.arange(256, dtype=torch.uint8).view(1, 1, 1, 16, 16).expand(1, 1, 3, 16, 16).contiguous()
     lab = torch.zeros(1, 1, 16, 16, dtype=torch.uint8)

@@ -22,7 +22,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.waldo_abi_version() == 1
+    assert lib.waldo_abi_version() == _lib.ABI_VERSION
     assert lib.waldo_has_device_code() == 1
     assert lib.waldo_last_error() is not None
 

@@ -42,6 +42,11 @@ def test_decode_deterministic(case):
 
 
 @pytest.mark.parametrize("case", parity.CASES)
+def test_decode_bf16_storage(case):
+    parity.check_decode_bf16(DEV, case)
+
+
+@pytest.mark.parametrize("case", parity.CASES)
 def test_end_to_end(case):
     parity.check_end_to_end(DEV, case)
 

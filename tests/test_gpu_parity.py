@@ -38,6 +38,11 @@ def test_decode(dev, case):
 
 
 @pytest.mark.parametrize("case", parity.CASES)
+def test_decode_bf16_storage(dev, case):
+    parity.check_decode_bf16(dev, case)
+
+
+@pytest.mark.parametrize("case", parity.CASES)
 def test_decode_deterministic(dev, case):
     parity.check_decode_deterministic(dev, case)
 

@@ -65,7 +65,7 @@ class DecodeFwd(C.Structure):
                 ("a_lo", c_void_p), ("prof_part", c_void_p), ("prof_ctas", C.c_int), ("prof_sum", c_void_p),
                 ("prof_p", c_void_p), ("lyt_lo", c_void_p), ("f_lo", c_void_p), ("s_lo", c_void_p), ("live_ctx", c_void_p), ("live_pred", c_void_p),
                 ("alpha", c_void_p), ("flow", c_void_p), ("raw_output", c_void_p), ("out_full", c_void_p),
-                ("norm", c_void_p), ("score", c_void_p), ("stages", C.c_int)]
+                ("norm", c_void_p), ("score", c_void_p), ("stages", C.c_int), ("storage", C.c_int)]
 
 
 class DecodeBwd(C.Structure):
@@ -101,7 +101,7 @@ class Resize(C.Structure):
 
 class PackInput(C.Structure):
     _fields_ = [("n", C.c_int), ("Nl", C.c_int), ("HW", C.c_int), ("on", C.c_float), ("off", C.c_float),
-                ("rgb_u8", c_void_p), ("rgb_f32", c_void_p), ("label", c_void_p), ("input", c_void_p)]
+                ("rgb_u8", c_void_p), ("rgb_f32", c_void_p), ("label", c_void_p), ("input", c_void_p), ("storage", C.c_int)]
 
 
 class FramesU8(C.Structure):
@@ -112,6 +112,8 @@ class FramesU8(C.Structure):
 F_RESTRICT_CTX, F_FILTER, F_WEIGHT_CLS, F_HAS_CLS, F_IS_OBJ, F_INCLUDE_SELF, F_USE_DISOCC, F_OCC_PAIRS = (1 << i for i in range(8))
 
 MAX_LAYERS, MAX_CH, MAX_LYT, MAX_TPS_K = 17, 24, 21, 256
+ABI_VERSION = 2
+ST_F32, ST_BF16 = 0, 1   # DecodeFwd.storage
 
 STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwarp_fwd_t": InvWarpFwd,
              "waldo_invwarp_bwd_t": InvWarpBwd, "waldo_geom_t": Geom, "waldo_decode_fwd_t": DecodeFwd,
@@ -166,7 +168,7 @@ def load(build_if_missing: bool = True):
             raise RuntimeError(f"waldo_b200: {LIB_PATH} not found; run `python -m waldo_b200.build` (needs nvcc). "
                                "There is no CPU fallback.")
         lib = _declare(C.CDLL(LIB_PATH))
-        if lib.waldo_abi_version() != 1:
+        if lib.waldo_abi_version() != ABI_VERSION:
             raise RuntimeError("waldo_b200: ABI version mismatch between _lib.py and libwaldo_b200.so")
         if lib.waldo_has_device_code() != 1:
             raise RuntimeError("waldo_b200: library was built without device code; refusing to use it")

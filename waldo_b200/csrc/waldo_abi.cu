@@ -45,6 +45,63 @@ static inline unsigned wb_blocks(long long total, int threads, long long cap = 1
   return (unsigned)b;
 }
 
+// ST = storage type of input / alpha / raw_output / out_full (float, or wb_bf16 for the forward-only bf16-storage variant)
+template <typename ST>
+static int wb_decode_fwd_launch(const waldo_decode_fwd_t& A, waldo_stream_t st) {
+  const waldo_decode_fwd_t* a = &A;
+  const waldo_geom_t& g = a->g;
+  const bool filt = (g.flags & WALDO_F_FILTER) != 0;
+  const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);
+  const int L = g.No + 1, HW = g.H * g.W;
+  const long long HWd = (long long)g.Hd * g.Wd;
+  const bool st_prep = a->stages == 0 || (a->stages & 1), st_layers = a->stages == 0 || (a->stages & 2), st_gather = a->stages == 0 || (a->stages & 4);
+  const bool st_aprep = a->stages == 0 || (a->stages & 8);
+  if (st_prep) {
+  // B1
+  WB_LAUNCH(k_project_alpha, dim3(wb_blocks((long long)g.B * g.Tw * HW, 128)), dim3(128), 0, st, *a);
+  WB_LAUNCHED();
+  // B2
+  if (filt) {
+    if (!from_cls) {
+      if (g.Nl == 20) WB_LAUNCH((k_class_profile<20, ST>), dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
+      else if (g.Nl == 19) WB_LAUNCH((k_class_profile<19, ST>), dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
+      else WB_LAUNCH((k_class_profile<0, ST>), dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
+      WB_LAUNCHED();
+    }
+    WB_LAUNCH(k_profile_final, dim3(g.B), dim3(352), 0, st, *a);
+    WB_LAUNCHED();
+  }
+  }
+  // B2b-B4
+  if (st_aprep) {
+    const dim3 pgrid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tw);
+    if (g.Nl == 20) WB_LAUNCH((k_alpha_prep<20, ST>), pgrid, dim3(WB_TILE_PX), 0, st, *a);        // Cityscapes
+    else if (g.Nl == 19) WB_LAUNCH((k_alpha_prep<19, ST>), pgrid, dim3(WB_TILE_PX), 0, st, *a);   // KITTI
+    else WB_LAUNCH((k_alpha_prep<0, ST>), pgrid, dim3(WB_TILE_PX), 0, st, *a);
+    WB_LAUNCHED();
+  }
+  if (st_prep) {
+  // B5
+  WB_LAUNCH(k_layer_flow_lo, dim3(wb_blocks((long long)g.B * g.Tp * HW, 128)), dim3(128), 0, st, *a);
+  WB_LAUNCHED();
+  }
+  // B5(up)-B9: the layer kernel
+  const dim3 grid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tp);
+  if (st_layers) {
+    WB_LAUNCH(k_layers_fwd<ST>, grid, dim3(WB_TILE_PX), 0, st, *a);
+    WB_LAUNCHED();
+  }
+  // stage C: the gather kernel
+  if (st_gather) {
+    const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
+    if (g.Tc == 4 && !self) WB_LAUNCH((k_gather_fwd<4, true, ST>), grid, dim3(WB_TILE_PX), 0, st, *a);
+    else if (g.Tc <= 4) WB_LAUNCH((k_gather_fwd<4, false, ST>), grid, dim3(WB_TILE_PX), 0, st, *a);
+    else WB_LAUNCH((k_gather_fwd<8, false, ST>), grid, dim3(WB_TILE_PX), 0, st, *a);
+    WB_LAUNCHED();
+  }
+  return 0;
+}
+
 extern "C" {
 
 const char* waldo_last_error(void) { return g_err; }
@@ -186,54 +243,8 @@ int waldo_decode_fwd(const waldo_decode_fwd_t* a, waldo_stream_t st) {
     WB_REQUIRE(a->prof_p, "decode_fwd: prof_p needed for the filter");
     if (!from_cls) WB_REQUIRE(a->prof_part && a->prof_sum && a->prof_ctas > 0, "decode_fwd: profile scratch needed");
   }
-  const int L = g.No + 1, HW = g.H * g.W;
-  const long long HWd = (long long)g.Hd * g.Wd;
-  const bool st_prep = a->stages == 0 || (a->stages & 1), st_layers = a->stages == 0 || (a->stages & 2), st_gather = a->stages == 0 || (a->stages & 4);
-  const bool st_aprep = a->stages == 0 || (a->stages & 8);
-  if (st_prep) {
-  // B1
-  WB_LAUNCH(k_project_alpha, dim3(wb_blocks((long long)g.B * g.Tw * HW, 128)), dim3(128), 0, st, *a);
-  WB_LAUNCHED();
-  // B2
-  if (filt) {
-    if (!from_cls) {
-      if (g.Nl == 20) WB_LAUNCH(k_class_profile<20>, dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
-      else if (g.Nl == 19) WB_LAUNCH(k_class_profile<19>, dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
-      else WB_LAUNCH(k_class_profile<0>, dim3(a->prof_ctas, g.B), dim3(256), 0, st, *a);
-      WB_LAUNCHED();
-    }
-    WB_LAUNCH(k_profile_final, dim3(g.B), dim3(352), 0, st, *a);
-    WB_LAUNCHED();
-  }
-  }
-  // B2b-B4
-  if (st_aprep) {
-    const dim3 pgrid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tw);
-    if (g.Nl == 20) WB_LAUNCH(k_alpha_prep<20>, pgrid, dim3(WB_TILE_PX), 0, st, *a);        // Cityscapes
-    else if (g.Nl == 19) WB_LAUNCH(k_alpha_prep<19>, pgrid, dim3(WB_TILE_PX), 0, st, *a);   // KITTI
-    else WB_LAUNCH(k_alpha_prep<0>, pgrid, dim3(WB_TILE_PX), 0, st, *a);
-    WB_LAUNCHED();
-  }
-  if (st_prep) {
-  // B5
-  WB_LAUNCH(k_layer_flow_lo, dim3(wb_blocks((long long)g.B * g.Tp * HW, 128)), dim3(128), 0, st, *a);
-  WB_LAUNCHED();
-  }
-  // B5(up)-B9: the layer kernel
-  const dim3 grid(wb_blocks(HWd, WB_TILE_PX, 1024), g.B * g.Tp);
-  if (st_layers) {
-    WB_LAUNCH(k_layers_fwd, grid, dim3(WB_TILE_PX), 0, st, *a);
-    WB_LAUNCHED();
-  }
-  // stage C: the gather kernel
-  if (st_gather) {
-    const bool self = (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
-    if (g.Tc == 4 && !self) WB_LAUNCH((k_gather_fwd<4, true>), grid, dim3(WB_TILE_PX), 0, st, *a);
-    else if (g.Tc <= 4) WB_LAUNCH((k_gather_fwd<4, false>), grid, dim3(WB_TILE_PX), 0, st, *a);
-    else WB_LAUNCH((k_gather_fwd<8, false>), grid, dim3(WB_TILE_PX), 0, st, *a);
-    WB_LAUNCHED();
-  }
-  return 0;
+  WB_REQUIRE(a->storage == WALDO_ST_F32 || a->storage == WALDO_ST_BF16, "decode_fwd: unknown storage type %d", a->storage);
+  return a->storage == WALDO_ST_BF16 ? wb_decode_fwd_launch<wb_bf16>(*a, st) : wb_decode_fwd_launch<float>(*a, st);
 }
 
 int waldo_decode_bwd(const waldo_decode_bwd_t* a, waldo_stream_t st) {
@@ -282,7 +293,10 @@ int waldo_pack_input(const waldo_pack_input_t* a, waldo_stream_t st) {
   WB_REQUIRE(a && a->n >= 0 && a->Nl >= 1 && a->HW > 0, "pack_input: bad sizes");
   WB_REQUIRE((a->rgb_u8 || a->rgb_f32) && a->label && a->input, "pack_input: null pointer");
   if (a->n == 0) return 0;
-  WB_LAUNCH(k_pack_input, dim3(wb_blocks(((long long)a->HW + 3) / 4, 256, 1024), a->n), dim3(256), 0, st, *a);
+  WB_REQUIRE(a->storage == WALDO_ST_F32 || a->storage == WALDO_ST_BF16, "pack_input: unknown storage type %d", a->storage);
+  const dim3 grid(wb_blocks(((long long)a->HW + 3) / 4, 256, 1024), a->n);
+  if (a->storage == WALDO_ST_BF16) WB_LAUNCH(k_pack_input<wb_bf16>, grid, dim3(256), 0, st, *a);
+  else WB_LAUNCH(k_pack_input<float>, grid, dim3(256), 0, st, *a);
   WB_LAUNCHED();
   return 0;
 }

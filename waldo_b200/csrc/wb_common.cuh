@@ -45,6 +45,7 @@ static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; retu
 static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
 struct double2 { double x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
@@ -286,6 +287,26 @@ WB_DEV void wb_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0
 WB_DEV int wb_nth_bit(unsigned m, int nth) { return (int)__fns(m, 0, nth + 1); }
 #endif
 
+// ------------------------------------------------------------------ storage types of the HD activations
+// `input`, `alpha`, `raw_output` and `out_full` are stored either as fp32 (the reference's precision; parity rules 1-3) or
+// as bf16 (waldo_decode_fwd_t.storage = 1: half the HBM bytes, fp32 arithmetic throughout; forward / inference only;
+// parity rule 4, tolerance stated in tests/parity.py).  Kernels are templates over the storage type ST.
+struct wb_bf16 { unsigned short x; };
+WB_DEV float wb_lds(const float* p) { return __ldg(p); }
+WB_DEV float wb_lds(const wb_bf16* p) {
+  union { unsigned u; float f; } c;
+  c.u = ((unsigned)__ldg(reinterpret_cast<const unsigned short*>(p))) << 16;   // bf16 -> fp32 is exact
+  return c.f;
+}
+WB_DEV void wb_sts(float* p, float v) { *p = v; }
+WB_DEV void wb_sts(wb_bf16* p, float v) {   // round to nearest even (NaN stays NaN)
+  union { unsigned u; float f; } c;
+  c.f = v;
+  unsigned r = c.u + 0x7fffu + ((c.u >> 16) & 1u);
+  if ((c.u & 0x7fffffffu) > 0x7f800000u) r = c.u | 0x00400000u;
+  p->x = (unsigned short)(r >> 16);
+}
+
 // 128-bit read-only load of four consecutive floats (16-byte aligned): LDG.E.128
 WB_DEV float4 wb_ld4f(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -377,9 +398,10 @@ WB_DEV float wb_gather2(const float* __restrict__ p0, const float* __restrict__ 
   return __fmaf_rn(__ldg(p1 + 1), w[3], __fmaf_rn(__ldg(p1), w[2], __fmaf_rn(__ldg(p0 + 1), w[1], __fmul_rn(__ldg(p0), w[0]))));
 }
 // same for a plane that stores 2A-1 while the sampled quantity is A (zero padding applies to A)
-WB_DEV float wb_gather2_01(const float* __restrict__ p0, const float* __restrict__ p1, const float* w) {
-  const float v0 = (__ldg(p0) + 1.f) * 0.5f, v1 = (__ldg(p0 + 1) + 1.f) * 0.5f;
-  const float v2 = (__ldg(p1) + 1.f) * 0.5f, v3 = (__ldg(p1 + 1) + 1.f) * 0.5f;
+template <typename ST>
+WB_DEV float wb_gather2_01(const ST* __restrict__ p0, const ST* __restrict__ p1, const float* w) {
+  const float v0 = (wb_lds(p0) + 1.f) * 0.5f, v1 = (wb_lds(p0 + 1) + 1.f) * 0.5f;
+  const float v2 = (wb_lds(p1) + 1.f) * 0.5f, v3 = (wb_lds(p1 + 1) + 1.f) * 0.5f;
   return __fmaf_rn(v3, w[3], __fmaf_rn(v2, w[2], __fmaf_rn(v1, w[1], __fmul_rn(v0, w[0]))));
 }
 

@@ -54,9 +54,9 @@ template <int NA> struct WbLay {
 
 // alpha_c = stored context alpha (2A-1) of frame (b,c): (L, Hd, Wd).  All per-thread addressing is 32-bit element
 // offsets against warp-uniform 64-bit bases (a frame never exceeds 2^31 elements).
-template <int NA>
+template <int NA, typename ST>
 WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, const float* __restrict__ f_lo /* (L,H,W,2) of this pair */,
-                          const float* __restrict__ alpha_c, const float* __restrict__ s_occ, WbLay<NA>& ly) {
+                          const ST* __restrict__ alpha_c, const float* __restrict__ s_occ, WbLay<NA>& ly) {
   const waldo_geom_t& g = d.g;
   const int L = g.No + 1;
   const unsigned HW = (unsigned)(g.H * g.W), HWd = (unsigned)(g.Hd * g.Wd);
@@ -78,7 +78,7 @@ WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, 
       if ((px.isobj >> k) & 1u) {
         const WbTaps t = wb_taps(__fadd_rn(px.gx, fx), __fadd_rn(px.gy, fy), g.Wd, g.Hd);
         const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-        const float* pl = alpha_c + (size_t)k * HWd;
+        const ST* pl = alpha_c + (size_t)k * HWd;
         r = wb_gather2_01(pl + t2.o0, pl + t2.o1, t2.w);
       }
       ly.R[s] = r;
@@ -109,28 +109,28 @@ struct WbFwdCtx {   // per-CTA constants of the fused forward
 
 // Layer part of one (pixel, context): evaluates the live layers, writes the alpha channels of raw_output (+ disocc),
 // the reduced flow, and returns (flow, score) for the channel part.
-template <int NA>
+template <int NA, typename ST>
 WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, unsigned wm, const WbIdx<NA>& ix, unsigned q, int c_t, size_t pair,
-                          float* __restrict__ raw, float& flow_x, float& flow_y, float& score) {
+                          ST* __restrict__ raw, float& flow_x, float& flow_y, float& score) {
   const waldo_geom_t& g = d.g;
   const int L = c.L, C = c.C;
   const unsigned HWd = c.HWd;
   const float* f_lo = d.f_lo + pair * L * c.HW * 2;
-  const float* alpha_c = d.alpha + ((size_t)c.b * g.Tw + c_t) * L * HWd;
+  const ST* alpha_c = reinterpret_cast<const ST*>(d.alpha) + ((size_t)c.b * g.Tw + c_t) * L * HWd;
   WbLay<NA> ly;
-  wb_layers_fwd<NA>(d, px, ix, f_lo, alpha_c, c.s_occ, ly);
-  float* ra = raw + (size_t)C * HWd + q;
-  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) *ra = -1.f; ra += HWd; }
+  wb_layers_fwd<NA, ST>(d, px, ix, f_lo, alpha_c, c.s_occ, ly);
+  ST* ra = raw + (size_t)C * HWd + q;
+  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) wb_sts(ra, -1.f); ra += HWd; }
   ra = raw + (size_t)C * HWd + q;
-  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) if (s < ix.n) ra[(size_t)ix.k[s] * HWd] = ly.A[s] * 2.f - 1.f;
-  if (c.disocc_ch) ra[(size_t)L * HWd] = ly.disocc;
+  WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) if (s < ix.n) wb_sts(ra + (size_t)ix.k[s] * HWd, ly.A[s] * 2.f - 1.f);
+  if (c.disocc_ch) wb_sts(ra + (size_t)L * HWd, ly.disocc);
   float* fl = d.flow + pair * 2 * HWd + q;
   fl[0] = ly.flow_x; fl[HWd] = ly.flow_y;
   flow_x = ly.flow_x; flow_y = ly.flow_y; score = ly.score;
 }
 
 // all contexts of one pixel: the slot list is built once
-template <int NA>
+template <int NA, typename ST>
 WB_DEV void wb_fwd_layers_ctxs(const WbDec& d, const WbFwdCtx& c, const WbPix& px, unsigned wm, unsigned q) {
   const waldo_geom_t& g = d.g;
   const int b = c.b, tp = c.tp;
@@ -139,9 +139,9 @@ WB_DEV void wb_fwd_layers_ctxs(const WbDec& d, const WbFwdCtx& c, const WbPix& p
   for (int tc = 0; tc < g.Tc; ++tc) {
     const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
     const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
-    float* raw = d.raw_output + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
+    ST* raw = reinterpret_cast<ST*>(d.raw_output) + (((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR * HWd;
     float flow_x, flow_y, score;
-    wb_fwd_layers<NA>(d, c, px, wm, ix, q, c_t, pair, raw, flow_x, flow_y, score);
+    wb_fwd_layers<NA, ST>(d, c, px, wm, ix, q, c_t, pair, raw, flow_x, flow_y, score);
     d.score[pair * HWd + q] = score;
   }
 }
@@ -153,7 +153,7 @@ WB_DEV void wb_fwd_layers_ctxs(const WbDec& d, const WbFwdCtx& c, const WbPix& p
 // the layers of a pixel load in parallel, the occlusion product and the reductions over layers run on warp shuffles,
 // and there is no per-thread array indexed by a layer.  Results are those of wb_layers_fwd up to the order of the sums
 // over layers in flow / score (each A_k, R_k is bit-identical).
-template <int LP>
+template <int LP, typename ST>
 WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, int n, unsigned isobj_lane, int tx0, int Y,
                                 const WbAxis& ay, float gy) {
   constexpr int PPW = 32 / LP;
@@ -173,12 +173,12 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
     const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
     const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
     const float2* fl = reinterpret_cast<const float2*>(d.f_lo) + (pair * L + k) * HW;
-    const float* alpha_k = d.alpha + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
-    float* ra = d.raw_output + ((((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR + C) * HWd;   // alpha channels of this pair
+    const ST* alpha_k = reinterpret_cast<const ST*>(d.alpha) + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
+    ST* ra = reinterpret_cast<ST*>(d.raw_output) + ((((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR + C) * HWd;   // alpha channels of this pair
     float* flo = d.flow + pair * 2 * HWd;
     float* sco = d.score + pair * HWd;
     // layers outside the row's union are fully transparent
-    { float* o = ra + ql; WB_UNROLL for (int kk = 0; kk < WB_MAX_L; ++kk) { if (kk < L && !((wm >> kk) & 1u)) *o = -1.f; o += HWd; } }
+    { ST* o = ra + ql; WB_UNROLL for (int kk = 0; kk < WB_MAX_L; ++kk) { if (kk < L && !((wm >> kk) & 1u)) wb_sts(o, -1.f); o += HWd; } }
 #pragma unroll 1
     for (int r = 0; r < LP; ++r) {
       const int p = r * PPW + pl, X = min(tx0 + p, g.Wd - 1);
@@ -217,10 +217,10 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
         fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o);
         sc += __shfl_xor_sync(0xffffffffu, sc, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       }
-      if (valid) ra[(size_t)k * HWd + q] = A * 2.f - 1.f;
+      if (valid) wb_sts(ra + ((size_t)k * HWd + q), A * 2.f - 1.f);
       if (slot == 0) {
         flo[q] = fx; flo[HWd + q] = fy; sco[q] = sc;
-        if (c.disocc_ch) ra[(size_t)L * HWd + q] = mx;
+        if (c.disocc_ch) wb_sts(ra + ((size_t)L * HWd + q), mx);
       }
     }
   }
@@ -236,6 +236,7 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
 // ------------------------------------------------------------------------------------------------------------------
 
 // grid = (CTAs, B*Tp), 32x8 pixel tiles, one thread per HD pixel, rolled loop over the contexts.
+template <typename ST>
 __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_FWD) k_layers_fwd(WbDec d) {
   const waldo_geom_t g = d.g;
   WbFwdCtx c;
@@ -263,20 +264,20 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_FWD) k_layers_fwd(Wb
       const unsigned wm = wb_warp_or(px.isobj);
       const int n = __popc(wm);
 #if !defined(WB_HOST_EMU) && !defined(WB_NO_LANES) && !defined(WB_NO_LANES_FWD)
-      if (n == 1) wb_lanes_layers_fwd<1>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
-      else if (n == 2) wb_lanes_layers_fwd<2>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
-      else if (n <= 4) wb_lanes_layers_fwd<4>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
-      else if (n <= 8) wb_lanes_layers_fwd<8>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
-      else wb_fwd_layers_ctxs<WB_MAX_L>(d, c, px, wm, q);
+      if (n == 1) wb_lanes_layers_fwd<1, ST>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
+      else if (n == 2) wb_lanes_layers_fwd<2, ST>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
+      else if (n <= 4) wb_lanes_layers_fwd<4, ST>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
+      else if (n <= 8) wb_lanes_layers_fwd<8, ST>(d, c, wm, n, px.isobj, tx0, Y, px.ay, px.gy);
+      else wb_fwd_layers_ctxs<WB_MAX_L, ST>(d, c, px, wm, q);
 #else
-      if (WB_NA_VARIANTS_FWD >= 2 && n <= 4) wb_fwd_layers_ctxs<4>(d, c, px, wm, q);
-      else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_fwd_layers_ctxs<8>(d, c, px, wm, q);
-      else wb_fwd_layers_ctxs<WB_MAX_L>(d, c, px, wm, q);
+      if (WB_NA_VARIANTS_FWD >= 2 && n <= 4) wb_fwd_layers_ctxs<4, ST>(d, c, px, wm, q);
+      else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_fwd_layers_ctxs<8, ST>(d, c, px, wm, q);
+      else wb_fwd_layers_ctxs<WB_MAX_L, ST>(d, c, px, wm, q);
 #endif
       if (c.self) {   // lvd.py:842-845: the target frame itself is fully opaque
-        float* raw = d.raw_output + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q;
-        for (int k = 0; k < c.L; ++k) raw[(size_t)(c.C + k) * HWd] = 1.f;
-        if (c.disocc_ch) raw[(size_t)(c.C + c.L) * HWd] = 1.f;
+        ST* raw = reinterpret_cast<ST*>(d.raw_output) + (((size_t)b * c.TcR + g.Tc) * g.Tp + tp) * c.CR * HWd + q;
+        for (int k = 0; k < c.L; ++k) wb_sts(raw + (size_t)(c.C + k) * HWd, 1.f);
+        if (c.disocc_ch) wb_sts(raw + (size_t)(c.C + c.L) * HWd, 1.f);
       }
     }
   }
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_LAYERS_FWD) k_layers_fwd(Wb
 // registers; ONE rolled loop walks the C image channels with the contexts unrolled inside: every channel of every
 // context frame is gathered, stored to raw_output and fused into `output` (lvd.py:850-851) on the fly.
 // FAST = exactly TCAP contexts and no include_self context, resolved at compile time (no predicates in the channel loop).
-template <int TCAP, bool FAST>
+template <int TCAP, bool FAST, typename ST>
 __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_FWD) k_gather_fwd(WbDec d) {
   const waldo_geom_t g = d.g;
   const int C = g.C, L = g.No + 1;
@@ -294,12 +295,12 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_FWD) k_gather_fwd(Wb
   const int btp = blockIdx.y, b = btp / g.Tp, tp = btp - b * g.Tp;
   const bool self = !FAST && (g.flags & WALDO_F_INCLUDE_SELF) && g.Tp == g.T;
   const int TcR = g.Tc + (self ? 1 : 0), CR = C + L + ((g.flags & WALDO_F_USE_DISOCC) ? 1 : 0);
-  __shared__ const float* s_src[TCAP];   // context frame of every context (CTA-uniform)
-  __shared__ float* s_raw[TCAP];         // raw_output block of every context
+  __shared__ const ST* s_src[TCAP];   // context frame of every context (CTA-uniform)
+  __shared__ ST* s_raw[TCAP];         // raw_output block of every context
   for (int tc = wb_tid(); tc < g.Tc; tc += wb_nthr()) {
     const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
-    s_src[tc] = d.input + ((size_t)b * g.T + c_t) * C * HWd;
-    s_raw[tc] = d.raw_output + (((size_t)b * TcR + tc) * g.Tp + tp) * CR * HWd;
+    s_src[tc] = reinterpret_cast<const ST*>(d.input) + ((size_t)b * g.T + c_t) * C * HWd;
+    s_raw[tc] = reinterpret_cast<ST*>(d.raw_output) + (((size_t)b * TcR + tc) * g.Tp + tp) * CR * HWd;
   }
   __syncthreads();
   const WbTileIter ti(g.Hd, g.Wd);
@@ -328,17 +329,17 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_FWD) k_gather_fwd(Wb
           accs += wgt[tc] * (score * 2.f - 1.f);
         }
       }
-      const float* self_src = nullptr;
-      float* self_raw = nullptr;
+      const ST* self_src = nullptr;
+      ST* self_raw = nullptr;
       float wself = 0.f;
       if (self) {   // lvd.py:842-845: the target frame itself, score 1
-        self_raw = d.raw_output + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q;
-        self_src = d.input + ((size_t)b * g.T + tp) * C * HWd + q;
+        self_raw = reinterpret_cast<ST*>(d.raw_output) + (((size_t)b * TcR + g.Tc) * g.Tp + tp) * CR * HWd + q;
+        self_src = reinterpret_cast<const ST*>(d.input) + ((size_t)b * g.T + tp) * C * HWd + q;
         wself = 1.f + 1e-6f;
         den += wself; accs += wself;
       }
       const float inv = 1.f / fmaxf(den, 1e-12f);
-      float* of = d.out_full + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
+      ST* of = reinterpret_cast<ST*>(d.out_full) + ((size_t)b * g.Tp + tp) * (C + 1) * HWd + q;
       unsigned choff = 0u;   // ch * HWd
 #ifndef WB_HOST_EMU
 #pragma unroll 2
@@ -348,25 +349,25 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_GATHER_FWD) k_gather_fwd(Wb
         float v[TCAP][4];
         WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
           if (FAST || tc < g.Tc) {
-            const float* pl = s_src[tc] + choff;
-            const float* p0 = pl + o0[tc];
-            const float* p1 = pl + o1[tc];
-            v[tc][0] = __ldg(p0); v[tc][1] = __ldg(p0 + 1); v[tc][2] = __ldg(p1); v[tc][3] = __ldg(p1 + 1);
+            const ST* pl = s_src[tc] + choff;
+            const ST* p0 = pl + o0[tc];
+            const ST* p1 = pl + o1[tc];
+            v[tc][0] = wb_lds(p0); v[tc][1] = wb_lds(p0 + 1); v[tc][2] = wb_lds(p1); v[tc][3] = wb_lds(p1 + 1);
           }
         }
         float acc = 0.f;
         WB_UNROLL for (int tc = 0; tc < TCAP; ++tc) {
           if (FAST || tc < g.Tc) {
             const float r = __fmaf_rn(v[tc][3], w[tc][3], __fmaf_rn(v[tc][2], w[tc][2], __fmaf_rn(v[tc][1], w[tc][1], __fmul_rn(v[tc][0], w[tc][0]))));
-            s_raw[tc][choff + q] = r;
+            wb_sts(s_raw[tc] + (choff + q), r);
             acc += wgt[tc] * r;
           }
         }
-        if (self) { const float v = __ldg(self_src + choff); self_raw[choff] = v; acc += wself * v; }
-        of[choff] = acc * inv;
+        if (self) { const float v = wb_lds(self_src + choff); wb_sts(self_raw + choff, v); acc += wself * v; }
+        wb_sts(of + choff, acc * inv);
         choff += HWd;
       }
-      of[choff] = accs * inv;
+      wb_sts(of + choff, accs * inv);
       d.norm[((size_t)b * g.Tp + tp) * HWd + q] = den;
     }
   }

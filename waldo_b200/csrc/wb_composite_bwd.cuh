@@ -195,7 +195,7 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
   const unsigned HWd = c.HWd;
   const float* alpha_c = d.alpha + ((size_t)c.b * g.Tw + c_t) * L * HWd;
   WbLay<NA> ly;
-  wb_layers_fwd<NA>(d, px, ix, d.f_lo + pair * L * HW * 2, alpha_c, c.s_occ, ly);
+  wb_layers_fwd<NA, float>(d, px, ix, d.f_lo + pair * L * HW * 2, alpha_c, c.s_occ, ly);
   float gA[NA], gR[NA], gFx[NA], gFy[NA];
   WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     gR[s] = 0.f; gA[s] = 0.f; gFx[s] = 0.f; gFy[s] = 0.f;
@@ -1644,6 +1644,7 @@ static int wb_decode_bwd_launch(const WbDecB& a, waldo_stream_t st) {
   WB_BREQ(g.B > 0 && g.No >= 1 && g.No + 1 <= WB_MAX_L && g.Nl <= WB_MAX_NL && g.C <= WB_MAX_C, "bad geometry");
   WB_BREQ(d.input && d.alpha && d.f_lo && d.a_lo && d.out_full && d.norm && d.occ && d.ctx_ts && d.pred_ts, "forward state missing");
   WB_BREQ(a.red_ctas > 0, "red_ctas must be positive");
+  WB_BREQ(d.storage == WALDO_ST_F32, "the backward needs fp32 storage (bf16 storage is forward / inference only)");
   const int L = g.No + 1, HW = g.H * g.W;
   const bool filt = (g.flags & WALDO_F_FILTER) != 0;
   const bool from_cls = (g.flags & WALDO_F_HAS_CLS) && !(g.flags & WALDO_F_WEIGHT_CLS);

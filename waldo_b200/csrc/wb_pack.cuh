@@ -11,6 +11,17 @@
 
 WB_DEV float wb_norm_u8(unsigned v) { return __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), 0.5f), 0.5f); }
 
+// four consecutive elements in one store: STG.E.128 (fp32) / STG.E.64 (bf16)
+WB_DEV void wb_st4(float* o, float a, float b, float c, float d) { *reinterpret_cast<float4*>(o) = make_float4(a, b, c, d); }
+WB_DEV void wb_st4(wb_bf16* o, float a, float b, float c, float d) {
+  wb_bf16 t[4];
+  wb_sts(t + 0, a); wb_sts(t + 1, b); wb_sts(t + 2, c); wb_sts(t + 3, d);
+  uint2 w;
+  w.x = (unsigned)t[0].x | ((unsigned)t[1].x << 16); w.y = (unsigned)t[2].x | ((unsigned)t[3].x << 16);
+  *reinterpret_cast<uint2*>(o) = w;
+}
+
+template <typename ST>
 __global__ void __launch_bounds__(256) k_pack_input(waldo_pack_input_t p) {
   const int C = 3 + p.Nl;
   const size_t HW = (size_t)p.HW;
@@ -20,7 +31,7 @@ __global__ void __launch_bounds__(256) k_pack_input(waldo_pack_input_t p) {
   for (size_t gq = (size_t)blockIdx.x * wb_nthr() + wb_tid(); gq < nq; gq += (size_t)gridDim.x * wb_nthr()) {
     const size_t q = gq * 4;
     const int npx = (int)(HW - q < 4 ? HW - q : 4);
-    float* out = p.input + (size_t)f * C * HW + q;
+    ST* out = reinterpret_cast<ST*>(p.input) + (size_t)f * C * HW + q;
     unsigned lab[4] = {255u, 255u, 255u, 255u};
     if (vec) {
       const unsigned w = *reinterpret_cast<const unsigned*>(p.label + (size_t)f * HW + q);
@@ -42,16 +53,16 @@ __global__ void __launch_bounds__(256) k_pack_input(waldo_pack_input_t p) {
         const float* s = p.rgb_f32 + ((size_t)f * 3 + c) * HW + q;
         for (int i = 0; i < npx; ++i) v[i] = s[i];
       }
-      float* o = out + (size_t)c * HW;
-      if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      else for (int i = 0; i < npx; ++i) o[i] = v[i];
+      ST* o = out + (size_t)c * HW;
+      if (vec) wb_st4(o, v[0], v[1], v[2], v[3]);
+      else for (int i = 0; i < npx; ++i) wb_sts(o + i, v[i]);
     }
     for (int c = 0; c < p.Nl; ++c) {
-      float* o = out + (size_t)(3 + c) * HW;
+      ST* o = out + (size_t)(3 + c) * HW;
       const float v0 = lab[0] == (unsigned)c ? p.on : p.off, v1 = lab[1] == (unsigned)c ? p.on : p.off;
       const float v2 = lab[2] == (unsigned)c ? p.on : p.off, v3 = lab[3] == (unsigned)c ? p.on : p.off;
-      if (vec) *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
-      else { const float vv[4] = {v0, v1, v2, v3}; for (int i = 0; i < npx; ++i) o[i] = vv[i]; }
+      if (vec) wb_st4(o, v0, v1, v2, v3);
+      else { const float vv[4] = {v0, v1, v2, v3}; for (int i = 0; i < npx; ++i) wb_sts(o + i, vv[i]); }
     }
   }
 }

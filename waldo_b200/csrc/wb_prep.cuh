@@ -76,7 +76,7 @@ WB_DEV void wb_softmax(const float* x, float* y, int n) {
 // The class count is a template parameter (20 / 19 / generic) and the object loop is unrolled over the compiled maximum:
 // the per-class vectors stay in registers (run-time trip counts put them in local memory) and the rows of `cls` are read
 // from shared memory at compile-time offsets.  Same operations in the same order as the generic loops.
-template <int NLC>
+template <int NLC, typename ST>
 __global__ void __launch_bounds__(256) k_class_profile(WbDec d) {
   constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
   constexpr int NO = WB_MAX_L - 1;
@@ -108,13 +108,13 @@ __global__ void __launch_bounds__(256) k_class_profile(WbDec d) {
       {   // same arithmetic as wb_lyt_lo
         const int y = p / g.W, x = p - y * g.W;
         const WbAxis ay = wb_axis(y, r, g.Hd), ax = wb_axis(x, r, g.Wd);
-        const float* base = d.input + (((size_t)b * g.T + t) * g.C + 3) * HWd;
+        const ST* base = reinterpret_cast<const ST*>(d.input) + (((size_t)b * g.T + t) * g.C + 3) * HWd;
         const size_t h00 = (size_t)ay.i0 * g.Wd + ax.i0, h01 = (size_t)ay.i0 * g.Wd + ax.i1;
         const size_t h10 = (size_t)ay.i1 * g.Wd + ax.i0, h11 = (size_t)ay.i1 * g.Wd + ax.i1;
         WB_UNROLL for (int c = 0; c < NN; ++c)
           if (NLC > 0 || c < Nl) {
-            const float* pl = base + c * HWd;
-            lyt[c] = wb_lerp2(__ldg(pl + h00), __ldg(pl + h01), __ldg(pl + h10), __ldg(pl + h11), ax, ay);
+            const ST* pl = base + c * HWd;
+            lyt[c] = wb_lerp2(wb_lds(pl + h00), wb_lds(pl + h01), wb_lds(pl + h10), wb_lds(pl + h11), ax, ay);
           }
       }
       if (wcls) {   // same arithmetic as wb_softmax
@@ -217,21 +217,22 @@ template <int NA> WB_DEV WbIdx<NA> wb_idx(unsigned wm) {
   return r;
 }
 
-struct WbPrepCtx {
+template <typename ST> struct WbPrepCtx {
   int b, t, L, Nl, HW;
   size_t HWd;
   bool filt;
-  const float *s_P, *s_occ, *lyt_base, *alo;
-  float* out;
+  const float *s_P, *s_occ, *alo;
+  const ST* lyt_base;
+  ST* out;
 };
 
 // softmax of the HD layout logits of pixel q (lvd.py:744).  NLC = compile-time class count (0: run-time Nl).
-template <int NLC>
-WB_DEV void wb_softmax_hd(const float* __restrict__ lyt_base, unsigned HWd, unsigned q, int Nl, float* sm) {
+template <int NLC, typename ST = float>
+WB_DEV void wb_softmax_hd(const ST* __restrict__ lyt_base, unsigned HWd, unsigned q, int Nl, float* sm) {
   constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
   float lyt[NN];
-  const float* p = lyt_base + q;
-  WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { lyt[c] = __ldg(p); p += HWd; }
+  const ST* p = lyt_base + q;
+  WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) { lyt[c] = wb_lds(p); p += HWd; }
   float mx = lyt[0];
   WB_UNROLL for (int c = 1; c < NN; ++c) if (NLC > 0 || c < Nl) mx = fmaxf(mx, lyt[c]);
   float s = 0.f;
@@ -240,8 +241,8 @@ WB_DEV void wb_softmax_hd(const float* __restrict__ lyt_base, unsigned HWd, unsi
   WB_UNROLL for (int c = 0; c < NN; ++c) if (NLC > 0 || c < Nl) sm[c] *= inv;
 }
 
-template <int NA, int NLC>
-WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, unsigned q, const WbAxis& ax, const WbAxis& ay,
+template <int NA, int NLC, typename ST>
+WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx<ST>& c, unsigned wm, unsigned q, const WbAxis& ax, const WbAxis& ay,
                           int o00, int o01, int o10, int o11) {
   constexpr int NN = NLC > 0 ? NLC : WB_MAX_NL;
   const waldo_geom_t& g = d.g;
@@ -249,7 +250,7 @@ WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, unsig
   const unsigned HWd = (unsigned)c.HWd;
   const WbIdx<NA> ix = wb_idx<NA>(wm);
   float sm[NN];
-  if (c.filt && (wm >> 1)) wb_softmax_hd<NLC>(c.lyt_base, HWd, q, Nl, sm);
+  if (c.filt && (wm >> 1)) wb_softmax_hd<NLC, ST>(c.lyt_base, HWd, q, Nl, sm);
   float a[NA];
   WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     a[s] = 0.f;
@@ -267,23 +268,23 @@ WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx& c, unsigned wm, unsig
       a[s] = v;
     }
   }
-  float* o = c.out + q;
-  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) *o = -1.f; o += HWd; }
+  ST* o = c.out + q;
+  WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) wb_sts(o, -1.f); o += HWd; }
   o = c.out + q;
   WB_UNROLL_NA for (int i = 0; i < WB_NEND; ++i) {
     if (i < ix.n) {
       const float* oc = c.s_occ + ix.k[i];
       float vis = 1.f;
       WB_UNROLL_NA for (int j = 0; j < WB_NEND; ++j) if (j < ix.n) vis *= 1.f - a[j] * oc[ix.k[j] * L];
-      o[(size_t)ix.k[i] * HWd] = (vis * a[i]) * 2.f - 1.f;
+      wb_sts(o + (size_t)ix.k[i] * HWd, (vis * a[i]) * 2.f - 1.f);
     }
   }
 }
 
-template <int NLC>
+template <int NLC, typename ST>
 __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_FWD) k_alpha_prep(WbDec d) {
   const waldo_geom_t g = d.g;
-  WbPrepCtx c;
+  WbPrepCtx<ST> c;
   c.L = g.No + 1; c.Nl = g.Nl; c.HW = g.H * g.W; c.HWd = (size_t)g.Hd * g.Wd;
   const int bt = blockIdx.y;
   c.b = bt / g.Tw; c.t = bt - c.b * g.Tw;
@@ -295,10 +296,10 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_FWD) k_alpha_prep(WbDe
   __syncthreads();
   c.s_P = s_P; c.s_occ = s_occ;
   const float r = (float)g.H / (float)g.Hd;   // 1 / scale_hd
-  c.lyt_base = d.input + (((size_t)c.b * g.T + c.t) * g.C + 3) * c.HWd;
+  c.lyt_base = reinterpret_cast<const ST*>(d.input) + (((size_t)c.b * g.T + c.t) * g.C + 3) * c.HWd;
   c.alo = d.a_lo + ((size_t)c.b * g.Tw + c.t) * c.L * c.HW;
   const uint32_t* live = d.live_ctx + ((size_t)c.b * g.Tw + c.t) * c.HW;
-  c.out = d.alpha + ((size_t)c.b * g.Tw + c.t) * c.L * c.HWd;
+  c.out = reinterpret_cast<ST*>(d.alpha) + ((size_t)c.b * g.Tw + c.t) * c.L * c.HWd;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;
@@ -310,9 +311,9 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_FWD) k_alpha_prep(WbDe
       const int o00 = ay.i0 * g.W + ax.i0, o01 = ay.i0 * g.W + ax.i1, o10 = ay.i1 * g.W + ax.i0, o11 = ay.i1 * g.W + ax.i1;
       const unsigned wm = wb_warp_or(wb_live4(live, o00, o01, o10, o11));
       const int n = __popc(wm);
-      if (WB_NA_VARIANTS_FWD >= 2 && n <= 4) wb_prep_pixel<4, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
-      else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_prep_pixel<8, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
-      else wb_prep_pixel<WB_MAX_L, NLC>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
+      if (WB_NA_VARIANTS_FWD >= 2 && n <= 4) wb_prep_pixel<4, NLC, ST>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
+      else if (WB_NA_VARIANTS_FWD >= 3 && n <= 8) wb_prep_pixel<8, NLC, ST>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
+      else wb_prep_pixel<WB_MAX_L, NLC, ST>(d, c, wm, q, ax, ay, o00, o01, o10, o11);
     }
   }
 }

@@ -18,10 +18,12 @@ class DevicePrefetcher:
     `num_lyt` is given, the yielded dict gets "input" = pack_input(rgb, label).  Tensors of a yielded batch stay valid
     until the consumer asks for the batch after the next one (two device buffers per key)."""
 
-    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device, num_lyt: Optional[int] = None, depth: int = 2):
+    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device, num_lyt: Optional[int] = None, depth: int = 2,
+                 input_dtype=torch.float32):
         self.it: Iterator = iter(batches)
         self.device = torch.device(device)
         self.num_lyt = num_lyt
+        self.input_dtype = input_dtype                    # torch.bfloat16: input of the bf16-storage inference variant
         self.stream = torch.cuda.Stream(self.device)
         self.depth = depth
         self.slots = [dict() for _ in range(depth)]      # reusable device buffers
@@ -57,9 +59,9 @@ class DevicePrefetcher:
                     inp = dev.get("input")
                     B, T, _, Hd, Wd = out["rgb"].shape
                     if inp is None or inp.shape != (B, T, 3 + self.num_lyt, Hd, Wd):
-                        inp = torch.empty(B, T, 3 + self.num_lyt, Hd, Wd, device=self.device, dtype=torch.float32)
+                        inp = torch.empty(B, T, 3 + self.num_lyt, Hd, Wd, device=self.device, dtype=self.input_dtype)
                         dev["input"] = inp
-                    out["input"] = Fn.pack_input(out["rgb"], out["label"], self.num_lyt, out=inp)
+                    out["input"] = Fn.pack_input(out["rgb"], out["label"], self.num_lyt, out=inp, dtype=self.input_dtype)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
             self.ready[s] = ev

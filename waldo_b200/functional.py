@@ -310,11 +310,13 @@ def _staged(fn, arg, stream, what, dev):
 def _fwd_struct(g, prof_ctas, t):
     (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part, prof_sum, prof_p,
      f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score, lyt_lo) = t
-    return L.DecodeFwd(g, L.ptr(inp_c, name="input"), L.ptr(tgo_c), L.ptr(sgo_c), L.ptr(tgb_c), L.ptr(sgb_c), L.ptr(occ_c),
+    st = inp_c.dtype   # storage type of the HD activations: fp32, or bf16 (forward / inference only)
+    return L.DecodeFwd(g, L.ptr(inp_c, st, name="input"), L.ptr(tgo_c), L.ptr(sgo_c), L.ptr(tgb_c), L.ptr(sgb_c), L.ptr(occ_c),
                        L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
                        L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
                        L.ptr(prof_p), L.ptr(lyt_lo), L.ptr(f_lo), L.ptr(s_lo), L.ptr(live_ctx, torch.int32), L.ptr(live_pred, torch.int32),
-                       L.ptr(alpha), L.ptr(flow), L.ptr(raw), L.ptr(out_full), L.ptr(norm), L.ptr(score), 0)
+                       L.ptr(alpha, st), L.ptr(flow), L.ptr(raw, st), L.ptr(out_full, st), L.ptr(norm), L.ptr(score), 0,
+                       L.ST_BF16 if st == torch.bfloat16 else L.ST_F32)
 
 
 _ts_checked = {}
@@ -345,7 +347,13 @@ class _Decode(torch.autograd.Function):
     def forward(ctx, spec, ctx_ts, pred_ts, xs_hd, ys_hd, inp, tgo, sgo, tgb, sgb, occ, obj_alpha, bg_alpha, cls):
         lib = L.load()
         ctx.set_materialize_grads(False)   # unused outputs must not cost a zero-filled HD tensor each
-        inp_c, tgo_c, sgo_c, tgb_c, sgb_c = (_c(t.detach()) for t in (inp, tgo, sgo, tgb, sgb))
+        # bf16 `input` selects the bf16-storage variant: input / alpha / raw_output / output are bf16 in HBM, all arithmetic
+        # is fp32 (include/waldo_b200.h WALDO_ST_BF16; tolerance: tests/parity.py TOL_BF16).  Forward / inference only.
+        st = torch.bfloat16 if inp.dtype == torch.bfloat16 else torch.float32
+        if st == torch.bfloat16 and any(ctx.needs_input_grad):
+            raise RuntimeError("waldo_b200.decode: bf16 storage is forward / inference only (run under torch.no_grad(), or pass fp32 input)")
+        inp_c = _c(inp.detach(), st)
+        tgo_c, sgo_c, tgb_c, sgb_c = (_c(t.detach()) for t in (tgo, sgo, tgb, sgb))
         occ_c, oa_c, ba_c = _c(occ.detach()), _c(obj_alpha.detach()), _c(bg_alpha.detach())
         cls_c = _c(cls.detach()) if cls is not None else None
         B, T, Cc, Hd, Wd = inp_c.shape
@@ -391,10 +399,10 @@ class _Decode(torch.autograd.Function):
         s_lo = torch.empty(B, Tp, spec.num_obj, spec.H, spec.W, **f32)
         live_ctx = torch.empty(B, g.Tw, spec.H, spec.W, device=dev, dtype=torch.int32)
         live_pred = torch.empty(B, Tp, spec.H, spec.W, device=dev, dtype=torch.int32)
-        alpha = torch.empty(B, g.Tw, Lr, Hd, Wd, **f32)
+        alpha = torch.empty(B, g.Tw, Lr, Hd, Wd, device=dev, dtype=st)
         flow = torch.empty(B, Tc, Tp, 2, Hd, Wd, **f32)
-        raw = torch.empty(B, TcR, Tp, CR, Hd, Wd, **f32)
-        out_full = torch.empty(B, Tp, Cc + 1, Hd, Wd, **f32)
+        raw = torch.empty(B, TcR, Tp, CR, Hd, Wd, device=dev, dtype=st)
+        out_full = torch.empty(B, Tp, Cc + 1, Hd, Wd, device=dev, dtype=st)
         norm = torch.empty(B, Tp, Hd, Wd, **f32)
         score = torch.empty(B, Tc, Tp, Hd, Wd, **f32)
         # low-res layout logits: kept only when a backward will follow (it saves re-reading the HD layout planes)
@@ -532,9 +540,10 @@ def wif_fuse(raw_output, unet_out, ab=True):
 
 
 # ===================================================================================== f-3 input packing
-def pack_input(rgb, label, num_lyt, on=5.0, off=-5.0, out=None):
-    """Build `input` (B,T,3+Nl,Hd,Wd) fp32 on the device from rgb (B,T,3,Hd,Wd; uint8 raw pixels or fp32 already in
+def pack_input(rgb, label, num_lyt, on=5.0, off=-5.0, out=None, dtype=torch.float32):
+    """Build `input` (B,T,3+Nl,Hd,Wd) on the device from rgb (B,T,3,Hd,Wd; uint8 raw pixels or fp32 already in
     [-1,1]) and label (B,T,Hd,Wd) uint8 class ids -- data/base_dataset.py:173-183,:355-372 + synthesizer.py:444.
+    dtype: torch.float32 (the reference's), or torch.bfloat16 for the bf16-storage inference variant of decode.
     Data preparation: no gradient."""
     lib = L.load()
     if rgb.dim() != 5 or rgb.size(2) != 3 or label.shape != rgb.shape[:2] + rgb.shape[3:]:
@@ -543,14 +552,17 @@ def pack_input(rgb, label, num_lyt, on=5.0, off=-5.0, out=None):
         raise RuntimeError("waldo_b200.pack_input: label must be uint8 class ids")
     B, T, _, Hd, Wd = rgb.shape
     rgb_c, lab_c = rgb.detach().contiguous(), label.contiguous()
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("waldo_b200.pack_input: dtype must be torch.float32 or torch.bfloat16")
     if out is None:
-        out = torch.empty(B, T, 3 + num_lyt, Hd, Wd, device=rgb.device, dtype=torch.float32)
-    elif out.shape != (B, T, 3 + num_lyt, Hd, Wd):
-        raise RuntimeError("waldo_b200.pack_input: out has the wrong shape")
+        out = torch.empty(B, T, 3 + num_lyt, Hd, Wd, device=rgb.device, dtype=dtype)
+    elif out.shape != (B, T, 3 + num_lyt, Hd, Wd) or out.dtype != dtype:
+        raise RuntimeError("waldo_b200.pack_input: out has the wrong shape / dtype")
     u8 = rgb_c.dtype == torch.uint8
     a = L.PackInput(B * T, num_lyt, Hd * Wd, float(on), float(off),
                     L.ptr(rgb_c, torch.uint8, "rgb") if u8 else None, None if u8 else L.ptr(rgb_c, name="rgb"),
-                    L.ptr(lab_c, torch.uint8, "label"), L.ptr(out, name="out"))
+                    L.ptr(lab_c, torch.uint8, "label"), L.ptr(out, dtype, name="out"),
+                    L.ST_BF16 if dtype == torch.bfloat16 else L.ST_F32)
     L.call(lib.waldo_pack_input, a, out, "pack_input")
     return out
 

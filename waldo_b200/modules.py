@@ -324,10 +324,11 @@ def wif_fuse(vid, unet_out, ab=True):
 
 
 # ----------------------------------------------------------------------------- f-3 (caller side: the input pipeline)
-def pack_input(rgb, label, num_lyt, out=None):
+def pack_input(rgb, label, num_lyt, out=None, dtype=torch.float32):
     """`input` = cat([vid, lyt], dim=2) (synthesizer.py:444) built on the device from 8-bit RGB (or normalised fp32
-    frames) and the 8-bit label map, i.e. base_dataset.py:173-183 / :355-372 moved after the host->device copy."""
-    return Fn.pack_input(rgb, label, num_lyt, out=out)
+    frames) and the 8-bit label map, i.e. base_dataset.py:173-183 / :355-372 moved after the host->device copy.
+    dtype=torch.bfloat16 builds the input of the bf16-storage inference variant of decode_output."""
+    return Fn.pack_input(rgb, label, num_lyt, out=out, dtype=dtype)
 
 
 # ----------------------------------------------------------------------------- f-4 (caller side: the output pipeline)
