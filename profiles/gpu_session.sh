@@ -17,6 +17,13 @@ benchdet)
 launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_launches.log 2>&1; echo "launches rc=$?";;
+launchesw)
+  # launch list of another workload, eager (no graph) so that every kernel shows:  LW=kitti_rollout
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/${TAG}_launches_${LW}.csv \
+     python bench.py --workload $LW --no-graph --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-others > $OUT/${TAG}_launches_${LW}.log 2>&1; echo "launchesw rc=$?";;
+benchw)
+  # one line of another workload:  LW=nonrigid_train
+  timeout 600 python bench.py --workload $LW --no-cpu-baseline --no-others > $OUT/${TAG}_bench_$LW.jsonl 2> $OUT/${TAG}_bench_$LW.err; echo "bench $LW rc=$?"; cat $OUT/${TAG}_bench_$LW.jsonl; tail -2 $OUT/${TAG}_bench_$LW.err;;
 workloads)
   for w in city_rollout kitti_rollout; do
     timeout 600 python bench.py --workload $w --no-cpu-baseline > $OUT/${TAG}_bench_$w.jsonl 2> $OUT/${TAG}_bench_$w.err; echo "bench $w rc=$?"; cat $OUT/${TAG}_bench_$w.jsonl; tail -2 $OUT/${TAG}_bench_$w.err

@@ -26,6 +26,15 @@ def test_inverse_warp(case):
     parity.check_inverse_warp(DEV, case)
 
 
+@pytest.mark.parametrize("knob", [("WALDO_INV_CAP", "64"), ("WALDO_INV_CAP", "1500"), ("WALDO_INV_MARGIN", "-6"), ("WALDO_INV_UNFUSED", "1")])
+@pytest.mark.parametrize("case", ["city_x4", "city_real", "kitti_real"])
+def test_inverse_warp_paths(case, knob, monkeypatch):
+    """The fused one-CTA-per-item object kernel with its work area in global memory (box over the cell budget: all / some
+    items), after a sample landed outside the predicted box (margin shrunk artificially), and the phase-per-kernel path."""
+    monkeypatch.setenv(*knob)
+    parity.check_inverse_warp(DEV, case)
+
+
 @pytest.mark.parametrize("case", parity.CASES)
 def test_occ(case):
     parity.check_occ(DEV, case)

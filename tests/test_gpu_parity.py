@@ -27,6 +27,15 @@ def test_inverse_warp(dev, case):
     parity.check_inverse_warp(dev, case)
 
 
+@pytest.mark.parametrize("knob", [("WALDO_INV_CAP", "64"), ("WALDO_INV_CAP", "1500"), ("WALDO_INV_MARGIN", "-6"), ("WALDO_INV_UNFUSED", "1")])
+@pytest.mark.parametrize("case", ["city_x4", "city_real", "kitti_real"])
+def test_inverse_warp_paths(dev, case, knob, monkeypatch):
+    """k_inv_fused with its work area in global memory (box over the cell budget), after a sample landed outside the
+    predicted box (margin shrunk artificially), and the phase-per-kernel path: all bit-identical index maps."""
+    monkeypatch.setenv(*knob)
+    parity.check_inverse_warp(dev, case)
+
+
 @pytest.mark.parametrize("case", parity.CASES)
 def test_occ(dev, case):
     parity.check_occ(dev, case)

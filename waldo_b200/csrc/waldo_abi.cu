@@ -2,6 +2,7 @@
 // no allocation, no synchronisation, launches on the caller's stream.
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include "wb_common.cuh"
 #include "wb_geom.cuh"
 #include "wb_prep.cuh"
@@ -37,6 +38,12 @@ static int wb_check_launch(const char* file, int line) {
 
 #define WB_REQUIRE(cond, ...) do { if (!(cond)) return wb_fail(WALDO_EINVAL, __VA_ARGS__); } while (0)
 #define WB_LAUNCHED() do { int rc_ = WB_CHECK_LAUNCH(); if (rc_) return rc_; } while (0)
+
+// WALDO_INV_UNFUSED=1: objects take the phase-per-kernel inverse warp (A/B runs, and the tests of that path)
+static bool wb_inv_unfused() {
+  const char* e = getenv("WALDO_INV_UNFUSED");
+  return e && e[0] == '1';
+}
 
 static inline unsigned wb_blocks(long long total, int threads, long long cap = 1 << 20) {
   long long b = (total + threads - 1) / threads;
@@ -156,12 +163,29 @@ int waldo_invwarp_fwd(const waldo_invwarp_fwd_t* a, waldo_stream_t st) {
   const int m = a->niter + 1, PP = (a->Ht + 2 * m) * (a->Wt + 2 * m), P = a->Ht * a->Wt;
   const dim3 gpp(wb_blocks(PP, 256, 512), a->n), gp(wb_blocks(P, 256, 512), a->n);
   const dim3 gband((a->Ht + 2 * m + WB_INV_ROWS - 1) / WB_INV_ROWS, a->n);
+  // a forward map defined on a lattice much smaller than the target (an object canvas) lands in a small box of the target
+  const bool small_box = (long long)a->Hs * a->Ws * 4 <= (long long)a->Ht * a->Wt;
+  if (small_box && a->Hs * a->Ws <= WB_INVF_MAX_SRC && !wb_inv_unfused()) {
+    // ... and all its phases run in one CTA with the working set in shared memory (k_inv_fused)
+    const int NS = a->Hs * a->Ws;
+    const size_t budget = 224 * 1024;
+    int cap = (int)((budget - (size_t)NS * 8) / 14) & ~3;
+    // test knobs: a smaller cell budget (boxes that do not fit take the global-memory work area) and a margin adjustment
+    // (a negative one makes samples land outside the predicted box, which must send the item down the fallback)
+    if (const char* e = getenv("WALDO_INV_CAP")) cap = max(4, min(cap, atoi(e))) & ~3;
+    const char* em = getenv("WALDO_INV_MARGIN");
+    const int mg_adj = em ? atoi(em) : 0;
+    const size_t smem = (size_t)NS * 8 + (size_t)cap * 14;
+#ifndef WB_HOST_EMU
+    cudaFuncSetAttribute(k_inv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);   // > 48 KB: opt in
+#endif
+    WB_LAUNCH(k_inv_fused, dim3(a->n), dim3(WB_INVF_THREADS), smem, st, k, cap, mg_adj); WB_LAUNCHED();
+    return 0;
+  }
   WB_LAUNCH(k_inv_clear, gpp, dim3(256), 0, st, k); WB_LAUNCHED();
   WB_LAUNCH(k_inv_claim, gp, dim3(256), 0, st, k); WB_LAUNCHED();
   WB_LAUNCH(k_inv_deposit, gp, dim3(256), 0, st, k); WB_LAUNCHED();
-  // a forward map defined on a lattice much smaller than the target (an object canvas) lands in a small box of the target:
-  // one CTA per item runs all growth iterations there; otherwise (background) one flat launch per iteration
-  const bool small_box = (long long)a->Hs * a->Ws * 4 <= (long long)a->Ht * a->Wt;
+  // one CTA per item runs all growth iterations of a small box; otherwise (background) one flat launch per iteration
   if (small_box) { WB_LAUNCH(k_inv_grow_fused, dim3(a->n), dim3(512), 0, st, k); WB_LAUNCHED(); }
   else {
     for (int it = 1; it <= a->niter; ++it) { WB_LAUNCH(k_inv_dilate, gband, dim3(256), 0, st, k, it); WB_LAUNCHED(); }

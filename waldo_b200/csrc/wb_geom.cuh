@@ -296,6 +296,220 @@ __global__ void __launch_bounds__(512) k_inv_grow_fused(WbInvArgs a) {
     }
   }
 }
+// ------------------------------------------------------------------------------------------------------------------
+// Objects, all phases in ONE kernel: one CTA per item, working set in shared memory.
+// An object canvas (Hs x Ws lattice, 64 x 64 at the benchmark shape) lands in a small box of the Ht x Wt image.  The
+// CTA stages the lattice displacements (fwd - identity) in shared memory, bounds the landing box from them, and runs
+// clear -> claim -> deposit -> dilations -> erosions -> final over that box (grown by niter + 1) entirely in shared
+// memory: `val` never reaches HBM, the displacement of a sample is interpolated from shared memory, and five launches
+// (each a pass over n x Ht x Wt cells in global memory) become one.  The maps the backward and the parity checks read
+// (field, winner, level, eroded, bbox) are written once at the end.  A box that does not fit the shared-memory budget,
+// or a sample that lands outside the predicted box (the claim phase checks every sample, so the bound is never trusted),
+// sends the item down the same code with the work area in global memory.  Same arithmetic, same tie rule, same results.
+#define WB_INVF_THREADS 1024
+#define WB_INVF_MAX_SRC 4096   // lattice points staged per item
+struct WbInvArea {             // work area in padded coordinates: cell (x, y) -> (y - y0) * w + (x - x0)
+  int x0, y0, w, h;
+  int wx0, wy0, ww;            // the same for `winner` (unpadded image layout when the area lives in global memory)
+  int* winner; float* vx; float* vy; uint8_t* level; uint8_t* eroded;
+};
+WB_DEV int wb_warp_min(int v) {
+#ifndef WB_HOST_EMU
+  v = __reduce_min_sync(0xffffffffu, v);
+#endif
+  return v;
+}
+WB_DEV int wb_warp_max(int v) {
+#ifndef WB_HOST_EMU
+  v = __reduce_max_sync(0xffffffffu, v);
+#endif
+  return v;
+}
+// displacement of sample (X, Y) in pixels from the staged lattice displacements: the arithmetic of wb_inv_disp
+WB_DEV void wb_inv_disp_s(const WbInvArgs& a, const float2* s_d, int X, int Y, float& dx, float& dy) {
+  const float rh = (float)a.Hs / (float)a.Ht, rw = (float)a.Ws / (float)a.Wt;
+  const WbAxis ay = wb_axis(Y, rh, a.Hs), ax = wb_axis(X, rw, a.Ws);
+  const float2 v00 = s_d[ay.i0 * a.Ws + ax.i0], v01 = s_d[ay.i0 * a.Ws + ax.i1];
+  const float2 v10 = s_d[ay.i1 * a.Ws + ax.i0], v11 = s_d[ay.i1 * a.Ws + ax.i1];
+  const float d0 = wb_lerp2(v00.x, v01.x, v10.x, v11.x, ax, ay), d1 = wb_lerp2(v00.y, v01.y, v10.y, v11.y, ax, ay);
+  dx = __fdiv_rn(__fmul_rn(d0, (float)a.Wt), 2.f); dy = __fdiv_rn(__fmul_rn(d1, (float)a.Ht), 2.f);
+}
+// wb_inv_dilate_cell / wb_inv_erode_cell on a work area (bounds are those of the padded frame, Hp x Wp)
+WB_DEV void wb_inv_dilate_area(const WbInvArea& A, const float* g, int x, int y, int iter, int Hp, int Wp) {
+  const uint8_t* level = A.level;
+  const int c = (y - A.y0) * A.w + (x - A.x0), S = A.w;
+  if (level[c] != 255) return;
+  bool front = (y > 0 && wb_level_known_before(level[c - S], iter)) || (y < Hp - 1 && wb_level_known_before(level[c + S], iter)) ||
+               (x > 0 && wb_level_known_before(level[c - 1], iter)) || (x < Wp - 1 && wb_level_known_before(level[c + 1], iter));
+  if (!front) return;
+  float sx = 0.f, sy = 0.f, sw = 0.f;
+  WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
+    WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
+      int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
+      int q = c + dy * S + dx;
+      if (!wb_level_known_before(level[q], iter)) continue;
+      float w = g[(dy + 1) * 3 + dx + 1];
+      sx += w * A.vx[q]; sy += w * A.vy[q]; sw += w;
+    }
+  A.vx[c] = sx / sw; A.vy[c] = sy / sw; A.level[c] = (uint8_t)iter;
+}
+WB_DEV void wb_inv_erode_area(const WbInvArea& A, int x, int y, int iter, int Hp, int Wp) {
+  const uint8_t* level = A.level;
+  const uint8_t* eroded = A.eroded;
+  const int c = (y - A.y0) * A.w + (x - A.x0), S = A.w;
+  if (level[c] == 255 || eroded[c] != 0) return;
+#define WB_GONE(q) (level[q] == 255 || (eroded[q] != 0 && (int)eroded[q] < iter))
+  bool edge = (y > 0 && WB_GONE(c - S)) || (y < Hp - 1 && WB_GONE(c + S)) ||
+              (x > 0 && WB_GONE(c - 1)) || (x < Wp - 1 && WB_GONE(c + 1));
+#undef WB_GONE
+  if (edge) A.eroded[c] = (uint8_t)iter;
+}
+// cells of the hit box grown by `grow`, clipped to the work area
+WB_DEV void wb_inv_box_area(const int* bb, int grow, const WbInvArea& A, int& x0, int& y0, int& w, int& cells) {
+  x0 = y0 = w = cells = 0;
+  if (bb[2] < 0) return;
+  x0 = max(A.x0, bb[0] - grow); y0 = max(A.y0, bb[1] - grow);
+  const int x1 = min(A.x0 + A.w - 1, bb[2] + grow), y1 = min(A.y0 + A.h - 1, bb[3] + grow);
+  if (x1 < x0 || y1 < y0) return;
+  w = x1 - x0 + 1; cells = w * (y1 - y0 + 1);
+}
+__global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, int cap, int mg_adj) {
+  WB_INV_GEOM;
+  const WbInvItem it = wb_inv_item(a, blockIdx.x, P, PP);
+  const int NS = a.Hs * a.Ws, tid = wb_tid(), nthr = wb_nthr();
+  WB_DYN_SMEM(smem);
+  float2* s_d = reinterpret_cast<float2*>(smem);          // lattice displacements fwd - identity   warp.py:76
+  int* s_win = reinterpret_cast<int*>(smem + 2 * NS);
+  float* s_vx = smem + 2 * NS + cap;
+  float* s_vy = s_vx + cap;
+  uint8_t* s_lv = reinterpret_cast<uint8_t*>(s_vy + cap);
+  uint8_t* s_er = s_lv + cap;
+  __shared__ int s_bb[4], s_hit[4], s_over;
+  float g[9];
+  WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
+  if (tid < 4) { s_bb[tid] = tid < 2 ? INT_MAX : INT_MIN; s_hit[tid] = tid < 2 ? INT_MAX : -1; }
+  if (tid == 0) s_over = 0;
+  __syncthreads();
+  {   // stage the lattice, bound where its points land (pixels)
+    int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
+    for (int i = tid; i < NS; i += nthr) {
+      const float fx = __ldg(it.fwd + 2 * i), fy = __ldg(it.fwd + 2 * i + 1);
+      s_d[i] = make_float2(__fsub_rn(fx, __ldg(a.id_src + 2 * i)), __fsub_rn(fy, __ldg(a.id_src + 2 * i + 1)));
+      const float px = fminf(fmaxf(((fx + 1.f) * (float)Wt - 1.f) * 0.5f, -8.f), (float)Wt + 8.f);
+      const float py = fminf(fmaxf(((fy + 1.f) * (float)Ht - 1.f) * 0.5f, -8.f), (float)Ht + 8.f);
+      bx0 = min(bx0, (int)floorf(px)); bx1 = max(bx1, (int)ceilf(px));
+      by0 = min(by0, (int)floorf(py)); by1 = max(by1, (int)ceilf(py));
+    }
+    bx0 = wb_warp_min(bx0); by0 = wb_warp_min(by0); bx1 = wb_warp_max(bx1); by1 = wb_warp_max(by1);
+    if (wb_lane() == 0) { atomicMin(&s_bb[0], bx0); atomicMin(&s_bb[1], by0); atomicMax(&s_bb[2], bx1); atomicMax(&s_bb[3], by1); }
+  }
+  __syncthreads();
+  // samples between lattice points land between the lattice points' own landing positions; beyond the outermost lattice
+  // points the displacement is extended as a constant over half a lattice step (+ rounding): the margin
+  const int mgx = (Wt + a.Ws - 1) / a.Ws / 2 + 2 + mg_adj, mgy = (Ht + a.Hs - 1) / a.Hs / 2 + 2 + mg_adj;   // (mg_adj: tests only)
+  const int ix0 = max(0, s_bb[0] - mgx), ix1 = min(Wt - 1, s_bb[2] + mgx), iy0 = max(0, s_bb[1] - mgy), iy1 = min(Ht - 1, s_bb[3] + mgy);
+  const bool some = ix0 <= ix1 && iy0 <= iy1;
+  const int aw = some ? ix1 - ix0 + 1 + 2 * m : 0, ah = some ? iy1 - iy0 + 1 + 2 * m : 0;   // padded coordinates: + m on both sides
+  bool fits = (long long)aw * ah <= (long long)cap;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    WbInvArea A;
+    if (fits) {
+      A.x0 = ix0; A.y0 = iy0; A.w = aw; A.h = ah; A.wx0 = ix0; A.wy0 = iy0; A.ww = aw;
+      A.winner = s_win; A.vx = s_vx; A.vy = s_vy; A.level = s_lv; A.eroded = s_er;
+      for (int i = tid; i < aw * ah; i += nthr) { s_lv[i] = 255; s_er[i] = 0; s_win[i] = INT_MAX; }
+    } else {
+      A.x0 = 0; A.y0 = 0; A.w = Wp; A.h = Hp; A.wx0 = m; A.wy0 = m; A.ww = Wt;
+      A.winner = it.winner; A.vx = it.vx; A.vy = it.vy; A.level = it.level; A.eroded = it.eroded;
+      for (int i = tid; i < PP; i += nthr) { it.level[i] = 255; it.eroded[i] = 0; it.vx[i] = 0.f; it.vy[i] = 0.f; if (i < P) it.winner[i] = INT_MAX; }
+    }
+    __syncthreads();
+    // claim: landing cell of every sample; the lowest sample index takes the cell            warp.py:76-88,113-117
+    for (int s = tid; s < P; s += nthr) {
+      const int Y = s / Wt, X = s - Y * Wt;
+      float dx, dy;
+      wb_inv_disp_s(a, s_d, X, Y, dx, dy);
+      const float fx = rintf(__fadd_rn((float)X, dx)), fy = rintf(__fadd_rn((float)Y, dy));   // half-to-even
+      int cell = -1;
+      if (fx >= 0.f && fy >= 0.f && fx <= (float)(Wt - 1) && fy <= (float)(Ht - 1)) {
+        const int cx = (int)fx, cy = (int)fy, px = cx + m, py = cy + m;
+        cell = cy * Wt + cx;
+        if (px < A.x0 || px >= A.x0 + A.w || py < A.y0 || py >= A.y0 + A.h) s_over = 1;   // outside the predicted box
+        else atomicMin(&A.winner[(py - A.wy0) * A.ww + (px - A.wx0)], s);
+      }
+      it.field[s] = cell;
+    }
+    __syncthreads();
+    if (!(fits && s_over)) {
+      // deposit: winners write the negated displacement                                       warp.py:121-123
+      int hx0 = INT_MAX, hy0 = INT_MAX, hx1 = -1, hy1 = -1;
+      for (int s = tid; s < P; s += nthr) {
+        const int cell = it.field[s];
+        if (cell < 0) continue;
+        const int cy = cell / Wt, cx = cell - cy * Wt, px = cx + m, py = cy + m;
+        if (A.winner[(py - A.wy0) * A.ww + (px - A.wx0)] != s) continue;
+        const int Y = s / Wt, X = s - Y * Wt;
+        float dx, dy;
+        wb_inv_disp_s(a, s_d, X, Y, dx, dy);
+        const int c = (py - A.y0) * A.w + (px - A.x0);
+        A.vx[c] = -dx; A.vy[c] = -dy; A.level[c] = 0;
+        hx0 = min(hx0, px); hy0 = min(hy0, py); hx1 = max(hx1, px); hy1 = max(hy1, py);
+      }
+      hx0 = wb_warp_min(hx0); hy0 = wb_warp_min(hy0); hx1 = wb_warp_max(hx1); hy1 = wb_warp_max(hy1);
+      if (wb_lane() == 0 && hx1 >= 0) { atomicMin(&s_hit[0], hx0); atomicMin(&s_hit[1], hy0); atomicMax(&s_hit[2], hx1); atomicMax(&s_hit[3], hy1); }
+      __syncthreads();
+      if (tid < 4) it.bbox[tid] = s_hit[tid];
+      // dilations, erosions over the hit box grown by the iteration count                     warp.py:135-162
+      int x0, y0, w, cells;
+      for (int iter = 1; iter <= a.niter; ++iter) {
+        wb_inv_box_area(s_hit, iter, A, x0, y0, w, cells);
+        for (int i = tid; i < cells; i += nthr) wb_inv_dilate_area(A, g, x0 + i % w, y0 + i / w, iter, Hp, Wp);
+        __syncthreads();
+      }
+      if (a.erode) {
+        wb_inv_box_area(s_hit, a.niter, A, x0, y0, w, cells);
+        for (int iter = 1; iter <= a.niter; ++iter) {
+          for (int i = tid; i < cells; i += nthr) wb_inv_erode_area(A, x0 + i % w, y0 + i / w, iter, Hp, Wp);
+          __syncthreads();
+        }
+      }
+      // final: sentinel for unknown cells, crop, back to normalised coordinates                warp.py:164-174
+      float* out = a.out + (size_t)blockIdx.x * P * 2;
+      for (int s = tid; s < P; s += nthr) {
+        const int Y = s / Wt, X = s - Y * Wt, px = X + m, py = Y + m;
+        bool known = false;
+        int c = 0;
+        if (px >= A.x0 && px < A.x0 + A.w && py >= A.y0 && py < A.y0 + A.h) {
+          c = (py - A.y0) * A.w + (px - A.x0);
+          known = A.level[c] != 255 && A.eroded[c] == 0;
+        }
+        const float ix = known ? A.vx[c] : (float)(2 * Wt), iy = known ? A.vy[c] : (float)(2 * Ht);
+        out[2 * s] = __fadd_rn(__ldg(a.id_tgt + 2 * s), __fdiv_rn(__fmul_rn(ix, 2.f), (float)Wt));
+        out[2 * s + 1] = __fadd_rn(__ldg(a.id_tgt + 2 * s + 1), __fdiv_rn(__fmul_rn(iy, 2.f), (float)Ht));
+      }
+      if (fits) {   // the maps the backward (and the index-map parity checks) read
+        for (int i = tid; i < PP; i += nthr) {
+          const int y = i / Wp, x = i - y * Wp;
+          const bool in = x >= A.x0 && x < A.x0 + A.w && y >= A.y0 && y < A.y0 + A.h;
+          const int c = in ? (y - A.y0) * A.w + (x - A.x0) : 0;
+          it.level[i] = in ? s_lv[c] : (uint8_t)255;
+          it.eroded[i] = in ? s_er[c] : (uint8_t)0;
+          if (i < P) {
+            const int Y = i / Wt, X = i - Y * Wt, qx = X + m, qy = Y + m;
+            const bool inw = qx >= A.x0 && qx < A.x0 + A.w && qy >= A.y0 && qy < A.y0 + A.h;
+            it.winner[i] = inw ? s_win[(qy - A.y0) * A.w + (qx - A.x0)] : INT_MAX;
+          }
+        }
+      }
+      return;
+    }
+    // a sample landed outside the predicted box: redo the item with the work area in global memory
+    fits = false;
+    __syncthreads();
+    if (tid == 0) s_over = 0;
+    __syncthreads();
+  }
+}
 // phase 5: sentinel for unknown cells, crop, back to normalised coordinates              warp.py:164-174
 __global__ void __launch_bounds__(256) k_inv_final(WbInvArgs a) {
   WB_INV_GEOM;

@@ -254,10 +254,14 @@ PREFILL = True
 _side_streams = {}
 
 
-def _side_stream(dev):
-    s = _side_streams.get(dev)
+def _side_stream(dev, which=0):
+    """Side streams of a device: 0 = gradient-buffer fills during the forward, 1 = background chain of Warper.forward."""
+    dev = torch.device(dev)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    s = _side_streams.get((dev, which))
     if s is None:
-        s = _side_streams[dev] = torch.cuda.Stream(dev)
+        s = _side_streams[(dev, which)] = torch.cuda.Stream(dev)
     return s
 
 

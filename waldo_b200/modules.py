@@ -95,6 +95,9 @@ class InverseWarp(nn.Module):
         return Fn.inverse_warp(src_grid, self.src_grid[0], self.tgt_grid[0], self.kernel.view(-1), h, w, niter, erode, trace_box)
 
 
+OVERLAP_BG = True   # Warper.forward: background TPS + inverse warp on a side stream (see there)
+
+
 # ----------------------------------------------------------------------------- a-3, a-5..a-7
 class Warper(nn.Module):
     """models/nets/lvd.py:469-870.  Same option fields, buffers (src_pts, tgt_pts, src_grid, src_grid_hd, tgt_grid,
@@ -139,10 +142,27 @@ class Warper(nn.Module):
         """lvd.py:855-870 -> (tgt_grid_obj, src_grid_obj, tgt_grid_bg, src_grid_bg)."""
         B, T, No = obj_pose.shape[:3]
         Lo, Lb = self.latent_obj_size, self.latent_size
+        # The background chain (40 items at the benchmark shape: small grids, one launch per dilation) and the object chain
+        # (640 items) are independent: the background runs on a side stream and overlaps with the object kernels, forward
+        # and -- autograd replays each node on its forward stream -- backward.  OVERLAP_BG = False serialises them.
+        dev = obj_pose.device
+        fork = OVERLAP_BG and obj_pose.is_cuda
+        if fork:
+            main, side = torch.cuda.current_stream(dev), Fn._side_stream(dev, 1)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                tgb = self.tps_bg(bg_pose.reshape(B * T, Lb, 2))
+                sgb = self.invert_bg(tgb, erode=False) if invert else None
         tgo = self.tps_obj(obj_pose.reshape(B * T * No, Lo, 2))
         sgo = self.invert_obj(tgo) if invert else None
-        tgb = self.tps_bg(bg_pose.reshape(B * T, Lb, 2))
-        sgb = self.invert_bg(tgb, erode=False) if invert else None
+        if fork:
+            main.wait_stream(side)
+            for t in (tgb, sgb):
+                if t is not None:
+                    t.record_stream(main)
+        else:
+            tgb = self.tps_bg(bg_pose.reshape(B * T, Lb, 2))
+            sgb = self.invert_bg(tgb, erode=False) if invert else None
         tgo = tgo.view(B, T, No, *tgo.shape[1:])
         tgb = tgb.view(B, T, *tgb.shape[1:])
         if invert:
