@@ -396,6 +396,45 @@ class Runner:
                 "hbm_frac_step": ((fwd_b + bwd_b) / (ms * 1e-3) / 1e9) / PEAK["gbs"]}
 
 
+def loss_epilogues(dev, steps=20):
+    """f-2 kernels at the LVD-training shape (B=8, T=5, 17 layers, 128x256 low-res lattice): layer entropy + fg_mask forward and
+    backward (HBM streaming: (L + 2) + (2L + 2) floats per pixel) and the 23-tap Gaussian blur of a 3-plane map, fwd + bwd."""
+    import waldo_b200 as wb
+    B, T, L, H, W = 8, 5, 17, 128, 256
+    gen = torch.Generator(device=dev).manual_seed(3)
+    alpha = torch.tanh(torch.randn(B, T, L, H, W, device=dev, generator=gen)).requires_grad_(True)
+    maps = torch.randn(B, T, 3, H, W, device=dev, generator=gen).requires_grad_(True)
+    g1 = torch.randn(B, T, 1, H, W, device=dev, generator=gen)
+    g3 = torch.randn(B, T, 3, H, W, device=dev, generator=gen)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps
+
+    def ent():
+        alpha.grad = None
+        e, f = wb.layer_entropy(alpha)
+        torch.autograd.backward([e, f], [g1, g1])
+
+    def blr():
+        maps.grad = None
+        wb.blur(maps, 3.0, 23).backward(g3)
+    ms_e, ms_b = timed(ent), timed(blr)
+    px = B * T * H * W * 4
+    be, bb = px * ((L + 2) + (2 * L + 2)), px * 3 * 4
+    return {"shape": f"B={B} T={T} L={L} {H}x{W}", "timing": "autograd fwd+bwd, launch overhead of the two small kernels included",
+            "layer_entropy_fwd_bwd": {"ms": ms_e, "alg_bytes": be, "frac": be / (ms_e * 1e-3) / 1e9 / PEAK["gbs"]},
+            "blur23_fwd_bwd": {"ms": ms_b, "alg_bytes": bb, "frac": bb / (ms_b * 1e-3) / 1e9 / PEAK["gbs"]}}
+
+
 PEAK = {"gbs": 6650.0, "src": "B200_PROFILING.md fallback"}
 
 
@@ -529,6 +568,11 @@ def main():
                 torch.cuda.empty_cache()
             except Exception as e:   # never lose the headline line to a side measurement
                 others[name] = {"error": str(e)[:200]}
+        if world == 1:
+            try:
+                others["loss_epilogues"] = loss_epilogues(dev)
+            except Exception as e:
+                others["loss_epilogues"] = {"error": str(e)[:200]}
 
     clocks.close()
     if rank == 0:

@@ -316,6 +316,42 @@ typedef struct {
 } waldo_frames_u8_t;
 int waldo_frames_to_u8(const waldo_frames_u8_t*, waldo_stream_t);
 
+/* ------------------------------------------------------------------ f-2  loss epilogues of LVD training (consumer side of the path)
+ * models/synthesizer.py:1114-1118 `blur(vid, sigma, kernel_size)`: torchvision GaussianBlur = per-plane 2-D convolution
+ * with the outer product of the normalised Gaussian taps, reflect padding (used at :893, :914, :946-947, :974-975).
+ * waldo_blur_bwd is its adjoint: in = d out, out = d in. */
+typedef struct {
+  int n;                      /* planes (product of all leading dims) */
+  int H, W;                   /* both > ksize / 2 (reflect padding) */
+  int ksize;                  /* odd, <= 31; reference default 23 */
+  float sigma;                /* reference default 3 */
+  const float* in;            /* (n, H, W) */
+  float* out;                 /* out (n, H, W) */
+} waldo_blur_t;
+int waldo_blur_fwd(const waldo_blur_t*, waldo_stream_t);
+int waldo_blur_bwd(const waldo_blur_t*, waldo_stream_t);
+
+/* models/synthesizer.py:886-889 (entropy of the normalised layer opacities, divided by 0.37) and :933 (fg_mask):
+ *   x_k = (alpha_k + 1) / 2 + 1e-6;  p = x / max(sum_k |x_k|, 1e-12);  entropy = -sum_k p_k log(p_k + 1e-6) / 0.37
+ *   fg = sum_{k >= 1} (alpha_k + 1) / 2 */
+typedef struct {
+  int n;                      /* B*T */
+  int L;                      /* layers, layer 0 = background */
+  int HW;
+  const float* alpha;         /* (n, L, HW) in [-1, 1] */
+  float* entropy;             /* out (n, HW) or NULL */
+  float* fg;                  /* out (n, HW) or NULL */
+} waldo_layer_entropy_t;
+int waldo_layer_entropy_fwd(const waldo_layer_entropy_t*, waldo_stream_t);
+
+typedef struct {
+  waldo_layer_entropy_t f;    /* alpha as in the forward; the two outputs are not read */
+  const float* d_entropy;     /* (n, HW) or NULL (= zero) */
+  const float* d_fg;          /* (n, HW) or NULL (= zero) */
+  float* d_alpha;             /* out (n, L, HW), written (not accumulated) */
+} waldo_layer_entropy_bwd_t;
+int waldo_layer_entropy_bwd(const waldo_layer_entropy_bwd_t*, waldo_stream_t);
+
 #ifdef __cplusplus
 }
 #endif

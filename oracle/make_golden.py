@@ -118,10 +118,33 @@ def run_reference(cfg: wo.PathConfig, B, T, Tc, smooth, seed=0, lean=False):
     return {k: v.detach().cpu().numpy() for k, v in res.items()}
 
 
+def blur_fixture():
+    """f-2: the reference's own `blur` (models/synthesizer.py:1114-1118, torchvision GaussianBlur) on seeded planes, with the
+    autograd gradient of a seeded projection: default 23 taps / sigma 3 (:914 blur_sigma), the 3-tap sigma-2 call of :893,
+    a ragged size and one barely larger than the reflect margin."""
+    import importlib
+    ref_loader.load()
+    syn = importlib.import_module("models.synthesizer")
+    gen = torch.Generator().manual_seed(77)
+    res = {}
+    for i, (shape, sigma, k) in enumerate((((2, 3, 2, 40, 72), 3.0, 23), ((1, 2, 5, 33, 47), 2.0, 3), ((1, 1, 1, 12, 13), 3.0, 23),
+                                           ((2, 1, 3, 64, 128), 1.5, 9))):
+        x = torch.randn(shape, generator=gen).requires_grad_(True)
+        w = torch.randn(shape, generator=gen)
+        y = syn.blur(x, sigma=sigma, kernel_size=k)
+        (y * w).sum().backward()
+        res.update({f"x{i}": x.detach(), f"w{i}": w, f"y{i}": y.detach(), f"g{i}": x.grad, f"p{i}": torch.tensor([sigma, float(k)])})
+    path = os.path.join(OUT, "blur.npz")
+    np.savez_compressed(path, **{k: v.numpy() for k, v in res.items()})
+    print(f"blur: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     only = sys.argv[1:]
+    if not only or "blur" in only:
+        blur_fixture()
     for name, (kw, B, T, Tc, smooth) in CASES.items():
         if only and name not in only:
             continue

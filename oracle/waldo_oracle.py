@@ -523,6 +523,38 @@ def wif_fuse(raw_output: torch.Tensor, unet_out: torch.Tensor, ab: bool = True) 
     return ((gate * v[:, :, :, :3] + beta) * score).sum(dim=2)
 
 
+# --------------------------------------------------------------------------- f-2: loss epilogues
+def gaussian_taps(kernel_size: int, sigma: float, dtype=torch.float32) -> torch.Tensor:
+    """The 1-D taps torchvision's gaussian_blur builds (the reference calls it through models/synthesizer.py:1116
+    `GaussianBlur(kernel_size=kernel_size, sigma=sigma)`): linspace(-half, half, k), exp(-0.5 (x / sigma)^2), normalised."""
+    half = (kernel_size - 1) * 0.5
+    x = torch.linspace(-half, half, steps=kernel_size, dtype=dtype)
+    pdf = torch.exp(-0.5 * (x / sigma).pow(2))
+    return pdf / pdf.sum()
+
+
+def blur(vid: torch.Tensor, sigma: float = 3.0, kernel_size: int = 23) -> torch.Tensor:
+    """models/synthesizer.py:1114-1118: every (H, W) plane of vid (..., C, H, W) convolved with the outer product of the
+    Gaussian taps after reflect padding (what torchvision's GaussianBlur does; restated with plain torch ops so that the
+    oracle does not need torchvision and has an fp64 twin)."""
+    k1 = gaussian_taps(kernel_size, sigma, vid.dtype)
+    k2 = torch.mm(k1[:, None], k1[None, :])
+    H, W = vid.shape[-2:]
+    img = vid.reshape(-1, 1, H, W)
+    r = kernel_size // 2
+    img = F.pad(img, [r, r, r, r], mode="reflect")
+    return F.conv2d(img, k2[None, None]).view_as(vid)
+
+
+def layer_entropy(alpha: torch.Tensor):
+    """models/synthesizer.py:886-889 and :933 -> (entropy (B,T,1,H,W), fg_mask (B,T,1,H,W)) of alpha (B,T,L,H,W)."""
+    entropy = (alpha + 1) / 2
+    entropy = F.normalize(entropy + 1e-6, p=1, dim=2)
+    entropy = -torch.sum(torch.mul(entropy, torch.log(entropy + 1e-6)), dim=2, keepdim=True) / 0.37
+    fg_mask = ((alpha[:, :, 1:] + 1) / 2).sum(dim=2, keepdim=True)
+    return entropy, fg_mask
+
+
 # --------------------------------------------------------------------------- synthetic inputs (SURVEY.md §8d)
 def synth_inputs(cfg: PathConfig, B: int, T: int, Tc: int, seed: int = 0, dtype=torch.float32, smooth: bool = False,
                  radius: float = 0.5):

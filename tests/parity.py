@@ -543,6 +543,56 @@ def check_pack_input(dev, B=2, T=3, Hd=12, Wd=20, num_lyt=20, seed=5):
     assert torch.equal(wb.pack_input(ramp.to(dev), lab.to(dev), 2).cpu()[:, :, :3], reference_pack(ramp, lab, 2)[:, :, :3])
 
 
+# ------------------------------------------------------------------------------------------------ f-2 loss epilogues
+def check_blur(dev):
+    """f-2 `blur` (synthesizer.py:1114-1118) against the outputs and autograd gradients of the REFERENCE's own function
+    (tests/golden/blur.npz, oracle/make_golden.blur_fixture) and against the oracle restatement + its fp64 twin."""
+    z = np.load(os.path.join(GOLDEN, "blur.npz"))
+    i = 0
+    while f"x{i}" in z.files:
+        x, w, y_ref, g_ref = (torch.from_numpy(z[f"{n}{i}"]) for n in "xwyg")
+        sigma, k = float(z[f"p{i}"][0]), int(z[f"p{i}"][1])
+        xd = x.clone().to(dev).requires_grad_(True)
+        y = wb.blur(xd, sigma=sigma, kernel_size=k)
+        (y * w.to(dev)).sum().backward()
+        x64 = x.double().requires_grad_(True)
+        y64 = wo.blur(x64, sigma, k)
+        (y64 * w.double()).sum().backward()
+        arbitrated(y, y_ref, y64, FWD_TOL, f"blur[{i}] vs the reference")
+        arbitrated(y, wo.blur(x, sigma, k), y64, FWD_TOL, f"blur[{i}] vs the oracle")
+        grad_close(xd.grad, g_ref, x64.grad, f"blur[{i}] d vid")
+        i += 1
+    assert i >= 4
+
+
+def check_layer_entropy(dev, seed=11):
+    """f-2 layer entropy + fg_mask (synthesizer.py:886-889, :933) against the oracle (fp32 + fp64 twin), forward and
+    gradients, on a random stack, a saturated one (alpha = +-1 exactly: the 1e-6 floors matter) and one with L = 2."""
+    gen = torch.Generator().manual_seed(seed)
+    cases = [torch.tanh(2 * torch.randn(2, 3, 17, 20, 36, generator=gen)),
+             torch.where(torch.rand(1, 2, 5, 9, 11, generator=gen) > 0.5, torch.ones(()), -torch.ones(())),
+             torch.tanh(torch.randn(1, 1, 2, 7, 5, generator=gen))]
+    for i, a in enumerate(cases):
+        we, wf = torch.randn(a.shape[0], a.shape[1], 1, *a.shape[3:], generator=gen), torch.randn(a.shape[0], a.shape[1], 1, *a.shape[3:], generator=gen)
+        ad = a.clone().to(dev).requires_grad_(True)
+        ent, fg = wb.layer_entropy(ad)
+        ((ent * we.to(dev)).sum() + (fg * wf.to(dev)).sum()).backward()
+        a32, a64 = a.clone().requires_grad_(True), a.double().requires_grad_(True)
+        e32, f32 = wo.layer_entropy(a32)
+        e64, f64 = wo.layer_entropy(a64)
+        ((e32 * we).sum() + (f32 * wf).sum()).backward()
+        ((e64 * we.double()).sum() + (f64 * wf.double()).sum()).backward()
+        arbitrated(ent, e32, e64, FWD_TOL, f"layer_entropy[{i}]")
+        arbitrated(fg, f32, f64, FWD_TOL, f"fg_mask[{i}]")
+        grad_close(ad.grad, a32.grad, a64.grad, f"layer_entropy[{i}] d alpha")
+        # each output alone (the other upstream gradient is None)
+        ad2 = a.clone().to(dev).requires_grad_(True)
+        (wb.layer_entropy(ad2)[1] * wf.to(dev)).sum().backward()
+        a2 = a.clone().requires_grad_(True)
+        (wo.layer_entropy(a2)[1] * wf).sum().backward()
+        grad_close(ad2.grad, a2.grad, a2.grad.double(), f"fg_mask[{i}] d alpha")
+
+
 # ------------------------------------------------------------------------------------------------ f-4 output side
 def check_frames_to_u8(dev, seed=9):
     """Bit-exact against the reference's own formulas (tools/utils.py:246-249 normalize, :258-264 dump_video), restated

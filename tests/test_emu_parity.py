@@ -69,6 +69,14 @@ def test_kats():
     parity.check_kats(DEV)
 
 
+def test_blur():
+    parity.check_blur(DEV)
+
+
+def test_layer_entropy():
+    parity.check_layer_entropy(DEV)
+
+
 def test_pack_input():
     parity.check_pack_input(DEV)
 

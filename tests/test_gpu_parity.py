@@ -94,6 +94,14 @@ def test_small_chain_deterministic_gradients(dev):
     parity.check_chain_deterministic(dev, cfg, B, T, Tc, seed=5)
 
 
+def test_blur(dev):
+    parity.check_blur(dev)
+
+
+def test_layer_entropy(dev):
+    parity.check_layer_entropy(dev)
+
+
 def test_pack_input(dev):
     parity.check_pack_input(dev)
     parity.check_pack_input(dev, B=1, T=2, Hd=256, Wd=832, num_lyt=19)

@@ -80,3 +80,21 @@ def test_aten_formulas_restated():
     y = torch.randn(2, 3, 16, 24, generator=gen)
     assert float((wo.resize(y, 0.25) - wo.resize_explicit(y, (4, 6), (4, 4))).abs().max()) < 1e-6
     assert float((wo.resize(y, 0.25) - y[..., 1::4, :][..., 1::4].add(y[..., 1::4, :][..., 2::4]).add(y[..., 2::4, :][..., 1::4]).add(y[..., 2::4, :][..., 2::4]) / 4).abs().max()) < 1e-6
+
+
+def test_blur_against_the_reference_fixture():
+    """f-2: the oracle's `blur` restatement against outputs and autograd gradients of the reference's own function
+    (models/synthesizer.py:1114-1118 through torchvision's GaussianBlur), tests/golden/blur.npz."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(parity.GOLDEN, "blur.npz"))
+    i = 0
+    while f"x{i}" in z.files:
+        x = torch.from_numpy(z[f"x{i}"]).requires_grad_(True)
+        w, y_ref, g_ref = (torch.from_numpy(z[f"{n}{i}"]) for n in "wyg")
+        y = wo.blur(x, float(z[f"p{i}"][0]), int(z[f"p{i}"][1]))
+        (y * w).sum().backward()
+        assert float((y - y_ref).abs().max()) <= 2e-6, i
+        assert float((x.grad - g_ref).abs().max()) <= 1e-5 * float(g_ref.abs().max()), i
+        i += 1
+    assert i >= 4

@@ -16,6 +16,7 @@
 #include "wb_wif.cuh"
 #include "wb_pack.cuh"
 #include "wb_field.cuh"
+#include "wb_loss.cuh"
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_wb_launches{0};
@@ -332,6 +333,50 @@ int waldo_frames_to_u8(const waldo_frames_u8_t* a, waldo_stream_t st) {
   WB_REQUIRE(((uintptr_t)a->frames & 15) == 0 && ((uintptr_t)a->out & 3) == 0, "frames_to_u8: frames must be 16-byte, out 4-byte aligned");
   if (a->n == 0) return 0;
   WB_LAUNCH(k_frames_to_u8, dim3(wb_blocks(((long long)a->HW + 3) / 4, 256, 1024), a->n), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ loss epilogues
+static int wb_blur_check(const waldo_blur_t* a, const char* who) {
+  WB_REQUIRE(a && a->n >= 0 && a->H > 0 && a->W > 0, "%s: bad sizes", who);
+  WB_REQUIRE(a->ksize >= 1 && (a->ksize & 1) && a->ksize <= WB_BLUR_MAX_K, "%s: kernel_size must be odd and <= %d", who, WB_BLUR_MAX_K);
+  WB_REQUIRE(a->H > a->ksize / 2 && a->W > a->ksize / 2, "%s: reflect padding needs H, W > kernel_size / 2", who);
+  WB_REQUIRE(a->sigma > 0.f && a->in && a->out && a->in != a->out, "%s: bad sigma / pointers", who);
+  WB_REQUIRE(a->n <= 65535, "%s: more than 65535 planes in one call", who);
+  return 0;
+}
+int waldo_blur_fwd(const waldo_blur_t* a, waldo_stream_t st) {
+  int rc = wb_blur_check(a, "blur_fwd");
+  if (rc) return rc;
+  if (a->n == 0) return 0;
+  const int tiles = ((a->W + WB_BLUR_T - 1) / WB_BLUR_T) * ((a->H + WB_BLUR_T - 1) / WB_BLUR_T);
+  WB_LAUNCH(k_blur<false>, dim3(tiles, a->n), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+int waldo_blur_bwd(const waldo_blur_t* a, waldo_stream_t st) {
+  int rc = wb_blur_check(a, "blur_bwd");
+  if (rc) return rc;
+  if (a->n == 0) return 0;
+  const int tiles = ((a->W + WB_BLUR_T - 1) / WB_BLUR_T) * ((a->H + WB_BLUR_T - 1) / WB_BLUR_T);
+  WB_LAUNCH(k_blur<true>, dim3(tiles, a->n), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+int waldo_layer_entropy_fwd(const waldo_layer_entropy_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->L >= 1 && a->HW > 0 && a->n <= 65535, "layer_entropy_fwd: bad sizes");
+  WB_REQUIRE(a->alpha && (a->entropy || a->fg), "layer_entropy_fwd: null pointer");
+  if (a->n == 0) return 0;
+  WB_LAUNCH(k_layer_entropy_fwd, dim3(wb_blocks(a->HW, 256, 1024), a->n), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+int waldo_layer_entropy_bwd(const waldo_layer_entropy_bwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->f.n >= 0 && a->f.L >= 1 && a->f.HW > 0 && a->f.n <= 65535, "layer_entropy_bwd: bad sizes");
+  WB_REQUIRE(a->f.alpha && a->d_alpha, "layer_entropy_bwd: null pointer");
+  if (a->f.n == 0) return 0;
+  WB_LAUNCH(k_layer_entropy_bwd, dim3(wb_blocks(a->f.HW, 256, 1024), a->f.n), dim3(256), 0, st, *a);
   WB_LAUNCHED();
   return 0;
 }

@@ -325,10 +325,22 @@ WB_DEV int wb_warp_max(int v) {
 #endif
   return v;
 }
-// displacement of sample (X, Y) in pixels from the staged lattice displacements: the arithmetic of wb_inv_disp
-WB_DEV void wb_inv_disp_s(const WbInvArgs& a, const float2* s_d, int X, int Y, float& dx, float& dy) {
-  const float rh = (float)a.Hs / (float)a.Ht, rw = (float)a.Ws / (float)a.Wt;
-  const WbAxis ay = wb_axis(Y, rh, a.Hs), ax = wb_axis(X, rw, a.Ws);
+// walk s = tid, tid + nthr, ... over a W-wide lattice as (X, Y) without a division per step
+struct WbWalk { int X, Y, sx, sy, W; };
+WB_DEV WbWalk wb_walk(int tid, int nthr, int W) {
+  WbWalk w;
+  w.Y = tid / W; w.X = tid - w.Y * W; w.sy = nthr / W; w.sx = nthr - w.sy * W; w.W = W;
+  return w;
+}
+WB_DEV void wb_walk_next(WbWalk& w) { w.X += w.sx; w.Y += w.sy; if (w.X >= w.W) { w.X -= w.W; ++w.Y; } }
+// c / W for 0 <= c < 2^24 through a float reciprocal, corrected to the exact quotient
+WB_DEV int wb_div_small(int c, int W, float invW) {
+  int q = (int)((float)c * invW);
+  if (q * W > c) --q; else if ((q + 1) * W <= c) ++q;
+  return q;
+}
+// displacement of a sample in pixels from the staged lattice displacements: the arithmetic of wb_inv_disp
+WB_DEV void wb_inv_disp_s(const WbInvArgs& a, const float2* s_d, const WbAxis& ax, const WbAxis& ay, float& dx, float& dy) {
   const float2 v00 = s_d[ay.i0 * a.Ws + ax.i0], v01 = s_d[ay.i0 * a.Ws + ax.i1];
   const float2 v10 = s_d[ay.i1 * a.Ws + ax.i0], v11 = s_d[ay.i1 * a.Ws + ax.i1];
   const float d0 = wb_lerp2(v00.x, v01.x, v10.x, v11.x, ax, ay), d1 = wb_lerp2(v00.y, v01.y, v10.y, v11.y, ax, ay);
@@ -388,8 +400,8 @@ __global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, i
   __shared__ int s_bb[4], s_hit[4], s_over;
   float g[9];
   WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
-  if (tid < 4) { s_bb[tid] = tid < 2 ? INT_MAX : INT_MIN; s_hit[tid] = tid < 2 ? INT_MAX : -1; }
-  if (tid == 0) s_over = 0;
+  for (int i = tid; i < 4; i += nthr) { s_bb[i] = i < 2 ? INT_MAX : INT_MIN; s_hit[i] = i < 2 ? INT_MAX : -1; }   // (block-stride: the
+  if (tid == 0) s_over = 0;                                                                                      //  emulation runs one thread)
   __syncthreads();
   {   // stage the lattice, bound where its points land (pixels)
     int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
@@ -412,6 +424,9 @@ __global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, i
   const bool some = ix0 <= ix1 && iy0 <= iy1;
   const int aw = some ? ix1 - ix0 + 1 + 2 * m : 0, ah = some ? iy1 - iy0 + 1 + 2 * m : 0;   // padded coordinates: + m on both sides
   bool fits = (long long)aw * ah <= (long long)cap;
+  const float rh = (float)a.Hs / (float)Ht, rw = (float)a.Ws / (float)Wt, invWt = 1.f / (float)Wt;
+  const bool xconst = nthr % Wt == 0;        // every thread stays in one column: its x taps are computed once
+  WbAxis ax = wb_axis(tid % Wt, rw, a.Ws);
   for (int attempt = 0; attempt < 2; ++attempt) {
     WbInvArea A;
     if (fits) {
@@ -425,10 +440,12 @@ __global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, i
     }
     __syncthreads();
     // claim: landing cell of every sample; the lowest sample index takes the cell            warp.py:76-88,113-117
-    for (int s = tid; s < P; s += nthr) {
-      const int Y = s / Wt, X = s - Y * Wt;
+    WbWalk wk = wb_walk(tid, nthr, Wt);
+    for (int s = tid; s < P; s += nthr, wb_walk_next(wk)) {
+      const int Y = wk.Y, X = wk.X;
+      if (!xconst) ax = wb_axis(X, rw, a.Ws);
       float dx, dy;
-      wb_inv_disp_s(a, s_d, X, Y, dx, dy);
+      wb_inv_disp_s(a, s_d, ax, wb_axis(Y, rh, a.Hs), dx, dy);
       const float fx = rintf(__fadd_rn((float)X, dx)), fy = rintf(__fadd_rn((float)Y, dy));   // half-to-even
       int cell = -1;
       if (fx >= 0.f && fy >= 0.f && fx <= (float)(Wt - 1) && fy <= (float)(Ht - 1)) {
@@ -443,14 +460,16 @@ __global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, i
     if (!(fits && s_over)) {
       // deposit: winners write the negated displacement                                       warp.py:121-123
       int hx0 = INT_MAX, hy0 = INT_MAX, hx1 = -1, hy1 = -1;
-      for (int s = tid; s < P; s += nthr) {
+      wk = wb_walk(tid, nthr, Wt);
+      for (int s = tid; s < P; s += nthr, wb_walk_next(wk)) {
         const int cell = it.field[s];
         if (cell < 0) continue;
-        const int cy = cell / Wt, cx = cell - cy * Wt, px = cx + m, py = cy + m;
+        const int cy = wb_div_small(cell, Wt, invWt), cx = cell - cy * Wt, px = cx + m, py = cy + m;
         if (A.winner[(py - A.wy0) * A.ww + (px - A.wx0)] != s) continue;
-        const int Y = s / Wt, X = s - Y * Wt;
+        const int Y = wk.Y, X = wk.X;
+        if (!xconst) ax = wb_axis(X, rw, a.Ws);
         float dx, dy;
-        wb_inv_disp_s(a, s_d, X, Y, dx, dy);
+        wb_inv_disp_s(a, s_d, ax, wb_axis(Y, rh, a.Hs), dx, dy);
         const int c = (py - A.y0) * A.w + (px - A.x0);
         A.vx[c] = -dx; A.vy[c] = -dy; A.level[c] = 0;
         hx0 = min(hx0, px); hy0 = min(hy0, py); hx1 = max(hx1, px); hy1 = max(hy1, py);
@@ -458,25 +477,26 @@ __global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, i
       hx0 = wb_warp_min(hx0); hy0 = wb_warp_min(hy0); hx1 = wb_warp_max(hx1); hy1 = wb_warp_max(hy1);
       if (wb_lane() == 0 && hx1 >= 0) { atomicMin(&s_hit[0], hx0); atomicMin(&s_hit[1], hy0); atomicMax(&s_hit[2], hx1); atomicMax(&s_hit[3], hy1); }
       __syncthreads();
-      if (tid < 4) it.bbox[tid] = s_hit[tid];
+      for (int i = tid; i < 4; i += nthr) it.bbox[i] = s_hit[i];
       // dilations, erosions over the hit box grown by the iteration count                     warp.py:135-162
       int x0, y0, w, cells;
       for (int iter = 1; iter <= a.niter; ++iter) {
         wb_inv_box_area(s_hit, iter, A, x0, y0, w, cells);
-        for (int i = tid; i < cells; i += nthr) wb_inv_dilate_area(A, g, x0 + i % w, y0 + i / w, iter, Hp, Wp);
+        if (cells) { WbWalk wc = wb_walk(tid, nthr, w); for (int i = tid; i < cells; i += nthr, wb_walk_next(wc)) wb_inv_dilate_area(A, g, x0 + wc.X, y0 + wc.Y, iter, Hp, Wp); }
         __syncthreads();
       }
       if (a.erode) {
         wb_inv_box_area(s_hit, a.niter, A, x0, y0, w, cells);
         for (int iter = 1; iter <= a.niter; ++iter) {
-          for (int i = tid; i < cells; i += nthr) wb_inv_erode_area(A, x0 + i % w, y0 + i / w, iter, Hp, Wp);
+          if (cells) { WbWalk wc = wb_walk(tid, nthr, w); for (int i = tid; i < cells; i += nthr, wb_walk_next(wc)) wb_inv_erode_area(A, x0 + wc.X, y0 + wc.Y, iter, Hp, Wp); }
           __syncthreads();
         }
       }
       // final: sentinel for unknown cells, crop, back to normalised coordinates                warp.py:164-174
       float* out = a.out + (size_t)blockIdx.x * P * 2;
-      for (int s = tid; s < P; s += nthr) {
-        const int Y = s / Wt, X = s - Y * Wt, px = X + m, py = Y + m;
+      wk = wb_walk(tid, nthr, Wt);
+      for (int s = tid; s < P; s += nthr, wb_walk_next(wk)) {
+        const int px = wk.X + m, py = wk.Y + m;
         bool known = false;
         int c = 0;
         if (px >= A.x0 && px < A.x0 + A.w && py >= A.y0 && py < A.y0 + A.h) {
@@ -488,17 +508,19 @@ __global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, i
         out[2 * s + 1] = __fadd_rn(__ldg(a.id_tgt + 2 * s + 1), __fdiv_rn(__fmul_rn(iy, 2.f), (float)Ht));
       }
       if (fits) {   // the maps the backward (and the index-map parity checks) read
-        for (int i = tid; i < PP; i += nthr) {
-          const int y = i / Wp, x = i - y * Wp;
+        WbWalk wp = wb_walk(tid, nthr, Wp);
+        for (int i = tid; i < PP; i += nthr, wb_walk_next(wp)) {
+          const int y = wp.Y, x = wp.X;
           const bool in = x >= A.x0 && x < A.x0 + A.w && y >= A.y0 && y < A.y0 + A.h;
           const int c = in ? (y - A.y0) * A.w + (x - A.x0) : 0;
           it.level[i] = in ? s_lv[c] : (uint8_t)255;
           it.eroded[i] = in ? s_er[c] : (uint8_t)0;
-          if (i < P) {
-            const int Y = i / Wt, X = i - Y * Wt, qx = X + m, qy = Y + m;
-            const bool inw = qx >= A.x0 && qx < A.x0 + A.w && qy >= A.y0 && qy < A.y0 + A.h;
-            it.winner[i] = inw ? s_win[(qy - A.y0) * A.w + (qx - A.x0)] : INT_MAX;
-          }
+        }
+        wk = wb_walk(tid, nthr, Wt);
+        for (int i = tid; i < P; i += nthr, wb_walk_next(wk)) {
+          const int qx = wk.X + m, qy = wk.Y + m;
+          const bool inw = qx >= A.x0 && qx < A.x0 + A.w && qy >= A.y0 && qy < A.y0 + A.h;
+          it.winner[i] = inw ? s_win[(qy - A.y0) * A.w + (qx - A.x0)] : INT_MAX;
         }
       }
       return;

@@ -593,6 +593,79 @@ def frames_to_u8(vid, span=(-1.0, 1.0), out=None):
     return out
 
 
+# ===================================================================================== f-2 loss epilogues
+class _Blur(torch.autograd.Function):
+    """models/synthesizer.py:1114-1118 `blur`: torchvision GaussianBlur(kernel_size, sigma) over the last two dims."""
+
+    @staticmethod
+    def forward(ctx, vid, sigma, kernel_size):
+        lib = L.load()
+        x = _c(vid.detach())
+        H, W = x.shape[-2:]
+        n = x.numel() // (H * W)
+        out = torch.empty_like(x)
+        a = L.Blur(n, H, W, int(kernel_size), float(sigma), L.ptr(x, name="vid"), L.ptr(out))
+        L.call(lib.waldo_blur_fwd, a, x, "blur_fwd")
+        ctx.dims = (n, H, W, int(kernel_size), float(sigma))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = L.load()
+        n, H, W, K, sigma = ctx.dims
+        g = _c(d_out)
+        d_in = torch.empty_like(g)
+        a = L.Blur(n, H, W, K, sigma, L.ptr(g), L.ptr(d_in))
+        L.call(lib.waldo_blur_bwd, a, g, "blur_bwd")
+        return d_in, None, None
+
+
+def blur(vid, sigma=3.0, kernel_size=23):
+    if vid.dim() < 3:
+        raise RuntimeError(f"waldo_b200.blur: expected (..., C, H, W), got {tuple(vid.shape)}")
+    return _Blur.apply(vid, sigma, kernel_size)
+
+
+class _LayerEntropy(torch.autograd.Function):
+    """models/synthesizer.py:886-889 (entropy of the normalised layer opacities / 0.37) and :933 (fg_mask), one pass."""
+
+    @staticmethod
+    def forward(ctx, alpha):
+        lib = L.load()
+        a_c = _c(alpha.detach())
+        *lead, Lr, H, W = a_c.shape
+        n = 1
+        for v in lead:
+            n *= v
+        ent = torch.empty(*lead, 1, H, W, device=a_c.device, dtype=torch.float32)
+        fg = torch.empty(*lead, 1, H, W, device=a_c.device, dtype=torch.float32)
+        a = L.LayerEntropy(n, Lr, H * W, L.ptr(a_c, name="alpha"), L.ptr(ent), L.ptr(fg))
+        L.call(lib.waldo_layer_entropy_fwd, a, a_c, "layer_entropy_fwd")
+        ctx.save_for_backward(a_c)
+        ctx.dims = (n, Lr, H * W)
+        ctx.set_materialize_grads(False)
+        return ent, fg
+
+    @staticmethod
+    def backward(ctx, d_ent, d_fg):
+        lib = L.load()
+        (a_c,) = ctx.saved_tensors
+        n, Lr, HW = ctx.dims
+        d_ent = _c(d_ent) if d_ent is not None else None
+        d_fg = _c(d_fg) if d_fg is not None else None
+        d_alpha = torch.empty_like(a_c)
+        b = L.LayerEntropyBwd(L.LayerEntropy(n, Lr, HW, L.ptr(a_c), None, None), L.ptr(d_ent), L.ptr(d_fg), L.ptr(d_alpha))
+        L.call(lib.waldo_layer_entropy_bwd, b, a_c, "layer_entropy_bwd")
+        return d_alpha
+
+
+def layer_entropy(alpha):
+    """alpha (..., L, H, W) in [-1, 1] -> (entropy (..., 1, H, W), fg_mask (..., 1, H, W))."""
+    if alpha.dim() < 3:
+        raise RuntimeError(f"waldo_b200.layer_entropy: expected (..., L, H, W), got {tuple(alpha.shape)}")
+    return _LayerEntropy.apply(alpha)
+
+
 # ===================================================================================== a-5 / a-11 field warp, scale
 def _no_grad_path(*tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):

@@ -356,3 +356,17 @@ def frames_to_u8(vid, span=(-1.0, 1.0), out=None):
     """What dump_video does to a predicted video before encoding (tools/utils.py:246-249, :258-264), on the device:
     (..., 3, H, W) fp32 -> (..., H, W, 3) uint8.  save_vid (synthesizer.py:184-193) then copies a quarter of the bytes."""
     return Fn.frames_to_u8(vid, span, out)
+
+
+# ----------------------------------------------------------------------------- f-2 (consumer side: LVD-training loss epilogues)
+def blur(vid, sigma=3.0, kernel_size=23):
+    """models/synthesizer.py:1114-1118: Gaussian blur (torchvision GaussianBlur, reflect padding) of every (H, W) plane of
+    vid (..., C, H, W); differentiable (the adjoint folds the reflected margins back)."""
+    return Fn.blur(vid, sigma, kernel_size)
+
+
+def layer_entropy(alpha):
+    """models/synthesizer.py:886-889 and :933 in one pass over the layer stack alpha (B, T, L, H, W) in [-1, 1]:
+    (entropy (B, T, 1, H, W) = -sum_k p_k log(p_k + 1e-6) / 0.37 with p = normalize((alpha + 1) / 2 + 1e-6, p=1),
+     fg_mask (B, T, 1, H, W) = sum_{k >= 1} (alpha_k + 1) / 2); differentiable."""
+    return Fn.layer_entropy(alpha)
