@@ -460,19 +460,20 @@ __global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, i
     if (!(fits && s_over)) {
       // deposit: winners write the negated displacement                                       warp.py:121-123
       int hx0 = INT_MAX, hy0 = INT_MAX, hx1 = -1, hy1 = -1;
-      wk = wb_walk(tid, nthr, Wt);
-      for (int s = tid; s < P; s += nthr, wb_walk_next(wk)) {
-        const int cell = it.field[s];
-        if (cell < 0) continue;
-        const int cy = wb_div_small(cell, Wt, invWt), cx = cell - cy * Wt, px = cx + m, py = cy + m;
-        if (A.winner[(py - A.wy0) * A.ww + (px - A.wx0)] != s) continue;
-        const int Y = wk.Y, X = wk.X;
-        if (!xconst) ax = wb_axis(X, rw, a.Ws);
-        float dx, dy;
-        wb_inv_disp_s(a, s_d, ax, wb_axis(Y, rh, a.Hs), dx, dy);
-        const int c = (py - A.y0) * A.w + (px - A.x0);
-        A.vx[c] = -dx; A.vy[c] = -dy; A.level[c] = 0;
-        hx0 = min(hx0, px); hy0 = min(hy0, py); hx1 = max(hx1, px); hy1 = max(hy1, py);
+      {   // (walks the winner map -- the landing box -- not the samples: a quarter of the trips at the benchmark shape)
+        const int nwin = fits ? aw * ah : P;
+        WbWalk ww = wb_walk(tid, nthr, A.ww);
+        for (int i = tid; i < nwin; i += nthr, wb_walk_next(ww)) {
+          const int s = A.winner[i];
+          if (s == INT_MAX) continue;
+          const int px = A.wx0 + ww.X, py = A.wy0 + ww.Y;
+          const int Y = wb_div_small(s, Wt, invWt), X = s - Y * Wt;
+          float dx, dy;
+          wb_inv_disp_s(a, s_d, wb_axis(X, rw, a.Ws), wb_axis(Y, rh, a.Hs), dx, dy);
+          const int c = (py - A.y0) * A.w + (px - A.x0);
+          A.vx[c] = -dx; A.vy[c] = -dy; A.level[c] = 0;
+          hx0 = min(hx0, px); hy0 = min(hy0, py); hx1 = max(hx1, px); hy1 = max(hy1, py);
+        }
       }
       hx0 = wb_warp_min(hx0); hy0 = wb_warp_min(hy0); hx1 = wb_warp_max(hx1); hy1 = wb_warp_max(hy1);
       if (wb_lane() == 0 && hx1 >= 0) { atomicMin(&s_hit[0], hx0); atomicMin(&s_hit[1], hy0); atomicMax(&s_hit[2], hx1); atomicMax(&s_hit[3], hy1); }
@@ -499,15 +500,17 @@ __global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, i
         const int px = wk.X + m, py = wk.Y + m;
         bool known = false;
         int c = 0;
-        if (px >= A.x0 && px < A.x0 + A.w && py >= A.y0 && py < A.y0 + A.h) {
+        const bool in = px >= A.x0 && px < A.x0 + A.w && py >= A.y0 && py < A.y0 + A.h;
+        if (in) {
           c = (py - A.y0) * A.w + (px - A.x0);
           known = A.level[c] != 255 && A.eroded[c] == 0;
         }
         const float ix = known ? A.vx[c] : (float)(2 * Wt), iy = known ? A.vy[c] : (float)(2 * Ht);
         out[2 * s] = __fadd_rn(__ldg(a.id_tgt + 2 * s), __fdiv_rn(__fmul_rn(ix, 2.f), (float)Wt));
         out[2 * s + 1] = __fadd_rn(__ldg(a.id_tgt + 2 * s + 1), __fdiv_rn(__fmul_rn(iy, 2.f), (float)Ht));
+        if (fits) it.winner[s] = in ? s_win[c] : INT_MAX;   // (shared-memory winner map: same indexing as the area)
       }
-      if (fits) {   // the maps the backward (and the index-map parity checks) read
+      if (fits) {   // the byte maps the backward (and the index-map parity checks) read
         WbWalk wp = wb_walk(tid, nthr, Wp);
         for (int i = tid; i < PP; i += nthr, wb_walk_next(wp)) {
           const int y = wp.Y, x = wp.X;
@@ -515,12 +518,6 @@ __global__ void __launch_bounds__(WB_INVF_THREADS, 1) k_inv_fused(WbInvArgs a, i
           const int c = in ? (y - A.y0) * A.w + (x - A.x0) : 0;
           it.level[i] = in ? s_lv[c] : (uint8_t)255;
           it.eroded[i] = in ? s_er[c] : (uint8_t)0;
-        }
-        wk = wb_walk(tid, nthr, Wt);
-        for (int i = tid; i < P; i += nthr, wb_walk_next(wk)) {
-          const int qx = wk.X + m, qy = wk.Y + m;
-          const bool inw = qx >= A.x0 && qx < A.x0 + A.w && qy >= A.y0 && qy < A.y0 + A.h;
-          it.winner[i] = inw ? s_win[(qy - A.y0) * A.w + (qx - A.x0)] : INT_MAX;
         }
       }
       return;
