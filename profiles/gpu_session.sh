@@ -39,7 +39,7 @@ fullk)
      -o $OUT/${TAG}_fullk -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_fullk.log 2>&1; echo "fullk rc=$?"; tail -2 $OUT/${TAG}_fullk.log;;
 full)
   timeout 1500 ncu --set full --clock-control none --import-source on \
-     -k 'regex:k_gather_bwd|k_layers_bwd|k_alpha_prep_bwd|k_gather_fwd|k_layers_fwd|k_alpha_prep|k_class_profile' -c 8 \
+     -k 'regex:k_gather_bwd|k_layers_bwd|k_alpha_prep_bwd|k_gather_fwd|k_layers_fwd|k_alpha_prep|k_class_profile|k_inv_fused' -c 9 \
      -o $OUT/${TAG}_full -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_full.log 2>&1; echo "full rc=$?"; tail -2 $OUT/${TAG}_full.log;;
 esac
 done

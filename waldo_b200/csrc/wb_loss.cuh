@@ -64,22 +64,39 @@ __global__ void __launch_bounds__(256) k_blur(waldo_blur_t p) {
       s_in[ly][lx] = v;
     }
     __syncthreads();
-    for (int i = tid; i < IN * WB_BLUR_T; i += nthr) {   // horizontal pass
-      const int ly = i / WB_BLUR_T, ox = i - ly * WB_BLUR_T;
-      float acc = 0.f;
-      if (ADJ) { for (int t = 0; t < K; ++t) acc += wb_blur_adj_w(s_k, K, r, tx0 + ox, t, W) * s_in[ly][ox + t]; }
-      else { for (int t = 0; t < K; ++t) acc += s_k[t] * s_in[ly][ox + t]; }
-      s_h[ly][ox] = acc;
+    // Each thread produces 4 consecutive outputs of a pass from one sliding window (K + 3 shared-memory reads for 4 K
+    // multiply-adds).  The adjoint's folded weights are only needed by tiles within r of an image border.
+    const bool fold_x = ADJ && (tx0 <= r || tx0 + WB_BLUR_T - 1 >= W - 1 - r);
+    const bool fold_y = ADJ && (ty0 <= r || ty0 + WB_BLUR_T - 1 >= H - 1 - r);
+    for (int i = tid; i < IN * (WB_BLUR_T / 4); i += nthr) {   // horizontal pass
+      const int ly = i / (WB_BLUR_T / 4), ox = (i - ly * (WB_BLUR_T / 4)) * 4;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (fold_x) {
+        WB_UNROLL for (int j = 0; j < 4; ++j)
+          for (int t = 0; t < K; ++t) acc[j] += wb_blur_adj_w(s_k, K, r, tx0 + ox + j, t, W) * s_in[ly][ox + j + t];
+      } else {
+        for (int t = 0; t < K + 3; ++t) {
+          const float v = s_in[ly][ox + t];
+          WB_UNROLL for (int j = 0; j < 4; ++j) { const int tt = t - j; if (tt >= 0 && tt < K) acc[j] += s_k[tt] * v; }
+        }
+      }
+      WB_UNROLL for (int j = 0; j < 4; ++j) s_h[ly][ox + j] = acc[j];
     }
     __syncthreads();
-    for (int i = tid; i < WB_BLUR_T * WB_BLUR_T; i += nthr) {   // vertical pass
-      const int oy = i / WB_BLUR_T, ox = i - oy * WB_BLUR_T;
-      const int gy = ty0 + oy, gx = tx0 + ox;
-      if (gy >= H || gx >= W) continue;
-      float acc = 0.f;
-      if (ADJ) { for (int t = 0; t < K; ++t) acc += wb_blur_adj_w(s_k, K, r, gy, t, H) * s_h[oy + t][ox]; }
-      else { for (int t = 0; t < K; ++t) acc += s_k[t] * s_h[oy + t][ox]; }
-      out[(size_t)gy * W + gx] = acc;
+    for (int i = tid; i < (WB_BLUR_T / 4) * WB_BLUR_T; i += nthr) {   // vertical pass
+      const int oyq = i / WB_BLUR_T, ox = i - oyq * WB_BLUR_T, oy = oyq * 4;
+      const int gx = tx0 + ox;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (fold_y) {
+        WB_UNROLL for (int j = 0; j < 4; ++j)
+          if (ty0 + oy + j < H) for (int t = 0; t < K; ++t) acc[j] += wb_blur_adj_w(s_k, K, r, ty0 + oy + j, t, H) * s_h[oy + j + t][ox];
+      } else {
+        for (int t = 0; t < K + 3; ++t) {
+          const float v = s_h[oy + t][ox];
+          WB_UNROLL for (int j = 0; j < 4; ++j) { const int tt = t - j; if (tt >= 0 && tt < K) acc[j] += s_k[tt] * v; }
+        }
+      }
+      if (gx < W) { WB_UNROLL for (int j = 0; j < 4; ++j) if (ty0 + oy + j < H) out[(size_t)(ty0 + oy + j) * W + gx] = acc[j]; }
     }
   }
 }
