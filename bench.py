@@ -86,19 +86,49 @@ def kernel_bytes(cfg, B, Tc, Tp):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons, polled every 200 ms by ONE long-lived nvidia-smi process that is started
-    well before the timed region (its start-up takes driver locks and would otherwise stall the first timed launches);
-    summary() keeps the samples whose arrival time falls inside [mark_begin(), mark_end()]."""
+    """SM clock + throttle reasons sampled DURING the timed region: an in-process NVML poll every 50 ms on a daemon thread
+    (pynvml; two light driver queries per poll).  A polling `nvidia-smi -lms` child process, used before, re-queries the
+    whole device state on every poll and -- in the first process on a fresh box -- stalled kernel launches for 3 to 200 ms per
+    poll (measured: profiles/r2/r2_notes.md); it remains the fallback when pynvml is missing.
+    summary() keeps the samples taken inside [mark_begin(), mark_end()]."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
+        self.stop, self.max_mhz, self.source = False, None, None
+        if os.environ.get("WALDO_NO_SAMPLER"):   # experiments only
+            return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            threading.Thread(target=self._poll_nvml, daemon=True).start()
+            return
+        except Exception:
+            self.source = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.stop:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((time.time(), [str(mhz), str(self.max_mhz)] + ["Active" if mask & bit else "Not Active" for bit, _ in self.REASONS]))
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -106,7 +136,7 @@ class ClockSampler:
 
     def wait_ready(self, timeout=5.0):
         t = time.time()
-        while self.proc and not self.rows and time.time() - t < timeout:
+        while self.source and not self.rows and time.time() - t < timeout:
             time.sleep(0.05)
 
     def mark_begin(self):
@@ -116,6 +146,7 @@ class ClockSampler:
         self.t1 = time.time()
 
     def close(self):
+        self.stop = True
         if self.proc:
             self.proc.terminate()
             try:
@@ -135,7 +166,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def make_inputs(cfg, B, T, Tc, seed):
@@ -360,13 +391,25 @@ class Runner:
         torch.cuda.synchronize()
 
     def timed(self, fn, steps):
-        self.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        self.barrier()
+        import gc
+        gc.collect()
+        gc.disable()   # no collector pause inside the timed region (thousands of short-lived tensor wrappers per step)
+        try:
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            marks = []
+            for _ in range(steps):
+                fn()
+                if os.environ.get("WALDO_STEP_TIMES"):   # experiments only: per-step device times
+                    m = torch.cuda.Event(enable_timing=True); m.record(); marks.append(m)
+            e1.record()
+            self.barrier()
+            if marks:
+                ts = [e0.elapsed_time(m) for m in marks]
+                print("[step times]", " ".join(f"{b - a:.2f}" for a, b in zip([0.0] + ts[:-1], ts)), file=sys.stderr, flush=True)
+        finally:
+            gc.enable()
         return self.sharding.max_over_ranks([e0.elapsed_time(e1)], device=self.dev)[0] / steps
 
     def measure(self, steps, warmup, profile=True):
@@ -486,15 +529,24 @@ def main():
     B, T, Tc, Tp, backward = r.B, r.T, r.Tc, r.Tp, r.backward
     Hd, Wd = cfg.hd_shape
 
+    # The sampler's nvidia-smi process takes driver locks while it initialises (seconds on a fresh box: the first process to
+    # open the driver pays for it) and would stall kernel launches in whatever runs meanwhile: wait until it delivers samples,
+    # THEN warm up, then time.
     clocks = ClockSampler(local_rank)
-    for _ in range(max(args.warmup, 3)):
+    clocks.wait_ready(timeout=60.0)
+    for _ in range(max(args.warmup, 3) + 3):
         r.step(r.resident)
-    clocks.wait_ready()
-    # ---- device-resident timing, with the dominant kernels bracketed by events inside the timed region
+    torch.cuda.synchronize()
+    # ---- device-resident timing.  Two timed regions of K steps each, back to back: the plain one gives the headline (the calls
+    # a user makes: one C-ABI call per entry point), the instrumented one issues the same kernels stage by stage with a CUDA-event
+    # pair around each HD kernel (the roofline figures); both numbers are reported.
     clocks.mark_begin()
-    ms_step, launches, prof = r.measure(args.steps, 0)
+    ms_step, launches, _ = r.measure(args.steps, 0, profile=False)
+    ms_instr, prof = ms_step, {}
+    if r.graphed is None:
+        ms_instr, _, prof = r.measure(args.steps, 0)
     clocks.mark_end()
-    kernel_timing = "CUDA events around each kernel inside the timed region"
+    kernel_timing = "CUDA events around each kernel in a second timed region of the same K steps, right after the plain one (%.3f ms/step instrumented)" % ms_instr
     if r.graphed is not None:
         # a replayed graph cannot be bracketed kernel by kernel: time the same kernels in an extra eager pass
         with torch.no_grad():
@@ -617,7 +669,8 @@ def main():
                          "traffic": traffic.get(dom), "ms_per_launch": dms, "alg_bytes_per_launch": dbytes, "peak_source": peak_src,
                          "other": {k: {"ms_per_launch": v[0], "alg_bytes_per_launch": v[1],
                                        "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None} for k, v in kern.items() if k != dom},
-                         "stages_ms": {k: round(v, 4) for k, v in prof.items()}, "kernel_timing": kernel_timing},
+                         "stages_ms": {k: round(v, 4) for k, v in prof.items()}, "kernel_timing": kernel_timing,
+                         "ms_per_step_instrumented": ms_instr},
         }
         if e2e:
             line["e2e"] = e2e

@@ -219,11 +219,13 @@ def is_deterministic() -> bool:
     return _DETERMINISTIC or torch.are_deterministic_algorithms_enabled()
 
 
-def _scatter_targets(refs, det):
+def _scatter_targets(refs, det, fill=True):
     """Zero-filled gradient / scratch buffers shaped like `refs` (None stays None).  In deterministic mode they are views
-    of ONE float arena (16-byte aligned each) shadowed by an int64 arena: returns (targets, arena, shadow)."""
+    of ONE float arena (16-byte aligned each) shadowed by an int64 arena: returns (targets, arena, shadow).  fill=False: the
+    caller zero-fills (the targets, or the two arenas in deterministic mode)."""
+    new = torch.zeros if fill else torch.empty
     if not det:
-        return [torch.zeros_like(r) if r is not None else None for r in refs], None, None
+        return [(torch.zeros_like(r) if fill else torch.empty_like(r)) if r is not None else None for r in refs], None, None
     live = [r for r in refs if r is not None]
     if not live:   # nothing to accumulate: the call degenerates to the default path
         return [None] * len(refs), None, None
@@ -232,8 +234,8 @@ def _scatter_targets(refs, det):
         offs.append(n)
         n += (r.numel() + 3) // 4 * 4
     dev = live[0].device
-    arena = torch.zeros(max(n, 4), device=dev, dtype=torch.float32)
-    shadow = torch.zeros(max(n, 4), device=dev, dtype=torch.int64)
+    arena = new(max(n, 4), device=dev, dtype=torch.float32)
+    shadow = new(max(n, 4), device=dev, dtype=torch.int64)
     it = iter(offs)
     out = []
     for r in refs:
@@ -246,10 +248,9 @@ def _scatter_targets(refs, det):
 
 
 # The scatter targets of decode_bwd must be zero-filled (1.9 GB of `d input` + 1.1 GB of context-opacity gradient at the
-# benchmark shape: 0.5 ms of pure HBM writes).  When gradients will be asked for, the fills are issued during the FORWARD on a
-# side stream: they overlap with the forward HD kernels, which are bound by instruction issue and leave most of the HBM
-# bandwidth idle, instead of sitting on the critical path at the start of the backward.  PREFILL = False restores the fills
-# at the start of backward.
+# benchmark shape: 0.5 ms of pure HBM writes).  When gradients will be asked for, the fills are issued at the end of the
+# FORWARD on a side stream (see _Decode.forward), so that they overlap with the caller's work between forward and backward
+# instead of sitting at the start of the backward.  PREFILL = False restores the fills at the start of backward.
 PREFILL = True
 _side_streams = {}
 
@@ -276,13 +277,13 @@ def _scatter_plan(need, g, cls_present):
                 filt=filt, geom=geom, chain=chain)
 
 
-def _alloc_scatter(plan, refs, det):
+def _alloc_scatter(plan, refs, det, fill=True):
     inp_c, alpha, f_lo, a_lo, tgo_c, sgo_c, tgb_c, sgb_c, oa_c, ba_c = refs
     on = lambda ref, cond: ref if cond else None
     p = plan
     return _scatter_targets(
         [on(inp_c, p["n_inp"]), on(alpha, p["chain"]), on(f_lo, p["geom"]), on(a_lo, p["chain"]), on(tgo_c, p["geom"]), on(sgo_c, p["geom"]),
-         on(tgb_c, p["geom"]), on(sgb_c, p["geom"]), on(oa_c, p["n_oa"]), on(ba_c, p["n_ba"])], det)
+         on(tgb_c, p["geom"]), on(sgb_c, p["geom"]), on(oa_c, p["n_oa"]), on(ba_c, p["n_ba"])], det, fill)
 
 
 # When bench.py sets PROFILE = {"decode_fwd": [], "decode_bwd": []}, the two entry points are issued stage by stage
@@ -413,27 +414,39 @@ class _Decode(torch.autograd.Function):
         lyt_lo = torch.empty(B, g.Tw, Nl, spec.H, spec.W, **f32) if (spec.use_filter and any(ctx.needs_input_grad)) else None
         tensors = (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
                    prof_sum, prof_p, f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score, lyt_lo)
+        # The fills are issued right after the forward kernels, on a side stream (`side.wait_stream(main)`: after the forward),
+        # and the backward waits for them: they overlap with whatever the caller runs between this forward and its backward
+        # (WIF's UNet, the losses).  Overlapping them with the forward kernels themselves was measured on the B200 and gains
+        # nothing: fill CTAs and forward CTAs compete for the same SM slots (forward + 0.45 ms, exactly the fills' own time;
+        # profiles/r2/r2_notes.md).  The buffers come from the MAIN stream's pool (allocation and release follow the main
+        # stream like every other tensor of the step); only the fill kernels run on the side stream.
+        ctx.prefill = None
+        hook = None
+        if PREFILL and inp_c.is_cuda and any(ctx.needs_input_grad[5:]):
+            plan = _scatter_plan(ctx.needs_input_grad[5:], g, cls_c is not None)
+            det = is_deterministic()
+
+            def hook():
+                main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                bufs = _alloc_scatter(plan, (inp_c, alpha, f_lo, a_lo, tgo_c, sgo_c, tgb_c, sgb_c, oa_c, ba_c), det, fill=False)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for t in ([bufs[1], bufs[2]] if det else bufs[0]):
+                        if t is not None:
+                            t.zero_()
+                            t.record_stream(side)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                ctx.prefill = (plan, det, bufs, ev)
         a = _fwd_struct(g, prof_ctas, tensors)
         _staged(lib.waldo_decode_fwd, a, L.stream_of(inp_c), "decode_fwd", dev=dev)
+        if hook is not None:
+            hook()
         # saved through save_for_backward (NOT as ctx attributes): four of them are outputs of this very Function, and an
         # attribute would tie them into a reference cycle that only the cyclic GC frees (tens of GB per step)
         ctx.save_for_backward(*[t for t in tensors if t is not None])
         ctx.present = [t is not None for t in tensors]
         ctx.geom, ctx.prof_ctas = g, prof_ctas
-        ctx.prefill = None
-        if PREFILL and inp_c.is_cuda and any(ctx.needs_input_grad[5:]):
-            plan = _scatter_plan(ctx.needs_input_grad[5:], g, cls_c is not None)
-            det = is_deterministic()
-            main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-            side.wait_stream(main)     # (allocator safety: blocks freed on `main` may be re-used here only after `main` got there)
-            with torch.cuda.stream(side):
-                bufs = _alloc_scatter(plan, (inp_c, alpha, f_lo, a_lo, tgo_c, sgo_c, tgb_c, sgb_c, oa_c, ba_c), det)
-                ev = torch.cuda.Event()
-                ev.record(side)
-            for t in list(bufs[0]) + [bufs[1], bufs[2]]:
-                if t is not None:
-                    t.record_stream(main)
-            ctx.prefill = (plan, det, bufs, ev)
         ctx.shapes = dict(obj_alpha=obj_alpha.shape, bg_alpha=bg_alpha.shape)
         return out_full[:, :, :Cc], out_full[:, :, Cc:], raw, flow, alpha
 
