@@ -478,6 +478,43 @@ def loss_epilogues(dev, steps=20):
             "blur23_fwd_bwd": {"ms": ms_b, "alg_bytes": bb, "frac": bb / (ms_b * 1e-3) / 1e9 / PEAK["gbs"]}}
 
 
+def wif_to_emb_leg(dev, steps=10):
+    """f-1 first layer at the WIF shape of the default workload: raw_output (B=8, Tc=4, Tp=1, 40 channels, 512x1024) -> 16 planes
+    per image; HBM streaming: (40 + 16) floats per pixel and image."""
+    import waldo_b200 as wb
+    B, Tc, Tp, Cin, Cout, H, W = 8, 4, 1, 40, 16, 512, 1024
+    gen = torch.Generator(device=dev).manual_seed(4)
+    raw = torch.randn(B, Tc, Tp, Cin, H, W, device=dev, generator=gen)
+    wgt = torch.randn(Cout, Cin, 3, 3, device=dev, generator=gen) * 0.05
+    with torch.no_grad():
+        for _ in range(3):
+            wb.wif_to_emb(raw, wgt)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            wb.wif_to_emb(raw, wgt)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        # the same layer as the reference runs it: permute + reshape copy, then cuDNN (torch default: TF32 allowed)
+        x = raw.permute(0, 2, 1, 3, 4, 5).reshape(B * Tp * Tc, Cin, H, W)
+        for _ in range(3):
+            torch.nn.functional.conv2d(raw.permute(0, 2, 1, 3, 4, 5).reshape(B * Tp * Tc, Cin, H, W), wgt, padding=1)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            torch.nn.functional.conv2d(raw.permute(0, 2, 1, 3, 4, 5).reshape(B * Tp * Tc, Cin, H, W), wgt, padding=1)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_ref = e0.elapsed_time(e1) / steps
+        del x
+    nbytes = B * Tc * Tp * H * W * 4 * (Cin + Cout)
+    return {"shape": f"raw_output (B={B}, Tc={Tc}, Tp={Tp}, {Cin}, {H}, {W}) -> ({B * Tc * Tp}, {Cout}, {H}, {W})", "ms": ms, "alg_bytes": nbytes,
+            "frac": nbytes / (ms * 1e-3) / 1e9 / PEAK["gbs"], "tflops": 2 * 9 * Cin * Cout * B * Tc * Tp * H * W / (ms * 1e-3) / 1e12,
+            "stock_torch_ms": ms_ref, "stock_torch": "permute + reshape copy + F.conv2d (cuDNN, allow_tf32 default)"}
+
+
 PEAK = {"gbs": 6650.0, "src": "B200_PROFILING.md fallback"}
 
 
@@ -625,6 +662,11 @@ def main():
                 others["loss_epilogues"] = loss_epilogues(dev)
             except Exception as e:
                 others["loss_epilogues"] = {"error": str(e)[:200]}
+            try:
+                torch.cuda.empty_cache()
+                others["wif_to_emb"] = wif_to_emb_leg(dev)
+            except Exception as e:
+                others["wif_to_emb"] = {"error": str(e)[:200]}
 
     clocks.close()
     if rank == 0:

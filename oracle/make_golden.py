@@ -139,12 +139,42 @@ def blur_fixture():
     print(f"blur: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def pack_fixture():
+    """f-3: what the reference's dataset class makes of an 8-bit frame and an 8-bit label map -- `BaseDataset.load_rgb_path` /
+    `load_layout_path` with the transforms `__getitem__` builds (data/base_dataset.py:167-183, :213-220, :329-372; no
+    augmentation, native size) -- on seeded PNG files; `input` = cat([rgb, layout]) as models/synthesizer.py:444 does.
+    Stored: the raw bytes and the reference's fp32 result, for two frame sizes (one not a multiple of 4 pixels)."""
+    import importlib
+    import tempfile
+    import PIL.Image
+    ref_loader.load()
+    bd = importlib.import_module("data.base_dataset")
+    rng = np.random.default_rng(5)
+    res, tmp = {}, tempfile.mkdtemp(prefix="waldo_pack_")
+    for i, (H, W, Nl) in enumerate(((12, 20, 20), (7, 9, 19))):
+        rgb = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        lab = rng.integers(0, Nl, (H, W), dtype=np.uint8)
+        PIL.Image.fromarray(rgb).save(os.path.join(tmp, "f.png"))
+        PIL.Image.fromarray(lab, mode="L").save(os.path.join(tmp, "l.png"))
+        fake = types.SimpleNamespace(opt=types.SimpleNamespace(remap_lyt=[], num_lyt=Nl))
+        t_rgb = bd.get_transform(H, aspect_ratio=W / H, is_PIL=True)
+        t_lyt = bd.get_transform(H, aspect_ratio=W / H, is_PIL=False, normalize=False)
+        img = bd.BaseDataset.load_rgb_path(fake, os.path.join(tmp, "f.png"), t_rgb)
+        lyt = bd.BaseDataset.load_layout_path(fake, os.path.join(tmp, "l.png"), t_lyt)
+        res.update({f"rgb{i}": rgb.transpose(2, 0, 1).copy(), f"lab{i}": lab, f"input{i}": torch.cat([img, lyt], dim=0).numpy()})
+    path = os.path.join(OUT, "pack.npz")
+    np.savez_compressed(path, **res)
+    print(f"pack: {os.path.getsize(path) / 1e3:.1f} kB")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     only = sys.argv[1:]
     if not only or "blur" in only:
         blur_fixture()
+    if not only or "pack" in only:
+        pack_fixture()
     for name, (kw, B, T, Tc, smooth) in CASES.items():
         if only and name not in only:
             continue

@@ -537,6 +537,17 @@ def check_pack_input(dev, B=2, T=3, Hd=12, Wd=20, num_lyt=20, seed=5):
         # bf16 storage: the same values rounded once to bf16 (round to nearest even, as Tensor.to(torch.bfloat16))
         got = wb.pack_input(rgb8.to(dev), lab.to(dev), num_lyt, dtype=torch.bfloat16).cpu()
         assert got.dtype == torch.bfloat16 and torch.equal(got, want.to(torch.bfloat16)), "pack_input(bf16) differs"
+    # pinned by the reference's own dataset class: tests/golden/pack.npz holds what BaseDataset.load_rgb_path / load_layout_path
+    # (data/base_dataset.py:167-183 with the transforms of :213-220) made of seeded PNG files (oracle/make_golden.pack_fixture)
+    z = np.load(os.path.join(GOLDEN, "pack.npz"))
+    i = 0
+    while f"rgb{i}" in z.files:
+        rgb8, lab, want = torch.from_numpy(z[f"rgb{i}"])[None, None], torch.from_numpy(z[f"lab{i}"])[None, None], torch.from_numpy(z[f"input{i}"])
+        got = wb.pack_input(rgb8.to(dev), lab.to(dev), want.shape[0] - 3).cpu()[0, 0]
+        assert torch.equal(got, want), f"pack_input differs from the reference's dataset class (fixture {i})"
+        assert torch.equal(reference_pack(rgb8, lab, want.shape[0] - 3)[0, 0], want)   # ... and so does the restatement above
+        i += 1
+    assert i >= 2
     # every 8-bit value maps exactly as torchvision's ToTensor + Normalize
     ramp = torch.arange(256, dtype=torch.uint8).view(1, 1, 1, 16, 16).expand(1, 1, 3, 16, 16).contiguous()
     lab = torch.zeros(1, 1, 16, 16, dtype=torch.uint8)
@@ -591,6 +602,47 @@ def check_layer_entropy(dev, seed=11):
         a2 = a.clone().requires_grad_(True)
         (wo.layer_entropy(a2)[1] * wf).sum().backward()
         grad_close(ad2.grad, a2.grad, a2.grad.double(), f"fg_mask[{i}] d alpha")
+
+
+# ------------------------------------------------------------------------------------------------ f-1 first UNet layer
+TOL_TF32 = 3e-3   # conv3x3 with TF32 products (10-bit mantissa operands: activations truncated by the tensor core, weights
+                  # rounded to nearest; fp32 accumulation): max|k - exact| <= 3e-3 * max|exact|
+
+
+def _tf32(x, nearest=True):
+    """TF32 on the host, 10 mantissa bits: cvt.rna.tf32.f32 (round to nearest, ties away; the staged weights) or what the tensor
+    core makes of a raw fp32 pattern (low 13 bits ignored: toward zero; the activations)."""
+    u = x.contiguous().view(torch.int32)
+    return (((u + 0x1000) if nearest else u) & ~0x1fff).view(torch.float32)
+
+
+def check_conv3x3(dev, seed=21):
+    """f-1 first layer, `UNet.to_emb` (conv.py:9-11, :54) as WIF.forward feeds it (wif.py:33-38): against F.conv2d in fp64 on
+    TF32-rounded operands (the kernel's exact arithmetic up to fp32 accumulation order: 2e-5) and on the original operands (the
+    stated TF32 tolerance); ragged sizes, the WIF image permute, Cin that is not a multiple of 8, every supported Cout."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(seed)
+    # (W % 4 == 0 takes the 16-byte staging; Cin 40 / 41 with Cout 16 the compile-time-unrolled WIF instantiations)
+    for (B, Tc, Tp, Cin, H, W, Cout) in ((1, 2, 2, 40, 19, 45, 16), (2, 1, 3, 41, 8, 32, 8), (1, 2, 1, 24, 33, 70, 32), (1, 1, 1, 3, 9, 7, 24),
+                                         (1, 2, 1, 40, 17, 64, 16), (1, 1, 2, 41, 9, 36, 16), (1, 1, 1, 16, 8, 4, 32)):
+        raw = torch.randn(B, Tc, Tp, Cin, H, W, generator=gen)
+        wgt = torch.randn(Cout, Cin, 3, 3, generator=gen) / (3 * Cin ** 0.5)
+        want_order = raw.permute(0, 2, 1, 3, 4, 5).reshape(B * Tp * Tc, Cin, H, W)     # wif.py:33-38
+        exact = F.conv2d(want_order.double(), wgt.double(), padding=1)
+        exact_tf32 = F.conv2d(_tf32(want_order, nearest=False).double(), _tf32(wgt).double(), padding=1)
+        got = wb.wif_to_emb(raw.to(dev), wgt.to(dev)).cpu().double()
+        assert tuple(got.shape) == tuple(exact.shape)
+        scale = float(exact.abs().max())
+        assert float((got - exact_tf32).abs().max()) <= 2e-5 * scale, f"conv3x3 vs TF32-operand convolution: {float((got - exact_tf32).abs().max()) / scale:.3e}"
+        assert float((got - exact).abs().max()) <= TOL_TF32 * scale, f"conv3x3 vs exact convolution: {float((got - exact).abs().max()) / scale:.3e}"
+        plain = wb.conv3x3(want_order.contiguous().to(dev), wgt.to(dev)).cpu().double()
+        assert torch.equal(plain, got), "conv3x3: the permuted addressing and the plain one disagree"
+    try:
+        wb.conv3x3(torch.zeros(1, 3, 8, 8, device=dev).requires_grad_(True), torch.zeros(8, 3, 3, 3, device=dev))
+    except NotImplementedError:
+        pass
+    else:
+        raise AssertionError("conv3x3 is forward-only and must say so")
 
 
 # ------------------------------------------------------------------------------------------------ f-4 output side

@@ -69,6 +69,10 @@ def test_kats():
     parity.check_kats(DEV)
 
 
+def test_conv3x3():
+    parity.check_conv3x3(DEV)
+
+
 def test_blur():
     parity.check_blur(DEV)
 

@@ -94,6 +94,10 @@ def test_small_chain_deterministic_gradients(dev):
     parity.check_chain_deterministic(dev, cfg, B, T, Tc, seed=5)
 
 
+def test_conv3x3(dev):
+    parity.check_conv3x3(dev)
+
+
 def test_blur(dev):
     parity.check_blur(dev)
 

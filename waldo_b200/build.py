@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwaldo_b200.so")
 SOURCES = ["waldo_abi.cu"]
-HEADERS = ["wb_common.cuh", "wb_geom.cuh", "wb_prep.cuh", "wb_composite.cuh", "wb_composite_bwd.cuh", "wb_wif.cuh", "wb_pack.cuh", "wb_field.cuh", "wb_loss.cuh",
+HEADERS = ["wb_common.cuh", "wb_geom.cuh", "wb_prep.cuh", "wb_composite.cuh", "wb_composite_bwd.cuh", "wb_wif.cuh", "wb_pack.cuh", "wb_field.cuh", "wb_loss.cuh", "wb_conv.cuh",
            os.path.join("..", "..", "include", "waldo_b200.h")]
 
 

@@ -17,6 +17,7 @@
 #include "wb_pack.cuh"
 #include "wb_field.cuh"
 #include "wb_loss.cuh"
+#include "wb_conv.cuh"
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_wb_launches{0};
@@ -377,6 +378,35 @@ int waldo_layer_entropy_bwd(const waldo_layer_entropy_bwd_t* a, waldo_stream_t s
   WB_REQUIRE(a->f.alpha && a->d_alpha, "layer_entropy_bwd: null pointer");
   if (a->f.n == 0) return 0;
   WB_LAUNCH(k_layer_entropy_bwd, dim3(wb_blocks(a->f.HW, 256, 1024), a->f.n), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ first UNet layer
+int waldo_conv3x3_fwd(const waldo_conv3x3_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->n >= 0 && a->H > 0 && a->W > 0, "conv3x3_fwd: bad sizes");
+  WB_REQUIRE(a->Cin >= 1 && a->Cin <= WB_CV_MAX_CIN, "conv3x3_fwd: Cin=%d unsupported (1..%d)", a->Cin, WB_CV_MAX_CIN);
+  WB_REQUIRE(a->Cout >= 8 && a->Cout <= WB_CV_MAX_COUT && a->Cout % 8 == 0, "conv3x3_fwd: Cout=%d must be a multiple of 8, <= %d", a->Cout, WB_CV_MAX_COUT);
+  WB_REQUIRE((a->Tc > 0) == (a->Tp > 0), "conv3x3_fwd: Tc and Tp must both be set or both be 0");
+  if (a->Tc > 0) WB_REQUIRE(a->n % (a->Tc * a->Tp) == 0, "conv3x3_fwd: n must be a multiple of Tc*Tp");
+  WB_REQUIRE(a->in && a->weight && a->out && a->in != a->out, "conv3x3_fwd: null pointer");
+  if (a->n == 0) return 0;
+  const int Cp = (a->Cin + 7) & ~7, WP = a->Cout <= 24 ? 24 : 40;
+  // 16-byte staging needs whole 4-pixel chunks inside / outside the image and 16-byte aligned rows
+  const bool vec = a->W % 4 == 0 && ((uintptr_t)a->in & 15) == 0;
+  const size_t smem = ((size_t)Cp * WB_CV_ROWS * (vec ? WB_CV_PITCH_V : WB_CV_PITCH_S) + (size_t)9 * Cp * WP) * sizeof(float);
+  const long long tiles = (long long)a->n * ((a->W + WB_CV_TW - 1) / WB_CV_TW) * ((a->H + WB_CV_TH - 1) / WB_CV_TH);
+  const dim3 grid(wb_blocks(tiles, 1, 2 * 148));   // persistent: 2 CTAs per SM
+#ifdef WB_HOST_EMU
+#define WB_CV_GO(K) WB_LAUNCH(K, grid, dim3(256), smem, st, *a)
+#else
+#define WB_CV_GO(K) do { cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); WB_LAUNCH(K, grid, dim3(256), smem, st, *a); } while (0)
+#endif
+  if (vec && Cp == 40 && a->Cout == 16) WB_CV_GO((k_conv3x3_fwd<40, 2, true>));        // WIF's to_emb: 3 + 20 + 17 channels -> 16
+  else if (vec && Cp == 48 && a->Cout == 16) WB_CV_GO((k_conv3x3_fwd<48, 2, true>));   // ... with the disocc channel (41 -> 48)
+  else if (vec) WB_CV_GO((k_conv3x3_fwd<0, 0, true>));
+  else WB_CV_GO((k_conv3x3_fwd<0, 0, false>));
+#undef WB_CV_GO
   WB_LAUNCHED();
   return 0;
 }

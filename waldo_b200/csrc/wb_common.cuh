@@ -273,6 +273,18 @@ WB_DEV void wb_cp4(float* smem_dst, const float* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
 }
+// same with zero fill: `valid` false copies nothing and writes 0.f (src-size operand 0); gsrc must still be a mapped address
+WB_DEV void wb_cp4z(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gsrc), "r"(n) : "memory");
+}
+// 16-byte form (LDGSTS.128, L2 only): both addresses 16-byte aligned
+WB_DEV void wb_cp16z(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(n) : "memory");
+}
 WB_DEV void wb_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> WB_DEV void wb_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 

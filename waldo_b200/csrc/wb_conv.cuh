@@ -1,0 +1,183 @@
+// f-1, first layer: the consumer of the path's `raw_output`.
+// WIF's UNet starts with  to_emb = conv3x3(Cin = 3 + num_lyt + num_obj + 1 [+ disocc] -> embed_dim / 2^(depth-1) = 16), stride 1, padding 1,
+// no bias (models/modules/conv.py:9-11, :36, :54), applied to raw_output permuted to (B, Tp, Tc, C, H, W) and flattened to
+// B*Tp*Tc images (models/nets/wif.py:33-38).  At 512 x 1024 this layer reads the whole of raw_output (2.7 GB per step) and
+// writes 16 planes per image: 3.75 GB for 193 GFLOP, i.e. bound by HBM, not by the tensor pipes -- so it is an implicit GEMM
+// on warp-level tensor-core instructions (TF32 mma.sync m16n8k8, fp32 accumulate; TF32 is also what the reference's own
+// cuDNN convolution uses on this GPU with torch's default allow_tf32), not a tcgen05 pipeline: M = pixels, N = Cout = 16,
+// K = 9 * Cin.  The (b, tc, tp) -> (b, tp, tc) permute of wif.py:33 is folded into the addressing (no 2.7 GB copy).
+//
+// CTA = 256 threads = 8 warps, output tile 32 x 8 pixels; warp w owns tile row w = two 16-pixel M tiles x Cout / 8 N tiles.
+// Shared memory: the input tile + halo, copied as is by cp.async (the tensor core ignores the low 13 mantissa bits of an fp32
+// pattern: round toward zero; the weights are rounded to nearest once, when staged), [Cin padded to 8][10 rows][36 floats] (channel stride 360 = 8 mod 32:
+// the four A-fragment loads of a warp each hit 32 different banks), and all weights [tap][cin][Cout pitch 24 | 40] (the two
+// B-fragment loads likewise).  Persistent CTAs: the weights are staged once per CTA.
+#pragma once
+#include "wb_common.cuh"
+#include "../../include/waldo_b200.h"
+
+#define WB_CV_TW 32
+#define WB_CV_TH 8
+#define WB_CV_ROWS (WB_CV_TH + 2)
+// Two staging forms.  VEC (W a multiple of 4, 16-byte aligned planes): the tile's columns [tx0 - 4, tx0 + 36) as ten 16-byte
+// cp.async per (channel, row); row pitch 44 floats, channel stride 440 = 24 (mod 32).  Otherwise columns [tx0 - 1, tx0 + 33) with
+// 4-byte cp.async; pitch 36, channel stride 360 = 8 (mod 32).  Either way the four A-fragment loads of a warp hit 32 banks.
+#define WB_CV_PITCH_V 44
+#define WB_CV_PITCH_S 36
+#define WB_CV_MAX_CIN 48
+#define WB_CV_MAX_COUT 32
+
+WB_DEV float wb_tf32(float v) {   // round to nearest, ties away from zero, 10-bit mantissa (cvt.rna.tf32.f32)
+#ifdef WB_HOST_EMU
+  union { float f; unsigned u; } c;
+  c.f = v;
+  if ((c.u & 0x7f800000u) == 0x7f800000u) return v;
+  c.u = (c.u + 0x1000u) & 0xffffe000u;
+  return c.f;
+#else
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+#endif
+}
+
+// what the tensor core makes of an fp32 bit pattern handed to it as TF32: the low 13 mantissa bits are ignored
+WB_DEV float wb_tf32_rz(float v) {
+  union { float f; unsigned u; } c;
+  c.f = v;
+  c.u &= 0xffffe000u;
+  return c.f;
+}
+
+WB_DEV int wb_cv_wpitch(int Cout) { return Cout <= 24 ? 24 : 40; }
+
+// image of `in` that output image i reads: identity, or (b, tp, tc) <- (b, tc, tp)
+WB_DEV int wb_cv_src_image(const waldo_conv3x3_t& p, int i) {
+  if (p.Tc <= 0) return i;
+  const int tc = i % p.Tc, tp = (i / p.Tc) % p.Tp, b = i / (p.Tc * p.Tp);
+  return (b * p.Tc + tc) * p.Tp + tp;
+}
+
+// CPT: Cin padded to a multiple of 8, compile-time (0: run-time); NTT: Cout / 8, compile-time (0: run-time)
+template <int CPT, int NTT, bool VEC>
+__global__ void __launch_bounds__(256, 2) k_conv3x3_fwd(waldo_conv3x3_t p) {
+  WB_DYN_SMEM(smem);
+  constexpr int WB_CV_PITCH = VEC ? WB_CV_PITCH_V : WB_CV_PITCH_S, WB_CV_CH = WB_CV_ROWS * WB_CV_PITCH;
+  constexpr int COL0 = VEC ? 3 : 0;            // staged column of pixel x under tap dx: x + dx + COL0
+  const int Cin = p.Cin, Cout = p.Cout, H = p.H, W = p.W;
+  const int Cp = CPT > 0 ? CPT : ((Cin + 7) & ~7), WP = wb_cv_wpitch(Cout), NT = NTT > 0 ? NTT : Cout / 8;
+  float* s_in = smem;                          // [Cp][10][36]
+  float* s_w = smem + Cp * WB_CV_CH;           // [9][Cp][WP]
+  const int tid = wb_tid(), nthr = wb_nthr();
+  for (int i = tid; i < 9 * Cp * WP; i += nthr) {
+    const int n = i % WP, ch = (i / WP) % Cp, tap = i / (WP * Cp);
+    s_w[i] = (n < Cout && ch < Cin) ? wb_tf32(__ldg(p.weight + ((size_t)n * Cin + ch) * 9 + tap)) : 0.f;
+  }
+  const int tiles_x = (W + WB_CV_TW - 1) / WB_CV_TW, tiles_y = (H + WB_CV_TH - 1) / WB_CV_TH;
+  const long long ntiles = (long long)p.n * tiles_x * tiles_y;
+  const size_t HW = (size_t)H * W;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int img = (int)(tile / (tiles_x * tiles_y)), tt = (int)(tile - (long long)img * tiles_x * tiles_y);
+    const int ty0 = (tt / tiles_x) * WB_CV_TH, tx0 = (tt % tiles_x) * WB_CV_TW;
+    const float* in = p.in + (size_t)wb_cv_src_image(p, img) * Cin * HW;
+    float* out = p.out + (size_t)img * Cout * HW;
+    __syncthreads();   // weights staged / the previous tile's MMAs done
+    if (VEC) {
+      // staging: 16-byte chunks, 10 per (channel, row); a chunk is wholly inside or wholly outside the image (W % 4 == 0)
+      for (int id = tid; id < Cp * WB_CV_ROWS * 10; id += nthr) {
+        const int ch = id / (WB_CV_ROWS * 10), rem = id - ch * (WB_CV_ROWS * 10), r = rem / 10, j4 = rem - r * 10;
+        const int gy = ty0 + r - 1, gx = tx0 - 4 + 4 * j4;
+        const bool ok = ch < Cin && gy >= 0 && gy < H && gx >= 0 && gx < W;
+        float* dst = s_in + ch * WB_CV_CH + r * WB_CV_PITCH + 4 * j4;
+#ifdef WB_HOST_EMU
+        for (int e = 0; e < 4; ++e) dst[e] = ok ? wb_tf32_rz(in[(size_t)ch * HW + (size_t)gy * W + gx + e]) : 0.f;
+#else
+        wb_cp16z(dst, ok ? in + (size_t)ch * HW + (size_t)gy * W + gx : in, ok);
+#endif
+      }
+    } else {
+    // staging: one (channel, row) of 34 floats per warp and trip (lanes = columns; lanes 0, 1 also take columns 32, 33)
+    {
+      const int ws = nthr < 32 ? nthr : 32;   // (the host emulation runs one thread per CTA)
+      const int nw = (nthr + ws - 1) / ws, wi = tid / ws, ln = tid % ws;
+      for (int pr = wi; pr < Cp * WB_CV_ROWS; pr += nw) {
+        const int ch = pr / WB_CV_ROWS, r = pr - ch * WB_CV_ROWS;
+        const int gy = ty0 + r - 1;
+        const bool rok = ch < Cin && gy >= 0 && gy < H;
+        const float* src = in + (size_t)ch * HW + (size_t)(rok ? gy : 0) * W;
+        float* dst = s_in + ch * WB_CV_CH + r * WB_CV_PITCH;
+        for (int c = ln; c < WB_CV_TW + 2; c += ws) {
+          const int gx = tx0 + c - 1;
+          const bool ok = rok && gx >= 0 && gx < W;
+#ifdef WB_HOST_EMU
+          dst[c] = ok ? wb_tf32_rz(src[gx]) : 0.f;
+#else
+          wb_cp4z(dst + c, ok ? src + gx : in, ok);   // LDGSTS: no register staging, every copy of the tile in flight at once
+#endif
+        }
+      }
+    }
+    }
+#ifndef WB_HOST_EMU
+    wb_cp_commit();
+    wb_cp_wait<0>();
+#endif
+    __syncthreads();
+#ifdef WB_HOST_EMU
+    // one host thread per CTA: the same sums (TF32-rounded operands, fp32 accumulation), pixel by pixel
+    for (int y = 0; y < WB_CV_TH; ++y)
+      for (int x = 0; x < WB_CV_TW; ++x) {
+        if (ty0 + y >= H || tx0 + x >= W) continue;
+        for (int n = 0; n < Cout; ++n) {
+          float acc = 0.f;
+          for (int tap = 0; tap < 9; ++tap)
+            for (int ch = 0; ch < Cp; ++ch)
+              acc += s_in[ch * WB_CV_CH + (y + tap / 3) * WB_CV_PITCH + x + tap % 3 + COL0] * s_w[(tap * Cp + ch) * WP + n];
+          out[(size_t)n * HW + (size_t)(ty0 + y) * W + tx0 + x] = acc;
+        }
+      }
+#else
+    const int lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    float acc[2][WB_CV_MAX_COUT / 8][4];
+    WB_UNROLL for (int mt = 0; mt < 2; ++mt)
+      WB_UNROLL for (int nt = 0; nt < WB_CV_MAX_COUT / 8; ++nt)
+        WB_UNROLL for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap - dy * 3;
+      const float* arow = s_in + tig * WB_CV_CH + (w + dy) * WB_CV_PITCH + dx + gid + COL0;
+      const float* brow = s_w + (tap * Cp + tig) * WP + gid;
+      WB_PRAGMA(unroll (CPT > 0 ? CPT / 8 : 1))
+      for (int c0 = 0; c0 < Cp; c0 += 8) {
+        unsigned a[2][4];
+        WB_UNROLL for (int mt = 0; mt < 2; ++mt) {
+          const float* q = arow + c0 * WB_CV_CH + mt * 16;
+          a[mt][0] = __float_as_uint(q[0]); a[mt][1] = __float_as_uint(q[8]);
+          a[mt][2] = __float_as_uint(q[4 * WB_CV_CH]); a[mt][3] = __float_as_uint(q[4 * WB_CV_CH + 8]);
+        }
+        WB_UNROLL for (int nt = 0; nt < WB_CV_MAX_COUT / 8; ++nt) {
+          if (nt < NT) {
+            const unsigned b0 = __float_as_uint(brow[c0 * WP + nt * 8]), b1 = __float_as_uint(brow[(c0 + 4) * WP + nt * 8]);
+            WB_UNROLL for (int mt = 0; mt < 2; ++mt)
+              asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                           : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+                           : "r"(a[mt][0]), "r"(a[mt][1]), "r"(a[mt][2]), "r"(a[mt][3]), "r"(b0), "r"(b1));
+          }
+        }
+      }
+    }
+    const int y = ty0 + w;
+    if (y < H) {
+      WB_UNROLL for (int mt = 0; mt < 2; ++mt)
+        WB_UNROLL for (int nt = 0; nt < WB_CV_MAX_COUT / 8; ++nt) {
+          if (nt < NT) {
+            const int x0 = tx0 + mt * 16 + gid, n0 = nt * 8 + 2 * tig;
+            float* o = out + (size_t)n0 * HW + (size_t)y * W;
+            if (x0 < W) { o[x0] = acc[mt][nt][0]; o[HW + x0] = acc[mt][nt][1]; }
+            if (x0 + 8 < W) { o[x0 + 8] = acc[mt][nt][2]; o[HW + x0 + 8] = acc[mt][nt][3]; }
+          }
+        }
+    }
+#endif
+  }
+}

@@ -679,6 +679,35 @@ def layer_entropy(alpha):
     return _LayerEntropy.apply(alpha)
 
 
+# ===================================================================================== f-1 first UNet layer
+def conv3x3(x, weight, wif_permute=False):
+    """UNet.to_emb (models/modules/conv.py:9-11, :54): conv3x3(stride 1, padding 1, no bias) with TF32 tensor-core products and
+    fp32 accumulation.  x (n, Cin, H, W) -> (n, Cout, H, W); with wif_permute, x is raw_output (B, Tc, Tp, Cin, H, W) as
+    decode_output returns it and the result is (B*Tp*Tc, Cout, H, W) in the image order of WIF.forward (wif.py:33-38), without the
+    permuted copy.  Forward / inference only."""
+    _no_grad_path(x, weight)
+    lib = L.load()
+    xc, wc = _c(x.detach()), _c(weight.detach())
+    if wc.dim() != 4 or wc.shape[2:] != (3, 3):
+        raise RuntimeError(f"waldo_b200.conv3x3: weight must be (Cout, Cin, 3, 3), got {tuple(wc.shape)}")
+    if wif_permute:
+        if xc.dim() != 6:
+            raise RuntimeError(f"waldo_b200.conv3x3: wif_permute expects raw_output (B, Tc, Tp, C, H, W), got {tuple(xc.shape)}")
+        B, Tc, Tp, Cin, H, W = xc.shape
+        n = B * Tc * Tp
+    else:
+        if xc.dim() != 4:
+            raise RuntimeError(f"waldo_b200.conv3x3: expected (n, Cin, H, W), got {tuple(xc.shape)}")
+        n, Cin, H, W = xc.shape
+        Tc = Tp = 0
+    if wc.shape[1] != Cin:
+        raise RuntimeError(f"waldo_b200.conv3x3: weight has {wc.shape[1]} input channels, x has {Cin}")
+    out = torch.empty(n, wc.shape[0], H, W, device=xc.device, dtype=torch.float32)
+    a = L.Conv3x3(n, Cin, wc.shape[0], H, W, Tc, Tp, L.ptr(xc, name="x"), L.ptr(wc, name="weight"), L.ptr(out))
+    L.call(lib.waldo_conv3x3_fwd, a, xc, "conv3x3_fwd")
+    return out
+
+
 # ===================================================================================== a-5 / a-11 field warp, scale
 def _no_grad_path(*tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):

@@ -370,3 +370,17 @@ def layer_entropy(alpha):
     (entropy (B, T, 1, H, W) = -sum_k p_k log(p_k + 1e-6) / 0.37 with p = normalize((alpha + 1) / 2 + 1e-6, p=1),
      fg_mask (B, T, 1, H, W) = sum_{k >= 1} (alpha_k + 1) / 2); differentiable."""
     return Fn.layer_entropy(alpha)
+
+
+# ----------------------------------------------------------------------------- f-1, first layer (consumer side: WIF's UNet)
+def wif_to_emb(raw_output, weight):
+    """`UNet.to_emb` as WIF.forward applies it to raw_output (models/nets/wif.py:33-38 + models/modules/conv.py:54):
+    raw_output (B, Tc, Tp, Cin, H, W) straight from decode_output, weight = unet.to_emb.weight (Cout, Cin, 3, 3)
+    -> (B*Tp*Tc, Cout, H, W), the first feature map of the UNet.  The permute of wif.py:33 is folded into the kernel's
+    addressing.  TF32 products / fp32 accumulation; inference only."""
+    return Fn.conv3x3(raw_output, weight, wif_permute=True)
+
+
+def conv3x3(x, weight):
+    """models/modules/conv.py:9-11 conv3x3 (stride 1, padding 1, no bias) on (n, Cin <= 48, H, W), Cout in {8, 16, 24, 32}."""
+    return Fn.conv3x3(x, weight)
