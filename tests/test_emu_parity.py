@@ -110,8 +110,8 @@ def test_deterministic_mode_rejects_targets_outside_the_arena(monkeypatch):
     from waldo_b200 import functional as F
     orig = F._scatter_targets
 
-    def broken(refs, det):
-        out, arena, shadow = orig(refs, det)
+    def broken(refs, det, fill=True):
+        out, arena, shadow = orig(refs, det, fill)
         if det:   # d_input allocated on its own instead of as a view of the arena
             out[0] = torch.zeros_like(refs[0]) if refs[0] is not None else None
         return out, arena, shadow
