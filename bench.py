@@ -373,7 +373,12 @@ class Runner:
         if backward:
             # the trainable net's gradient exchange rides NCCL's own stream while this path's backward runs (what DDP's
             # bucketed all-reduce does with the rest of a backward pass); the step ends when both are done
-            work = self.grad_buf.reduce_async() if self.grad_buf is not None else None
+            # (deterministic mode: the exchange runs to completion first.  Concurrent with the 64-bit reductions of the
+            #  deterministic backward kernels the step took 3x longer on the B200, profiles/r2/r2_notes.md)
+            overlap = self.grad_buf is not None and not self.deterministic
+            if self.grad_buf is not None and not overlap:
+                self.grad_buf.reduce()
+            work = self.grad_buf.reduce_async() if overlap else None
             torch.autograd.backward([out[0], out[1], out[5]], [self.g_output, self.g_flow, self.g_raw])
             if work is not None:
                 self.grad_buf.finish(work)

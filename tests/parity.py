@@ -604,6 +604,47 @@ def check_layer_entropy(dev, seed=11):
         grad_close(ad2.grad, a2.grad, a2.grad.double(), f"fg_mask[{i}] d alpha")
 
 
+def check_deterministic_large_gradients(dev, seed=1, B=8):
+    """Deterministic mode on the benchmark inputs of rank 1 (seed 1), whose background-grid gradient is amplified 1e8 x (max
+    |d bg_pose| 6e8 for upstream gradients of ~6): single addends exceed 2^52 fixed-point units there.  They must be
+    accumulated (checked 64-bit add), not flagged: gradients finite, flag clear, equal to the float-reduction mode to rounding."""
+    from waldo_b200 import functional as F, workloads as wl
+    cfg, spec = wl.workload("city_train")
+    T, Tc = spec["T"], spec["Tc"]
+    d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in wl.synth_inputs(cfg, B, T, Tc, seed=seed).items()}
+    opt = wl.make_opt(cfg)
+    warper = wb.Warper(opt).to(dev)
+    om, bg = wb.alpha_masks(opt)
+    om, bg = om.to(dev), bg.to(dev)
+    C, L = 3 + cfg.num_lyt, cfg.num_obj + 1
+    Hd, Wd = cfg.hd_shape
+    gen = torch.Generator(device=dev).manual_seed(1 + seed) if dev.type == "cuda" else torch.Generator().manual_seed(1 + seed)
+    ups = [torch.randn(B, T - Tc, C, Hd, Wd, device=dev, generator=gen), torch.randn(B, Tc, T - Tc, 2, Hd, Wd, device=dev, generator=gen),
+           torch.randn(B, Tc, T - Tc, C + L, Hd, Wd, device=dev, generator=gen)]
+    names = ("input", "obj_alpha_raw", "obj_pose", "bg_pose", "occ_score", "cls")
+
+    def run():
+        lv = {k: d[k].detach().clone().requires_grad_(True) for k in names}
+        occ, oa, ba, grid = wb.estimate_alpha_grid_occ(warper, lv["obj_alpha_raw"], om, bg, lv["obj_pose"], lv["bg_pose"], lv["occ_score"])
+        out = wb.decode_output(warper, lv["input"], grid, occ, oa, ba, lv["cls"], d["ctx_ts"].contiguous(), d["pred_ts"], cfg.restrict_to_ctx)
+        torch.autograd.backward([out[0], out[1], out[5]], ups)
+        return {k: v.grad for k, v in lv.items()}
+    g0 = run()
+    wb.set_deterministic(True)
+    try:
+        g1 = run()
+        flag = float(F.LAST_DET_SCALE.cpu()[3])
+    finally:
+        wb.set_deterministic(False)
+    assert flag == 0.0, "fixed-point overflow flag raised"
+    big = max(float(g0[k].abs().max()) for k in names)
+    assert big > 1e8, f"this input no longer produces the large gradients the test is about (max {big:.3e})"
+    for k in names:
+        assert bool(torch.isfinite(g1[k]).all()), k
+        ref = g0[k]
+        assert float((g1[k] - ref).abs().max()) <= 1e-4 * float(ref.abs().max()), f"d {k}: deterministic vs default"
+
+
 # ------------------------------------------------------------------------------------------------ f-1 first UNet layer
 TOL_TF32 = 3e-3   # conv3x3 with TF32 products (10-bit mantissa operands: activations truncated by the tensor core, weights
                   # rounded to nearest; fp32 accumulation): max|k - exact| <= 3e-3 * max|exact|

@@ -94,6 +94,10 @@ def test_small_chain_deterministic_gradients(dev):
     parity.check_chain_deterministic(dev, cfg, B, T, Tc, seed=5)
 
 
+def test_deterministic_mode_survives_large_intermediate_gradients(dev):
+    parity.check_deterministic_large_gradients(dev)
+
+
 def test_conv3x3(dev):
     parity.check_conv3x3(dev)
 

@@ -248,10 +248,14 @@ def _scatter_targets(refs, det, fill=True):
 
 
 # The scatter targets of decode_bwd must be zero-filled (1.9 GB of `d input` + 1.1 GB of context-opacity gradient at the
-# benchmark shape: 0.5 ms of pure HBM writes).  When gradients will be asked for, the fills are issued at the end of the
-# FORWARD on a side stream (see _Decode.forward), so that they overlap with the caller's work between forward and backward
-# instead of sitting at the start of the backward.  PREFILL = False restores the fills at the start of backward.
-PREFILL = True
+# benchmark shape: 0.5 ms of pure HBM writes), by default at the start of the backward, on its stream.
+# PREFILL = True (or WALDO_PREFILL=1) issues the fills at the end of the FORWARD on a side stream instead (see
+# _Decode.forward), so that they overlap with the caller's work between forward and backward.  It is OFF by default: the
+# buffers then carry a Tensor.record_stream mark, which defers the release of their blocks until the host observes the side
+# stream's event -- with the host running many steps ahead of the GPU the caching allocator keeps allocating fresh 3 GB
+# sets (reserved memory 13 -> 89 GiB over 40 steps on the B200, profiles/r2/r2_notes.md) -- and inside a step with nothing
+# between forward and backward the overlap gains nothing (the fills compete with the forward kernels for SM slots).
+PREFILL = os.environ.get("WALDO_PREFILL", "") == "1"
 _side_streams = {}
 
 

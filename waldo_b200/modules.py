@@ -156,10 +156,12 @@ class Warper(nn.Module):
         tgo = self.tps_obj(obj_pose.reshape(B * T * No, Lo, 2))
         sgo = self.invert_obj(tgo) if invert else None
         if fork:
+            # join.  No Tensor.record_stream on tgb / sgb: it would defer the release of their blocks until the host sees the
+            # main stream pass this point, and the host runs many steps ahead of the GPU -- reserved memory then grows by a set
+            # of buffers per step (measured: profiles/r2/r2_notes.md).  It is not needed either: the side stream touches memory
+            # again only after its next `wait_stream(main)` (the next fork, or autograd's own synchronisation before a backward
+            # node of this chain), i.e. after every main-stream consumer of these tensors has been enqueued before it.
             main.wait_stream(side)
-            for t in (tgb, sgb):
-                if t is not None:
-                    t.record_stream(main)
         else:
             tgb = self.tps_bg(bg_pose.reshape(B * T, Lb, 2))
             sgb = self.invert_bg(tgb, erode=False) if invert else None
