@@ -418,6 +418,7 @@ class _Decode(torch.autograd.Function):
         lyt_lo = torch.empty(B, g.Tw, Nl, spec.H, spec.W, **f32) if (spec.use_filter and any(ctx.needs_input_grad)) else None
         tensors = (inp_c, tgo_c, sgo_c, tgb_c, sgb_c, occ_c, oa_c, ba_c, cls_c, ts_c, ps_c, xs_hd, ys_hd, a_lo, prof_part,
                    prof_sum, prof_p, f_lo, s_lo, live_ctx, live_pred, alpha, flow, raw, out_full, norm, score, lyt_lo)
+        # (PREFILL only, off by default -- see the note at PREFILL.)
         # The fills are issued right after the forward kernels, on a side stream (`side.wait_stream(main)`: after the forward),
         # and the backward waits for them: they overlap with whatever the caller runs between this forward and its backward
         # (WIF's UNet, the losses).  Overlapping them with the forward kernels themselves was measured on the B200 and gains
