@@ -678,12 +678,25 @@ def check_conv3x3(dev, seed=21):
         assert float((got - exact).abs().max()) <= TOL_TF32 * scale, f"conv3x3 vs exact convolution: {float((got - exact).abs().max()) / scale:.3e}"
         plain = wb.conv3x3(want_order.contiguous().to(dev), wgt.to(dev)).cpu().double()
         assert torch.equal(plain, got), "conv3x3: the permuted addressing and the plain one disagree"
-    try:
-        wb.conv3x3(torch.zeros(1, 3, 8, 8, device=dev).requires_grad_(True), torch.zeros(8, 3, 3, 3, device=dev))
+    # gradients: d raw_output through the same kernel (flipped, transposed weights; Tc <-> Tp), d weight through torch
+    for (B, Tc, Tp, Cin, H, W, Cout) in ((1, 2, 2, 40, 12, 36, 16), (1, 3, 1, 16, 9, 20, 8), (2, 1, 2, 48, 8, 33, 16)):
+        raw = torch.randn(B, Tc, Tp, Cin, H, W, generator=gen)
+        wgt = torch.randn(Cout, Cin, 3, 3, generator=gen) / (3 * Cin ** 0.5)
+        proj = torch.randn(B * Tp * Tc, Cout, H, W, generator=gen)
+        rd, wd = raw.clone().to(dev).requires_grad_(True), wgt.clone().to(dev).requires_grad_(True)
+        (wb.wif_to_emb(rd, wd) * proj.to(dev)).sum().backward()
+        r64, w64 = raw.double().requires_grad_(True), wgt.double().requires_grad_(True)
+        (F.conv2d(r64.permute(0, 2, 1, 3, 4, 5).reshape(B * Tp * Tc, Cin, H, W), w64, padding=1) * proj.double()).sum().backward()
+        for name, k, e in (("d raw_output", rd.grad, r64.grad), ("d weight", wd.grad, w64.grad)):
+            err = float((k.detach().cpu().double() - e).abs().max()) / float(e.abs().max())
+            assert err <= TOL_TF32, f"conv3x3 {name}: {err:.3e}"
+    try:   # the input gradient is a convolution with Cout = Cin: a multiple of 8 is required, and said so
+        x = torch.zeros(1, 3, 8, 8, device=dev).requires_grad_(True)
+        wb.conv3x3(x, torch.zeros(8, 3, 3, 3, device=dev)).sum().backward()
     except NotImplementedError:
         pass
     else:
-        raise AssertionError("conv3x3 is forward-only and must say so")
+        raise AssertionError("conv3x3: d input with Cin % 8 != 0 must raise")
 
 
 # ------------------------------------------------------------------------------------------------ f-4 output side

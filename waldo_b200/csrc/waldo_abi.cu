@@ -391,7 +391,7 @@ int waldo_conv3x3_fwd(const waldo_conv3x3_t* a, waldo_stream_t st) {
   if (a->Tc > 0) WB_REQUIRE(a->n % (a->Tc * a->Tp) == 0, "conv3x3_fwd: n must be a multiple of Tc*Tp");
   WB_REQUIRE(a->in && a->weight && a->out && a->in != a->out, "conv3x3_fwd: null pointer");
   if (a->n == 0) return 0;
-  const int Cp = (a->Cin + 7) & ~7, WP = a->Cout <= 24 ? 24 : 40;
+  const int Cp = (a->Cin + 7) & ~7, WP = a->Cout <= 24 ? 24 : (a->Cout <= 40 ? 40 : 56);
   // 16-byte staging needs whole 4-pixel chunks inside / outside the image and 16-byte aligned rows
   const bool vec = a->W % 4 == 0 && ((uintptr_t)a->in & 15) == 0;
   const size_t smem = ((size_t)Cp * WB_CV_ROWS * (vec ? WB_CV_PITCH_V : WB_CV_PITCH_S) + (size_t)9 * Cp * WP) * sizeof(float);
@@ -404,6 +404,7 @@ int waldo_conv3x3_fwd(const waldo_conv3x3_t* a, waldo_stream_t st) {
 #endif
   if (vec && Cp == 40 && a->Cout == 16) WB_CV_GO((k_conv3x3_fwd<40, 2, true>));        // WIF's to_emb: 3 + 20 + 17 channels -> 16
   else if (vec && Cp == 48 && a->Cout == 16) WB_CV_GO((k_conv3x3_fwd<48, 2, true>));   // ... with the disocc channel (41 -> 48)
+  else if (vec && Cp == 16 && a->Cout == 40) WB_CV_GO((k_conv3x3_fwd<16, 5, true>));   // its backward-data: 16 -> 40 (flipped, transposed weights)
   else if (vec) WB_CV_GO((k_conv3x3_fwd<0, 0, true>));
   else WB_CV_GO((k_conv3x3_fwd<0, 0, false>));
 #undef WB_CV_GO

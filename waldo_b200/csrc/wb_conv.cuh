@@ -25,7 +25,7 @@
 #define WB_CV_PITCH_V 44
 #define WB_CV_PITCH_S 36
 #define WB_CV_MAX_CIN 48
-#define WB_CV_MAX_COUT 32
+#define WB_CV_MAX_COUT 48
 
 WB_DEV float wb_tf32(float v) {   // round to nearest, ties away from zero, 10-bit mantissa (cvt.rna.tf32.f32)
 #ifdef WB_HOST_EMU
@@ -49,7 +49,8 @@ WB_DEV float wb_tf32_rz(float v) {
   return c.f;
 }
 
-WB_DEV int wb_cv_wpitch(int Cout) { return Cout <= 24 ? 24 : 40; }
+// out-channel pitch of the staged weights: >= Cout and = 8 or 24 (mod 32), so that the B-fragment loads of a warp hit 32 banks
+WB_DEV int wb_cv_wpitch(int Cout) { return Cout <= 24 ? 24 : (Cout <= 40 ? 40 : 56); }
 
 // image of `in` that output image i reads: identity, or (b, tp, tc) <- (b, tc, tp)
 WB_DEV int wb_cv_src_image(const waldo_conv3x3_t& p, int i) {

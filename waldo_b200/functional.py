@@ -685,32 +685,67 @@ def layer_entropy(alpha):
 
 
 # ===================================================================================== f-1 first UNet layer
+def _conv3x3_launch(x, weight, n, Cin, H, W, Tc, Tp):
+    lib = L.load()
+    out = torch.empty(n, weight.shape[0], H, W, device=x.device, dtype=torch.float32)
+    a = L.Conv3x3(n, Cin, weight.shape[0], H, W, Tc, Tp, L.ptr(x, name="x"), L.ptr(weight, name="weight"), L.ptr(out))
+    L.call(lib.waldo_conv3x3_fwd, a, x, "conv3x3_fwd")
+    return out
+
+
+class _Conv3x3(torch.autograd.Function):
+    """conv3x3(stride 1, padding 1, no bias), models/modules/conv.py:9-11, TF32 products / fp32 accumulation.
+    forward + backward-data on waldo_conv3x3_fwd (the backward-data of a stride-1 3x3 convolution is the same convolution with
+    the weights flipped and transposed, and the image permute is undone by swapping Tc and Tp); the weight gradient -- a
+    reduction over all pixels of all images -- is left to torch (cuDNN)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, wif_permute):
+        xc, wc = _c(x.detach()), _c(weight.detach())
+        if wc.dim() != 4 or wc.shape[2:] != (3, 3):
+            raise RuntimeError(f"waldo_b200.conv3x3: weight must be (Cout, Cin, 3, 3), got {tuple(wc.shape)}")
+        if wif_permute:
+            if xc.dim() != 6:
+                raise RuntimeError(f"waldo_b200.conv3x3: wif_permute expects raw_output (B, Tc, Tp, C, H, W), got {tuple(xc.shape)}")
+            B, Tc, Tp, Cin, H, W = xc.shape
+            n = B * Tc * Tp
+        else:
+            if xc.dim() != 4:
+                raise RuntimeError(f"waldo_b200.conv3x3: expected (n, Cin, H, W), got {tuple(xc.shape)}")
+            n, Cin, H, W = xc.shape
+            Tc = Tp = 0
+        if wc.shape[1] != Cin:
+            raise RuntimeError(f"waldo_b200.conv3x3: weight has {wc.shape[1]} input channels, x has {Cin}")
+        ctx.save_for_backward(xc, wc)
+        ctx.dims = (n, Cin, H, W, Tc, Tp, bool(wif_permute))
+        return _conv3x3_launch(xc, wc, n, Cin, H, W, Tc, Tp)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        xc, wc = ctx.saved_tensors
+        n, Cin, H, W, Tc, Tp, perm = ctx.dims
+        g = _c(d_out)
+        d_x = d_w = None
+        if ctx.needs_input_grad[0]:
+            if Cin % 8 != 0:
+                raise NotImplementedError("waldo_b200.conv3x3: the input gradient needs Cin to be a multiple of 8 (it is the Cout of "
+                                          "the transposed convolution); pad the channels or detach the input")
+            wt = wc.flip(2, 3).transpose(0, 1).contiguous()                       # (Cin, Cout, 3, 3)
+            d_x = _conv3x3_launch(g, wt, n, wc.shape[0], H, W, Tp, Tc)            # Tc <-> Tp: the inverse image permute
+            d_x = d_x.view(xc.shape)
+        if ctx.needs_input_grad[1]:
+            x4 = xc.permute(0, 2, 1, 3, 4, 5).reshape(n, Cin, H, W) if perm else xc
+            d_w = torch.nn.grad.conv2d_weight(x4, wc.shape, g, padding=1)
+        return d_x, d_w, None
+
+
 def conv3x3(x, weight, wif_permute=False):
     """UNet.to_emb (models/modules/conv.py:9-11, :54): conv3x3(stride 1, padding 1, no bias) with TF32 tensor-core products and
     fp32 accumulation.  x (n, Cin, H, W) -> (n, Cout, H, W); with wif_permute, x is raw_output (B, Tc, Tp, Cin, H, W) as
     decode_output returns it and the result is (B*Tp*Tc, Cout, H, W) in the image order of WIF.forward (wif.py:33-38), without the
-    permuted copy.  Forward / inference only."""
-    _no_grad_path(x, weight)
-    lib = L.load()
-    xc, wc = _c(x.detach()), _c(weight.detach())
-    if wc.dim() != 4 or wc.shape[2:] != (3, 3):
-        raise RuntimeError(f"waldo_b200.conv3x3: weight must be (Cout, Cin, 3, 3), got {tuple(wc.shape)}")
-    if wif_permute:
-        if xc.dim() != 6:
-            raise RuntimeError(f"waldo_b200.conv3x3: wif_permute expects raw_output (B, Tc, Tp, C, H, W), got {tuple(xc.shape)}")
-        B, Tc, Tp, Cin, H, W = xc.shape
-        n = B * Tc * Tp
-    else:
-        if xc.dim() != 4:
-            raise RuntimeError(f"waldo_b200.conv3x3: expected (n, Cin, H, W), got {tuple(xc.shape)}")
-        n, Cin, H, W = xc.shape
-        Tc = Tp = 0
-    if wc.shape[1] != Cin:
-        raise RuntimeError(f"waldo_b200.conv3x3: weight has {wc.shape[1]} input channels, x has {Cin}")
-    out = torch.empty(n, wc.shape[0], H, W, device=xc.device, dtype=torch.float32)
-    a = L.Conv3x3(n, Cin, wc.shape[0], H, W, Tc, Tp, L.ptr(xc, name="x"), L.ptr(wc, name="weight"), L.ptr(out))
-    L.call(lib.waldo_conv3x3_fwd, a, xc, "conv3x3_fwd")
-    return out
+    permuted copy.  Differentiable: d x (= d raw_output, the upstream gradient of the warp backward) by the same kernel, d weight
+    by torch."""
+    return _Conv3x3.apply(x, weight, wif_permute)
 
 
 # ===================================================================================== a-5 / a-11 field warp, scale

@@ -379,7 +379,8 @@ def wif_to_emb(raw_output, weight):
     """`UNet.to_emb` as WIF.forward applies it to raw_output (models/nets/wif.py:33-38 + models/modules/conv.py:54):
     raw_output (B, Tc, Tp, Cin, H, W) straight from decode_output, weight = unet.to_emb.weight (Cout, Cin, 3, 3)
     -> (B*Tp*Tc, Cout, H, W), the first feature map of the UNet.  The permute of wif.py:33 is folded into the kernel's
-    addressing.  TF32 products / fp32 accumulation; inference only."""
+    addressing.  TF32 products / fp32 accumulation.  Differentiable: `d raw_output` (the upstream gradient of the warp
+    backward) comes from the same kernel with the flipped, transposed weights; `d weight` from torch."""
     return Fn.conv3x3(raw_output, weight, wif_permute=True)
 
 
