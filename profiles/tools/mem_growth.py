@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""Does reserved device memory keep growing over steps?"""
+import os, sys, types
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import torch, bench
+import waldo_b200 as wb
+from waldo_b200 import modules as M
+args = types.SimpleNamespace(no_graph=True, no_input_grad=False)
+cfg, spec = bench.workload_cfg(sys.argv[1] if len(sys.argv) > 1 else "city_train")
+bench.load_peak()
+det = os.environ.get("DET", "0") == "1"
+M.OVERLAP_BG = os.environ.get("NO_OVERLAP", "0") != "1"
+r = bench.Runner(args, cfg, spec, 0, 0, 1, deterministic=det)
+wb.set_deterministic(det)
+out = []
+for i in range(40):
+    r.step(r.resident)
+    ms = torch.cuda.memory_stats()
+    out.append((round(torch.cuda.memory_reserved() / 2**30, 2), ms.get("num_device_alloc", 0)))
+torch.cuda.synchronize()
+print("det", det, "overlap_bg", M.OVERLAP_BG, "prefill", wb.functional.PREFILL)
+print(" reserved GiB:", [o[0] for o in out[::3]])
+print(" device allocs:", [o[1] for o in out[::3]])
