@@ -22,6 +22,24 @@ def test_full_shape_vs_oracle_and_reference(name):
     print(name, json.dumps(rep))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(parity.FULL_SHAPES))
+def test_full_shape_bf16_storage(name):
+    assert torch.cuda.is_available()
+    rep = parity.check_full_shape_bf16(torch.device("cuda:0"), name)
+    out = os.path.join(parity.ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"parity_bf16_{name}.json"), "w") as f:
+            json.dump(rep, f, indent=1)
+
+
+@pytest.mark.parametrize("name", ["city_128x256", "kitti_64x208"])
+def test_reduced_shape_bf16_storage_emulated(name):
+    from tests.emu.harness import emulated
+    with emulated():
+        parity.check_full_shape_bf16(torch.device("cpu"), name)
+
+
 @pytest.mark.parametrize("name", list(parity.REDUCED_SHAPES))
 def test_reduced_shape_vs_oracle_and_reference_emulated(name):
     from tests.emu.harness import emulated
