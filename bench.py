@@ -51,15 +51,16 @@ def alg_bytes(cfg, B, Tc, Tp, backward):
 
 
 def step_bytes(cfg, B, Tc, Tp, backward, storage="f32"):
-    """alg_bytes for a storage type: with bf16 storage the HD activation streams (input, alpha, raw_output, output) are 2-byte
-    elements, flow (2 floats per pair and pixel, written by the layer kernel and read by the gather kernel) stays fp32."""
+    """alg_bytes for a storage type: with bf16 storage the big HD streams (input, raw_output, output) are 2-byte elements; alpha
+    (written once per context frame, gathered by the layer kernel), flow and score stay fp32."""
     from waldo_b200 import workloads as wl
     if storage != "bf16":
         return wl.alg_bytes(cfg, B, Tc, Tp, backward)
     assert not backward
     fwd2, _ = wl.alg_bytes(cfg, B, Tc, Tp, False, elem=2)
     Hd, Wd = cfg.hd_shape
-    return fwd2 + Hd * Wd * 2 * (B * Tc * Tp * (2 + 2 + 1)), 0   # flow written + read, score read: fp32
+    L = cfg.num_obj + 1
+    return fwd2 + Hd * Wd * 2 * (B * Tc * Tp * (2 + 2 + 1) + B * Tc * L + B * Tc * Tp * L), 0   # flow w + r, score r, alpha w + gathered: fp32
 
 
 def kernel_bytes(cfg, B, Tc, Tp):

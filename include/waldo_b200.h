@@ -53,11 +53,12 @@ enum {
                                     and diagonal (constants of lvd.py:63-66, never read there) are left at zero      */
 };
 
-/* storage type of the HD activations of waldo_decode_fwd_t (input, alpha, raw_output, out_full) */
+/* storage type of the big HD streams of waldo_decode_fwd_t: input, raw_output, out_full (alpha, flow, norm, score and every low-res
+ * tensor stay fp32: the sampling positions do not depend on the storage type) */
 enum {
   WALDO_ST_F32  = 0,  /* the reference's precision: parity rules 1-3 apply                                                */
-  WALDO_ST_BF16 = 1   /* bf16 storage, fp32 arithmetic, forward / inference only (half the HBM bytes of the HD streams);
-                         the four pointers then address bf16 elements; tolerance stated in tests/parity.py (rule 4)       */
+  WALDO_ST_BF16 = 1   /* bf16 storage, fp32 arithmetic, forward / inference only (half the HBM bytes of those streams);
+                         the three pointers then address bf16 elements; tolerance stated in tests/parity.py (rule 4)     */
 };
 
 typedef void* waldo_stream_t; /* cudaStream_t */
@@ -187,8 +188,8 @@ typedef struct {
   float* score;               /* (B, Tc, Tp, Hd, Wd) sum_k Actx_k per pair (lvd.py:841), glue between the two HD kernels */
   int stages;                 /* 0 = everything; else bit 0 = low-res kernels (B1, B2, B5), bit 3 = HD context-alpha kernel (B2b-B4),
                                  bit 1 = HD layer kernel (B5up-B9), bit 2 = HD gather kernel (stage C) */
-  int storage;                /* WALDO_ST_F32 | WALDO_ST_BF16: element type of input, alpha, raw_output, out_full (everything else,
-                                 incl. flow / norm / score and all low-res tensors, stays fp32).  waldo_decode_bwd needs WALDO_ST_F32 */
+  int storage;                /* WALDO_ST_F32 | WALDO_ST_BF16: element type of input, raw_output, out_full (everything else, incl.
+                                 alpha / flow / norm / score and all low-res tensors, stays fp32).  waldo_decode_bwd needs WALDO_ST_F32 */
 } waldo_decode_fwd_t;
 int waldo_decode_fwd(const waldo_decode_fwd_t*, waldo_stream_t);
 

@@ -36,21 +36,19 @@ OUT_NAMES = ["output", "flow", "alpha_unflt", "alpha", "raw_alpha", "raw_output"
 
 FWD_TOL = 1e-5
 GRAD_TOL = 1e-4
-# Rule (4), the bf16-STORAGE variant (input / alpha / raw_output / output held as bf16 in HBM, fp32 arithmetic, forward only;
-# include/waldo_b200.h WALDO_ST_BF16), stated against the fp32 path on the same inputs:
-#   * flow (stays fp32; only sees the bf16 rounding of the stored context opacities): max-abs <= 1e-3 (normalised units);
-#   * alpha, alpha_ctx, raw_alpha (values in [-1, 1]; one bf16 rounding is 2^-9 relative): max-abs <= 1.6e-2 (= 2^-6);
-#   * raw_output image / layout channels (values in [-5, 5]): one rounding at |v| >= 4 is 1.56e-2, and a warped channel turns a tap
-#     shift into (shift in pixels) x (difference between neighbouring input pixels).  The shift is the flow deviation above times
-#     Wd / 2 (0.12 pixel at 1024 columns); the difference is 10 wherever two neighbouring pixels have different classes (one-hot
-#     +-5 logits) -- in the benchmark's synthetic inputs that is EVERY pair of neighbours (a random class per pixel), the worst
-#     case.  Stated for that worst case: mean-abs <= 5e-3, 99.9th percentile <= 0.25, max-abs <= 1.0 (measured at the full
-#     benchmark shapes: mean 1.4e-3 .. 2.6e-3, p99.9 0.11, max 0.46; on the piecewise-constant fixtures 5x smaller);
+# Rule (4), the bf16-STORAGE variant (input / raw_output / output held as bf16 in HBM; alpha, flow and all arithmetic fp32; forward
+# only; include/waldo_b200.h WALDO_ST_BF16), stated against the fp32 path on the same inputs:
+#   * flow, alpha (fp32 in both variants; they only see the bf16 rounding of the INPUT's layout logits): with the dataset's one-hot
+#     +-5 logits (data/base_dataset.py:173-183: exactly representable in bf16) they are BIT-IDENTICAL to the fp32 path -- sampling
+#     positions and every index-valued decision do not depend on the storage type; with arbitrary (smooth) logits: flow max-abs
+#     <= 1e-3 (normalised units), alpha max-abs <= 1.6e-2;
+#   * alpha_ctx, raw_alpha (values in [-1, 1], one bf16 rounding = 2^-9 relative): max-abs <= 1.6e-2 (= 2^-6);
+#   * raw_output image / layout channels (values in [-5, 5]): one rounding at |v| >= 4 is 1.56e-2 (the whole deviation with one-hot
+#     logits); with smooth logits the flow deviation above shifts the taps: mean-abs <= 5e-3, 99.9th percentile <= 0.1, max-abs <= 0.5;
 #   * output (the score-weighted mean of the contexts, lvd.py:850-851: divides by the summed score, which is ~1e-6 where no
 #     context sees the pixel -- the reference's own fp32-vs-fp64 error is O(1) there): where the summed
-#     context score sum_tc sum_k A_k is >= 0.1: mean-abs <= 1.5e-2, max-abs <= 1.0 (measured: mean 4e-3 .. 9.8e-3, max 0.75);
-#     elsewhere finite.
-TOL_BF16 = dict(flow_max=1e-3, alpha_max=1.6e-2, raw_mean=5e-3, raw_p999=0.25, raw_max=1.0, out_norm=0.1, out_mean=1.5e-2, out_max=1.0)
+#     context score sum_tc sum_k A_k is >= 0.1: mean-abs <= 8e-3, max-abs <= 0.25; elsewhere finite.
+TOL_BF16 = dict(flow_max=1e-3, alpha_max=1.6e-2, raw_mean=5e-3, raw_p999=0.1, raw_max=0.5, out_norm=0.1, out_mean=8e-3, out_max=0.25)
 
 
 def load_case(name):
@@ -255,8 +253,9 @@ def _pct(e, q):
     return float(e.kthvalue(max(1, min(e.numel(), int(round(e.numel() * q)))))[0])
 
 
-def bf16_close(out32, out16, what, report=None):
-    """TOL_BF16 between a tuple of fp32 outputs (OUT_NAMES order) and the bf16-storage variant's."""
+def bf16_close(out32, out16, what, report=None, exact_positions=False):
+    """TOL_BF16 between a tuple of fp32 outputs (OUT_NAMES order) and the bf16-storage variant's.  exact_positions: the layout
+    logits of the input are exactly representable in bf16 (one-hot +-5), so flow and alpha must be bit-identical."""
     t = TOL_BF16
     ac = out32[OUT_NAMES.index("alpha_ctx")].detach().float().cpu()
     seen = (((ac + 1) / 2).sum(3).sum(1) >= t["out_norm"]).unsqueeze(2)   # (B, Tp, 1, Hd, Wd): some context sees the pixel
@@ -264,13 +263,15 @@ def bf16_close(out32, out16, what, report=None):
         assert (x is None) == (y is None), n
         if x is None:
             continue
-        want = torch.float32 if n == "flow" else torch.bfloat16
+        want = torch.float32 if n in ("flow", "alpha", "alpha_unflt") else torch.bfloat16   # alpha stays fp32: the flow is computed from it
         assert y.dtype == want and tuple(y.shape) == tuple(x.shape), f"{what}/{n}: {y.dtype} {tuple(y.shape)}"
         e = (x.detach().float().cpu() - y.detach().float().cpu()).abs()
         assert bool(torch.isfinite(e).all()), f"{what}/{n}: non-finite"
         mx, mean = float(e.max()), float(e.mean())
         if report is not None:
             report[n] = dict(max_abs=mx, mean_abs=mean, p99=_pct(e, 0.99), p999=_pct(e, 0.999))
+        if exact_positions and n in ("flow", "alpha", "alpha_unflt"):
+            assert mx == 0.0, f"{what}/{n}: not bit-identical with exactly representable layout logits ({mx:.3e})"
         if n == "flow":
             assert mx <= t["flow_max"], f"{what}/flow: {mx:.3e}"
         elif n in ("alpha", "alpha_unflt", "alpha_ctx", "raw_alpha"):
@@ -860,7 +861,7 @@ def check_full_shape_bf16(dev, name, report=None):
         k32 = wb.decode_output(warper, d["input"], *args)
         k16 = wb.decode_output(warper, d["input"].to(torch.bfloat16), *args)
     rep = report if report is not None else {}
-    bf16_close(k32, k16, f"{name} bf16 storage", rep)
+    bf16_close(k32, k16, f"{name} bf16 storage", rep, exact_positions=True)   # synth_inputs: one-hot +-5 layout logits
     return rep
 
 

@@ -317,9 +317,10 @@ WB_DEV int wb_nth_bit(unsigned m, int nth) { return (int)__fns(m, 0, nth + 1); }
 #endif
 
 // ------------------------------------------------------------------ storage types of the HD activations
-// `input`, `alpha`, `raw_output` and `out_full` are stored either as fp32 (the reference's precision; parity rules 1-3) or
-// as bf16 (waldo_decode_fwd_t.storage = 1: half the HBM bytes, fp32 arithmetic throughout; forward / inference only;
-// parity rule 4, tolerance stated in tests/parity.py).  Kernels are templates over the storage type ST.
+// `input`, `raw_output` and `out_full` are stored either as fp32 (the reference's precision; parity rules 1-3) or as bf16
+// (waldo_decode_fwd_t.storage = 1: half the HBM bytes of the big HD streams, fp32 arithmetic throughout; forward / inference
+// only; parity rule 4, tolerance stated in tests/parity.py).  `alpha` -- from which the flow is computed -- stays fp32, so the
+// sampling positions do not depend on the storage type.  Kernels are templates over the storage type ST.
 struct wb_bf16 { unsigned short x; };
 WB_DEV float wb_lds(const float* p) { return __ldg(p); }
 WB_DEV float wb_lds(const wb_bf16* p) {

@@ -54,9 +54,9 @@ template <int NA> struct WbLay {
 
 // alpha_c = stored context alpha (2A-1) of frame (b,c): (L, Hd, Wd).  All per-thread addressing is 32-bit element
 // offsets against warp-uniform 64-bit bases (a frame never exceeds 2^31 elements).
-template <int NA, typename ST>
+template <int NA>
 WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, const float* __restrict__ f_lo /* (L,H,W,2) of this pair */,
-                          const ST* __restrict__ alpha_c, const float* __restrict__ s_occ, WbLay<NA>& ly) {
+                          const float* __restrict__ alpha_c, const float* __restrict__ s_occ, WbLay<NA>& ly) {
   const waldo_geom_t& g = d.g;
   const int L = g.No + 1;
   const unsigned HW = (unsigned)(g.H * g.W), HWd = (unsigned)(g.Hd * g.Wd);
@@ -78,7 +78,7 @@ WB_DEV void wb_layers_fwd(const WbDec& d, const WbPix& px, const WbIdx<NA>& ix, 
       if ((px.isobj >> k) & 1u) {
         const WbTaps t = wb_taps(__fadd_rn(px.gx, fx), __fadd_rn(px.gy, fy), g.Wd, g.Hd);
         const WbTap2 t2 = wb_tap2(t, g.Wd, g.Hd);
-        const ST* pl = alpha_c + (size_t)k * HWd;
+        const float* pl = alpha_c + (size_t)k * HWd;
         r = wb_gather2_01(pl + t2.o0, pl + t2.o1, t2.w);
       }
       ly.R[s] = r;
@@ -116,9 +116,9 @@ WB_DEV void wb_fwd_layers(const WbDec& d, const WbFwdCtx& c, const WbPix& px, un
   const int L = c.L, C = c.C;
   const unsigned HWd = c.HWd;
   const float* f_lo = d.f_lo + pair * L * c.HW * 2;
-  const ST* alpha_c = reinterpret_cast<const ST*>(d.alpha) + ((size_t)c.b * g.Tw + c_t) * L * HWd;
+  const float* alpha_c = d.alpha + ((size_t)c.b * g.Tw + c_t) * L * HWd;   // (fp32 in every storage variant)
   WbLay<NA> ly;
-  wb_layers_fwd<NA, ST>(d, px, ix, f_lo, alpha_c, c.s_occ, ly);
+  wb_layers_fwd<NA>(d, px, ix, f_lo, alpha_c, c.s_occ, ly);
   ST* ra = raw + (size_t)C * HWd + q;
   WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) wb_sts(ra, -1.f); ra += HWd; }
   ra = raw + (size_t)C * HWd + q;
@@ -173,7 +173,7 @@ WB_DEV void wb_lanes_layers_fwd(const WbDec& d, const WbFwdCtx& c, unsigned wm, 
     const int c_t = (int)d.ctx_ts[((size_t)b * g.Tc + tc) * g.Tp + tp];
     const size_t pair = ((size_t)b * g.Tc + tc) * g.Tp + tp;
     const float2* fl = reinterpret_cast<const float2*>(d.f_lo) + (pair * L + k) * HW;
-    const ST* alpha_k = reinterpret_cast<const ST*>(d.alpha) + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
+    const float* alpha_k = d.alpha + (((size_t)b * g.Tw + c_t) * L + k) * HWd;
     ST* ra = reinterpret_cast<ST*>(d.raw_output) + ((((size_t)b * c.TcR + tc) * g.Tp + tp) * c.CR + C) * HWd;   // alpha channels of this pair
     float* flo = d.flow + pair * 2 * HWd;
     float* sco = d.score + pair * HWd;

@@ -195,7 +195,7 @@ WB_DEV void wb_bwd_layers_bwd(const WbDecB& a, const WbBwdCtx& c, const WbPix& p
   const unsigned HWd = c.HWd;
   const float* alpha_c = d.alpha + ((size_t)c.b * g.Tw + c_t) * L * HWd;
   WbLay<NA> ly;
-  wb_layers_fwd<NA, float>(d, px, ix, d.f_lo + pair * L * HW * 2, alpha_c, c.s_occ, ly);
+  wb_layers_fwd<NA>(d, px, ix, d.f_lo + pair * L * HW * 2, alpha_c, c.s_occ, ly);
   float gA[NA], gR[NA], gFx[NA], gFy[NA];
   WB_UNROLL_NA for (int s = 0; s < WB_NEND; ++s) {
     gR[s] = 0.f; gA[s] = 0.f; gFx[s] = 0.f; gFy[s] = 0.f;

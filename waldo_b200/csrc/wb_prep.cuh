@@ -223,7 +223,7 @@ template <typename ST> struct WbPrepCtx {
   bool filt;
   const float *s_P, *s_occ, *alo;
   const ST* lyt_base;
-  ST* out;
+  float* out;   // alpha stays fp32 in every storage variant: the flow is computed from it
 };
 
 // softmax of the HD layout logits of pixel q (lvd.py:744).  NLC = compile-time class count (0: run-time Nl).
@@ -268,7 +268,7 @@ WB_DEV void wb_prep_pixel(const WbDec& d, const WbPrepCtx<ST>& c, unsigned wm, u
       a[s] = v;
     }
   }
-  ST* o = c.out + q;
+  float* o = c.out + q;
   WB_UNROLL for (int k = 0; k < WB_MAX_L; ++k) { if (k < L && !((wm >> k) & 1u)) wb_sts(o, -1.f); o += HWd; }
   o = c.out + q;
   WB_UNROLL_NA for (int i = 0; i < WB_NEND; ++i) {
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(WB_TILE_PX, WB_OCC_PREP_FWD) k_alpha_prep(WbDe
   c.lyt_base = reinterpret_cast<const ST*>(d.input) + (((size_t)c.b * g.T + c.t) * g.C + 3) * c.HWd;
   c.alo = d.a_lo + ((size_t)c.b * g.Tw + c.t) * c.L * c.HW;
   const uint32_t* live = d.live_ctx + ((size_t)c.b * g.Tw + c.t) * c.HW;
-  c.out = reinterpret_cast<ST*>(d.alpha) + ((size_t)c.b * g.Tw + c.t) * c.L * c.HWd;
+  c.out = d.alpha + ((size_t)c.b * g.Tw + c.t) * c.L * c.HWd;
   const WbTileIter ti(g.Hd, g.Wd);
   for (int tile = blockIdx.x; tile < ti.ntiles; tile += gridDim.x) {
     const int ty0 = (tile / ti.tiles_x) * WB_TILE_H, tx0 = (tile % ti.tiles_x) * WB_TILE_W;

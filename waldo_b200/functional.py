@@ -324,7 +324,7 @@ def _fwd_struct(g, prof_ctas, t):
                        L.ptr(oa_c), L.ptr(ba_c), L.ptr(cls_c), L.ptr(ts_c, torch.int64), L.ptr(ps_c, torch.int64),
                        L.ptr(xs_hd), L.ptr(ys_hd), L.ptr(a_lo), L.ptr(prof_part), prof_ctas, L.ptr(prof_sum),
                        L.ptr(prof_p), L.ptr(lyt_lo), L.ptr(f_lo), L.ptr(s_lo), L.ptr(live_ctx, torch.int32), L.ptr(live_pred, torch.int32),
-                       L.ptr(alpha, st), L.ptr(flow), L.ptr(raw, st), L.ptr(out_full, st), L.ptr(norm), L.ptr(score), 0,
+                       L.ptr(alpha), L.ptr(flow), L.ptr(raw, st), L.ptr(out_full, st), L.ptr(norm), L.ptr(score), 0,
                        L.ST_BF16 if st == torch.bfloat16 else L.ST_F32)
 
 
@@ -356,8 +356,8 @@ class _Decode(torch.autograd.Function):
     def forward(ctx, spec, ctx_ts, pred_ts, xs_hd, ys_hd, inp, tgo, sgo, tgb, sgb, occ, obj_alpha, bg_alpha, cls):
         lib = L.load()
         ctx.set_materialize_grads(False)   # unused outputs must not cost a zero-filled HD tensor each
-        # bf16 `input` selects the bf16-storage variant: input / alpha / raw_output / output are bf16 in HBM, all arithmetic
-        # is fp32 (include/waldo_b200.h WALDO_ST_BF16; tolerance: tests/parity.py TOL_BF16).  Forward / inference only.
+        # bf16 `input` selects the bf16-storage variant: input / raw_output / output are bf16 in HBM (alpha stays fp32), all
+        # arithmetic is fp32 (include/waldo_b200.h WALDO_ST_BF16; tolerance: tests/parity.py TOL_BF16).  Forward / inference only.
         st = torch.bfloat16 if inp.dtype == torch.bfloat16 else torch.float32
         if st == torch.bfloat16 and any(ctx.needs_input_grad):
             raise RuntimeError("waldo_b200.decode: bf16 storage is forward / inference only (run under torch.no_grad(), or pass fp32 input)")
@@ -408,7 +408,7 @@ class _Decode(torch.autograd.Function):
         s_lo = torch.empty(B, Tp, spec.num_obj, spec.H, spec.W, **f32)
         live_ctx = torch.empty(B, g.Tw, spec.H, spec.W, device=dev, dtype=torch.int32)
         live_pred = torch.empty(B, Tp, spec.H, spec.W, device=dev, dtype=torch.int32)
-        alpha = torch.empty(B, g.Tw, Lr, Hd, Wd, device=dev, dtype=st)
+        alpha = torch.empty(B, g.Tw, Lr, Hd, Wd, **f32)   # fp32 in every storage variant: the flow is computed from it
         flow = torch.empty(B, Tc, Tp, 2, Hd, Wd, **f32)
         raw = torch.empty(B, TcR, Tp, CR, Hd, Wd, device=dev, dtype=st)
         out_full = torch.empty(B, Tp, Cc + 1, Hd, Wd, device=dev, dtype=st)
