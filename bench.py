@@ -515,8 +515,32 @@ def wif_to_emb_leg(dev, steps=10):
         torch.cuda.synchronize(dev)
         ms_ref = e0.elapsed_time(e1) / steps
         del x
+    # training: forward + backward-data (d raw_output) + weight gradient, ours and stock torch
+    raw_g, wgt_g = raw.detach().requires_grad_(True), wgt.detach().requires_grad_(True)
+    gy = torch.randn(B * Tc * Tp, Cout, H, W, device=dev, generator=gen)
+
+    def train_step(fn):
+        raw_g.grad = None
+        wgt_g.grad = None
+        fn().backward(gy)
+
+    def timed(fn, n=5):
+        for _ in range(2):
+            train_step(fn)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            train_step(fn)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / n
+    ms_train = timed(lambda: wb.wif_to_emb(raw_g, wgt_g))
+    ms_train_ref = timed(lambda: torch.nn.functional.conv2d(raw_g.permute(0, 2, 1, 3, 4, 5).reshape(B * Tp * Tc, Cin, H, W), wgt_g, padding=1))
+    del raw_g, gy
     nbytes = B * Tc * Tp * H * W * 4 * (Cin + Cout)
     return {"shape": f"raw_output (B={B}, Tc={Tc}, Tp={Tp}, {Cin}, {H}, {W}) -> ({B * Tc * Tp}, {Cout}, {H}, {W})", "ms": ms, "alg_bytes": nbytes,
+            "fwd_bwd_ms": ms_train, "stock_torch_fwd_bwd_ms": ms_train_ref,
             "frac": nbytes / (ms * 1e-3) / 1e9 / PEAK["gbs"], "tflops": 2 * 9 * Cin * Cout * B * Tc * Tp * H * W / (ms * 1e-3) / 1e12,
             "stock_torch_ms": ms_ref, "stock_torch": "permute + reshape copy + F.conv2d (cuDNN, allow_tf32 default)"}
 

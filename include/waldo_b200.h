@@ -370,6 +370,18 @@ typedef struct {
 } waldo_conv3x3_t;
 int waldo_conv3x3_fwd(const waldo_conv3x3_t*, waldo_stream_t);
 
+/* Weight gradient of the same layer: dweight[co][ci][ky][kx] = sum_{image, y, x} dout[image][co][y][x] * in[src(image)][ci][y+ky-1][x+kx-1]
+ * (zero padding).  Per-CTA partial sums in registers over all tiles of the CTA, added in CTA order (deterministic).
+ * Needs Cout <= 16, Cin <= 40, W % 4 == 0 and 16-byte aligned `in` / `dout`. */
+typedef struct {
+  waldo_conv3x3_t c;          /* the forward call's arguments (weight and out are not read) */
+  const float* dout;          /* (n, Cout, H, W), in the forward's OUTPUT image order */
+  int ctas;                   /* CTAs of the launch = number of partials, <= 296 */
+  float* part;                /* scratch (ctas, Cout, Cin, 3, 3) */
+  float* dweight;             /* out (Cout, Cin, 3, 3) */
+} waldo_conv3x3_wgrad_t;
+int waldo_conv3x3_wgrad(const waldo_conv3x3_wgrad_t*, waldo_stream_t);
+
 #ifdef __cplusplus
 }
 #endif

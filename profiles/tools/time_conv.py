@@ -25,4 +25,4 @@ def timed(fn, n=5):
 ours = timed(lambda: wb.wif_to_emb(raw, wgt))
 ref = timed(lambda: torch.nn.functional.conv2d(raw.permute(0, 2, 1, 3, 4, 5).reshape(B * Tp * Tc, Cin, H, W), wgt, padding=1))
 wgt_only = wgt.detach().requires_grad_(True)
-print(f"fwd+bwd: waldo_b200 {ours:.3f} ms (d raw_output by k_conv3x3_fwd<16,5>, d weight by cuDNN), stock torch {ref:.3f} ms")
+print(f"fwd+bwd: waldo_b200 {ours:.3f} ms (d raw_output by k_conv3x3_fwd<16,5>, d weight by k_conv3x3_wgrad), stock torch {ref:.3f} ms")

@@ -125,6 +125,10 @@ class Conv3x3(C.Structure):
                 ("in", c_void_p), ("weight", c_void_p), ("out", c_void_p)]
 
 
+class Conv3x3Wgrad(C.Structure):
+    _fields_ = [("c", Conv3x3), ("dout", c_void_p), ("ctas", C.c_int), ("part", c_void_p), ("dweight", c_void_p)]
+
+
 # flags of Geom.flags (include/waldo_b200.h)
 F_RESTRICT_CTX, F_FILTER, F_WEIGHT_CLS, F_HAS_CLS, F_IS_OBJ, F_INCLUDE_SELF, F_USE_DISOCC, F_OCC_PAIRS = (1 << i for i in range(8))
 
@@ -137,12 +141,12 @@ STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwar
              "waldo_decode_bwd_t": DecodeBwd, "waldo_wif_fuse_fwd_t": WifFuseFwd, "waldo_wif_fuse_bwd_t": WifFuseBwd,
              "waldo_pack_input_t": PackInput, "waldo_warp_field_t": WarpField, "waldo_resize_t": Resize,
              "waldo_frames_u8_t": FramesU8, "waldo_blur_t": Blur, "waldo_layer_entropy_t": LayerEntropy,
-             "waldo_layer_entropy_bwd_t": LayerEntropyBwd, "waldo_conv3x3_t": Conv3x3}
+             "waldo_layer_entropy_bwd_t": LayerEntropyBwd, "waldo_conv3x3_t": Conv3x3, "waldo_conv3x3_wgrad_t": Conv3x3Wgrad}
 
 EXPORTS = ["waldo_last_error", "waldo_abi_version", "waldo_has_device_code", "waldo_launch_count", "waldo_tps_fwd", "waldo_tps_bwd",
            "waldo_invwarp_fwd", "waldo_invwarp_bwd", "waldo_occ_fwd", "waldo_occ_bwd", "waldo_decode_fwd",
            "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input", "waldo_warp_field_fwd", "waldo_resize_bilinear_fwd",
-           "waldo_frames_to_u8", "waldo_blur_fwd", "waldo_blur_bwd", "waldo_layer_entropy_fwd", "waldo_layer_entropy_bwd", "waldo_conv3x3_fwd"]
+           "waldo_frames_to_u8", "waldo_blur_fwd", "waldo_blur_bwd", "waldo_layer_entropy_fwd", "waldo_layer_entropy_bwd", "waldo_conv3x3_fwd", "waldo_conv3x3_wgrad"]
 
 _lock = threading.Lock()
 _lib = None
@@ -158,7 +162,7 @@ def _declare(lib):
                      ("waldo_invwarp_bwd", InvWarpBwd), ("waldo_decode_fwd", DecodeFwd), ("waldo_decode_bwd", DecodeBwd),
                      ("waldo_wif_fuse_fwd", WifFuseFwd), ("waldo_wif_fuse_bwd", WifFuseBwd), ("waldo_pack_input", PackInput), ("waldo_warp_field_fwd", WarpField),
                      ("waldo_resize_bilinear_fwd", Resize), ("waldo_frames_to_u8", FramesU8), ("waldo_blur_fwd", Blur), ("waldo_blur_bwd", Blur),
-                     ("waldo_layer_entropy_fwd", LayerEntropy), ("waldo_layer_entropy_bwd", LayerEntropyBwd), ("waldo_conv3x3_fwd", Conv3x3)):
+                     ("waldo_layer_entropy_fwd", LayerEntropy), ("waldo_layer_entropy_bwd", LayerEntropyBwd), ("waldo_conv3x3_fwd", Conv3x3), ("waldo_conv3x3_wgrad", Conv3x3Wgrad)):
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(st), c_void_p]
         fn.restype = C.c_int

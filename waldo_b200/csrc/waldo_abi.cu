@@ -412,4 +412,29 @@ int waldo_conv3x3_fwd(const waldo_conv3x3_t* a, waldo_stream_t st) {
   return 0;
 }
 
+int waldo_conv3x3_wgrad(const waldo_conv3x3_wgrad_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a && a->c.n >= 0 && a->c.H > 0 && a->c.W > 0, "conv3x3_wgrad: bad sizes");
+  WB_REQUIRE(a->c.Cin >= 1 && a->c.Cin <= 40, "conv3x3_wgrad: Cin=%d unsupported (1..40)", a->c.Cin);
+  WB_REQUIRE(a->c.Cout >= 1 && a->c.Cout <= 16, "conv3x3_wgrad: Cout=%d unsupported (1..16)", a->c.Cout);
+  WB_REQUIRE((a->c.Tc > 0) == (a->c.Tp > 0), "conv3x3_wgrad: Tc and Tp must both be set or both be 0");
+  if (a->c.Tc > 0) WB_REQUIRE(a->c.n % (a->c.Tc * a->c.Tp) == 0, "conv3x3_wgrad: n must be a multiple of Tc*Tp");
+  WB_REQUIRE(a->c.in && a->dout && a->part && a->dweight && a->ctas >= 1 && a->ctas <= 2 * 148, "conv3x3_wgrad: bad pointers / ctas");
+  WB_REQUIRE(a->c.W % 4 == 0 && ((uintptr_t)a->c.in & 15) == 0 && ((uintptr_t)a->dout & 15) == 0,
+             "conv3x3_wgrad: needs W %% 4 == 0 and 16-byte aligned in / dout");
+  const int Cp = (a->c.Cin + 7) & ~7;
+  const size_t smem = ((size_t)Cp * WB_CW_XS + (size_t)16 * WB_CW_YS) * sizeof(float);
+#ifdef WB_HOST_EMU
+#define WB_CW_GO(K) WB_LAUNCH(K, dim3(a->ctas), dim3(256), smem, st, *a)
+#else
+#define WB_CW_GO(K) do { cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); WB_LAUNCH(K, dim3(a->ctas), dim3(256), smem, st, *a); } while (0)
+#endif
+  if (Cp == 40) WB_CW_GO(k_conv3x3_wgrad<40>);
+  else WB_CW_GO(k_conv3x3_wgrad<0>);
+#undef WB_CW_GO
+  WB_LAUNCHED();
+  WB_LAUNCH(k_conv3x3_wgrad_final, dim3(wb_blocks((long long)a->c.Cout * a->c.Cin * 9, 256)), dim3(256), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
 }  // extern "C"

@@ -182,3 +182,123 @@ __global__ void __launch_bounds__(256, 2) k_conv3x3_fwd(waldo_conv3x3_t p) {
 #endif
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the same layer:  dW[co][ci][tap] = sum over images and pixels of dY[co][y][x] * X[ci][y + dy - 1][x + dx - 1].
+// As a GEMM: M = Cout = 16 (one M tile), N = 9 * Cin columns (ci, tap), K = all pixels of all images.  Persistent CTAs walk the
+// same 32 x 8 tiles as the forward: X tile + halo and the dY tile are staged by cp.async, each warp owns N tiles j = warp,
+// warp + 8, ... (8 columns = 8 consecutive input channels under one tap) and keeps their 16 x 8 accumulators in registers over
+// ALL tiles of the CTA; K advances 8 pixels of one tile row per MMA.  Plane strides = 4 (mod 32) floats: the A (dY) and B (X)
+// fragment loads of a warp each hit 32 banks.  Each CTA writes its partial dW once; k_conv3x3_wgrad_final adds the partials in
+// CTA order (deterministic).  TF32 products (both operands truncated by the tensor core), fp32 accumulation.
+#define WB_CW_XS (WB_CV_ROWS * WB_CV_PITCH_V + 12)   // 452: X plane stride
+#define WB_CW_YS (WB_CV_TH * WB_CV_TW + 4)          // 260: dY plane stride
+#define WB_CW_MAX_NT 6                               // N tiles per warp: 9 * 48 / 8 = 54 tiles over 8 warps -> at most 7; capped by Cin <= 40 here
+
+template <int CPT>
+__global__ void __launch_bounds__(256, 2) k_conv3x3_wgrad(waldo_conv3x3_wgrad_t p) {
+  WB_DYN_SMEM(smem);
+  const int Cin = p.c.Cin, Cout = p.c.Cout, H = p.c.H, W = p.c.W;
+  const int Cp = CPT > 0 ? CPT : ((Cin + 7) & ~7), NTt = 9 * (Cp / 8);
+  float* s_x = smem;                       // [Cp][452]
+  float* s_y = smem + Cp * WB_CW_XS;       // [16][260]
+  const int tid = wb_tid(), nthr = wb_nthr();
+  const int tiles_x = (W + WB_CV_TW - 1) / WB_CV_TW, tiles_y = (H + WB_CV_TH - 1) / WB_CV_TH, tpi = tiles_x * tiles_y;
+  const long long ntiles = (long long)p.c.n * tpi;
+  const size_t HW = (size_t)H * W;
+  float* part = p.part + (size_t)blockIdx.x * Cout * Cin * 9;
+#ifdef WB_HOST_EMU
+  for (int i = 0; i < Cout * Cin * 9; ++i) part[i] = 0.f;
+#else
+  const int lane = tid & 31, wp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+  float acc[WB_CW_MAX_NT][4];
+  WB_UNROLL for (int j = 0; j < WB_CW_MAX_NT; ++j) WB_UNROLL for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#endif
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int img = (int)(tile / tpi), tt = (int)(tile - (long long)img * tpi);
+    const int ty0 = (tt / tiles_x) * WB_CV_TH, tx0 = (tt % tiles_x) * WB_CV_TW;
+    const float* in = p.c.in + (size_t)wb_cv_src_image(p.c, img) * Cin * HW;
+    const float* dy = p.dout + (size_t)img * Cout * HW;
+    __syncthreads();   // the previous tile's MMAs are done
+    for (int id = tid; id < Cp * WB_CV_ROWS * 10; id += nthr) {   // X tile + halo, 16-byte chunks (W % 4 == 0)
+      const int ch = id / (WB_CV_ROWS * 10), rem = id - ch * (WB_CV_ROWS * 10), r = rem / 10, j4 = rem - r * 10;
+      const int gy = ty0 + r - 1, gx = tx0 - 4 + 4 * j4;
+      const bool ok = ch < Cin && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      float* dst = s_x + ch * WB_CW_XS + r * WB_CV_PITCH_V + 4 * j4;
+#ifdef WB_HOST_EMU
+      for (int e = 0; e < 4; ++e) dst[e] = ok ? wb_tf32_rz(in[(size_t)ch * HW + (size_t)gy * W + gx + e]) : 0.f;
+#else
+      wb_cp16z(dst, ok ? in + (size_t)ch * HW + (size_t)gy * W + gx : in, ok);
+#endif
+    }
+    for (int id = tid; id < 16 * WB_CV_TH * 8; id += nthr) {       // dY tile (16 planes: zeros beyond Cout), 16-byte chunks
+      const int co = id / (WB_CV_TH * 8), rem = id - co * (WB_CV_TH * 8), r = rem / 8, j4 = rem - r * 8;
+      const int gy = ty0 + r, gx = tx0 + 4 * j4;
+      const bool ok = co < Cout && gy < H && gx < W;
+      float* dst = s_y + co * WB_CW_YS + r * WB_CV_TW + 4 * j4;
+#ifdef WB_HOST_EMU
+      for (int e = 0; e < 4; ++e) dst[e] = ok ? wb_tf32_rz(dy[(size_t)co * HW + (size_t)gy * W + gx + e]) : 0.f;
+#else
+      wb_cp16z(dst, ok ? dy + (size_t)co * HW + (size_t)gy * W + gx : dy, ok);
+#endif
+    }
+#ifndef WB_HOST_EMU
+    wb_cp_commit();
+    wb_cp_wait<0>();
+#endif
+    __syncthreads();
+#ifdef WB_HOST_EMU
+    for (int co = 0; co < Cout; ++co)
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int tap = 0; tap < 9; ++tap) {
+          float a = 0.f;
+          for (int y = 0; y < WB_CV_TH; ++y)
+            for (int x = 0; x < WB_CV_TW; ++x)
+              a += s_y[co * WB_CW_YS + y * WB_CV_TW + x] * s_x[ci * WB_CW_XS + (y + tap / 3) * WB_CV_PITCH_V + x + tap % 3 + 3];
+          part[((size_t)co * Cin + ci) * 9 + tap] += a;
+        }
+#else
+#pragma unroll 1
+    for (int ks = 0; ks < WB_CV_TH * 4; ++ks) {   // 8 pixels of one tile row per step
+      const int y = ks >> 2, x0 = (ks & 3) * 8;
+      const float* ay = s_y + gid * WB_CW_YS + y * WB_CV_TW + x0 + tig;
+      unsigned a[4];
+      a[0] = __float_as_uint(ay[0]); a[1] = __float_as_uint(ay[8 * WB_CW_YS]);
+      a[2] = __float_as_uint(ay[4]); a[3] = __float_as_uint(ay[8 * WB_CW_YS + 4]);
+      WB_UNROLL for (int j = 0; j < WB_CW_MAX_NT; ++j) {
+        const int nt = wp + 8 * j;
+        if (nt < NTt) {
+          const int tap = nt / (Cp / 8), c0 = (nt - tap * (Cp / 8)) * 8, dyy = tap / 3, dxx = tap - dyy * 3;
+          const float* bx = s_x + (c0 + gid) * WB_CW_XS + (y + dyy) * WB_CV_PITCH_V + x0 + tig + dxx + 3;
+          const unsigned b0 = __float_as_uint(bx[0]), b1 = __float_as_uint(bx[4]);
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+        }
+      }
+    }
+#endif
+  }
+#ifndef WB_HOST_EMU
+  WB_UNROLL for (int j = 0; j < WB_CW_MAX_NT; ++j) {
+    const int nt = wp + 8 * j;
+    if (nt < NTt) {
+      const int tap = nt / (Cp / 8), c0 = (nt - tap * (Cp / 8)) * 8;
+      WB_UNROLL for (int e = 0; e < 4; ++e) {
+        const int co = gid + (e >> 1) * 8, ci = c0 + 2 * tig + (e & 1);
+        if (co < Cout && ci < Cin) part[((size_t)co * Cin + ci) * 9 + tap] = acc[j][e];
+      }
+    }
+  }
+#endif
+}
+
+// dW = sum of the CTA partials, in CTA order
+__global__ void __launch_bounds__(256) k_conv3x3_wgrad_final(waldo_conv3x3_wgrad_t p) {
+  const int n = p.c.Cout * p.c.Cin * 9;
+  for (int i = blockIdx.x * wb_nthr() + wb_tid(); i < n; i += gridDim.x * wb_nthr()) {
+    float acc = 0.f;
+    for (int c = 0; c < p.ctas; ++c) acc += p.part[(size_t)c * n + i];
+    p.dweight[i] = acc;
+  }
+}

@@ -697,7 +697,8 @@ class _Conv3x3(torch.autograd.Function):
     """conv3x3(stride 1, padding 1, no bias), models/modules/conv.py:9-11, TF32 products / fp32 accumulation.
     forward + backward-data on waldo_conv3x3_fwd (the backward-data of a stride-1 3x3 convolution is the same convolution with
     the weights flipped and transposed, and the image permute is undone by swapping Tc and Tp); the weight gradient -- a
-    reduction over all pixels of all images -- is left to torch (cuDNN)."""
+    reduction over all pixels of all images -- on waldo_conv3x3_wgrad for the shapes it covers (Cout <= 16, Cin <= 40,
+    W % 4 == 0; per-CTA partials added in CTA order: deterministic), else torch (cuDNN)."""
 
     @staticmethod
     def forward(ctx, x, weight, wif_permute):
@@ -734,8 +735,17 @@ class _Conv3x3(torch.autograd.Function):
             d_x = _conv3x3_launch(g, wt, n, wc.shape[0], H, W, Tp, Tc)            # Tc <-> Tp: the inverse image permute
             d_x = d_x.view(xc.shape)
         if ctx.needs_input_grad[1]:
-            x4 = xc.permute(0, 2, 1, 3, 4, 5).reshape(n, Cin, H, W) if perm else xc
-            d_w = torch.nn.grad.conv2d_weight(x4, wc.shape, g, padding=1)
+            Cout = wc.shape[0]
+            if Cout <= 16 and Cin <= 40 and W % 4 == 0 and xc.data_ptr() % 16 == 0 and g.data_ptr() % 16 == 0:
+                lib = L.load()
+                ctas = 2 * 148
+                part = torch.empty(ctas, Cout, Cin, 3, 3, device=xc.device, dtype=torch.float32)
+                d_w = torch.empty_like(wc)
+                a = L.Conv3x3Wgrad(L.Conv3x3(n, Cin, Cout, H, W, Tc, Tp, L.ptr(xc), None, None), L.ptr(g), ctas, L.ptr(part), L.ptr(d_w))
+                L.call(lib.waldo_conv3x3_wgrad, a, xc, "conv3x3_wgrad")
+            else:   # shapes the kernel does not cover: cuDNN
+                x4 = xc.permute(0, 2, 1, 3, 4, 5).reshape(n, Cin, H, W) if perm else xc
+                d_w = torch.nn.grad.conv2d_weight(x4, wc.shape, g, padding=1)
         return d_x, d_w, None
 
 
