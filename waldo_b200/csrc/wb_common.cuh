@@ -212,34 +212,42 @@ WB_DEV void wb_red(float* p, float v) {
                                 // 1.5e-8 of it, i.e. fp32-grade for the image gradients (addends <= 2 max|upstream|), with
                                 // 2^37 of it as the range of a sum and 2^36 of it as the range of one addend (intermediate
                                 // gradients reach 1e6 .. 1e8 x the upstream ones where the fused score `norm` is small)
-// raise the "gradients invalid" flag once (a plain store from every thread that gets here would hammer one address)
-WB_DEV void wb_det_flag(float* sc) {
-  if (reinterpret_cast<volatile float*>(sc)[3] == 0.f) sc[3] = 1.f;
+// The rare path of wb_red_fixed, NOT inlined (it is reached from ~1000 call sites of the deterministic kernels: inlined it grows
+// them by a third and costs 5 % through the instruction cache):
+//   * NaN / inf / beyond 2^62 units: raise the "gradients invalid" flag once (a plain store from every thread that gets here
+//     would hammer one address); k_det_convert turns a raised flag into NaN gradients, so the caller's NaN guard sees it;
+//   * a large addend, 2^52 .. 2^62 units (intermediate gradients reach 1e8 x the upstream ones where the fused score `norm`
+//     is ~1e-6: seed 1 of the benchmark inputs, profiles/r2/r2_notes.md): add with the old value returned and check that
+//     the 64-bit sum did not wrap.
+#ifdef WB_HOST_EMU
+static inline void wb_red_fixed_rare(unsigned long long* q, float* sc, float x) {
+#else
+static __device__ __noinline__ void wb_red_fixed_rare(unsigned long long* q, float* sc, float x) {
+#endif
+  bool bad = !(fabsf(x) < 4.6e18f);
+  if (!bad) {
+#ifdef WB_HOST_EMU
+    const long long iv = llrintf(x), old = (long long)*q;
+    *q += (unsigned long long)iv;
+    const long long nw = (long long)*q;
+#else
+    const long long iv = __float2ll_rn(x);
+    const long long old = (long long)atomicAdd(q, (unsigned long long)iv);
+    const long long nw = (long long)((unsigned long long)old + (unsigned long long)iv);
+#endif
+    bad = ((old ^ nw) & (iv ^ nw)) < 0;
+  }
+  if (bad && reinterpret_cast<volatile float*>(sc)[3] == 0.f) sc[3] = 1.f;
 }
 WB_DEV void wb_red_fixed(const float* base, int64_t* shadow, float* sc, float* p, float v) {
   const float x = v * __ldg(sc);
-  const float ax = fabsf(x);
-  // NaN / inf / beyond 2^62 units: flag it, never wrap silently.  k_det_convert turns a raised flag into NaN gradients, so the
-  // caller's NaN guard sees it
-  if (!(ax < 4.6e18f)) { wb_det_flag(sc); return; }
   unsigned long long* q = reinterpret_cast<unsigned long long*>(shadow + (p - base));
+  if (!(fabsf(x) < 4.5e15f)) { wb_red_fixed_rare(q, sc, x); return; }
+  // the usual case, up to 2^52 units (2^11 such addends cannot wrap the sum): fire and forget
 #ifdef WB_HOST_EMU
-  const long long iv = llrintf(x), old = (long long)*q;
-  *q += (unsigned long long)iv;
-  const long long nw = (long long)*q;
-  if (((old ^ nw) & (iv ^ nw)) < 0) wb_det_flag(sc);
+  *q += (unsigned long long)llrintf(x);
 #else
-  const long long iv = __float2ll_rn(x);
-  if (ax < 4.5e15f) {   // the usual case, up to 2^52 units (2^11 such addends cannot wrap the sum): fire and forget
-    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(q), "l"((unsigned long long)iv));
-  } else {
-    // a large addend, 2^52 .. 2^62 units (intermediate gradients reach 1e8 x the upstream ones where the fused score `norm`
-    // is ~1e-6: seed 1 of the benchmark inputs, profiles/r2/r2_notes.md): add with the old value returned and check that
-    // the 64-bit sum did not wrap
-    const long long old = (long long)atomicAdd(q, (unsigned long long)iv);
-    const long long nw = (long long)((unsigned long long)old + (unsigned long long)iv);
-    if (((old ^ nw) & (iv ^ nw)) < 0) wb_det_flag(sc);
-  }
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(q), "l"((unsigned long long)__float2ll_rn(x)));
 #endif
 }
 
