@@ -353,14 +353,14 @@ typedef struct {
 } waldo_layer_entropy_bwd_t;
 int waldo_layer_entropy_bwd(const waldo_layer_entropy_bwd_t*, waldo_stream_t);
 
-/* ------------------------------------------------------------------ f-1 (first layer)  the consumer of raw_output
- * models/modules/conv.py:9-11, :36, :54: UNet.to_emb = conv3x3(Cin -> Cout), stride 1, padding 1, no bias, as WIF.forward applies it
- * to raw_output (models/nets/wif.py:33-38).  TF32 tensor-core products, fp32 accumulation (what the reference's cuDNN convolution
+/* ------------------------------------------------------------------ f-1 (the two full-resolution layers)  the consumer of raw_output
+ * models/modules/conv.py:9-11, :36-37, :54, :63: UNet.to_emb = conv3x3(Cin -> 16) as WIF.forward applies it to raw_output
+ * (models/nets/wif.py:33-38) and UNet.from_emb = conv3x3(2 x 16 -> 4 | 5); stride 1, padding 1, no bias.  TF32 tensor-core products, fp32 accumulation (what the reference's cuDNN convolution
  * does on this GPU with torch's default allow_tf32).  The backward-data of the same layer is this entry point again, called with the
  * flipped, transposed weights (Cout <-> Cin) and Tc <-> Tp (the image permute is its own inverse with the two swapped). */
 typedef struct {
   int n;                      /* images */
-  int Cin, Cout;              /* Cin <= 48; Cout a multiple of 8, <= 48 */
+  int Cin, Cout;              /* Cin <= 48, Cout <= 48 */
   int H, W;
   int Tc, Tp;                 /* both > 0: output image (b, tp, tc) reads input image (b, tc, tp) -- the permute of wif.py:33 folded into
                                  the addressing (n = B*Tc*Tp); 0, 0: output image i reads input image i */

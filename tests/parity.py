@@ -684,7 +684,7 @@ def check_conv3x3(dev, seed=21):
         plain = wb.conv3x3(want_order.contiguous().to(dev), wgt.to(dev)).cpu().double()
         assert torch.equal(plain, got), "conv3x3: the permuted addressing and the plain one disagree"
     # gradients: d raw_output through the same kernel (flipped, transposed weights; Tc <-> Tp), d weight through torch
-    for (B, Tc, Tp, Cin, H, W, Cout) in ((1, 2, 2, 40, 12, 36, 16), (1, 3, 1, 16, 9, 20, 8), (2, 1, 2, 48, 8, 33, 16)):
+    for (B, Tc, Tp, Cin, H, W, Cout) in ((1, 2, 2, 40, 12, 36, 16), (1, 3, 1, 16, 9, 20, 8), (2, 1, 2, 48, 8, 33, 16), (1, 1, 2, 41, 8, 12, 16)):
         raw = torch.randn(B, Tc, Tp, Cin, H, W, generator=gen)
         wgt = torch.randn(Cout, Cin, 3, 3, generator=gen) / (3 * Cin ** 0.5)
         proj = torch.randn(B * Tp * Tc, Cout, H, W, generator=gen)
@@ -695,13 +695,19 @@ def check_conv3x3(dev, seed=21):
         for name, k, e in (("d raw_output", rd.grad, r64.grad), ("d weight", wd.grad, w64.grad)):
             err = float((k.detach().cpu().double() - e).abs().max()) / float(e.abs().max())
             assert err <= TOL_TF32, f"conv3x3 {name}: {err:.3e}"
-    try:   # the input gradient is a convolution with Cout = Cin: a multiple of 8 is required, and said so
-        x = torch.zeros(1, 3, 8, 8, device=dev).requires_grad_(True)
-        wb.conv3x3(x, torch.zeros(8, 3, 3, 3, device=dev)).sum().backward()
-    except NotImplementedError:
-        pass
-    else:
-        raise AssertionError("conv3x3: d input with Cin % 8 != 0 must raise")
+    # UNet.from_emb (conv.py:37, :63): 2 x 16 -> 5 channels at full resolution, forward and both gradients
+    x = torch.randn(3, 32, 10, 24, generator=gen)
+    wgt = torch.randn(5, 32, 3, 3, generator=gen) / (3 * 32 ** 0.5)
+    proj = torch.randn(3, 5, 10, 24, generator=gen)
+    xd, wd = x.clone().to(dev).requires_grad_(True), wgt.clone().to(dev).requires_grad_(True)
+    y = wb.conv3x3(xd, wd)
+    (y * proj.to(dev)).sum().backward()
+    x64, w64 = x.double().requires_grad_(True), wgt.double().requires_grad_(True)
+    y64 = F.conv2d(x64, w64, padding=1)
+    (y64 * proj.double()).sum().backward()
+    for name, k, e in (("from_emb", y, y64), ("from_emb d x", xd.grad, x64.grad), ("from_emb d weight", wd.grad, w64.grad)):
+        err = float((k.detach().cpu().double() - e.detach()).abs().max()) / float(e.abs().max())
+        assert err <= TOL_TF32, f"conv3x3 {name}: {err:.3e}"
 
 
 # ------------------------------------------------------------------------------------------------ f-4 output side

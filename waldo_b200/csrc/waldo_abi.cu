@@ -386,7 +386,7 @@ int waldo_layer_entropy_bwd(const waldo_layer_entropy_bwd_t* a, waldo_stream_t s
 int waldo_conv3x3_fwd(const waldo_conv3x3_t* a, waldo_stream_t st) {
   WB_REQUIRE(a && a->n >= 0 && a->H > 0 && a->W > 0, "conv3x3_fwd: bad sizes");
   WB_REQUIRE(a->Cin >= 1 && a->Cin <= WB_CV_MAX_CIN, "conv3x3_fwd: Cin=%d unsupported (1..%d)", a->Cin, WB_CV_MAX_CIN);
-  WB_REQUIRE(a->Cout >= 8 && a->Cout <= WB_CV_MAX_COUT && a->Cout % 8 == 0, "conv3x3_fwd: Cout=%d must be a multiple of 8, <= %d", a->Cout, WB_CV_MAX_COUT);
+  WB_REQUIRE(a->Cout >= 1 && a->Cout <= WB_CV_MAX_COUT, "conv3x3_fwd: Cout=%d unsupported (1..%d)", a->Cout, WB_CV_MAX_COUT);
   WB_REQUIRE((a->Tc > 0) == (a->Tp > 0), "conv3x3_fwd: Tc and Tp must both be set or both be 0");
   if (a->Tc > 0) WB_REQUIRE(a->n % (a->Tc * a->Tp) == 0, "conv3x3_fwd: n must be a multiple of Tc*Tp");
   WB_REQUIRE(a->in && a->weight && a->out && a->in != a->out, "conv3x3_fwd: null pointer");
@@ -405,6 +405,8 @@ int waldo_conv3x3_fwd(const waldo_conv3x3_t* a, waldo_stream_t st) {
   if (vec && Cp == 40 && a->Cout == 16) WB_CV_GO((k_conv3x3_fwd<40, 2, true>));        // WIF's to_emb: 3 + 20 + 17 channels -> 16
   else if (vec && Cp == 48 && a->Cout == 16) WB_CV_GO((k_conv3x3_fwd<48, 2, true>));   // ... with the disocc channel (41 -> 48)
   else if (vec && Cp == 16 && a->Cout == 40) WB_CV_GO((k_conv3x3_fwd<16, 5, true>));   // its backward-data: 16 -> 40 (flipped, transposed weights)
+  else if (vec && Cp == 32 && a->Cout <= 8) WB_CV_GO((k_conv3x3_fwd<32, 1, true>));    // UNet.from_emb: 2 x 16 -> 5 (4) channels
+  else if (vec && Cp == 8 && a->Cout == 32) WB_CV_GO((k_conv3x3_fwd<8, 4, true>));     // ... and its backward-data
   else if (vec) WB_CV_GO((k_conv3x3_fwd<0, 0, true>));
   else WB_CV_GO((k_conv3x3_fwd<0, 0, false>));
 #undef WB_CV_GO

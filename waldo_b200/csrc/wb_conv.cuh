@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, 2) k_conv3x3_fwd(waldo_conv3x3_t p) {
   constexpr int WB_CV_PITCH = VEC ? WB_CV_PITCH_V : WB_CV_PITCH_S, WB_CV_CH = WB_CV_ROWS * WB_CV_PITCH;
   constexpr int COL0 = VEC ? 3 : 0;            // staged column of pixel x under tap dx: x + dx + COL0
   const int Cin = p.Cin, Cout = p.Cout, H = p.H, W = p.W;
-  const int Cp = CPT > 0 ? CPT : ((Cin + 7) & ~7), WP = wb_cv_wpitch(Cout), NT = NTT > 0 ? NTT : Cout / 8;
+  const int Cp = CPT > 0 ? CPT : ((Cin + 7) & ~7), WP = wb_cv_wpitch(Cout), NT = NTT > 0 ? NTT : (Cout + 7) / 8;
   float* s_in = smem;                          // [Cp][10][36]
   float* s_w = smem + Cp * WB_CV_CH;           // [9][Cp][WP]
   const int tid = wb_tid(), nthr = wb_nthr();
@@ -174,8 +174,9 @@ __global__ void __launch_bounds__(256, 2) k_conv3x3_fwd(waldo_conv3x3_t p) {
           if (nt < NT) {
             const int x0 = tx0 + mt * 16 + gid, n0 = nt * 8 + 2 * tig;
             float* o = out + (size_t)n0 * HW + (size_t)y * W;
-            if (x0 < W) { o[x0] = acc[mt][nt][0]; o[HW + x0] = acc[mt][nt][1]; }
-            if (x0 + 8 < W) { o[x0 + 8] = acc[mt][nt][2]; o[HW + x0 + 8] = acc[mt][nt][3]; }
+            const bool c0ok = n0 < Cout, c1ok = n0 + 1 < Cout;   // (Cout need not be a multiple of 8: the staged weights beyond it are 0)
+            if (x0 < W) { if (c0ok) o[x0] = acc[mt][nt][0]; if (c1ok) o[HW + x0] = acc[mt][nt][1]; }
+            if (x0 + 8 < W) { if (c0ok) o[x0 + 8] = acc[mt][nt][2]; if (c1ok) o[HW + x0 + 8] = acc[mt][nt][3]; }
           }
         }
     }

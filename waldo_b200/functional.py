@@ -728,9 +728,6 @@ class _Conv3x3(torch.autograd.Function):
         g = _c(d_out)
         d_x = d_w = None
         if ctx.needs_input_grad[0]:
-            if Cin % 8 != 0:
-                raise NotImplementedError("waldo_b200.conv3x3: the input gradient needs Cin to be a multiple of 8 (it is the Cout of "
-                                          "the transposed convolution); pad the channels or detach the input")
             wt = wc.flip(2, 3).transpose(0, 1).contiguous()                       # (Cin, Cout, 3, 3)
             d_x = _conv3x3_launch(g, wt, n, wc.shape[0], H, W, Tp, Tc)            # Tc <-> Tp: the inverse image permute
             d_x = d_x.view(xc.shape)

@@ -385,5 +385,6 @@ def wif_to_emb(raw_output, weight):
 
 
 def conv3x3(x, weight):
-    """models/modules/conv.py:9-11 conv3x3 (stride 1, padding 1, no bias) on (n, Cin <= 48, H, W), Cout in {8, 16, 24, 32}."""
+    """models/modules/conv.py:9-11 conv3x3 (stride 1, padding 1, no bias) on (n, Cin <= 48, H, W), Cout <= 48 -- the UNet's two
+    full-resolution layers, `to_emb` and `from_emb` (conv.py:36-37); differentiable."""
     return Fn.conv3x3(x, weight)
