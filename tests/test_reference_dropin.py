@@ -103,6 +103,23 @@ def _run(dev, use_disocc):
         y_ours = wif_ours(res["ours"][5])
     assert tuple(y_ours.shape) == tuple(y_ref.shape)
     assert float((y_ours - y_ref).abs().max()) <= 1e-3      # random-init UNet amplifies the 1e-4 deviations of its input
+    # f-1: the UNet's two full-resolution convolutions swapped for waldo_b200.Conv3x3 (conv.py:36-37), same state dict.
+    # from_emb is zero-initialised in the reference (conv.py:49-50): give both nets the same random weights so that it counts.
+    import copy
+    torch.manual_seed(3)
+    wif_a = copy.deepcopy(wif_ref)
+    wif_a.unet.from_emb.weight.data.normal_(0, 0.05)
+    wif_b = copy.deepcopy(wif_a)
+    for name in ("to_emb", "from_emb"):
+        old = getattr(wif_b.unet, name)
+        new = wb.Conv3x3(old.in_channels, old.out_channels).to(dev)
+        new.load_state_dict(old.state_dict(), strict=True)
+        setattr(wif_b.unet, name, new)
+    with torch.no_grad():
+        y_a, y_b = wif_a(res["ref"][5]), wif_b(res["ref"][5])
+    scale = float(y_a.abs().max())
+    # TF32 products in two of the fourteen convolutions (tests/parity.py TOL_TF32 per layer; the layers between amplify)
+    assert float((y_a - y_b).abs().max()) <= 2e-2 * scale, f"WIF with waldo_b200.Conv3x3: {float((y_a - y_b).abs().max()) / scale:.3e}"
 
 
 @needs_ref

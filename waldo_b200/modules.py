@@ -388,3 +388,20 @@ def conv3x3(x, weight):
     """models/modules/conv.py:9-11 conv3x3 (stride 1, padding 1, no bias) on (n, Cin <= 48, H, W), Cout <= 48 -- the UNet's two
     full-resolution layers, `to_emb` and `from_emb` (conv.py:36-37); differentiable."""
     return Fn.conv3x3(x, weight)
+
+
+class Conv3x3(nn.Module):
+    """Drop-in for `conv3x3(in_planes, out_planes)` at stride 1 (models/modules/conv.py:9-11: nn.Conv2d(kernel_size=3, padding=1,
+    bias=False)): same parameter name and shape (`weight`, (out, in, 3, 3)) -- state dicts are interchangeable --, same default
+    initialisation; forward and both gradients on waldo_conv3x3_fwd / waldo_conv3x3_wgrad."""
+
+    def __init__(self, in_planes, out_planes):
+        super().__init__()
+        if in_planes > 48 or out_planes > 48:
+            raise NotImplementedError("waldo_b200.Conv3x3: up to 48 input and 48 output channels are compiled")
+        ref = nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=1, padding=1, bias=False)   # the reference's initialisation
+        self.weight = nn.Parameter(ref.weight.detach().clone())
+        self.in_channels, self.out_channels = in_planes, out_planes
+
+    def forward(self, x):
+        return Fn.conv3x3(x, self.weight)
