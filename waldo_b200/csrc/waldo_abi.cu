@@ -210,7 +210,7 @@ int waldo_invwarp_bwd(const waldo_invwarp_bwd_t* a, waldo_stream_t st) {
   const int m = a->niter + 1, PP = (a->Ht + 2 * m) * (a->Wt + 2 * m), P = a->Ht * a->Wt;
   const dim3 gpp(wb_blocks(PP, 256, 512), a->n), gp(wb_blocks(P, 256, 512), a->n), gs(wb_blocks(a->Hs * a->Ws, 256, 512), a->n);
   const dim3 gband((a->Ht + 2 * m + WB_INV_ROWS - 1) / WB_INV_ROWS, a->n);
-  WB_LAUNCH(k_invb_init, gpp, dim3(256), 0, st, k); WB_LAUNCHED();
+  WB_LAUNCH(k_invb_init, gband, dim3(256), 0, st, k); WB_LAUNCHED();
   if ((long long)a->Hs * a->Ws * 4 <= (long long)a->Ht * a->Wt) { WB_LAUNCH(k_invb_levels_fused, dim3(a->n), dim3(512), 0, st, k); WB_LAUNCHED(); }
   else
     for (int lv = a->niter - 1; lv >= 0; --lv) { WB_LAUNCH(k_invb_level, gband, dim3(256), 0, st, k, lv); WB_LAUNCHED(); }

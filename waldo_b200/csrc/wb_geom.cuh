@@ -568,30 +568,31 @@ WB_DEV WbInvBItem wb_invb_item(const WbInvBwdArgs& a, int item, int P, int PP) {
   r.dout = a.dout + (size_t)item * P * 2;
   return r;
 }
-// own gradient of every padded cell + 1/sum-of-weights of the filled ones
+// own gradient of every padded cell + 1/sum-of-weights of the filled ones.  grid = (bands of WB_INV_ROWS padded rows, n): a CTA
+// walks only the cells of its band inside the hit cells' bounding box grown by niter -- the level kernels and the handoff never
+// read gx / gy / isw outside it (a level-lv cell lies within lv of a hit cell and reads neighbours one further out).
 __global__ void __launch_bounds__(256) k_invb_init(WbInvBwdArgs a) {
   WB_INV_GEOM;
   const WbInvBItem it = wb_invb_item(a, blockIdx.y, P, PP);
   float g[9];
   WB_UNROLL for (int i = 0; i < 9; ++i) g[i] = __ldg(a.gauss + i);
-  for (int c = blockIdx.x * wb_nthr() + wb_tid(); c < PP; c += gridDim.x * wb_nthr()) {
-    int y = c / Wp, x = c - y * Wp;
+  const WbInvBand band = wb_inv_band(it.bbox, a.niter, Hp, Wp);
+  for (int i = wb_tid(); i < band.cells; i += wb_nthr()) {
+    const int y = band.y0 + i / band.w, x = band.x0 + i % band.w, c = y * Wp + x;
     float ox = 0.f, oy = 0.f, sw = 0.f;
-    if (!wb_inv_outside(it.bbox, x, y, a.niter)) {
-      int Y = y - m, X = x - m;
-      const int lv = it.level[c];
-      if (Y >= 0 && Y < Ht && X >= 0 && X < Wt && lv != 255 && it.eroded[c] == 0) {
-        ox = it.dout[2 * (Y * Wt + X)] * 2.f / (float)Wt;
-        oy = it.dout[2 * (Y * Wt + X) + 1] * 2.f / (float)Ht;
-      }
-      if (lv != 255 && lv > 0) {
-        WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
-          WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
-            int yy = y + dy, xx = x + dx;
-            if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
-            if (wb_level_known_before(it.level[yy * Wp + xx], lv)) sw += g[(dy + 1) * 3 + dx + 1];
-          }
-      }
+    const int Y = y - m, X = x - m;
+    const int lv = it.level[c];
+    if (Y >= 0 && Y < Ht && X >= 0 && X < Wt && lv != 255 && it.eroded[c] == 0) {
+      ox = it.dout[2 * (Y * Wt + X)] * 2.f / (float)Wt;
+      oy = it.dout[2 * (Y * Wt + X) + 1] * 2.f / (float)Ht;
+    }
+    if (lv != 255 && lv > 0) {
+      WB_UNROLL for (int dy = -1; dy <= 1; ++dy)
+        WB_UNROLL for (int dx = -1; dx <= 1; ++dx) {
+          int yy = y + dy, xx = x + dx;
+          if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
+          if (wb_level_known_before(it.level[yy * Wp + xx], lv)) sw += g[(dy + 1) * 3 + dx + 1];
+        }
     }
     it.gx[c] = ox; it.gy[c] = oy;
     it.isw[c] = sw > 0.f ? 1.f / sw : 0.f;
