@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "waldo_b200", "libwaldo_b200.so")
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-COLS = ["LDG.E.128", "LDG.E.64", "LDG.E", "STG.E.128", "STG.E.64", "STG.E", "REDG", "RED.E.ADD.64", "ATOMG", "LDGSTS", "LDS", "STS", "ATOMS", "SHFL", "REDUX", "BAR", "MUFU"]
+COLS = ["LDG.E.128", "LDG.E.64", "LDG.E", "STG.E.128", "STG.E.64", "STG.E", "REDG", "RED.E.ADD.64", "ATOMG", "LDGSTS", "UBLKCP", "SYNCS", "HMMA", "LDS", "STS", "ATOMS", "SHFL", "REDUX", "BAR", "MUFU"]
 per = collections.OrderedDict()
 cur = None
 for line in txt.splitlines():
@@ -32,7 +32,7 @@ for line in txt.splitlines():
         elif op.startswith("REDG") or op.startswith("RED."):
             c["RED.E.ADD.64" if ".64" in op else "REDG"] += 1
         else:
-            for k in ("ATOMG", "LDGSTS", "LDS", "STS", "ATOMS", "SHFL", "REDUX", "BAR", "MUFU"):
+            for k in ("ATOMG", "LDGSTS", "UBLKCP", "SYNCS", "HMMA", "LDS", "STS", "ATOMS", "SHFL", "REDUX", "BAR", "MUFU"):
                 if op.startswith(k):
                     c[k] += 1
                     break
@@ -56,5 +56,6 @@ for name, c in sorted(per.items(), key=lambda kv: -kv[1]["total"]):
     print(f"| `{short(name)}` | {c['total']} | " + " | ".join(str(c[k]) if c[k] else "" for k in COLS) + " |")
     tot.update(c)
 print(f"| **all {len(per)} kernels** | {tot['total']} | " + " | ".join(str(tot[k]) for k in COLS) + " |")
-print("\nNo `UTMALDG` / `UTMASTG` / `UTCMMA` / `SYNCS` (TMA, tcgen05, mbarrier) in this library: "
-      + str(sum(len(re.findall(k, txt)) for k in ("UTMALDG", "UTMASTG", "UTCMMA", "SYNCS"))) + " occurrences.")
+print("\nTMA bulk copies (`UBLKCP`) with transaction barriers (`SYNCS`) and warp-level tensor-core MMAs (`HMMA`, here TF32 m16n8k8) are in the "
+      "convolution kernels of f-1; tensor-map TMA (`UTMALDG` / `UTMASTG`) and tcgen05 (`UTCMMA`) occurrences: "
+      + str(sum(len(re.findall(k, txt)) for k in ("UTMALDG", "UTMASTG", "UTCMMA"))) + ".")

@@ -313,6 +313,27 @@ WB_DEV void wb_cp16z(float* smem_dst, const float* gsrc, bool valid) {
 WB_DEV void wb_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> WB_DEV void wb_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + transaction barrier (mbarrier, SASS SYNCS): a contiguous run of global memory
+// lands in shared memory without passing through the load/store pipe of the SM; completion is counted in bytes on an mbarrier.
+WB_DEV unsigned wb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+WB_DEV void wb_mbar_init(unsigned long long* bar, int arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(wb_smem_addr(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+WB_DEV void wb_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {   // one arrival + the number of bytes the copies will deliver
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(wb_smem_addr(bar)), "r"(bytes) : "memory");
+}
+WB_DEV void wb_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile("{\n.reg .pred P1;\nWB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra WB_DONE;\nbra WB_WAIT;\nWB_DONE:\n}\n"
+               ::"r"(wb_smem_addr(bar)), "r"(parity) : "memory");
+}
+// `bytes` (a multiple of 16) from 16-byte aligned global memory to 16-byte aligned shared memory
+WB_DEV void wb_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(wb_smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(wb_smem_addr(bar)) : "memory");
+}
+WB_DEV void wb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // L1 prefetch hint (no register, no dependency): used to pull the NEXT context's low-res flow cells while the current
 // context is processed
 WB_DEV void wb_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }

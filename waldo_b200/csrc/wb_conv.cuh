@@ -8,8 +8,9 @@
 // K = 9 * Cin.  The (b, tc, tp) -> (b, tp, tc) permute of wif.py:33 is folded into the addressing (no 2.7 GB copy).
 //
 // CTA = 256 threads = 8 warps, output tile 32 x 8 pixels; warp w owns tile row w = two 16-pixel M tiles x Cout / 8 N tiles.
-// Shared memory: the input tile + halo, copied as is by cp.async (the tensor core ignores the low 13 mantissa bits of an fp32
-// pattern: round toward zero; the weights are rounded to nearest once, when staged), [Cin padded to 8][10 rows][36 floats] (channel stride 360 = 8 mod 32:
+// Shared memory: the input tile + halo, copied as is -- by TMA bulk copies (cp.async.bulk + mbarrier: one copy per (channel, row),
+// no load/store-pipe instruction per element) when the rows are 16-byte aligned, else by cp.async -- (the tensor core ignores the
+// low 13 mantissa bits of an fp32 pattern: round toward zero; the weights are rounded to nearest once, when staged), [Cin padded to 8][10 rows][36 floats] (channel stride 360 = 8 mod 32:
 // the four A-fragment loads of a warp each hit 32 different banks), and all weights [tap][cin][Cout pitch 24 | 40] (the two
 // B-fragment loads likewise).  Persistent CTAs: the weights are staged once per CTA.
 #pragma once
@@ -25,6 +26,9 @@
 #define WB_CV_PITCH_V 44
 #define WB_CV_PITCH_S 36
 #define WB_CV_MAX_CIN 48
+#ifndef WB_CV_TMA
+#define WB_CV_TMA 1   // 16-byte-aligned tiles are staged by TMA bulk copies + an mbarrier instead of per-thread cp.async
+#endif
 #define WB_CV_MAX_COUT 48
 
 WB_DEV float wb_tf32(float v) {   // round to nearest, ties away from zero, 10-bit mantissa (cvt.rna.tf32.f32)
@@ -77,6 +81,11 @@ __global__ void __launch_bounds__(256, 2) k_conv3x3_fwd(waldo_conv3x3_t p) {
   const int tiles_x = (W + WB_CV_TW - 1) / WB_CV_TW, tiles_y = (H + WB_CV_TH - 1) / WB_CV_TH;
   const long long ntiles = (long long)p.n * tiles_x * tiles_y;
   const size_t HW = (size_t)H * W;
+#if !defined(WB_HOST_EMU) && WB_CV_TMA
+  __shared__ __align__(8) unsigned long long s_bar;
+  unsigned phase = 0u;
+  if (VEC && tid == 0) wb_mbar_init(&s_bar, 1);
+#endif
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int img = (int)(tile / (tiles_x * tiles_y)), tt = (int)(tile - (long long)img * tiles_x * tiles_y);
     const int ty0 = (tt / tiles_x) * WB_CV_TH, tx0 = (tt % tiles_x) * WB_CV_TW;
@@ -84,6 +93,32 @@ __global__ void __launch_bounds__(256, 2) k_conv3x3_fwd(waldo_conv3x3_t p) {
     float* out = p.out + (size_t)img * Cout * HW;
     __syncthreads();   // weights staged / the previous tile's MMAs done
     if (VEC) {
+#if !defined(WB_HOST_EMU) && WB_CV_TMA
+      // staging by TMA bulk copies: one copy per (channel, row) of the in-image part of the 40-float row (every offset and length is
+      // a multiple of 16 bytes: W % 4 == 0), counted in bytes on an mbarrier; the out-of-image chunks / rows are zeroed by hand.
+      // No load/store-pipe instruction per element: the staging of this kernel competes with its fragment loads for that pipe.
+      {
+        const int gx_lo = max(tx0 - 4, 0), gx_hi = min(tx0 + WB_CV_TW + 4, W);
+        const unsigned rowbytes = (unsigned)(gx_hi - gx_lo) * 4u;
+        const int d_lo = gx_lo - (tx0 - 4);                       // first in-image float of the staged row
+        const int r_lo = max(0, 1 - ty0), r_hi = min(WB_CV_ROWS, H - ty0 + 1);   // rows r with 0 <= ty0 + r - 1 < H
+        wb_fence_async_smem();                                     // the previous tile's reads (and zero stores) before the async writes
+        if (tid == 0) wb_mbar_expect_tx(&s_bar, (unsigned)(Cin * (r_hi - r_lo)) * rowbytes);
+        for (int pr = tid; pr < Cp * WB_CV_ROWS; pr += nthr) {
+          const int ch = pr / WB_CV_ROWS, r = pr - ch * WB_CV_ROWS;
+          float* dst = s_in + ch * WB_CV_CH + r * WB_CV_PITCH;
+          if (ch < Cin && r >= r_lo && r < r_hi) {
+            wb_bulk_g2s(dst + d_lo, in + (size_t)ch * HW + (size_t)(ty0 + r - 1) * W + gx_lo, rowbytes, &s_bar);
+            for (int c = 0; c < d_lo; ++c) dst[c] = 0.f;                                   // left of the image
+            for (int c = d_lo + (gx_hi - gx_lo); c < WB_CV_TW + 8; ++c) dst[c] = 0.f;      // right of the image
+          } else {
+            for (int c = 0; c < WB_CV_TW + 8; ++c) dst[c] = 0.f;                           // padding channel / row outside the image
+          }
+        }
+        wb_mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+      }
+#else
       // staging: 16-byte chunks, 10 per (channel, row); a chunk is wholly inside or wholly outside the image (W % 4 == 0)
       for (int id = tid; id < Cp * WB_CV_ROWS * 10; id += nthr) {
         const int ch = id / (WB_CV_ROWS * 10), rem = id - ch * (WB_CV_ROWS * 10), r = rem / 10, j4 = rem - r * 10;
@@ -96,6 +131,7 @@ __global__ void __launch_bounds__(256, 2) k_conv3x3_fwd(waldo_conv3x3_t p) {
         wb_cp16z(dst, ok ? in + (size_t)ch * HW + (size_t)gy * W + gx : in, ok);
 #endif
       }
+#endif
     } else {
     // staging: one (channel, row) of 34 floats per warp and trip (lanes = columns; lanes 0, 1 also take columns 32, 33)
     {
@@ -208,6 +244,11 @@ __global__ void __launch_bounds__(256, 2) k_conv3x3_wgrad(waldo_conv3x3_wgrad_t 
   const long long ntiles = (long long)p.c.n * tpi;
   const size_t HW = (size_t)H * W;
   float* part = p.part + (size_t)blockIdx.x * Cout * Cin * 9;
+#if !defined(WB_HOST_EMU) && WB_CV_TMA
+  __shared__ __align__(8) unsigned long long s_bar;
+  unsigned phase = 0u;
+  if (tid == 0) wb_mbar_init(&s_bar, 1);
+#endif
 #ifdef WB_HOST_EMU
   for (int i = 0; i < Cout * Cin * 9; ++i) part[i] = 0.f;
 #else
@@ -221,6 +262,42 @@ __global__ void __launch_bounds__(256, 2) k_conv3x3_wgrad(waldo_conv3x3_wgrad_t 
     const float* in = p.c.in + (size_t)wb_cv_src_image(p.c, img) * Cin * HW;
     const float* dy = p.dout + (size_t)img * Cout * HW;
     __syncthreads();   // the previous tile's MMAs are done
+#if !defined(WB_HOST_EMU) && WB_CV_TMA
+    {   // X tile + halo and the dY tile by TMA bulk copies, one per (plane, row), counted on one mbarrier (see k_conv3x3_fwd)
+      const int gx_lo = max(tx0 - 4, 0), gx_hi = min(tx0 + WB_CV_TW + 4, W);
+      const unsigned xbytes = (unsigned)(gx_hi - gx_lo) * 4u;
+      const int d_lo = gx_lo - (tx0 - 4);
+      const int r_lo = max(0, 1 - ty0), r_hi = min(WB_CV_ROWS, H - ty0 + 1);
+      const int yw = min(WB_CV_TW, W - tx0), yr = min(WB_CV_TH, H - ty0);   // in-image part of the dY tile
+      const unsigned ybytes = (unsigned)yw * 4u;
+      wb_fence_async_smem();
+      if (tid == 0) wb_mbar_expect_tx(&s_bar, (unsigned)(Cin * (r_hi - r_lo)) * xbytes + (unsigned)(Cout * yr) * ybytes);
+      for (int pr = tid; pr < Cp * WB_CV_ROWS; pr += nthr) {
+        const int ch = pr / WB_CV_ROWS, r = pr - ch * WB_CV_ROWS;
+        float* dst = s_x + ch * WB_CW_XS + r * WB_CV_PITCH_V;
+        if (ch < Cin && r >= r_lo && r < r_hi) {
+          wb_bulk_g2s(dst + d_lo, in + (size_t)ch * HW + (size_t)(ty0 + r - 1) * W + gx_lo, xbytes, &s_bar);
+          for (int c = 0; c < d_lo; ++c) dst[c] = 0.f;
+          for (int c = d_lo + (gx_hi - gx_lo); c < WB_CV_TW + 8; ++c) dst[c] = 0.f;
+        } else {
+          for (int c = 0; c < WB_CV_TW + 8; ++c) dst[c] = 0.f;
+        }
+      }
+      for (int pr = tid; pr < 16 * WB_CV_TH; pr += nthr) {
+        const int co = pr / WB_CV_TH, r = pr - co * WB_CV_TH;
+        float* dst = s_y + co * WB_CW_YS + r * WB_CV_TW;
+        if (co < Cout && r < yr) {
+          wb_bulk_g2s(dst, dy + (size_t)co * HW + (size_t)(ty0 + r) * W + tx0, ybytes, &s_bar);
+          for (int c = yw; c < WB_CV_TW; ++c) dst[c] = 0.f;
+        } else {
+          for (int c = 0; c < WB_CV_TW; ++c) dst[c] = 0.f;
+        }
+      }
+      wb_mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+    }
+    __syncthreads();
+#else
     for (int id = tid; id < Cp * WB_CV_ROWS * 10; id += nthr) {   // X tile + halo, 16-byte chunks (W % 4 == 0)
       const int ch = id / (WB_CV_ROWS * 10), rem = id - ch * (WB_CV_ROWS * 10), r = rem / 10, j4 = rem - r * 10;
       const int gy = ty0 + r - 1, gx = tx0 - 4 + 4 * j4;
@@ -248,6 +325,7 @@ __global__ void __launch_bounds__(256, 2) k_conv3x3_wgrad(waldo_conv3x3_wgrad_t 
     wb_cp_wait<0>();
 #endif
     __syncthreads();
+#endif
 #ifdef WB_HOST_EMU
     for (int co = 0; co < Cout; ++co)
       for (int ci = 0; ci < Cin; ++ci)
