@@ -16,9 +16,13 @@ wb.set_deterministic(det)
 out = []
 for i in range(40):
     r.step(r.resident)
+    if os.environ.get("GC_EACH_STEP") == "1":
+        import gc
+        gc.collect()
     ms = torch.cuda.memory_stats()
-    out.append((round(torch.cuda.memory_reserved() / 2**30, 2), ms.get("num_device_alloc", 0)))
+    out.append((round(torch.cuda.memory_reserved() / 2**30, 2), ms.get("num_device_alloc", 0), round(torch.cuda.memory_allocated() / 2**30, 2)))
 torch.cuda.synchronize()
 print("det", det, "overlap_bg", M.OVERLAP_BG, "prefill", wb.functional.PREFILL)
 print(" reserved GiB:", [o[0] for o in out[::3]])
 print(" device allocs:", [o[1] for o in out[::3]])
+print(" allocated GiB (live tensors at the end of the step):", [o[2] for o in out[::3]])

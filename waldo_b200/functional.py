@@ -512,6 +512,14 @@ class _Decode(torch.autograd.Function):
         if det:
             global LAST_DET_SCALE
             LAST_DET_SCALE = det_scale
+        if det:
+            # The two background-grid gradients are consumed on the side stream of Warper.forward's background chain, and autograd
+            # marks a tensor that crosses streams with record_stream.  As views of the deterministic arena that mark would sit
+            # on the whole 3.2 GB block: its release would wait until the host has seen the side stream pass, and with the host
+            # many steps ahead of the GPU every step took a fresh arena (reserved memory 20 -> 72 GiB over 25 steps, the
+            # allocations inside the timed steps; profiles/r2/r2_notes.md).  Two 10 MB copies keep the arena out of it.
+            d_tgb = d_tgb.clone() if d_tgb is not None else None
+            d_sgb = d_sgb.clone() if d_sgb is not None else None
         if d_oa is not None:
             d_oa = d_oa.view(ctx.shapes["obj_alpha"])
         if d_ba is not None:
