@@ -678,7 +678,7 @@ def main():
             try:
                 c2, s2 = workload_cfg(name)
                 r2 = Runner(args, c2, s2, rank, local_rank, world, storage=sto)
-                ms2, _, _ = r2.measure(max(3, args.steps // 2), 3, profile=False)
+                ms2, _, _ = r2.measure(max(5, args.steps), 3, profile=False)   # (steps of 1.4 - 3 ms: the full count, for a stable mean)
                 if sto == "bf16":
                     name, s2["label"] = name + "_bf16", s2["label"] + ", bf16 storage / fp32 arithmetic (tolerance: tests/parity.py TOL_BF16)"
                 others[name] = dict(r2.summary(ms2), workload=s2["label"],
