@@ -344,10 +344,12 @@ class Runner:
         self.resident["input"] = wb.pack_input(self.pinned["rgb"].to(dev), self.pinned["label"].to(dev), cfg.num_lyt, dtype=self.st_dtype)
         del host
         self.grad_buf = None
-        if world > 1 and backward:   # the trainable net's gradients (WIF-sized), exchanged as DDP would: one flat all-reduce per step
+        if world > 1 and backward and not args.no_exchange:   # the trainable net's gradients (WIF-sized), exchanged as DDP would: one flat all-reduce per step
             wif_like = torch.nn.Parameter(torch.zeros(WIF_GRAD_ELEMS, device=dev))
             wif_like.grad = torch.zeros_like(wif_like)
-            self.grad_buf = sharding.FlatGradReducer([wif_like])
+            # (if init_nccl capped the default group's CTAs: deterministic mode exchanges before the backward starts, on a
+            #  communicator of NCCL's own width)
+            self.grad_buf = sharding.FlatGradReducer([wif_like], group=sharding.full_width_group() if deterministic else None)
         self.loss_host = torch.zeros(1).pin_memory()
         # upstream gradients as a downstream consumer (WIF / losses) would supply them: fixed seeded tensors, so that no
         # loss kernel of torch sits inside the timed region and the backward reads d output, d flow and d raw_output
@@ -416,7 +418,9 @@ class Runner:
                 print("[step times]", " ".join(f"{b - a:.2f}" for a, b in zip([0.0] + ts[:-1], ts)), file=sys.stderr, flush=True)
         finally:
             gc.enable()
-        return self.sharding.max_over_ranks([e0.elapsed_time(e1)], device=self.dev)[0] / steps
+        mine = e0.elapsed_time(e1)
+        self.last_per_rank_ms = [v / steps for v in self.sharding.gather_over_ranks(mine, device=self.dev)]
+        return self.sharding.max_over_ranks([mine], device=self.dev)[0] / steps
 
     def measure(self, steps, warmup, profile=True):
         """(ms per step, launches of this library in the timed region, per-stage event times)."""
@@ -568,6 +572,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE workloads and the deterministic-mode leg")
     ap.add_argument("--no-input-grad", action="store_true", help="experiment: do not request d input")
+    ap.add_argument("--no-exchange", action="store_true", help="experiment (N > 1): no gradient all-reduce, so that ms_per_step_per_rank shows the GPUs' own spread")
     ap.add_argument("--no-graph", action="store_true", help="inference workloads: eager launches instead of CUDA-graph replay")
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"],
                     help="bf16: input / alpha / raw_output / output stored as bf16, fp32 arithmetic (forward / inference workloads only)")
@@ -590,7 +595,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from waldo_b200 import sharding
+        sharding.init_nccl(dev)
     load_peak()
     r = Runner(args, cfg, spec, rank, local_rank, world, deterministic=args.deterministic, storage=args.storage)
     B, T, Tc, Tp, backward = r.B, r.T, r.Tc, r.Tp, r.backward
@@ -609,6 +615,7 @@ def main():
     # pair around each HD kernel (the roofline figures); both numbers are reported.
     clocks.mark_begin()
     ms_step, launches, _ = r.measure(args.steps, 0, profile=False)
+    per_rank_ms = list(r.last_per_rank_ms)   # the headline region's device time on every rank (ms_step is their max)
     ms_instr, prof = ms_step, {}
     if r.graphed is None:
         ms_instr, _, prof = r.measure(args.steps, 0)
@@ -744,6 +751,8 @@ def main():
                          "stages_ms": {k: round(v, 4) for k, v in prof.items()}, "kernel_timing": kernel_timing,
                          "ms_per_step_instrumented": ms_instr},
         }
+        if world > 1:
+            line["ms_per_step_per_rank"] = [round(v, 4) for v in per_rank_ms]
         if e2e:
             line["e2e"] = e2e
         if det_leg:

@@ -57,6 +57,16 @@ def _worker(rank, world, port, out):
         for i, p in enumerate(params):
             want = sum(per_rank[r][i] for r in range(world)) / world
             assert torch.allclose(p.grad, want, atol=1e-6, rtol=1e-6), ("async", i)
+        # --- gradients of the wire dtype are views of the flat buffer (nothing to pack / unpack); a replaced .grad falls back to copies
+        assert all(red._is_view(p, o) for p, o in zip(red.params, red.offsets))
+        for p, g in zip(params, per_rank[rank]):
+            p.grad.copy_(g)                       # what autograd's in-place accumulation does
+        params[1].grad = per_rank[rank][1].clone()   # ... and a gradient tensor the reducer has not seen
+        assert not red._is_view(params[1], red.offsets[1]) and red._is_view(params[0], red.offsets[0])
+        red.reduce()
+        for i, p in enumerate(params):
+            want = sum(per_rank[r][i] for r in range(world)) / world
+            assert torch.allclose(p.grad, want, atol=1e-6, rtol=1e-6), ("views", i)
         # --- a parameter unused on THIS rank still receives the averaged gradient (replicas must not diverge)
         q = [torch.nn.Parameter(torch.zeros(4))]
         q[0].grad = torch.full((4,), 2.0) if rank == 0 else None
@@ -67,6 +77,7 @@ def _worker(rank, world, port, out):
         assert sharding.any_nan(torch.tensor(False)) is False
         assert sharding.max_over_ranks([1.0 + rank, 5.0 - rank]) == [2.0, 5.0]
         assert sharding.whole_job_rate(8, 1000.0) == 16.0
+        assert sharding.gather_over_ranks(3.0 + rank) == [3.0, 4.0]
         out.put((rank, "ok"))
     except Exception as e:  # surface the failure in the parent
         out.put((rank, repr(e)))
