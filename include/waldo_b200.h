@@ -353,6 +353,39 @@ typedef struct {
 } waldo_layer_entropy_bwd_t;
 int waldo_layer_entropy_bwd(const waldo_layer_entropy_bwd_t*, waldo_stream_t);
 
+/* models/synthesizer.py:965-979 (`cell_dis`, `center_dis` of LVD training): per low-res pixel g (warper.src_grid),
+ *   cell_min   = min_o ( (mov + eps) (1 - fg) * sum_{cells k of object o} d(g, c_{o,k}) )     c = mean of the cell's 4 control points
+ *   center_min = min_o ( mov * d(g, m_o) )                                                    m = mean of all control points of o
+ *   d(g, c) = |g|^2 + |c|^2 - 2 c.g   (the reference's expanded form)
+ * The reference's two scalars are the means of the two maps.  The (B, T, No, cells, H, W) distance tensor is never stored. */
+typedef struct {
+  int n;                      /* B*T, <= 65535 */
+  int No, ho, wo;             /* objects (<= 32), control-point lattice of an object (opt.obj_shape), No (ho-1)(wo-1) <= 1024 */
+  int HW;
+  float eps;                  /* opt.cell_dis_eps */
+  const float* mov;           /* (n, HW) mov_obj_mask (blurred) */
+  const float* fg;            /* (n, HW) fg_mask (blurred) */
+  const float* pose;          /* (n, No, ho*wo, 2) obj_pose */
+  const float* grid;          /* (HW, 2) */
+  float* cell_min;            /* out (n, HW) */
+  float* center_min;          /* out (n, HW) */
+  uint8_t* cell_arg;          /* out (n, HW) argmin object of cell_min (first index on ties), read by the backward */
+  uint8_t* center_arg;       /* out (n, HW) */
+} waldo_pose_dis_t;
+int waldo_pose_dis_fwd(const waldo_pose_dis_t*, waldo_stream_t);
+
+typedef struct {
+  waldo_pose_dis_t f;         /* inputs and the two argmin maps as in the forward; cell_min / center_min are not read */
+  const float* d_cell;        /* (n, HW) or NULL (= zero) */
+  const float* d_center;      /* (n, HW) or NULL (= zero) */
+  float* d_fg;                /* out (n, HW) or NULL */
+  float* d_mov;               /* out (n, HW) or NULL (the reference's mask carries no gradient) */
+  int ctas;                   /* CTAs per frame of the pixel pass, 1 .. 1024 */
+  float* part;                /* scratch (n, ctas, No, 6): per-CTA sums, added in CTA order (deterministic) */
+  float* d_pose;              /* out (n, No, ho*wo, 2), written (not accumulated) */
+} waldo_pose_dis_bwd_t;
+int waldo_pose_dis_bwd(const waldo_pose_dis_bwd_t*, waldo_stream_t);
+
 /* ------------------------------------------------------------------ f-1 (the two full-resolution layers)  the consumer of raw_output
  * models/modules/conv.py:9-11, :36-37, :54, :63: UNet.to_emb = conv3x3(Cin -> 16) as WIF.forward applies it to raw_output
  * (models/nets/wif.py:33-38) and UNet.from_emb = conv3x3(2 x 16 -> 4 | 5); stride 1, padding 1, no bias.  TF32 tensor-core products, fp32 accumulation (what the reference's cuDNN convolution

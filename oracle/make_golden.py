@@ -167,6 +167,42 @@ def pack_fixture():
     print(f"pack: {os.path.getsize(path) / 1e3:.1f} kB")
 
 
+def pose_dis_fixture():
+    """f-2: `cell_dis` / `center_dis` (models/synthesizer.py:965-979).  The statements sit inside `Synthesizer.extract_object`
+    and cannot be called on their own, so the generator EXECUTES those source lines of the reference file unchanged (read from
+    /root/reference at generation time, nothing copied into the repo) in a namespace holding seeded inputs, and lets autograd
+    supply the gradients of a seeded combination of the two scalars."""
+    import textwrap
+    import types as _t
+    src = open(os.path.join(ref_loader._find_root(), "models", "synthesizer.py")).read().splitlines()
+    first = next(i for i, l in enumerate(src) if "grid = self.net_pe.module.warper.src_grid" in l)
+    last = next(i for i, l in enumerate(src) if l.strip().startswith('log_dic["scalar"]["center_dis"] ='))
+    assert (first, last) == (964, 978), (first, last)   # lines 965-979, 1-based
+    code = compile(textwrap.dedent("\n".join(src[first:last + 1])), "synthesizer.py:965-979", "exec")
+    gen = torch.Generator().manual_seed(31)
+    res = {}
+    for i, (B, T, No, obj_shape, H, W, eps, zeros) in enumerate(((2, 3, 16, (4, 4), 16, 32, 0.0, False), (1, 2, 5, (3, 2), 9, 13, 0.05, False),
+                                                                 (1, 2, 16, (4, 4), 16, 32, 0.0, True))):
+        ys, xs = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing="ij")
+        grid = torch.stack([xs, ys], dim=-1)[None]                       # (1, H, W, 2) like warper.src_grid
+        obj_pose = (torch.rand(B, T, No, obj_shape[0] * obj_shape[1], 2, generator=gen) * 2 - 1).requires_grad_(True)
+        mov = torch.rand(B, T, 1, H, W, generator=gen)
+        if zeros:                                                        # a blurred 0/1 mask is exactly 0 far from every moving object
+            mov = mov * (torch.rand(B, T, 1, H, W, generator=gen) > 0.6).float()
+        fg = (torch.rand(B, T, 1, H, W, generator=gen) * 1.1).requires_grad_(True)   # a blurred sum of opacities can pass 1
+        opt = _t.SimpleNamespace(num_obj=No, obj_shape=obj_shape, cell_dis_eps=eps, blur_alpha=False, blur_sigma=3.0)
+        ns = {"self": _t.SimpleNamespace(opt=opt, net_pe=_t.SimpleNamespace(module=_t.SimpleNamespace(warper=_t.SimpleNamespace(src_grid=grid)))),
+              "obj_pose": obj_pose, "mov_obj_mask": mov, "fg_mask": fg, "log_dic": {"scalar": {}}, "blur": None}
+        exec(code, ns)
+        cell, center = ns["log_dic"]["scalar"]["cell_dis"], ns["log_dic"]["scalar"]["center_dis"]
+        (cell * 1.5 + center * 0.75).backward()
+        res.update({f"grid{i}": grid, f"pose{i}": obj_pose.detach(), f"mov{i}": mov, f"fg{i}": fg.detach(), f"cell{i}": cell.detach(), f"center{i}": center.detach(),
+                    f"d_pose{i}": obj_pose.grad, f"d_fg{i}": fg.grad, f"p{i}": torch.tensor([float(obj_shape[0]), float(obj_shape[1]), eps])})
+    path = os.path.join(OUT, "pose_dis.npz")
+    np.savez_compressed(path, **{k: v.numpy() for k, v in res.items()})
+    print(f"pose_dis: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -175,6 +211,8 @@ def main():
         blur_fixture()
     if not only or "pack" in only:
         pack_fixture()
+    if not only or "pose_dis" in only:
+        pose_dis_fixture()
     for name, (kw, B, T, Tc, smooth) in CASES.items():
         if only and name not in only:
             continue

@@ -555,6 +555,22 @@ def layer_entropy(alpha: torch.Tensor):
     return entropy, fg_mask
 
 
+def pose_distances(mov_obj_mask: torch.Tensor, fg_mask: torch.Tensor, obj_pose: torch.Tensor, grid: torch.Tensor, obj_shape, eps: float):
+    """models/synthesizer.py:965-979 up to (not including) the two `.mean()`s: (cell_min, center_min), each (B, T, H, W).
+    mov_obj_mask, fg_mask (B, T, 1, H, W); obj_pose (B, T, No, ho*wo, 2); grid (1, H, W, 2)."""
+    num_obj = obj_pose.shape[2]
+    obj_grid = obj_pose.view(*obj_pose.shape[:3], *obj_shape, 2)                                     # :966
+    obj_cell = (obj_grid[:, :, :, 1:, 1:] + obj_grid[:, :, :, 1:, :-1] + obj_grid[:, :, :, :-1, 1:] + obj_grid[:, :, :, :-1, :-1]) / 4   # :967
+    obj_center = obj_grid.view(*obj_pose.shape[:3], -1, 2).mean(dim=3)                               # :968
+    obj_cell_dis = (grid ** 2).sum(dim=-1).view(1, -1) + (obj_cell ** 2).sum(dim=-1).view(-1, 1) - 2 * obj_cell.reshape(-1, 2) @ grid.view(-1, 2).t()   # :969
+    obj_cell_dis = obj_cell_dis.view(*obj_grid.shape[:2], num_obj, -1, *grid.shape[1:3]).sum(dim=3)  # :970-971
+    obj_center_dis = (grid ** 2).sum(dim=-1).view(1, -1) + (obj_center ** 2).sum(dim=-1).view(-1, 1) - 2 * obj_center.view(-1, 2) @ grid.view(-1, 2).t()   # :972
+    obj_center_dis = obj_center_dis.view(*obj_grid.shape[:2], num_obj, *grid.shape[1:3])             # :973
+    cell = ((mov_obj_mask + eps) * (1 - fg_mask) * obj_cell_dis).min(dim=2)[0]                       # :976
+    center = (mov_obj_mask * obj_center_dis).min(dim=2)[0]                                           # :978
+    return cell, center
+
+
 # --------------------------------------------------------------------------- synthetic inputs (SURVEY.md §8d)
 def synth_inputs(cfg: PathConfig, B: int, T: int, Tc: int, seed: int = 0, dtype=torch.float32, smooth: bool = False,
                  radius: float = 0.5):

@@ -18,6 +18,7 @@ import sys
 import types
 
 import numpy as np
+import pytest
 import torch
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
@@ -607,6 +608,53 @@ def check_layer_entropy(dev, seed=11):
         a2 = a.clone().requires_grad_(True)
         (wo.layer_entropy(a2)[1] * wf).sum().backward()
         grad_close(ad2.grad, a2.grad, a2.grad.double(), f"fg_mask[{i}] d alpha")
+
+
+def check_pose_distances(dev):
+    """f-2 `cell_dis` / `center_dis` (synthesizer.py:965-979) against the scalars and autograd gradients of the REFERENCE's own
+    source lines (tests/golden/pose_dis.npz, oracle/make_golden.pose_dis_fixture) and, map by map, against the oracle
+    restatement + its fp64 twin; the pose gradient is a fixed-order reduction: bit-identical from run to run."""
+    z = np.load(os.path.join(GOLDEN, "pose_dis.npz"))
+    i = 0
+    while f"pose{i}" in z.files:
+        grid, pose, mov, fg = (torch.from_numpy(z[f"{n}{i}"]) for n in ("grid", "pose", "mov", "fg"))
+        obj_shape, eps = (int(z[f"p{i}"][0]), int(z[f"p{i}"][1])), float(z[f"p{i}"][2])
+        runs = []
+        for _ in range(2):
+            pd, fd = pose.clone().to(dev).requires_grad_(True), fg.clone().to(dev).requires_grad_(True)
+            cell, center = wb.pose_distance_losses(mov.to(dev), fd, pd, grid.to(dev), obj_shape, eps)
+            (cell * 1.5 + center * 0.75).backward()
+            runs.append((cell.detach().cpu(), center.detach().cpu(), pd.grad.cpu(), fd.grad.cpu()))
+        assert all(torch.equal(a, b) for a, b in zip(*runs)), f"pose_dis[{i}]: not bit-identical from run to run"
+        cell, center, d_pose, d_fg = runs[0]
+        p64, f64 = pose.double().requires_grad_(True), fg.double().requires_grad_(True)
+        c64, m64 = wo.pose_distances(mov.double(), f64, p64, grid.double(), obj_shape, eps)
+        (c64.mean() * 1.5 + m64.mean() * 0.75).backward()
+        arbitrated(cell, torch.from_numpy(z[f"cell{i}"]), c64.mean(), FWD_TOL, f"cell_dis[{i}] vs the reference")
+        arbitrated(center, torch.from_numpy(z[f"center{i}"]), m64.mean(), FWD_TOL, f"center_dis[{i}] vs the reference")
+        grad_close(d_pose, torch.from_numpy(z[f"d_pose{i}"]), p64.grad, f"pose_dis[{i}] d obj_pose")
+        grad_close(d_fg, torch.from_numpy(z[f"d_fg{i}"]), f64.grad, f"pose_dis[{i}] d fg_mask")
+        # the two maps and the argmin objects, pixel by pixel (ties -- a zero weight -- go to the first object, as torch.min does on the CPU)
+        with torch.no_grad():
+            cm, mm, ca, ma = wb.functional.pose_distances(mov.to(dev), fg.to(dev), pose.to(dev), grid.to(dev), obj_shape, eps)
+            c32, m32 = wo.pose_distances(mov, fg, pose, grid, obj_shape, eps)
+            arbitrated(cm, c32, c64, FWD_TOL, f"cell_min[{i}]")
+            arbitrated(mm, m32, m64, FWD_TOL, f"center_min[{i}]")
+            assert int(ca.max()) < pose.shape[2] and int(ma.max()) < pose.shape[2]
+        # d mov_obj_mask (no gradient in the reference: the mask comes from a threshold), where no two objects tie
+        md = mov.clone().to(dev).requires_grad_(True)
+        cell, center = wb.pose_distance_losses(md, fg.to(dev), pose.to(dev), grid.to(dev), obj_shape, eps)
+        (cell * 1.5 + center * 0.75).backward()
+        m64_ = mov.double().requires_grad_(True)
+        c, m = wo.pose_distances(m64_, fg.double(), pose.double(), grid.double(), obj_shape, eps)
+        (c.mean() * 1.5 + m.mean() * 0.75).backward()
+        live = (mov > 0) & ((mov + eps) * (1 - fg) != 0)
+        sc = float(m64_.grad.abs().max())
+        assert float(((md.grad.cpu().double() - m64_.grad) * live).abs().max()) <= GRAD_TOL * sc, f"pose_dis[{i}] d mov_obj_mask"
+        i += 1
+    assert i >= 3
+    with pytest.raises(RuntimeError, match="obj_pose must be"):
+        wb.pose_distance_losses(mov.to(dev), fg.to(dev), pose[:, :, :, :-1].contiguous().to(dev), grid.to(dev), obj_shape, eps)
 
 
 def check_deterministic_large_gradients(dev, seed=1, B=8):

@@ -81,6 +81,10 @@ def test_layer_entropy():
     parity.check_layer_entropy(DEV)
 
 
+def test_pose_distances():
+    parity.check_pose_distances(DEV)
+
+
 def test_pack_input():
     parity.check_pack_input(DEV)
 

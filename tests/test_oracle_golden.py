@@ -98,3 +98,25 @@ def test_blur_against_the_reference_fixture():
         assert float((x.grad - g_ref).abs().max()) <= 1e-5 * float(g_ref.abs().max()), i
         i += 1
     assert i >= 4
+
+
+def test_pose_distances_against_the_reference_fixture():
+    """f-2: the oracle's restatement of `cell_dis` / `center_dis` against the scalars and autograd gradients produced by the
+    reference's own source lines (models/synthesizer.py:965-979, executed by oracle/make_golden.pose_dis_fixture)."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(parity.GOLDEN, "pose_dis.npz"))
+    i = 0
+    while f"pose{i}" in z.files:
+        grid, mov = torch.from_numpy(z[f"grid{i}"]), torch.from_numpy(z[f"mov{i}"])
+        pose, fg = torch.from_numpy(z[f"pose{i}"]).requires_grad_(True), torch.from_numpy(z[f"fg{i}"]).requires_grad_(True)
+        obj_shape, eps = (int(z[f"p{i}"][0]), int(z[f"p{i}"][1])), float(z[f"p{i}"][2])
+        cell, center = wo.pose_distances(mov, fg, pose, grid, obj_shape, eps)
+        (cell.mean() * 1.5 + center.mean() * 0.75).backward()
+        assert abs(float(cell.mean()) - float(z[f"cell{i}"])) <= 1e-6 * max(1.0, abs(float(z[f"cell{i}"]))), i
+        assert abs(float(center.mean()) - float(z[f"center{i}"])) <= 1e-6 * max(1.0, abs(float(z[f"center{i}"]))), i
+        for g, name in ((pose.grad, "d_pose"), (fg.grad, "d_fg")):
+            ref = torch.from_numpy(z[f"{name}{i}"])
+            assert float((g - ref).abs().max()) <= 1e-5 * max(float(ref.abs().max()), 1e-30), (i, name)
+        i += 1
+    assert i >= 3

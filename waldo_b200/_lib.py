@@ -120,6 +120,17 @@ class LayerEntropyBwd(C.Structure):
     _fields_ = [("f", LayerEntropy), ("d_entropy", c_void_p), ("d_fg", c_void_p), ("d_alpha", c_void_p)]
 
 
+class PoseDis(C.Structure):
+    _fields_ = [("n", C.c_int), ("No", C.c_int), ("ho", C.c_int), ("wo", C.c_int), ("HW", C.c_int), ("eps", C.c_float),
+                ("mov", c_void_p), ("fg", c_void_p), ("pose", c_void_p), ("grid", c_void_p),
+                ("cell_min", c_void_p), ("center_min", c_void_p), ("cell_arg", c_void_p), ("center_arg", c_void_p)]
+
+
+class PoseDisBwd(C.Structure):
+    _fields_ = [("f", PoseDis), ("d_cell", c_void_p), ("d_center", c_void_p), ("d_fg", c_void_p), ("d_mov", c_void_p),
+                ("ctas", C.c_int), ("part", c_void_p), ("d_pose", c_void_p)]
+
+
 class Conv3x3(C.Structure):
     _fields_ = [("n", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Tc", C.c_int), ("Tp", C.c_int),
                 ("in", c_void_p), ("weight", c_void_p), ("out", c_void_p)]
@@ -141,12 +152,14 @@ STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwar
              "waldo_decode_bwd_t": DecodeBwd, "waldo_wif_fuse_fwd_t": WifFuseFwd, "waldo_wif_fuse_bwd_t": WifFuseBwd,
              "waldo_pack_input_t": PackInput, "waldo_warp_field_t": WarpField, "waldo_resize_t": Resize,
              "waldo_frames_u8_t": FramesU8, "waldo_blur_t": Blur, "waldo_layer_entropy_t": LayerEntropy,
-             "waldo_layer_entropy_bwd_t": LayerEntropyBwd, "waldo_conv3x3_t": Conv3x3, "waldo_conv3x3_wgrad_t": Conv3x3Wgrad}
+             "waldo_layer_entropy_bwd_t": LayerEntropyBwd, "waldo_conv3x3_t": Conv3x3, "waldo_conv3x3_wgrad_t": Conv3x3Wgrad,
+             "waldo_pose_dis_t": PoseDis, "waldo_pose_dis_bwd_t": PoseDisBwd}
 
 EXPORTS = ["waldo_last_error", "waldo_abi_version", "waldo_has_device_code", "waldo_launch_count", "waldo_tps_fwd", "waldo_tps_bwd",
            "waldo_invwarp_fwd", "waldo_invwarp_bwd", "waldo_occ_fwd", "waldo_occ_bwd", "waldo_decode_fwd",
            "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input", "waldo_warp_field_fwd", "waldo_resize_bilinear_fwd",
-           "waldo_frames_to_u8", "waldo_blur_fwd", "waldo_blur_bwd", "waldo_layer_entropy_fwd", "waldo_layer_entropy_bwd", "waldo_conv3x3_fwd", "waldo_conv3x3_wgrad"]
+           "waldo_frames_to_u8", "waldo_blur_fwd", "waldo_blur_bwd", "waldo_layer_entropy_fwd", "waldo_layer_entropy_bwd", "waldo_conv3x3_fwd", "waldo_conv3x3_wgrad",
+           "waldo_pose_dis_fwd", "waldo_pose_dis_bwd"]
 
 _lock = threading.Lock()
 _lib = None
@@ -162,7 +175,8 @@ def _declare(lib):
                      ("waldo_invwarp_bwd", InvWarpBwd), ("waldo_decode_fwd", DecodeFwd), ("waldo_decode_bwd", DecodeBwd),
                      ("waldo_wif_fuse_fwd", WifFuseFwd), ("waldo_wif_fuse_bwd", WifFuseBwd), ("waldo_pack_input", PackInput), ("waldo_warp_field_fwd", WarpField),
                      ("waldo_resize_bilinear_fwd", Resize), ("waldo_frames_to_u8", FramesU8), ("waldo_blur_fwd", Blur), ("waldo_blur_bwd", Blur),
-                     ("waldo_layer_entropy_fwd", LayerEntropy), ("waldo_layer_entropy_bwd", LayerEntropyBwd), ("waldo_conv3x3_fwd", Conv3x3), ("waldo_conv3x3_wgrad", Conv3x3Wgrad)):
+                     ("waldo_layer_entropy_fwd", LayerEntropy), ("waldo_layer_entropy_bwd", LayerEntropyBwd), ("waldo_conv3x3_fwd", Conv3x3), ("waldo_conv3x3_wgrad", Conv3x3Wgrad),
+                     ("waldo_pose_dis_fwd", PoseDis), ("waldo_pose_dis_bwd", PoseDisBwd)):
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(st), c_void_p]
         fn.restype = C.c_int

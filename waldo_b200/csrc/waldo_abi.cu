@@ -382,6 +382,36 @@ int waldo_layer_entropy_bwd(const waldo_layer_entropy_bwd_t* a, waldo_stream_t s
   return 0;
 }
 
+static int wb_pose_dis_check(const waldo_pose_dis_t* a, const char* who) {
+  WB_REQUIRE(a && a->n >= 0 && a->n <= 65535 && a->HW > 0, "pose_dis: bad sizes");
+  WB_REQUIRE(a->No >= 1 && a->No <= WB_PD_MAX_NO && a->ho >= 2 && a->wo >= 2 && (long long)a->No * (a->ho - 1) * (a->wo - 1) <= WB_PD_MAX_CELLS,
+             "pose_dis: No <= 32, obj_shape >= (2, 2), No (ho-1)(wo-1) <= 1024");
+  WB_REQUIRE(a->mov && a->fg && a->pose && a->grid && a->cell_arg && a->center_arg, "pose_dis: null pointer");
+  (void)who;
+  return 0;
+}
+int waldo_pose_dis_fwd(const waldo_pose_dis_t* a, waldo_stream_t st) {
+  int rc = wb_pose_dis_check(a, "pose_dis_fwd");
+  if (rc) return rc;
+  WB_REQUIRE(a->cell_min && a->center_min, "pose_dis_fwd: null output");
+  if (a->n == 0) return 0;
+  WB_LAUNCH(k_pose_dis_fwd, dim3(wb_blocks(a->HW, WB_PD_THREADS, 1024), a->n), dim3(WB_PD_THREADS), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+int waldo_pose_dis_bwd(const waldo_pose_dis_bwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a, "pose_dis_bwd: null");
+  int rc = wb_pose_dis_check(&a->f, "pose_dis_bwd");
+  if (rc) return rc;
+  WB_REQUIRE(a->part && a->d_pose && a->ctas >= 1 && a->ctas <= 1024, "pose_dis_bwd: part / d_pose / ctas");
+  if (a->f.n == 0) return 0;
+  WB_LAUNCH(k_pose_dis_bwd, dim3(a->ctas, a->f.n), dim3(WB_PD_THREADS), 0, st, *a);
+  WB_LAUNCHED();
+  WB_LAUNCH(k_pose_dis_bwd_final, dim3(wb_blocks((long long)a->f.n * a->f.No, 128, 1024)), dim3(128), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ first UNet layer
 int waldo_conv3x3_fwd(const waldo_conv3x3_t* a, waldo_stream_t st) {
   WB_REQUIRE(a && a->n >= 0 && a->H > 0 && a->W > 0, "conv3x3_fwd: bad sizes");

@@ -158,3 +158,158 @@ __global__ void __launch_bounds__(256) k_layer_entropy_bwd(waldo_layer_entropy_b
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------ pose distances
+// synthesizer.py:965-979 (`cell_dis`, `center_dis`): squared distances between every lattice point g of the low-res grid and
+//   c_{o,k} = the centre of cell k of object o's control-point lattice (mean of its 4 corners), summed over the cells, and
+//   m_o     = the mean of all control points of object o,
+// each in the expanded form the reference uses (|g|^2 + |c|^2 - 2 c.g), weighted per pixel and minimised over the objects:
+//   cell_min   = min_o ( (mov + eps) (1 - fg) * sum_k d(g, c_{o,k}) )        center_min = min_o ( mov * d(g, m_o) )
+// The reference materialises the (B, T, No, cells, H, W) distance tensor through a K = 2 matmul (755 MB at B = 8, T = 5,
+// 16 objects, 9 cells, 128 x 256); here one thread per pixel walks the objects with the centres staged in shared memory:
+// 4 floats in, 2 floats + 2 bytes out per pixel.  The argmin objects are saved for the backward (first index on ties).
+#define WB_PD_MAX_NO 32
+#define WB_PD_MAX_CELLS 1024   // No * (ho - 1) * (wo - 1)
+#define WB_PD_THREADS 256
+
+// cell centres (x, y, |c|^2) and object means (x, y, |m|^2) of frame f into shared memory
+WB_DEV void wb_pd_stage(const waldo_pose_dis_t& p, int f, float* s_c, float* s_m) {
+  const int K = p.ho * p.wo, ncell = (p.ho - 1) * (p.wo - 1);
+  const float* pose = p.pose + (size_t)f * p.No * K * 2;
+  for (int i = wb_tid(); i < p.No * ncell; i += wb_nthr()) {
+    const int o = i / ncell, k = i - o * ncell, cy = k / (p.wo - 1), cx = k - cy * (p.wo - 1);
+    const float* q = pose + ((size_t)o * K + (size_t)cy * p.wo + cx) * 2;   // corner (cy, cx); the reference adds (1,1) + (1,0) + (0,1) + (0,0)
+    const float x = (((q[(p.wo + 1) * 2] + q[p.wo * 2]) + q[2]) + q[0]) / 4.f;
+    const float y = (((q[(p.wo + 1) * 2 + 1] + q[p.wo * 2 + 1]) + q[3]) + q[1]) / 4.f;
+    s_c[i * 3] = x; s_c[i * 3 + 1] = y; s_c[i * 3 + 2] = x * x + y * y;
+  }
+  for (int o = wb_tid(); o < p.No; o += wb_nthr()) {
+    float sx = 0.f, sy = 0.f;
+    for (int k = 0; k < K; ++k) { sx += pose[((size_t)o * K + k) * 2]; sy += pose[((size_t)o * K + k) * 2 + 1]; }
+    const float x = sx / (float)K, y = sy / (float)K;
+    s_m[o * 3] = x; s_m[o * 3 + 1] = y; s_m[o * 3 + 2] = x * x + y * y;
+  }
+}
+WB_DEV float wb_pd_cell_sum(const float* s_c, int o, int ncell, float gx, float gy, float g2) {
+  float d = 0.f;
+  for (int k = 0; k < ncell; ++k) {
+    const float* c = s_c + (o * ncell + k) * 3;
+    d += (g2 + c[2]) - 2.f * (c[0] * gx + c[1] * gy);
+  }
+  return d;
+}
+WB_DEV float wb_pd_center(const float* s_m, int o, float gx, float gy, float g2) {
+  return (g2 + s_m[o * 3 + 2]) - 2.f * (s_m[o * 3] * gx + s_m[o * 3 + 1] * gy);
+}
+
+__global__ void __launch_bounds__(WB_PD_THREADS) k_pose_dis_fwd(waldo_pose_dis_t p) {
+  __shared__ float s_c[WB_PD_MAX_CELLS * 3];
+  __shared__ float s_m[WB_PD_MAX_NO * 3];
+  const int f = blockIdx.y, ncell = (p.ho - 1) * (p.wo - 1);
+  wb_pd_stage(p, f, s_c, s_m);
+  __syncthreads();
+  const size_t base = (size_t)f * p.HW;
+  for (int q = blockIdx.x * wb_nthr() + wb_tid(); q < p.HW; q += gridDim.x * wb_nthr()) {
+    const float gx = __ldg(p.grid + 2 * q), gy = __ldg(p.grid + 2 * q + 1), g2 = gx * gx + gy * gy;
+    const float mov = __ldg(p.mov + base + q), fg = __ldg(p.fg + base + q);
+    const float w = (mov + p.eps) * (1.f - fg);
+    float bc = 0.f, bm = 0.f;
+    int ac = 0, am = 0;
+    for (int o = 0; o < p.No; ++o) {
+      const float vc = w * wb_pd_cell_sum(s_c, o, ncell, gx, gy, g2);
+      const float vm = mov * wb_pd_center(s_m, o, gx, gy, g2);
+      if (o == 0 || vc < bc) { bc = vc; ac = o; }
+      if (o == 0 || vm < bm) { bm = vm; am = o; }
+    }
+    p.cell_min[base + q] = bc; p.center_min[base + q] = bm;
+    p.cell_arg[base + q] = (unsigned char)ac; p.center_arg[base + q] = (unsigned char)am;
+  }
+}
+
+// Backward, pixel pass.  With o* / o' the saved argmins, Dc = sum_k d(g, c_{o*,k}), Dm = d(g, m_{o'}):
+//   d fg  = -d cell_min (mov + eps) Dc          d mov = d cell_min (1 - fg) Dc + d center_min Dm
+//   d c_{o*,k} += wc (2 c_{o*,k} - 2 g),  wc = d cell_min (mov + eps)(1 - fg)      d m_{o'} += wm (2 m_{o'} - 2 g),  wm = d center_min mov
+// The sums over pixels only need S0 = sum w and S1 = sum w g per (frame, object) and term: six floats.  Each warp adds its lanes'
+// values object by object (only the objects present in the warp) into its own shared-memory row, the rows are added in warp order
+// and leave the CTA as one partial per (frame, CTA, object): no atomics, the same bits on every run.
+__global__ void __launch_bounds__(WB_PD_THREADS) k_pose_dis_bwd(waldo_pose_dis_bwd_t b) {
+  const waldo_pose_dis_t& p = b.f;
+  __shared__ float s_c[WB_PD_MAX_CELLS * 3];
+  __shared__ float s_m[WB_PD_MAX_NO * 3];
+  __shared__ float s_acc[WB_PD_THREADS / 32][WB_PD_MAX_NO * 6];
+  const int f = blockIdx.y, ncell = (p.ho - 1) * (p.wo - 1);
+  wb_pd_stage(p, f, s_c, s_m);
+  for (int i = wb_tid(); i < (WB_PD_THREADS / 32) * WB_PD_MAX_NO * 6; i += wb_nthr()) (&s_acc[0][0])[i] = 0.f;
+  __syncthreads();
+  float* acc = s_acc[wb_warp()];
+  const size_t base = (size_t)f * p.HW;
+  const int span = gridDim.x * wb_nthr();
+  for (int q0 = blockIdx.x * wb_nthr(); q0 < p.HW; q0 += span) {   // whole warps stay in the loop: the reductions need every lane
+    const int q = q0 + wb_tid();
+    const bool on = q < p.HW;
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int oc = 0, om = 0;
+    if (on) {
+      const float gx = __ldg(p.grid + 2 * q), gy = __ldg(p.grid + 2 * q + 1), g2 = gx * gx + gy * gy;
+      const float mov = __ldg(p.mov + base + q), fg = __ldg(p.fg + base + q);
+      const float gc = b.d_cell ? __ldg(b.d_cell + base + q) : 0.f, gm = b.d_center ? __ldg(b.d_center + base + q) : 0.f;
+      oc = p.cell_arg[base + q]; om = p.center_arg[base + q];
+      const float Dc = wb_pd_cell_sum(s_c, oc, ncell, gx, gy, g2), Dm = wb_pd_center(s_m, om, gx, gy, g2);
+      if (b.d_fg) b.d_fg[base + q] = -gc * (mov + p.eps) * Dc;
+      if (b.d_mov) b.d_mov[base + q] = gc * (1.f - fg) * Dc + gm * Dm;
+      const float wc = gc * ((mov + p.eps) * (1.f - fg)), wm = gm * mov;
+      v[0] = wc; v[1] = wc * gx; v[2] = wc * gy; v[3] = wm; v[4] = wm * gx; v[5] = wm * gy;
+    }
+    unsigned present = wb_warp_or(on ? ((1u << oc) | (1u << om)) : 0u);
+    while (present) {
+      const int o = __ffs((int)present) - 1;
+      present &= present - 1u;
+      WB_UNROLL for (int j = 0; j < 6; ++j) {
+        const bool mine = on && (j < 3 ? oc == o : om == o);
+        const float s = wb_warp_sum(mine ? v[j] : 0.f);
+        if (wb_lane() == 0) acc[o * 6 + j] += s;
+      }
+    }
+  }
+  __syncthreads();
+  float* part = b.part + ((size_t)f * gridDim.x + blockIdx.x) * p.No * 6;
+  for (int i = wb_tid(); i < p.No * 6; i += wb_nthr()) {
+    float s = 0.f;
+    WB_UNROLL for (int w = 0; w < WB_PD_THREADS / 32; ++w) s += s_acc[w][i];   // (emulation: one warp, the other rows stay zero)
+    part[i] = s;
+  }
+}
+// one thread per (frame, object): partials added in CTA order, then spread over the control points
+//   d pose_{o,(i,j)} = sum_{cells k that have (i,j) as a corner} (2 c_k S0c - 2 S1c) / 4  +  (2 m S0m - 2 S1m) / (ho wo)
+__global__ void __launch_bounds__(128) k_pose_dis_bwd_final(waldo_pose_dis_bwd_t b) {
+  const waldo_pose_dis_t& p = b.f;
+  const int K = p.ho * p.wo;
+  for (int i = blockIdx.x * wb_nthr() + wb_tid(); i < p.n * p.No; i += gridDim.x * wb_nthr()) {
+    const int f = i / p.No, o = i - f * p.No;
+    float S[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < b.ctas; ++c) {
+      const float* part = b.part + (((size_t)f * b.ctas + c) * p.No + o) * 6;
+      WB_UNROLL for (int j = 0; j < 6; ++j) S[j] += part[j];
+    }
+    const float* pose = p.pose + ((size_t)f * p.No + o) * K * 2;
+    float* dp = b.d_pose + ((size_t)f * p.No + o) * K * 2;
+    float mx = 0.f, my = 0.f;
+    for (int k = 0; k < K; ++k) { mx += pose[k * 2]; my += pose[k * 2 + 1]; }
+    mx /= (float)K; my /= (float)K;
+    const float cmx = (2.f * mx * S[3] - 2.f * S[4]) / (float)K, cmy = (2.f * my * S[3] - 2.f * S[5]) / (float)K;
+    for (int y = 0; y < p.ho; ++y)
+      for (int x = 0; x < p.wo; ++x) {
+        float gx = cmx, gy = cmy;
+        for (int cy = y - 1; cy <= y; ++cy)
+          for (int cx = x - 1; cx <= x; ++cx) {
+            if (cy < 0 || cx < 0 || cy >= p.ho - 1 || cx >= p.wo - 1) continue;
+            const float* q = pose + ((size_t)cy * p.wo + cx) * 2;
+            const float ccx = (((q[(p.wo + 1) * 2] + q[p.wo * 2]) + q[2]) + q[0]) / 4.f;
+            const float ccy = (((q[(p.wo + 1) * 2 + 1] + q[p.wo * 2 + 1]) + q[3]) + q[1]) / 4.f;
+            gx += (2.f * ccx * S[0] - 2.f * S[1]) * 0.25f;
+            gy += (2.f * ccy * S[0] - 2.f * S[2]) * 0.25f;
+          }
+        dp[(y * p.wo + x) * 2] = gx; dp[(y * p.wo + x) * 2 + 1] = gy;
+      }
+  }
+}

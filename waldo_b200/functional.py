@@ -692,6 +692,65 @@ def layer_entropy(alpha):
     return _LayerEntropy.apply(alpha)
 
 
+class _PoseDis(torch.autograd.Function):
+    """models/synthesizer.py:965-979: the per-pixel minima over the objects behind `cell_dis` and `center_dis`."""
+
+    @staticmethod
+    def forward(ctx, mov, fg, pose, grid, eps, ho, wo):
+        lib = L.load()
+        mov_c, fg_c, pose_c, grid_c = _c(mov.detach()), _c(fg.detach()), _c(pose.detach()), _c(grid.detach())
+        *lead, one, H, W = mov_c.shape
+        n = 1
+        for v in lead:
+            n *= v
+        No = pose_c.shape[-3]
+        cell = torch.empty(*lead, H, W, device=mov_c.device, dtype=torch.float32)
+        center = torch.empty_like(cell)
+        carg = torch.empty(*lead, H, W, device=mov_c.device, dtype=torch.uint8)
+        marg = torch.empty_like(carg)
+        a = L.PoseDis(n, No, ho, wo, H * W, float(eps), L.ptr(mov_c, name="mov_obj_mask"), L.ptr(fg_c, name="fg_mask"), L.ptr(pose_c, name="obj_pose"),
+                      L.ptr(grid_c, name="grid"), L.ptr(cell), L.ptr(center), L.ptr(carg, torch.uint8), L.ptr(marg, torch.uint8))
+        L.call(lib.waldo_pose_dis_fwd, a, mov_c, "pose_dis_fwd")
+        ctx.save_for_backward(mov_c, fg_c, pose_c, grid_c, carg, marg)
+        ctx.dims = (n, No, ho, wo, H * W, float(eps))
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(carg, marg)
+        return cell, center, carg, marg
+
+    @staticmethod
+    def backward(ctx, d_cell, d_center, _a, _b):
+        lib = L.load()
+        mov_c, fg_c, pose_c, grid_c, carg, marg = ctx.saved_tensors
+        n, No, ho, wo, HW, eps = ctx.dims
+        d_cell = _c(d_cell) if d_cell is not None else None
+        d_center = _c(d_center) if d_center is not None else None
+        d_fg = torch.empty_like(fg_c) if ctx.needs_input_grad[1] else None
+        d_mov = torch.empty_like(mov_c) if ctx.needs_input_grad[0] else None
+        d_pose = torch.empty_like(pose_c)
+        ctas = max(1, min(1024, (HW + 255) // 256))
+        part = torch.empty(max(n, 1), ctas, No, 6, device=mov_c.device, dtype=torch.float32)
+        f = L.PoseDis(n, No, ho, wo, HW, eps, L.ptr(mov_c), L.ptr(fg_c), L.ptr(pose_c), L.ptr(grid_c), None, None, L.ptr(carg, torch.uint8), L.ptr(marg, torch.uint8))
+        b = L.PoseDisBwd(f, L.ptr(d_cell), L.ptr(d_center), L.ptr(d_fg), L.ptr(d_mov), ctas, L.ptr(part), L.ptr(d_pose))
+        L.call(lib.waldo_pose_dis_bwd, b, mov_c, "pose_dis_bwd")
+        return d_mov, d_fg, (d_pose if ctx.needs_input_grad[2] else None), None, None, None, None
+
+
+def pose_distances(mov_obj_mask, fg_mask, obj_pose, grid, obj_shape, eps):
+    """(cell_min, center_min, cell_arg, center_arg), each (..., H, W): the maps whose means are the reference's `cell_dis` and
+    `center_dis` (synthesizer.py:965-979) and the objects that attain the minima.
+    mov_obj_mask, fg_mask (..., 1, H, W); obj_pose (..., No, ho*wo, 2); grid (1, H, W, 2) = warper.src_grid."""
+    ho, wo = int(obj_shape[0]), int(obj_shape[1])
+    if mov_obj_mask.dim() < 3 or mov_obj_mask.shape[-3] != 1 or mov_obj_mask.shape != fg_mask.shape:
+        raise RuntimeError(f"waldo_b200.pose_distances: masks must both be (..., 1, H, W), got {tuple(mov_obj_mask.shape)} / {tuple(fg_mask.shape)}")
+    H, W = mov_obj_mask.shape[-2:]
+    lead = tuple(mov_obj_mask.shape[:-3])
+    if obj_pose.dim() != len(lead) + 3 or tuple(obj_pose.shape[:len(lead)]) != lead or obj_pose.shape[-2] != ho * wo or obj_pose.shape[-1] != 2:
+        raise RuntimeError(f"waldo_b200.pose_distances: obj_pose must be {lead + ('No', ho * wo, 2)}, got {tuple(obj_pose.shape)}")
+    if grid.numel() != H * W * 2 or grid.shape[-1] != 2:
+        raise RuntimeError(f"waldo_b200.pose_distances: grid must be (1, {H}, {W}, 2), got {tuple(grid.shape)}")
+    return _PoseDis.apply(mov_obj_mask, fg_mask, obj_pose, grid, eps, ho, wo)
+
+
 # ===================================================================================== f-1 first UNet layer
 def _conv3x3_launch(x, weight, n, Cin, H, W, Tc, Tp):
     lib = L.load()

@@ -374,6 +374,16 @@ def layer_entropy(alpha):
     return Fn.layer_entropy(alpha)
 
 
+def pose_distance_losses(mov_obj_mask, fg_mask, obj_pose, grid, obj_shape, cell_dis_eps):
+    """models/synthesizer.py:965-979: `cell_dis` and `center_dis` of LVD training -- the mean over pixels of the minimum over
+    the objects of (mov_obj_mask + eps)(1 - fg_mask) * (summed squared distance of the pixel to the object's cell centres) and of
+    mov_obj_mask * (squared distance to the object's mean control point) -- without the reference's (B, T, No, cells, H, W)
+    distance tensor.  mov_obj_mask, fg_mask (B, T, 1, H, W) (already blurred if opt.blur_alpha); obj_pose (B, T, No, ho*wo, 2);
+    grid = warper.src_grid (1, H, W, 2).  Differentiable in fg_mask and obj_pose (and mov_obj_mask)."""
+    cell, center, _, _ = Fn.pose_distances(mov_obj_mask, fg_mask, obj_pose, grid, obj_shape, cell_dis_eps)
+    return cell.mean(), center.mean()
+
+
 # ----------------------------------------------------------------------------- f-1, first layer (consumer side: WIF's UNet)
 def wif_to_emb(raw_output, weight):
     """`UNet.to_emb` as WIF.forward applies it to raw_output (models/nets/wif.py:33-38 + models/modules/conv.py:54):
