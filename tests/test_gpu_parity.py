@@ -110,6 +110,10 @@ def test_layer_entropy(dev):
     parity.check_layer_entropy(dev)
 
 
+def test_pose_distances(dev):
+    parity.check_pose_distances(dev)
+
+
 def test_pack_input(dev):
     parity.check_pack_input(dev)
     parity.check_pack_input(dev, B=1, T=2, Hd=256, Wd=832, num_lyt=19)

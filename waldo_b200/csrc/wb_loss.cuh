@@ -1,6 +1,6 @@
 // f-2: loss epilogues of LVD training over the path's low-res outputs.
-// Reference: models/synthesizer.py:1114-1118 `blur` (torchvision GaussianBlur, reflect padding) and
-// :886-892 the layer-entropy regulariser, :933 `fg_mask`; both forward and backward.
+// Reference: models/synthesizer.py:1114-1118 `blur` (torchvision GaussianBlur, reflect padding),
+// :886-892 the layer-entropy regulariser, :933 `fg_mask`, :965-979 `cell_dis` / `center_dis`; all forward and backward.
 #pragma once
 #include "wb_common.cuh"
 #include "../../include/waldo_b200.h"
