@@ -386,6 +386,30 @@ typedef struct {
 } waldo_pose_dis_bwd_t;
 int waldo_pose_dis_bwd(const waldo_pose_dis_bwd_t*, waldo_stream_t);
 
+/* models/synthesizer.py:864-868 (`obj_flow`, "same mean motion in layers"):
+ *   a_o = (alpha_{o+1} + 1) / 2 + 1e-6 (object layers),  m_o = sum_p a_o f / sum_p a_o  (f = real_flow),
+ *   dev_map(p) = sum_o a_o(p) (|fx(p) - mx_o| + |fy(p) - my_o|);   the reference's scalar is sum(dev_map) / (n (L-1) HW). */
+typedef struct {
+  int n;                      /* B*T, <= 65535 */
+  int L;                      /* layers incl. the background layer 0 (skipped), 2 .. 33 */
+  int HW;
+  const float* alpha;         /* (n, L, HW) in [-1, 1] */
+  const float* flow;          /* (n, 2, HW) */
+  int ctas;                   /* CTAs per frame of the reduction passes, 1 .. 1024 */
+  float* part;                /* scratch (n, ctas, L-1, 3): per-CTA sums, added in CTA order (deterministic) */
+  float* mom;                 /* out (n, L-1, 3): sum a, sum a fx, sum a fy (read by the backward) */
+  float* dev_map;             /* out (n, HW) */
+} waldo_obj_flow_t;
+int waldo_obj_flow_fwd(const waldo_obj_flow_t*, waldo_stream_t);
+
+typedef struct {
+  waldo_obj_flow_t f;         /* alpha, flow, mom as in / from the forward; part is scratch again; dev_map is not read */
+  const float* d_map;         /* (n, HW) upstream gradient of dev_map */
+  float* tsum;                /* scratch (n, L-1, 2) */
+  float* d_alpha;             /* out (n, L, HW), written (layer 0 = 0) */
+} waldo_obj_flow_bwd_t;
+int waldo_obj_flow_bwd(const waldo_obj_flow_bwd_t*, waldo_stream_t);
+
 /* ------------------------------------------------------------------ f-1 (the two full-resolution layers)  the consumer of raw_output
  * models/modules/conv.py:9-11, :36-37, :54, :63: UNet.to_emb = conv3x3(Cin -> 16) as WIF.forward applies it to raw_output
  * (models/nets/wif.py:33-38) and UNet.from_emb = conv3x3(2 x 16 -> 4 | 5); stride 1, padding 1, no bias.  TF32 tensor-core products, fp32 accumulation (what the reference's cuDNN convolution

@@ -203,6 +203,33 @@ def pose_dis_fixture():
     print(f"pose_dis: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def obj_flow_fixture():
+    """f-2: `obj_flow` (models/synthesizer.py:865-868), produced like pose_dis_fixture: the reference's own source lines executed
+    unchanged on seeded inputs, autograd for the gradient with respect to the layer opacities."""
+    import textwrap
+    src = open(os.path.join(ref_loader._find_root(), "models", "synthesizer.py")).read().splitlines()
+    first = next(i for i, l in enumerate(src) if l.strip().startswith("a = (rec_output_alpha[:, :, 1:] + 1) / 2 + 1e-6"))
+    last = next(i for i, l in enumerate(src) if l.strip().startswith('log_dic["scalar"]["obj_flow"] ='))
+    assert (first, last) == (864, 867), (first, last)   # lines 865-868, 1-based
+    code = compile(textwrap.dedent("\n".join(src[first:last + 1])), "synthesizer.py:865-868", "exec")
+    gen = torch.Generator().manual_seed(41)
+    res = {}
+    for i, (B, T, L, H, W, sat) in enumerate(((2, 3, 17, 16, 32, False), (1, 2, 3, 9, 13, False), (1, 1, 6, 12, 20, True))):
+        alpha = torch.tanh(2 * torch.randn(B, T, L, H, W, generator=gen))
+        if sat:   # saturated opacities (+-1 exactly): layers that are empty everywhere keep sum_a = 1e-6 HW
+            alpha = torch.where(alpha > 0.3, torch.ones(()), -torch.ones(()))
+        alpha = alpha.requires_grad_(True)
+        flow = torch.randn(B, T, 2, H, W, generator=gen) * 0.1
+        ns = {"rec_output_alpha": alpha, "real_flow": flow, "log_dic": {"scalar": {}}}
+        exec(code, ns)
+        val = ns["log_dic"]["scalar"]["obj_flow"]
+        (val * 3.0).backward()
+        res.update({f"alpha{i}": alpha.detach(), f"flow{i}": flow, f"val{i}": val.detach(), f"d_alpha{i}": alpha.grad})
+    path = os.path.join(OUT, "obj_flow.npz")
+    np.savez_compressed(path, **{k: v.numpy() for k, v in res.items()})
+    print(f"obj_flow: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -213,6 +240,8 @@ def main():
         pack_fixture()
     if not only or "pose_dis" in only:
         pose_dis_fixture()
+    if not only or "obj_flow" in only:
+        obj_flow_fixture()
     for name, (kw, B, T, Tc, smooth) in CASES.items():
         if only and name not in only:
             continue

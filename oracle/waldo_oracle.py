@@ -571,6 +571,14 @@ def pose_distances(mov_obj_mask: torch.Tensor, fg_mask: torch.Tensor, obj_pose: 
     return cell, center
 
 
+def obj_flow(rec_output_alpha: torch.Tensor, real_flow: torch.Tensor) -> torch.Tensor:
+    """models/synthesizer.py:864-868 -> the scalar `obj_flow`.  rec_output_alpha (B, T, No+1, H, W), real_flow (B, T, 2, H, W)."""
+    a = (rec_output_alpha[:, :, 1:] + 1) / 2 + 1e-6                                                   # :865
+    sum_a = a.sum(dim=3, keepdim=True).sum(dim=4, keepdim=True)                                       # :866
+    mean_flow = (real_flow.unsqueeze(2) * a.unsqueeze(3)).sum(dim=4, keepdim=True).sum(dim=5, keepdim=True) / sum_a.unsqueeze(3)   # :867
+    return (a * (real_flow.unsqueeze(2) - mean_flow).abs().sum(dim=3)).mean()                         # :868
+
+
 # --------------------------------------------------------------------------- synthetic inputs (SURVEY.md §8d)
 def synth_inputs(cfg: PathConfig, B: int, T: int, Tc: int, seed: int = 0, dtype=torch.float32, smooth: bool = False,
                  radius: float = 0.5):

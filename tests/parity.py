@@ -657,6 +657,44 @@ def check_pose_distances(dev):
         wb.pose_distance_losses(mov.to(dev), fg.to(dev), pose[:, :, :, :-1].contiguous().to(dev), grid.to(dev), obj_shape, eps)
 
 
+def check_obj_flow(dev):
+    """f-2 `obj_flow` (synthesizer.py:865-868) against the scalar and the autograd gradient of the REFERENCE's own source lines
+    (tests/golden/obj_flow.npz, oracle/make_golden.obj_flow_fixture) and against the oracle's fp64 twin; fixed-order reductions:
+    bit-identical from run to run."""
+    z = np.load(os.path.join(GOLDEN, "obj_flow.npz"))
+    i = 0
+    while f"alpha{i}" in z.files:
+        alpha, flow = torch.from_numpy(z[f"alpha{i}"]), torch.from_numpy(z[f"flow{i}"])
+        runs = []
+        for _ in range(2):
+            ad = alpha.clone().to(dev).requires_grad_(True)
+            val = wb.obj_flow_loss(ad, flow.to(dev))
+            (val * 3.0).backward()
+            runs.append((val.detach().cpu(), ad.grad.cpu()))
+        assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1]), f"obj_flow[{i}]: not bit-identical from run to run"
+        a64 = alpha.double().requires_grad_(True)
+        v64 = wo.obj_flow(a64, flow.double())
+        (v64 * 3.0).backward()
+        arbitrated(runs[0][0], torch.from_numpy(z[f"val{i}"]), v64, FWD_TOL, f"obj_flow[{i}] vs the reference")
+        grad_close(runs[0][1], torch.from_numpy(z[f"d_alpha{i}"]), a64.grad, f"obj_flow[{i}] d rec_output_alpha")
+        assert float(runs[0][1][:, :, 0].abs().max()) == 0.0, "the background layer takes no part"
+        # a non-uniform upstream gradient of the per-pixel map (the T sums then depend on it)
+        gen = torch.Generator().manual_seed(3 + i)
+        w = torch.randn(alpha.shape[0], alpha.shape[1], *alpha.shape[3:], generator=gen)
+        ad = alpha.clone().to(dev).requires_grad_(True)
+        (wb.functional.obj_flow_map(ad, flow.to(dev)) * w.to(dev)).sum().backward()
+        a64 = alpha.double().requires_grad_(True)
+        a_ = (a64[:, :, 1:] + 1) / 2 + 1e-6
+        f_ = flow.double().unsqueeze(2)
+        m_ = (f_ * a_.unsqueeze(3)).sum(dim=(4, 5), keepdim=True) / a_.sum(dim=(3, 4), keepdim=True).unsqueeze(3)
+        ((a_ * (f_ - m_).abs().sum(dim=3)).sum(dim=2) * w.double()).sum().backward()
+        grad_close(ad.grad, a64.grad.float(), a64.grad, f"obj_flow[{i}] d alpha under a weighted map")
+        i += 1
+    assert i >= 3
+    with pytest.raises(RuntimeError, match="expected alpha"):
+        wb.obj_flow_loss(alpha.to(dev), flow[:, :, :1].contiguous().to(dev))
+
+
 def check_deterministic_large_gradients(dev, seed=1, B=8):
     """Deterministic mode on the benchmark inputs of rank 1 (seed 1), whose background-grid gradient is amplified 1e8 x (max
     |d bg_pose| 6e8 for upstream gradients of ~6): single addends exceed 2^52 fixed-point units there.  They must be

@@ -85,6 +85,10 @@ def test_pose_distances():
     parity.check_pose_distances(DEV)
 
 
+def test_obj_flow():
+    parity.check_obj_flow(DEV)
+
+
 def test_pack_input():
     parity.check_pack_input(DEV)
 

@@ -120,3 +120,21 @@ def test_pose_distances_against_the_reference_fixture():
             assert float((g - ref).abs().max()) <= 1e-5 * max(float(ref.abs().max()), 1e-30), (i, name)
         i += 1
     assert i >= 3
+
+
+def test_obj_flow_against_the_reference_fixture():
+    """f-2: the oracle's restatement of `obj_flow` against the scalar and autograd gradient produced by the reference's own source
+    lines (models/synthesizer.py:865-868, executed by oracle/make_golden.obj_flow_fixture)."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(parity.GOLDEN, "obj_flow.npz"))
+    i = 0
+    while f"alpha{i}" in z.files:
+        alpha = torch.from_numpy(z[f"alpha{i}"]).requires_grad_(True)
+        val = wo.obj_flow(alpha, torch.from_numpy(z[f"flow{i}"]))
+        (val * 3.0).backward()
+        assert abs(float(val) - float(z[f"val{i}"])) <= 1e-6 * max(1.0, abs(float(z[f"val{i}"]))), i
+        ref = torch.from_numpy(z[f"d_alpha{i}"])
+        assert float((alpha.grad - ref).abs().max()) <= 1e-5 * max(float(ref.abs().max()), 1e-30), i
+        i += 1
+    assert i >= 3

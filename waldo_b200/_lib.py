@@ -131,6 +131,15 @@ class PoseDisBwd(C.Structure):
                 ("ctas", C.c_int), ("part", c_void_p), ("d_pose", c_void_p)]
 
 
+class ObjFlow(C.Structure):
+    _fields_ = [("n", C.c_int), ("L", C.c_int), ("HW", C.c_int), ("alpha", c_void_p), ("flow", c_void_p), ("ctas", C.c_int),
+                ("part", c_void_p), ("mom", c_void_p), ("dev_map", c_void_p)]
+
+
+class ObjFlowBwd(C.Structure):
+    _fields_ = [("f", ObjFlow), ("d_map", c_void_p), ("tsum", c_void_p), ("d_alpha", c_void_p)]
+
+
 class Conv3x3(C.Structure):
     _fields_ = [("n", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Tc", C.c_int), ("Tp", C.c_int),
                 ("in", c_void_p), ("weight", c_void_p), ("out", c_void_p)]
@@ -153,13 +162,14 @@ STRUCT_OF = {"waldo_tps_fwd_t": TpsFwd, "waldo_tps_bwd_t": TpsBwd, "waldo_invwar
              "waldo_pack_input_t": PackInput, "waldo_warp_field_t": WarpField, "waldo_resize_t": Resize,
              "waldo_frames_u8_t": FramesU8, "waldo_blur_t": Blur, "waldo_layer_entropy_t": LayerEntropy,
              "waldo_layer_entropy_bwd_t": LayerEntropyBwd, "waldo_conv3x3_t": Conv3x3, "waldo_conv3x3_wgrad_t": Conv3x3Wgrad,
-             "waldo_pose_dis_t": PoseDis, "waldo_pose_dis_bwd_t": PoseDisBwd}
+             "waldo_pose_dis_t": PoseDis, "waldo_pose_dis_bwd_t": PoseDisBwd,
+             "waldo_obj_flow_t": ObjFlow, "waldo_obj_flow_bwd_t": ObjFlowBwd}
 
 EXPORTS = ["waldo_last_error", "waldo_abi_version", "waldo_has_device_code", "waldo_launch_count", "waldo_tps_fwd", "waldo_tps_bwd",
            "waldo_invwarp_fwd", "waldo_invwarp_bwd", "waldo_occ_fwd", "waldo_occ_bwd", "waldo_decode_fwd",
            "waldo_decode_bwd", "waldo_wif_fuse_fwd", "waldo_wif_fuse_bwd", "waldo_pack_input", "waldo_warp_field_fwd", "waldo_resize_bilinear_fwd",
            "waldo_frames_to_u8", "waldo_blur_fwd", "waldo_blur_bwd", "waldo_layer_entropy_fwd", "waldo_layer_entropy_bwd", "waldo_conv3x3_fwd", "waldo_conv3x3_wgrad",
-           "waldo_pose_dis_fwd", "waldo_pose_dis_bwd"]
+           "waldo_pose_dis_fwd", "waldo_pose_dis_bwd", "waldo_obj_flow_fwd", "waldo_obj_flow_bwd"]
 
 _lock = threading.Lock()
 _lib = None
@@ -176,7 +186,8 @@ def _declare(lib):
                      ("waldo_wif_fuse_fwd", WifFuseFwd), ("waldo_wif_fuse_bwd", WifFuseBwd), ("waldo_pack_input", PackInput), ("waldo_warp_field_fwd", WarpField),
                      ("waldo_resize_bilinear_fwd", Resize), ("waldo_frames_to_u8", FramesU8), ("waldo_blur_fwd", Blur), ("waldo_blur_bwd", Blur),
                      ("waldo_layer_entropy_fwd", LayerEntropy), ("waldo_layer_entropy_bwd", LayerEntropyBwd), ("waldo_conv3x3_fwd", Conv3x3), ("waldo_conv3x3_wgrad", Conv3x3Wgrad),
-                     ("waldo_pose_dis_fwd", PoseDis), ("waldo_pose_dis_bwd", PoseDisBwd)):
+                     ("waldo_pose_dis_fwd", PoseDis), ("waldo_pose_dis_bwd", PoseDisBwd),
+                     ("waldo_obj_flow_fwd", ObjFlow), ("waldo_obj_flow_bwd", ObjFlowBwd)):
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(st), c_void_p]
         fn.restype = C.c_int

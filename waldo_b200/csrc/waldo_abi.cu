@@ -412,6 +412,41 @@ int waldo_pose_dis_bwd(const waldo_pose_dis_bwd_t* a, waldo_stream_t st) {
   return 0;
 }
 
+static int wb_obj_flow_check(const waldo_obj_flow_t* a) {
+  WB_REQUIRE(a && a->n >= 0 && a->n <= 65535 && a->HW > 0 && a->L >= 2 && a->L <= WB_OF_MAX_L, "obj_flow: bad sizes (2 <= L <= 33)");
+  WB_REQUIRE(a->alpha && a->flow && a->part && a->mom && a->ctas >= 1 && a->ctas <= 1024, "obj_flow: null pointer / ctas");
+  return 0;
+}
+int waldo_obj_flow_fwd(const waldo_obj_flow_t* a, waldo_stream_t st) {
+  int rc = wb_obj_flow_check(a);
+  if (rc) return rc;
+  WB_REQUIRE(a->dev_map, "obj_flow_fwd: null output");
+  if (a->n == 0) return 0;
+  const int No = a->L - 1;
+  WB_LAUNCH(k_of_reduce<0>, dim3(a->ctas, a->n), dim3(WB_OF_THREADS), 0, st, *a, (const float*)nullptr);
+  WB_LAUNCHED();
+  WB_LAUNCH(k_of_reduce_final, dim3(wb_blocks((long long)a->n * No * 3, 128, 1024)), dim3(128), 0, st, (const float*)a->part, a->mom, a->n, a->ctas, No * 3);
+  WB_LAUNCHED();
+  WB_LAUNCH(k_of_map, dim3(wb_blocks(a->HW, WB_OF_THREADS, 1024), a->n), dim3(WB_OF_THREADS), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+int waldo_obj_flow_bwd(const waldo_obj_flow_bwd_t* a, waldo_stream_t st) {
+  WB_REQUIRE(a, "obj_flow_bwd: null");
+  int rc = wb_obj_flow_check(&a->f);
+  if (rc) return rc;
+  WB_REQUIRE(a->d_map && a->tsum && a->d_alpha, "obj_flow_bwd: null pointer");
+  if (a->f.n == 0) return 0;
+  const int No = a->f.L - 1;
+  WB_LAUNCH(k_of_reduce<1>, dim3(a->f.ctas, a->f.n), dim3(WB_OF_THREADS), 0, st, a->f, a->d_map);
+  WB_LAUNCHED();
+  WB_LAUNCH(k_of_reduce_final, dim3(wb_blocks((long long)a->f.n * No * 2, 128, 1024)), dim3(128), 0, st, (const float*)a->f.part, a->tsum, a->f.n, a->f.ctas, No * 2);
+  WB_LAUNCHED();
+  WB_LAUNCH(k_of_dalpha, dim3(wb_blocks(a->f.HW, WB_OF_THREADS, 1024), a->f.n), dim3(WB_OF_THREADS), 0, st, *a);
+  WB_LAUNCHED();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ first UNet layer
 int waldo_conv3x3_fwd(const waldo_conv3x3_t* a, waldo_stream_t st) {
   WB_REQUIRE(a && a->n >= 0 && a->H > 0 && a->W > 0, "conv3x3_fwd: bad sizes");

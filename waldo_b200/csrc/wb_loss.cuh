@@ -313,3 +313,107 @@ __global__ void __launch_bounds__(128) k_pose_dis_bwd_final(waldo_pose_dis_bwd_t
       }
   }
 }
+
+// ------------------------------------------------------------------------------------------------ obj_flow
+// synthesizer.py:864-868 ("same mean motion in layers"):  a_o = (alpha_{o+1} + 1) / 2 + 1e-6  (o = 0 .. L-2, the object layers),
+//   S_o = sum_p a_o,  m_o = sum_p a_o f / S_o  (f = real_flow, 2 components),  obj_flow = mean_{o,p} a_o (|fx - mx_o| + |fy - my_o|).
+// The reference builds (B, T, No, 2, H, W) products for the means and again for the deviations; here
+//   k_of_moments (+ final): per (frame, object) S, sum a fx, sum a fy   -- per-CTA partials, added in CTA order
+//   k_of_map:               per pixel  V = sum_o a_o (|fx - mx_o| + |fy - my_o|)          (obj_flow = sum V / (n No HW))
+// Backward, with gV the upstream gradient of V:
+//   d a_o(p) = gV(p) D_o(p) - ((fx(p) - mx_o) Tx_o + (fy(p) - my_o) Ty_o) / S_o,   T_o = sum_q gV(q) a_o(q) sign(f(q) - m_o)
+//   k_of_tsum (+ final): T;   k_of_dalpha: d alpha_{o+1} = d a_o / 2, d alpha_0 = 0.
+#define WB_OF_THREADS 256
+#define WB_OF_MAX_L 33
+
+// sum of `nv` values per thread over the CTA, in a fixed order (lanes by shuffles, warps one after the other); result valid in thread 0
+template <int NV>
+WB_DEV void wb_of_block_sum(float (&v)[NV], float (*s_w)[4]) {
+  WB_UNROLL for (int j = 0; j < NV; ++j) v[j] = wb_warp_sum(v[j]);
+  __syncthreads();   // (the previous use of s_w is over)
+  if (wb_lane() == 0) { WB_UNROLL for (int j = 0; j < NV; ++j) s_w[wb_warp()][j] = v[j]; }
+  __syncthreads();
+  if (wb_tid() == 0) {
+    const int nw = (wb_nthr() + 31) / 32;
+    WB_UNROLL for (int j = 0; j < NV; ++j) { float s = 0.f; for (int w = 0; w < nw; ++w) s += s_w[w][j]; v[j] = s; }
+  }
+}
+
+// MODE 0: moments (a, a fx, a fy) -> part (n, ctas, L-1, 3);  MODE 1: T sums (gV a sign(fx - mx), gV a sign(fy - my)) -> part (n, ctas, L-1, 2)
+template <int MODE>
+__global__ void __launch_bounds__(WB_OF_THREADS) k_of_reduce(waldo_obj_flow_t p, const float* d_map) {
+  __shared__ float s_w[WB_OF_THREADS / 32][4];
+  const int f = blockIdx.y, No = p.L - 1, NV = MODE == 0 ? 3 : 2;
+  const float* fx = p.flow + (size_t)f * 2 * p.HW;
+  const float* fy = fx + p.HW;
+  const float* gv = MODE == 1 ? d_map + (size_t)f * p.HW : nullptr;
+  float* part = p.part + ((size_t)f * gridDim.x + blockIdx.x) * No * NV;
+  for (int o = 0; o < No; ++o) {
+    const float* al = p.alpha + ((size_t)f * p.L + o + 1) * p.HW;
+    float mx = 0.f, my = 0.f;
+    if (MODE == 1) { const float* m = p.mom + ((size_t)f * No + o) * 3; mx = m[1] / m[0]; my = m[2] / m[0]; }
+    float v[3] = {0.f, 0.f, 0.f};
+    for (int q = blockIdx.x * wb_nthr() + wb_tid(); q < p.HW; q += gridDim.x * wb_nthr()) {
+      const float a = (__ldg(al + q) + 1.f) * 0.5f + 1e-6f, x = __ldg(fx + q), y = __ldg(fy + q);
+      if (MODE == 0) { v[0] += a; v[1] += a * x; v[2] += a * y; }
+      else {
+        const float g = __ldg(gv + q) * a, dx = x - mx, dy = y - my;
+        v[0] += g * (dx > 0.f ? 1.f : (dx < 0.f ? -1.f : 0.f));
+        v[1] += g * (dy > 0.f ? 1.f : (dy < 0.f ? -1.f : 0.f));
+      }
+    }
+    wb_of_block_sum<3>(v, s_w);
+    if (wb_tid() == 0) { for (int j = 0; j < NV; ++j) part[o * NV + j] = v[j]; }
+  }
+}
+// one thread per (frame, object, value): partials added in CTA order
+__global__ void __launch_bounds__(128) k_of_reduce_final(const float* part, float* out, int n, int ctas, int per_frame) {
+  for (int i = blockIdx.x * wb_nthr() + wb_tid(); i < n * per_frame; i += gridDim.x * wb_nthr()) {
+    const int f = i / per_frame, e = i - f * per_frame;
+    float s = 0.f;
+    for (int c = 0; c < ctas; ++c) s += part[((size_t)f * ctas + c) * per_frame + e];
+    out[i] = s;
+  }
+}
+__global__ void __launch_bounds__(WB_OF_THREADS) k_of_map(waldo_obj_flow_t p) {
+  __shared__ float s_m[WB_OF_MAX_L * 2];
+  const int f = blockIdx.y, No = p.L - 1;
+  for (int o = wb_tid(); o < No; o += wb_nthr()) {
+    const float* m = p.mom + ((size_t)f * No + o) * 3;
+    s_m[o * 2] = m[1] / m[0]; s_m[o * 2 + 1] = m[2] / m[0];
+  }
+  __syncthreads();
+  const float* fx = p.flow + (size_t)f * 2 * p.HW;
+  const float* fy = fx + p.HW;
+  for (int q = blockIdx.x * wb_nthr() + wb_tid(); q < p.HW; q += gridDim.x * wb_nthr()) {
+    const float x = __ldg(fx + q), y = __ldg(fy + q);
+    float v = 0.f;
+    for (int o = 0; o < No; ++o) {
+      const float a = (__ldg(p.alpha + ((size_t)f * p.L + o + 1) * p.HW + q) + 1.f) * 0.5f + 1e-6f;
+      v += a * (fabsf(x - s_m[o * 2]) + fabsf(y - s_m[o * 2 + 1]));
+    }
+    p.dev_map[(size_t)f * p.HW + q] = v;
+  }
+}
+__global__ void __launch_bounds__(WB_OF_THREADS) k_of_dalpha(waldo_obj_flow_bwd_t b) {
+  const waldo_obj_flow_t& p = b.f;
+  __shared__ float s_m[WB_OF_MAX_L * 5];   // mx, my, Tx / S, Ty / S per object
+  const int f = blockIdx.y, No = p.L - 1;
+  for (int o = wb_tid(); o < No; o += wb_nthr()) {
+    const float* m = p.mom + ((size_t)f * No + o) * 3;
+    const float* t = b.tsum + ((size_t)f * No + o) * 2;
+    s_m[o * 4] = m[1] / m[0]; s_m[o * 4 + 1] = m[2] / m[0]; s_m[o * 4 + 2] = t[0] / m[0]; s_m[o * 4 + 3] = t[1] / m[0];
+  }
+  __syncthreads();
+  const float* fx = p.flow + (size_t)f * 2 * p.HW;
+  const float* fy = fx + p.HW;
+  float* da = b.d_alpha + (size_t)f * p.L * p.HW;
+  for (int q = blockIdx.x * wb_nthr() + wb_tid(); q < p.HW; q += gridDim.x * wb_nthr()) {
+    const float x = __ldg(fx + q), y = __ldg(fy + q), g = __ldg(b.d_map + (size_t)f * p.HW + q);
+    da[q] = 0.f;
+    for (int o = 0; o < No; ++o) {
+      const float dx = x - s_m[o * 4], dy = y - s_m[o * 4 + 1];
+      da[(size_t)(o + 1) * p.HW + q] = 0.5f * (g * (fabsf(dx) + fabsf(dy)) - (dx * s_m[o * 4 + 2] + dy * s_m[o * 4 + 3]));
+    }
+  }
+}

@@ -751,6 +751,54 @@ def pose_distances(mov_obj_mask, fg_mask, obj_pose, grid, obj_shape, eps):
     return _PoseDis.apply(mov_obj_mask, fg_mask, obj_pose, grid, eps, ho, wo)
 
 
+class _ObjFlow(torch.autograd.Function):
+    """models/synthesizer.py:864-868: dev_map (..., H, W) = sum_o a_o (|fx - mx_o| + |fy - my_o|) of the object layers."""
+
+    @staticmethod
+    def forward(ctx, alpha, flow):
+        lib = L.load()
+        a_c, f_c = _c(alpha.detach()), _c(flow.detach())
+        *lead, Lr, H, W = a_c.shape
+        n = 1
+        for v in lead:
+            n *= v
+        HW = H * W
+        ctas = max(1, min(64, (HW + 1023) // 1024))
+        part = torch.empty(max(n, 1), ctas, Lr - 1, 3, device=a_c.device, dtype=torch.float32)
+        mom = torch.empty(max(n, 1), Lr - 1, 3, device=a_c.device, dtype=torch.float32)
+        dev = torch.empty(*lead, H, W, device=a_c.device, dtype=torch.float32)
+        a = L.ObjFlow(n, Lr, HW, L.ptr(a_c, name="alpha"), L.ptr(f_c, name="flow"), ctas, L.ptr(part), L.ptr(mom), L.ptr(dev))
+        L.call(lib.waldo_obj_flow_fwd, a, a_c, "obj_flow_fwd")
+        ctx.save_for_backward(a_c, f_c, mom)
+        ctx.dims = (n, Lr, HW, ctas)
+        return dev
+
+    @staticmethod
+    def backward(ctx, d_map):
+        lib = L.load()
+        a_c, f_c, mom = ctx.saved_tensors
+        n, Lr, HW, ctas = ctx.dims
+        d_map = _c(d_map)
+        part = torch.empty(max(n, 1), ctas, Lr - 1, 3, device=a_c.device, dtype=torch.float32)
+        tsum = torch.empty(max(n, 1), Lr - 1, 2, device=a_c.device, dtype=torch.float32)
+        d_alpha = torch.empty_like(a_c)
+        f = L.ObjFlow(n, Lr, HW, L.ptr(a_c), L.ptr(f_c), ctas, L.ptr(part), L.ptr(mom), None)
+        b = L.ObjFlowBwd(f, L.ptr(d_map), L.ptr(tsum), L.ptr(d_alpha))
+        L.call(lib.waldo_obj_flow_bwd, b, a_c, "obj_flow_bwd")
+        return d_alpha, None
+
+
+def obj_flow_map(alpha, flow):
+    """alpha (..., L, H, W) in [-1, 1], flow (..., 2, H, W) -> dev_map (..., H, W); differentiable in alpha."""
+    if alpha.dim() < 3 or flow.dim() != alpha.dim() or flow.shape[-3] != 2 or flow.shape[-2:] != alpha.shape[-2:] or flow.shape[:-3] != alpha.shape[:-3]:
+        raise RuntimeError(f"waldo_b200.obj_flow: expected alpha (..., L, H, W) and flow (..., 2, H, W), got {tuple(alpha.shape)} / {tuple(flow.shape)}")
+    if alpha.shape[-3] < 2:
+        raise RuntimeError("waldo_b200.obj_flow: needs at least one object layer besides the background")
+    if flow.requires_grad:
+        raise NotImplementedError("waldo_b200.obj_flow: no gradient with respect to the flow (real_flow is data in the reference)")
+    return _ObjFlow.apply(alpha, flow)
+
+
 # ===================================================================================== f-1 first UNet layer
 def _conv3x3_launch(x, weight, n, Cin, H, W, Tc, Tp):
     lib = L.load()

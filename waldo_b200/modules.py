@@ -384,6 +384,14 @@ def pose_distance_losses(mov_obj_mask, fg_mask, obj_pose, grid, obj_shape, cell_
     return cell.mean(), center.mean()
 
 
+def obj_flow_loss(rec_output_alpha, real_flow):
+    """models/synthesizer.py:864-868 (`obj_flow`): mean over (B, T, No, H, W) of a_o |real_flow - mean flow of layer o|_1 with
+    a_o = (alpha_{o+1} + 1) / 2 + 1e-6, without the reference's (B, T, No, 2, H, W) products.
+    rec_output_alpha (B, T, No+1, H, W), real_flow (B, T, 2, H, W); differentiable in rec_output_alpha."""
+    dev = Fn.obj_flow_map(rec_output_alpha, real_flow)
+    return dev.sum() / (dev.numel() * (rec_output_alpha.shape[-3] - 1))
+
+
 # ----------------------------------------------------------------------------- f-1, first layer (consumer side: WIF's UNet)
 def wif_to_emb(raw_output, weight):
     """`UNet.to_emb` as WIF.forward applies it to raw_output (models/nets/wif.py:33-38 + models/modules/conv.py:54):
