@@ -695,6 +695,40 @@ def check_obj_flow(dev):
         wb.obj_flow_loss(alpha.to(dev), flow[:, :, :1].contiguous().to(dev))
 
 
+def check_loss_epilogue_shapes(dev, seed=23):
+    """pose distances and obj_flow on shapes outside the fixtures (ragged sizes, one object, 2 .. 17 layers, lattices from 2x2 to
+    4x5, more pixels than one CTA covers) against the oracle's fp64 twin."""
+    gen = torch.Generator().manual_seed(seed)
+    for (B, T, No, obj_shape, H, W, eps) in ((1, 1, 1, (2, 2), 5, 7, 0.01), (2, 1, 7, (4, 5), 33, 47, 0.0), (1, 2, 16, (4, 4), 40, 72, 0.1), (1, 1, 32, (2, 3), 8, 8, 0.0)):
+        ys, xs = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing="ij")
+        grid = torch.stack([xs, ys], dim=-1)[None]
+        pose = torch.rand(B, T, No, obj_shape[0] * obj_shape[1], 2, generator=gen) * 2 - 1
+        mov, fg = torch.rand(B, T, 1, H, W, generator=gen), torch.rand(B, T, 1, H, W, generator=gen) * 1.1
+        pd, fd = pose.clone().to(dev).requires_grad_(True), fg.clone().to(dev).requires_grad_(True)
+        cell, center = wb.pose_distance_losses(mov.to(dev), fd, pd, grid.to(dev), obj_shape, eps)
+        (cell - 2 * center).backward()
+        p64, f64 = pose.double().requires_grad_(True), fg.double().requires_grad_(True)
+        c64, m64 = wo.pose_distances(mov.double(), f64, p64, grid.double(), obj_shape, eps)
+        (c64.mean() - 2 * m64.mean()).backward()
+        c32, m32 = wo.pose_distances(mov, fg, pose, grid, obj_shape, eps)
+        what = f"pose_dis {(B, T, No, obj_shape, H, W)}"
+        arbitrated(cell, c32.mean(), c64.mean(), FWD_TOL, what + " cell_dis")
+        arbitrated(center, m32.mean(), m64.mean(), FWD_TOL, what + " center_dis")
+        grad_close(pd.grad, p64.grad.float(), p64.grad, what + " d obj_pose")
+        grad_close(fd.grad, f64.grad.float(), f64.grad, what + " d fg_mask")
+    for (B, T, L, H, W) in ((1, 1, 2, 5, 7), (2, 1, 8, 33, 47), (1, 2, 17, 40, 72), (1, 1, 33, 8, 8)):
+        alpha = torch.tanh(2 * torch.randn(B, T, L, H, W, generator=gen))
+        flow = torch.randn(B, T, 2, H, W, generator=gen) * 0.1
+        ad = alpha.clone().to(dev).requires_grad_(True)
+        val = wb.obj_flow_loss(ad, flow.to(dev))
+        val.backward()
+        a64 = alpha.double().requires_grad_(True)
+        v64 = wo.obj_flow(a64, flow.double())
+        v64.backward()
+        arbitrated(val, wo.obj_flow(alpha, flow), v64, FWD_TOL, f"obj_flow {(B, T, L, H, W)}")
+        grad_close(ad.grad, a64.grad.float(), a64.grad, f"obj_flow {(B, T, L, H, W)} d alpha")
+
+
 def check_deterministic_large_gradients(dev, seed=1, B=8):
     """Deterministic mode on the benchmark inputs of rank 1 (seed 1), whose background-grid gradient is amplified 1e8 x (max
     |d bg_pose| 6e8 for upstream gradients of ~6): single addends exceed 2^52 fixed-point units there.  They must be

@@ -89,6 +89,10 @@ def test_obj_flow():
     parity.check_obj_flow(DEV)
 
 
+def test_loss_epilogue_shapes():
+    parity.check_loss_epilogue_shapes(DEV)
+
+
 def test_pack_input():
     parity.check_pack_input(DEV)
 

@@ -11,3 +11,9 @@ from tests import parity
 def test_obj_flow_gpu():
     assert torch.cuda.is_available()
     parity.check_obj_flow(torch.device("cuda:0"))
+
+
+@pytest.mark.gpu
+def test_loss_epilogue_shapes_gpu():
+    assert torch.cuda.is_available()
+    parity.check_loss_epilogue_shapes(torch.device("cuda:0"))
